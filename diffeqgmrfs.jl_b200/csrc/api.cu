@@ -1,0 +1,654 @@
+// C ABI: contexts, symbolic analysis handles, numeric factorisation, solves, samples, marginal variances.
+// (sparse-matrix helpers live in spm.cu, the block-tridiagonal path in btd.cu)
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "common.hpp"
+#include "handles.hpp"
+
+namespace gmrfb {
+
+std::string& global_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+gmrfb_status run_plan(gmrfb_ctx* ctx, const DevPlan& P, const Arenas& ar, const LaunchAux& aux) {
+  for (const Launch& L : P.host.launches) {
+    cudaError_t e = run_launch(L, P.tasks.p, ar, aux, ctx->stream);
+    if (e != cudaSuccess)
+      return fail(ctx, GMRFB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  return GMRFB_OK;
+}
+
+}  // namespace gmrfb
+
+using namespace gmrfb;
+
+// ------------------------------------------------------------------------------------------ context ----
+extern "C" int32_t gmrfb_version(void) { return 100; }
+
+extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) {
+  if (!out) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(nullptr, GMRFB_ERR_CUDA,
+                std::string("gmrfb_ctx_create: no CUDA device available (") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                    "); libgmrfb has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_ctx_create: bad device index");
+  std::unique_ptr<gmrfb_ctx> c(new gmrfb_ctx());
+  c->device = device;
+  GMRFB_CU(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GMRFB_CU(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(nullptr, GMRFB_ERR_CUDA, "gmrfb_ctx_create: device is not sm_100-class; libgmrfb is built for sm_100a only");
+  c->sm_count = prop.multiProcessorCount;
+  GMRFB_CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_info, sizeof(int)));
+  GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_scalar, 16 * sizeof(double)));
+  GMRFB_CU(nullptr, kernels_init());
+  GMRFB_CU(nullptr, sparse_kernels_init());
+  *out = c.release();
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx) {
+  if (!ctx) return GMRFB_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_info) cudaFree(ctx->d_info);
+  if (ctx->d_scalar) cudaFree(ctx->d_scalar);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GMRFB_OK;
+}
+
+extern "C" const char* gmrfb_last_error(gmrfb_ctx* ctx) { return ctx ? ctx->err.c_str() : global_error().c_str(); }
+
+extern "C" gmrfb_status gmrfb_ctx_sync(gmrfb_ctx* ctx) {
+  if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "ctx is NULL");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+extern "C" uint64_t gmrfb_ctx_stream(gmrfb_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+extern "C" int64_t gmrfb_ctx_launch_count(gmrfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------ symbolic ----
+extern "C" gmrfb_status gmrfb_analyze(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                                      const int64_t* perm, const gmrfb_analyze_opts* opts, gmrfb_sym** out) {
+  if (!out) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_analyze: out is NULL");
+  *out = nullptr;
+  AnalyzeOptions o;
+  if (opts) {
+    o.ordering_kind = opts->ordering_kind;
+    o.storage = opts->storage;
+    o.base = opts->base;
+    o.coord_dim = opts->coord_dim;
+    o.coords = opts->coords;
+    o.nd_leaf = opts->nd_leaf;
+    o.relax_small = opts->relax_small;
+    o.relax_zeros = opts->relax_zeros;
+  }
+  std::unique_ptr<gmrfb_sym> s(new gmrfb_sym());
+  s->ctx = ctx;
+  std::string err = analyze_pattern(n, colptr, rowval, perm, o, s->S);
+  if (!err.empty()) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_analyze: " + err);
+  *out = s.release();
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_sym_destroy(gmrfb_sym* sym) {
+  if (!sym) return GMRFB_OK;
+  if (sym->ctx) cudaSetDevice(sym->ctx->device);
+  delete sym;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_sym_get_info(const gmrfb_sym* sym, gmrfb_sym_info* info) {
+  if (!sym || !info) return fail(sym ? sym->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get_info: NULL argument");
+  const Symbolic& S = sym->S;
+  info->n = S.n;
+  info->nnz_lower_A = S.nnz_lower_A;
+  info->nnz_L = S.nnzL;
+  info->nnz_L_stored = S.nnzL_stored;
+  info->flops = S.flops;
+  info->nsuper = S.nsuper;
+  info->nlevels = (int64_t)S.levels.size();
+  info->max_front = S.max_front;
+  info->front_bytes = S.arena * (int64_t)sizeof(double);
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_sym_get(const gmrfb_sym* sym, int64_t* perm, int64_t* parent, int64_t* colcount,
+                                      int64_t* super_ptr, int64_t* ipost) {
+  if (!sym) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get: sym is NULL");
+  const Symbolic& S = sym->S;
+  const int b = S.base;
+  for (int64_t k = 0; k < S.n; k++) {
+    if (perm) perm[k] = S.perm_user[k] + b;
+    if (parent) parent[k] = S.parent_user[k] < 0 ? b - 1 : S.parent_user[k] + b;
+    if (colcount) colcount[k] = S.colcount_user[k];
+    if (ipost) ipost[k] = S.ipost[k] + b;
+  }
+  if (super_ptr)
+    for (int32_t s = 0; s <= S.nsuper; s++) super_ptr[s] = S.sptr[s] + b;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_sym_get_super_rows(const gmrfb_sym* sym, int64_t s, int64_t* rows, int64_t cap,
+                                                 int64_t* nrows) {
+  if (!sym || s < 0 || s >= sym->S.nsuper)
+    return fail(sym ? sym->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get_super_rows: bad argument");
+  const Symbolic& S = sym->S;
+  int64_t cnt = S.rptr[s + 1] - S.rptr[s];
+  if (nrows) *nrows = cnt;
+  if (rows)
+    for (int64_t k = 0; k < std::min(cnt, cap); k++) rows[k] = S.rows[S.rptr[s] + k] + S.base;
+  return GMRFB_OK;
+}
+
+// Upload everything the numeric phases need (once per symbolic handle).
+static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
+  if (sym->dev_ready) return GMRFB_OK;
+  gmrfb_ctx* ctx = sym->ctx;
+  if (!ctx) return fail(nullptr, GMRFB_ERR_STATE, "symbolic handle was created without a context (host-only analysis)");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const Symbolic& S = sym->S;
+  cudaStream_t st = ctx->stream;
+  GMRFB_CU(ctx, sym->d_amap.upload(S.amap, st));
+  GMRFB_CU(ctx, sym->d_relmap.upload(S.relmap, st));
+  GMRFB_CU(ctx, sym->d_rows.upload(S.rows, st));
+  GMRFB_CU(ctx, sym->d_perm.upload(S.perm, st));
+  GMRFB_CU(ctx, sym->d_post.upload(S.post, st));
+  GMRFB_CU(ctx, sym->d_child_idx.upload(S.child_idx, st));
+  std::vector<SnodeDesc> sd(S.nsuper);
+  int64_t uo = 0;
+  for (int32_t s = 0; s < S.nsuper; s++) {
+    SnodeDesc& D = sd[s];
+    D.foff = S.foff[s];
+    D.rows_off = S.rptr[s];
+    D.uoff = uo;
+    D.ld = S.ld[s];
+    D.d = S.front_order(s);
+    D.s = S.ncols(s);
+    D.col0 = S.sptr[s];
+    D.child0 = S.child_ptr[s];
+    D.nchild = S.child_ptr[s + 1] - S.child_ptr[s];
+    uo += D.d - D.s;
+  }
+  sym->uvec_rows = uo;
+  GMRFB_CU(ctx, sym->d_snodes.upload(sd, st));
+  std::vector<int32_t> lists;
+  sym->level_off.assign(1, 0);
+  sym->level_maxd.clear();
+  for (auto& L : S.levels) {
+    int md = 0;
+    for (int32_t s : L.snodes) {
+      lists.push_back(s);
+      md = std::max(md, S.front_order(s));
+    }
+    sym->level_off.push_back((int32_t)lists.size());
+    sym->level_maxd.push_back(md);
+  }
+  GMRFB_CU(ctx, sym->d_level_lists.upload(lists, st));
+  if (solve_smem_bytes(S.max_front) > 227 * 1024)
+    return fail(ctx, GMRFB_ERR_ALLOC, "largest front does not fit the shared-memory solve kernel");
+  build_factor_plan(S, sym->factor_plan.host);
+  GMRFB_CU(ctx, sym->factor_plan.tasks.upload(sym->factor_plan.host.tasks, st));
+  sym->factor_plan.ready = true;
+  sym->dev_ready = true;
+  return GMRFB_OK;
+}
+
+static gmrfb_status sym_ensure_selinv(gmrfb_sym* sym) {
+  if (sym->selinv_plan.ready) return GMRFB_OK;
+  gmrfb_ctx* ctx = sym->ctx;
+  build_selinv_plan(sym->S, sym->selinv_plan.host);
+  GMRFB_CU(ctx, sym->selinv_plan.tasks.upload(sym->selinv_plan.host.tasks, ctx->stream));
+  sym->selinv_plan.ready = true;
+  return GMRFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- numeric ----
+extern "C" gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out) {
+  if (!sym || !out) return fail(sym ? sym->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_create: NULL argument");
+  *out = nullptr;
+  gmrfb_status rc = sym_ensure_device(sym);
+  if (rc != GMRFB_OK) return rc;
+  gmrfb_ctx* ctx = sym->ctx;
+  std::unique_ptr<gmrfb_fac> f(new gmrfb_fac());
+  f->sym = sym;
+  f->ctx = ctx;
+  const Symbolic& S = sym->S;
+  GMRFB_CU(ctx, f->arena.alloc((size_t)std::max<int64_t>(S.arena, 1)));
+  GMRFB_CU(ctx, f->nzval.alloc((size_t)std::max<int64_t>(S.nnzA, 1)));
+  GMRFB_CU(ctx, f->xwork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
+  GMRFB_CU(ctx, f->bwork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
+  GMRFB_CU(ctx, f->uvec.alloc((size_t)std::max<int64_t>(sym->uvec_rows, 1) * SOLVE_NRC));
+  *out = f.release();
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_fac_destroy(gmrfb_fac* fac) {
+  if (!fac) return GMRFB_OK;
+  cudaSetDevice(fac->ctx->device);
+  cudaStreamSynchronize(fac->ctx->stream);
+  delete fac;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzval) {
+  if (!fac || !d_nzval) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_factorize_dev: NULL argument");
+  gmrfb_ctx* ctx = fac->ctx;
+  gmrfb_sym* sym = fac->sym;
+  const Symbolic& S = sym->S;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  fac->factored = false;
+  fac->z_valid = false;
+  fac->logdet_valid = false;
+  GMRFB_CU(ctx, cudaMemsetAsync(fac->arena.p, 0, fac->arena.n * sizeof(double), st));
+  const int big = INT_MAX;
+  GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, st));
+  GMRFB_CU(ctx, launch_scatter_values(d_nzval, sym->d_amap.p, S.nnzA, fac->arena.p, st));
+  ctx->launches++;
+  Arenas ar{{fac->arena.p, nullptr, nullptr, nullptr}};
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  aux.d_relmap = sym->d_relmap.p;
+  gmrfb_status rc = run_plan(ctx, sym->factor_plan, ar, aux);
+  if (rc != GMRFB_OK) return rc;
+  int info = 0;
+  GMRFB_CU(ctx, cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GMRFB_CU(ctx, cudaStreamSynchronize(st));
+  if (info != INT_MAX) {
+    fac->status = GMRFB_ERR_NOT_SPD;
+    fac->fail_column = (info >= 0 && info < S.n) ? S.post[info] : -1;
+    return fail(ctx, GMRFB_ERR_NOT_SPD,
+                "matrix is not positive definite (pivot failed at permuted column " + std::to_string(fac->fail_column) + ")");
+  }
+  fac->status = GMRFB_OK;
+  fac->fail_column = -1;
+  fac->factored = true;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_factorize(gmrfb_fac* fac, const double* nzval) {
+  if (!fac || !nzval) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_factorize: NULL argument");
+  gmrfb_ctx* ctx = fac->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  GMRFB_CU(ctx, cudaMemcpyAsync(fac->nzval.p, nzval, (size_t)fac->sym->S.nnzA * sizeof(double), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  return gmrfb_factorize_dev(fac, fac->nzval.p);
+}
+
+static gmrfb_status fac_diag_host(gmrfb_fac* fac, std::vector<double>& dl) {
+  // diag(L) in the internal ordering
+  gmrfb_ctx* ctx = fac->ctx;
+  const Symbolic& S = fac->sym->S;
+  DevBuf<double> d;
+  GMRFB_CU(ctx, d.alloc((size_t)std::max<int64_t>(S.n, 1)));
+  GMRFB_CU(ctx, launch_diag_L(fac->sym->d_snodes.p, S.nsuper, fac->arena.p, d.p, ctx->stream));
+  ctx->launches++;
+  dl.resize(S.n);
+  GMRFB_CU(ctx, cudaMemcpyAsync(dl.data(), d.p, (size_t)S.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_fac_get_info(gmrfb_fac* fac, gmrfb_fac_info* info) {
+  if (!fac || !info) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_get_info: NULL argument");
+  GMRFB_CU(fac->ctx, cudaSetDevice(fac->ctx->device));
+  info->status = fac->status;
+  info->fail_column = fac->fail_column;
+  info->nnz_L = fac->sym->S.nnzL_stored;
+  info->logdet = NAN;
+  if (fac->factored) {
+    if (!fac->logdet_valid) {
+      std::vector<double> dl;
+      gmrfb_status rc = fac_diag_host(fac, dl);
+      if (rc != GMRFB_OK) return rc;
+      double s = 0;
+      for (double v : dl) s += std::log(v);
+      fac->logdet = 2.0 * s;
+      fac->logdet_valid = true;
+    }
+    info->logdet = fac->logdet;
+  }
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_fac_diag(gmrfb_fac* fac, double* diagL) {
+  if (!fac || !diagL) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_diag: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_fac_diag: no successful factorisation");
+  GMRFB_CU(fac->ctx, cudaSetDevice(fac->ctx->device));
+  std::vector<double> dl;
+  gmrfb_status rc = fac_diag_host(fac, dl);
+  if (rc != GMRFB_OK) return rc;
+  const Symbolic& S = fac->sym->S;
+  for (int64_t k = 0; k < S.n; k++) diagL[S.post[k]] = dl[k];
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_fac_get_L(gmrfb_fac* fac, int32_t base, int32_t drop_zeros, int64_t* colptr,
+                                        int64_t* rowval, double* nzval) {
+  if (!fac || !colptr) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_get_L: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_fac_get_L: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const Symbolic& S = fac->sym->S;
+  // L in the perm_user ordering: user column ku = post[k]; rows mapped the same way and sorted.
+  const bool want_vals = rowval && nzval;
+  std::vector<double> front;
+  std::vector<std::pair<int64_t, double>> col;
+  // first pass sizes (and second pass fills) column by column in user order: build per-internal-column data
+  std::vector<std::vector<std::pair<int64_t, double>>> cols;
+  if (want_vals || drop_zeros) cols.resize(S.n);
+  std::vector<int64_t> cnt(S.n, 0);
+  for (int32_t s = 0; s < S.nsuper; s++) {
+    int d = S.front_order(s), sc = S.ncols(s), ld = S.ld[s];
+    if (want_vals || drop_zeros) {
+      front.resize((size_t)ld * sc);
+      GMRFB_CU(ctx, cudaMemcpyAsync(front.data(), fac->arena.p + S.foff[s], front.size() * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+      GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int j = 0; j < sc; j++) {
+      int32_t k = S.sptr[s] + j;
+      int64_t ku = S.post[k];
+      for (int i = j; i < d; i++) {
+        double v = (want_vals || drop_zeros) ? front[(size_t)j * ld + i] : 1.0;
+        if (drop_zeros && v == 0.0 && i != j) continue;
+        cnt[ku]++;
+        if (want_vals || drop_zeros) cols[ku].push_back({(int64_t)S.post[S.rows[S.rptr[s] + i]], v});
+      }
+    }
+  }
+  colptr[0] = base;
+  for (int64_t k = 0; k < S.n; k++) colptr[k + 1] = colptr[k] + cnt[k];
+  if (want_vals) {
+    for (int64_t k = 0; k < S.n; k++) {
+      auto& c = cols[k];
+      std::sort(c.begin(), c.end());
+      int64_t o = colptr[k] - base;
+      for (auto& e : c) {
+        rowval[o] = e.first + base;
+        nzval[o] = e.second;
+        o++;
+      }
+    }
+  }
+  return GMRFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- solves ----
+namespace {
+
+// Run the level-scheduled sweeps on fac->xwork (internal ordering, n x nr, ld n).
+gmrfb_status sweep(gmrfb_fac* fac, bool fwd, bool bwd, int nr) {
+  gmrfb_ctx* ctx = fac->ctx;
+  gmrfb_sym* sym = fac->sym;
+  const int64_t n = sym->S.n;
+  const int nlev = (int)sym->S.levels.size();
+  if (fwd) {
+    for (int l = 0; l < nlev; l++) {
+      int cnt = sym->level_off[l + 1] - sym->level_off[l];
+      GMRFB_CU(ctx, launch_fwd_level(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt, sym->level_maxd[l],
+                                     sym->d_child_idx.p, sym->d_relmap.p, fac->arena.p, fac->xwork.p, n, fac->uvec.p,
+                                     nr, ctx->stream));
+      ctx->launches++;
+    }
+  }
+  if (bwd) {
+    for (int l = nlev - 1; l >= 0; l--) {
+      int cnt = sym->level_off[l + 1] - sym->level_off[l];
+      GMRFB_CU(ctx, launch_bwd_level(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt, sym->level_maxd[l],
+                                     sym->d_rows.p, fac->arena.p, fac->xwork.p, n, nr, ctx->stream));
+      ctx->launches++;
+    }
+  }
+  return GMRFB_OK;
+}
+
+struct ModeSpec {
+  bool fwd, bwd;
+  bool in_perm;   // gather input through perm (original ordering) instead of post (perm ordering)
+  bool out_perm;  // scatter output through perm instead of post
+};
+bool mode_spec(int mode, ModeSpec& m) {
+  switch (mode) {
+    case GMRFB_SOLVE_A: m = {true, true, true, true}; return true;
+    case GMRFB_SOLVE_PTL: m = {true, false, true, false}; return true;
+    case GMRFB_SOLVE_UP: m = {false, true, false, true}; return true;
+    case GMRFB_SOLVE_L: m = {true, false, false, false}; return true;
+    case GMRFB_SOLVE_LT: m = {false, true, false, false}; return true;
+  }
+  return false;
+}
+
+// d_X (device, n x nrhs, ldx) solved in place, NRC columns at a time; optional mean added on output.
+gmrfb_status solve_device(gmrfb_fac* fac, int mode, const double* d_in, int64_t ldin, double* d_out, int64_t ldout,
+                          int64_t nrhs, const double* d_mean) {
+  gmrfb_ctx* ctx = fac->ctx;
+  gmrfb_sym* sym = fac->sym;
+  const int64_t n = sym->S.n;
+  ModeSpec m;
+  if (!mode_spec(mode, m)) return fail(ctx, GMRFB_ERR_INVALID, "unknown solve mode");
+  for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
+    int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
+    GMRFB_CU(ctx, launch_perm_gather(d_in + c0 * ldin, ldin, fac->xwork.p, n, m.in_perm ? sym->d_perm.p : sym->d_post.p,
+                                     n, nr, ctx->stream));
+    ctx->launches++;
+    gmrfb_status rc = sweep(fac, m.fwd, m.bwd, nr);
+    if (rc != GMRFB_OK) return rc;
+    GMRFB_CU(ctx, launch_perm_scatter(fac->xwork.p, n, d_out + c0 * ldout, ldout,
+                                      m.out_perm ? sym->d_perm.p : sym->d_post.p, n, nr, d_mean, ctx->stream));
+    ctx->launches++;
+  }
+  return GMRFB_OK;
+}
+
+}  // namespace
+
+extern "C" gmrfb_status gmrfb_solve_dev(gmrfb_fac* fac, int32_t mode, double* d_X, int64_t ldx, int64_t nrhs) {
+  if (!fac || !d_X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_solve_dev: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_solve: no successful factorisation");
+  if (ldx < fac->sym->S.n || nrhs < 0) return fail(fac->ctx, GMRFB_ERR_INVALID, "gmrfb_solve: bad ldx/nrhs");
+  GMRFB_CU(fac->ctx, cudaSetDevice(fac->ctx->device));
+  // in-place: stage each chunk through bwork so gather/scatter never alias
+  gmrfb_ctx* ctx = fac->ctx;
+  const int64_t n = fac->sym->S.n;
+  for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
+    int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), d_X + c0 * ldx, ldx * sizeof(double),
+                                    n * sizeof(double), nr, cudaMemcpyDeviceToDevice, ctx->stream));
+    gmrfb_status rc = solve_device(fac, mode, fac->bwork.p, n, d_X + c0 * ldx, ldx, nr, nullptr);
+    if (rc != GMRFB_OK) return rc;
+  }
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int64_t ldx, int64_t nrhs) {
+  if (!fac || !X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_solve: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_solve: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  const int64_t n = fac->sym->S.n;
+  if (ldx < n || nrhs < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_solve: bad ldx/nrhs");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> out;
+  GMRFB_CU(ctx, out.alloc((size_t)std::max<int64_t>(n, 1) * SOLVE_NRC));
+  for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
+    int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), X + c0 * ldx, ldx * sizeof(double),
+                                    n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
+    gmrfb_status rc = solve_device(fac, mode, fac->bwork.p, n, out.p, n, nr, nullptr);
+    if (rc != GMRFB_OK) return rc;
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(X + c0 * ldx, ldx * sizeof(double), out.p, n * sizeof(double), n * sizeof(double), nr,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_sample(gmrfb_fac* fac, const double* mean, const double* Z, int64_t ldz, double* X,
+                                     int64_t ldx, int64_t nrhs) {
+  if (!fac || !Z || !X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sample: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_sample: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  const int64_t n = fac->sym->S.n;
+  if (ldz < n || ldx < n || nrhs < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_sample: bad leading dimension");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> out, dmean;
+  GMRFB_CU(ctx, out.alloc((size_t)std::max<int64_t>(n, 1) * SOLVE_NRC));
+  if (mean) {
+    GMRFB_CU(ctx, dmean.alloc((size_t)std::max<int64_t>(n, 1)));
+    GMRFB_CU(ctx, cudaMemcpyAsync(dmean.p, mean, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
+    int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
+                                    n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
+    gmrfb_status rc = solve_device(fac, GMRFB_SOLVE_UP, fac->bwork.p, n, out.p, n, nr, mean ? dmean.p : nullptr);
+    if (rc != GMRFB_OK) return rc;
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(X + c0 * ldx, ldx * sizeof(double), out.p, n * sizeof(double), n * sizeof(double), nr,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return GMRFB_OK;
+}
+
+// ------------------------------------------------------------------------------------ marginal variances ----
+static gmrfb_status selinv_run(gmrfb_fac* fac) {
+  gmrfb_ctx* ctx = fac->ctx;
+  gmrfb_sym* sym = fac->sym;
+  gmrfb_status rc = sym_ensure_selinv(sym);
+  if (rc != GMRFB_OK) return rc;
+  if (!fac->zarena.p) GMRFB_CU(ctx, fac->zarena.alloc(fac->arena.n));
+  if (!fac->zdiag.p) GMRFB_CU(ctx, fac->zdiag.alloc((size_t)std::max<int64_t>(sym->S.n, 1)));
+  Arenas ar{{fac->arena.p, fac->zarena.p, nullptr, nullptr}};
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  aux.d_relmap = sym->d_relmap.p;
+  aux.d_out = fac->zdiag.p;
+  rc = run_plan(ctx, sym->selinv_plan, ar, aux);
+  if (rc != GMRFB_OK) return rc;
+  fac->z_valid = true;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_var_selinv_dev(gmrfb_fac* fac, double* d_var_out) {
+  if (!fac || !d_var_out) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_var_selinv: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_var_selinv: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  gmrfb_status rc = selinv_run(fac);
+  if (rc != GMRFB_OK) return rc;
+  const int64_t n = fac->sym->S.n;
+  GMRFB_CU(ctx, launch_perm_scatter(fac->zdiag.p, n, d_var_out, n, fac->sym->d_perm.p, n, 1, nullptr, ctx->stream));
+  ctx->launches++;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_var_selinv(gmrfb_fac* fac, double* var_out) {
+  if (!fac || !var_out) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_var_selinv: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_var_selinv: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = fac->sym->S.n;
+  DevBuf<double> out;
+  GMRFB_CU(ctx, out.alloc((size_t)std::max<int64_t>(n, 1)));
+  gmrfb_status rc = gmrfb_var_selinv_dev(fac, out.p);
+  if (rc != GMRFB_OK) return rc;
+  GMRFB_CU(ctx, cudaMemcpyAsync(var_out, out.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_selinv_entries(gmrfb_fac* fac, int32_t base, int64_t count, const int64_t* rows,
+                                             const int64_t* cols, double* out) {
+  if (!fac || (count > 0 && (!rows || !cols || !out)))
+    return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_selinv_entries: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_selinv_entries: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const Symbolic& S = fac->sym->S;
+  std::vector<int64_t> map(count);
+  for (int64_t k = 0; k < count; k++) {
+    int64_t r = rows[k] - base, c = cols[k] - base;
+    if (r < 0 || r >= S.n || c < 0 || c >= S.n) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_selinv_entries: index out of range");
+    int32_t a = S.iperm[r], b = S.iperm[c];
+    if (a < b) std::swap(a, b);
+    int32_t s = S.snode[b];
+    int32_t f = S.sptr[s], l = S.sptr[s + 1] - 1;
+    int64_t lr;
+    if (a <= l) {
+      lr = a - f;
+    } else {
+      auto bg = S.rows.begin() + S.rptr[s] + (l - f + 1), en = S.rows.begin() + S.rptr[s + 1];
+      auto it = std::lower_bound(bg, en, a);
+      if (it == en || *it != a)
+        return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_selinv_entries: entry lies outside the filled pattern of the factor");
+      lr = it - (S.rows.begin() + S.rptr[s]);
+    }
+    map[k] = S.foff[s] + (int64_t)(b - f) * S.ld[s] + lr;
+  }
+  if (!fac->z_valid) {
+    gmrfb_status rc = selinv_run(fac);
+    if (rc != GMRFB_OK) return rc;
+  }
+  if (count == 0) return GMRFB_OK;
+  DevBuf<int64_t> dmap;
+  DevBuf<double> dout;
+  GMRFB_CU(ctx, dmap.upload(map, ctx->stream));
+  GMRFB_CU(ctx, dout.alloc((size_t)count));
+  GMRFB_CU(ctx, launch_gather_values(fac->zarena.p, dmap.p, count, dout.p, ctx->stream));
+  ctx->launches++;
+  GMRFB_CU(ctx, cudaMemcpyAsync(out, dout.p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
+                                       int64_t nsamp, double* var_out) {
+  if (!fac || !Q || !Z || !var_out) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_var_rbmc: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_var_rbmc: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  gmrfb_sym* sym = fac->sym;
+  const int64_t n = sym->S.n;
+  if (Q->m != n || Q->n != n) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_var_rbmc: Q has the wrong shape");
+  if (ldz < n || nsamp <= 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_var_rbmc: bad ldz/nsamp");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t ldk = (nsamp + 3) & ~(int64_t)3;
+  DevBuf<double> Xs, dvar;
+  GMRFB_CU(ctx, Xs.alloc((size_t)ldk * std::max<int64_t>(n, 1)));
+  GMRFB_CU(ctx, dvar.alloc((size_t)std::max<int64_t>(n, 1)));
+  for (int64_t c0 = 0; c0 < nsamp; c0 += SOLVE_NRC) {
+    int nr = (int)std::min<int64_t>(SOLVE_NRC, nsamp - c0);
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
+                                    n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
+    GMRFB_CU(ctx, launch_perm_gather(fac->bwork.p, n, fac->xwork.p, n, sym->d_post.p, n, nr, ctx->stream));
+    ctx->launches++;
+    gmrfb_status rc = sweep(fac, false, true, nr);
+    if (rc != GMRFB_OK) return rc;
+    GMRFB_CU(ctx, launch_perm_scatter_nodemajor(fac->xwork.p, n, Xs.p, ldk, sym->d_perm.p, n, (int)c0, nr, ctx->stream));
+    ctx->launches++;
+  }
+  // Q is symmetric: its CSC columns double as rows
+  GMRFB_CU(ctx, launch_rbmc(n, Q->d_colptr.p, Q->d_rowidx.p, Q->d_val.p, Xs.p, ldk, (int)nsamp, dvar.p, ctx->stream));
+  ctx->launches++;
+  GMRFB_CU(ctx, cudaMemcpyAsync(var_out, dvar.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}

@@ -1,0 +1,512 @@
+// C ABI: dense block-tridiagonal Cholesky (space-time GMRFs with implicit time stepping).
+// Restates src/tridiagonal_cholesky.jl:65-82 (factor) and the intended semantics of :24-63 (solves) on the
+// tile engine:  L_1 = chol(D_1);  C_i = B_i L_{i-1}^{-T};  L_i = chol(D_i - C_i C_i').
+//
+// Device layout: one slot per time block, slot i = [ L_i (b x b, ld) | C_i (b x b, ld) ], contiguous, so the
+// task list of one block step is position independent and is replayed with a moving base pointer.
+// Right-hand sides are kept "node-major" (nrhs x n, column-major) on the device so that every solve step is a
+// right-sided GEMM/TRSM of the same kernels that factorise.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <memory>
+
+#include "common.hpp"
+#include "handles.hpp"
+
+using namespace gmrfb;
+
+struct gmrfb_btd {
+  gmrfb_ctx* ctx = nullptr;
+  int64_t b = 0, N = 0;
+  int ld = 0;
+  int64_t slot = 0;  // doubles per block slot
+  DevBuf<double> arena;
+  DevPlan plan_first, plan_step;
+  int32_t status = GMRFB_ERR_STATE;
+  int64_t fail_block = -1;
+  bool factored = false;
+  // solve plans are built per nrhs on demand
+  int plan_nrhs = -1;
+  DevPlan fwd_first, fwd_step, bwd_last, bwd_step;
+  DevPlan sel_last, sel_step;
+  bool sel_ready = false;
+};
+
+namespace {
+
+__global__ void k_btd_scatter_csc(int64_t ncols, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                                  const double* __restrict__ nzval, int base, int64_t b, int64_t N, int ld, int64_t slot,
+                                  double* __restrict__ arena) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const int64_t bj = c / b, cj = c % b;
+  if (bj >= N) return;
+  for (int64_t p = colptr[c] - base; p < colptr[c + 1] - base; p++) {
+    const int64_t r = rowval[p] - base;
+    const int64_t bi = r / b, ri = r % b;
+    if (bi >= N) continue;
+    if (bi == bj)
+      arena[bi * slot + cj * ld + ri] = nzval[p];
+    else if (bi == bj + 1)
+      arena[bi * slot + (int64_t)ld * b + cj * ld + ri] = nzval[p];
+  }
+}
+
+// out (cols x rows, ldo) = in' (rows x cols, ldi)
+__global__ void k_transpose_rect(const double* __restrict__ in, int64_t ldi, double* __restrict__ out, int64_t ldo,
+                                 int64_t rows, int64_t cols) {
+  __shared__ double t[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int64_t r = r0 + threadIdx.x, c = c0 + j;
+    t[j][threadIdx.x] = (r < rows && c < cols) ? in[r + c * ldi] : 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int64_t c = c0 + threadIdx.x, r = r0 + j;
+    if (r < rows && c < cols) out[c + r * ldo] = t[threadIdx.x][j];
+  }
+}
+
+__global__ void k_btd_diag(const double* __restrict__ arena, int64_t slot, int ld, int64_t b, int64_t N,
+                           double* __restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= b * N) return;
+  int64_t i = k / b, j = k % b;
+  out[k] = arena[i * slot + j * ld + j];
+}
+
+__global__ void k_diag_strided(const double* __restrict__ M, int ld, int64_t b, double* __restrict__ out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < b) out[j] = M[j * ld + j];
+}
+
+gmrfb_status upload_plan(gmrfb_ctx* ctx, DevPlan& P) {
+  GMRFB_CU(ctx, P.tasks.upload(P.host.tasks, ctx->stream));
+  P.ready = true;
+  return GMRFB_OK;
+}
+
+gmrfb_status btd_alloc(gmrfb_ctx* ctx, int64_t b, int64_t N, std::unique_ptr<gmrfb_btd>& f) {
+  if (b <= 0 || N <= 0) return fail(ctx, GMRFB_ERR_INVALID, "btd: block size and block count must be positive");
+  if (b > 60000) return fail(ctx, GMRFB_ERR_INVALID, "btd: block size too large");
+  f.reset(new gmrfb_btd());
+  f->ctx = ctx;
+  f->b = b;
+  f->N = N;
+  f->ld = (int)((b + 1) & ~(int64_t)1);
+  f->slot = 2 * (int64_t)f->ld * b;
+  GMRFB_CU(ctx, f->arena.alloc((size_t)(f->slot * N)));
+  // factor plans (offsets relative to the current slot; the previous slot is at -slot)
+  {
+    PlanBuilder B(f->plan_first.host);
+    plan_potrf(B, f->plan_first.host, 0, 0, (int)b, f->ld, 0);
+  }
+  {
+    Plan& P = f->plan_step.host;
+    PlanBuilder B(P);
+    const int64_t coff = (int64_t)f->ld * b;
+    plan_trsm_rlt(B, P, 0, -f->slot, f->ld, 0, coff, (int)b, (int)b, f->ld);
+    B.begin(LK_GEMM_NT);
+    {
+      Task t = make_task();
+      t.a = coff;
+      t.b = coff;
+      t.c = 0;
+      t.lda = t.ldb = t.ldc = f->ld;
+      t.M = t.N = t.K = (int)b;
+      t.alpha = -1.0;
+      t.beta = 1.0;
+      t.flags = TF_TRI;
+      B.add(t, gemm_tiles((int)b, (int)b, true));
+      P.flops += (double)b * b * (b + 1);
+    }
+    B.end();
+    plan_potrf(B, P, 0, 0, (int)b, f->ld, 0);
+  }
+  gmrfb_status rc = upload_plan(ctx, f->plan_first);
+  if (rc != GMRFB_OK) return rc;
+  return upload_plan(ctx, f->plan_step);
+}
+
+gmrfb_status btd_run_factor(gmrfb_btd* f) {
+  gmrfb_ctx* ctx = f->ctx;
+  const int big = INT_MAX;
+  GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  for (int64_t i = 0; i < f->N; i++) {
+    Arenas ar{{f->arena.p + i * f->slot, nullptr, nullptr, nullptr}};
+    gmrfb_status rc = run_plan(ctx, i == 0 ? f->plan_first : f->plan_step, ar, aux);
+    if (rc != GMRFB_OK) return rc;
+  }
+  int info = 0;
+  GMRFB_CU(ctx, cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  f->status = GMRFB_OK;
+  f->fail_block = -1;
+  f->factored = true;
+  if (info != INT_MAX) {
+    // locate the first block whose diagonal is poisoned
+    std::vector<double> dg((size_t)(f->b * f->N));
+    DevBuf<double> dd;
+    GMRFB_CU(ctx, dd.alloc(dg.size()));
+    k_btd_diag<<<(unsigned)((dg.size() + 255) / 256), 256, 0, ctx->stream>>>(f->arena.p, f->slot, f->ld, f->b, f->N, dd.p);
+    GMRFB_CU(ctx, cudaGetLastError());
+    GMRFB_CU(ctx, cudaMemcpyAsync(dg.data(), dd.p, dg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < dg.size(); k++)
+      if (!(dg[k] > 0.0)) {
+        f->fail_block = (int64_t)(k / f->b);
+        break;
+      }
+    f->status = GMRFB_ERR_NOT_SPD;
+    f->factored = false;
+    return fail(ctx, GMRFB_ERR_NOT_SPD, "btd: block " + std::to_string(f->fail_block) + " is not positive definite");
+  }
+  return GMRFB_OK;
+}
+
+}  // namespace
+
+extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D,
+                                               const double* Bsub, gmrfb_btd** out) {
+  if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor_dense: ctx is NULL");
+  if (!out || !D || (nblocks > 1 && !Bsub)) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_factor_dense: NULL argument");
+  *out = nullptr;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<gmrfb_btd> f;
+  gmrfb_status rc = btd_alloc(ctx, b, nblocks, f);
+  if (rc != GMRFB_OK) return rc;
+  for (int64_t i = 0; i < nblocks; i++) {
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot, f->ld * sizeof(double), D + i * b * b, b * sizeof(double),
+                                    b * sizeof(double), b, cudaMemcpyHostToDevice, ctx->stream));
+    if (i > 0)
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot + (int64_t)f->ld * b, f->ld * sizeof(double),
+                                      Bsub + (i - 1) * b * b, b * sizeof(double), b * sizeof(double), b,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+  }
+  rc = btd_run_factor(f.get());
+  *out = f.release();  // the handle is returned even when not SPD so that get_info can report the block
+  return rc;
+}
+
+extern "C" gmrfb_status gmrfb_btd_factor(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                                         const double* nzval, int32_t base, int64_t nblocks, gmrfb_btd** out) {
+  if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor: ctx is NULL");
+  if (!out || !colptr || !rowval || !nzval || n <= 0 || nblocks <= 0 || (base != 0 && base != 1))
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_factor: bad argument");
+  *out = nullptr;
+  const int64_t b = n / nblocks;  // src/tridiagonal_cholesky.jl:66 — the remainder rows are ignored
+  if (b <= 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_factor: more blocks than rows");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<gmrfb_btd> f;
+  gmrfb_status rc = btd_alloc(ctx, b, nblocks, f);
+  if (rc != GMRFB_OK) return rc;
+  const int64_t nnz = colptr[n] - base;
+  DevBuf<int64_t> dcp, drv;
+  DevBuf<double> dnz;
+  GMRFB_CU(ctx, dcp.alloc((size_t)n + 1));
+  GMRFB_CU(ctx, drv.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  GMRFB_CU(ctx, dnz.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  GMRFB_CU(ctx, cudaMemcpyAsync(dcp.p, colptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  GMRFB_CU(ctx, cudaMemcpyAsync(drv.p, rowval, nnz * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  GMRFB_CU(ctx, cudaMemcpyAsync(dnz.p, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GMRFB_CU(ctx, cudaMemsetAsync(f->arena.p, 0, f->arena.n * sizeof(double), ctx->stream));
+  k_btd_scatter_csc<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, dcp.p, drv.p, dnz.p, base, b, nblocks,
+                                                                          f->ld, f->slot, f->arena.p);
+  GMRFB_CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  rc = btd_run_factor(f.get());
+  *out = f.release();
+  return rc;
+}
+
+extern "C" gmrfb_status gmrfb_btd_destroy(gmrfb_btd* f) {
+  if (!f) return GMRFB_OK;
+  cudaSetDevice(f->ctx->device);
+  cudaStreamSynchronize(f->ctx->stream);
+  delete f;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_btd_get_info(gmrfb_btd* f, gmrfb_btd_info* info) {
+  if (!f || !info) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_get_info: NULL argument");
+  info->b = f->b;
+  info->nblocks = f->N;
+  info->status = f->status;
+  info->fail_block = f->fail_block;
+  const double b3 = (double)f->b * f->b * f->b;
+  info->flops = (double)(f->N - 1) * (7.0 / 3.0) * b3 + b3 / 3.0;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_btd_get_block(gmrfb_btd* f, int64_t i, int32_t which, double* out, int64_t ldo) {
+  if (!f || !out) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_get_block: NULL argument");
+  gmrfb_ctx* ctx = f->ctx;
+  if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_get_block: no successful factorisation");
+  const int64_t b = f->b;
+  if (ldo < b) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_get_block: ldo too small");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const double* src;
+  if (which == GMRFB_BTD_BLOCK_L) {
+    if (i < 0 || i >= f->N) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_get_block: block index out of range");
+    src = f->arena.p + i * f->slot;
+  } else if (which == GMRFB_BTD_BLOCK_C) {
+    if (i < 0 || i >= f->N - 1) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_get_block: block index out of range");
+    src = f->arena.p + (i + 1) * f->slot + (int64_t)f->ld * b;
+  } else {
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_get_block: bad selector");
+  }
+  GMRFB_CU(ctx, cudaMemcpy2DAsync(out, ldo * sizeof(double), src, f->ld * sizeof(double), b * sizeof(double), b,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (which == GMRFB_BTD_BLOCK_L)
+    for (int64_t c = 1; c < b; c++)
+      for (int64_t r = 0; r < c; r++) out[r + c * ldo] = 0.0;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_btd_logdet(gmrfb_btd* f, double* logdet) {
+  if (!f || !logdet) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_logdet: NULL argument");
+  gmrfb_ctx* ctx = f->ctx;
+  if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_logdet: no successful factorisation");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  std::vector<double> dg((size_t)(f->b * f->N));
+  DevBuf<double> dd;
+  GMRFB_CU(ctx, dd.alloc(dg.size()));
+  k_btd_diag<<<(unsigned)((dg.size() + 255) / 256), 256, 0, ctx->stream>>>(f->arena.p, f->slot, f->ld, f->b, f->N, dd.p);
+  GMRFB_CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  GMRFB_CU(ctx, cudaMemcpyAsync(dg.data(), dd.p, dg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  double s = 0;
+  for (double v : dg) s += std::log(v);
+  *logdet = 2.0 * s;
+  return GMRFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- solve ----
+// Device RHS layout: Xt is nrhs x (b*N), leading dimension ldr; block i occupies columns [i*b, (i+1)*b).
+// Arena 0 = factor slots (moving base), arena 1 = Xt (moving base at block i).
+static gmrfb_status btd_build_solve_plans(gmrfb_btd* f, int nrhs, int ldr) {
+  if (f->plan_nrhs == nrhs) return GMRFB_OK;
+  gmrfb_ctx* ctx = f->ctx;
+  const int b = (int)f->b;
+  const int64_t coff = (int64_t)f->ld * b;
+  const int64_t xstep = (int64_t)ldr * b;  // doubles between consecutive blocks of Xt
+  for (DevPlan* dp : {&f->fwd_first, &f->fwd_step, &f->bwd_last, &f->bwd_step}) {
+    dp->host = Plan();
+    dp->tasks.release();
+    dp->ready = false;
+  }
+  {  // x_1 = b_1 L_1^{-T}
+    PlanBuilder B(f->fwd_first.host);
+    plan_trsm_rlt(B, f->fwd_first.host, 0, 0, f->ld, 1, 0, nrhs, b, ldr);
+  }
+  {  // x_i = (b_i - x_{i-1} C_i') L_i^{-T}
+    Plan& P = f->fwd_step.host;
+    PlanBuilder B(P);
+    B.begin(LK_GEMM_NT);
+    Task t = make_task();
+    t.a = -xstep;
+    t.lda = ldr;
+    t.b = coff;
+    t.ldb = f->ld;
+    t.c = 0;
+    t.ldc = ldr;
+    t.M = nrhs;
+    t.N = b;
+    t.K = b;
+    t.alpha = -1.0;
+    t.beta = 1.0;
+    t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (1 << TF_C_SHIFT);
+    B.add(t, gemm_tiles(nrhs, b, false));
+    B.end();
+    plan_trsm_rlt(B, P, 0, 0, f->ld, 1, 0, nrhs, b, ldr);
+  }
+  {  // x_N = b_N L_N^{-1}
+    PlanBuilder B(f->bwd_last.host);
+    plan_trsm_rln(B, f->bwd_last.host, 0, 0, f->ld, 1, 0, nrhs, b, ldr, false);
+  }
+  {  // x_i = (b_i - x_{i+1} C_{i+1}) L_i^{-1}; C_{i+1} sits in the next slot
+    Plan& P = f->bwd_step.host;
+    PlanBuilder B(P);
+    B.begin(LK_GEMM_NN);
+    Task t = make_task();
+    t.a = xstep;
+    t.lda = ldr;
+    t.b = f->slot + coff;
+    t.ldb = f->ld;
+    t.c = 0;
+    t.ldc = ldr;
+    t.M = nrhs;
+    t.N = b;
+    t.K = b;
+    t.alpha = -1.0;
+    t.beta = 1.0;
+    t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (1 << TF_C_SHIFT);
+    B.add(t, gemm_tiles(nrhs, b, false));
+    B.end();
+    plan_trsm_rln(B, P, 0, 0, f->ld, 1, 0, nrhs, b, ldr, false);
+  }
+  gmrfb_status rc;
+  if ((rc = upload_plan(ctx, f->fwd_first)) != GMRFB_OK) return rc;
+  if ((rc = upload_plan(ctx, f->fwd_step)) != GMRFB_OK) return rc;
+  if ((rc = upload_plan(ctx, f->bwd_last)) != GMRFB_OK) return rc;
+  if ((rc = upload_plan(ctx, f->bwd_step)) != GMRFB_OK) return rc;
+  f->plan_nrhs = nrhs;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, int64_t ldx, int64_t nrhs) {
+  if (!f || !X) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_solve: NULL argument");
+  gmrfb_ctx* ctx = f->ctx;
+  if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_solve: no successful factorisation");
+  const int64_t n = f->b * f->N;
+  if (ldx < n || nrhs <= 0 || nrhs > 4096) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_solve: bad ldx/nrhs");
+  if (mode < GMRFB_BTD_SOLVE_A || mode > GMRFB_BTD_SOLVE_BWD) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_solve: bad mode");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int ldr = (int)((nrhs + 1) & ~(int64_t)1);
+  gmrfb_status rc = btd_build_solve_plans(f, (int)nrhs, ldr);
+  if (rc != GMRFB_OK) return rc;
+  DevBuf<double> dX, dXt;
+  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs)));
+  GMRFB_CU(ctx, dXt.alloc((size_t)((int64_t)ldr * n)));
+  GMRFB_CU(ctx, cudaMemcpy2DAsync(dX.p, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), nrhs,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+  dim3 tb(32, 8);
+  k_transpose_rect<<<dim3((unsigned)((n + 31) / 32), (unsigned)((nrhs + 31) / 32)), tb, 0, ctx->stream>>>(dX.p, n, dXt.p, ldr, n, nrhs);
+  GMRFB_CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  const int64_t xstep = (int64_t)ldr * f->b;
+  if (mode == GMRFB_BTD_SOLVE_A || mode == GMRFB_BTD_SOLVE_FWD) {
+    for (int64_t i = 0; i < f->N; i++) {
+      Arenas ar{{f->arena.p + i * f->slot, dXt.p + i * xstep, nullptr, nullptr}};
+      rc = run_plan(ctx, i == 0 ? f->fwd_first : f->fwd_step, ar, aux);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  if (mode == GMRFB_BTD_SOLVE_A || mode == GMRFB_BTD_SOLVE_BWD) {
+    for (int64_t i = f->N - 1; i >= 0; i--) {
+      Arenas ar{{f->arena.p + i * f->slot, dXt.p + i * xstep, nullptr, nullptr}};
+      rc = run_plan(ctx, i == f->N - 1 ? f->bwd_last : f->bwd_step, ar, aux);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  k_transpose_rect<<<dim3((unsigned)((nrhs + 31) / 32), (unsigned)((n + 31) / 32)), tb, 0, ctx->stream>>>(dXt.p, ldr, dX.p, n, nrhs, n);
+  GMRFB_CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  GMRFB_CU(ctx, cudaMemcpy2DAsync(X, ldx * sizeof(double), dX.p, n * sizeof(double), n * sizeof(double), nrhs,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+// ------------------------------------------------------------------------------- selected inversion ----
+// S_N = L_N^{-T} L_N^{-1};  S_i = L_i^{-T} (I + C_{i+1}' S_{i+1} C_{i+1}) L_i^{-1}.
+// Arena 0 = factor slot i (C_{i+1} in the next slot), 1 = S_{i+1} (b x b, ld), 2 = T scratch, 3 = S_i (output).
+extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
+  if (!f || !var_out) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_selinv_diag: NULL argument");
+  gmrfb_ctx* ctx = f->ctx;
+  if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_selinv_diag: no successful factorisation");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int b = (int)f->b, ld = f->ld;
+  const int64_t coff = (int64_t)ld * b;
+  if (!f->sel_ready) {
+    auto tail = [&](Plan& P, PlanBuilder& B) {
+      // arena 3 holds H; S = (H L^{-1})' L^{-1}
+      plan_trsm_rln(B, P, 0, 0, ld, 3, 0, b, b, ld, false);
+      B.begin(LK_TRANSPOSE);
+      Task t = make_task();
+      t.c = 0;
+      t.ldc = ld;
+      t.M = b;
+      t.flags = 3 << TF_C_SHIFT;
+      int nt = cdiv(b, 32);
+      B.add(t, nt * (nt + 1) / 2);
+      B.end();
+      plan_trsm_rln(B, P, 0, 0, ld, 3, 0, b, b, ld, false);
+    };
+    auto ident = [&](PlanBuilder& B) {
+      B.begin(LK_SET_IDENTITY);
+      Task t = make_task();
+      t.c = 0;
+      t.ldc = ld;
+      t.M = t.N = b;
+      t.flags = 3 << TF_C_SHIFT;
+      B.add(t, cdiv(b, 64) * cdiv(b, 64));
+      B.end();
+    };
+    {
+      Plan& P = f->sel_last.host;
+      PlanBuilder B(P);
+      ident(B);
+      tail(P, B);
+    }
+    {
+      Plan& P = f->sel_step.host;
+      PlanBuilder B(P);
+      // T = -S_{i+1} C_{i+1}  (S symmetric, both triangles valid)
+      B.begin(LK_GEMM_NN);
+      Task t = make_task();
+      t.a = 0;
+      t.lda = ld;
+      t.b = f->slot + coff;
+      t.ldb = ld;
+      t.c = 0;
+      t.ldc = ld;
+      t.M = t.N = t.K = b;
+      t.alpha = -1.0;
+      t.beta = 0.0;
+      t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (2 << TF_C_SHIFT);
+      B.add(t, gemm_tiles(b, b, false));
+      B.end();
+      ident(B);
+      // H = I - C_{i+1}' T
+      B.begin(LK_GEMM_TN);
+      Task u = make_task();
+      u.a = f->slot + coff;
+      u.lda = ld;
+      u.b = 0;
+      u.ldb = ld;
+      u.c = 0;
+      u.ldc = ld;
+      u.M = u.N = u.K = b;
+      u.alpha = -1.0;
+      u.beta = 1.0;
+      u.flags = (0 << TF_A_SHIFT) | (2 << TF_B_SHIFT) | (3 << TF_C_SHIFT);
+      B.add(u, gemm_tiles(b, b, false));
+      B.end();
+      tail(P, B);
+    }
+    gmrfb_status rc;
+    if ((rc = upload_plan(ctx, f->sel_last)) != GMRFB_OK) return rc;
+    if ((rc = upload_plan(ctx, f->sel_step)) != GMRFB_OK) return rc;
+    f->sel_ready = true;
+  }
+  DevBuf<double> S0, S1, T, dvar;
+  GMRFB_CU(ctx, S0.alloc((size_t)coff));
+  GMRFB_CU(ctx, S1.alloc((size_t)coff));
+  GMRFB_CU(ctx, T.alloc((size_t)coff));
+  GMRFB_CU(ctx, dvar.alloc((size_t)(f->b * f->N)));
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  double* prev = S0.p;
+  double* cur = S1.p;
+  for (int64_t i = f->N - 1; i >= 0; i--) {
+    Arenas ar{{f->arena.p + i * f->slot, prev, T.p, cur}};
+    gmrfb_status rc = run_plan(ctx, i == f->N - 1 ? f->sel_last : f->sel_step, ar, aux);
+    if (rc != GMRFB_OK) return rc;
+    k_diag_strided<<<(unsigned)((b + 255) / 256), 256, 0, ctx->stream>>>(cur, ld, b, dvar.p + i * f->b);
+    GMRFB_CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    std::swap(prev, cur);
+  }
+  GMRFB_CU(ctx, cudaMemcpyAsync(var_out, dvar.p, f->b * f->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}

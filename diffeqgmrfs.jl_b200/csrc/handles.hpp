@@ -1,0 +1,40 @@
+// Opaque handle definitions behind include/gmrfb.h.
+#pragma once
+#include <vector>
+
+#include "common.hpp"
+
+struct gmrfb_sym {
+  gmrfb_ctx* ctx = nullptr;
+  gmrfb::Symbolic S;
+  bool dev_ready = false;
+  gmrfb::DevBuf<int64_t> d_amap;
+  gmrfb::DevBuf<int32_t> d_relmap, d_rows, d_perm, d_post, d_child_idx, d_level_lists;
+  gmrfb::DevBuf<gmrfb::SnodeDesc> d_snodes;
+  std::vector<int32_t> level_off, level_maxd;
+  int64_t uvec_rows = 0;
+  gmrfb::DevPlan factor_plan, selinv_plan;
+};
+
+struct gmrfb_fac {
+  gmrfb_ctx* ctx = nullptr;
+  gmrfb_sym* sym = nullptr;
+  gmrfb::DevBuf<double> arena, zarena, zdiag, nzval, xwork, bwork, uvec;
+  bool factored = false, z_valid = false, logdet_valid = false;
+  int32_t status = GMRFB_ERR_STATE;
+  int64_t fail_column = -1;
+  double logdet = 0;
+};
+
+struct gmrfb_spm {
+  gmrfb_ctx* ctx = nullptr;
+  int64_t m = 0, n = 0, nnz = 0;
+  // host copy of the pattern (0-based) for symbolic work
+  std::vector<int64_t> colptr;
+  std::vector<int32_t> rowidx;
+  // device CSC and the row-wise (transposed) copy used by y = A x
+  gmrfb::DevBuf<int64_t> d_colptr, d_rowptr, d_tmap;
+  gmrfb::DevBuf<int32_t> d_rowidx, d_colidx;
+  gmrfb::DevBuf<double> d_val, d_tval;
+  bool owned_by_plan = false;
+};

@@ -1,0 +1,509 @@
+// Dense tile engine for sm_100a: grouped (batched, variable-size) FP64 kernels driven by Task lists.
+//
+//  k_gemm<TA,TB>   128x128x16 tiles, 3-stage cp.async pipeline, FP64 tensor cores (DMMA m8n8k4 via
+//                  mma.sync.aligned.m8n8k4.f64 — tcgen05 has no f64 kind; measured 37.1 TFLOP/s peak on B200,
+//                  profiles/r01_fp64_probe.txt).  Used for every SYRK/GEMM of the multifrontal factorisation,
+//                  selected inversion and the block-tridiagonal factor.
+//  k_potrf64       Cholesky of one <=64x64 diagonal block per CTA in shared memory.
+//  k_trsm_rlt/rln  X <- X L^{-T} / X L^{-1} with a <=64x64 triangle: one matrix row per thread in registers.
+//  k_extend_add, k_gather_sym, ...  index-mapped assembly kernels of the multifrontal method.
+//
+// No CPU fallback exists for any of these; the host only builds task lists (plan.cpp) and launches.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.hpp"
+#include "tasks.hpp"
+
+namespace gmrfb {
+
+// ------------------------------------------------------------------------------------------ helpers ----
+__device__ __forceinline__ int find_task(const Task* __restrict__ tasks, int ntasks, int cta) {
+  int lo = 0, hi = ntasks - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (tasks[mid].tile0 <= cta)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 8 : 0;  // src-size 0 => the 8 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// lower-triangular tile index -> (row tile, col tile)
+__device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
+  int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+  while ((r + 1) * (r + 2) / 2 <= t) r++;
+  while (r * (r + 1) / 2 > t) r--;
+  ti = r;
+  tj = t - r * (r + 1) / 2;
+}
+
+// --------------------------------------------------------------------------------------------- GEMM ----
+// C = beta*C + alpha*op(A)*op(B);  all column-major.
+//   TA=false: A is M x K (m contiguous)     TA=true: A is K x M (k contiguous), used as A'
+//   TB=false: B is N x K (n contiguous), used as B'   TB=true: B is K x N (k contiguous)
+constexpr int G_STAGES = 3;
+constexpr int G_LDN = GEMM_BM + 4;  // [k][m] layout, +4 doubles: conflict-free 64-bit fragment loads
+constexpr int G_LDT = GEMM_BK + 4;  // [m][k] layout
+constexpr int G_STAGE_N = GEMM_BK * G_LDN;
+constexpr int G_STAGE_T = GEMM_BM * G_LDT;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
+  constexpr int A_STAGE = TA ? G_STAGE_T : G_STAGE_N;
+  constexpr int B_STAGE = TB ? G_STAGE_T : G_STAGE_N;
+  double* As = smem;
+  double* Bs = smem + G_STAGES * A_STAGE;
+
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int local = blockIdx.x - T.tile0;
+  const int M = T.M, N = T.N, K = T.K;
+  const int ntn = (N + BN - 1) / BN;
+  int tm, tn;
+  if (T.flags & TF_TRI) {
+    const int tri = ntn * (ntn + 1) / 2;
+    if (local < tri) {
+      tri_decode(local, tm, tn);
+    } else {
+      int r = local - tri;
+      tm = ntn + r / ntn;
+      tn = r % ntn;
+    }
+  } else {
+    tm = local / ntn;
+    tn = local % ntn;
+  }
+  const int m0 = tm * BM, n0 = tn * BN;
+  const double* __restrict__ A = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
+  const double* __restrict__ B = ar.p[(T.flags >> TF_B_SHIFT) & 3] + T.b;
+  double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  const int lda = T.lda, ldb = T.ldb, ldc = T.ldc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+
+  auto load_stage = [&](int stage, int k0) {
+    double* as = As + stage * A_STAGE;
+    double* bs = Bs + stage * B_STAGE;
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / 256; i++) {
+      int e = tid + i * 256;
+      if (!TA) {
+        int m = e & (BM - 1), kk = e >> 7;
+        int gm = m0 + m, gk = k0 + kk;
+        bool ok = (gm < M) && (gk < K);
+        cp_async8(as + kk * G_LDN + m, ok ? A + gm + (int64_t)gk * lda : A, ok);
+      } else {
+        int kk = e & (BK - 1), m = e >> 4;
+        int gm = m0 + m, gk = k0 + kk;
+        bool ok = (gm < M) && (gk < K);
+        cp_async8(as + m * G_LDT + kk, ok ? A + gk + (int64_t)gm * lda : A, ok);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * BK) / 256; i++) {
+      int e = tid + i * 256;
+      if (!TB) {
+        int n = e & (BN - 1), kk = e >> 7;
+        int gn = n0 + n, gk = k0 + kk;
+        bool ok = (gn < N) && (gk < K);
+        cp_async8(bs + kk * G_LDN + n, ok ? B + gn + (int64_t)gk * ldb : B, ok);
+      } else {
+        int kk = e & (BK - 1), n = e >> 4;
+        int gn = n0 + n, gk = k0 + kk;
+        bool ok = (gn < N) && (gk < K);
+        cp_async8(bs + n * G_LDT + kk, ok ? B + gk + (int64_t)gn * ldb : B, ok);
+      }
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nkt = (K + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < G_STAGES - 1; s++) {
+    if (s < nkt) load_stage(s, s * BK);
+    cp_async_commit();
+  }
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int kt = 0; kt < nkt; kt++) {
+    cp_async_wait<G_STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + G_STAGES - 1;
+      if (nk < nkt) load_stage(nk % G_STAGES, nk * BK);
+      cp_async_commit();
+    }
+    const double* as = As + (kt % G_STAGES) * A_STAGE;
+    const double* bs = Bs + (kt % G_STAGES) * B_STAGE;
+#pragma unroll
+    for (int kb = 0; kb < BK; kb += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int im = 0; im < 8; im++)
+        af[im] = TA ? as[(wm0 + im * 8 + lr) * G_LDT + kb + lc] : as[(kb + lc) * G_LDN + wm0 + im * 8 + lr];
+#pragma unroll
+      for (int in = 0; in < 4; in++)
+        bf[in] = TB ? bs[(wn0 + in * 8 + lr) * G_LDT + kb + lc] : bs[(kb + lc) * G_LDN + wn0 + in * 8 + lr];
+#pragma unroll
+      for (int im = 0; im < 8; im++)
+#pragma unroll
+        for (int in = 0; in < 4; in++) dmma884(acc[im][in][0], acc[im][in][1], af[im], bf[in]);
+    }
+  }
+  cp_async_wait<0>();
+
+  const bool tri = (T.flags & TF_TRI) != 0;
+  const double alpha = T.alpha, beta = T.beta;
+#pragma unroll
+  for (int im = 0; im < 8; im++) {
+    const int row = m0 + wm0 + im * 8 + lr;
+    if (row >= M) continue;
+#pragma unroll
+    for (int in = 0; in < 4; in++) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int col = n0 + wn0 + in * 8 + 2 * lc + h;
+        if (col < N && (!tri || row >= col)) {
+          double* p = C + row + (int64_t)col * ldc;
+          double v = alpha * acc[im][in][h];
+          if (beta != 0.0) v += beta * (*p);
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------- POTRF ----
+// In-place Cholesky of an n x n (n <= 64) diagonal block; only the lower triangle is read and written.
+// A non-positive or NaN pivot records (aux0 + j) in *info (minimum over all failures) and poisons the block.
+constexpr int P_LD = 65;
+__global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks, int ntasks, Arenas ar,
+                                                 int* __restrict__ info) {
+  __shared__ double S[64 * P_LD];
+  const Task T = tasks[blockIdx.x];
+  const int n = T.M, lda = T.lda;
+  double* __restrict__ A = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < n * n; e += 256) {
+    int i = e % n, j = e / n;
+    if (i >= j) S[j * P_LD + i] = A[i + (int64_t)j * lda];
+  }
+  for (int j = 0; j < n; j++) {
+    __syncthreads();
+    const double d = S[j * P_LD + j];
+    __syncthreads();
+    double ljj;
+    if (d > 0.0) {
+      ljj = sqrt(d);
+    } else {
+      ljj = nan("");
+      if (tid == 0) atomicMin(info, T.aux0 + j);
+    }
+    const double inv = 1.0 / ljj;
+    for (int i = j + tid; i < n; i += 256) S[j * P_LD + i] = (i == j) ? ljj : S[j * P_LD + i] * inv;
+    __syncthreads();
+    const int w = n - j - 1;
+    for (int e = tid; e < w * w; e += 256) {
+      int i = j + 1 + e % w, k = j + 1 + e / w;
+      if (i >= k) S[k * P_LD + i] -= S[j * P_LD + i] * S[j * P_LD + k];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < n * n; e += 256) {
+    int i = e % n, j = e / n;
+    if (i >= j) A[i + (int64_t)j * lda] = S[j * P_LD + i];
+  }
+}
+
+// --------------------------------------------------------------------------------------------- TRSM ----
+// One CTA = TRSM_ROWS rows of X, one row per thread held in registers; the <=64x64 triangle sits in shared
+// memory padded to 64x64 with an identity so the substitution is fully unrolled.
+template <bool TRANS>
+__global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
+  __shared__ __align__(16) double Ls[64 * 64];
+  __shared__ double invd[64];
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int M = T.M, N = T.N;
+  const double* __restrict__ L = ar.p[(T.flags >> TF_B_SHIFT) & 3] + T.b;
+  double* __restrict__ X = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  const int ldl = T.ldb, ldx = T.ldc;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * 64; e += TRSM_ROWS) {
+    int r = e & 63, c = e >> 6;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < N && c < N && r >= c) v = L[r + (int64_t)c * ldl];
+    Ls[c * 64 + r] = v;
+  }
+  __syncthreads();
+  if (tid < 64) invd[tid] = 1.0 / Ls[tid * 64 + tid];
+  __syncthreads();
+  const int row = (blockIdx.x - T.tile0) * TRSM_ROWS + tid;
+  if (row >= M) return;
+  double x[64];
+#pragma unroll
+  for (int j = 0; j < 64; j++) x[j] = (j < N) ? X[row + (int64_t)j * ldx] : 0.0;
+  if (TRANS) {
+    // x L' = b  =>  x_j = (b_j - sum_{k<j} x_k L[j][k]) / L[j][j]; column-oriented elimination
+#pragma unroll
+    for (int j = 0; j < 64; j++) {
+      x[j] *= invd[j];
+#pragma unroll
+      for (int k = j + 1; k < 64; k++) x[k] -= x[j] * Ls[j * 64 + k];
+    }
+  } else {
+    // x L = b   =>  x_c = (b_c - sum_{m>c} x_m L[m][c]) / L[c][c], c descending
+#pragma unroll
+    for (int c = 63; c >= 0; c--) {
+      x[c] *= invd[c];
+#pragma unroll
+      for (int m = 0; m < c; m++) x[m] -= x[c] * Ls[m * 64 + c];
+    }
+  }
+  const double sgn = (T.flags & TF_NEG) ? -1.0 : 1.0;
+#pragma unroll
+  for (int j = 0; j < 64; j++)
+    if (j < N) X[row + (int64_t)j * ldx] = sgn * x[j];
+}
+
+// ------------------------------------------------------------------------------ multifrontal assembly ----
+// P[rel[i], rel[j]] += U[i, j] for i >= j (child update matrix into the parent front).  One CTA = one
+// 64x64 tile of the lower triangle of U.  Children of one parent are issued in separate launches, so no two
+// CTAs of a launch touch the same parent entry: the assembly is deterministic and atomic-free.
+__global__ void __launch_bounds__(256) k_extend_add(const Task* __restrict__ tasks, int ntasks, Arenas ar,
+                                                    const int32_t* __restrict__ relmap) {
+  __shared__ int32_t ri[EA_TILE], rj[EA_TILE];
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  int ti, tj;
+  tri_decode(blockIdx.x - T.tile0, ti, tj);
+  const int M = T.M;
+  const double* __restrict__ U = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
+  double* __restrict__ P = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  const int32_t* rel = relmap + (((int64_t)T.aux1 << 32) | (uint32_t)T.aux0);
+  const int tid = threadIdx.x;
+  const int i0 = ti * EA_TILE, j0 = tj * EA_TILE;
+  if (tid < EA_TILE) {
+    ri[tid] = (i0 + tid < M) ? rel[i0 + tid] : 0;
+  } else if (tid < 2 * EA_TILE) {
+    int t = tid - EA_TILE;
+    rj[t] = (j0 + t < M) ? rel[j0 + t] : 0;
+  }
+  __syncthreads();
+  const int li = tid & 63;
+  const int i = i0 + li;
+  if (i >= M) return;
+  const int64_t pr = ri[li];
+  for (int lj = tid >> 6; lj < EA_TILE; lj += 4) {
+    const int j = j0 + lj;
+    if (j > i || j >= M) continue;
+    P[pr + (int64_t)rj[lj] * T.ldc] += U[i + (int64_t)j * T.lda];
+  }
+}
+
+// Zc[i, j] = Zp[rel[i], rel[j]] (Zp symmetric, lower triangle valid), full square written.
+__global__ void __launch_bounds__(256) k_gather_sym(const Task* __restrict__ tasks, int ntasks, Arenas ar,
+                                                    const int32_t* __restrict__ relmap) {
+  __shared__ int32_t ri[EA_TILE], rj[EA_TILE];
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int M = T.M;
+  const int nt = (M + EA_TILE - 1) / EA_TILE;
+  const int local = blockIdx.x - T.tile0;
+  const int ti = local % nt, tj = local / nt;
+  const double* __restrict__ Zp = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
+  double* __restrict__ Zc = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  const int32_t* rel = relmap + (((int64_t)T.aux1 << 32) | (uint32_t)T.aux0);
+  const int tid = threadIdx.x;
+  const int i0 = ti * EA_TILE, j0 = tj * EA_TILE;
+  if (tid < EA_TILE) {
+    ri[tid] = (i0 + tid < M) ? rel[i0 + tid] : 0;
+  } else if (tid < 2 * EA_TILE) {
+    int t = tid - EA_TILE;
+    rj[t] = (j0 + t < M) ? rel[j0 + t] : 0;
+  }
+  __syncthreads();
+  const int li = tid & 63;
+  const int i = i0 + li;
+  if (i >= M) return;
+  const int64_t a = ri[li];
+  for (int lj = tid >> 6; lj < EA_TILE; lj += 4) {
+    const int j = j0 + lj;
+    if (j >= M) continue;
+    const int64_t b = rj[lj];
+    const double v = (a >= b) ? Zp[a + b * T.lda] : Zp[b + a * T.lda];
+    Zc[i + (int64_t)j * T.ldc] = v;
+  }
+}
+
+// Simple element-wise task kernels: one CTA per 64x64 tile.
+__global__ void __launch_bounds__(256) k_tile_op(const Task* __restrict__ tasks, int ntasks, Arenas ar, int op) {
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int M = T.M, N = T.N;
+  const int ntm = (M + 63) / 64;
+  const int local = blockIdx.x - T.tile0;
+  const int ti = local % ntm, tj = local / ntm;
+  double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  const int tid = threadIdx.x, li = tid & 63;
+  const int i = ti * 64 + li;
+  if (i >= M) return;
+  for (int lj = tid >> 6; lj < 64; lj += 4) {
+    const int j = tj * 64 + lj;
+    if (j >= N) continue;
+    double* p = C + i + (int64_t)j * T.ldc;
+    if (op == LK_SET_IDENTITY)
+      *p = (i == j) ? 1.0 : 0.0;
+    else if (op == LK_SCALE)
+      *p = T.alpha * (*p);
+    else if (op == LK_SYMMETRIZE) {
+      if (j > i) *p = C[j + (int64_t)i * T.ldc];
+    }
+  }
+}
+
+// In-place transpose of a square M x M matrix: one CTA per 32x32 tile pair of the lower triangle.
+__global__ void __launch_bounds__(256) k_transpose(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
+  __shared__ double sa[32][33], sb[32][33];
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int M = T.M;
+  int ti, tj;
+  tri_decode(blockIdx.x - T.tile0, ti, tj);
+  double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  const int tid = threadIdx.x, li = tid & 31;
+  const int i = ti * 32 + li, i2 = tj * 32 + li;
+  for (int lj = tid >> 5; lj < 32; lj += 8) {
+    const int j = tj * 32 + lj, j2 = ti * 32 + lj;
+    sa[lj][li] = (i < M && j < M) ? C[i + (int64_t)j * T.ldc] : 0.0;      // tile (ti,tj), element (li,lj)
+    sb[lj][li] = (i2 < M && j2 < M) ? C[i2 + (int64_t)j2 * T.ldc] : 0.0;  // mirror tile (tj,ti), element (li,lj)
+  }
+  __syncthreads();
+  for (int lj = tid >> 5; lj < 32; lj += 8) {
+    const int j = tj * 32 + lj, j2 = ti * 32 + lj;
+    if (i < M && j < M) C[i + (int64_t)j * T.ldc] = sb[li][lj];
+    if (ti != tj && i2 < M && j2 < M) C[i2 + (int64_t)j2 * T.ldc] = sa[li][lj];
+  }
+}
+
+// out[aux + i] = C[i,i]
+__global__ void __launch_bounds__(256) k_diag_out(const Task* __restrict__ tasks, int ntasks, Arenas ar,
+                                                  double* __restrict__ out) {
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int i = (blockIdx.x - T.tile0) * 256 + threadIdx.x;
+  if (i >= T.M) return;
+  const double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  out[(((int64_t)T.aux1 << 32) | (uint32_t)T.aux0) + i] = C[i + (int64_t)i * T.ldc];
+}
+
+// arena[amap[k]] = nzval[k] for every stored entry that belongs to the analysed triangle.
+__global__ void k_scatter_values(const double* __restrict__ nzval, const int64_t* __restrict__ amap, int64_t nnz,
+                                 double* __restrict__ arena) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  int64_t d = amap[k];
+  if (d >= 0) arena[d] = nzval[k];
+}
+
+// ---------------------------------------------------------------------------------- host launchers ----
+static size_t gemm_smem(bool ta, bool tb) {
+  size_t a = ta ? G_STAGE_T : G_STAGE_N, b = tb ? G_STAGE_T : G_STAGE_N;
+  return (a + b) * G_STAGES * sizeof(double);
+}
+
+cudaError_t kernels_init() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)gemm_smem(false, false));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)gemm_smem(false, true));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)gemm_smem(true, true));
+  return e;
+}
+
+cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, const LaunchAux& aux,
+                       cudaStream_t st) {
+  if (L.grid <= 0 || L.ntasks <= 0) return cudaSuccess;
+  const Task* t = d_tasks + L.task0;
+  switch (L.kind) {
+    case LK_GEMM_NT:
+      k_gemm<false, false><<<L.grid, 256, gemm_smem(false, false), st>>>(t, L.ntasks, ar);
+      break;
+    case LK_GEMM_NN:
+      k_gemm<false, true><<<L.grid, 256, gemm_smem(false, true), st>>>(t, L.ntasks, ar);
+      break;
+    case LK_GEMM_TN:
+      k_gemm<true, true><<<L.grid, 256, gemm_smem(true, true), st>>>(t, L.ntasks, ar);
+      break;
+    case LK_POTRF:
+      k_potrf64<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_info);
+      break;
+    case LK_TRSM_RLT:
+      k_trsm<true><<<L.grid, TRSM_ROWS, 0, st>>>(t, L.ntasks, ar);
+      break;
+    case LK_TRSM_RLN:
+      k_trsm<false><<<L.grid, TRSM_ROWS, 0, st>>>(t, L.ntasks, ar);
+      break;
+    case LK_EXTEND_ADD:
+      k_extend_add<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_relmap);
+      break;
+    case LK_GATHER_SYM:
+      k_gather_sym<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_relmap);
+      break;
+    case LK_TRANSPOSE:
+      k_transpose<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar);
+      break;
+    case LK_SET_IDENTITY:
+    case LK_SCALE:
+    case LK_SYMMETRIZE:
+      k_tile_op<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, L.kind);
+      break;
+    case LK_DIAG_OUT:
+      k_diag_out<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_out);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_values(const double* d_nzval, const int64_t* d_amap, int64_t nnz, double* d_arena,
+                                  cudaStream_t st) {
+  if (nnz <= 0) return cudaSuccess;
+  int64_t grid = (nnz + 255) / 256;
+  k_scatter_values<<<(unsigned)grid, 256, 0, st>>>(d_nzval, d_amap, nnz, d_arena);
+  return cudaGetLastError();
+}
+
+}  // namespace gmrfb

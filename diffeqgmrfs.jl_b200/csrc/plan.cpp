@@ -1,0 +1,381 @@
+// Plan builders: static launch lists for the multifrontal factorisation, the Takahashi selected inversion and
+// the dense building blocks of the block-tridiagonal factor.  All dense work is expressed as batched
+// ("grouped") launches of the tile engine in kernels.cu; fronts of one elimination-tree level advance in
+// lock-step through the blocked POTRF/TRSM so one launch serves every front of the level.
+#include "plan.hpp"
+
+#include <algorithm>
+
+namespace gmrfb {
+
+namespace {
+
+inline int32_t arena_flags(int a, int b, int c) { return (a << TF_A_SHIFT) | (b << TF_B_SHIFT) | (c << TF_C_SHIFT); }
+
+double gemm_flops(int M, int N, int K, bool tri) {
+  if (!tri) return 2.0 * M * N * K;
+  double n = std::min(M, N);
+  return 2.0 * K * (n * (n + 1) / 2 + (double)(M - n) * n);
+}
+
+void add_gemm(PlanBuilder& B, Plan& P, int aa, int64_t a, int lda, int ab, int64_t b, int ldb, int ac, int64_t c,
+              int ldc, int M, int N, int K, bool tri, double alpha, double beta) {
+  if (M <= 0 || N <= 0) return;
+  Task t = make_task();
+  t.a = a;
+  t.b = b;
+  t.c = c;
+  t.lda = lda;
+  t.ldb = ldb;
+  t.ldc = ldc;
+  t.M = M;
+  t.N = N;
+  t.K = K;
+  t.alpha = alpha;
+  t.beta = beta;
+  t.flags = arena_flags(aa, ab, ac) | (tri ? TF_TRI : 0);
+  B.add(t, gemm_tiles(M, N, tri));
+  P.flops += gemm_flops(M, N, K, tri);
+}
+
+void add_trsm(PlanBuilder& B, Plan& P, int al, int64_t l, int ldl, int ax, int64_t x, int ldx, int M, int n) {
+  if (M <= 0 || n <= 0) return;
+  Task t = make_task();
+  t.b = l;
+  t.ldb = ldl;
+  t.c = x;
+  t.ldc = ldx;
+  t.M = M;
+  t.N = n;
+  t.flags = arena_flags(0, al, ax);
+  B.add(t, cdiv(M, TRSM_ROWS));
+  P.flops += (double)M * n * n;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------ partial factorisation batch ----
+// Each problem is a d x d front (column-major, ld) whose first s columns are eliminated:
+//   [F11 .; F21 F22] -> L11 = chol(F11), L21 = F21 L11^{-T}, F22 <- F22 - L21 L21'.
+// Two-level blocking: outer panels of `nbo` columns (trailing updates with K = nbo), inner blocks of NB = 64
+// (POTRF in shared memory, TRSM by register substitution).  The F22 update is a single SYRK with K = s.
+struct FactorProb {
+  int arena;
+  int64_t off;
+  int ld, d, s, col0;
+};
+
+static void plan_partial_factor_batch(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int nbo) {
+  int max_s = 0;
+  for (auto& p : probs) max_s = std::max(max_s, p.s);
+  for (int j0 = 0; j0 < max_s; j0 += nbo) {
+    for (int jj = j0; jj < std::min(j0 + nbo, max_s); jj += NB) {
+      B.begin(LK_POTRF);
+      for (auto& p : probs) {
+        if (jj >= p.s) continue;
+        int nb = std::min(NB, p.s - jj);
+        Task t = make_task();
+        t.a = p.off + (int64_t)jj * p.ld + jj;
+        t.lda = p.ld;
+        t.M = nb;
+        t.aux0 = p.col0 + jj;
+        t.flags = arena_flags(p.arena, 0, 0);
+        B.add(t, 1);
+        P.flops += (double)nb * nb * nb / 3.0;
+      }
+      B.end();
+      B.begin(LK_TRSM_RLT);
+      for (auto& p : probs) {
+        if (jj >= p.s) continue;
+        int nb = std::min(NB, p.s - jj);
+        int row0 = jj + nb;
+        add_trsm(B, P, p.arena, p.off + (int64_t)jj * p.ld + jj, p.ld, p.arena, p.off + (int64_t)jj * p.ld + row0,
+                 p.ld, p.d - row0, nb);
+      }
+      B.end();
+      B.begin(LK_GEMM_NT);
+      for (auto& p : probs) {
+        if (jj >= p.s) continue;
+        int nb = std::min(NB, p.s - jj);
+        int c0 = jj + nb, c1 = std::min(j0 + nbo, p.s);
+        if (c1 <= c0) continue;
+        int64_t a = p.off + (int64_t)jj * p.ld + c0;
+        add_gemm(B, P, p.arena, a, p.ld, p.arena, a, p.ld, p.arena, p.off + (int64_t)c0 * p.ld + c0, p.ld,
+                 p.d - c0, c1 - c0, nb, true, -1.0, 1.0);
+      }
+      B.end();
+    }
+    B.begin(LK_GEMM_NT);
+    for (auto& p : probs) {
+      if (j0 >= p.s) continue;
+      int pe = std::min(j0 + nbo, p.s);
+      if (p.s <= pe) continue;
+      int64_t a = p.off + (int64_t)j0 * p.ld + pe;
+      add_gemm(B, P, p.arena, a, p.ld, p.arena, a, p.ld, p.arena, p.off + (int64_t)pe * p.ld + pe, p.ld, p.d - pe,
+               p.s - pe, pe - j0, true, -1.0, 1.0);
+    }
+    B.end();
+  }
+  B.begin(LK_GEMM_NT);
+  for (auto& p : probs) {
+    int r = p.d - p.s;
+    if (r <= 0 || p.s <= 0) continue;
+    int64_t a = p.off + p.s;
+    add_gemm(B, P, p.arena, a, p.ld, p.arena, a, p.ld, p.arena, p.off + (int64_t)p.s * p.ld + p.s, p.ld, r, r, p.s,
+             true, -1.0, 1.0);
+  }
+  B.end();
+}
+
+// ------------------------------------------------------------------------------- blocked TRSM batch ----
+// X (M x n) <- X L^{-T} (trans) or X L^{-1} (!trans), L n x n lower.  Left-looking over outer blocks of
+// `nbo` columns (GEMM with the already-solved columns, full-width tiles), inner blocks of NB.
+struct TrsmProb {
+  int arenaL;
+  int64_t loff;
+  int ldl;
+  int arenaX;
+  int64_t xoff;
+  int ldx;
+  int M, n;
+};
+
+static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>& probs, bool trans, int nbo) {
+  int max_n = 0;
+  for (auto& p : probs) max_n = std::max(max_n, p.n);
+  if (max_n == 0) return;
+  if (trans) {
+    // ascending: X_J = (B_J - X_{<J} L[J,<J]') L_JJ^{-T}
+    for (int o0 = 0; o0 < max_n; o0 += nbo) {
+      B.begin(LK_GEMM_NT);
+      for (auto& p : probs) {
+        if (o0 >= p.n || o0 == 0) continue;
+        int o1 = std::min(o0 + nbo, p.n);
+        add_gemm(B, P, p.arenaX, p.xoff, p.ldx, p.arenaL, p.loff + o0, p.ldl, p.arenaX,
+                 p.xoff + (int64_t)o0 * p.ldx, p.ldx, p.M, o1 - o0, o0, false, -1.0, 1.0);
+      }
+      B.end();
+      for (int jj = o0; jj < std::min(o0 + nbo, max_n); jj += NB) {
+        if (jj > o0) {
+          B.begin(LK_GEMM_NT);
+          for (auto& p : probs) {
+            if (jj >= p.n) continue;
+            int nb = std::min(NB, p.n - jj);
+            add_gemm(B, P, p.arenaX, p.xoff + (int64_t)o0 * p.ldx, p.ldx, p.arenaL,
+                     p.loff + (int64_t)o0 * p.ldl + jj, p.ldl, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M,
+                     nb, jj - o0, false, -1.0, 1.0);
+          }
+          B.end();
+        }
+        B.begin(LK_TRSM_RLT);
+        for (auto& p : probs) {
+          if (jj >= p.n) continue;
+          int nb = std::min(NB, p.n - jj);
+          add_trsm(B, P, p.arenaL, p.loff + (int64_t)jj * p.ldl + jj, p.ldl, p.arenaX,
+                   p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
+        }
+        B.end();
+      }
+    }
+  } else {
+    // descending: X_J = (B_J - X_{>J} L[>J,J]) L_JJ^{-1}.  Blocks are aligned to multiples of NB/nbo from 0 so
+    // that every problem sees the same block boundaries regardless of its n.
+    int nouter = cdiv(max_n, nbo);
+    for (int ob = nouter - 1; ob >= 0; ob--) {
+      int o0 = ob * nbo;
+      B.begin(LK_GEMM_NN);
+      for (auto& p : probs) {
+        if (o0 >= p.n) continue;
+        int o1 = std::min(o0 + nbo, p.n);
+        if (o1 >= p.n) continue;  // nothing to the right
+        add_gemm(B, P, p.arenaX, p.xoff + (int64_t)o1 * p.ldx, p.ldx, p.arenaL, p.loff + (int64_t)o0 * p.ldl + o1,
+                 p.ldl, p.arenaX, p.xoff + (int64_t)o0 * p.ldx, p.ldx, p.M, o1 - o0, p.n - o1, false, -1.0, 1.0);
+      }
+      B.end();
+      int ninner = nbo / NB;
+      for (int ib = ninner - 1; ib >= 0; ib--) {
+        int jj = o0 + ib * NB;
+        if (jj >= max_n) continue;
+        // update block jj with the already solved inner blocks to its right inside this outer block
+        B.begin(LK_GEMM_NN);
+        for (auto& p : probs) {
+          if (jj >= p.n) continue;
+          int nb = std::min(NB, p.n - jj);
+          int r0 = jj + nb, r1 = std::min(o0 + nbo, p.n);
+          if (r1 <= r0) continue;
+          add_gemm(B, P, p.arenaX, p.xoff + (int64_t)r0 * p.ldx, p.ldx, p.arenaL, p.loff + (int64_t)jj * p.ldl + r0,
+                   p.ldl, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb, r1 - r0, false, -1.0, 1.0);
+        }
+        B.end();
+        B.begin(LK_TRSM_RLN);
+        for (auto& p : probs) {
+          if (jj >= p.n) continue;
+          int nb = std::min(NB, p.n - jj);
+          add_trsm(B, P, p.arenaL, p.loff + (int64_t)jj * p.ldl + jj, p.ldl, p.arenaX,
+                   p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
+        }
+        B.end();
+      }
+    }
+  }
+}
+
+constexpr int NBO = 128;
+
+void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0) {
+  std::vector<FactorProb> v{{arena, off, ld, n, n, col0}};
+  plan_partial_factor_batch(B, P, v, NBO);
+}
+void plan_trsm_rlt(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
+                   int n, int ldx) {
+  std::vector<TrsmProb> v{{arenaL, loff, ldl, arenaX, xoff, ldx, M, n}};
+  plan_trsm_batch(B, P, v, true, NBO);
+}
+void plan_trsm_rln(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
+                   int n, int ldx, bool negate) {
+  std::vector<TrsmProb> v{{arenaL, loff, ldl, arenaX, xoff, ldx, M, n}};
+  plan_trsm_batch(B, P, v, false, NBO);
+  if (negate) {
+    B.begin(LK_SCALE);
+    Task t = make_task();
+    t.c = xoff;
+    t.ldc = ldx;
+    t.M = M;
+    t.N = n;
+    t.alpha = -1.0;
+    t.flags = arena_flags(0, 0, arenaX);
+    B.add(t, cdiv(M, 64) * cdiv(n, 64));
+    B.end();
+  }
+}
+
+// ------------------------------------------------------------------------------------ sparse factor ----
+void build_factor_plan(const Symbolic& S, Plan& P) {
+  PlanBuilder B(P);
+  for (size_t lev = 0; lev < S.levels.size(); lev++) {
+    const auto& sn = S.levels[lev].snodes;
+    // 1. assemble children update matrices, one child rank per launch (deterministic, no atomics)
+    int maxc = 0;
+    for (int32_t s : sn) maxc = std::max(maxc, S.child_ptr[s + 1] - S.child_ptr[s]);
+    for (int k = 0; k < maxc; k++) {
+      B.begin(LK_EXTEND_ADD);
+      for (int32_t s : sn) {
+        if (S.child_ptr[s + 1] - S.child_ptr[s] <= k) continue;
+        int32_t c = S.child_idx[S.child_ptr[s] + k];
+        int sc = S.ncols(c), dc = S.front_order(c), rc = dc - sc;
+        if (rc <= 0) continue;
+        Task t = make_task();
+        t.a = S.foff[c] + (int64_t)sc * S.ld[c] + sc;
+        t.lda = S.ld[c];
+        t.M = rc;
+        t.c = S.foff[s];
+        t.ldc = S.ld[s];
+        int64_t ro = S.rptr[c] + sc;
+        t.aux0 = (int32_t)(ro & 0xffffffff);
+        t.aux1 = (int32_t)(ro >> 32);
+        t.flags = arena_flags(AR_FRONT, 0, AR_FRONT);
+        int nt = cdiv(rc, EA_TILE);
+        B.add(t, nt * (nt + 1) / 2);
+      }
+      B.end();
+    }
+    // 2. partial factorisation of every front of the level
+    std::vector<FactorProb> probs;
+    probs.reserve(sn.size());
+    for (int32_t s : sn) probs.push_back({AR_FRONT, S.foff[s], S.ld[s], S.front_order(s), S.ncols(s), S.sptr[s]});
+    plan_partial_factor_batch(B, P, probs, NBO);
+  }
+}
+
+// -------------------------------------------------------------------------------- selected inversion ----
+// For a front with columns C (s) and below-rows R (r), given Z_RR (from the parent):
+//   T    = -Z_RR L21                     (r x s)
+//   H    = I - L21' T = I + L21' Z_RR L21 (s x s)
+//   Z_RC = T L11^{-1},   Z_CC = L11^{-T} H L11^{-1}
+void build_selinv_plan(const Symbolic& S, Plan& P) {
+  PlanBuilder B(P);
+  for (int lev = (int)S.levels.size() - 1; lev >= 0; lev--) {
+    const auto& sn = S.levels[lev].snodes;
+    B.begin(LK_GATHER_SYM);
+    for (int32_t s : sn) {
+      int sc = S.ncols(s), d = S.front_order(s), r = d - sc;
+      int32_t p = S.sparent[s];
+      if (r <= 0 || p < 0) continue;
+      Task t = make_task();
+      t.a = S.foff[p];
+      t.lda = S.ld[p];
+      t.c = S.foff[s] + (int64_t)sc * S.ld[s] + sc;
+      t.ldc = S.ld[s];
+      t.M = r;
+      int64_t ro = S.rptr[s] + sc;
+      t.aux0 = (int32_t)(ro & 0xffffffff);
+      t.aux1 = (int32_t)(ro >> 32);
+      t.flags = arena_flags(AR_ZINV, 0, AR_ZINV);
+      int nt = cdiv(r, EA_TILE);
+      B.add(t, nt * nt);
+    }
+    B.end();
+    B.begin(LK_GEMM_NN);  // T = -Z_RR L21
+    for (int32_t s : sn) {
+      int sc = S.ncols(s), d = S.front_order(s), r = d - sc, ld = S.ld[s];
+      add_gemm(B, P, AR_ZINV, S.foff[s] + (int64_t)sc * ld + sc, ld, AR_FRONT, S.foff[s] + sc, ld, AR_ZINV,
+               S.foff[s] + sc, ld, r, sc, r, false, -1.0, 0.0);
+    }
+    B.end();
+    B.begin(LK_SET_IDENTITY);
+    for (int32_t s : sn) {
+      int sc = S.ncols(s);
+      Task t = make_task();
+      t.c = S.foff[s];
+      t.ldc = S.ld[s];
+      t.M = sc;
+      t.N = sc;
+      t.flags = arena_flags(0, 0, AR_ZINV);
+      B.add(t, cdiv(sc, 64) * cdiv(sc, 64));
+    }
+    B.end();
+    B.begin(LK_GEMM_TN);  // H = I - L21' T
+    for (int32_t s : sn) {
+      int sc = S.ncols(s), d = S.front_order(s), r = d - sc, ld = S.ld[s];
+      if (r <= 0) continue;
+      add_gemm(B, P, AR_FRONT, S.foff[s] + sc, ld, AR_ZINV, S.foff[s] + sc, ld, AR_ZINV, S.foff[s], ld, sc, sc, r,
+               false, -1.0, 1.0);
+    }
+    B.end();
+    // [H; T] <- [H; T] L11^{-1}
+    std::vector<TrsmProb> tp;
+    for (int32_t s : sn)
+      tp.push_back({AR_FRONT, S.foff[s], S.ld[s], AR_ZINV, S.foff[s], S.ld[s], S.front_order(s), S.ncols(s)});
+    plan_trsm_batch(B, P, tp, false, NBO);
+    // Z_CC = (H L11^{-1})' L11^{-1}
+    B.begin(LK_TRANSPOSE);
+    for (int32_t s : sn) {
+      int sc = S.ncols(s);
+      Task t = make_task();
+      t.c = S.foff[s];
+      t.ldc = S.ld[s];
+      t.M = sc;
+      t.flags = arena_flags(0, 0, AR_ZINV);
+      int nt = cdiv(sc, 32);
+      B.add(t, nt * (nt + 1) / 2);
+    }
+    B.end();
+    for (auto& q : tp) q.M = q.n;
+    plan_trsm_batch(B, P, tp, false, NBO);
+    B.begin(LK_DIAG_OUT);
+    for (int32_t s : sn) {
+      int sc = S.ncols(s);
+      Task t = make_task();
+      t.c = S.foff[s];
+      t.ldc = S.ld[s];
+      t.M = sc;
+      t.aux0 = S.sptr[s];
+      t.aux1 = 0;
+      t.flags = arena_flags(0, 0, AR_ZINV);
+      B.add(t, cdiv(sc, 256));
+    }
+    B.end();
+  }
+}
+
+}  // namespace gmrfb

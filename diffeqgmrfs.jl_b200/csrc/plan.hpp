@@ -1,0 +1,68 @@
+// Host-side plan builders: compile a symbolic structure into static launch/task lists for the tile engine.
+#pragma once
+#include <vector>
+
+#include "symbolic.hpp"
+#include "tasks.hpp"
+
+namespace gmrfb {
+
+struct Plan {
+  std::vector<Task> tasks;
+  std::vector<Launch> launches;
+  double flops = 0;  // floating-point operations of the GEMM/SYRK/TRSM/POTRF tasks (useful work, not tile padding)
+};
+
+// Incremental builder: open a launch, append tasks with their CTA counts, close it (empty launches vanish).
+class PlanBuilder {
+ public:
+  explicit PlanBuilder(Plan& p) : P(p) {}
+  void begin(int kind) {
+    cur.kind = kind;
+    cur.task0 = (int32_t)P.tasks.size();
+    cur.ntasks = 0;
+    cur.grid = 0;
+  }
+  void add(Task t, int ctas) {
+    if (ctas <= 0) return;
+    t.tile0 = cur.grid;
+    P.tasks.push_back(t);
+    cur.ntasks++;
+    cur.grid += ctas;
+  }
+  void end() {
+    if (cur.ntasks > 0) P.launches.push_back(cur);
+  }
+
+ private:
+  Plan& P;
+  Launch cur{};
+};
+
+inline Task make_task() {
+  Task t{};
+  t.alpha = 1.0;
+  t.beta = 0.0;
+  return t;
+}
+
+// Arena indices used by the sparse plans.
+enum { AR_FRONT = 0, AR_ZINV = 1 };
+
+// Multifrontal numeric factorisation of every front, level by level (arena 0 = frontal arena).
+void build_factor_plan(const Symbolic& S, Plan& P);
+// Takahashi selected inversion, top-down (arena 0 = factor fronts, arena 1 = inverse fronts);
+// DIAG_OUT tasks write diag(Z) by internal column index.
+void build_selinv_plan(const Symbolic& S, Plan& P);
+
+// Dense building blocks shared with the block-tridiagonal path (offsets relative to a moving base).
+//  blocked in-place Cholesky of the n x n matrix at `off` (ld), reporting failures at column col0 + j
+void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0);
+//  X (M x n at xoff, ldx) <- X L^{-T}, L n x n lower at loff (ldl); left-looking blocked
+void plan_trsm_rlt(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
+                   int n, int ldx);
+//  X <- sign * X L^{-1}
+void plan_trsm_rln(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
+                   int n, int ldx, bool negate);
+
+}  // namespace gmrfb

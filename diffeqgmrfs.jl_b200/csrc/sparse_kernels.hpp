@@ -1,0 +1,46 @@
+// Host-visible interface of sparse_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace gmrfb {
+
+constexpr int SOLVE_NRC = 4;  // right-hand sides processed per pass of the level-scheduled solves
+
+// Per-supernode record used by the solve kernels (device copy of the symbolic structure).
+struct SnodeDesc {
+  int64_t foff;      // front offset in the frontal arena
+  int64_t rows_off;  // offset of the front's row list / relmap
+  int64_t uoff;      // offset (in rows) of the supernode's update vector
+  int32_t ld, d, s, col0;
+  int32_t child0, nchild;
+};
+
+cudaError_t sparse_kernels_init();
+size_t solve_smem_bytes(int maxd);
+cudaError_t launch_perm_gather(const double* src, int64_t lds, double* dst, int64_t ldd, const int32_t* perm,
+                               int64_t n, int nrhs, cudaStream_t st);
+cudaError_t launch_perm_scatter(const double* src, int64_t lds, double* dst, int64_t ldd, const int32_t* perm,
+                                int64_t n, int nrhs, const double* add, cudaStream_t st);
+cudaError_t launch_perm_scatter_nodemajor(const double* src, int64_t lds, double* dst, int64_t ldk,
+                                          const int32_t* perm, int64_t n, int k0, int nr, cudaStream_t st);
+cudaError_t launch_fwd_level(const SnodeDesc* sd, const int32_t* list, int count, int maxd, const int32_t* child_idx,
+                             const int32_t* relmap, const double* F, double* x, int64_t ldx, double* uvec, int nr,
+                             cudaStream_t st);
+cudaError_t launch_bwd_level(const SnodeDesc* sd, const int32_t* list, int count, int maxd, const int32_t* rows,
+                             const double* F, double* x, int64_t ldx, int nr, cudaStream_t st);
+cudaError_t launch_spmv_rows(int64_t nrows, const int64_t* ptr, const int32_t* idx, const double* val,
+                             const double* x, double* y, double alpha, double beta, cudaStream_t st);
+cudaError_t launch_rbmc(int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, const double* X,
+                        int64_t ldk, int nsamp, double* var, cudaStream_t st);
+cudaError_t launch_gather_values(const double* src, const int64_t* map, int64_t nnz, double* dst, cudaStream_t st);
+cudaError_t launch_postprec(int64_t nnz_out, const int64_t* qsrc, const double* Qval, const int64_t* pptr,
+                            const int32_t* prow, const int64_t* pa, const int64_t* pb, const double* Aval,
+                            const double* wdiag, double wscalar, double* out, cudaStream_t st);
+cudaError_t launch_dot(const double* a, const double* b, int64_t n, double* out, cudaStream_t st);
+cudaError_t launch_axpby(int64_t n, double a, const double* x, double b, const double* y, double* out,
+                         cudaStream_t st);
+cudaError_t launch_diag_L(const SnodeDesc* sd, int nsuper, const double* F, double* out, cudaStream_t st);
+
+}  // namespace gmrfb

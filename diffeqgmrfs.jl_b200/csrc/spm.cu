@@ -1,0 +1,282 @@
+// C ABI: device-resident sparse matrices, SpMV, sqmahal and the fixed-pattern posterior-precision assembly
+//   Qpost = Q + A' diag(w) A    (condition_on_observations, scripts/darcy/solve_darcy_gmrf-fem.jl:165-167;
+//                                Q + noise*J'*J, scripts/solve_burger.jl:145)
+#include <algorithm>
+#include <memory>
+
+#include "common.hpp"
+#include "handles.hpp"
+
+using namespace gmrfb;
+
+struct gmrfb_postprec {
+  gmrfb_ctx* ctx = nullptr;
+  const gmrfb_spm* Q = nullptr;
+  const gmrfb_spm* A = nullptr;
+  gmrfb_spm out;  // owned result matrix
+  DevBuf<int64_t> d_qsrc, d_pptr, d_pa, d_pb;
+  DevBuf<int32_t> d_prow;
+  DevBuf<double> d_w;
+  int64_t nprod = 0;
+};
+
+static gmrfb_status spm_build(gmrfb_ctx* ctx, gmrfb_spm* M, int64_t m, int64_t n, const int64_t* colptr,
+                              const int64_t* rowval, const double* nzval, int base) {
+  M->ctx = ctx;
+  M->m = m;
+  M->n = n;
+  if (colptr[0] != base) return fail(ctx, GMRFB_ERR_INVALID, "spm: colptr[0] must equal base");
+  M->nnz = colptr[n] - base;
+  M->colptr.resize(n + 1);
+  M->rowidx.resize(M->nnz);
+  for (int64_t j = 0; j <= n; j++) M->colptr[j] = colptr[j] - base;
+  for (int64_t j = 0; j < n; j++) {
+    if (M->colptr[j + 1] < M->colptr[j]) return fail(ctx, GMRFB_ERR_INVALID, "spm: colptr is not monotone");
+    for (int64_t p = M->colptr[j]; p < M->colptr[j + 1]; p++) {
+      int64_t r = rowval[p] - base;
+      if (r < 0 || r >= m) return fail(ctx, GMRFB_ERR_INVALID, "spm: row index out of range");
+      if (p > M->colptr[j] && rowval[p] <= rowval[p - 1])
+        return fail(ctx, GMRFB_ERR_INVALID, "spm: row indices must be strictly increasing within a column");
+      M->rowidx[p] = (int32_t)r;
+    }
+  }
+  // row-wise copy: rowptr/colidx and the map from row-wise position to CSC position
+  std::vector<int64_t> rowptr(m + 1, 0), tmap(M->nnz);
+  std::vector<int32_t> colidx(M->nnz);
+  for (int64_t p = 0; p < M->nnz; p++) rowptr[M->rowidx[p] + 1]++;
+  for (int64_t i = 0; i < m; i++) rowptr[i + 1] += rowptr[i];
+  {
+    std::vector<int64_t> fillp(rowptr.begin(), rowptr.end() - 1);
+    for (int64_t j = 0; j < n; j++)
+      for (int64_t p = M->colptr[j]; p < M->colptr[j + 1]; p++) {
+        int64_t q = fillp[M->rowidx[p]]++;
+        colidx[q] = (int32_t)j;
+        tmap[q] = p;
+      }
+  }
+  cudaStream_t st = ctx->stream;
+  GMRFB_CU(ctx, M->d_colptr.upload(M->colptr, st));
+  GMRFB_CU(ctx, M->d_rowidx.upload(M->rowidx, st));
+  GMRFB_CU(ctx, M->d_rowptr.upload(rowptr, st));
+  GMRFB_CU(ctx, M->d_colidx.upload(colidx, st));
+  GMRFB_CU(ctx, M->d_tmap.upload(tmap, st));
+  GMRFB_CU(ctx, M->d_val.alloc((size_t)std::max<int64_t>(M->nnz, 1)));
+  GMRFB_CU(ctx, M->d_tval.alloc((size_t)std::max<int64_t>(M->nnz, 1)));
+  if (nzval) {
+    GMRFB_CU(ctx, cudaMemcpyAsync(M->d_val.p, nzval, M->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+    GMRFB_CU(ctx, launch_gather_values(M->d_val.p, M->d_tmap.p, M->nnz, M->d_tval.p, st));
+    ctx->launches++;
+    GMRFB_CU(ctx, cudaStreamSynchronize(st));
+  }
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_spm_create(gmrfb_ctx* ctx, int64_t m, int64_t n, const int64_t* colptr,
+                                         const int64_t* rowval, const double* nzval, int32_t base, gmrfb_spm** out) {
+  if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_create: ctx is NULL");
+  if (!out || !colptr || m < 0 || n < 0 || (base != 0 && base != 1))
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_spm_create: bad argument");
+  if (m > 2000000000 || n > 2000000000) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_spm_create: dimension too large");
+  *out = nullptr;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<gmrfb_spm> M(new gmrfb_spm());
+  gmrfb_status rc = spm_build(ctx, M.get(), m, n, colptr, rowval, nzval, base);
+  if (rc != GMRFB_OK) return rc;
+  *out = M.release();
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_spm_set_values(gmrfb_spm* A, const double* nzval) {
+  if (!A || !nzval) return fail(A ? A->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_set_values: NULL argument");
+  gmrfb_ctx* ctx = A->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  GMRFB_CU(ctx, cudaMemcpyAsync(A->d_val.p, nzval, A->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GMRFB_CU(ctx, launch_gather_values(A->d_val.p, A->d_tmap.p, A->nnz, A->d_tval.p, ctx->stream));
+  ctx->launches++;
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_spm_destroy(gmrfb_spm* A) {
+  if (!A) return GMRFB_OK;
+  if (A->owned_by_plan) return fail(A->ctx, GMRFB_ERR_INVALID, "matrix is owned by a posterior-precision plan");
+  cudaSetDevice(A->ctx->device);
+  cudaStreamSynchronize(A->ctx->stream);
+  delete A;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_spm_dims(const gmrfb_spm* A, int64_t* m, int64_t* n, int64_t* nnz) {
+  if (!A) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_dims: NULL argument");
+  if (m) *m = A->m;
+  if (n) *n = A->n;
+  if (nnz) *nnz = A->nnz;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_spm_get(const gmrfb_spm* A, int32_t base, int64_t* colptr, int64_t* rowval,
+                                      double* nzval) {
+  if (!A) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_get: NULL argument");
+  gmrfb_ctx* ctx = A->ctx;
+  if (colptr)
+    for (int64_t j = 0; j <= A->n; j++) colptr[j] = A->colptr[j] + base;
+  if (rowval)
+    for (int64_t p = 0; p < A->nnz; p++) rowval[p] = A->rowidx[p] + base;
+  if (nzval) {
+    GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+    GMRFB_CU(ctx, cudaMemcpyAsync(nzval, A->d_val.p, A->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return GMRFB_OK;
+}
+
+extern "C" const double* gmrfb_spm_values_dev(const gmrfb_spm* A) { return A ? A->d_val.p : nullptr; }
+
+extern "C" gmrfb_status gmrfb_spmv(const gmrfb_spm* A, int32_t trans, double alpha, const double* x, double beta,
+                                   double* y) {
+  if (!A || !x || !y) return fail(A ? A->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_spmv: NULL argument");
+  gmrfb_ctx* ctx = A->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t nx = trans ? A->m : A->n, ny = trans ? A->n : A->m;
+  DevBuf<double> dx, dy;
+  GMRFB_CU(ctx, dx.alloc((size_t)std::max<int64_t>(nx, 1)));
+  GMRFB_CU(ctx, dy.alloc((size_t)std::max<int64_t>(ny, 1)));
+  GMRFB_CU(ctx, cudaMemcpyAsync(dx.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (beta != 0.0) GMRFB_CU(ctx, cudaMemcpyAsync(dy.p, y, ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (trans)  // y_j = sum over column j of A: the CSC arrays are the rows of A'
+    GMRFB_CU(ctx, launch_spmv_rows(A->n, A->d_colptr.p, A->d_rowidx.p, A->d_val.p, dx.p, dy.p, alpha, beta, ctx->stream));
+  else
+    GMRFB_CU(ctx, launch_spmv_rows(A->m, A->d_rowptr.p, A->d_colidx.p, A->d_tval.p, dx.p, dy.p, alpha, beta, ctx->stream));
+  ctx->launches++;
+  GMRFB_CU(ctx, cudaMemcpyAsync(y, dy.p, ny * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_sqmahal(const gmrfb_spm* Q, const double* mu, const double* v, double* out) {
+  if (!Q || !v || !out) return fail(Q ? Q->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sqmahal: NULL argument");
+  if (Q->m != Q->n) return fail(Q->ctx, GMRFB_ERR_INVALID, "gmrfb_sqmahal: Q must be square");
+  gmrfb_ctx* ctx = Q->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = Q->n;
+  DevBuf<double> dv, dmu, dd, dt;
+  GMRFB_CU(ctx, dv.alloc((size_t)std::max<int64_t>(n, 1)));
+  GMRFB_CU(ctx, dd.alloc((size_t)std::max<int64_t>(n, 1)));
+  GMRFB_CU(ctx, dt.alloc((size_t)std::max<int64_t>(n, 1)));
+  GMRFB_CU(ctx, cudaMemcpyAsync(dv.p, v, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (mu) {
+    GMRFB_CU(ctx, dmu.alloc((size_t)std::max<int64_t>(n, 1)));
+    GMRFB_CU(ctx, cudaMemcpyAsync(dmu.p, mu, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  GMRFB_CU(ctx, launch_axpby(n, 1.0, dv.p, -1.0, mu ? dmu.p : nullptr, dd.p, ctx->stream));
+  GMRFB_CU(ctx, launch_spmv_rows(n, Q->d_rowptr.p, Q->d_colidx.p, Q->d_tval.p, dd.p, dt.p, 1.0, 0.0, ctx->stream));
+  GMRFB_CU(ctx, launch_dot(dd.p, dt.p, n, ctx->d_scalar, ctx->stream));
+  ctx->launches += 3;
+  GMRFB_CU(ctx, cudaMemcpyAsync(out, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+// ------------------------------------------------------------------------------ posterior precision ----
+extern "C" gmrfb_status gmrfb_postprec_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, const gmrfb_spm* A,
+                                              gmrfb_postprec** out) {
+  if (!ctx || !Q || !A || !out) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_postprec_create: NULL argument");
+  if (Q->m != Q->n || A->n != Q->n) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_postprec_create: shape mismatch");
+  *out = nullptr;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = Q->n, m = A->m;
+  // rows of A (host): rowptr / (col, csc position)
+  std::vector<int64_t> rptr(m + 1, 0);
+  for (int64_t p = 0; p < A->nnz; p++) rptr[A->rowidx[p] + 1]++;
+  for (int64_t i = 0; i < m; i++) rptr[i + 1] += rptr[i];
+  std::vector<int32_t> rcol(A->nnz);
+  std::vector<int64_t> rpos(A->nnz);
+  {
+    std::vector<int64_t> fillp(rptr.begin(), rptr.end() - 1);
+    for (int64_t j = 0; j < A->n; j++)
+      for (int64_t p = A->colptr[j]; p < A->colptr[j + 1]; p++) {
+        int64_t q = fillp[A->rowidx[p]]++;
+        rcol[q] = (int32_t)j;
+        rpos[q] = p;
+      }
+  }
+  // column by column: merge pattern(Q[:,j]) with the columns i reached through shared rows k
+  struct Prod {
+    int32_t i;   // output row
+    int32_t k;   // observation row
+    int64_t pa;  // position of A[k,i]
+    int64_t pb;  // position of A[k,j]
+  };
+  std::vector<int64_t> ocolptr(n + 1, 0), qsrc, pptr, pa, pb;
+  std::vector<int32_t> orow, prow;
+  std::vector<Prod> prods;
+  pptr.push_back(0);
+  for (int64_t j = 0; j < n; j++) {
+    prods.clear();
+    for (int64_t p = A->colptr[j]; p < A->colptr[j + 1]; p++) {
+      int32_t k = A->rowidx[p];
+      for (int64_t q = rptr[k]; q < rptr[k + 1]; q++) prods.push_back({rcol[q], k, rpos[q], p});
+    }
+    std::sort(prods.begin(), prods.end(), [](const Prod& a, const Prod& b) { return a.i < b.i || (a.i == b.i && a.k < b.k); });
+    size_t ip = 0;
+    int64_t qp = Q->colptr[j], qe = Q->colptr[j + 1];
+    while (ip < prods.size() || qp < qe) {
+      int32_t ri = ip < prods.size() ? prods[ip].i : INT32_MAX;
+      int32_t rq = qp < qe ? Q->rowidx[qp] : INT32_MAX;
+      int32_t r = std::min(ri, rq);
+      orow.push_back(r);
+      qsrc.push_back(rq == r ? qp++ : -1);
+      while (ip < prods.size() && prods[ip].i == r) {
+        prow.push_back(prods[ip].k);
+        pa.push_back(prods[ip].pa);
+        pb.push_back(prods[ip].pb);
+        ip++;
+      }
+      pptr.push_back((int64_t)prow.size());
+    }
+    ocolptr[j + 1] = (int64_t)orow.size();
+  }
+  std::unique_ptr<gmrfb_postprec> P(new gmrfb_postprec());
+  P->ctx = ctx;
+  P->Q = Q;
+  P->A = A;
+  P->nprod = (int64_t)prow.size();
+  std::vector<int64_t> orow64(orow.begin(), orow.end());
+  gmrfb_status rc = spm_build(ctx, &P->out, n, n, ocolptr.data(), orow64.data(), nullptr, 0);
+  if (rc != GMRFB_OK) return rc;
+  P->out.owned_by_plan = true;
+  cudaStream_t st = ctx->stream;
+  GMRFB_CU(ctx, P->d_qsrc.upload(qsrc, st));
+  GMRFB_CU(ctx, P->d_pptr.upload(pptr, st));
+  GMRFB_CU(ctx, P->d_pa.upload(pa, st));
+  GMRFB_CU(ctx, P->d_pb.upload(pb, st));
+  GMRFB_CU(ctx, P->d_prow.upload(prow, st));
+  GMRFB_CU(ctx, P->d_w.alloc((size_t)std::max<int64_t>(m, 1)));
+  *out = P.release();
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_postprec_destroy(gmrfb_postprec* plan) {
+  if (!plan) return GMRFB_OK;
+  cudaSetDevice(plan->ctx->device);
+  cudaStreamSynchronize(plan->ctx->stream);
+  delete plan;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps_scalar, const double* qeps_diag,
+                                               const gmrfb_spm** Qpost) {
+  if (!plan) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_postprec_compute: NULL plan");
+  gmrfb_ctx* ctx = plan->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  if (qeps_diag)
+    GMRFB_CU(ctx, cudaMemcpyAsync(plan->d_w.p, qeps_diag, plan->A->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GMRFB_CU(ctx, launch_postprec(plan->out.nnz, plan->d_qsrc.p, plan->Q->d_val.p, plan->d_pptr.p, plan->d_prow.p,
+                                plan->d_pa.p, plan->d_pb.p, plan->A->d_val.p, qeps_diag ? plan->d_w.p : nullptr,
+                                qeps_scalar, plan->out.d_val.p, ctx->stream));
+  GMRFB_CU(ctx, launch_gather_values(plan->out.d_val.p, plan->out.d_tmap.p, plan->out.nnz, plan->out.d_tval.p, ctx->stream));
+  ctx->launches += 2;
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (Qpost) *Qpost = &plan->out;
+  return GMRFB_OK;
+}

@@ -1,0 +1,692 @@
+// Symbolic analysis (host, integer): ordering, elimination tree, column counts, supernodes, frontal layout.
+// See symbolic.hpp.  Algorithms are the published ones, restated here from their descriptions:
+//  - elimination tree: Liu (1990), ancestor path compression;
+//  - column counts: Gilbert, Ng & Peyton (1994) skeleton-leaf / least-common-ancestor scheme;
+//  - nested dissection: George & Liu automatic ND (BFS level-structure bisection from a pseudo-peripheral
+//    vertex) with a boundary-layer vertex separator; coordinate bisection when node coordinates are supplied;
+//  - relaxed supernode amalgamation in the spirit of CHOLMOD's nrelax/zrelax rule, tuned for wide GPU fronts.
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace gmrfb {
+
+// ---------------------------------------------------------------------------------------------------------
+// Elimination tree of a symmetric pattern given as sorted adjacency lists (no diagonal), both triangles.
+void etree_lower(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
+                 std::vector<int32_t>& parent) {
+  parent.assign(n, -1);
+  std::vector<int32_t> anc(n, -1);
+  for (int32_t i = 0; i < n; i++) {
+    for (int64_t p = xadj[i]; p < xadj[i + 1]; p++) {
+      int32_t k = adj[p];
+      if (k >= i) break;  // sorted: only neighbours below i
+      // climb from k to the current root of its subtree, redirecting every visited node to i
+      while (k != -1 && k < i) {
+        int32_t next = anc[k];
+        anc[k] = i;
+        if (next == -1) parent[k] = i;
+        k = next;
+      }
+    }
+  }
+}
+
+// Postorder of a forest: children visited in ascending order, roots in ascending order.
+void postorder_tree(int32_t n, const std::vector<int32_t>& parent, std::vector<int32_t>& post) {
+  std::vector<int32_t> head(n, -1), next(n, -1);
+  for (int32_t j = n - 1; j >= 0; j--) {
+    int32_t p = parent[j];
+    if (p >= 0) {
+      next[j] = head[p];
+      head[p] = j;
+    }
+  }
+  post.clear();
+  post.reserve(n);
+  std::vector<int32_t> stack;
+  for (int32_t r = 0; r < n; r++) {
+    if (parent[r] != -1) continue;
+    stack.push_back(r);
+    while (!stack.empty()) {
+      int32_t v = stack.back();
+      int32_t c = head[v];
+      if (c == -1) {
+        post.push_back(v);
+        stack.pop_back();
+      } else {
+        head[v] = next[c];
+        stack.push_back(c);
+      }
+    }
+  }
+}
+
+// Column counts of L (incl. diagonal) without forming L.  post[k] = k-th vertex of a postorder.
+void column_counts(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
+                   const std::vector<int32_t>& parent, const std::vector<int32_t>& post,
+                   std::vector<int32_t>& colcount) {
+  std::vector<int32_t> first(n, -1), maxfirst(n, -1), prevleaf(n, -1), setroot(n);
+  std::vector<int64_t> delta(n, 0);
+  // first[j]: postorder rank of the first descendant of j; a vertex is an etree leaf iff it is its own first.
+  for (int32_t k = 0; k < n; k++) {
+    int32_t j = post[k];
+    delta[j] = (first[j] == -1) ? 1 : 0;
+    for (; j != -1 && first[j] == -1; j = parent[j]) first[j] = k;
+  }
+  std::iota(setroot.begin(), setroot.end(), 0);
+  for (int32_t k = 0; k < n; k++) {
+    int32_t j = post[k];
+    if (parent[j] != -1) delta[parent[j]]--;
+    // rows i > j with A(i,j) != 0: is j a leaf of the row subtree of i?
+    for (int64_t p = xadj[j]; p < xadj[j + 1]; p++) {
+      int32_t i = adj[p];
+      if (i <= j) continue;
+      if (first[j] <= maxfirst[i]) continue;  // j lies under a previously seen leaf's subtree: not a leaf
+      maxfirst[i] = first[j];
+      int32_t jprev = prevleaf[i];
+      prevleaf[i] = j;
+      delta[j]++;
+      if (jprev != -1) {
+        // least common ancestor of jprev and j = representative of jprev's merged set
+        int32_t q = jprev;
+        while (q != setroot[q]) q = setroot[q];
+        for (int32_t s = jprev; s != q;) {
+          int32_t sn = setroot[s];
+          setroot[s] = q;
+          s = sn;
+        }
+        delta[q]--;
+      }
+    }
+    if (parent[j] != -1) setroot[j] = parent[j];
+  }
+  // accumulate along the tree: children are always numbered below their parent
+  for (int32_t j = 0; j < n; j++)
+    if (parent[j] != -1) delta[parent[j]] += delta[j];
+  colcount.resize(n);
+  for (int32_t j = 0; j < n; j++) colcount[j] = (int32_t)delta[j];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Nested dissection.
+namespace {
+
+struct NDWork {
+  int32_t n;
+  const std::vector<int64_t>& xadj;
+  const std::vector<int32_t>& adj;
+  std::vector<int32_t> verts;   // current elimination order, rearranged in place
+  std::vector<int32_t> label;   // subset id of each vertex
+  std::vector<int32_t> lvl;     // BFS level scratch (valid where stamp matches)
+  std::vector<int32_t> stamp;   // visit stamp
+  std::vector<int32_t> queue;
+  int32_t next_label = 1, next_stamp = 1;
+  int leaf;
+  int coord_dim;
+  const double* coords;
+  NDWork(int32_t n_, const std::vector<int64_t>& xa, const std::vector<int32_t>& a)
+      : n(n_), xadj(xa), adj(a), verts(n_), label(n_, 0), lvl(n_, 0), stamp(n_, 0) {
+    std::iota(verts.begin(), verts.end(), 0);
+    queue.reserve(n_);
+  }
+
+  // BFS inside subset `lab` from `root`; fills queue (visit order) and lvl; returns number of levels.
+  int bfs(int32_t root, int32_t lab, int32_t st, bool append) {
+    if (!append) queue.clear();
+    size_t head = queue.size();
+    queue.push_back(root);
+    stamp[root] = st;
+    lvl[root] = 0;
+    int maxl = 0;
+    while (head < queue.size()) {
+      int32_t v = queue[head++];
+      int32_t lv = lvl[v];
+      for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+        int32_t u = adj[p];
+        if (label[u] != lab || stamp[u] == st) continue;
+        stamp[u] = st;
+        lvl[u] = lv + 1;
+        if (lv + 1 > maxl) maxl = lv + 1;
+        queue.push_back(u);
+      }
+    }
+    return maxl + 1;
+  }
+
+  int32_t degree_in(int32_t v, int32_t lab) const {
+    int32_t d = 0;
+    for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) d += (label[adj[p]] == lab);
+    return d;
+  }
+};
+
+}  // namespace
+
+void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
+                       int leaf, int coord_dim, const double* coords, std::vector<int32_t>& perm) {
+  NDWork W(n, xadj, adj);
+  W.leaf = leaf > 0 ? leaf : 24;
+  W.coord_dim = coord_dim;
+  W.coords = coords;
+  struct Range {
+    int32_t lo, hi;
+  };
+  std::vector<Range> todo;
+  todo.push_back({0, n});
+  std::vector<int32_t> side;  // scratch: 0 = A, 1 = B, 2 = S for vertices of the current range (by position)
+  std::vector<int32_t> tmp;
+  while (!todo.empty()) {
+    Range r = todo.back();
+    todo.pop_back();
+    int32_t m = r.hi - r.lo;
+    if (m <= W.leaf) continue;  // leaf: keep the order it inherited (BFS order of the parent bisection)
+    int32_t lab = W.next_label++;
+    for (int32_t k = r.lo; k < r.hi; k++) W.label[W.verts[k]] = lab;
+    // --- choose a bipartition A0 | B of the range; mark with stamp: in A0 <=> inA[v] ---
+    // inA encoded in lvl sign via separate stamp array `side` indexed by position.
+    side.assign(m, 1);
+    bool split_done = false;
+    std::vector<int32_t>& q = W.queue;
+    if (W.coords && W.coord_dim > 0) {
+      // coordinate bisection along the widest axis, at the median
+      int cd = W.coord_dim, best = 0;
+      double bestw = -1;
+      for (int d = 0; d < cd; d++) {
+        double lo = 1e300, hi = -1e300;
+        for (int32_t k = r.lo; k < r.hi; k++) {
+          double c = W.coords[(int64_t)W.verts[k] * cd + d];
+          lo = std::min(lo, c);
+          hi = std::max(hi, c);
+        }
+        if (hi - lo > bestw) {
+          bestw = hi - lo;
+          best = d;
+        }
+      }
+      tmp.assign(W.verts.begin() + r.lo, W.verts.begin() + r.hi);
+      int32_t half = m / 2;
+      std::nth_element(tmp.begin(), tmp.begin() + half, tmp.end(), [&](int32_t a, int32_t b) {
+        double ca = W.coords[(int64_t)a * cd + best], cb = W.coords[(int64_t)b * cd + best];
+        return ca < cb || (ca == cb && a < b);
+      });
+      // stamp A0 members
+      int32_t st = W.next_stamp++;
+      for (int32_t k = 0; k < half; k++) W.stamp[tmp[k]] = st;
+      // reorder range as tmp (A0 first), set side
+      for (int32_t k = 0; k < m; k++) {
+        W.verts[r.lo + k] = tmp[k];
+        side[k] = (k < half) ? 0 : 1;
+      }
+      // lvl used as "in A0" flag via stamp
+      split_done = true;
+      // boundary of A0 -> S
+      for (int32_t k = 0; k < half; k++) {
+        int32_t v = W.verts[r.lo + k];
+        for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+          int32_t u = adj[p];
+          if (W.label[u] == lab && W.stamp[u] != st) {
+            side[k] = 2;
+            break;
+          }
+        }
+      }
+    } else {
+      // pseudo-peripheral root by repeated BFS
+      int32_t root = W.verts[r.lo];
+      int32_t st = W.next_stamp++;
+      int nl = W.bfs(root, lab, st, false);
+      if ((int32_t)q.size() == m) {
+        for (int it = 0; it < 4; it++) {
+          // candidate: minimum in-subset degree among the last level
+          int32_t cand = q.back(), cd = INT32_MAX;
+          for (int32_t k = (int32_t)q.size() - 1; k >= 0 && W.lvl[q[k]] == nl - 1; k--) {
+            int32_t d = W.degree_in(q[k], lab);
+            if (d < cd || (d == cd && q[k] < cand)) {
+              cd = d;
+              cand = q[k];
+            }
+          }
+          int32_t st2 = W.next_stamp++;
+          int nl2 = W.bfs(cand, lab, st2, false);
+          st = st2;
+          root = cand;
+          if (nl2 <= nl) {
+            nl = nl2;
+            break;
+          }
+          nl = nl2;
+        }
+      }
+      if ((int32_t)q.size() < m) {
+        // disconnected: gather whole components into A until half the range is covered; S is empty.
+        int32_t half = m / 2;
+        int32_t last_start = 0;
+        if ((int32_t)q.size() < half) {
+          for (int32_t k = r.lo; k < r.hi && (int32_t)q.size() < half; k++) {
+            int32_t v = W.verts[k];
+            if (W.stamp[v] != st) {
+              last_start = (int32_t)q.size();
+              W.bfs(v, lab, st, true);
+            }
+          }
+        }
+        int32_t na = (int32_t)q.size();
+        if (na == m) na = last_start;  // everything gathered: the last component becomes B
+        tmp.clear();
+        tmp.insert(tmp.end(), q.begin(), q.end());
+        for (int32_t k = r.lo; k < r.hi; k++)
+          if (W.stamp[W.verts[k]] != st) tmp.push_back(W.verts[k]);
+        for (int32_t k = 0; k < m; k++) {
+          W.verts[r.lo + k] = tmp[k];
+          side[k] = (k < na) ? 0 : 1;
+        }
+        split_done = true;
+      }
+      if (!split_done) {
+        // connected: q holds the BFS order from `root`, levels in W.lvl, nl levels
+        if (nl < 3) continue;  // (near-)clique: no useful separator, treat as leaf
+        // smallest level index mcut with |levels <= mcut| >= m/2, but keep at least one level on each side
+        std::vector<int32_t> cnt(nl, 0);
+        for (int32_t v : q) cnt[W.lvl[v]]++;
+        int32_t acc = 0, mcut = 0;
+        for (int l = 0; l < nl; l++) {
+          acc += cnt[l];
+          if (acc * 2 >= m) {
+            mcut = l;
+            break;
+          }
+        }
+        if (mcut >= nl - 1) mcut = nl - 2;
+        if (mcut < 1) mcut = 1;
+        tmp.assign(q.begin(), q.end());
+        for (int32_t k = 0; k < m; k++) {
+          int32_t v = tmp[k];
+          W.verts[r.lo + k] = v;
+          int32_t l = W.lvl[v];
+          if (l < mcut)
+            side[k] = 0;
+          else if (l > mcut)
+            side[k] = 1;
+          else {
+            // level mcut: separator only if adjacent to level mcut+1
+            bool b = false;
+            for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+              int32_t u = adj[p];
+              if (W.label[u] == lab && W.lvl[u] == mcut + 1) {
+                b = true;
+                break;
+              }
+            }
+            side[k] = b ? 2 : 0;
+          }
+        }
+        split_done = true;
+      }
+    }
+    // stable partition of the range into A | B | S
+    tmp.resize(m);
+    int32_t na = 0, nb = 0, ns = 0;
+    for (int32_t k = 0; k < m; k++) na += (side[k] == 0), nb += (side[k] == 1), ns += (side[k] == 2);
+    if (nb == 0 || na == 0) {
+      // degenerate split (everything on one side): accept as leaf to guarantee progress
+      if (ns == 0 || na + nb == 0) continue;
+    }
+    int32_t pa = 0, pb = na, ps = na + nb;
+    for (int32_t k = 0; k < m; k++) {
+      int32_t v = W.verts[r.lo + k];
+      if (side[k] == 0)
+        tmp[pa++] = v;
+      else if (side[k] == 1)
+        tmp[pb++] = v;
+      else
+        tmp[ps++] = v;
+    }
+    std::copy(tmp.begin(), tmp.end(), W.verts.begin() + r.lo);
+    // separator vertices leave the active graph
+    for (int32_t k = na + nb; k < m; k++) W.label[W.verts[r.lo + k]] = -1;
+    if (nb > 0) todo.push_back({r.lo + na, r.lo + na + nb});
+    if (na > 0) todo.push_back({r.lo, r.lo + na});
+  }
+  perm = W.verts;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static std::string build_adjacency(int64_t n, const int64_t* colptr, const int64_t* rowval, int base,
+                                   std::vector<int64_t>& xadj, std::vector<int32_t>& adj) {
+  // symmetrised pattern without the diagonal, sorted, de-duplicated
+  int64_t nnz = colptr[n] - base;
+  std::vector<int64_t> deg(n + 1, 0);
+  for (int64_t c = 0; c < n; c++) {
+    int64_t p0 = colptr[c] - base, p1 = colptr[c + 1] - base;
+    if (p0 > p1 || p0 < 0 || p1 > nnz) return "colptr is not monotone";
+    for (int64_t p = p0; p < p1; p++) {
+      int64_t r = rowval[p] - base;
+      if (r < 0 || r >= n) return "row index out of range";
+      if (p > p0 && rowval[p] <= rowval[p - 1]) return "row indices must be strictly increasing within a column";
+      if (r != c) {
+        deg[r + 1]++;
+        deg[c + 1]++;
+      }
+    }
+  }
+  std::vector<int64_t> start(n + 1, 0);
+  for (int64_t i = 0; i < n; i++) start[i + 1] = start[i] + deg[i + 1];
+  std::vector<int32_t> raw(start[n]);
+  std::vector<int64_t> fill(start.begin(), start.end() - 1);
+  for (int64_t c = 0; c < n; c++)
+    for (int64_t p = colptr[c] - base; p < colptr[c + 1] - base; p++) {
+      int64_t r = rowval[p] - base;
+      if (r != c) {
+        raw[fill[r]++] = (int32_t)c;
+        raw[fill[c]++] = (int32_t)r;
+      }
+    }
+  xadj.assign(n + 1, 0);
+  adj.clear();
+  adj.reserve(raw.size() / 2 + n);
+  for (int64_t i = 0; i < n; i++) {
+    auto b = raw.begin() + start[i], e = raw.begin() + start[i + 1];
+    std::sort(b, e);
+    auto e2 = std::unique(b, e);
+    adj.insert(adj.end(), b, e2);
+    xadj[i + 1] = (int64_t)adj.size();
+  }
+  return "";
+}
+
+std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* rowval, const int64_t* perm_in,
+                            const AnalyzeOptions& opt, Symbolic& S) {
+  if (n64 < 0 || n64 > (int64_t)2000000000) return "n out of range";
+  if (!colptr || (n64 > 0 && !rowval)) return "null pattern";
+  if (opt.base != 0 && opt.base != 1) return "base must be 0 or 1";
+  if (opt.storage < 0 || opt.storage > 2) return "bad storage kind";
+  const int32_t n = (int32_t)n64;
+  const int base = opt.base;
+  S = Symbolic();
+  S.n = n;
+  S.base = base;
+  S.storage = opt.storage;
+  S.nnzA = colptr[n] - base;
+  if (colptr[0] != base) return "colptr[0] must equal base";
+
+  std::vector<int64_t> xadj;
+  std::vector<int32_t> adj;
+  std::string err = build_adjacency(n, colptr, rowval, base, xadj, adj);
+  if (!err.empty()) return err;
+
+  // ---- ordering ----
+  S.perm_user.resize(n);
+  if (opt.ordering_kind == 0) {
+    if (!perm_in) return "ORDER_GIVEN needs a permutation";
+    std::vector<char> seen(n, 0);
+    for (int32_t k = 0; k < n; k++) {
+      int64_t v = perm_in[k] - base;
+      if (v < 0 || v >= n || seen[v]) return "perm is not a permutation";
+      seen[v] = 1;
+      S.perm_user[k] = (int32_t)v;
+    }
+  } else if (opt.ordering_kind == 1) {
+    std::iota(S.perm_user.begin(), S.perm_user.end(), 0);
+  } else if (opt.ordering_kind == 2) {
+    if (opt.coords && (opt.coord_dim < 1 || opt.coord_dim > 3)) return "coord_dim must be 1..3";
+    nested_dissection(n, xadj, adj, opt.nd_leaf, opt.coords ? opt.coord_dim : 0, opt.coords, S.perm_user);
+  } else {
+    return "unknown ordering kind";
+  }
+
+  // ---- permuted adjacency (perm_user ordering) ----
+  std::vector<int32_t> ipu(n);
+  for (int32_t k = 0; k < n; k++) ipu[S.perm_user[k]] = k;
+  std::vector<int64_t> pxadj(n + 1, 0);
+  std::vector<int32_t> padj(adj.size());
+  for (int32_t k = 0; k < n; k++) pxadj[k + 1] = pxadj[k] + (xadj[S.perm_user[k] + 1] - xadj[S.perm_user[k]]);
+  for (int32_t k = 0; k < n; k++) {
+    int32_t v = S.perm_user[k];
+    int64_t o = pxadj[k];
+    for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) padj[o++] = ipu[adj[p]];
+    std::sort(padj.begin() + pxadj[k], padj.begin() + pxadj[k + 1]);
+  }
+  S.nnz_lower_A = (int64_t)adj.size() / 2 + n;
+
+  // ---- etree, postorder, column counts in the perm_user ordering ----
+  etree_lower(n, pxadj, padj, S.parent_user);
+  postorder_tree(n, S.parent_user, S.post);
+  column_counts(n, pxadj, padj, S.parent_user, S.post, S.colcount_user);
+  S.nnzL = 0;
+  S.flops = 0;
+  for (int32_t j = 0; j < n; j++) {
+    S.nnzL += S.colcount_user[j];
+    S.flops += (double)S.colcount_user[j] * (double)S.colcount_user[j];
+  }
+
+  // ---- internal (postordered) numbering ----
+  S.ipost.resize(n);
+  S.perm.resize(n);
+  S.iperm.resize(n);
+  for (int32_t k = 0; k < n; k++) S.ipost[S.post[k]] = k;
+  for (int32_t k = 0; k < n; k++) {
+    S.perm[k] = S.perm_user[S.post[k]];
+    S.iperm[S.perm[k]] = k;
+  }
+  S.parent.resize(n);
+  S.colcount.resize(n);
+  for (int32_t k = 0; k < n; k++) {
+    int32_t pu = S.parent_user[S.post[k]];
+    S.parent[k] = pu < 0 ? -1 : S.ipost[pu];
+    S.colcount[k] = S.colcount_user[S.post[k]];
+  }
+  // internal adjacency (needed for the supernode row structures): neighbours above each column
+  std::vector<int64_t> ixadj(n + 1, 0);
+  std::vector<int32_t> iadj;  // for internal column k: sorted internal neighbours i > k
+  {
+    std::vector<int64_t> cnt(n + 1, 0);
+    for (int32_t k = 0; k < n; k++) {
+      int32_t ku = S.post[k];
+      int64_t c = 0;
+      for (int64_t p = pxadj[ku]; p < pxadj[ku + 1]; p++) c += (S.ipost[padj[p]] > k);
+      cnt[k + 1] = c;
+    }
+    for (int32_t k = 0; k < n; k++) ixadj[k + 1] = ixadj[k] + cnt[k + 1];
+    iadj.resize(ixadj[n]);
+    for (int32_t k = 0; k < n; k++) {
+      int32_t ku = S.post[k];
+      int64_t o = ixadj[k];
+      for (int64_t p = pxadj[ku]; p < pxadj[ku + 1]; p++) {
+        int32_t i = S.ipost[padj[p]];
+        if (i > k) iadj[o++] = i;
+      }
+      std::sort(iadj.begin() + ixadj[k], iadj.begin() + ixadj[k + 1]);
+    }
+  }
+
+  // ---- fundamental supernodes ----
+  std::vector<int32_t> nchild(n, 0);
+  for (int32_t k = 0; k < n; k++)
+    if (S.parent[k] >= 0) nchild[S.parent[k]]++;
+  struct SN {
+    int32_t first, last;  // column range
+    int64_t true_nnz;     // Σ colcount over its columns
+    int32_t order;        // front order = colcount of first column after merges (s + r)
+  };
+  std::vector<SN> sn;
+  sn.reserve(n / 2 + 1);
+  const int relax_small = opt.relax_small > 0 ? opt.relax_small : 16;
+  const double relax_zeros = opt.relax_zeros > 0 ? opt.relax_zeros : 0.0;  // 0 => tiered default below
+  auto trapezoid = [](int64_t s, int64_t d) { return s * d - s * (s - 1) / 2; };
+  for (int32_t k = 0; k < n;) {
+    int32_t f = k;
+    int64_t tn = S.colcount[k];
+    while (k + 1 < n && S.parent[k] == k + 1 && S.colcount[k + 1] == S.colcount[k] - 1 && nchild[k + 1] == 1) {
+      k++;
+      tn += S.colcount[k];
+    }
+    SN cur{f, k, tn, S.colcount[f]};
+    // relaxed amalgamation with the immediately preceding supernode when it is a child of `cur`
+    while (!sn.empty()) {
+      SN& c = sn.back();
+      int32_t pc = S.parent[c.last];
+      if (pc < cur.first || pc > cur.last) break;  // not a child
+      int64_t s_new = (cur.last - cur.first + 1) + (c.last - c.first + 1);
+      int64_t d_new = (c.last - c.first + 1) + cur.order;
+      int64_t stored = trapezoid(s_new, d_new);
+      int64_t truen = c.true_nnz + cur.true_nnz;
+      double zfrac = (double)(stored - truen) / (double)stored;
+      bool merge;
+      if (s_new <= relax_small)
+        merge = true;
+      else if (relax_zeros > 0)
+        merge = zfrac <= relax_zeros;
+      else if (s_new <= 32)
+        merge = zfrac <= 0.5;
+      else if (s_new <= 64)
+        merge = zfrac <= 0.15;
+      else
+        merge = zfrac <= 0.05;
+      if (!merge) break;
+      cur.first = c.first;
+      cur.true_nnz = truen;
+      cur.order = (int32_t)d_new;
+      sn.pop_back();
+    }
+    sn.push_back(cur);
+    k++;
+  }
+  S.nsuper = (int32_t)sn.size();
+  S.sptr.resize(S.nsuper + 1);
+  S.snode.resize(n);
+  for (int32_t s = 0; s < S.nsuper; s++) {
+    S.sptr[s] = sn[s].first;
+    for (int32_t k = sn[s].first; k <= sn[s].last; k++) S.snode[k] = s;
+  }
+  S.sptr[S.nsuper] = n;
+  S.sparent.assign(S.nsuper, -1);
+  for (int32_t s = 0; s < S.nsuper; s++) {
+    int32_t p = S.parent[sn[s].last];
+    S.sparent[s] = p < 0 ? -1 : S.snode[p];
+  }
+  // children lists
+  S.child_ptr.assign(S.nsuper + 1, 0);
+  for (int32_t s = 0; s < S.nsuper; s++)
+    if (S.sparent[s] >= 0) S.child_ptr[S.sparent[s] + 1]++;
+  for (int32_t s = 0; s < S.nsuper; s++) S.child_ptr[s + 1] += S.child_ptr[s];
+  S.child_idx.resize(S.child_ptr[S.nsuper]);
+  {
+    std::vector<int32_t> fillp(S.child_ptr.begin(), S.child_ptr.end() - 1);
+    for (int32_t s = 0; s < S.nsuper; s++)
+      if (S.sparent[s] >= 0) S.child_idx[fillp[S.sparent[s]]++] = s;
+  }
+
+  // ---- row structures (bottom-up union) ----
+  S.rptr.assign(S.nsuper + 1, 0);
+  S.rows.clear();
+  S.rows.reserve((size_t)n * 4);
+  {
+    std::vector<int32_t> mark(n, -1);
+    std::vector<int32_t> below;
+    for (int32_t s = 0; s < S.nsuper; s++) {
+      int32_t f = S.sptr[s], l = S.sptr[s + 1] - 1;
+      below.clear();
+      for (int32_t k = f; k <= l; k++) {
+        S.rows.push_back(k);
+        mark[k] = s;
+      }
+      for (int32_t k = f; k <= l; k++)
+        for (int64_t p = ixadj[k]; p < ixadj[k + 1]; p++) {
+          int32_t i = iadj[p];
+          if (i > l && mark[i] != s) {
+            mark[i] = s;
+            below.push_back(i);
+          }
+        }
+      for (int32_t ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ci++) {
+        int32_t c = S.child_idx[ci];
+        int32_t sc = S.sptr[c + 1] - S.sptr[c];
+        for (int64_t p = S.rptr[c] + sc; p < S.rptr[c + 1]; p++) {
+          int32_t i = S.rows[p];
+          if (i > l && mark[i] != s) {
+            mark[i] = s;
+            below.push_back(i);
+          }
+        }
+      }
+      std::sort(below.begin(), below.end());
+      S.rows.insert(S.rows.end(), below.begin(), below.end());
+      S.rptr[s + 1] = (int64_t)S.rows.size();
+      if ((int32_t)(S.rptr[s + 1] - S.rptr[s]) != sn[s].order)
+        return "internal error: column counts disagree with the supernodal row structure";
+    }
+  }
+  // ---- relmap, layout, levels ----
+  S.relmap.assign(S.rows.size(), -1);
+  S.ld.resize(S.nsuper);
+  S.foff.resize(S.nsuper);
+  S.level.assign(S.nsuper, 0);
+  S.arena = 0;
+  S.nnzL_stored = 0;
+  S.max_front = 0;
+  for (int32_t s = 0; s < S.nsuper; s++) {
+    int32_t d = S.front_order(s), sc = S.ncols(s);
+    S.max_front = std::max(S.max_front, d);
+    S.ld[s] = (d + 1) & ~1;  // even leading dimension: 16-byte aligned columns
+    S.foff[s] = S.arena;
+    S.arena += (int64_t)S.ld[s] * d;
+    S.arena = (S.arena + 15) & ~(int64_t)15;  // 128-byte aligned fronts
+    S.nnzL_stored += trapezoid(sc, d);
+    int32_t p = S.sparent[s];
+    if (p >= 0) {
+      // positions of s's below-rows inside the parent's (sorted) row list
+      int64_t q = S.rptr[p];
+      const int64_t qe = S.rptr[p + 1];
+      for (int64_t k = S.rptr[s] + sc; k < S.rptr[s + 1]; k++) {
+        int32_t i = S.rows[k];
+        while (q < qe && S.rows[q] < i) q++;
+        if (q >= qe || S.rows[q] != i) return "internal error: child row missing from parent front";
+        S.relmap[k] = (int32_t)(q - S.rptr[p]);
+      }
+      S.level[p] = std::max(S.level[p], S.level[s] + 1);
+    }
+  }
+  int32_t nlev = 0;
+  for (int32_t s = 0; s < S.nsuper; s++) nlev = std::max(nlev, S.level[s] + 1);
+  S.levels.assign(nlev, Level());
+  for (int32_t s = 0; s < S.nsuper; s++) S.levels[S.level[s]].snodes.push_back(s);
+
+  // ---- scatter map of the user's stored entries into the frontal arena ----
+  S.amap.assign(S.nnzA, -1);
+  for (int64_t c = 0; c < n; c++) {
+    int32_t jc = S.iperm[c];
+    for (int64_t p = colptr[c] - base; p < colptr[c + 1] - base; p++) {
+      int64_t r = rowval[p] - base;
+      int32_t ir = S.iperm[r];
+      int32_t i = ir, j = jc;
+      if (opt.storage == 0) {
+        // both triangles stored: take the copy that lands in the lower triangle of the permuted matrix;
+        // the diagonal is taken once
+        if (i < j) continue;
+      } else {
+        if (opt.storage == 1 && r < c) return "STORAGE_LOWER matrix has an entry above the diagonal";
+        if (opt.storage == 2 && r > c) return "STORAGE_UPPER matrix has an entry below the diagonal";
+        if (i < j) std::swap(i, j);
+      }
+      int32_t s = S.snode[j];
+      int32_t f = S.sptr[s], l = S.sptr[s + 1] - 1;
+      int64_t lr;
+      if (i <= l) {
+        lr = i - f;
+      } else {
+        auto b = S.rows.begin() + S.rptr[s] + (l - f + 1), e = S.rows.begin() + S.rptr[s + 1];
+        auto it = std::lower_bound(b, e, i);
+        if (it == e || *it != i) return "internal error: matrix entry outside the symbolic structure";
+        lr = (it - (S.rows.begin() + S.rptr[s]));
+      }
+      S.amap[p] = S.foff[s] + (int64_t)(j - f) * S.ld[s] + lr;
+    }
+  }
+  return "";
+}
+
+}  // namespace gmrfb

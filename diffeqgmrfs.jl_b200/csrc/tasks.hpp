@@ -1,0 +1,70 @@
+// Task descriptors shared by the host plan builders and the CUDA kernels.
+//
+// Every numeric phase of the library (multifrontal factorisation, triangular solves, selected inversion,
+// block-tridiagonal factorisation) is compiled on the host into a static list of *launches*; each launch is
+// one kernel over a contiguous range of Task records (a "grouped"/batched launch: many dense problems of
+// different sizes in one grid).  The lists depend only on the sparsity pattern, are uploaded once, and are
+// replayed for every new set of values (Gauss-Newton refactorisation) without further host work.
+#pragma once
+#include <cstdint>
+
+namespace gmrfb {
+
+// Which arena an operand lives in (2 bits each in Task::flags).
+enum : int32_t {
+  TF_A_SHIFT = 0,   // bits 0-1: arena of operand a
+  TF_B_SHIFT = 2,   // bits 2-3: arena of operand b
+  TF_C_SHIFT = 4,   // bits 4-5: arena of operand c
+  TF_TRI = 1 << 8,  // C is lower-trapezoidal: tiles strictly above the diagonal are skipped, diagonal tiles masked
+  TF_NEG = 1 << 9,  // kind-specific: negate result
+};
+
+struct alignas(16) Task {
+  int64_t a, b, c;  // element offsets into the arenas selected by flags
+  int32_t M, N, K;
+  int32_t lda, ldb, ldc;
+  int32_t tile0;  // index of this task's first CTA inside its launch
+  int32_t flags;
+  int32_t aux0, aux1;  // kind-specific
+  double alpha, beta;
+};
+
+enum LaunchKind : int32_t {
+  LK_GEMM_NT = 0,     // C = beta C + alpha A B'        A: MxK, B: NxK
+  LK_GEMM_NN = 1,     // C = beta C + alpha A B         A: MxK, B: KxN
+  LK_GEMM_TN = 2,     // C = beta C + alpha A' B        A: KxM, B: KxN
+  LK_POTRF = 3,       // in-place Cholesky of an n<=64 diagonal block (a, lda, M=n); aux0 = global column
+  LK_TRSM_RLT = 4,    // X <- X L^{-T}   L: b (NxN, ldb), X: c (MxN, ldc), N<=64
+  LK_TRSM_RLN = 5,    // X <- X L^{-1}
+  LK_EXTEND_ADD = 6,  // P[rel[i], rel[j]] += U[i,j] (i>=j): U: a (MxM, lda), P: c (ldc), rel at aux0
+  LK_GATHER_SYM = 7,  // Zc[i,j] = Zp[rel[i], rel[j]] symmetric read: Zp: a (lda), Zc: c (MxM, ldc), rel at aux0
+  LK_SET_IDENTITY = 8,  // c (MxM, ldc) <- I
+  LK_TRANSPOSE = 9,     // c (MxM, ldc) <- c' in place
+  LK_SCALE = 10,        // c (MxN, ldc) <- alpha c
+  LK_DIAG_OUT = 11,     // out[aux0 + i] = c[i,i], i < M   (out = int-indexed double buffer)
+  LK_SYMMETRIZE = 12,   // c (MxM): copy lower triangle to the upper
+};
+
+struct Launch {
+  int32_t kind;
+  int32_t task0, ntasks;
+  int32_t grid;  // number of CTAs
+};
+
+// GEMM tile geometry used by both the plan builder (tile counts) and the kernels.
+constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16;
+constexpr int NB = 64;           // panel width of the blocked POTRF/TRSM
+constexpr int TRSM_ROWS = 128;   // rows per CTA in the TRSM kernels
+constexpr int EA_TILE = 64;      // extend-add / gather tile edge
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// number of 128x128 tiles of an M x N result; lower-trapezoidal results skip tiles above the diagonal
+inline int gemm_tiles(int M, int N, bool tri) {
+  int tm = cdiv(M, GEMM_BM), tn = cdiv(N, GEMM_BN);
+  if (!tri) return tm * tn;
+  int t = 0;
+  for (int i = 0; i < tm; i++) t += (i + 1 < tn ? i + 1 : tn);
+  return t;
+}
+
+}  // namespace gmrfb

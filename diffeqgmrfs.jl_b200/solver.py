@@ -1,0 +1,678 @@
+"""Host-side mirror of the reference's solver/blueprint interface on top of libgmrfb (ctypes).
+
+The reference selects its linear-algebra backend by passing GaussianMarkovRandomFields.jl *blueprints*
+(``CholeskySolverBlueprint(var_strategy=RBMCStrategy(50), perm=p)``, ``GNCholeskySolverBlueprint(p)``) to
+``condition_on_observations`` / ``GaussNewtonOptimizer`` and then calls ``mean``, ``std``, ``rand``,
+``sqmahal`` on the resulting GMRF (e.g. scripts/darcy/solve_darcy_gmrf-fem.jl:100,165-192).
+Julia is not installed in this image, so the host side above the C ABI is written in Python with the same
+names, argument meaning and error behaviour; ``julia/GMRFB200.jl`` holds the equivalent ``ccall`` shim.
+
+Everything numeric happens in CUDA kernels behind ``include/gmrfb.h``; this module only marshals arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as B
+
+
+# ----------------------------------------------------------------------------------------------- context --
+class Context:
+    """A device + stream (gmrfb_ctx).  Raises if no sm_100-class GPU is visible — there is no CPU fallback."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        st = B.lib().gmrfb_ctx_create(device, C.byref(h))
+        B.check(st, None)
+        self.h = h
+        self.device = device
+        self._fin = weakref.finalize(self, B.lib().gmrfb_ctx_destroy, h)
+
+    def sync(self):
+        B.check(B.lib().gmrfb_ctx_sync(self.h), self.h)
+
+    @property
+    def stream(self) -> int:
+        return int(B.lib().gmrfb_ctx_stream(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(B.lib().gmrfb_ctx_launch_count(self.h))
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _csc(A):
+    A = sp.csc_matrix(A)
+    if not A.has_sorted_indices:
+        A = A.copy()
+        A.sort_indices()
+    A.sum_duplicates()
+    return A
+
+
+# --------------------------------------------------------------------------------------- sparse matrices --
+class SparseMatrix:
+    """Device-resident CSC matrix (gmrfb_spm)."""
+
+    def __init__(self, A, ctx: Context | None = None, _handle=None, _owner=None):
+        self.ctx = ctx or default_context()
+        if _handle is not None:
+            self.h = _handle
+            self._owner = _owner
+            return
+        A = _csc(A)
+        self.shape = A.shape
+        _, cp = B.i64(A.indptr)
+        _, ri = B.i64(A.indices)
+        _, nz = B.f64(A.data)
+        h = C.c_void_p()
+        st = B.lib().gmrfb_spm_create(self.ctx.h, A.shape[0], A.shape[1], cp, ri, nz, 0, C.byref(h))
+        B.check(st, self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_spm_destroy, h)
+
+    def dims(self):
+        m, n, z = C.c_int64(), C.c_int64(), C.c_int64()
+        B.check(B.lib().gmrfb_spm_dims(self.h, C.byref(m), C.byref(n), C.byref(z)), self.ctx.h)
+        return m.value, n.value, z.value
+
+    def set_values(self, data):
+        _, nz = B.f64(data)
+        B.check(B.lib().gmrfb_spm_set_values(self.h, nz), self.ctx.h)
+
+    def to_scipy(self):
+        m, n, z = self.dims()
+        cp = np.empty(n + 1, np.int64)
+        ri = np.empty(z, np.int64)
+        nz = np.empty(z, np.float64)
+        B.check(B.lib().gmrfb_spm_get(self.h, 0, cp.ctypes.data_as(B._I64P), ri.ctypes.data_as(B._I64P),
+                                      nz.ctypes.data_as(B._F64P)), self.ctx.h)
+        return sp.csc_matrix((nz, ri, cp), shape=(m, n))
+
+    def values_dev(self) -> int:
+        return int(B.lib().gmrfb_spm_values_dev(self.h) or 0)
+
+    def matvec(self, x, trans=False, alpha=1.0, beta=0.0, y=None):
+        m, n, _ = self.dims()
+        x, xp = B.f64(x)
+        out = np.zeros(n if trans else m) if y is None else np.array(y, dtype=np.float64)
+        B.check(B.lib().gmrfb_spmv(self.h, int(trans), alpha, xp, beta, out.ctypes.data_as(B._F64P)), self.ctx.h)
+        return out
+
+    def sqmahal(self, v, mu=None):
+        _, vp = B.f64(v)
+        mup = None
+        if mu is not None:
+            mu, mup = B.f64(mu)
+        out = C.c_double()
+        B.check(B.lib().gmrfb_sqmahal(self.h, mup, vp, C.byref(out)), self.ctx.h)
+        return out.value
+
+
+class PosteriorPrecision:
+    """Fixed-pattern plan for Q + A' diag(q_eps) A (gmrfb_postprec): symbolic once, numeric per call."""
+
+    def __init__(self, Q: SparseMatrix, A: SparseMatrix):
+        self.ctx = Q.ctx
+        self.Q, self.A = Q, A
+        h = C.c_void_p()
+        B.check(B.lib().gmrfb_postprec_create(self.ctx.h, Q.h, A.h, C.byref(h)), self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_postprec_destroy, h)
+
+    def compute(self, q_eps) -> SparseMatrix:
+        out = C.c_void_p()
+        if np.isscalar(q_eps):
+            st = B.lib().gmrfb_postprec_compute(self.h, float(q_eps), None, C.byref(out))
+        else:
+            _, wp = B.f64(q_eps)
+            st = B.lib().gmrfb_postprec_compute(self.h, 0.0, wp, C.byref(out))
+        B.check(st, self.ctx.h)
+        return SparseMatrix(None, ctx=self.ctx, _handle=out, _owner=self)
+
+
+# ------------------------------------------------------------------------------------ symbolic + numeric --
+class Symbolic:
+    """Symbolic analysis of one sparsity pattern (gmrfb_sym).  ``perm`` is 0-based new->old (Julia's
+    ``perm=p`` is 1-based; the Julia shim passes base=1)."""
+
+    def __init__(self, A, perm=None, ordering="nd", coords=None, ctx: Context | None = None, host_only=False,
+                 nd_leaf=0, relax_small=0, relax_zeros=0.0, storage=B.STORAGE_FULL):
+        A = _csc(A)
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("matrix must be square")
+        self.ctx = None if host_only else (ctx or default_context())
+        self.n = A.shape[0]
+        self.nnz = A.nnz
+        opts = B.AnalyzeOpts()
+        if perm is not None:
+            opts.ordering_kind = B.ORDER_GIVEN
+        else:
+            opts.ordering_kind = {"nd": B.ORDER_ND, "natural": B.ORDER_NATURAL}[ordering]
+        opts.storage = storage
+        opts.base = 0
+        self._coords = None
+        if coords is not None:
+            self._coords = np.ascontiguousarray(coords, dtype=np.float64)
+            opts.coord_dim = self._coords.shape[1]
+            opts.coords = self._coords.ctypes.data_as(B._F64P)
+        opts.nd_leaf = nd_leaf
+        opts.relax_small = relax_small
+        opts.relax_zeros = relax_zeros
+        _, cp = B.i64(A.indptr)
+        _, ri = B.i64(A.indices)
+        pp = None
+        if perm is not None:
+            _, pp = B.i64(perm)
+        h = C.c_void_p()
+        ch = self.ctx.h if self.ctx else None
+        st = B.lib().gmrfb_analyze(ch, self.n, cp, ri, pp, C.byref(opts), C.byref(h))
+        B.check(st, ch)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_sym_destroy, h)
+        self._cache = None
+
+    @property
+    def info(self) -> B.SymInfo:
+        info = B.SymInfo()
+        B.check(B.lib().gmrfb_sym_get_info(self.h, C.byref(info)), None)
+        return info
+
+    def _get(self):
+        if self._cache is None:
+            n = self.n
+            ns = self.info.nsuper
+            perm, parent, cc, ip = (np.empty(n, np.int64) for _ in range(4))
+            sptr = np.empty(ns + 1, np.int64)
+            B.check(B.lib().gmrfb_sym_get(self.h, *(a.ctypes.data_as(B._I64P) for a in (perm, parent, cc, sptr, ip))),
+                    None)
+            self._cache = dict(perm=perm, parent=parent, colcount=cc, super_ptr=sptr, ipost=ip)
+        return self._cache
+
+    p = property(lambda self: self._get()["perm"])
+    parent = property(lambda self: self._get()["parent"])
+    colcount = property(lambda self: self._get()["colcount"])
+    super_ptr = property(lambda self: self._get()["super_ptr"])
+    ipost = property(lambda self: self._get()["ipost"])
+
+    def super_rows(self, s):
+        cnt = C.c_int64()
+        B.check(B.lib().gmrfb_sym_get_super_rows(self.h, s, None, 0, C.byref(cnt)), None)
+        rows = np.empty(cnt.value, np.int64)
+        B.check(B.lib().gmrfb_sym_get_super_rows(self.h, s, rows.ctypes.data_as(B._I64P), cnt.value, C.byref(cnt)), None)
+        return rows
+
+
+class CholeskyFactor:
+    """Numeric supernodal factor (gmrfb_fac) with the CHOLMOD-factor surface the reference touches:
+    ``F \\ b`` -> ``solve``; ``F.PtL \\ b`` -> ``PtL_solve``; ``F.UP \\ z`` -> ``UP_solve``; ``F.p``; ``nnz``;
+    ``F.L``; ``issuccess``."""
+
+    def __init__(self, sym: Symbolic):
+        if sym.ctx is None:
+            raise B.GmrfbError(B.ERR_STATE, "symbolic handle is host-only")
+        self.sym = sym
+        self.ctx = sym.ctx
+        h = C.c_void_p()
+        B.check(B.lib().gmrfb_fac_create(sym.h, C.byref(h)), self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_fac_destroy, h)
+        self.success = False
+
+    def factorize(self, nzval, check=True):
+        nzval, p = B.f64(nzval)
+        if nzval.size != self.sym.nnz:
+            raise ValueError("nzval length does not match the analysed pattern")
+        st = B.lib().gmrfb_factorize(self.h, p)
+        self.success = st == B.OK
+        if st == B.ERR_NOT_SPD and not check:
+            return self
+        B.check(st, self.ctx.h)
+        return self
+
+    def factorize_dev(self, dptr: int, check=True):
+        st = B.lib().gmrfb_factorize_dev(self.h, C.c_void_p(dptr))
+        self.success = st == B.OK
+        if st == B.ERR_NOT_SPD and not check:
+            return self
+        B.check(st, self.ctx.h)
+        return self
+
+    def issuccess(self):
+        return self.success
+
+    @property
+    def info(self) -> B.FacInfo:
+        info = B.FacInfo()
+        B.check(B.lib().gmrfb_fac_get_info(self.h, C.byref(info)), self.ctx.h)
+        return info
+
+    @property
+    def p(self):
+        return self.sym.p
+
+    @property
+    def nnz(self):
+        return int(self.info.nnz_L)
+
+    def logdet(self):
+        return float(self.info.logdet)
+
+    def diagL(self):
+        out = np.empty(self.sym.n)
+        B.check(B.lib().gmrfb_fac_diag(self.h, out.ctypes.data_as(B._F64P)), self.ctx.h)
+        return out
+
+    @property
+    def L(self):
+        n = self.sym.n
+        cp = np.empty(n + 1, np.int64)
+        B.check(B.lib().gmrfb_fac_get_L(self.h, 0, 1, cp.ctypes.data_as(B._I64P), None, None), self.ctx.h)
+        ri = np.empty(cp[-1], np.int64)
+        nz = np.empty(cp[-1], np.float64)
+        B.check(B.lib().gmrfb_fac_get_L(self.h, 0, 1, cp.ctypes.data_as(B._I64P), ri.ctypes.data_as(B._I64P),
+                                        nz.ctypes.data_as(B._F64P)), self.ctx.h)
+        return sp.csc_matrix((nz, ri, cp), shape=(n, n))
+
+    def _solve(self, mode, b):
+        b = np.asarray(b, dtype=np.float64)
+        one = b.ndim == 1
+        X = np.asfortranarray(b.reshape(self.sym.n, -1).copy(order="F"))
+        B.check(B.lib().gmrfb_solve(self.h, mode, X.ctypes.data_as(B._F64P), self.sym.n, X.shape[1]), self.ctx.h)
+        return X[:, 0].copy() if one else X
+
+    def solve(self, b):
+        return self._solve(B.SOLVE_A, b)
+
+    def PtL_solve(self, b):
+        return self._solve(B.SOLVE_PTL, b)
+
+    def UP_solve(self, z):
+        return self._solve(B.SOLVE_UP, z)
+
+    def L_solve(self, b):
+        return self._solve(B.SOLVE_L, b)
+
+    def Lt_solve(self, b):
+        return self._solve(B.SOLVE_LT, b)
+
+    def solve_dev(self, dptr: int, nrhs=1, mode=B.SOLVE_A):
+        B.check(B.lib().gmrfb_solve_dev(self.h, mode, C.c_void_p(dptr), self.sym.n, nrhs), self.ctx.h)
+
+    def sample(self, Z, mean=None):
+        Z = np.asarray(Z, dtype=np.float64)
+        one = Z.ndim == 1
+        Zf = np.asfortranarray(Z.reshape(self.sym.n, -1))
+        X = np.empty_like(Zf, order="F")
+        mp = None
+        if mean is not None:
+            mean, mp = B.f64(mean)
+        B.check(B.lib().gmrfb_sample(self.h, mp, Zf.ctypes.data_as(B._F64P), self.sym.n, X.ctypes.data_as(B._F64P),
+                                     self.sym.n, Zf.shape[1]), self.ctx.h)
+        return X[:, 0].copy() if one else X
+
+    def var_selinv(self):
+        out = np.empty(self.sym.n)
+        B.check(B.lib().gmrfb_var_selinv(self.h, out.ctypes.data_as(B._F64P)), self.ctx.h)
+        return out
+
+    def var_selinv_dev(self, dptr: int):
+        B.check(B.lib().gmrfb_var_selinv_dev(self.h, C.c_void_p(dptr)), self.ctx.h)
+
+    def var_rbmc(self, Q: SparseMatrix, Z):
+        Zf = np.asfortranarray(np.asarray(Z, dtype=np.float64).reshape(self.sym.n, -1))
+        out = np.empty(self.sym.n)
+        B.check(B.lib().gmrfb_var_rbmc(self.h, Q.h, Zf.ctypes.data_as(B._F64P), self.sym.n, Zf.shape[1],
+                                       out.ctypes.data_as(B._F64P)), self.ctx.h)
+        return out
+
+    def selinv_entries(self, rows, cols):
+        rows, rp = B.i64(rows)
+        cols, cp = B.i64(cols)
+        out = np.empty(rows.size)
+        B.check(B.lib().gmrfb_selinv_entries(self.h, 0, rows.size, rp, cp, out.ctypes.data_as(B._F64P)), self.ctx.h)
+        return out
+
+
+def cholesky(A, perm=None, check=True, ctx=None, coords=None) -> CholeskyFactor:
+    """``cholesky(Symmetric(A); perm=perm, check=check)`` (scripts/solve_burger.jl:147,
+    scripts/darcy/solve_darcy_fem.jl:93).  ``perm`` is 0-based here."""
+    A = _csc(A)
+    sym = Symbolic(A, perm=perm, ctx=ctx, coords=coords)
+    return CholeskyFactor(sym).factorize(A.data, check=check)
+
+
+# ------------------------------------------------------------------------------- blueprints and the GMRF --
+class RBMCStrategy:
+    """``RBMCStrategy(N; rng)`` (scripts/darcy/solve_darcy_gmrf-fem.jl:100)."""
+
+    def __init__(self, n_samples: int, rng=None):
+        self.n_samples = int(n_samples)
+        self.rng = rng if rng is not None else np.random.default_rng()
+
+
+class TakahashiStrategy:
+    """Exact marginal variances by selected inversion (north-star capability)."""
+
+
+class CholeskySolverBlueprint:
+    """``CholeskySolverBlueprint(; var_strategy, perm)`` (scripts/darcy/solve_darcy_gmrf-fem.jl:100,174)."""
+
+    def __init__(self, var_strategy=None, perm=None, coords=None, ctx=None):
+        self.var_strategy = var_strategy if var_strategy is not None else TakahashiStrategy()
+        self.perm = perm
+        self.coords = coords
+        self.ctx = ctx
+
+
+class GNCholeskySolverBlueprint(CholeskySolverBlueprint):
+    """``GNCholeskySolverBlueprint(p)`` (scripts/burgers/solve_burgers_gmrf-fem.jl:170)."""
+
+    def __init__(self, perm=None, **kw):
+        super().__init__(perm=perm, **kw)
+
+
+class _Ref:
+    """Julia ``Ref``: ``x.solver_ref[]`` is spelled ``x.solver_ref[()]`` / ``x.solver_ref.value`` here."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __getitem__(self, _):
+        return self.value
+
+
+class CholeskySolver:
+    """What ``x.solver_ref[]`` points to: holds ``precision_chol`` (with ``.p``, ``.L``, ``nnz``)."""
+
+    def __init__(self, gmrf, blueprint: CholeskySolverBlueprint, symbolic: Symbolic | None = None):
+        self.gmrf = gmrf
+        self.blueprint = blueprint
+        Q = gmrf.precision
+        sym = symbolic or Symbolic(Q, perm=blueprint.perm, coords=blueprint.coords, ctx=blueprint.ctx)
+        self.precision_chol = CholeskyFactor(sym).factorize(Q.data)
+        self._mean = None
+        self._var = None
+
+    def compute_mean(self):
+        if self._mean is None:
+            g = self.gmrf
+            if g.information is None:
+                self._mean = g.prior_mean
+            else:
+                self._mean = g.prior_mean + self.precision_chol.solve(g.information)
+        return self._mean
+
+    def compute_variance(self):
+        if self._var is None:
+            vs = self.blueprint.var_strategy
+            if isinstance(vs, RBMCStrategy):
+                Z = vs.rng.standard_normal((self.gmrf.n, vs.n_samples))
+                Qd = SparseMatrix(self.gmrf.precision, ctx=self.precision_chol.ctx)
+                self._var = self.precision_chol.var_rbmc(Qd, Z)
+            else:
+                self._var = self.precision_chol.var_selinv()
+        return self._var
+
+    def compute_rand(self, rng):
+        z = rng.standard_normal(self.gmrf.n)
+        return self.precision_chol.sample(z, mean=self.compute_mean())
+
+
+class GMRF:
+    """``GMRF(mean, precision, solver_blueprint)`` (_research/elliptic_chen24.jl:166).  ``information`` carries
+    the lazy right-hand side of a conditioned GMRF: mean = prior_mean + Q^{-1} information."""
+
+    def __init__(self, mean, precision, solver_blueprint=None, information=None, _symbolic=None):
+        self.precision = _csc(precision)
+        self.n = self.precision.shape[0]
+        self.prior_mean = np.asarray(mean, dtype=np.float64)
+        self.information = information
+        bp = solver_blueprint or CholeskySolverBlueprint()
+        self.solver_ref = _Ref(CholeskySolver(self, bp, _symbolic))
+
+    def __len__(self):
+        return self.n
+
+
+def precision_map(x: GMRF):
+    return x.precision
+
+
+def to_matrix(Q):
+    return Q
+
+
+def mean(x: GMRF):
+    return x.solver_ref.value.compute_mean()
+
+
+def var(x: GMRF):
+    return x.solver_ref.value.compute_variance()
+
+
+def std(x: GMRF):
+    return np.sqrt(var(x))
+
+
+def rand(rng, x: GMRF):
+    return x.solver_ref.value.compute_rand(rng)
+
+
+def sqmahal(x: GMRF, v):
+    ch = x.solver_ref.value.precision_chol
+    return SparseMatrix(x.precision, ctx=ch.ctx).sqmahal(v, mu=mean(x))
+
+
+def condition_on_observations(x: GMRF, A, Q_eps, y, solver_blueprint=None) -> GMRF:
+    """``condition_on_observations(x, A, Q_eps, y; solver_blueprint)``
+    (scripts/darcy/solve_darcy_gmrf-fem.jl:165-167,188-189): posterior precision Q + A'Q_eps A (device
+    SpGEMM on a fixed pattern), posterior mean mu + Qpost^{-1} A'Q_eps (y - A mu)."""
+    bp = solver_blueprint or x.solver_ref.value.blueprint
+    ctx = x.solver_ref.value.precision_chol.ctx
+    A = _csc(A)
+    mu = mean(x)
+    Qd = SparseMatrix(x.precision, ctx=ctx)
+    Ad = SparseMatrix(A, ctx=ctx)
+    plan = PosteriorPrecision(Qd, Ad)
+    Qpost = plan.compute(Q_eps).to_scipy()
+    w = np.broadcast_to(np.asarray(Q_eps, dtype=np.float64), (A.shape[0],))
+    resid = np.asarray(y, dtype=np.float64) - Ad.matvec(mu)
+    info = Ad.matvec(w * resid, trans=True)
+    return GMRF(mu, Qpost, bp, information=info)
+
+
+# ------------------------------------------------------------------------------------------ Gauss-Newton --
+class GaussNewtonOptimizer:
+    """``GaussNewtonOptimizer(mu, Q, f_and_J, noise, y, x0; solver_bp, stopping_criterion)``
+    (scripts/burgers/solve_burgers_gmrf-fem.jl:172-182).  Each step is scripts/solve_burger.jl:143-149 with the
+    pattern analysed once and only the numeric factorisation repeated."""
+
+    def __init__(self, mu, Q, f_and_J, noise, y, x0, solver_bp=None, max_steps=20, rel_tol=1e-4):
+        self.mu = np.asarray(mu, dtype=np.float64)
+        self.Q_prior = _csc(Q)
+        self.f_and_J = f_and_J
+        self.noise = float(noise)
+        self.y = np.asarray(y, dtype=np.float64)
+        self.xk = np.asarray(x0, dtype=np.float64).copy()
+        self.bp = solver_bp or GNCholeskySolverBlueprint()
+        self.max_steps, self.rel_tol = max_steps, rel_tol
+        self.r_obs_norm_history = []
+        self.obj_history = []
+        self.Jk = None
+        self.Q_mat = None
+        self._sym = None
+        self._fac = None
+        self._plan = None
+
+    def _objective(self, x, fx):
+        d = self.mu - x
+        r = self.y - fx
+        return float(d @ (self.Q_prior @ d) + self.noise * (r @ r)), r
+
+    def step(self):
+        ctx = self.bp.ctx or default_context()
+        fx, J = self.f_and_J(self.xk)
+        J = _csc(J)
+        if self._plan is None:
+            self._Qd = SparseMatrix(self.Q_prior, ctx=ctx)
+            self._Jd = SparseMatrix(J, ctx=ctx)
+            self._plan = PosteriorPrecision(self._Qd, self._Jd)
+        else:
+            self._Jd.set_values(J.data)
+        Apost = self._plan.compute(self.noise)
+        if self._sym is None:
+            pat = Apost.to_scipy()
+            self._sym = Symbolic(pat, perm=self.bp.perm, coords=self.bp.coords, ctx=ctx)
+            self._fac = CholeskyFactor(self._sym)
+        self._fac.factorize_dev(Apost.values_dev())
+        rhs = self.Q_prior @ self.mu + self.noise * (J.T @ (J @ self.xk + (self.y - fx)))
+        self.xk = self._fac.solve(rhs)
+        self.Jk = J
+        self._Apost = Apost
+        return self.xk
+
+
+def optimize(gno: GaussNewtonOptimizer):
+    """``optimize(gno)``: iterate until the relative objective change < rel_tol or max_steps
+    (stopping rule of scripts/solve_burger.jl:171-180)."""
+    fx, _ = gno.f_and_J(gno.xk)
+    obj, r = gno._objective(gno.xk, fx)
+    last = np.inf
+    steps = 0
+    while (abs(last - obj) / abs(obj) > gno.rel_tol) and steps < gno.max_steps:
+        gno.step()
+        fx, _ = gno.f_and_J(gno.xk)
+        last = obj
+        obj, r = gno._objective(gno.xk, fx)
+        gno.obj_history.append(obj)
+        gno.r_obs_norm_history.append(float(np.linalg.norm(r)))
+        steps += 1
+    gno.Q_mat = gno._Apost.to_scipy() if steps > 0 else gno.Q_prior
+    gno.n_steps = steps
+    return gno.xk
+
+
+# ------------------------------------------------------------------------------- block tridiagonal factor --
+class _DenseChol:
+    """Stand-in for LinearAlgebra.Cholesky: ``.L`` is the lower factor."""
+
+    def __init__(self, L):
+        self.L = L
+
+
+class TridiagonalCholeskyFactor:
+    """``TridiagonalCholeskyFactor{T}`` (src/tridiagonal_cholesky.jl:5-9): ``N`` total rows, ``chos`` the
+    per-block factors, ``Cs`` the sub-diagonal blocks (``Cs[k]`` belongs to block row k+1).  The factor lives
+    on the device; blocks are copied out on access."""
+
+    def __init__(self, handle, ctx, N, b, nblocks):
+        self.h, self.ctx, self.N, self.b, self.nblocks = handle, ctx, N, b, nblocks
+        self._fin = weakref.finalize(self, B.lib().gmrfb_btd_destroy, handle)
+
+    def _block(self, i, which):
+        out = np.empty((self.b, self.b), order="F")
+        B.check(B.lib().gmrfb_btd_get_block(self.h, i, which, out.ctypes.data_as(B._F64P), self.b), self.ctx.h)
+        return out
+
+    @property
+    def chos(self):
+        return [_DenseChol(self._block(i, B.BTD_BLOCK_L)) for i in range(self.nblocks)]
+
+    @property
+    def Cs(self):
+        return [self._block(i, B.BTD_BLOCK_C) for i in range(self.nblocks - 1)]
+
+    @property
+    def info(self) -> B.BtdInfo:
+        info = B.BtdInfo()
+        B.check(B.lib().gmrfb_btd_get_info(self.h, C.byref(info)), self.ctx.h)
+        return info
+
+    def _solve(self, mode, b):
+        b = np.asarray(b, dtype=np.float64)
+        n = self.b * self.nblocks
+        one = b.ndim == 1
+        X = np.asfortranarray(b.reshape(b.shape[0], -1)[:n].copy(order="F"))
+        B.check(B.lib().gmrfb_btd_solve(self.h, mode, X.ctypes.data_as(B._F64P), n, X.shape[1]), self.ctx.h)
+        return X[:, 0].copy() if one else X
+
+    def logdet(self):
+        out = C.c_double()
+        B.check(B.lib().gmrfb_btd_logdet(self.h, C.byref(out)), self.ctx.h)
+        return out.value
+
+    def selinv_diag(self):
+        out = np.empty(self.b * self.nblocks)
+        B.check(B.lib().gmrfb_btd_selinv_diag(self.h, out.ctypes.data_as(B._F64P)), self.ctx.h)
+        return out
+
+
+def tridiagonal_cholesky(A, N_blocks, ctx=None) -> TridiagonalCholeskyFactor:
+    """``tridiagonal_cholesky(A::SparseMatrixCSC, N_blocks)`` (src/tridiagonal_cholesky.jl:65-82)."""
+    ctx = ctx or default_context()
+    A = _csc(A)
+    _, cp = B.i64(A.indptr)
+    _, ri = B.i64(A.indices)
+    _, nz = B.f64(A.data)
+    h = C.c_void_p()
+    st = B.lib().gmrfb_btd_factor(ctx.h, A.shape[0], cp, ri, nz, 0, N_blocks, C.byref(h))
+    if st != B.OK and h.value:
+        B.lib().gmrfb_btd_destroy(h)
+    B.check(st, ctx.h)
+    return TridiagonalCholeskyFactor(h, ctx, A.shape[0], A.shape[0] // N_blocks, N_blocks)
+
+
+def tridiagonal_cholesky_dense(D, Bsub, ctx=None) -> TridiagonalCholeskyFactor:
+    """Dense-block entry: D[b,b,N] diagonal blocks, Bsub[b,b,N-1] sub-diagonal blocks (Fortran order)."""
+    ctx = ctx or default_context()
+    D = np.asfortranarray(D, dtype=np.float64)
+    b, _, N = D.shape
+    Bp = None
+    if N > 1:
+        Bsub = np.asfortranarray(Bsub, dtype=np.float64)
+        Bp = Bsub.ctypes.data_as(B._F64P)
+    h = C.c_void_p()
+    st = B.lib().gmrfb_btd_factor_dense(ctx.h, b, N, D.ctypes.data_as(B._F64P), Bp, C.byref(h))
+    if st != B.OK and h.value:
+        B.lib().gmrfb_btd_destroy(h)
+    B.check(st, ctx.h)
+    return TridiagonalCholeskyFactor(h, ctx, b * N, b, N)
+
+
+def forward_solve(L, b):
+    """``forward_solve`` (src/tridiagonal_cholesky.jl:35-52): block factor -> L^{-1} b; sparse factor -> F.PtL \\ b."""
+    if isinstance(L, TridiagonalCholeskyFactor):
+        return L._solve(B.BTD_SOLVE_FWD, b)
+    return L.PtL_solve(b)
+
+
+def backward_solve(L, b):
+    """``backward_solve`` (src/tridiagonal_cholesky.jl:16-33): block factor -> L^{-T} b; sparse factor -> F.UP \\ b."""
+    if isinstance(L, TridiagonalCholeskyFactor):
+        return L._solve(B.BTD_SOLVE_BWD, b)
+    return L.UP_solve(b)
+
+
+def ldiv(L: TridiagonalCholeskyFactor, b):
+    """``ldiv(L, b)`` (src/tridiagonal_cholesky.jl:60-63), intended semantics A^{-1} b."""
+    return L._solve(B.BTD_SOLVE_A, b)
+
+
+def ldiv_(y, L: TridiagonalCholeskyFactor, b):
+    """``ldiv!(y, L, b)`` (:54-58)."""
+    y[...] = ldiv(L, b)
+    return y

@@ -1,0 +1,262 @@
+/*
+ * gmrfb.h — C ABI of libgmrfb, the B200-native (sm_100a) precision-matrix linear algebra
+ * behind Gaussian-Markov-random-field PDE solvers.
+ *
+ * This is the drop-in boundary for the hot path of timweiland/DiffEqGMRFs.jl: every entry
+ * point below names the reference call (file:line under /root/reference) it replaces.  The
+ * reference has no FFI of its own (it is pure Julia on top of SparseArrays.CHOLMOD and
+ * GaussianMarkovRandomFields.jl); a Julia `ccall` shim (julia/GMRFB200.jl) or the
+ * Python ctypes host in `diffeqgmrfs.jl_b200/` binds exactly these symbols.
+ *
+ * Conventions
+ *  - Every function returns a gmrfb_status (0 = ok).  Nothing throws or aborts across the ABI.
+ *    `gmrfb_last_error(ctx)` returns a human-readable message for the last failure on that context.
+ *  - All host arrays are caller-owned and only read/written during the call (calls are synchronous:
+ *    when a call returns, its host outputs are complete).  All device memory is owned by the library
+ *    behind opaque handles released by the matching *_destroy.
+ *  - Sparse matrices are CSC with 64-bit indices (Julia `SparseMatrixCSC{Float64,Int64}`):
+ *    colptr[n+1], rowval[nnz] sorted within a column, nzval[nnz]; `base` is 0 or 1 and applies to
+ *    colptr, rowval and permutations alike, so Julia passes its arrays untouched.
+ *  - Dense matrices are column-major Float64 with an explicit leading dimension.
+ *  - There is no CPU fallback: every numeric entry point runs CUDA kernels on the context's device
+ *    and fails with GMRFB_ERR_CUDA if that is impossible.
+ *  - One handle is used by one host thread at a time; distinct contexts may be used concurrently.
+ */
+#ifndef GMRFB_H
+#define GMRFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t gmrfb_status;
+enum {
+  GMRFB_OK = 0,
+  GMRFB_ERR_INVALID = 1,  /* bad argument (null pointer, size mismatch, unsorted/duplicate indices, bad perm) */
+  GMRFB_ERR_NOT_SPD = 2,  /* a pivot was <= 0 or NaN; gmrfb_factor_info reports the failing column */
+  GMRFB_ERR_ALLOC = 3,    /* host or device allocation failed */
+  GMRFB_ERR_CUDA = 4,     /* CUDA runtime error, or no usable device */
+  GMRFB_ERR_COMM = 5,     /* multi-GPU exchange failed */
+  GMRFB_ERR_STATE = 6     /* handle used in the wrong state (e.g. solve before a successful factorize) */
+};
+
+typedef struct gmrfb_ctx gmrfb_ctx; /* device + stream + scratch              */
+typedef struct gmrfb_sym gmrfb_sym; /* symbolic analysis of one sparsity pattern */
+typedef struct gmrfb_fac gmrfb_fac; /* numeric supernodal factor L (Q = P' L L' P) */
+typedef struct gmrfb_btd gmrfb_btd; /* dense block-tridiagonal factor          */
+typedef struct gmrfb_spm gmrfb_spm; /* device-resident sparse matrix (CSC)      */
+
+/* ---------------------------------------------------------------- context ---- */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int32_t gmrfb_version(void);
+
+/* Create a context bound to CUDA device `device` (its own stream).  Fails loudly without a GPU. */
+gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out);
+gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx);
+/* Message of the last error raised through `ctx` ("" if none).  Valid until the next call on ctx.
+ * With ctx == NULL returns the last context-free error (e.g. from a failed gmrfb_ctx_create). */
+const char* gmrfb_last_error(gmrfb_ctx* ctx);
+/* Block until all work queued on the context's stream has finished. */
+gmrfb_status gmrfb_ctx_sync(gmrfb_ctx* ctx);
+/* The context's cudaStream_t, as an integer, so a host (torch, CUDA.jl) can order its own work
+ * (event timing, NCCL exchanges) against the library's kernels. */
+uint64_t gmrfb_ctx_stream(gmrfb_ctx* ctx);
+/* Number of kernels this library has launched through `ctx` since creation (for benchmarks). */
+int64_t gmrfb_ctx_launch_count(gmrfb_ctx* ctx);
+
+/* ------------------------------------------------------ symbolic analysis ---- */
+/* Replaces the symbolic half of `cholesky(Symmetric(A); perm=p)` — CHOLMOD analyze / analyze_p:
+ *   scripts/solve_burger.jl:147, scripts/darcy/solve_darcy_fem.jl:93 and every
+ *   CholeskySolverBlueprint(perm=p) (scripts/darcy/solve_darcy_gmrf-fem.jl:100,174). */
+
+enum { /* ordering_kind */
+  GMRFB_ORDER_GIVEN = 0,   /* use `perm` exactly (Julia `perm=p`): the factor's .p equals perm */
+  GMRFB_ORDER_NATURAL = 1, /* identity */
+  GMRFB_ORDER_ND = 2       /* library's nested dissection (graph BFS bisection; coordinates if supplied) */
+};
+enum { /* storage */
+  GMRFB_STORAGE_FULL = 0,  /* both triangles stored (Julia Symmetric(sparse) of an assembled matrix) */
+  GMRFB_STORAGE_LOWER = 1, /* only entries with row >= col are stored                                */
+  GMRFB_STORAGE_UPPER = 2  /* only entries with row <= col are stored                                */
+};
+
+typedef struct gmrfb_analyze_opts {
+  int32_t ordering_kind;   /* GMRFB_ORDER_*                                                   */
+  int32_t storage;         /* GMRFB_STORAGE_*                                                 */
+  int32_t base;            /* 0 or 1: index base of colptr/rowval/perm                        */
+  int32_t coord_dim;       /* 0, or 2/3 when `coords` is given (ND then bisects geometrically) */
+  const double* coords;    /* optional n*coord_dim node coordinates, node-major; may be NULL  */
+  int32_t nd_leaf;         /* ND leaf size (0 = default)                                      */
+  int32_t relax_small;     /* supernode amalgamation: always merge when merged width <= this (0 = default) */
+  double relax_zeros;      /* ... or when the fraction of explicit zeros stays below this (0 = default)   */
+} gmrfb_analyze_opts;
+
+/* Analyse the pattern of a symmetric n-by-n matrix.  `perm` (length n, `base`-based, new->old as in
+ * Julia/CHOLMOD: row k of the permuted matrix is row perm[k] of A) is required for ORDER_GIVEN and
+ * ignored otherwise.  Produces: the fill-reducing permutation, elimination tree, column counts,
+ * supernode partition and every index map the numeric phases need (uploaded to the device once). */
+gmrfb_status gmrfb_analyze(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                           const int64_t* perm, const gmrfb_analyze_opts* opts, gmrfb_sym** out);
+gmrfb_status gmrfb_sym_destroy(gmrfb_sym* sym);
+
+typedef struct gmrfb_sym_info {
+  int64_t n;
+  int64_t nnz_lower_A;  /* stored entries of tril(P A P')                                 */
+  int64_t nnz_L;        /* Σ_j colcount[j]  (exact factor, before supernode relaxation)    */
+  int64_t nnz_L_stored; /* entries of the supernodal storage incl. explicit zeros          */
+  double flops;         /* Σ_j colcount[j]^2 (CHOLMOD's `fl` convention)                   */
+  int64_t nsuper;       /* number of supernodes                                            */
+  int64_t nlevels;      /* height of the supernodal elimination tree                       */
+  int64_t max_front;    /* largest frontal matrix order                                    */
+  int64_t front_bytes;  /* device bytes of the frontal arena (factor + update matrices)    */
+} gmrfb_sym_info;
+gmrfb_status gmrfb_sym_get_info(const gmrfb_sym* sym, gmrfb_sym_info* info);
+
+/* Copy out symbolic results.  Any pointer may be NULL.  All index outputs are `base`-based.
+ *   perm[n]      new->old, the `.p` field of a CHOLMOD factor (scripts/darcy/solve_darcy_gmrf-fem.jl:169)
+ *   parent[n]    elimination tree of P A P' in that ordering (root: base-1, i.e. -1 / 0)
+ *   colcount[n]  nnz of each column of L incl. the diagonal
+ *   super_ptr[nsuper+1]  first column (in the library's internal postordered numbering) of each supernode
+ *   ipost[n]     internal position of column k of the `perm` ordering (an etree postorder; identity-like
+ *                relabelling that leaves L unchanged up to symmetric permutation) */
+gmrfb_status gmrfb_sym_get(const gmrfb_sym* sym, int64_t* perm, int64_t* parent, int64_t* colcount,
+                           int64_t* super_ptr, int64_t* ipost);
+/* Row structure of supernode `s` (internal numbering, `base`-based): writes up to `cap` indices,
+ * returns the full count in *nrows.  Columns of the supernode come first. */
+gmrfb_status gmrfb_sym_get_super_rows(const gmrfb_sym* sym, int64_t s, int64_t* rows, int64_t cap,
+                                      int64_t* nrows);
+
+/* ------------------------------------------------- numeric factorisation ---- */
+/* Replaces the numeric half of `cholesky(A; perm, check=false)` (scripts/solve_burger.jl:147) and the
+ * factorisation inside condition_on_observations / GaussNewtonOptimizer for CholeskySolverBlueprint,
+ * GNCholeskySolverBlueprint (scripts/darcy/solve_darcy_gmrf-fem.jl:188, scripts/burgers/solve_burgers_gmrf-fem.jl:170-182). */
+
+/* Allocate the factor storage for `sym` (no values yet). */
+gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out);
+gmrfb_status gmrfb_fac_destroy(gmrfb_fac* fac);
+/* Numeric Cholesky from host values: nzval[nnz] in the order of the analysed colptr/rowval.
+ * Re-callable with new values on the same pattern (the Gauss-Newton loop, scripts/solve_burger.jl:171-180).
+ * Returns GMRFB_ERR_NOT_SPD (Julia: `check=false` leaves a queryable flag) if a pivot fails. */
+gmrfb_status gmrfb_factorize(gmrfb_fac* fac, const double* nzval);
+/* Same, values already on the device (device pointer, same order). */
+gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzval);
+
+typedef struct gmrfb_fac_info {
+  int32_t status;       /* GMRFB_OK or GMRFB_ERR_NOT_SPD for the last factorisation          */
+  int64_t fail_column;  /* first failing column (in `perm` order, 0-based) or -1              */
+  double logdet;        /* log det Q = 2 Σ log L_jj                                           */
+  int64_t nnz_L;        /* as `nnz(F)` (scripts/darcy/solve_darcy_gmrf-fem.jl:170): stored factor entries */
+} gmrfb_fac_info;
+gmrfb_status gmrfb_fac_get_info(gmrfb_fac* fac, gmrfb_fac_info* info);
+/* diag(L) in the `perm` ordering — `diag(sparse(F.L))` (scripts/burgers/solve_burgers_gmrf-collocation.jl:209). */
+gmrfb_status gmrfb_fac_diag(gmrfb_fac* fac, double* diagL);
+/* L as CSC (lower, `perm` ordering, `base`-based, sorted rows, explicit supernodal zeros dropped when
+ * drop_zeros != 0) — `sparse(F.L)`.  Call with colptr only to size the arrays (colptr[n] - base = nnz). */
+gmrfb_status gmrfb_fac_get_L(gmrfb_fac* fac, int32_t base, int32_t drop_zeros, int64_t* colptr,
+                             int64_t* rowval, double* nzval);
+
+/* ------------------------------------------------------------------ solves --- */
+/* X (n-by-nrhs, column-major, leading dimension ldx, host memory) is overwritten in place.
+ * Modes follow the CHOLMOD factor views the reference uses (src/tridiagonal_cholesky.jl:20-22,39-41):
+ *   A    : X <- Q^{-1} X            `F \ b`        (scripts/solve_burger.jl:148; posterior mean)
+ *   PtL  : X <- L^{-1} P X          `F.PtL \ b`    (forward_solve)
+ *   UP   : X <- P' L^{-T} X         `F.UP \ z`     (backward_solve; a N(0, Q^{-1}) sample for z ~ N(0,I))
+ *   L, Lt: X <- L^{-1} X, L^{-T} X in the permuted ordering (no P). */
+enum { GMRFB_SOLVE_A = 0, GMRFB_SOLVE_PTL = 1, GMRFB_SOLVE_UP = 2, GMRFB_SOLVE_L = 3, GMRFB_SOLVE_LT = 4 };
+gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int64_t ldx, int64_t nrhs);
+/* Device-pointer variant: d_X is n-by-nrhs column-major on the context's device. */
+gmrfb_status gmrfb_solve_dev(gmrfb_fac* fac, int32_t mode, double* d_X, int64_t ldx, int64_t nrhs);
+
+/* Samples  X[:,k] = mean + P' L^{-T} Z[:,k]  — `rand(rng, x)` (scripts/darcy/solve_darcy_gmrf-fem.jl:191).
+ * The host supplies the standard normals Z (n-by-nrhs) so "same seed" means "same z"; mean may be NULL. */
+gmrfb_status gmrfb_sample(gmrfb_fac* fac, const double* mean, const double* Z, int64_t ldz, double* X,
+                          int64_t ldx, int64_t nrhs);
+
+/* ------------------------------------------------------ marginal variances --- */
+/* diag(Q^{-1}) by Takahashi selected inversion on the supernodal factor (north-star capability;
+ * GMRF.jl `var`/`std` with the default strategy).  var_out[n] in the original ordering. */
+gmrfb_status gmrfb_var_selinv(gmrfb_fac* fac, double* var_out);
+gmrfb_status gmrfb_var_selinv_dev(gmrfb_fac* fac, double* d_var_out);
+/* Rao-Blackwellised Monte-Carlo variances, RBMCStrategy(N) (scripts/darcy/solve_darcy_gmrf-fem.jl:100,174,192):
+ *   var_i = 1/Q_ii + mean_k ( Σ_{j != i} Q_ij x_j^(k) )^2 / Q_ii^2,   x^(k) = P' L^{-T} z^(k).
+ * Q is the precision the factor was computed from; Z is n-by-nsamp standard normals supplied by the host. */
+gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
+                            int64_t nsamp, double* var_out);
+/* Selected entries of Q^{-1}: for each k, out[k] = (Q^{-1})[rows[k], cols[k]] (`base`-based indices in
+ * the original ordering).  Entries outside the filled pattern of L + L' yield GMRFB_ERR_INVALID. */
+gmrfb_status gmrfb_selinv_entries(gmrfb_fac* fac, int32_t base, int64_t count, const int64_t* rows,
+                                  const int64_t* cols, double* out);
+
+/* --------------------------------------------------- sparse matrix helpers --- */
+/* Device-resident CSC matrix (m-by-n, any shape) for SpMV and posterior-precision assembly. */
+gmrfb_status gmrfb_spm_create(gmrfb_ctx* ctx, int64_t m, int64_t n, const int64_t* colptr,
+                              const int64_t* rowval, const double* nzval, int32_t base, gmrfb_spm** out);
+gmrfb_status gmrfb_spm_set_values(gmrfb_spm* A, const double* nzval);
+gmrfb_status gmrfb_spm_destroy(gmrfb_spm* A);
+/* y <- alpha * op(A) x + beta * y  (host vectors; trans != 0 selects A').  `Q*x`, `J*x`, `J'*r`
+ * (scripts/solve_burger.jl:146,157). */
+gmrfb_status gmrfb_spmv(const gmrfb_spm* A, int32_t trans, double alpha, const double* x, double beta,
+                        double* y);
+/* (v - mu)' Q (v - mu) — `sqmahal` (scripts/burgers/solve_burgers_gmrf-collocation.jl:262). mu may be NULL. */
+gmrfb_status gmrfb_sqmahal(const gmrfb_spm* Q, const double* mu, const double* v, double* out);
+
+/* Posterior precision  Qpost = Q + A' diag(qeps) A  — the assembly inside condition_on_observations
+ * (scripts/darcy/solve_darcy_gmrf-fem.jl:165-167) and `Q + noise * J' * J` (scripts/solve_burger.jl:145).
+ * The pattern is computed once (symbolic, host) and the values by a device kernel; re-running with new
+ * values of A on the same pattern reuses the plan (Gauss-Newton). qeps_diag may be NULL (then qeps_scalar
+ * is used for every observation).  The result is a new gmrfb_spm (full symmetric storage). */
+typedef struct gmrfb_postprec gmrfb_postprec;
+gmrfb_status gmrfb_postprec_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, const gmrfb_spm* A,
+                                   gmrfb_postprec** out);
+gmrfb_status gmrfb_postprec_destroy(gmrfb_postprec* plan);
+/* Numeric phase; `Qpost` is owned by the plan and valid until the plan is destroyed. */
+gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps_scalar, const double* qeps_diag,
+                                    const gmrfb_spm** Qpost);
+/* Copy a device matrix's pattern/values back (any pointer may be NULL; sizes from gmrfb_spm_dims). */
+gmrfb_status gmrfb_spm_dims(const gmrfb_spm* A, int64_t* m, int64_t* n, int64_t* nnz);
+gmrfb_status gmrfb_spm_get(const gmrfb_spm* A, int32_t base, int64_t* colptr, int64_t* rowval,
+                           double* nzval);
+/* Device pointer to the matrix values (for gmrfb_factorize_dev). */
+const double* gmrfb_spm_values_dev(const gmrfb_spm* A);
+
+/* ------------------------------------------- block-tridiagonal Cholesky ------ */
+/* Replaces src/tridiagonal_cholesky.jl:
+ *   tridiagonal_cholesky(A, N_blocks)            :65-82   -> gmrfb_btd_factor
+ *   TridiagonalCholeskyFactor{N, chos, Cs}       :5-9     -> gmrfb_btd + gmrfb_btd_get_block
+ *   forward_solve / backward_solve / ldiv!       :24-63   -> gmrfb_btd_solve (intended semantics)
+ * A is block tridiagonal with N_blocks blocks of size b = n / N_blocks (integer division; trailing
+ * n mod N_blocks rows are ignored exactly as at :66; entries outside the block tridiagonal are ignored).
+ *   L_1 = chol(D_1);  C_i = B_i L_{i-1}^{-T};  L_i = chol(D_i - C_i C_i').                          */
+gmrfb_status gmrfb_btd_factor(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                              const double* nzval, int32_t base, int64_t nblocks, gmrfb_btd** out);
+/* Dense-block entry: D is b-by-b-by-N (diagonal blocks, lower triangle read), B is b-by-b-by-(N-1)
+ * (B[:,:,k] = block (k+2, k+1) of A, 1-based), both column-major and contiguous. */
+gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D,
+                                    const double* B, gmrfb_btd** out);
+gmrfb_status gmrfb_btd_destroy(gmrfb_btd* f);
+enum { GMRFB_BTD_BLOCK_L = 0, GMRFB_BTD_BLOCK_C = 1 };
+/* Copy block i (0-based) out: which = L -> `chos[i+1].L` (b-by-b lower, upper zeroed);
+ * which = C -> `Cs[i+1]` (the sub-diagonal block of L in block row i+2), i in [0, N-2]. */
+gmrfb_status gmrfb_btd_get_block(gmrfb_btd* f, int64_t i, int32_t which, double* out, int64_t ldo);
+enum { GMRFB_BTD_SOLVE_A = 0, GMRFB_BTD_SOLVE_FWD = 1, GMRFB_BTD_SOLVE_BWD = 2 };
+/* X (b*N-by-nrhs, column-major, host) in place: FWD = L^{-1} X, BWD = L^{-T} X, A = A^{-1} X. */
+gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, int64_t ldx, int64_t nrhs);
+gmrfb_status gmrfb_btd_logdet(gmrfb_btd* f, double* logdet);
+/* diag(A^{-1}) via the block Takahashi recursion  S_N = L_N^{-T} L_N^{-1},
+ * S_i = L_i^{-T}(I + C_{i+1}' S_{i+1} C_{i+1}) L_i^{-1}. */
+gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out);
+typedef struct gmrfb_btd_info {
+  int64_t b, nblocks;
+  int32_t status;      /* GMRFB_OK or GMRFB_ERR_NOT_SPD      */
+  int64_t fail_block;  /* first block whose POTRF failed, or -1 */
+  double flops;        /* (N-1) * 7/3 b^3 + b^3/3             */
+} gmrfb_btd_info;
+gmrfb_status gmrfb_btd_get_info(gmrfb_btd* f, gmrfb_btd_info* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMRFB_H */

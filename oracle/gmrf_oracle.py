@@ -1,0 +1,346 @@
+"""oracle/gmrf_oracle.py — TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of the reference's precision-matrix linear-algebra path.  Nothing under
+``diffeqgmrfs.jl_b200/`` imports this module; only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do.
+
+PARITY UNPINNED.  The reference (timweiland/DiffEqGMRFs.jl) pins no numerical results
+(test/runtests.jl:5-10 is Aqua lint only), Julia/CHOLMOD/GaussianMarkovRandomFields.jl are not installed
+here, and the only hot-path arithmetic whose source is in the reference is src/tridiagonal_cholesky.jl.
+The oracle therefore has three tiers, each pinned against something independent:
+
+* Tier A (dense, n <~ 8000): LAPACK through numpy/scipy — ``cho_factor``, triangular solves, ``inv``.
+* Tier B (sparse, mid size): ``sparse_chol.c`` — CHOLMOD's published simplicial algorithm
+  (Liu etree, row-subtree column counts, up-looking Cholesky, Takahashi recurrences); pinned against
+  Tier A in tests/test_oracle.py.
+* Block-tridiagonal: a line-by-line restatement of src/tridiagonal_cholesky.jl:65-82 (factor) and of the
+  *intended* semantics of :24-63 (solves; the three defects documented in SURVEY.md §8a T4/T5/T7 are not
+  reproduced), pinned against Tier A on the assembled matrix.
+
+For SPD Q and a fixed permutation, L is unique; means, ``P'L^{-T}z`` samples and ``diag(Q^{-1})`` are
+therefore implementation independent up to rounding, which is what makes these tiers a valid oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile sparse_chol.c into oracle/liboracle.so (gcc only)."""
+    src = os.path.join(_HERE, "sparse_chol.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _LIB_PATH, src, "-lm"])
+    return _LIB_PATH
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+        _lib.orc_symbolic.argtypes = [ctypes.c_int64, i64p, i64p, i64p, i64p, i64p]
+        _lib.orc_symbolic.restype = ctypes.c_int
+        _lib.orc_cholesky.argtypes = [ctypes.c_int64, i64p, i64p, f64p, i64p, i64p, i64p, i64p, f64p]
+        _lib.orc_cholesky.restype = ctypes.c_int
+        _lib.orc_lsolve.argtypes = [ctypes.c_int64, i64p, i64p, f64p, f64p, ctypes.c_int64]
+        _lib.orc_ltsolve.argtypes = [ctypes.c_int64, i64p, i64p, f64p, f64p, ctypes.c_int64]
+        _lib.orc_selinv.argtypes = [ctypes.c_int64, i64p, i64p, f64p, f64p]
+        _lib.orc_selinv.restype = ctypes.c_int
+    return _lib
+
+
+def _csc(A):
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    return A
+
+
+# ----------------------------------------------------------------------------------------------- Tier B --
+class SparseCholesky:
+    """P A P' = L L' with a given permutation (new->old, 0-based) — the CHOLMOD factor views the reference
+    uses: ``F \\ b``, ``F.PtL \\ b``, ``F.UP \\ z`` (src/tridiagonal_cholesky.jl:20-22,39-41), ``F.p``,
+    ``nnz``, ``diag(F.L)``."""
+
+    def __init__(self, A, perm):
+        lib = _load()
+        A = _csc(A)
+        n = A.shape[0]
+        self.n = n
+        self.perm = np.ascontiguousarray(perm, dtype=np.int64)
+        Ap = A.indptr.astype(np.int64)
+        Ai = A.indices.astype(np.int64)
+        Ax = A.data.astype(np.float64)
+        self.parent = np.empty(n, np.int64)
+        self.colcount = np.empty(n, np.int64)
+        rc = lib.orc_symbolic(n, Ap, Ai, self.perm, self.parent, self.colcount)
+        if rc != 0:
+            raise MemoryError("orc_symbolic failed")
+        self.Lp = np.zeros(n + 1, np.int64)
+        np.cumsum(self.colcount, out=self.Lp[1:])
+        self.Li = np.empty(int(self.Lp[-1]), np.int64)
+        self.Lx = np.empty(int(self.Lp[-1]), np.float64)
+        rc = lib.orc_cholesky(n, Ap, Ai, Ax, self.perm, self.parent, self.Lp, self.Li, self.Lx)
+        if rc != 0:
+            raise np.linalg.LinAlgError(f"not positive definite at permuted column {rc - 1}")
+
+    @property
+    def nnz(self):
+        return int(self.Lp[-1])
+
+    @property
+    def flops(self):
+        return float(np.sum(self.colcount.astype(np.float64) ** 2))
+
+    def L(self):
+        return sp.csc_matrix((self.Lx, self.Li, self.Lp), shape=(self.n, self.n))
+
+    def diagL(self):
+        return self.Lx[self.Lp[:-1]].copy()
+
+    def logdet(self):
+        return 2.0 * float(np.sum(np.log(self.diagL())))
+
+    def _cols(self, B):
+        B = np.asarray(B, dtype=np.float64)
+        one = B.ndim == 1
+        X = np.ascontiguousarray(B.reshape(self.n, -1).T).copy()  # rows = right-hand sides
+        return X, one
+
+    def solve_PtL(self, B):
+        """L^{-1} P b  (``F.PtL \\ b``)."""
+        X, one = self._cols(B)
+        X = np.ascontiguousarray(X[:, self.perm])
+        _load().orc_lsolve(self.n, self.Lp, self.Li, self.Lx, X, X.shape[0])
+        return X[0] if one else X.T.copy()
+
+    def solve_UP(self, Z):
+        """P' L^{-T} z  (``F.UP \\ z``) — a N(0, A^{-1}) sample for z ~ N(0, I)."""
+        X, one = self._cols(Z)
+        _load().orc_ltsolve(self.n, self.Lp, self.Li, self.Lx, X, X.shape[0])
+        out = np.empty_like(X)
+        out[:, self.perm] = X
+        return out[0] if one else out.T.copy()
+
+    def solve(self, B):
+        """A^{-1} b  (``F \\ b``)."""
+        X, one = self._cols(B)
+        X = np.ascontiguousarray(X[:, self.perm])
+        lib = _load()
+        lib.orc_lsolve(self.n, self.Lp, self.Li, self.Lx, X, X.shape[0])
+        lib.orc_ltsolve(self.n, self.Lp, self.Li, self.Lx, X, X.shape[0])
+        out = np.empty_like(X)
+        out[:, self.perm] = X
+        return out[0] if one else out.T.copy()
+
+    def selinv_diag(self):
+        """diag(A^{-1}) in the original ordering by the Takahashi recurrences on L's pattern."""
+        Zx = np.zeros_like(self.Lx)
+        rc = _load().orc_selinv(self.n, self.Lp, self.Li, self.Lx, Zx)
+        if rc != 0:
+            raise RuntimeError("orc_selinv failed")
+        d = np.empty(self.n)
+        d[self.perm] = Zx[self.Lp[:-1]]
+        return d
+
+    def selinv(self):
+        """Selected inverse on the pattern of L (permuted ordering), as a CSC lower-triangular matrix."""
+        Zx = np.zeros_like(self.Lx)
+        rc = _load().orc_selinv(self.n, self.Lp, self.Li, self.Lx, Zx)
+        if rc != 0:
+            raise RuntimeError("orc_selinv failed")
+        return sp.csc_matrix((Zx, self.Li, self.Lp), shape=(self.n, self.n))
+
+
+def symbolic(A, perm):
+    """(parent, colcount) of P A P' for a given perm (0-based, new->old); root parent = -1."""
+    lib = _load()
+    A = _csc(A)
+    n = A.shape[0]
+    parent = np.empty(n, np.int64)
+    colcount = np.empty(n, np.int64)
+    rc = lib.orc_symbolic(n, A.indptr.astype(np.int64), A.indices.astype(np.int64),
+                          np.ascontiguousarray(perm, dtype=np.int64), parent, colcount)
+    if rc != 0:
+        raise MemoryError
+    return parent, colcount
+
+
+# ----------------------------------------------------------------------------------------------- Tier A --
+class DenseCholesky:
+    """LAPACK restatement of the same factor views for small n."""
+
+    def __init__(self, A, perm):
+        A = np.asarray(A.todense() if sp.issparse(A) else A, dtype=np.float64)
+        self.perm = np.asarray(perm, dtype=np.int64)
+        self.n = A.shape[0]
+        self.Lmat = np.linalg.cholesky(A[np.ix_(self.perm, self.perm)])
+
+    def solve_PtL(self, B):
+        B = np.asarray(B, dtype=np.float64)
+        return sla.solve_triangular(self.Lmat, B[self.perm], lower=True)
+
+    def solve_UP(self, Z):
+        X = sla.solve_triangular(self.Lmat, np.asarray(Z, dtype=np.float64), lower=True, trans="T")
+        out = np.empty_like(X)
+        out[self.perm] = X
+        return out
+
+    def solve(self, B):
+        B = np.asarray(B, dtype=np.float64)
+        Y = sla.solve_triangular(self.Lmat, B[self.perm], lower=True)
+        X = sla.solve_triangular(self.Lmat, Y, lower=True, trans="T")
+        out = np.empty_like(X)
+        out[self.perm] = X
+        return out
+
+    def logdet(self):
+        return 2.0 * float(np.sum(np.log(np.diag(self.Lmat))))
+
+    def diagL(self):
+        return np.diag(self.Lmat).copy()
+
+
+def dense_inverse_diag(A):
+    A = np.asarray(A.todense() if sp.issparse(A) else A, dtype=np.float64)
+    return np.diag(np.linalg.inv(A)).copy()
+
+
+# ------------------------------------------------------------------------------------ GMRF-level helpers --
+def posterior_precision(Q, A, qeps):
+    """Q + A' diag(qeps) A — the assembly inside condition_on_observations
+    (scripts/darcy/solve_darcy_gmrf-fem.jl:165-167) / ``Q + noise*J'*J`` (scripts/solve_burger.jl:145)."""
+    A = sp.csc_matrix(A)
+    W = sp.diags(np.broadcast_to(np.asarray(qeps, dtype=np.float64), (A.shape[0],)))
+    return _csc(sp.csc_matrix(Q) + A.T @ W @ A)
+
+
+def posterior_mean(chol, Q, A, qeps, y, mu):
+    """mu + Qpost^{-1} A' Q_eps (y - A mu): standard Gaussian conditioning (GMRF.jl ``mean`` of a
+    conditioned GMRF; formula not in the reference tree — 'vs. restated oracle')."""
+    A = sp.csc_matrix(A)
+    w = np.broadcast_to(np.asarray(qeps, dtype=np.float64), (A.shape[0],))
+    return mu + chol.solve(A.T @ (w * (y - A @ mu)))
+
+
+def rbmc_variance(chol, Q, Z):
+    """Rao-Blackwellised Monte-Carlo marginal variances, RBMCStrategy(N)
+    (scripts/darcy/solve_darcy_gmrf-fem.jl:100,174,192); estimator of Siden et al. (2018):
+    var_i = 1/Q_ii + mean_k (sum_{j != i} Q_ij x_j^(k))^2 / Q_ii^2 with x^(k) = F.UP \\ z^(k)."""
+    Q = sp.csr_matrix(Q)
+    X = chol.solve_UP(Z)
+    d = Q.diagonal()
+    T = Q @ X - d[:, None] * X
+    return 1.0 / d + np.mean(T * T, axis=1) / d ** 2
+
+
+def gauss_newton_step(Q, J, noise, x, Qx_prior, obs_diff, perm, chol_cls=SparseCholesky):
+    """One step of scripts/solve_burger.jl:143-149:
+    A = Q + noise J'J;  rhs = Q x_prior + noise J'(J x + obs_diff);  x+ = A \\ rhs (fixed perm)."""
+    J = sp.csc_matrix(J)
+    A = _csc(sp.csc_matrix(Q) + noise * (J.T @ J))
+    rhs = Qx_prior + noise * (J.T @ (J @ x + obs_diff))
+    return chol_cls(A, perm).solve(rhs)
+
+
+def metrics(pred, truth):
+    """src/metrics.jl:3-13."""
+    pred = np.asarray(pred)
+    truth = np.asarray(truth)
+    rmse = float(np.sqrt(np.mean((pred - truth) ** 2)))
+    max_err = float(np.max(np.abs(pred - truth)))
+    rel_err = float(np.linalg.norm(pred - truth) / np.linalg.norm(truth))
+    return rmse, max_err, rel_err
+
+
+# ------------------------------------------------------------------------------------ block tridiagonal --
+class TridiagonalCholeskyFactor:
+    """src/tridiagonal_cholesky.jl:5-9 — N (total rows), chos (dense lower factors), Cs (sub-diagonal blocks;
+    Cs[k] belongs to block row k+1)."""
+
+    def __init__(self, N, chos, Cs):
+        self.N = N
+        self.chos = chos
+        self.Cs = Cs
+
+
+def tridiagonal_cholesky(A, n_blocks):
+    """src/tridiagonal_cholesky.jl:65-82, line by line (dense LAPACK blocks)."""
+    A = sp.csc_matrix(A)
+    b = A.shape[0] // n_blocks                                   # :66 (remainder rows ignored)
+    chos = [np.linalg.cholesky(A[:b, :b].toarray())]              # :67
+    Cs = []
+    for i in range(1, n_blocks):                                  # :70
+        r0, r1 = i * b, (i + 1) * b
+        B = A[r0:r1, (i - 1) * b:i * b].toarray()                 # :73
+        C = sla.solve_triangular(chos[-1], B.T, lower=True).T     # :74  C = B L^{-T}
+        Cs.append(C)
+        D = A[r0:r1, r0:r1].toarray()                             # :76
+        chos.append(np.linalg.cholesky(D - C @ C.T))              # :77
+    return TridiagonalCholeskyFactor(A.shape[0], chos, Cs)
+
+
+def btd_forward_solve(F, b):
+    """Intended semantics of src/tridiagonal_cholesky.jl:43-52: x_1 = L_1^{-1} b_1; x_i = L_i^{-1}(b_i - C_i x_{i-1})."""
+    nb = len(F.chos)
+    bs = F.chos[0].shape[0]
+    b = np.asarray(b, dtype=np.float64)
+    x = b[: nb * bs].copy()
+    for i in range(nb):
+        rhs = x[i * bs:(i + 1) * bs]
+        if i > 0:
+            rhs = rhs - F.Cs[i - 1] @ x[(i - 1) * bs:i * bs]
+        x[i * bs:(i + 1) * bs] = sla.solve_triangular(F.chos[i], rhs, lower=True)
+    return x
+
+
+def btd_backward_solve(F, b):
+    """Intended semantics of :24-33: x_N = L_N^{-T} b_N; x_i = L_i^{-T}(b_i - C_{i+1}' x_{i+1})."""
+    nb = len(F.chos)
+    bs = F.chos[0].shape[0]
+    b = np.asarray(b, dtype=np.float64)
+    x = b[: nb * bs].copy()
+    for i in range(nb - 1, -1, -1):
+        rhs = x[i * bs:(i + 1) * bs]
+        if i < nb - 1:
+            rhs = rhs - F.Cs[i].T @ x[(i + 1) * bs:(i + 2) * bs]
+        x[i * bs:(i + 1) * bs] = sla.solve_triangular(F.chos[i], rhs, lower=True, trans="T")
+    return x
+
+
+def btd_ldiv(F, b):
+    """Intended semantics of :54-63: A^{-1} b = backward(forward(b))."""
+    return btd_backward_solve(F, btd_forward_solve(F, b))
+
+
+def btd_logdet(F):
+    return 2.0 * float(sum(np.sum(np.log(np.diag(L))) for L in F.chos))
+
+
+def btd_selinv_diag(F):
+    """diag(A^{-1}) by the block Takahashi recursion S_N = L_N^{-T}L_N^{-1},
+    S_i = L_i^{-T}(I + C_{i+1}' S_{i+1} C_{i+1}) L_i^{-1}."""
+    nb = len(F.chos)
+    bs = F.chos[0].shape[0]
+    out = np.empty(nb * bs)
+    S = None
+    for i in range(nb - 1, -1, -1):
+        H = np.eye(bs)
+        if i < nb - 1:
+            C = F.Cs[i]
+            H = H + C.T @ S @ C
+        Li = sla.solve_triangular(F.chos[i], np.eye(bs), lower=True)
+        S = Li.T @ H @ Li
+        out[i * bs:(i + 1) * bs] = np.diag(S)
+    return out

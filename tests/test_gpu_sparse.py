@@ -1,0 +1,249 @@
+"""Parity of the CUDA sparse path (through the C ABI) against the CPU oracle on identical seeded inputs.
+Tolerances are the north star's: means/samples 1e-10 relative, marginal variances 1e-8 relative."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+TOL_SOLVE = 1e-10
+TOL_VAR = 1e-8
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def problems(W):
+    out = {}
+    for nx in (7, 24, 61, 130):
+        out[nx] = W.matern_posterior(nx, obs_frac=0.2, q_eps=1e2, corr_range=0.15, seed=nx)
+    return out
+
+
+@pytest.mark.parametrize("nx", [7, 24, 61, 130])
+@pytest.mark.parametrize("mode", ["nd", "geo", "given"])
+def test_factor_solve_sample(pkg, orc, ctx, problems, nx, mode):
+    prob = problems[nx]
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    rng = np.random.default_rng(nx)
+    if mode == "nd":
+        sym = pkg.Symbolic(Q, ctx=ctx)
+    elif mode == "geo":
+        sym = pkg.Symbolic(Q, ctx=ctx, coords=prob["nodes"])
+    else:
+        # "perm = p reused" path of the reference: ordering from a first analysis, then ORDER_GIVEN
+        p0 = pkg.Symbolic(Q, host_only=True).p
+        sym = pkg.Symbolic(Q, perm=p0, ctx=ctx)
+        assert np.array_equal(sym.p, p0)
+    fac = pkg.CholeskyFactor(sym).factorize(Q.data)
+    assert fac.issuccess()
+    ref = orc.SparseCholesky(Q, sym.p)
+    # pattern-level parity is bit exact
+    assert np.array_equal(sym.parent, ref.parent) and np.array_equal(sym.colcount, ref.colcount)
+    assert sym.info.nnz_L == ref.nnz
+    B = rng.standard_normal((n, 5))
+    assert rel(fac.solve(B), ref.solve(B)) < TOL_SOLVE            # F \ b (posterior mean)
+    assert rel(fac.solve(B[:, 0]), ref.solve(B[:, 0])) < TOL_SOLVE
+    assert rel(fac.PtL_solve(B), ref.solve_PtL(B)) < TOL_SOLVE    # F.PtL \ b
+    assert rel(fac.UP_solve(B), ref.solve_UP(B)) < TOL_SOLVE      # F.UP \ z (samples under the same z)
+    mu = rng.standard_normal(n)
+    assert rel(fac.sample(B, mean=mu), ref.solve_UP(B) + mu[:, None]) < TOL_SOLVE
+    np.testing.assert_allclose(fac.diagL(), ref.diagL(), rtol=1e-11)
+    assert abs(fac.logdet() - ref.logdet()) < 1e-10 * abs(ref.logdet())
+    # residual check, independent of the oracle
+    x = fac.solve(prob["rhs"])
+    assert np.linalg.norm(Q @ x - prob["rhs"]) < 1e-11 * np.linalg.norm(prob["rhs"]) * 1e2
+
+
+@pytest.mark.parametrize("nx", [7, 24, 61])
+def test_factor_values(pkg, orc, ctx, problems, nx):
+    Q = problems[nx]["Qpost"]
+    sym = pkg.Symbolic(Q, ctx=ctx)
+    fac = pkg.CholeskyFactor(sym).factorize(Q.data)
+    L = fac.L
+    Lref = orc.SparseCholesky(Q, sym.p).L()
+    d = (L - Lref)
+    assert abs(d).max() < 1e-11 * abs(Lref).max()
+    # same structural pattern up to exact zeros created by relaxed supernodes (dropped by get_L)
+    assert (abs(Lref) > 0).nnz >= L.nnz * 0.999
+
+
+@pytest.mark.parametrize("nx", [7, 24, 61, 130])
+def test_selected_inversion(pkg, orc, ctx, problems, nx):
+    Q = problems[nx]["Qpost"]
+    sym = pkg.Symbolic(Q, ctx=ctx)
+    fac = pkg.CholeskyFactor(sym).factorize(Q.data)
+    v = fac.var_selinv()
+    ref = orc.SparseCholesky(Q, sym.p)
+    vref = ref.selinv_diag()
+    assert np.max(np.abs(v - vref) / np.abs(vref)) < TOL_VAR
+    if nx <= 24:
+        np.testing.assert_allclose(v, orc.dense_inverse_diag(Q), rtol=TOL_VAR)
+    # off-diagonal selected entries on the pattern of Q
+    C = sp.coo_matrix(sp.tril(Q))
+    pick = np.random.default_rng(0).choice(C.nnz, size=min(200, C.nnz), replace=False)
+    vals = fac.selinv_entries(C.row[pick], C.col[pick])
+    Z = ref.selinv()  # permuted ordering, lower
+    ip = np.empty(Q.shape[0], np.int64)
+    ip[sym.p] = np.arange(Q.shape[0])
+    a, b = ip[C.row[pick]], ip[C.col[pick]]
+    want = np.asarray(Z[np.maximum(a, b), np.minimum(a, b)]).ravel()
+    np.testing.assert_allclose(vals, want, rtol=1e-8, atol=1e-14)
+
+
+def test_refactorize_same_pattern(pkg, orc, ctx, problems):
+    """Gauss-Newton pattern reuse: new values, same symbolic handle and factor storage."""
+    prob = problems[24]
+    Q = prob["Qpost"]
+    sym = pkg.Symbolic(Q, ctx=ctx)
+    fac = pkg.CholeskyFactor(sym)
+    b = np.random.default_rng(1).standard_normal(Q.shape[0])
+    for scale in (1.0, 3.5, 0.25):
+        Q2 = Q.copy()
+        Q2.data = Q.data * scale
+        Q2 = (Q2 + sp.identity(Q.shape[0]) * 0).tocsc()
+        fac.factorize(Q2.data)
+        ref = orc.SparseCholesky(Q2, sym.p)
+        assert rel(fac.solve(b), ref.solve(b)) < TOL_SOLVE
+        assert rel(fac.var_selinv(), ref.selinv_diag()) < TOL_VAR
+
+
+def test_not_positive_definite(pkg, ctx, problems):
+    Q = problems[24]["Qpost"].copy()
+    sym = pkg.Symbolic(Q, ctx=ctx)
+    fac = pkg.CholeskyFactor(sym)
+    bad = Q.data.copy()
+    bad[Q.indptr[100]:Q.indptr[101]][Q.indices[Q.indptr[100]:Q.indptr[101]] == 100] = -1.0
+    with pytest.raises(pkg.NotPositiveDefinite):
+        fac.factorize(bad)
+    fac.factorize(bad, check=False)  # Julia check=false: no throw, queryable flag
+    assert not fac.issuccess() and fac.info.status == 2 and fac.info.fail_column >= 0
+    with pytest.raises(pkg.GmrfbError):
+        fac.solve(np.ones(Q.shape[0]))
+    fac.factorize(Q.data)  # recovers
+    assert fac.issuccess()
+
+
+def test_edge_matrices(pkg, orc, ctx):
+    for A in (sp.identity(1, format="csc") * 4.0,
+              sp.diags(np.arange(1.0, 40.0)).tocsc(),
+              sp.diags([-np.ones(299), 2.5 * np.ones(300), -np.ones(299)], [-1, 0, 1], format="csc")):
+        sym = pkg.Symbolic(A, ctx=ctx)
+        fac = pkg.CholeskyFactor(sym).factorize(A.data)
+        b = np.random.default_rng(0).standard_normal(A.shape[0])
+        ref = orc.SparseCholesky(A, sym.p)
+        assert rel(fac.solve(b), ref.solve(b)) < TOL_SOLVE
+        np.testing.assert_allclose(fac.var_selinv(), ref.selinv_diag(), rtol=TOL_VAR)
+    # dense SPD matrix as a sparse one: a single big supernode (front order 300)
+    R = np.random.default_rng(1).standard_normal((300, 300))
+    A = sp.csc_matrix(R @ R.T + 300 * np.eye(300))
+    sym = pkg.Symbolic(A, ctx=ctx)
+    fac = pkg.CholeskyFactor(sym).factorize(A.data)
+    b = np.ones(300)
+    assert rel(fac.solve(b), np.linalg.solve(A.toarray(), b)) < TOL_SOLVE
+    np.testing.assert_allclose(fac.var_selinv(), np.diag(np.linalg.inv(A.toarray())), rtol=TOL_VAR)
+
+
+def test_rbmc_matches_oracle_same_z(pkg, orc, ctx, problems):
+    prob = problems[24]
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    sym = pkg.Symbolic(Q, ctx=ctx)
+    fac = pkg.CholeskyFactor(sym).factorize(Q.data)
+    Z = np.random.default_rng(5).standard_normal((n, 50))  # RBMCStrategy(50)
+    v = fac.var_rbmc(pkg.SparseMatrix(Q, ctx=ctx), Z)
+    vref = orc.rbmc_variance(orc.SparseCholesky(Q, sym.p), Q, Z)
+    np.testing.assert_allclose(v, vref, rtol=1e-9)
+
+
+def test_spmv_sqmahal_postprec(pkg, orc, ctx, problems):
+    prob = problems[24]
+    Q, A = prob["Q"], prob["A"]
+    n = Q.shape[0]
+    rng = np.random.default_rng(2)
+    Qd, Ad = pkg.SparseMatrix(Q, ctx=ctx), pkg.SparseMatrix(A, ctx=ctx)
+    x = rng.standard_normal(n)
+    r = rng.standard_normal(A.shape[0])
+    np.testing.assert_allclose(Qd.matvec(x), Q @ x, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(Ad.matvec(x), A @ x, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(Ad.matvec(r, trans=True), A.T @ r, rtol=1e-12, atol=1e-12)
+    y0 = rng.standard_normal(n)
+    np.testing.assert_allclose(Qd.matvec(x, alpha=2.0, beta=-0.5, y=y0), 2 * (Q @ x) - 0.5 * y0, rtol=1e-12, atol=1e-12)
+    mu = rng.standard_normal(n)
+    assert abs(Qd.sqmahal(x, mu) - (x - mu) @ (Q @ (x - mu))) < 1e-11 * abs((x - mu) @ (Q @ (x - mu)))
+    plan = pkg.PosteriorPrecision(Qd, Ad)
+    for qe in (1e2, 7.0):
+        got = plan.compute(qe).to_scipy()
+        want = orc.posterior_precision(Q, A, qe)
+        assert abs(got - want).max() < 1e-12 * abs(want).max()
+    w = rng.random(A.shape[0]) + 0.5
+    got = plan.compute(w).to_scipy()
+    assert abs(got - orc.posterior_precision(Q, A, w)).max() < 1e-12 * abs(got).max()
+    # a general (non-selection) observation operator: the Darcy case A = stiffness-like matrix
+    G = (Q.copy())
+    Gd = pkg.SparseMatrix(G, ctx=ctx)
+    plan2 = pkg.PosteriorPrecision(Qd, Gd)
+    got = plan2.compute(3.0).to_scipy()
+    want = orc.posterior_precision(Q, G, 3.0)
+    assert abs(got - want).max() < 1e-11 * abs(want).max()
+
+
+def test_gmrf_interface(pkg, orc, ctx, problems):
+    """condition_on_observations / mean / std / rand / sqmahal with the reference's blueprint spelling
+    (scripts/darcy/solve_darcy_gmrf-fem.jl:100,165-192)."""
+    prob = problems[24]
+    Q, A, y, qe = prob["Q"], prob["A"], prob["y"], prob["q_eps"]
+    n = Q.shape[0]
+    x = pkg.GMRF(np.zeros(n), Q, pkg.CholeskySolverBlueprint(ctx=ctx))
+    xc = pkg.condition_on_observations(x, A, qe, y)
+    p = xc.solver_ref[()].precision_chol.p
+    assert sorted(p.tolist()) == list(range(n))
+    # second conditioning with the permutation reused (cbp2 = perm p) and RBMC variances
+    bp2 = pkg.CholeskySolverBlueprint(var_strategy=pkg.RBMCStrategy(50, rng=np.random.default_rng(7)), perm=p, ctx=ctx)
+    xc2 = pkg.condition_on_observations(x, A, qe, y, solver_blueprint=bp2)
+    assert np.array_equal(xc2.solver_ref[()].precision_chol.p, p)
+    Qp = orc.posterior_precision(Q, A, qe)
+    ref = orc.SparseCholesky(Qp, p)
+    mref = orc.posterior_mean(ref, Q, A, qe, y, np.zeros(n))
+    assert rel(pkg.mean(xc), mref) < TOL_SOLVE and rel(pkg.mean(xc2), mref) < TOL_SOLVE
+    assert rel(pkg.std(xc), np.sqrt(ref.selinv_diag())) < TOL_VAR
+    Z = np.random.default_rng(7).standard_normal((n, 50))
+    assert rel(pkg.std(xc2), np.sqrt(orc.rbmc_variance(ref, Qp, Z))) < 1e-9
+    z = np.random.default_rng(11).standard_normal(n)
+    s = pkg.rand(np.random.default_rng(11), xc)
+    assert rel(s, mref + ref.solve_UP(z)) < TOL_SOLVE
+    v = np.random.default_rng(3).standard_normal(n)
+    want = (v - mref) @ (Qp @ (v - mref))
+    assert abs(pkg.sqmahal(xc, v) - want) < 1e-9 * abs(want)
+    assert xc.solver_ref[()].precision_chol.nnz >= ref.nnz
+
+
+def test_gauss_newton(pkg, orc, ctx, W):
+    """GaussNewtonOptimizer/optimize against the restated loop of scripts/solve_burger.jl:143-180."""
+    P = W.burgers_like_problem(48)
+    n = P["n"]
+    noise = 1e4
+    p0 = pkg.Symbolic(orc.posterior_precision(P["Q"], P["f_and_J"](P["mu"])[1], noise), host_only=True).p
+    gno = pkg.GaussNewtonOptimizer(P["mu"], P["Q"], P["f_and_J"], noise, P["y"], P["mu"],
+                                   solver_bp=pkg.GNCholeskySolverBlueprint(p0, ctx=ctx))
+    xg = pkg.optimize(gno)
+    # oracle loop
+    x = P["mu"].copy()
+    Qx = P["Q"] @ P["mu"]
+
+    def obj(x):
+        r = P["y"] - P["f"](x)
+        d = P["mu"] - x
+        return d @ (P["Q"] @ d) + noise * (r @ r)
+
+    last, cur, steps = np.inf, obj(x), 0
+    while abs(last - cur) / abs(cur) > 1e-4 and steps < 20:
+        fx, J = P["f_and_J"](x)
+        x = orc.gauss_newton_step(P["Q"], J, noise, x, Qx, P["y"] - fx, p0)
+        last, cur = cur, obj(x)
+        steps += 1
+    assert steps == gno.n_steps and steps >= 2
+    assert rel(xg, x) < 1e-9

@@ -1,0 +1,106 @@
+"""The oracle pinned against dense LAPACK (the reference ships no golden vectors: parity unpinned)."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("nx,seed", [(6, 0), (17, 1), (30, 2)])
+def test_sparse_oracle_matches_lapack(orc, W, nx, seed):
+    prob = W.matern_posterior(nx, obs_frac=0.3, corr_range=0.3, seed=seed)
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(n)
+    ch = orc.SparseCholesky(Q, perm)
+    dch = orc.DenseCholesky(Q, perm)
+    B = rng.standard_normal((n, 3))
+    for name in ("solve", "solve_UP", "solve_PtL"):
+        a, b = getattr(ch, name)(B), getattr(dch, name)(B)
+        assert np.linalg.norm(a - b) <= 1e-11 * np.linalg.norm(b), name
+    assert abs(ch.logdet() - dch.logdet()) <= 1e-9 * abs(dch.logdet())
+    np.testing.assert_allclose(ch.diagL(), dch.diagL(), rtol=1e-11)
+    np.testing.assert_allclose(ch.selinv_diag(), orc.dense_inverse_diag(Q), rtol=1e-9)
+    # L pattern/values against dense Cholesky of the permuted matrix
+    Ld = np.linalg.cholesky(Q.toarray()[np.ix_(perm, perm)])
+    np.testing.assert_allclose(ch.L().toarray(), Ld, atol=1e-11 * np.abs(Ld).max())
+    # column counts count exactly the structural nonzeros
+    assert ch.nnz == int(ch.colcount.sum())
+
+
+def test_sample_covariance_convention(orc, W):
+    """x = F.UP \\ z has covariance Q^{-1} (src/tridiagonal_cholesky.jl:20-22): check P'L^{-T} algebraically."""
+    prob = W.matern_posterior(8, obs_frac=0.5, corr_range=0.4)
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    perm = np.random.default_rng(3).permutation(n)
+    ch = orc.SparseCholesky(Q, perm)
+    M = ch.solve_UP(np.eye(n))  # M = P' L^{-T}
+    np.testing.assert_allclose(M @ M.T, np.linalg.inv(Q.toarray()), rtol=1e-9, atol=1e-12)
+
+
+def test_not_spd_raises(orc):
+    import scipy.sparse as sp
+
+    A = sp.csc_matrix(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    with pytest.raises(np.linalg.LinAlgError):
+        orc.SparseCholesky(A, np.arange(2))
+
+
+@pytest.mark.parametrize("b,N", [(1, 1), (5, 4), (16, 7)])
+def test_btd_oracle_matches_lapack(orc, W, b, N):
+    D, Bs = W.random_btd(b, N, seed=b + N)
+    A = W.btd_to_sparse(D, Bs)
+    Ad = A.toarray()
+    F = orc.tridiagonal_cholesky(A, N)
+    assert F.N == b * N and len(F.chos) == N and len(F.Cs) == N - 1
+    # the block factor is the Cholesky factor of the assembled matrix
+    Lfull = np.linalg.cholesky(Ad)
+    for i in range(N):
+        np.testing.assert_allclose(F.chos[i], Lfull[i * b:(i + 1) * b, i * b:(i + 1) * b], atol=1e-12)
+        if i > 0:
+            np.testing.assert_allclose(F.Cs[i - 1], Lfull[i * b:(i + 1) * b, (i - 1) * b:i * b], atol=1e-12)
+    rhs = np.random.default_rng(0).standard_normal(b * N)
+    np.testing.assert_allclose(orc.btd_ldiv(F, rhs), np.linalg.solve(Ad, rhs), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(orc.btd_forward_solve(F, rhs), np.linalg.solve(Lfull, rhs), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(orc.btd_backward_solve(F, rhs), np.linalg.solve(Lfull.T, rhs), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(orc.btd_selinv_diag(F), np.diag(np.linalg.inv(Ad)), rtol=1e-9)
+    assert abs(orc.btd_logdet(F) - np.linalg.slogdet(Ad)[1]) < 1e-9 * max(1.0, abs(orc.btd_logdet(F)))
+
+
+def test_btd_remainder_rows_ignored(orc, W):
+    """b = n div N_blocks; trailing rows are dropped (src/tridiagonal_cholesky.jl:66)."""
+    import scipy.sparse as sp
+
+    D, Bs = W.random_btd(4, 3, seed=5)
+    A = W.btd_to_sparse(D, Bs)
+    Apad = sp.block_diag([A, sp.identity(2) * 7.0]).tocsc()  # 14 rows, 3 blocks -> b = 4, 2 rows ignored
+    F = orc.tridiagonal_cholesky(Apad, 3)
+    F0 = orc.tridiagonal_cholesky(A, 3)
+    for a, b in zip(F.chos, F0.chos):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_rbmc_converges_to_exact(orc, W):
+    prob = W.matern_posterior(10, obs_frac=0.5, corr_range=0.3)
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    ch = orc.SparseCholesky(Q, np.arange(n))
+    Z = np.random.default_rng(0).standard_normal((n, 4000))
+    v = orc.rbmc_variance(ch, Q, Z)
+    np.testing.assert_allclose(v, orc.dense_inverse_diag(Q), rtol=0.1)
+
+
+def test_posterior_and_gauss_newton_restatement(orc, W):
+    prob = W.matern_posterior(9, obs_frac=0.4, corr_range=0.3)
+    Qp = orc.posterior_precision(prob["Q"], prob["A"], prob["q_eps"])
+    assert abs(Qp - prob["Qpost"]).max() < 1e-9 * abs(Qp).max()
+    n = Qp.shape[0]
+    ch = orc.SparseCholesky(Qp, np.arange(n))
+    mu = orc.posterior_mean(ch, prob["Q"], prob["A"], prob["q_eps"], prob["y"], np.zeros(n))
+    ref = np.linalg.solve(Qp.toarray(), prob["rhs"])
+    np.testing.assert_allclose(mu, ref, rtol=1e-9, atol=1e-12)
+    # linear f => one GN step lands on the posterior mean (scripts/solve_burger.jl:143-149)
+    A = prob["A"]
+    x0 = np.zeros(n)
+    x1 = orc.gauss_newton_step(prob["Q"], A, prob["q_eps"], x0, prob["Q"] @ np.zeros(n), prob["y"] - A @ x0,
+                               np.arange(n))
+    np.testing.assert_allclose(x1, ref, rtol=1e-9, atol=1e-12)

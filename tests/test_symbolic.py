@@ -1,0 +1,84 @@
+"""Host-side symbolic analysis of the library against the oracle: with the same permutation the elimination
+tree, column counts and nnz(L) must be bit-exact (SURVEY.md §7 'hard parts')."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+
+def _check(pkg, orc, A, perm=None, **kw):
+    sym = pkg.Symbolic(A, perm=perm, host_only=True, **kw)
+    n = A.shape[0]
+    p = sym.p
+    assert sorted(p.tolist()) == list(range(n))
+    if perm is not None:
+        assert np.array_equal(p, perm)  # Julia: F.p == perm
+    parent, cc = orc.symbolic(A, p)
+    assert np.array_equal(sym.parent, parent)
+    assert np.array_equal(sym.colcount, cc)
+    info = sym.info
+    assert info.nnz_L == int(cc.sum())
+    assert info.flops == float(np.sum(cc.astype(float) ** 2))
+    assert info.nnz_L_stored >= info.nnz_L
+    # supernodes partition the columns; row structures contain exactly the columns first
+    sptr = sym.super_ptr
+    assert sptr[0] == 0 and sptr[-1] == n and np.all(np.diff(sptr) > 0)
+    ipost = sym.ipost
+    assert sorted(ipost.tolist()) == list(range(n))
+    # ipost is an etree postorder: every parent comes after its children
+    for k in range(n):
+        if parent[k] >= 0:
+            assert ipost[parent[k]] > ipost[k]
+    return sym
+
+
+@pytest.mark.parametrize("nx", [2, 5, 13, 40])
+def test_nd_ordering_mesh(pkg, orc, W, nx):
+    prob = W.matern_posterior(nx, obs_frac=0.2, corr_range=0.3)
+    _check(pkg, orc, prob["Qpost"])
+    _check(pkg, orc, prob["Qpost"], coords=prob["nodes"])
+
+
+def test_given_and_natural_perm(pkg, orc, W):
+    prob = W.matern_posterior(12, obs_frac=0.2, corr_range=0.3)
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    _check(pkg, orc, Q, perm=np.random.default_rng(0).permutation(n))
+    _check(pkg, orc, Q, perm=np.arange(n)[::-1].copy())
+    _check(pkg, orc, Q, ordering="natural")
+
+
+def test_edge_patterns(pkg, orc):
+    _check(pkg, orc, sp.identity(1, format="csc"))
+    _check(pkg, orc, sp.identity(50, format="csc"))  # fully disconnected
+    # two disconnected cliques + isolated vertices
+    blocks = [sp.csc_matrix(np.ones((7, 7))), sp.identity(3), sp.csc_matrix(np.ones((20, 20)))]
+    _check(pkg, orc, sp.block_diag(blocks, format="csc"))
+    # arrow matrix (dense last row/col)
+    n = 30
+    A = sp.lil_matrix((n, n))
+    A.setdiag(1.0)
+    A[n - 1, :] = 1.0
+    A[:, n - 1] = 1.0
+    _check(pkg, orc, A.tocsc())
+    # 1-D chain and a random sparse symmetric pattern
+    chain = sp.diags([np.ones(99), np.ones(100), np.ones(99)], [-1, 0, 1], format="csc")
+    _check(pkg, orc, chain)
+    R = sp.random(200, 200, density=0.02, random_state=1, format="csc")
+    _check(pkg, orc, (R + R.T + sp.identity(200)).tocsc())
+
+
+def test_nd_fill_quality(pkg, W):
+    """Nested dissection must beat the natural (banded) ordering clearly on a 2-D mesh."""
+    prob = W.matern_posterior(60, obs_frac=0.1, corr_range=0.2)
+    nd = pkg.Symbolic(prob["Qpost"], host_only=True).info
+    geo = pkg.Symbolic(prob["Qpost"], host_only=True, coords=prob["nodes"]).info
+    nat = pkg.Symbolic(prob["Qpost"], host_only=True, ordering="natural").info
+    assert nd.flops < 0.5 * nat.flops and geo.flops < 0.5 * nat.flops
+
+
+def test_invalid_inputs(pkg):
+    A = sp.identity(4, format="csc")
+    with pytest.raises(pkg.GmrfbError):
+        pkg.Symbolic(A, perm=np.array([0, 1, 1, 3]), host_only=True)  # not a permutation
+    with pytest.raises(ValueError):
+        pkg.Symbolic(sp.csc_matrix(np.ones((3, 4))), host_only=True)
