@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native GMRF linear-algebra hot path.
+
+Metric (BASELINE.json): GMRF posterior (mean + marginal variance) solves/sec.
+One *step* = one posterior solve of BASELINE config 4 (synthetic 2-D Matern SPDE GMRF on a ~1M-node P1 mesh,
+10 % of nodes observed): numeric supernodal Cholesky of Q_post (symbolic analysis reused, as the reference does
+with `perm=p`) + posterior mean (forward + backward solve) + marginal variances by Takahashi selected inversion.
+
+    python bench.py --gpus N --steps K --warmup W          # product arm (CUDA, one process per GPU)
+    python bench.py --impl reference ...                    # CPU arm: the oracle port on the host cores
+
+`value`   : whole-job solves/s with the precision values and right-hand side resident in HBM (device entry points).
+`e2e`     : the same metric through the host C-ABI calls (pinned host buffers, H2D/D2H inside the timed region).
+`roofline`: the dominant kernel of the step, timed with CUDA events inside this run (profiled replay of the same
+            step), against the measured FP64 tensor peak (cuBLAS DGEMM, profiles/r01_fp64_probe.json) or the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json).
+N > 1     : independent posterior problems (the reference's dataset loop, scripts/darcy/solve_darcy_gmrf-fem.jl:210)
+            are sharded one per rank — no data-path collective; weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "GMRF posterior (mean+marginal var) solves/sec"
+UNIT = "solves/s"
+FP64_PEAK_TFLOPS_FALLBACK = 35.5  # cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_fp64_probe.json)
+
+
+def load_peaks():
+    hbm, fp64, src = 6650.0, FP64_PEAK_TFLOPS_FALLBACK, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm = float(json.load(f)["hbm_gbs"])
+            src = "measured"
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_fp64_probe.json")) as f:
+            fp64 = float(json.load(f)["dgemm_8192_tflops"])
+    except Exception:  # noqa: BLE001
+        pass
+    return hbm, fp64, src
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower() == "active":
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def build_problem(nx, seed):
+    pkg = entry.load_pkg()
+    prob = pkg.workloads.matern_posterior(nx, obs_frac=0.1, q_eps=1e2, corr_range=0.05, seed=seed)
+    return prob
+
+
+# --------------------------------------------------------------------------------------------- CPU arm ----
+def cpu_posterior_solve_time(nx_sample, seed=0):
+    """Time one posterior solve (numeric factor + mean + selected-inversion variances) of the oracle port on a
+    bounded sample mesh; symbolic analysis (ordering, etree, counts) is outside the timed region as on the GPU."""
+    pkg = entry.load_pkg()
+    orc = entry.load_oracle()
+    prob = build_problem(nx_sample, seed)
+    Qp = prob["Qpost"]
+    sym = pkg.Symbolic(Qp, coords=prob["nodes"], host_only=True)  # same ordering as the GPU arm (host-side, no GPU)
+    perm = sym.p
+    lib = orc._load()
+    n = Qp.shape[0]
+    Ap, Ai, Ax = Qp.indptr.astype(np.int64), Qp.indices.astype(np.int64), Qp.data.astype(np.float64)
+    parent = np.empty(n, np.int64)
+    cc = np.empty(n, np.int64)
+    lib.orc_symbolic(n, Ap, Ai, perm, parent, cc)
+    Lp = np.zeros(n + 1, np.int64)
+    np.cumsum(cc, out=Lp[1:])
+    Li = np.empty(int(Lp[-1]), np.int64)
+    Lx = np.empty(int(Lp[-1]), np.float64)
+    Zx = np.zeros_like(Lx)
+    t0 = time.perf_counter()
+    rc = lib.orc_cholesky(n, Ap, Ai, Ax, perm, parent, Lp, Li, Lx)
+    assert rc == 0
+    t1 = time.perf_counter()
+    x = np.ascontiguousarray(prob["rhs"][perm])[None, :].copy()
+    lib.orc_lsolve(n, Lp, Li, Lx, x, 1)
+    lib.orc_ltsolve(n, Lp, Li, Lx, x, 1)
+    t2 = time.perf_counter()
+    lib.orc_selinv(n, Lp, Li, Lx, Zx)
+    t3 = time.perf_counter()
+    flops = float(np.sum(cc.astype(np.float64) ** 2))
+    return dict(n=n, factor_s=t1 - t0, solve_s=t2 - t1, selinv_s=t3 - t2, total_s=t3 - t0, flops=flops,
+                nnzL=int(Lp[-1]))
+
+
+def cpu_baseline(nx_full, full_flops, full_nnzL, nx_sample=220):
+    """Scale the sample timing to the full mesh: factor and selected inversion by the flop ratio (sum cc^2), the
+    two triangular sweeps by the nnz(L) ratio."""
+    s = cpu_posterior_solve_time(nx_sample)
+    est = (s["factor_s"] + s["selinv_s"]) * (full_flops / s["flops"]) + s["solve_s"] * (full_nnzL / s["nnzL"])
+    return {
+        "value": 1.0 / est, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": (f"oracle/sparse_chol.c (scalar up-looking Cholesky + Takahashi) on a {nx_sample}x{nx_sample} mesh "
+                   f"(n={s['n']}): factor {s['factor_s']:.2f}s, solves {s['solve_s']:.3f}s, selinv {s['selinv_s']:.2f}s; "
+                   f"scaled to {nx_full}x{nx_full} by flops ratio {full_flops / s['flops']:.1f} and nnz(L) ratio "
+                   f"{full_nnzL / s['nnzL']:.1f}; restatement of CHOLMOD's simplicial algorithm, not CHOLMOD"),
+        "sample_seconds": s["total_s"], "estimated_full_seconds_per_solve": est,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = entry.load_pkg()
+    nx = args.nx
+    # symbolic quantities of the full problem (host-only analysis: integer work, no GPU needed)
+    prob = build_problem(nx, 0)
+    sym = pkg.Symbolic(prob["Qpost"], coords=prob["nodes"], host_only=True)
+    info = sym.info
+    full_flops, full_nnzL = info.flops, info.nnz_L
+    times = []
+    for it in range(args.warmup + args.steps):
+        s = cpu_posterior_solve_time(args.nx_sample, seed=it)
+        if it >= args.warmup:
+            times.append((s["factor_s"] + s["selinv_s"]) * (full_flops / s["flops"]) + s["solve_s"] * (full_nnzL / s["nnzL"]))
+    per = sum(times) / len(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": 1.0 / per, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config 4: 2-D Matern SPDE GMRF posterior, {nx}x{nx} P1 mesh (n={nx * nx}), "
+                               "numeric Cholesky + mean + selected-inversion variances",
+                   "n": nx * nx, "note": "CPU arm = oracle port (CHOLMOD/Julia are not installed); each step is a "
+                                         f"bounded {args.nx_sample}x{args.nx_sample} sample scaled by flop / nnz(L) ratios"},
+        "cpu_baseline": {"value": 1.0 / per, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{args.nx_sample}x{args.nx_sample} mesh per step, scaled to {nx}x{nx}"},
+        "e2e": {"value": 1.0 / per, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm ----
+def run_gpu_arm(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pkg = entry.load_pkg()
+    ctx = pkg.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    hbm_peak, fp64_peak, peak_src = load_peaks()
+
+    nx = args.nx
+    t_setup = time.perf_counter()
+    prob = build_problem(nx, rank)  # rank r solves problem r: independent problems, same pattern
+    Qp = prob["Qpost"]
+    n = Qp.shape[0]
+    sym = pkg.Symbolic(Qp, coords=prob["nodes"], ctx=ctx)
+    info = sym.info
+    fac = pkg.CholeskyFactor(sym)
+    t_setup = time.perf_counter() - t_setup
+
+    nz_host = torch.from_numpy(np.ascontiguousarray(Qp.data)).pin_memory()
+    rhs_host = torch.from_numpy(np.ascontiguousarray(prob["rhs"])).pin_memory()
+    d_nz = nz_host.to(dev)
+    d_rhs = rhs_host.to(dev)
+    d_x = torch.empty_like(d_rhs)
+    d_var = torch.empty_like(d_rhs)
+    torch.cuda.synchronize()
+
+    def step_device():
+        with torch.cuda.stream(ext):
+            d_x.copy_(d_rhs)
+        fac.factorize_dev(d_nz.data_ptr())
+        fac.solve_dev(d_x.data_ptr(), 1)
+        fac.var_selinv_dev(d_var.data_ptr())
+
+    x_host = np.empty(n)
+    var_host = np.empty(n)
+
+    def step_e2e():
+        fac.factorize(nz_host.numpy())
+        x_host[:] = rhs_host.numpy()
+        xs = fac.solve(x_host)
+        v = fac.var_selinv()
+        return xs, v
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e0.record()
+    for _ in range(args.steps):
+        step_device()
+    with torch.cuda.stream(ext):
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end through the host C-ABI calls (pinned host inputs, host outputs)
+    ke = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    with torch.cuda.stream(ext):
+        e0.record()
+    for _ in range(ke):
+        xs, v = step_e2e()
+    with torch.cuda.stream(ext):
+        e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / ke
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    # parity spot check of what was timed (size-independent property: residual of the mean, and var > 0)
+    mean = d_x.cpu().numpy()
+    resid = float(np.linalg.norm(Qp @ mean - prob["rhs"]) / np.linalg.norm(prob["rhs"]))
+    var = d_var.cpu().numpy()
+    ok = resid < 1e-9 and bool(np.all(var > 0)) and float(np.max(np.abs(xs - mean))) <= 1e-12 * float(np.max(np.abs(mean))) + 1e-300
+
+    # per-kernel profile of one more step (CUDA events around every launch on the library's stream)
+    roofline = None
+    prof_rows = []
+    if rank == 0:
+        ctx.profile_begin()
+        step_device()
+        prof = ctx.profile_end()
+        tot = sum(p["ms"] for p in prof)
+        for p in sorted(prof, key=lambda q: -q["ms"]):
+            row = dict(name=p["name"], launches=p["launches"], ms=round(p["ms"], 3), share=round(p["ms"] / tot, 4))
+            if p["flops"] > 0 and p["ms"] > 0:
+                row["tflops"] = round(p["flops"] / p["ms"] * 1e-9, 3)
+            if p["bytes"] > 0 and p["ms"] > 0:
+                row["gbs"] = round(p["bytes"] / p["ms"] * 1e-6, 1)
+            prof_rows.append(row)
+        top = max(prof, key=lambda q: q["ms"])
+        if top["flops"] > 0 and "gemm" in top["name"]:
+            ach = top["flops"] / top["ms"] * 1e-9
+            roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": fp64_peak,
+                        "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                        "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_probe.json); "
+                                       "FP64 tensor (DMMA) issue peak 37.1 TFLOP/s",
+                        "launches_per_step": top["launches"], "ms_per_step": top["ms"],
+                        "flops_per_step": top["flops"]}
+        else:
+            ach = top["bytes"] / top["ms"] * 1e-6 if top["ms"] > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                        "launches_per_step": top["launches"], "ms_per_step": top["ms"]}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(nx, info.flops, info.nnz_L, args.nx_sample)
+    per_step = ms / args.steps
+    line = {
+        "metric": METRIC, "value": world * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config 4: 2-D Matern SPDE GMRF posterior, {nx}x{nx} P1 mesh (n={n}), numeric "
+                               "supernodal Cholesky + mean + selected-inversion variances per step",
+                   "n": n, "nnz_Q": int(Qp.nnz), "nnz_L": int(info.nnz_L), "factor_flops": info.flops,
+                   "nsuper": int(info.nsuper), "levels": int(info.nlevels), "max_front": int(info.max_front),
+                   "front_arena_gb": info.front_bytes / 1e9, "ordering": "library nested dissection (geometric)",
+                   "problems_per_gpu": 1, "l2_policy": "working set (front arena) >> 126 MB L2; no flush needed",
+                   "setup_s_outside_timing": round(t_setup, 2)},
+        "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(nz_host.numel() * 8 + n * 8), "d2h_bytes_per_step": int(2 * n * 8)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernel_profile": prof_rows,
+        "parity_check": {"mean_residual": resid, "var_positive": bool(np.all(var > 0)), "ok": bool(ok)},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    if not ok:
+        sys.exit("bench: parity spot check failed")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=1001, help="mesh nodes per side (1001 -> 1,002,001 nodes)")
+    ap.add_argument("--nx-sample", dest="nx_sample", type=int, default=220, help="CPU sample mesh side")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,11 @@ class FacInfo(C.Structure):
     _fields_ = [("status", C.c_int32), ("fail_column", C.c_int64), ("logdet", C.c_double), ("nnz_L", C.c_int64)]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double), ("name", C.c_char * 32)]
+
+
 class BtdInfo(C.Structure):
     _fields_ = [("b", C.c_int64), ("nblocks", C.c_int64), ("status", C.c_int32), ("fail_block", C.c_int64),
                 ("flops", C.c_double)]
@@ -65,6 +70,8 @@ SIGNATURES = {
     "gmrfb_ctx_sync": (C.c_int32, [_P]),
     "gmrfb_ctx_stream": (C.c_uint64, [_P]),
     "gmrfb_ctx_launch_count": (C.c_int64, [_P]),
+    "gmrfb_ctx_profile_begin": (C.c_int32, [_P]),
+    "gmrfb_ctx_profile_end": (C.c_int32, [_P, C.POINTER(ProfileEntry), C.c_int32, C.POINTER(C.c_int32)]),
     "gmrfb_analyze": (C.c_int32, [_P, C.c_int64, _I64P, _I64P, _I64P, C.POINTER(AnalyzeOpts), C.POINTER(_P)]),
     "gmrfb_sym_destroy": (C.c_int32, [_P]),
     "gmrfb_sym_get_info": (C.c_int32, [_P, C.POINTER(SymInfo)]),

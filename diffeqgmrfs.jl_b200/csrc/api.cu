@@ -18,6 +18,7 @@ std::string& global_error() {
 
 gmrfb_status run_plan(gmrfb_ctx* ctx, const DevPlan& P, const Arenas& ar, const LaunchAux& aux) {
   for (const Launch& L : P.host.launches) {
+    ProfScope ps(ctx, L.kind, L.flops, L.bytes);
     cudaError_t e = run_launch(L, P.tasks.p, ar, aux, ctx->stream);
     if (e != cudaSuccess)
       return fail(ctx, GMRFB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
@@ -82,6 +83,76 @@ extern "C" gmrfb_status gmrfb_ctx_sync(gmrfb_ctx* ctx) {
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+extern "C" gmrfb_status gmrfb_ctx_profile_begin(gmrfb_ctx* ctx) {
+  if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "ctx is NULL");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  ctx->profiling = true;
+  return GMRFB_OK;
+}
+
+static const char* prof_name(int kind) {
+  switch (kind) {
+    case LK_GEMM_NT: return "k_gemm<NT> (DMMA)";
+    case LK_GEMM_NN: return "k_gemm<NN> (DMMA)";
+    case LK_GEMM_TN: return "k_gemm<TN> (DMMA)";
+    case LK_POTRF: return "k_potrf64";
+    case LK_TRSM_RLT: return "k_trsm<RLT>";
+    case LK_TRSM_RLN: return "k_trsm<RLN>";
+    case LK_EXTEND_ADD: return "k_extend_add";
+    case LK_GATHER_SYM: return "k_gather_sym";
+    case LK_SET_IDENTITY: return "k_tile_op<identity>";
+    case LK_TRANSPOSE: return "k_transpose";
+    case LK_SCALE: return "k_tile_op<scale>";
+    case LK_DIAG_OUT: return "k_diag_out";
+    case LK_SYMMETRIZE: return "k_tile_op<symmetrize>";
+    case PK_FWD_LEVEL: return "k_fwd_level";
+    case PK_BWD_LEVEL: return "k_bwd_level";
+    case PK_SCATTER: return "k_scatter_values";
+    case PK_MEMSET: return "memset(front arena)";
+    case PK_PERM: return "k_perm_gather/scatter";
+  }
+  return "other";
+}
+
+extern "C" gmrfb_status gmrfb_ctx_profile_end(gmrfb_ctx* ctx, gmrfb_profile_entry* entries, int32_t cap,
+                                              int32_t* count) {
+  if (!ctx || !count) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_ctx_profile_end: NULL argument");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->profiling = false;
+  gmrfb_profile_entry acc[PK_MAX];
+  memset(acc, 0, sizeof(acc));
+  for (auto& r : ctx->prof) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    int k = (r.kind >= 0 && r.kind < PK_MAX) ? r.kind : PK_MAX - 1;
+    acc[k].kind = k;
+    acc[k].launches++;
+    acc[k].ms += ms;
+    acc[k].flops += r.flops;
+    acc[k].bytes += r.bytes;
+  }
+  ctx->prof.clear();
+  int32_t n = 0;
+  for (int k = 0; k < PK_MAX; k++) {
+    if (acc[k].launches == 0) continue;
+    if (entries && n < cap) {
+      entries[n] = acc[k];
+      strncpy(entries[n].name, prof_name(k), sizeof(entries[n].name) - 1);
+    }
+    n++;
+  }
+  *count = n;
+  return GMRFB_OK;
+}
+
 extern "C" uint64_t gmrfb_ctx_stream(gmrfb_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 extern "C" int64_t gmrfb_ctx_launch_count(gmrfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -193,12 +264,24 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
   std::vector<int32_t> lists;
   sym->level_off.assign(1, 0);
   sym->level_maxd.clear();
+  sym->level_bytes.clear();
+  sym->level_vec_bytes.clear();
+  sym->level_flops.clear();
   for (auto& L : S.levels) {
     int md = 0;
+    double lb = 0, vb = 0, lf = 0;
     for (int32_t s : L.snodes) {
       lists.push_back(s);
       md = std::max(md, S.front_order(s));
+      double d = S.front_order(s), sc = S.ncols(s);
+      double trap = sc * d - sc * (sc - 1) / 2;
+      lb += 8.0 * trap;   // factor values read once per sweep
+      vb += 16.0 * d;     // solution/update vector entries read + written per right-hand side
+      lf += 2.0 * trap;   // one multiply-add per stored factor entry per right-hand side
     }
+    sym->level_bytes.push_back(lb);
+    sym->level_vec_bytes.push_back(vb);
+    sym->level_flops.push_back(lf);
     sym->level_off.push_back((int32_t)lists.size());
     sym->level_maxd.push_back(md);
   }
@@ -259,10 +342,16 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
   fac->factored = false;
   fac->z_valid = false;
   fac->logdet_valid = false;
-  GMRFB_CU(ctx, cudaMemsetAsync(fac->arena.p, 0, fac->arena.n * sizeof(double), st));
+  {
+    ProfScope ps(ctx, PK_MEMSET, 0, (double)fac->arena.n * sizeof(double));
+    GMRFB_CU(ctx, cudaMemsetAsync(fac->arena.p, 0, fac->arena.n * sizeof(double), st));
+  }
   const int big = INT_MAX;
   GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, st));
-  GMRFB_CU(ctx, launch_scatter_values(d_nzval, sym->d_amap.p, S.nnzA, fac->arena.p, st));
+  {
+    ProfScope ps(ctx, PK_SCATTER, 0, (double)S.nnzA * 16.0 + (double)S.nnz_lower_A * 8.0);
+    GMRFB_CU(ctx, launch_scatter_values(d_nzval, sym->d_amap.p, S.nnzA, fac->arena.p, st));
+  }
   ctx->launches++;
   Arenas ar{{fac->arena.p, nullptr, nullptr, nullptr}};
   LaunchAux aux;
@@ -405,6 +494,7 @@ gmrfb_status sweep(gmrfb_fac* fac, bool fwd, bool bwd, int nr) {
   if (fwd) {
     for (int l = 0; l < nlev; l++) {
       int cnt = sym->level_off[l + 1] - sym->level_off[l];
+      ProfScope ps(ctx, PK_FWD_LEVEL, sym->level_flops[l] * nr, sym->level_bytes[l] + sym->level_vec_bytes[l] * nr);
       GMRFB_CU(ctx, launch_fwd_level(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt, sym->level_maxd[l],
                                      sym->d_child_idx.p, sym->d_relmap.p, fac->arena.p, fac->xwork.p, n, fac->uvec.p,
                                      nr, ctx->stream));
@@ -414,6 +504,7 @@ gmrfb_status sweep(gmrfb_fac* fac, bool fwd, bool bwd, int nr) {
   if (bwd) {
     for (int l = nlev - 1; l >= 0; l--) {
       int cnt = sym->level_off[l + 1] - sym->level_off[l];
+      ProfScope ps(ctx, PK_BWD_LEVEL, sym->level_flops[l] * nr, sym->level_bytes[l] + sym->level_vec_bytes[l] * nr);
       GMRFB_CU(ctx, launch_bwd_level(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt, sym->level_maxd[l],
                                      sym->d_rows.p, fac->arena.p, fac->xwork.p, n, nr, ctx->stream));
       ctx->launches++;

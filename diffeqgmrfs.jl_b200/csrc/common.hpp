@@ -21,6 +21,14 @@ struct gmrfb_ctx {
   int* d_info = nullptr;       // POTRF failure column
   double* d_scalar = nullptr;  // small device scratch (reductions)
   int sm_count = 0;
+  // optional per-kernel profiling (CUDA events around every launch)
+  bool profiling = false;
+  struct ProfRec {
+    int32_t kind;
+    cudaEvent_t e0, e1;
+    double flops, bytes;
+  };
+  std::vector<ProfRec> prof;
 };
 
 namespace gmrfb {
@@ -80,6 +88,27 @@ struct DevPlan {
   Plan host;
   DevBuf<Task> tasks;
   bool ready = false;
+};
+
+// Profiling hooks: bracket one launch of `kind` with events when ctx->profiling is on.
+struct ProfScope {
+  gmrfb_ctx* ctx;
+  bool on;
+  gmrfb_ctx::ProfRec rec;
+  ProfScope(gmrfb_ctx* c, int32_t kind, double flops, double bytes) : ctx(c), on(c && c->profiling) {
+    if (!on) return;
+    rec.kind = kind;
+    rec.flops = flops;
+    rec.bytes = bytes;
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    cudaEventRecord(rec.e0, ctx->stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(rec.e1, ctx->stream);
+    ctx->prof.push_back(rec);
+  }
 };
 
 // Execute every launch of a plan on the context's stream.

@@ -12,6 +12,7 @@ struct gmrfb_sym {
   gmrfb::DevBuf<int32_t> d_relmap, d_rows, d_perm, d_post, d_child_idx, d_level_lists;
   gmrfb::DevBuf<gmrfb::SnodeDesc> d_snodes;
   std::vector<int32_t> level_off, level_maxd;
+  std::vector<double> level_bytes, level_vec_bytes, level_flops;  // algorithmic work of one solve sweep per level
   int64_t uvec_rows = 0;
   gmrfb::DevPlan factor_plan, selinv_plan;
 };

@@ -22,6 +22,8 @@ class PlanBuilder {
     cur.task0 = (int32_t)P.tasks.size();
     cur.ntasks = 0;
     cur.grid = 0;
+    cur.bytes = 0;
+    flops0 = P.flops;
   }
   void add(Task t, int ctas) {
     if (ctas <= 0) return;
@@ -31,12 +33,14 @@ class PlanBuilder {
     cur.grid += ctas;
   }
   void end() {
+    cur.flops = P.flops - flops0;
     if (cur.ntasks > 0) P.launches.push_back(cur);
   }
 
  private:
   Plan& P;
   Launch cur{};
+  double flops0 = 0;
 };
 
 inline Task make_task() {

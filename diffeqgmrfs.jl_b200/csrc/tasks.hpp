@@ -49,7 +49,12 @@ struct Launch {
   int32_t kind;
   int32_t task0, ntasks;
   int32_t grid;  // number of CTAs
+  double flops;  // useful floating-point operations of this launch (0 for data-movement kernels)
+  double bytes;  // algorithmic bytes of this launch (0 where not accounted)
 };
+
+// Profile slots for kernels that are not plan launches.
+enum : int32_t { PK_FWD_LEVEL = 20, PK_BWD_LEVEL = 21, PK_SCATTER = 22, PK_MEMSET = 23, PK_PERM = 24, PK_MAX = 32 };
 
 // GEMM tile geometry used by both the plan builder (tile counts) and the kernels.
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16;

@@ -35,6 +35,17 @@ class Context:
     def sync(self):
         B.check(B.lib().gmrfb_ctx_sync(self.h), self.h)
 
+    def profile_begin(self):
+        B.check(B.lib().gmrfb_ctx_profile_begin(self.h), self.h)
+
+    def profile_end(self):
+        """-> list of dicts(name, kind, launches, ms, flops, bytes), one per kernel kind."""
+        ent = (B.ProfileEntry * 32)()
+        cnt = C.c_int32()
+        B.check(B.lib().gmrfb_ctx_profile_end(self.h, ent, 32, C.byref(cnt)), self.h)
+        return [dict(name=e.name.decode(), kind=e.kind, launches=e.launches, ms=e.ms, flops=e.flops, bytes=e.bytes)
+                for e in ent[:cnt.value]]
+
     @property
     def stream(self) -> int:
         return int(B.lib().gmrfb_ctx_stream(self.h))

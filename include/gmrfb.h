@@ -67,6 +67,21 @@ uint64_t gmrfb_ctx_stream(gmrfb_ctx* ctx);
 /* Number of kernels this library has launched through `ctx` since creation (for benchmarks). */
 int64_t gmrfb_ctx_launch_count(gmrfb_ctx* ctx);
 
+/* Per-kernel profiling for benchmarks: between profile_begin and profile_end every kernel launched through
+ * `ctx` is bracketed by CUDA events on the context's stream; profile_end synchronises and returns one entry
+ * per kernel kind with its launch count, summed device time and the algorithmic flops / bytes of those launches
+ * (the numerators of the roofline; DESIGN.md states the per-unit figures). */
+typedef struct gmrfb_profile_entry {
+  int32_t kind;
+  int64_t launches;
+  double ms;
+  double flops;
+  double bytes;
+  char name[32];
+} gmrfb_profile_entry;
+gmrfb_status gmrfb_ctx_profile_begin(gmrfb_ctx* ctx);
+gmrfb_status gmrfb_ctx_profile_end(gmrfb_ctx* ctx, gmrfb_profile_entry* entries, int32_t cap, int32_t* count);
+
 /* ------------------------------------------------------ symbolic analysis ---- */
 /* Replaces the symbolic half of `cholesky(Symmetric(A); perm=p)` — CHOLMOD analyze / analyze_p:
  *   scripts/solve_burger.jl:147, scripts/darcy/solve_darcy_fem.jl:93 and every
