@@ -250,11 +250,20 @@ def run_gpu_arm(args):
     x_host = np.empty(n)
     var_host = np.empty(n)
 
+    e2e_parts = {"factorize": 0.0, "solve": 0.0, "var": 0.0}
+
     def step_e2e():
+        t0 = time.perf_counter()
         fac.factorize(nz_host.numpy())
+        t1 = time.perf_counter()
         x_host[:] = rhs_host.numpy()
         xs = fac.solve(x_host)
+        t2 = time.perf_counter()
         v = fac.var_selinv()
+        t3 = time.perf_counter()
+        e2e_parts["factorize"] += t1 - t0
+        e2e_parts["solve"] += t2 - t1
+        e2e_parts["var"] += t3 - t2
         return xs, v
 
     def barrier():
@@ -295,6 +304,8 @@ def run_gpu_arm(args):
         e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / ke
+    print("e2e host-side split (s, incl. the untimed first call):", {k: round(v, 4) for k, v in e2e_parts.items()},
+          file=sys.stderr)
 
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)

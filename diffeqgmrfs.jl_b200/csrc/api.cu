@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -18,7 +20,7 @@ std::string& global_error() {
 
 gmrfb_status run_plan(gmrfb_ctx* ctx, const DevPlan& P, const Arenas& ar, const LaunchAux& aux) {
   for (const Launch& L : P.host.launches) {
-    ProfScope ps(ctx, L.kind, L.flops, L.bytes);
+    ProfScope ps(ctx, L.kind, L.flops, L.bytes, L.grid, L.ntasks);
     cudaError_t e = run_launch(L, P.tasks.p, ar, aux, ctx->stream);
     if (e != cudaSuccess)
       return fail(ctx, GMRFB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
@@ -100,6 +102,7 @@ static const char* prof_name(int kind) {
     case LK_GEMM_NT: return "k_gemm<NT> (DMMA)";
     case LK_GEMM_NN: return "k_gemm<NN> (DMMA)";
     case LK_GEMM_TN: return "k_gemm<TN> (DMMA)";
+    case LK_GEMM_TT: return "k_gemm<TT> (DMMA)";
     case LK_POTRF: return "k_potrf64";
     case LK_TRSM_RLT: return "k_trsm<RLT>";
     case LK_TRSM_RLN: return "k_trsm<RLN>";
@@ -110,8 +113,12 @@ static const char* prof_name(int kind) {
     case LK_SCALE: return "k_tile_op<scale>";
     case LK_DIAG_OUT: return "k_diag_out";
     case LK_SYMMETRIZE: return "k_tile_op<symmetrize>";
-    case PK_FWD_LEVEL: return "k_fwd_level";
-    case PK_BWD_LEVEL: return "k_bwd_level";
+    case LK_FRONT_FACTOR_SMALL: return "k_front_factor_small";
+    case LK_FRONT_SELINV_SMALL: return "k_front_selinv_small";
+    case PK_FWD_LEVEL: return "k_fwd_step";
+    case PK_BWD_LEVEL: return "k_bwd_step";
+    case PK_FWD_ASM: return "k_fwd_assemble";
+    case PK_BWD_RPART: return "k_bwd_rpart";
     case PK_SCATTER: return "k_scatter_values";
     case PK_MEMSET: return "memset(front arena)";
     case PK_PERM: return "k_perm_gather/scatter";
@@ -127,9 +134,19 @@ extern "C" gmrfb_status gmrfb_ctx_profile_end(gmrfb_ctx* ctx, gmrfb_profile_entr
   ctx->profiling = false;
   gmrfb_profile_entry acc[PK_MAX];
   memset(acc, 0, sizeof(acc));
+  // GMRFB_PROFILE_DUMP=<file>: one CSV line per launch (kind, name, grid, ms, flops, bytes) for kernel tuning
+  FILE* dump = nullptr;
+  if (const char* path = getenv("GMRFB_PROFILE_DUMP")) {
+    dump = fopen(path, "w");
+    if (dump) fprintf(dump, "seq,kind,name,grid,ntasks,ms,flops,bytes\n");
+  }
+  int seq = 0;
   for (auto& r : ctx->prof) {
     float ms = 0;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (dump)
+      fprintf(dump, "%d,%d,%s,%d,%d,%.5f,%.6e,%.6e\n", seq++, r.kind, prof_name(r.kind), r.grid, r.ntasks, ms, r.flops,
+              r.bytes);
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
     int k = (r.kind >= 0 && r.kind < PK_MAX) ? r.kind : PK_MAX - 1;
@@ -140,6 +157,7 @@ extern "C" gmrfb_status gmrfb_ctx_profile_end(gmrfb_ctx* ctx, gmrfb_profile_entr
     acc[k].bytes += r.bytes;
   }
   ctx->prof.clear();
+  if (dump) fclose(dump);
   int32_t n = 0;
   for (int k = 0; k < PK_MAX; k++) {
     if (acc[k].launches == 0) continue;
@@ -244,6 +262,7 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
   GMRFB_CU(ctx, sym->d_perm.upload(S.perm, st));
   GMRFB_CU(ctx, sym->d_post.upload(S.post, st));
   GMRFB_CU(ctx, sym->d_child_idx.upload(S.child_idx, st));
+  GMRFB_CU(ctx, sym->d_sparent.upload(S.sparent, st));
   std::vector<SnodeDesc> sd(S.nsuper);
   int64_t uo = 0;
   for (int32_t s = 0; s < S.nsuper; s++) {
@@ -286,8 +305,97 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
     sym->level_maxd.push_back(md);
   }
   GMRFB_CU(ctx, sym->d_level_lists.upload(lists, st));
-  if (solve_smem_bytes(S.max_front) > 227 * 1024)
-    return fail(ctx, GMRFB_ERR_ALLOC, "largest front does not fit the shared-memory solve kernel");
+  // ---- solve schedule ----
+  {
+    std::vector<Task> tasks;
+    sym->solve_levels.assign(S.levels.size(), gmrfb_sym::SolveLevel());
+    int64_t poff = 0;
+    std::vector<int64_t> part_off(S.nsuper, 0);
+    std::vector<int32_t> nchunk(S.nsuper, 0);
+    for (int32_t s = 0; s < S.nsuper; s++) {
+      int r = S.front_order(s) - S.ncols(s);
+      nchunk[s] = cdiv(r, SOLVE_BR_ROWS);
+      part_off[s] = poff;
+      poff += (int64_t)nchunk[s] * S.ncols(s) * SOLVE_NRC;
+    }
+    sym->partial_doubles = poff;
+    auto base_task = [&](int32_t s, int k) {
+      Task t = make_task();
+      t.a = S.foff[s];
+      t.lda = S.ld[s];
+      t.M = S.front_order(s);
+      t.N = S.ncols(s);
+      t.K = k;
+      t.ldb = S.sptr[s];
+      t.b = sd[s].uoff;
+      t.c = part_off[s];
+      t.ldc = nchunk[s];
+      t.aux0 = (int32_t)(S.rptr[s] & 0xffffffff);
+      t.aux1 = (int32_t)(S.rptr[s] >> 32);
+      return t;
+    };
+    for (size_t l = 0; l < S.levels.size(); l++) {
+      const auto& sn = S.levels[l].snodes;
+      auto& SL = sym->solve_levels[l];
+      int maxs = 0;
+      for (int32_t s : sn) maxs = std::max(maxs, S.ncols(s));
+      int nsteps = cdiv(maxs, 64);
+      for (int k = 0; k < nsteps; k++) {
+        Launch Lf{};
+        Lf.kind = PK_FWD_LEVEL;
+        Lf.task0 = (int32_t)tasks.size();
+        Launch Lb = Lf;
+        // forward step k: CTAs over the rows below block k (at least one CTA to solve and publish the block)
+        for (int32_t s : sn) {
+          int sc = S.ncols(s), d = S.front_order(s);
+          if (k * 64 >= sc) continue;
+          int nb = std::min(64, sc - k * 64);
+          Task t = base_task(s, k);
+          t.tile0 = Lf.grid;
+          int ctas = std::max(1, cdiv(d - (k * 64 + nb), SOLVE_FS_ROWS));
+          tasks.push_back(t);
+          Lf.ntasks++;
+          Lf.grid += ctas;
+          double trap = (double)nb * (d - k * 64) - (double)nb * (nb - 1) / 2;
+          Lf.bytes += 8.0 * trap;
+          Lf.flops += 2.0 * trap;
+        }
+        SL.fwd_steps.push_back(Lf);
+        Lb.kind = PK_BWD_LEVEL;
+        Lb.task0 = (int32_t)tasks.size();
+        for (int32_t s : sn) {
+          int sc = S.ncols(s);
+          if (k * 64 >= sc) continue;
+          int nb = std::min(64, sc - k * 64);
+          Task t = base_task(s, k);
+          t.tile0 = Lb.grid;
+          tasks.push_back(t);
+          Lb.ntasks++;
+          Lb.grid += k + 1;
+          double tri = (double)nb * (k * 64) + (double)nb * (nb + 1) / 2;  // strip of L11 left of and incl. the block
+          Lb.bytes += 8.0 * tri;
+          Lb.flops += 2.0 * tri;
+        }
+        SL.bwd_steps.push_back(Lb);
+      }
+      Launch Lr{};
+      Lr.kind = PK_BWD_RPART;
+      Lr.task0 = (int32_t)tasks.size();
+      for (int32_t s : sn) {
+        int sc = S.ncols(s), d = S.front_order(s), r = d - sc;
+        if (r <= 0) continue;
+        Task t = base_task(s, 0);
+        t.tile0 = Lr.grid;
+        tasks.push_back(t);
+        Lr.ntasks++;
+        Lr.grid += cdiv(sc, 64) * nchunk[s];
+        Lr.bytes += 8.0 * (double)r * sc;
+        Lr.flops += 2.0 * (double)r * sc;
+      }
+      SL.rpart = Lr;
+    }
+    GMRFB_CU(ctx, sym->d_solve_tasks.upload(tasks, st));
+  }
   build_factor_plan(S, sym->factor_plan.host);
   GMRFB_CU(ctx, sym->factor_plan.tasks.upload(sym->factor_plan.host.tasks, st));
   sym->factor_plan.ready = true;
@@ -318,6 +426,9 @@ extern "C" gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out) {
   GMRFB_CU(ctx, f->arena.alloc((size_t)std::max<int64_t>(S.arena, 1)));
   GMRFB_CU(ctx, f->nzval.alloc((size_t)std::max<int64_t>(S.nnzA, 1)));
   GMRFB_CU(ctx, f->xwork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
+  GMRFB_CU(ctx, f->ywork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
+  GMRFB_CU(ctx, f->owork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
+  GMRFB_CU(ctx, f->partial.alloc((size_t)std::max<int64_t>(sym->partial_doubles, 1)));
   GMRFB_CU(ctx, f->bwork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
   GMRFB_CU(ctx, f->uvec.alloc((size_t)std::max<int64_t>(sym->uvec_rows, 1) * SOLVE_NRC));
   *out = f.release();
@@ -357,6 +468,9 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
   LaunchAux aux;
   aux.d_info = ctx->d_info;
   aux.d_relmap = sym->d_relmap.p;
+  aux.d_snodes = sym->d_snodes.p;
+  aux.d_child_idx = sym->d_child_idx.p;
+  aux.d_sparent = sym->d_sparent.p;
   gmrfb_status rc = run_plan(ctx, sym->factor_plan, ar, aux);
   if (rc != GMRFB_OK) return rc;
   int info = 0;
@@ -485,28 +599,54 @@ extern "C" gmrfb_status gmrfb_fac_get_L(gmrfb_fac* fac, int32_t base, int32_t dr
 // ---------------------------------------------------------------------------------------------- solves ----
 namespace {
 
-// Run the level-scheduled sweeps on fac->xwork (internal ordering, n x nr, ld n).
-gmrfb_status sweep(gmrfb_fac* fac, bool fwd, bool bwd, int nr) {
+// Level-scheduled sweeps.  Forward: working vector in `w` (destroyed), solution into `y`.  Backward: right-hand
+// side in `t` (destroyed), solution into `xs`.  Vectors are n x nr (internal ordering, leading dimension n).
+gmrfb_status sweep_fwd(gmrfb_fac* fac, double* w, double* y, int nr) {
   gmrfb_ctx* ctx = fac->ctx;
   gmrfb_sym* sym = fac->sym;
   const int64_t n = sym->S.n;
   const int nlev = (int)sym->S.levels.size();
-  if (fwd) {
-    for (int l = 0; l < nlev; l++) {
-      int cnt = sym->level_off[l + 1] - sym->level_off[l];
-      ProfScope ps(ctx, PK_FWD_LEVEL, sym->level_flops[l] * nr, sym->level_bytes[l] + sym->level_vec_bytes[l] * nr);
-      GMRFB_CU(ctx, launch_fwd_level(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt, sym->level_maxd[l],
-                                     sym->d_child_idx.p, sym->d_relmap.p, fac->arena.p, fac->xwork.p, n, fac->uvec.p,
-                                     nr, ctx->stream));
+  for (int l = 0; l < nlev; l++) {
+    int cnt = sym->level_off[l + 1] - sym->level_off[l];
+    if (l > 0) {
+      ProfScope ps(ctx, PK_FWD_ASM, 0, sym->level_vec_bytes[l] * nr, cnt, cnt);
+      GMRFB_CU(ctx, launch_fwd_assemble(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt,
+                                        sym->d_child_idx.p, sym->d_relmap.p, w, n, fac->uvec.p, ctx->stream));
+      ctx->launches++;
+    } else {
+      // leaves have no children: their update vectors start from zero
+      GMRFB_CU(ctx, launch_fwd_assemble(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt,
+                                        sym->d_child_idx.p, sym->d_relmap.p, w, n, fac->uvec.p, ctx->stream));
+      ctx->launches++;
+    }
+    for (const Launch& L : sym->solve_levels[l].fwd_steps) {
+      ProfScope ps(ctx, PK_FWD_LEVEL, L.flops * nr, L.bytes, L.grid, L.ntasks);
+      GMRFB_CU(ctx, launch_fwd_step(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, w, y, n,
+                                    fac->uvec.p, nr, ctx->stream));
       ctx->launches++;
     }
   }
-  if (bwd) {
-    for (int l = nlev - 1; l >= 0; l--) {
-      int cnt = sym->level_off[l + 1] - sym->level_off[l];
-      ProfScope ps(ctx, PK_BWD_LEVEL, sym->level_flops[l] * nr, sym->level_bytes[l] + sym->level_vec_bytes[l] * nr);
-      GMRFB_CU(ctx, launch_bwd_level(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt, sym->level_maxd[l],
-                                     sym->d_rows.p, fac->arena.p, fac->xwork.p, n, nr, ctx->stream));
+  return GMRFB_OK;
+}
+
+gmrfb_status sweep_bwd(gmrfb_fac* fac, double* t, double* xs, int nr) {
+  gmrfb_ctx* ctx = fac->ctx;
+  gmrfb_sym* sym = fac->sym;
+  const int64_t n = sym->S.n;
+  const int nlev = (int)sym->S.levels.size();
+  for (int l = nlev - 1; l >= 0; l--) {
+    const auto& SL = sym->solve_levels[l];
+    if (SL.rpart.grid > 0) {
+      ProfScope ps(ctx, PK_BWD_RPART, SL.rpart.flops * nr, SL.rpart.bytes, SL.rpart.grid, SL.rpart.ntasks);
+      GMRFB_CU(ctx, launch_bwd_rpart(sym->d_solve_tasks.p + SL.rpart.task0, SL.rpart.ntasks, SL.rpart.grid,
+                                     fac->arena.p, sym->d_rows.p, xs, n, fac->partial.p, nr, ctx->stream));
+      ctx->launches++;
+    }
+    for (int k = (int)SL.bwd_steps.size() - 1; k >= 0; k--) {
+      const Launch& L = SL.bwd_steps[k];
+      ProfScope ps(ctx, PK_BWD_LEVEL, L.flops * nr, L.bytes, L.grid, L.ntasks);
+      GMRFB_CU(ctx, launch_bwd_step(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, t, xs, n,
+                                    fac->partial.p, nr, ctx->stream));
       ctx->launches++;
     }
   }
@@ -539,13 +679,19 @@ gmrfb_status solve_device(gmrfb_fac* fac, int mode, const double* d_in, int64_t 
   if (!mode_spec(mode, m)) return fail(ctx, GMRFB_ERR_INVALID, "unknown solve mode");
   for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
-    GMRFB_CU(ctx, launch_perm_gather(d_in + c0 * ldin, ldin, fac->xwork.p, n, m.in_perm ? sym->d_perm.p : sym->d_post.p,
-                                     n, nr, ctx->stream));
+    // fwd: xwork -> ywork;  bwd: ywork -> xwork
+    double* first = m.fwd ? fac->xwork.p : fac->ywork.p;
+    GMRFB_CU(ctx, launch_perm_gather(d_in + c0 * ldin, ldin, first, n, m.in_perm ? sym->d_perm.p : sym->d_post.p, n, nr,
+                                     ctx->stream));
     ctx->launches++;
-    gmrfb_status rc = sweep(fac, m.fwd, m.bwd, nr);
+    gmrfb_status rc = GMRFB_OK;
+    if (m.fwd) rc = sweep_fwd(fac, fac->xwork.p, fac->ywork.p, nr);
     if (rc != GMRFB_OK) return rc;
-    GMRFB_CU(ctx, launch_perm_scatter(fac->xwork.p, n, d_out + c0 * ldout, ldout,
-                                      m.out_perm ? sym->d_perm.p : sym->d_post.p, n, nr, d_mean, ctx->stream));
+    if (m.bwd) rc = sweep_bwd(fac, fac->ywork.p, fac->xwork.p, nr);
+    if (rc != GMRFB_OK) return rc;
+    const double* result = m.bwd ? fac->xwork.p : fac->ywork.p;
+    GMRFB_CU(ctx, launch_perm_scatter(result, n, d_out + c0 * ldout, ldout, m.out_perm ? sym->d_perm.p : sym->d_post.p,
+                                      n, nr, d_mean, ctx->stream));
     ctx->launches++;
   }
   return GMRFB_OK;
@@ -578,8 +724,7 @@ extern "C" gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int
   const int64_t n = fac->sym->S.n;
   if (ldx < n || nrhs < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_solve: bad ldx/nrhs");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
-  DevBuf<double> out;
-  GMRFB_CU(ctx, out.alloc((size_t)std::max<int64_t>(n, 1) * SOLVE_NRC));
+  DevBuf<double>& out = fac->owork;  // persistent staging: no cudaMalloc/cudaFree on the solve path
   for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
     GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), X + c0 * ldx, ldx * sizeof(double),
@@ -601,8 +746,8 @@ extern "C" gmrfb_status gmrfb_sample(gmrfb_fac* fac, const double* mean, const d
   const int64_t n = fac->sym->S.n;
   if (ldz < n || ldx < n || nrhs < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_sample: bad leading dimension");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
-  DevBuf<double> out, dmean;
-  GMRFB_CU(ctx, out.alloc((size_t)std::max<int64_t>(n, 1) * SOLVE_NRC));
+  DevBuf<double>& out = fac->owork;
+  DevBuf<double> dmean;
   if (mean) {
     GMRFB_CU(ctx, dmean.alloc((size_t)std::max<int64_t>(n, 1)));
     GMRFB_CU(ctx, cudaMemcpyAsync(dmean.p, mean, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -628,11 +773,15 @@ static gmrfb_status selinv_run(gmrfb_fac* fac) {
   if (rc != GMRFB_OK) return rc;
   if (!fac->zarena.p) GMRFB_CU(ctx, fac->zarena.alloc(fac->arena.n));
   if (!fac->zdiag.p) GMRFB_CU(ctx, fac->zdiag.alloc((size_t)std::max<int64_t>(sym->S.n, 1)));
-  Arenas ar{{fac->arena.p, fac->zarena.p, nullptr, nullptr}};
+  if (!fac->zwork.p) GMRFB_CU(ctx, fac->zwork.alloc((size_t)std::max<int64_t>(sym->selinv_plan.host.scratch, 1)));
+  Arenas ar{{fac->arena.p, fac->zarena.p, fac->zwork.p, nullptr}};
   LaunchAux aux;
   aux.d_info = ctx->d_info;
   aux.d_relmap = sym->d_relmap.p;
   aux.d_out = fac->zdiag.p;
+  aux.d_snodes = sym->d_snodes.p;
+  aux.d_child_idx = sym->d_child_idx.p;
+  aux.d_sparent = sym->d_sparent.p;
   rc = run_plan(ctx, sym->selinv_plan, ar, aux);
   if (rc != GMRFB_OK) return rc;
   fac->z_valid = true;
@@ -658,8 +807,7 @@ extern "C" gmrfb_status gmrfb_var_selinv(gmrfb_fac* fac, double* var_out) {
   gmrfb_ctx* ctx = fac->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   const int64_t n = fac->sym->S.n;
-  DevBuf<double> out;
-  GMRFB_CU(ctx, out.alloc((size_t)std::max<int64_t>(n, 1)));
+  DevBuf<double>& out = fac->owork;
   gmrfb_status rc = gmrfb_var_selinv_dev(fac, out.p);
   if (rc != GMRFB_OK) return rc;
   GMRFB_CU(ctx, cudaMemcpyAsync(var_out, out.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -729,9 +877,9 @@ extern "C" gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nsamp - c0);
     GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
                                     n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
-    GMRFB_CU(ctx, launch_perm_gather(fac->bwork.p, n, fac->xwork.p, n, sym->d_post.p, n, nr, ctx->stream));
+    GMRFB_CU(ctx, launch_perm_gather(fac->bwork.p, n, fac->ywork.p, n, sym->d_post.p, n, nr, ctx->stream));
     ctx->launches++;
-    gmrfb_status rc = sweep(fac, false, true, nr);
+    gmrfb_status rc = sweep_bwd(fac, fac->ywork.p, fac->xwork.p, nr);
     if (rc != GMRFB_OK) return rc;
     GMRFB_CU(ctx, launch_perm_scatter_nodemajor(fac->xwork.p, n, Xs.p, ldk, sym->d_perm.p, n, (int)c0, nr, ctx->stream));
     ctx->launches++;

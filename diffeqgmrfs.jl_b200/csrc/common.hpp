@@ -27,6 +27,7 @@ struct gmrfb_ctx {
     int32_t kind;
     cudaEvent_t e0, e1;
     double flops, bytes;
+    int32_t grid, ntasks;
   };
   std::vector<ProfRec> prof;
 };
@@ -95,9 +96,12 @@ struct ProfScope {
   gmrfb_ctx* ctx;
   bool on;
   gmrfb_ctx::ProfRec rec;
-  ProfScope(gmrfb_ctx* c, int32_t kind, double flops, double bytes) : ctx(c), on(c && c->profiling) {
+  ProfScope(gmrfb_ctx* c, int32_t kind, double flops, double bytes, int32_t grid = 0, int32_t ntasks = 0)
+      : ctx(c), on(c && c->profiling) {
     if (!on) return;
     rec.kind = kind;
+    rec.grid = grid;
+    rec.ntasks = ntasks;
     rec.flops = flops;
     rec.bytes = bytes;
     cudaEventCreate(&rec.e0);

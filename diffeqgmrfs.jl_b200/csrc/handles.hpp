@@ -9,18 +9,26 @@ struct gmrfb_sym {
   gmrfb::Symbolic S;
   bool dev_ready = false;
   gmrfb::DevBuf<int64_t> d_amap;
-  gmrfb::DevBuf<int32_t> d_relmap, d_rows, d_perm, d_post, d_child_idx, d_level_lists;
+  gmrfb::DevBuf<int32_t> d_relmap, d_rows, d_perm, d_post, d_child_idx, d_level_lists, d_sparent;
   gmrfb::DevBuf<gmrfb::SnodeDesc> d_snodes;
   std::vector<int32_t> level_off, level_maxd;
   std::vector<double> level_bytes, level_vec_bytes, level_flops;  // algorithmic work of one solve sweep per level
   int64_t uvec_rows = 0;
   gmrfb::DevPlan factor_plan, selinv_plan;
+  // solve schedule: per level, one launch per 64-column block step
+  struct SolveLevel {
+    std::vector<gmrfb::Launch> fwd_steps, bwd_steps;
+    gmrfb::Launch rpart;
+  };
+  std::vector<SolveLevel> solve_levels;
+  gmrfb::DevBuf<gmrfb::Task> d_solve_tasks;
+  int64_t partial_doubles = 0;
 };
 
 struct gmrfb_fac {
   gmrfb_ctx* ctx = nullptr;
   gmrfb_sym* sym = nullptr;
-  gmrfb::DevBuf<double> arena, zarena, zdiag, nzval, xwork, bwork, uvec;
+  gmrfb::DevBuf<double> arena, zarena, zwork, zdiag, nzval, xwork, ywork, bwork, owork, uvec, partial;
   bool factored = false, z_valid = false, logdet_valid = false;
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_column = -1;

@@ -14,6 +14,7 @@
 #include <cstdint>
 
 #include "kernels.hpp"
+#include "sparse_kernels.hpp"
 #include "tasks.hpp"
 
 namespace gmrfb {
@@ -101,7 +102,21 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
   double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
   const int lda = T.lda, ldb = T.ldb, ldc = T.ldc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+  // Interleaved ownership of the 16 x 16 grid of 8x8 MMA sub-tiles: warp (wm, wn) owns row sub-tiles im*2 + wm and
+  // column sub-tiles in*4 + wn.  Sub-tiles outside the problem (or above the diagonal of a triangular result) are
+  // skipped with warp-uniform predicates, and the interleaving keeps the remaining work balanced across warps, so
+  // partially filled tiles (small fronts in a batched launch) cost only their useful 8x8 blocks of DMMA issue.
+  const int wm = warp & 1, wn = warp >> 1;
+  unsigned active = 0;
+#pragma unroll
+  for (int im = 0; im < 8; im++)
+#pragma unroll
+    for (int in = 0; in < 4; in++) {
+      const int r0 = m0 + (im * 2 + wm) * 8, c0 = n0 + (in * 4 + wn) * 8;
+      bool on = (r0 < M) && (c0 < N);
+      if ((T.flags & TF_TRI) && c0 > r0 + 7) on = false;
+      if (on) active |= 1u << (im * 4 + in);
+    }
 
   auto load_stage = [&](int stage, int k0) {
     double* as = As + stage * A_STAGE;
@@ -145,13 +160,14 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int nkt = (K + BK - 1) / BK;
+  const int kt0 = (TA && (T.flags & TF_KLOW)) ? min(m0 / BK, nkt) : 0;  // A' lower triangular: rows k < m0 are zero
 #pragma unroll
   for (int s = 0; s < G_STAGES - 1; s++) {
-    if (s < nkt) load_stage(s, s * BK);
+    if (kt0 + s < nkt) load_stage((kt0 + s) % G_STAGES, (kt0 + s) * BK);
     cp_async_commit();
   }
   const int lr = lane >> 2, lc = lane & 3;
-  for (int kt = 0; kt < nkt; kt++) {
+  for (int kt = kt0; kt < nkt; kt++) {
     cp_async_wait<G_STAGES - 2>();
     __syncthreads();
     {
@@ -165,15 +181,20 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
     for (int kb = 0; kb < BK; kb += 4) {
       double af[8], bf[4];
 #pragma unroll
+      for (int im = 0; im < 8; im++) {
+        const int rr = (im * 2 + wm) * 8 + lr;
+        af[im] = TA ? as[rr * G_LDT + kb + lc] : as[(kb + lc) * G_LDN + rr];
+      }
+#pragma unroll
+      for (int in = 0; in < 4; in++) {
+        const int cc = (in * 4 + wn) * 8 + lr;
+        bf[in] = TB ? bs[cc * G_LDT + kb + lc] : bs[(kb + lc) * G_LDN + cc];
+      }
+#pragma unroll
       for (int im = 0; im < 8; im++)
-        af[im] = TA ? as[(wm0 + im * 8 + lr) * G_LDT + kb + lc] : as[(kb + lc) * G_LDN + wm0 + im * 8 + lr];
 #pragma unroll
-      for (int in = 0; in < 4; in++)
-        bf[in] = TB ? bs[(wn0 + in * 8 + lr) * G_LDT + kb + lc] : bs[(kb + lc) * G_LDN + wn0 + in * 8 + lr];
-#pragma unroll
-      for (int im = 0; im < 8; im++)
-#pragma unroll
-        for (int in = 0; in < 4; in++) dmma884(acc[im][in][0], acc[im][in][1], af[im], bf[in]);
+        for (int in = 0; in < 4; in++)
+          if (active & (1u << (im * 4 + in))) dmma884(acc[im][in][0], acc[im][in][1], af[im], bf[in]);
     }
   }
   cp_async_wait<0>();
@@ -182,13 +203,14 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
   const double alpha = T.alpha, beta = T.beta;
 #pragma unroll
   for (int im = 0; im < 8; im++) {
-    const int row = m0 + wm0 + im * 8 + lr;
+    const int row = m0 + (im * 2 + wm) * 8 + lr;
     if (row >= M) continue;
 #pragma unroll
     for (int in = 0; in < 4; in++) {
+      if (!(active & (1u << (im * 4 + in)))) continue;
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int col = n0 + wn0 + in * 8 + 2 * lc + h;
+        const int col = n0 + (in * 4 + wn) * 8 + 2 * lc + h;
         if (col < N && (!tri || row >= col)) {
           double* p = C + row + (int64_t)col * ldc;
           double v = alpha * acc[im][in][h];
@@ -211,10 +233,9 @@ __global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks,
   const int n = T.M, lda = T.lda;
   double* __restrict__ A = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
   const int tid = threadIdx.x;
-  for (int e = tid; e < n * n; e += 256) {
-    int i = e % n, j = e / n;
-    if (i >= j) S[j * P_LD + i] = A[i + (int64_t)j * lda];
-  }
+  const int ti = tid & 63, tq = tid >> 6;  // thread = (row, column phase): no integer divisions in the hot loops
+  for (int j = tq; j < n; j += 4)
+    if (ti < n && ti >= j) S[j * P_LD + ti] = A[ti + (int64_t)j * lda];
   for (int j = 0; j < n; j++) {
     __syncthreads();
     const double d = S[j * P_LD + j];
@@ -227,19 +248,16 @@ __global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks,
       if (tid == 0) atomicMin(info, T.aux0 + j);
     }
     const double inv = 1.0 / ljj;
-    for (int i = j + tid; i < n; i += 256) S[j * P_LD + i] = (i == j) ? ljj : S[j * P_LD + i] * inv;
+    if (tq == 0 && ti >= j && ti < n) S[j * P_LD + ti] = (ti == j) ? ljj : S[j * P_LD + ti] * inv;
     __syncthreads();
-    const int w = n - j - 1;
-    for (int e = tid; e < w * w; e += 256) {
-      int i = j + 1 + e % w, k = j + 1 + e / w;
-      if (i >= k) S[k * P_LD + i] -= S[j * P_LD + i] * S[j * P_LD + k];
+    if (ti < n) {
+      const double lij = S[j * P_LD + ti];
+      for (int k = j + 1 + tq; k <= ti; k += 4) S[k * P_LD + ti] -= lij * S[j * P_LD + k];
     }
   }
   __syncthreads();
-  for (int e = tid; e < n * n; e += 256) {
-    int i = e % n, j = e / n;
-    if (i >= j) A[i + (int64_t)j * lda] = S[j * P_LD + i];
-  }
+  for (int j = tq; j < n; j += 4)
+    if (ti < n && ti >= j) A[ti + (int64_t)j * lda] = S[j * P_LD + ti];
 }
 
 // --------------------------------------------------------------------------------------------- TRSM ----
@@ -363,6 +381,142 @@ __global__ void __launch_bounds__(256) k_gather_sym(const Task* __restrict__ tas
   }
 }
 
+// ------------------------------------------------------------------------ fused small-front kernels ----
+// Fronts of order d <= SMALL_FRONT_MAX are processed by ONE CTA entirely in shared memory (the front is staged
+// once, every operation of the multifrontal step runs on-chip, results are written once):
+//   factor : load the assembled panel, extend-add the children's update matrices (fixed order), partial
+//            Cholesky of the first s columns with the full trailing update, write L and the update matrix.
+//   selinv : gather Z_RR from the parent's inverse front, then the dense Takahashi recurrence column by column
+//            (Z_ij = (delta_ij / L_jj - sum_{k>j} L_kj Z_ik) / L_jj), write the inverse front and its diagonal.
+// Task encoding: aux0 = supernode index.
+__global__ void __launch_bounds__(256) k_front_factor_small(const Task* __restrict__ tasks, Arenas ar,
+                                                            const SnodeDesc* __restrict__ sd,
+                                                            const int32_t* __restrict__ child_idx,
+                                                            const int32_t* __restrict__ relmap,
+                                                            int* __restrict__ info) {
+  extern __shared__ __align__(16) double S[];
+  __shared__ int32_t rel[SMALL_FRONT_MAX];
+  const SnodeDesc D = sd[tasks[blockIdx.x].aux0];
+  const int d = D.d, s = D.s, ldg = D.ld;
+  const int lds = d | 1;
+  double* __restrict__ F = ar.p[0] + D.foff;
+  const int tid = threadIdx.x, ti = tid & 63, tq = tid >> 6;
+  // stage: panel columns from the arena, update-matrix part starts from zero
+  for (int c = tq; c < d; c += 4)
+    for (int i = ti; i < d; i += 64) S[c * lds + i] = (c < s && i >= c) ? F[(int64_t)c * ldg + i] : 0.0;
+  __syncthreads();
+  for (int ci = 0; ci < D.nchild; ci++) {
+    const SnodeDesc C = sd[child_idx[D.child0 + ci]];
+    const int rc = C.d - C.s;
+    const double* __restrict__ U = ar.p[0] + C.foff + (int64_t)C.s * C.ld + C.s;
+    const int32_t* __restrict__ rl = relmap + C.rows_off + C.s;
+    if (rc <= SMALL_FRONT_MAX) {
+      for (int i = tid; i < rc; i += 256) rel[i] = rl[i];
+      __syncthreads();
+      for (int j = tq; j < rc; j += 4) {
+        const int pj = rel[j];
+        for (int i = j + ti - (j & 63) + ((ti < (j & 63)) ? 64 : 0); i < rc; i += 64)
+          S[pj * lds + rel[i]] += U[i + (int64_t)j * C.ld];
+      }
+    } else {
+      // a child with a long boundary: its rows still all map inside this (small) front
+      for (int j = tq; j < rc; j += 4) {
+        const int pj = rl[j];
+        for (int i = j + ti - (j & 63) + ((ti < (j & 63)) ? 64 : 0); i < rc; i += 64)
+          S[pj * lds + rl[i]] += U[i + (int64_t)j * C.ld];
+      }
+    }
+    __syncthreads();
+  }
+  for (int j = 0; j < s; j++) {
+    const double dj = S[j * lds + j];
+    __syncthreads();
+    double ljj;
+    if (dj > 0.0) {
+      ljj = sqrt(dj);
+    } else {
+      ljj = nan("");
+      if (tid == 0) atomicMin(info, D.col0 + j);
+    }
+    const double inv = 1.0 / ljj;
+    for (int i = j + tid; i < d; i += 256) S[j * lds + i] = (i == j) ? ljj : S[j * lds + i] * inv;
+    __syncthreads();
+    for (int k = j + 1 + tq; k < d; k += 4) {
+      const double lk = S[j * lds + k];
+      for (int i = k + ti - (k & 63) + ((ti < (k & 63)) ? 64 : 0); i < d; i += 64) S[k * lds + i] -= S[j * lds + i] * lk;
+    }
+    __syncthreads();
+  }
+  for (int c = tq; c < d; c += 4)
+    for (int i = c + ti - (c & 63) + ((ti < (c & 63)) ? 64 : 0); i < d; i += 64) F[(int64_t)c * ldg + i] = S[c * lds + i];
+}
+
+__global__ void __launch_bounds__(256) k_front_selinv_small(const Task* __restrict__ tasks, Arenas ar,
+                                                            const SnodeDesc* __restrict__ sd,
+                                                            const int32_t* __restrict__ relmap,
+                                                            const int32_t* __restrict__ sparent,
+                                                            double* __restrict__ zdiag) {
+  extern __shared__ __align__(16) double Z[];
+  __shared__ double lcol[SMALL_FRONT_MAX];
+  __shared__ double part[4][SMALL_FRONT_MAX];
+  __shared__ int32_t rel[SMALL_FRONT_MAX];
+  __shared__ double red[8];
+  const int sidx = tasks[blockIdx.x].aux0;
+  const SnodeDesc D = sd[sidx];
+  const int d = D.d, s = D.s, r = d - s, ldg = D.ld;
+  const int lds = d | 1;
+  const double* __restrict__ L = ar.p[0] + D.foff;
+  double* __restrict__ Zg = ar.p[1] + D.foff;
+  const int tid = threadIdx.x, ti = tid & 63, tq = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  if (r > 0) {
+    const SnodeDesc P = sd[sparent[sidx]];
+    const double* __restrict__ Zp = ar.p[1] + P.foff;
+    const int32_t* __restrict__ rl = relmap + D.rows_off + s;
+    for (int i = tid; i < r; i += 256) rel[i] = rl[i];
+    __syncthreads();
+    for (int j = tq; j < r; j += 4) {
+      const int64_t b = rel[j];
+      for (int i = ti; i < r; i += 64) {
+        const int64_t a = rel[i];
+        Z[(s + j) * lds + s + i] = (a >= b) ? Zp[a + b * P.ld] : Zp[b + a * P.ld];
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = s - 1; j >= 0; j--) {
+    for (int i = j + tid; i < d; i += 256) lcol[i] = L[(int64_t)j * ldg + i];
+    __syncthreads();
+    const double inv = 1.0 / lcol[j];
+    // partial sums over k = j+1+tq, step 4, for every row i > j
+    for (int i = j + 1 + ti; i < d; i += 64) {
+      double acc = 0.0;
+      for (int k = j + 1 + tq; k < d; k += 4) acc += lcol[k] * Z[k * lds + i];
+      part[tq][i] = acc;
+    }
+    __syncthreads();
+    double dot = 0.0;
+    for (int i = j + 1 + tid; i < d; i += 256) {
+      const double z = -(((part[0][i] + part[1][i]) + part[2][i]) + part[3][i]) * inv;
+      Z[j * lds + i] = z;
+      Z[i * lds + j] = z;
+      dot += lcol[i] * z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; w++) t += red[w];
+      Z[j * lds + j] = (inv - t) * inv;
+    }
+    __syncthreads();
+  }
+  for (int c = tq; c < d; c += 4)
+    for (int i = c + ti - (c & 63) + ((ti < (c & 63)) ? 64 : 0); i < d; i += 64) Zg[(int64_t)c * ldg + i] = Z[c * lds + i];
+  for (int c = tid; c < s; c += 256) zdiag[D.col0 + c] = Z[c * lds + c];
+}
+
 // Simple element-wise task kernels: one CTA per 64x64 tile.
 __global__ void __launch_bounds__(256) k_tile_op(const Task* __restrict__ tasks, int ntasks, Arenas ar, int op) {
   const int tix = find_task(tasks, ntasks, blockIdx.x);
@@ -449,6 +603,14 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)gemm_smem(true, true));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)gemm_smem(true, false));
+  if (e != cudaSuccess) return e;
+  const int small_smem = SMALL_FRONT_MAX * (SMALL_FRONT_MAX | 1) * (int)sizeof(double);
+  e = cudaFuncSetAttribute(k_front_factor_small, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_front_selinv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   return e;
 }
 
@@ -465,6 +627,9 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       break;
     case LK_GEMM_TN:
       k_gemm<true, true><<<L.grid, 256, gemm_smem(true, true), st>>>(t, L.ntasks, ar);
+      break;
+    case LK_GEMM_TT:
+      k_gemm<true, false><<<L.grid, 256, gemm_smem(true, false), st>>>(t, L.ntasks, ar);
       break;
     case LK_POTRF:
       k_potrf64<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_info);
@@ -491,6 +656,12 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       break;
     case LK_DIAG_OUT:
       k_diag_out<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_out);
+      break;
+    case LK_FRONT_FACTOR_SMALL:
+      k_front_factor_small<<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_child_idx, aux.d_relmap, aux.d_info);
+      break;
+    case LK_FRONT_SELINV_SMALL:
+      k_front_selinv_small<<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
       break;
     default:
       return cudaErrorInvalidValue;

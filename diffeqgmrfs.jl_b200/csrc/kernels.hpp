@@ -13,10 +13,14 @@ struct Arenas {
   double* p[4];
 };
 
+struct SnodeDesc;
 struct LaunchAux {
   int* d_info = nullptr;             // POTRF failure column (atomicMin)
   const int32_t* d_relmap = nullptr; // relative indices for extend-add / gather
   double* d_out = nullptr;           // DIAG_OUT destination
+  const SnodeDesc* d_snodes = nullptr;   // supernode records (fused small-front kernels)
+  const int32_t* d_child_idx = nullptr;  // children lists
+  const int32_t* d_sparent = nullptr;    // parent supernode of each supernode
 };
 
 cudaError_t kernels_init();

@@ -253,7 +253,37 @@ void plan_trsm_rln(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, i
 void build_factor_plan(const Symbolic& S, Plan& P) {
   PlanBuilder B(P);
   for (size_t lev = 0; lev < S.levels.size(); lev++) {
-    const auto& sn = S.levels[lev].snodes;
+    const auto& all = S.levels[lev].snodes;
+    // small fronts: one fused shared-memory kernel launch per size class
+    std::vector<int32_t> sn;
+    {
+      const int classes[3] = {72, 104, SMALL_FRONT_MAX};
+      std::vector<int32_t> cls[3];
+      for (int32_t s : all) {
+        int d = S.front_order(s);
+        if (d > SMALL_FRONT_MAX) {
+          sn.push_back(s);
+          continue;
+        }
+        cls[d <= classes[0] ? 0 : d <= classes[1] ? 1 : 2].push_back(s);
+      }
+      for (int c = 0; c < 3; c++) {
+        if (cls[c].empty()) continue;
+        B.begin(LK_FRONT_FACTOR_SMALL);
+        int maxd = 0;
+        for (int32_t s : cls[c]) {
+          Task t = make_task();
+          t.aux0 = s;
+          B.add(t, 1);
+          double d = S.front_order(s), sc = S.ncols(s), r = d - sc;
+          maxd = std::max(maxd, (int)d);
+          P.flops += sc * sc * sc / 3.0 + sc * sc * r + sc * r * (r + 1);
+          B.add_bytes(8.0 * (d * sc + r * r));
+        }
+        B.set_smem(maxd * (maxd | 1) * (int)sizeof(double));
+        B.end();
+      }
+    }
     // 1. assemble children update matrices, one child rank per launch (deterministic, no atomics)
     int maxc = 0;
     for (int32_t s : sn) maxc = std::max(maxc, S.child_ptr[s + 1] - S.child_ptr[s]);
@@ -295,7 +325,56 @@ void build_factor_plan(const Symbolic& S, Plan& P) {
 void build_selinv_plan(const Symbolic& S, Plan& P) {
   PlanBuilder B(P);
   for (int lev = (int)S.levels.size() - 1; lev >= 0; lev--) {
-    const auto& sn = S.levels[lev].snodes;
+    const auto& all = S.levels[lev].snodes;
+    std::vector<int32_t> sn;
+    {
+      const int classes[3] = {72, 104, SMALL_FRONT_MAX};
+      std::vector<int32_t> cls[3];
+      for (int32_t s : all) {
+        int d = S.front_order(s);
+        if (d > SMALL_FRONT_MAX) {
+          sn.push_back(s);
+          continue;
+        }
+        cls[d <= classes[0] ? 0 : d <= classes[1] ? 1 : 2].push_back(s);
+      }
+      for (int c = 0; c < 3; c++) {
+        if (cls[c].empty()) continue;
+        B.begin(LK_FRONT_SELINV_SMALL);
+        int maxd = 0;
+        for (int32_t s : cls[c]) {
+          Task t = make_task();
+          t.aux0 = s;
+          B.add(t, 1);
+          double d = S.front_order(s), sc = S.ncols(s), r = d - sc;
+          maxd = std::max(maxd, (int)d);
+          P.flops += 2.0 * (sc * r * r + sc * sc * r + sc * sc * sc / 3.0);
+          B.add_bytes(8.0 * (d * sc + d * d / 2 + r * r));
+        }
+        B.set_smem(maxd * (maxd | 1) * (int)sizeof(double));
+        B.end();
+      }
+    }
+    if (sn.empty()) continue;
+    // ---- large fronts of this level: GEMM-rich formulation with the explicit inverse W = L11^{-1} ----
+    //   Y' = W' L21'                 (s x r, parked in the unused upper-right block of the inverse front)
+    //   Z_RC = -Z_RR Y               (r x s)
+    //   Z_CC = W'W - Y' Z_RC         (s x s, lower triangle)
+    // W is used for the variances only (never for the factor or the solves), where its conditioning-dependent
+    // error (~cond(L11) eps) is far inside the 1e-8 tolerance and cannot propagate to posterior means.
+    std::vector<int64_t> woff(sn.size());
+    std::vector<int> ldw(sn.size());
+    {
+      int64_t off = 0;
+      for (size_t i = 0; i < sn.size(); i++) {
+        int sc = S.ncols(sn[i]);
+        ldw[i] = (sc + 1) & ~1;
+        woff[i] = off;
+        off += (int64_t)ldw[i] * sc;
+        off = (off + 15) & ~(int64_t)15;
+      }
+      P.scratch = std::max(P.scratch, off);
+    }
     B.begin(LK_GATHER_SYM);
     for (int32_t s : sn) {
       int sc = S.ncols(s), d = S.front_order(s), r = d - sc;
@@ -315,53 +394,85 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
       B.add(t, nt * nt);
     }
     B.end();
-    B.begin(LK_GEMM_NN);  // T = -Z_RR L21
+    // W = I L11^{-1}
+    B.begin(LK_SET_IDENTITY);
+    for (size_t i = 0; i < sn.size(); i++) {
+      int sc = S.ncols(sn[i]);
+      Task t = make_task();
+      t.c = woff[i];
+      t.ldc = ldw[i];
+      t.M = sc;
+      t.N = sc;
+      t.flags = arena_flags(0, 0, AR_WORK);
+      B.add(t, cdiv(sc, 64) * cdiv(sc, 64));
+    }
+    B.end();
+    {
+      std::vector<TrsmProb> tp;
+      for (size_t i = 0; i < sn.size(); i++) {
+        int32_t s = sn[i];
+        tp.push_back({AR_FRONT, S.foff[s], S.ld[s], AR_WORK, woff[i], ldw[i], S.ncols(s), S.ncols(s)});
+      }
+      plan_trsm_batch(B, P, tp, false, NBO);
+    }
+    B.begin(LK_GEMM_TT);  // Y' = W' L21'
+    for (size_t i = 0; i < sn.size(); i++) {
+      int32_t s = sn[i];
+      int sc = S.ncols(s), d = S.front_order(s), r = d - sc, ld = S.ld[s];
+      if (r <= 0) continue;
+      Task t = make_task();
+      t.a = woff[i];
+      t.lda = ldw[i];
+      t.b = S.foff[s] + sc;
+      t.ldb = ld;
+      t.c = S.foff[s] + (int64_t)sc * ld;
+      t.ldc = ld;
+      t.M = sc;
+      t.N = r;
+      t.K = sc;
+      t.alpha = 1.0;
+      t.beta = 0.0;
+      t.flags = arena_flags(AR_WORK, AR_FRONT, AR_ZINV) | TF_KLOW;
+      B.add(t, gemm_tiles(sc, r, false));
+      P.flops += (double)sc * sc * r;
+    }
+    B.end();
+    B.begin(LK_GEMM_NT);  // Z_RC = -Z_RR Y
     for (int32_t s : sn) {
       int sc = S.ncols(s), d = S.front_order(s), r = d - sc, ld = S.ld[s];
-      add_gemm(B, P, AR_ZINV, S.foff[s] + (int64_t)sc * ld + sc, ld, AR_FRONT, S.foff[s] + sc, ld, AR_ZINV,
+      add_gemm(B, P, AR_ZINV, S.foff[s] + (int64_t)sc * ld + sc, ld, AR_ZINV, S.foff[s] + (int64_t)sc * ld, ld, AR_ZINV,
                S.foff[s] + sc, ld, r, sc, r, false, -1.0, 0.0);
     }
     B.end();
-    B.begin(LK_SET_IDENTITY);
-    for (int32_t s : sn) {
+    B.begin(LK_GEMM_TN);  // Z_CC = W'W (lower)
+    for (size_t i = 0; i < sn.size(); i++) {
+      int32_t s = sn[i];
       int sc = S.ncols(s);
       Task t = make_task();
+      t.a = woff[i];
+      t.lda = ldw[i];
+      t.b = woff[i];
+      t.ldb = ldw[i];
       t.c = S.foff[s];
       t.ldc = S.ld[s];
       t.M = sc;
       t.N = sc;
-      t.flags = arena_flags(0, 0, AR_ZINV);
-      B.add(t, cdiv(sc, 64) * cdiv(sc, 64));
+      t.K = sc;
+      t.alpha = 1.0;
+      t.beta = 0.0;
+      t.flags = arena_flags(AR_WORK, AR_WORK, AR_ZINV) | TF_TRI | TF_KLOW;
+      B.add(t, gemm_tiles(sc, sc, true));
+      P.flops += (double)sc * sc * sc / 3.0;
     }
     B.end();
-    B.begin(LK_GEMM_TN);  // H = I - L21' T
+    B.begin(LK_GEMM_NN);  // Z_CC -= Y' Z_RC (lower)
     for (int32_t s : sn) {
       int sc = S.ncols(s), d = S.front_order(s), r = d - sc, ld = S.ld[s];
       if (r <= 0) continue;
-      add_gemm(B, P, AR_FRONT, S.foff[s] + sc, ld, AR_ZINV, S.foff[s] + sc, ld, AR_ZINV, S.foff[s], ld, sc, sc, r,
-               false, -1.0, 1.0);
+      add_gemm(B, P, AR_ZINV, S.foff[s] + (int64_t)sc * ld, ld, AR_ZINV, S.foff[s] + sc, ld, AR_ZINV, S.foff[s], ld, sc,
+               sc, r, true, -1.0, 1.0);
     }
     B.end();
-    // [H; T] <- [H; T] L11^{-1}
-    std::vector<TrsmProb> tp;
-    for (int32_t s : sn)
-      tp.push_back({AR_FRONT, S.foff[s], S.ld[s], AR_ZINV, S.foff[s], S.ld[s], S.front_order(s), S.ncols(s)});
-    plan_trsm_batch(B, P, tp, false, NBO);
-    // Z_CC = (H L11^{-1})' L11^{-1}
-    B.begin(LK_TRANSPOSE);
-    for (int32_t s : sn) {
-      int sc = S.ncols(s);
-      Task t = make_task();
-      t.c = S.foff[s];
-      t.ldc = S.ld[s];
-      t.M = sc;
-      t.flags = arena_flags(0, 0, AR_ZINV);
-      int nt = cdiv(sc, 32);
-      B.add(t, nt * (nt + 1) / 2);
-    }
-    B.end();
-    for (auto& q : tp) q.M = q.n;
-    plan_trsm_batch(B, P, tp, false, NBO);
     B.begin(LK_DIAG_OUT);
     for (int32_t s : sn) {
       int sc = S.ncols(s);

@@ -10,6 +10,7 @@ namespace gmrfb {
 struct Plan {
   std::vector<Task> tasks;
   std::vector<Launch> launches;
+  int64_t scratch = 0;  // doubles of scratch arena (AR_WORK) the plan needs
   double flops = 0;  // floating-point operations of the GEMM/SYRK/TRSM/POTRF tasks (useful work, not tile padding)
 };
 
@@ -23,6 +24,7 @@ class PlanBuilder {
     cur.ntasks = 0;
     cur.grid = 0;
     cur.bytes = 0;
+    cur.smem = 0;
     flops0 = P.flops;
   }
   void add(Task t, int ctas) {
@@ -32,6 +34,8 @@ class PlanBuilder {
     cur.ntasks++;
     cur.grid += ctas;
   }
+  void set_smem(int bytes) { cur.smem = bytes; }
+  void add_bytes(double b) { cur.bytes += b; }
   void end() {
     cur.flops = P.flops - flops0;
     if (cur.ntasks > 0) P.launches.push_back(cur);
@@ -51,7 +55,7 @@ inline Task make_task() {
 }
 
 // Arena indices used by the sparse plans.
-enum { AR_FRONT = 0, AR_ZINV = 1 };
+enum { AR_FRONT = 0, AR_ZINV = 1, AR_WORK = 2 };
 
 // Multifrontal numeric factorisation of every front, level by level (arena 0 = frontal arena).
 void build_factor_plan(const Symbolic& S, Plan& P);

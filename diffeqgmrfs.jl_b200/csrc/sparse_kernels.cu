@@ -6,10 +6,10 @@
 #include <cstdint>
 
 #include "sparse_kernels.hpp"
+#include "tasks.hpp"
 
 namespace gmrfb {
 
-constexpr int SOLVE_THREADS = 256;
 constexpr int DLD = 65;  // padded leading dimension of the 64x64 diagonal block in shared memory
 
 // ------------------------------------------------------------------------------------- permutations ----
@@ -32,53 +32,97 @@ __global__ void k_perm_scatter(const double* __restrict__ src, int64_t lds, doub
   for (int q = 0; q < nrhs; q++) dst[p + q * ldd] = src[k + q * lds] + a;
 }
 
-// --------------------------------------------------------------------------------- forward solve ----
-// One CTA per supernode J of the level.  w = [x_C ; 0] + sum_children u_c (mapped), then
-//   y_C = L11^{-1} w_C,   u_J = w_R - L21 y_C   (u holds minus the accumulated updates).
-template <int NRC>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_fwd_level(const SnodeDesc* __restrict__ sd,
-                                                             const int32_t* __restrict__ list,
-                                                             const int32_t* __restrict__ child_idx,
-                                                             const int32_t* __restrict__ relmap,
-                                                             const double* __restrict__ F, double* __restrict__ x,
-                                                             int64_t ldx, double* __restrict__ uvec, int nr) {
-  extern __shared__ __align__(16) double sm[];
-  double* Ld = sm;
-  double* invd = sm + 64 * DLD;
-  double* w = invd + 64;
-  const SnodeDesc D = sd[list[blockIdx.x]];
-  const int d = D.d, s = D.s, r = d - s, ld = D.ld;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* __restrict__ Fj = F + D.foff;
-  for (int i = tid; i < d; i += SOLVE_THREADS) {
-#pragma unroll
-    for (int q = 0; q < NRC; q++) w[i + q * d] = (i < s && q < nr) ? x[D.col0 + i + q * ldx] : 0.0;
+// ------------------------------------------------------------------------- supernodal triangular solves ----
+// Level-scheduled, multifrontal-style solves.  The right-hand side lives in global memory (x: n x nr, internal
+// ordering); every supernode J owns an update vector u_J (r_J x NRC) holding minus the accumulated
+// contributions to its below-rows.  Large supernodes are spread over many CTAs: a level is processed as one
+// assembly launch plus one launch per 64-column block step, and every factor entry is read exactly once with
+// rows contiguous across threads.  No atomics: all reductions have a fixed order (bit-reproducible results).
+//
+// Solve task encoding (Task): a = front offset, lda = ld, M = d, N = s, K = block step, ldb = col0,
+//   b = u offset (rows), c = partial-sum offset (doubles), ldc = number of row chunks of the R part,
+//   aux0/aux1 = offset of the front's row list.
+
+constexpr int FS_ROWS = 128;   // rows per CTA in the forward step
+constexpr int BR_ROWS = 512;   // rows per CTA in the backward R-part reduction
+
+__device__ __forceinline__ int find_task_s(const Task* __restrict__ tasks, int ntasks, int cta) {
+  int lo = 0, hi = ntasks - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (tasks[mid].tile0 <= cta)
+      lo = mid;
+    else
+      hi = mid - 1;
   }
+  return lo;
+}
+
+// x[C_J] += sum_children u_c (entries mapping into the columns), u_J = sum_children u_c (entries mapping below)
+template <int NRC>
+__global__ void __launch_bounds__(256) k_fwd_assemble(const SnodeDesc* __restrict__ sd,
+                                                      const int32_t* __restrict__ list,
+                                                      const int32_t* __restrict__ child_idx,
+                                                      const int32_t* __restrict__ relmap, double* __restrict__ x,
+                                                      int64_t ldx, double* __restrict__ uvec) {
+  const SnodeDesc D = sd[list[blockIdx.x]];
+  const int s = D.s, r = D.d - D.s;
+  const int tid = threadIdx.x;
+  double* __restrict__ uj = uvec + D.uoff * NRC;
+  for (int i = tid; i < r * NRC; i += 256) uj[i] = 0.0;
   __syncthreads();
   for (int ci = 0; ci < D.nchild; ci++) {
     const SnodeDesc C = sd[child_idx[D.child0 + ci]];
     const int rc = C.d - C.s;
     const double* __restrict__ uc = uvec + C.uoff * NRC;
     const int32_t* __restrict__ rel = relmap + C.rows_off + C.s;
-    for (int i = tid; i < rc; i += SOLVE_THREADS) {
+    for (int i = tid; i < rc; i += 256) {
       const int p = rel[i];
 #pragma unroll
-      for (int q = 0; q < NRC; q++) w[p + q * d] += uc[i + q * rc];
+      for (int q = 0; q < NRC; q++) {
+        const double v = uc[i + q * rc];
+        if (p < s)
+          x[D.col0 + p + q * ldx] += v;
+        else
+          uj[(p - s) + q * r] += v;
+      }
     }
     __syncthreads();
   }
-  for (int k0 = 0; k0 < s; k0 += 64) {
-    const int nb = min(64, s - k0);
-    for (int e = tid; e < nb * nb; e += SOLVE_THREADS) {
-      int i = e % nb, j = e / nb;
-      if (i >= j) Ld[j * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + j) * ld];
-    }
-    __syncthreads();
-    if (tid < nb) invd[tid] = 1.0 / Ld[tid * DLD + tid];
-    __syncthreads();
-    if (warp < NRC && warp < nr) {
-      double* wq = w + warp * d + k0;
-      double v0 = (lane < nb) ? wq[lane] : 0.0, v1 = (lane + 32 < nb) ? wq[lane + 32] : 0.0;
+}
+
+// Block step k of the forward solve of supernode J: every CTA solves the 64x64 diagonal block for y_k
+// (redundantly, identical arithmetic), CTA 0 publishes y_k, and each CTA updates its 128 rows below the block.
+template <int NRC>
+__global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ tasks, int ntasks,
+                                                      const double* __restrict__ F, double* __restrict__ x,
+                                                      double* __restrict__ ysol, int64_t ldx,
+                                                      double* __restrict__ uvec, int nr) {
+  __shared__ double Ld[64 * DLD];
+  __shared__ double invd[64];
+  __shared__ double yk[NRC][64];
+  const int tix = find_task_s(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int chunk = blockIdx.x - T.tile0;
+  const int d = T.M, s = T.N, ld = T.lda, col0 = T.ldb;
+  const int k0 = T.K * 64;
+  const int nb = min(64, s - k0);
+  const int r = d - s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* __restrict__ Fj = F + T.a;
+  for (int e = tid; e < nb * nb; e += FS_ROWS) {
+    int i = e % nb, j = e / nb;
+    if (i >= j) Ld[j * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + j) * ld];
+  }
+  __syncthreads();
+  if (tid < nb) invd[tid] = 1.0 / Ld[tid * DLD + tid];
+  __syncthreads();
+  if (warp < NRC) {
+    double v0 = 0.0, v1 = 0.0;
+    if (warp < nr) {
+      const double* xq = x + col0 + k0 + warp * ldx;
+      if (lane < nb) v0 = xq[lane];
+      if (lane + 32 < nb) v1 = xq[lane + 32];
       for (int c = 0; c < nb; c++) {
         double yc = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31) * invd[c];
         if (c < 32) {
@@ -89,102 +133,156 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd_level(const SnodeDesc* __
         }
         if (lane + 32 > c && lane + 32 < nb) v1 -= Ld[c * DLD + lane + 32] * yc;
       }
-      if (lane < nb) wq[lane] = v0;
-      if (lane + 32 < nb) wq[lane + 32] = v1;
     }
-    __syncthreads();
-    // rows below the block: w[row] -= sum_c F[row, k0+c] y[c]
-    for (int row = k0 + nb + tid; row < d; row += SOLVE_THREADS) {
-      double acc[NRC];
-#pragma unroll
-      for (int q = 0; q < NRC; q++) acc[q] = 0.0;
-      const double* __restrict__ fr = Fj + row + (int64_t)k0 * ld;
-      int c = 0;
-      for (; c + 8 <= nb; c += 8) {
-        double f[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) f[u] = fr[(int64_t)(c + u) * ld];
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-#pragma unroll
-          for (int q = 0; q < NRC; q++) acc[q] += f[u] * w[k0 + c + u + q * d];
-      }
-      for (; c < nb; c++) {
-        double f = fr[(int64_t)c * ld];
-#pragma unroll
-        for (int q = 0; q < NRC; q++) acc[q] += f * w[k0 + c + q * d];
-      }
-#pragma unroll
-      for (int q = 0; q < NRC; q++) w[row + q * d] -= acc[q];
+    yk[warp][lane] = v0;
+    yk[warp][lane + 32] = v1;
+    if (chunk == 0 && warp < nr) {
+      // published into a separate buffer: the other CTAs of this launch still read w_k from x
+      double* yq = ysol + col0 + k0 + warp * ldx;
+      if (lane < nb) yq[lane] = v0;
+      if (lane + 32 < nb) yq[lane + 32] = v1;
     }
-    __syncthreads();
   }
-  for (int i = tid; i < s; i += SOLVE_THREADS)
-    for (int q = 0; q < nr; q++) x[D.col0 + i + q * ldx] = w[i + q * d];
-  double* __restrict__ uj = uvec + D.uoff * NRC;
-  for (int i = tid; i < r; i += SOLVE_THREADS) {
+  __syncthreads();
+  const int row = k0 + nb + chunk * FS_ROWS + tid;
+  if (row >= d) return;
+  double acc[NRC];
 #pragma unroll
-    for (int q = 0; q < NRC; q++) uj[i + q * r] = w[s + i + q * d];
+  for (int q = 0; q < NRC; q++) acc[q] = 0.0;
+  const double* __restrict__ fr = Fj + row + (int64_t)k0 * ld;
+  int c = 0;
+  for (; c + 8 <= nb; c += 8) {
+    double f[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) f[u] = fr[(int64_t)(c + u) * ld];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int q = 0; q < NRC; q++) acc[q] += f[u] * yk[q][c + u];
+  }
+  for (; c < nb; c++) {
+    const double f = fr[(int64_t)c * ld];
+#pragma unroll
+    for (int q = 0; q < NRC; q++) acc[q] += f * yk[q][c];
+  }
+  if (row < s) {
+#pragma unroll
+    for (int q = 0; q < NRC; q++)
+      if (q < nr) x[col0 + row + q * ldx] -= acc[q];
+  } else {
+    double* __restrict__ uj = uvec + T.b * NRC;
+#pragma unroll
+    for (int q = 0; q < NRC; q++) uj[(row - s) + q * r] -= acc[q];
   }
 }
 
-// -------------------------------------------------------------------------------- backward solve ----
-// x_C = L11^{-T} (y_C - L21' x_R), x_R gathered from the already final ancestors.
+// Backward, R part: partial[chunk][c][q] = sum_{rows of the chunk} L21[row, c] * x[rows[row]][q] for the 64 columns
+// of block kb.  One CTA = 64 columns x BR_ROWS rows; fixed-order reductions (shuffle tree, then warps in order).
 template <int NRC>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_bwd_level(const SnodeDesc* __restrict__ sd,
-                                                             const int32_t* __restrict__ list,
-                                                             const int32_t* __restrict__ rows,
-                                                             const double* __restrict__ F, double* __restrict__ x,
-                                                             int64_t ldx, int nr) {
-  extern __shared__ __align__(16) double sm[];
-  double* Ld = sm;
-  double* invd = sm + 64 * DLD;
-  double* w = invd + 64;
-  const SnodeDesc D = sd[list[blockIdx.x]];
-  const int d = D.d, s = D.s, ld = D.ld;
+__global__ void __launch_bounds__(128) k_bwd_rpart(const Task* __restrict__ tasks, int ntasks,
+                                                   const double* __restrict__ F, const int32_t* __restrict__ rows,
+                                                   const double* __restrict__ x, int64_t ldx,
+                                                   double* __restrict__ partial, int nr) {
+  __shared__ double red[4][64][NRC];
+  const int tix = find_task_s(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int local = blockIdx.x - T.tile0;
+  const int d = T.M, s = T.N, ld = T.lda;
+  const int r = d - s;
+  const int nchunk = T.ldc;
+  const int kb = local / nchunk, chunk = local % nchunk;
+  const int k0 = kb * 64;
+  const int nb = min(64, s - k0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* __restrict__ Fj = F + D.foff;
-  const int32_t* __restrict__ rw = rows + D.rows_off;
-  for (int i = tid; i < d; i += SOLVE_THREADS) {
-    const int64_t g = (i < s) ? (D.col0 + i) : rw[i];
+  const double* __restrict__ Fj = F + T.a;
+  const int32_t* __restrict__ rw = rows + (((int64_t)T.aux1 << 32) | (uint32_t)T.aux0) + s;
+  // each thread owns up to BR_ROWS/128 rows of the chunk
+  constexpr int RPT = BR_ROWS / 128;
+  double xr[RPT][NRC];
+  int rloc[RPT];
 #pragma unroll
-    for (int q = 0; q < NRC; q++) w[i + q * d] = (q < nr) ? x[g + q * ldx] : 0.0;
+  for (int t = 0; t < RPT; t++) {
+    const int rr = chunk * BR_ROWS + t * 128 + tid;
+    rloc[t] = rr < r ? rr : -1;
+    const int64_t g = rr < r ? rw[rr] : 0;
+#pragma unroll
+    for (int q = 0; q < NRC; q++) xr[t][q] = (rr < r && q < nr) ? x[g + q * ldx] : 0.0;
   }
-  __syncthreads();
-  const int nblk = (s + 63) / 64;
-  for (int kb = nblk - 1; kb >= 0; kb--) {
-    const int k0 = kb * 64;
-    const int nb = min(64, s - k0);
-    for (int e = tid; e < nb * nb; e += SOLVE_THREADS) {
-      int i = e % nb, j = e / nb;
-      if (i >= j) Ld[j * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + j) * ld];
+  for (int c0 = 0; c0 < nb; c0 += 8) {
+    double acc[8][NRC];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int q = 0; q < NRC; q++) acc[u][q] = 0.0;
+#pragma unroll
+    for (int t = 0; t < RPT; t++) {
+      if (rloc[t] < 0) continue;
+      const double* __restrict__ fr = Fj + (s + rloc[t]) + (int64_t)(k0 + c0) * ld;
+      double f[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) f[u] = (c0 + u < nb) ? fr[(int64_t)u * ld] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int q = 0; q < NRC; q++) acc[u][q] += f[u] * xr[t][q];
     }
-    __syncthreads();
-    if (tid < nb) invd[tid] = 1.0 / Ld[tid * DLD + tid];
-    // t_c = w_c - sum_{row >= k0+nb} F[row, k0+c] w[row]: one warp per column, lanes stride the rows
-    for (int c = warp; c < nb; c += SOLVE_THREADS / 32) {
-      double acc[NRC];
 #pragma unroll
-      for (int q = 0; q < NRC; q++) acc[q] = 0.0;
-      const double* __restrict__ fc = Fj + (int64_t)(k0 + c) * ld;
-      for (int row = k0 + nb + lane; row < d; row += 32) {
-        double f = fc[row];
-#pragma unroll
-        for (int q = 0; q < NRC; q++) acc[q] += f * w[row + q * d];
-      }
+    for (int u = 0; u < 8; u++)
 #pragma unroll
       for (int q = 0; q < NRC; q++) {
-        double v = acc[q];
+        double v = acc[u][q];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) w[k0 + c + q * d] -= v;
+        if (lane == 0) red[warp][c0 + u][q] = v;
       }
-    }
-    __syncthreads();
-    // diagonal block: L' x = t, column-oriented elimination from the last column
-    if (warp < NRC && warp < nr) {
-      double* wq = w + warp * d + k0;
-      double v0 = (lane < nb) ? wq[lane] : 0.0, v1 = (lane + 32 < nb) ? wq[lane + 32] : 0.0;
+  }
+  __syncthreads();
+  double* __restrict__ pj = partial + T.c + (int64_t)chunk * s * NRC;
+  for (int e = tid; e < nb * NRC; e += 128) {
+    const int c = e / NRC, q = e % NRC;
+    pj[(int64_t)(k0 + c) * NRC + q] = ((red[0][c][q] + red[1][c][q]) + red[2][c][q]) + red[3][c][q];
+  }
+}
+
+// Block step k (descending) of the backward solve: t_k = x_k - sum_chunks partial - (updates already applied by
+// later blocks); solve L_kk' x_k = t_k; CTA j < k applies x[C_j] -= L[k-rows, j-cols]' x_k, CTA j == k publishes x_k.
+template <int NRC>
+__global__ void __launch_bounds__(128) k_bwd_step(const Task* __restrict__ tasks, int ntasks,
+                                                  const double* __restrict__ F, double* __restrict__ x,
+                                                  double* __restrict__ xsol, int64_t ldx,
+                                                  const double* __restrict__ partial, int nr) {
+  __shared__ double Ld[64 * DLD];
+  __shared__ double invd[64];
+  __shared__ double xk[NRC][64];
+  __shared__ double half[64][NRC];
+  const int tix = find_task_s(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int j = blockIdx.x - T.tile0;
+  const int s = T.N, ld = T.lda, col0 = T.ldb;
+  const int k = T.K, k0 = k * 64;
+  const int nb = min(64, s - k0);
+  const int nchunk = T.ldc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* __restrict__ Fj = F + T.a;
+  for (int e = tid; e < nb * nb; e += 128) {
+    int i = e % nb, jj = e / nb;
+    if (i >= jj) Ld[jj * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + jj) * ld];
+  }
+  __syncthreads();
+  if (tid < nb) invd[tid] = 1.0 / Ld[tid * DLD + tid];
+  __syncthreads();
+  if (warp < NRC) {
+    double v0 = 0.0, v1 = 0.0;
+    if (warp < nr) {
+      const double* xq = x + col0 + k0 + warp * ldx;
+      if (lane < nb) v0 = xq[lane];
+      if (lane + 32 < nb) v1 = xq[lane + 32];
+      const double* __restrict__ pj = partial + T.c;
+      for (int ch = 0; ch < nchunk; ch++) {
+        const double* pc = pj + (int64_t)ch * s * NRC;
+        if (lane < nb) v0 -= pc[(int64_t)(k0 + lane) * NRC + warp];
+        if (lane + 32 < nb) v1 -= pc[(int64_t)(k0 + lane + 32) * NRC + warp];
+      }
       for (int c = nb - 1; c >= 0; c--) {
         double xc = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31) * invd[c];
         if (c < 32) {
@@ -195,13 +293,39 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd_level(const SnodeDesc* __
         }
         if (lane < c && lane < nb) v0 -= Ld[lane * DLD + c] * xc;
       }
-      if (lane < nb) wq[lane] = v0;
-      if (lane + 32 < nb) wq[lane + 32] = v1;
     }
-    __syncthreads();
+    xk[warp][lane] = v0;
+    xk[warp][lane + 32] = v1;
+    if (j == k && warp < nr) {
+      double* xq = xsol + col0 + k0 + warp * ldx;
+      if (lane < nb) xq[lane] = v0;
+      if (lane + 32 < nb) xq[lane + 32] = v1;
+    }
   }
-  for (int i = tid; i < s; i += SOLVE_THREADS)
-    for (int q = 0; q < nr; q++) x[D.col0 + i + q * ldx] = w[i + q * d];
+  __syncthreads();
+  if (j == k) return;
+  // update block j (64 columns): thread = (column cc, row half)
+  const int cc = tid & 63, hf = tid >> 6;
+  const double* __restrict__ fc = Fj + k0 + (int64_t)(j * 64 + cc) * ld;
+  double acc[NRC];
+#pragma unroll
+  for (int q = 0; q < NRC; q++) acc[q] = 0.0;
+  const int r0 = hf * 32, r1 = min(nb, r0 + 32);
+  for (int rr = r0; rr < r1; rr++) {
+    const double f = fc[rr];
+#pragma unroll
+    for (int q = 0; q < NRC; q++) acc[q] += f * xk[q][rr];
+  }
+  if (hf == 1) {
+#pragma unroll
+    for (int q = 0; q < NRC; q++) half[cc][q] = acc[q];
+  }
+  __syncthreads();
+  if (hf == 0) {
+#pragma unroll
+    for (int q = 0; q < NRC; q++)
+      if (q < nr) x[col0 + j * 64 + cc + q * ldx] -= acc[q] + half[cc][q];
+  }
 }
 
 // --------------------------------------------------------------------------------------- SpMV/SpMM ----
@@ -337,26 +461,30 @@ cudaError_t launch_perm_scatter_nodemajor(const double* src, int64_t lds, double
   return cudaGetLastError();
 }
 
-size_t solve_smem_bytes(int maxd) { return (size_t)(64 * DLD + 64 + (size_t)maxd * SOLVE_NRC) * sizeof(double); }
+cudaError_t sparse_kernels_init() { return cudaSuccess; }
 
-cudaError_t sparse_kernels_init() {
-  cudaError_t e = cudaFuncSetAttribute(k_fwd_level<SOLVE_NRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_bwd_level<SOLVE_NRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-}
-
-cudaError_t launch_fwd_level(const SnodeDesc* sd, const int32_t* list, int count, int maxd, const int32_t* child_idx,
-                             const int32_t* relmap, const double* F, double* x, int64_t ldx, double* uvec, int nr,
-                             cudaStream_t st) {
+cudaError_t launch_fwd_assemble(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* child_idx,
+                                const int32_t* relmap, double* x, int64_t ldx, double* uvec, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  k_fwd_level<SOLVE_NRC><<<count, SOLVE_THREADS, solve_smem_bytes(maxd), st>>>(sd, list, child_idx, relmap, F, x, ldx,
-                                                                               uvec, nr);
+  k_fwd_assemble<SOLVE_NRC><<<count, 256, 0, st>>>(sd, list, child_idx, relmap, x, ldx, uvec);
   return cudaGetLastError();
 }
-cudaError_t launch_bwd_level(const SnodeDesc* sd, const int32_t* list, int count, int maxd, const int32_t* rows,
-                             const double* F, double* x, int64_t ldx, int nr, cudaStream_t st) {
-  if (count <= 0) return cudaSuccess;
-  k_bwd_level<SOLVE_NRC><<<count, SOLVE_THREADS, solve_smem_bytes(maxd), st>>>(sd, list, rows, F, x, ldx, nr);
+cudaError_t launch_fwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* w, double* ysol,
+                            int64_t ldx, double* uvec, int nr, cudaStream_t st) {
+  if (grid <= 0) return cudaSuccess;
+  k_fwd_step<SOLVE_NRC><<<grid, FS_ROWS, 0, st>>>(tasks, ntasks, F, w, ysol, ldx, uvec, nr);
+  return cudaGetLastError();
+}
+cudaError_t launch_bwd_rpart(const Task* tasks, int ntasks, int grid, const double* F, const int32_t* rows,
+                             const double* x, int64_t ldx, double* partial, int nr, cudaStream_t st) {
+  if (grid <= 0) return cudaSuccess;
+  k_bwd_rpart<SOLVE_NRC><<<grid, 128, 0, st>>>(tasks, ntasks, F, rows, x, ldx, partial, nr);
+  return cudaGetLastError();
+}
+cudaError_t launch_bwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* t, double* xsol,
+                            int64_t ldx, const double* partial, int nr, cudaStream_t st) {
+  if (grid <= 0) return cudaSuccess;
+  k_bwd_step<SOLVE_NRC><<<grid, 128, 0, st>>>(tasks, ntasks, F, t, xsol, ldx, partial, nr);
   return cudaGetLastError();
 }
 

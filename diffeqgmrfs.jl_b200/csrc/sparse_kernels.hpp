@@ -18,18 +18,23 @@ struct SnodeDesc {
 };
 
 cudaError_t sparse_kernels_init();
-size_t solve_smem_bytes(int maxd);
+constexpr int SOLVE_FS_ROWS = 128;  // rows per CTA of the forward block step
+constexpr int SOLVE_BR_ROWS = 512;  // rows per CTA of the backward R-part reduction
 cudaError_t launch_perm_gather(const double* src, int64_t lds, double* dst, int64_t ldd, const int32_t* perm,
                                int64_t n, int nrhs, cudaStream_t st);
 cudaError_t launch_perm_scatter(const double* src, int64_t lds, double* dst, int64_t ldd, const int32_t* perm,
                                 int64_t n, int nrhs, const double* add, cudaStream_t st);
 cudaError_t launch_perm_scatter_nodemajor(const double* src, int64_t lds, double* dst, int64_t ldk,
                                           const int32_t* perm, int64_t n, int k0, int nr, cudaStream_t st);
-cudaError_t launch_fwd_level(const SnodeDesc* sd, const int32_t* list, int count, int maxd, const int32_t* child_idx,
-                             const int32_t* relmap, const double* F, double* x, int64_t ldx, double* uvec, int nr,
-                             cudaStream_t st);
-cudaError_t launch_bwd_level(const SnodeDesc* sd, const int32_t* list, int count, int maxd, const int32_t* rows,
-                             const double* F, double* x, int64_t ldx, int nr, cudaStream_t st);
+struct Task;
+cudaError_t launch_fwd_assemble(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* child_idx,
+                                const int32_t* relmap, double* x, int64_t ldx, double* uvec, cudaStream_t st);
+cudaError_t launch_fwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* w, double* ysol,
+                            int64_t ldx, double* uvec, int nr, cudaStream_t st);
+cudaError_t launch_bwd_rpart(const Task* tasks, int ntasks, int grid, const double* F, const int32_t* rows,
+                             const double* x, int64_t ldx, double* partial, int nr, cudaStream_t st);
+cudaError_t launch_bwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* t, double* xsol,
+                            int64_t ldx, const double* partial, int nr, cudaStream_t st);
 cudaError_t launch_spmv_rows(int64_t nrows, const int64_t* ptr, const int32_t* idx, const double* val,
                              const double* x, double* y, double alpha, double beta, cudaStream_t st);
 cudaError_t launch_rbmc(int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, const double* X,

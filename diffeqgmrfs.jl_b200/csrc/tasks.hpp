@@ -17,6 +17,7 @@ enum : int32_t {
   TF_C_SHIFT = 4,   // bits 4-5: arena of operand c
   TF_TRI = 1 << 8,  // C is lower-trapezoidal: tiles strictly above the diagonal are skipped, diagonal tiles masked
   TF_NEG = 1 << 9,  // kind-specific: negate result
+  TF_KLOW = 1 << 10,  // GEMM with transposed A (K x M) that is lower triangular (zero for k < m): skip k < m0
 };
 
 struct alignas(16) Task {
@@ -43,6 +44,9 @@ enum LaunchKind : int32_t {
   LK_SCALE = 10,        // c (MxN, ldc) <- alpha c
   LK_DIAG_OUT = 11,     // out[aux0 + i] = c[i,i], i < M   (out = int-indexed double buffer)
   LK_SYMMETRIZE = 12,   // c (MxM): copy lower triangle to the upper
+  LK_FRONT_FACTOR_SMALL = 13,  // fused shared-memory factorisation of one small front per CTA (aux0 = supernode)
+  LK_FRONT_SELINV_SMALL = 14,  // fused shared-memory selected inversion of one small front per CTA
+  LK_GEMM_TT = 15,             // C = beta C + alpha A' B'       A: KxM, B: NxK
 };
 
 struct Launch {
@@ -51,16 +55,27 @@ struct Launch {
   int32_t grid;  // number of CTAs
   double flops;  // useful floating-point operations of this launch (0 for data-movement kernels)
   double bytes;  // algorithmic bytes of this launch (0 where not accounted)
+  int32_t smem;  // dynamic shared memory of the launch (fused small-front kernels)
 };
 
 // Profile slots for kernels that are not plan launches.
-enum : int32_t { PK_FWD_LEVEL = 20, PK_BWD_LEVEL = 21, PK_SCATTER = 22, PK_MEMSET = 23, PK_PERM = 24, PK_MAX = 32 };
+enum : int32_t {
+  PK_FWD_LEVEL = 20,
+  PK_BWD_LEVEL = 21,
+  PK_SCATTER = 22,
+  PK_MEMSET = 23,
+  PK_PERM = 24,
+  PK_FWD_ASM = 25,
+  PK_BWD_RPART = 26,
+  PK_MAX = 32
+};
 
 // GEMM tile geometry used by both the plan builder (tile counts) and the kernels.
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16;
 constexpr int NB = 64;           // panel width of the blocked POTRF/TRSM
 constexpr int TRSM_ROWS = 128;   // rows per CTA in the TRSM kernels
 constexpr int EA_TILE = 64;      // extend-add / gather tile edge
+constexpr int SMALL_FRONT_MAX = 160;  // fronts up to this order are processed by one CTA in shared memory
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // number of 128x128 tiles of an M x N result; lower-trapezoidal results skip tiles above the diagonal
