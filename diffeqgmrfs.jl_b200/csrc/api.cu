@@ -137,7 +137,7 @@ extern "C" gmrfb_status gmrfb_ctx_profile_end(gmrfb_ctx* ctx, gmrfb_profile_entr
   // GMRFB_PROFILE_DUMP=<file>: one CSV line per launch (kind, name, grid, ms, flops, bytes) for kernel tuning
   FILE* dump = nullptr;
   if (const char* path = getenv("GMRFB_PROFILE_DUMP")) {
-    dump = fopen(path, "w");
+    dump = fopen(path, "a");
     if (dump) fprintf(dump, "seq,kind,name,grid,ntasks,ms,flops,bytes\n");
   }
   int seq = 0;

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "kernels.hpp"
 #include "sparse_kernels.hpp"
@@ -44,9 +45,9 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
 // lower-triangular tile index -> (row tile, col tile)
@@ -62,18 +63,22 @@ __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
 // C = beta*C + alpha*op(A)*op(B);  all column-major.
 //   TA=false: A is M x K (m contiguous)     TA=true: A is K x M (k contiguous), used as A'
 //   TB=false: B is N x K (n contiguous), used as B'   TB=true: B is K x N (k contiguous)
-constexpr int G_STAGES = 3;
-constexpr int G_LDN = GEMM_BM + 4;  // [k][m] layout, +4 doubles: conflict-free 64-bit fragment loads
-constexpr int G_LDT = GEMM_BK + 4;  // [m][k] layout
-constexpr int G_STAGE_N = GEMM_BK * G_LDN;
-constexpr int G_STAGE_T = GEMM_BM * G_LDT;
+#ifndef GMRFB_GEMM_STAGES
+#define GMRFB_GEMM_STAGES 3
+#endif
+constexpr int G_STAGES = GMRFB_GEMM_STAGES;
+constexpr int G_LDNA = GEMM_BM + 4;  // A tile, [k][m] layout, +4 doubles: conflict-free 64-bit fragment loads
+constexpr int G_LDNB = GEMM_BN + 4;  // B tile, [k][n] layout
+constexpr int G_LDT = GEMM_BK + 4;   // [m][k] / [n][k] layouts
+constexpr int G_A_STAGE_N = GEMM_BK * G_LDNA, G_A_STAGE_T = GEMM_BM * G_LDT;
+constexpr int G_B_STAGE_N = GEMM_BK * G_LDNB, G_B_STAGE_T = GEMM_BN * G_LDT;
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
+__global__ void __launch_bounds__(256, 2) k_gemm(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
   extern __shared__ __align__(16) double smem[];
   constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-  constexpr int A_STAGE = TA ? G_STAGE_T : G_STAGE_N;
-  constexpr int B_STAGE = TB ? G_STAGE_T : G_STAGE_N;
+  constexpr int A_STAGE = TA ? G_A_STAGE_T : G_A_STAGE_N;
+  constexpr int B_STAGE = TB ? G_B_STAGE_T : G_B_STAGE_N;
   double* As = smem;
   double* Bs = smem + G_STAGES * A_STAGE;
 
@@ -84,14 +89,16 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
   const int ntn = (N + BN - 1) / BN;
   int tm, tn;
   if (T.flags & TF_TRI) {
-    const int tri = ntn * (ntn + 1) / 2;
-    if (local < tri) {
-      tri_decode(local, tm, tn);
-    } else {
-      int r = local - tri;
-      tm = ntn + r / ntn;
-      tn = r % ntn;
+    // row tile tm owns min(2*tm + 2, ntn) column tiles
+    int rem = local;
+    tm = 0;
+    for (;;) {
+      const int w = min(2 * tm + 2, ntn);
+      if (rem < w) break;
+      rem -= w;
+      tm++;
     }
+    tn = rem;
   } else {
     tm = local / ntn;
     tn = local % ntn;
@@ -102,17 +109,17 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
   double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
   const int lda = T.lda, ldb = T.ldb, ldc = T.ldc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // Interleaved ownership of the 16 x 16 grid of 8x8 MMA sub-tiles: warp (wm, wn) owns row sub-tiles im*2 + wm and
-  // column sub-tiles in*4 + wn.  Sub-tiles outside the problem (or above the diagonal of a triangular result) are
+  // Interleaved ownership of the 16 x 8 grid of 8x8 MMA sub-tiles: warp (wm, wn) owns row sub-tiles im*4 + wm and
+  // column sub-tiles in*2 + wn.  Sub-tiles outside the problem (or above the diagonal of a triangular result) are
   // skipped with warp-uniform predicates, and the interleaving keeps the remaining work balanced across warps, so
   // partially filled tiles (small fronts in a batched launch) cost only their useful 8x8 blocks of DMMA issue.
-  const int wm = warp & 1, wn = warp >> 1;
+  const int wm = warp & 3, wn = warp >> 2;
   unsigned active = 0;
 #pragma unroll
-  for (int im = 0; im < 8; im++)
+  for (int im = 0; im < 4; im++)
 #pragma unroll
     for (int in = 0; in < 4; in++) {
-      const int r0 = m0 + (im * 2 + wm) * 8, c0 = n0 + (in * 4 + wn) * 8;
+      const int r0 = m0 + (im * 4 + wm) * 8, c0 = n0 + (in * 2 + wn) * 8;
       bool on = (r0 < M) && (c0 < N);
       if ((T.flags & TF_TRI) && c0 > r0 + 7) on = false;
       if (on) active |= 1u << (im * 4 + in);
@@ -128,9 +135,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
         int m = e & (BM - 1), kk = e >> 7;
         int gm = m0 + m, gk = k0 + kk;
         bool ok = (gm < M) && (gk < K);
-        cp_async8(as + kk * G_LDN + m, ok ? A + gm + (int64_t)gk * lda : A, ok);
+        cp_async8(as + kk * G_LDNA + m, ok ? A + gm + (int64_t)gk * lda : A, ok);
       } else {
-        int kk = e & (BK - 1), m = e >> 4;
+        int kk = e & (BK - 1), m = e / BK;
         int gm = m0 + m, gk = k0 + kk;
         bool ok = (gm < M) && (gk < K);
         cp_async8(as + m * G_LDT + kk, ok ? A + gk + (int64_t)gm * lda : A, ok);
@@ -140,12 +147,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
     for (int i = 0; i < (BN * BK) / 256; i++) {
       int e = tid + i * 256;
       if (!TB) {
-        int n = e & (BN - 1), kk = e >> 7;
+        int n = e & (BN - 1), kk = e / BN;
         int gn = n0 + n, gk = k0 + kk;
         bool ok = (gn < N) && (gk < K);
-        cp_async8(bs + kk * G_LDN + n, ok ? B + gn + (int64_t)gk * ldb : B, ok);
+        cp_async8(bs + kk * G_LDNB + n, ok ? B + gn + (int64_t)gk * ldb : B, ok);
       } else {
-        int kk = e & (BK - 1), n = e >> 4;
+        int kk = e & (BK - 1), n = e / BK;
         int gn = n0 + n, gk = k0 + kk;
         bool ok = (gn < N) && (gk < K);
         cp_async8(bs + n * G_LDT + kk, ok ? B + gk + (int64_t)gn * ldb : B, ok);
@@ -153,9 +160,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
     }
   };
 
-  double acc[8][4][2];
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -167,106 +174,181 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Task* __restrict__ tasks,
     cp_async_commit();
   }
   const int lr = lane >> 2, lc = lane & 3;
-  for (int kt = kt0; kt < nkt; kt++) {
-    cp_async_wait<G_STAGES - 2>();
-    __syncthreads();
-    {
-      int nk = kt + G_STAGES - 1;
-      if (nk < nkt) load_stage(nk % G_STAGES, nk * BK);
-      cp_async_commit();
-    }
-    const double* as = As + (kt % G_STAGES) * A_STAGE;
-    const double* bs = Bs + (kt % G_STAGES) * B_STAGE;
-#pragma unroll
-    for (int kb = 0; kb < BK; kb += 4) {
-      double af[8], bf[4];
-#pragma unroll
-      for (int im = 0; im < 8; im++) {
-        const int rr = (im * 2 + wm) * 8 + lr;
-        af[im] = TA ? as[rr * G_LDT + kb + lc] : as[(kb + lc) * G_LDN + rr];
+  // Two instances of the main loop: full tiles run an unpredicated DMMA stream (no per-instruction predicate /
+  // reconvergence overhead); partially filled tiles skip inactive 8x8 sub-tiles with warp-uniform predicates.
+  auto main_loop = [&](auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    for (int kt = kt0; kt < nkt; kt++) {
+      cp_async_wait<G_STAGES - 2>();
+      __syncthreads();
+      {
+        int nk = kt + G_STAGES - 1;
+        if (nk < nkt) load_stage(nk % G_STAGES, nk * BK);
+        cp_async_commit();
       }
+      const double* as = As + (kt % G_STAGES) * A_STAGE;
+      const double* bs = Bs + (kt % G_STAGES) * B_STAGE;
 #pragma unroll
-      for (int in = 0; in < 4; in++) {
-        const int cc = (in * 4 + wn) * 8 + lr;
-        bf[in] = TB ? bs[cc * G_LDT + kb + lc] : bs[(kb + lc) * G_LDN + cc];
+      for (int kb = 0; kb < BK; kb += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int im = 0; im < 4; im++) {
+          const int rr = (im * 4 + wm) * 8 + lr;
+          af[im] = TA ? as[rr * G_LDT + kb + lc] : as[(kb + lc) * G_LDNA + rr];
+        }
+#pragma unroll
+        for (int in = 0; in < 4; in++) {
+          const int cc = (in * 2 + wn) * 8 + lr;
+          bf[in] = TB ? bs[cc * G_LDT + kb + lc] : bs[(kb + lc) * G_LDNB + cc];
+        }
+#pragma unroll
+        for (int im = 0; im < 4; im++)
+#pragma unroll
+          for (int in = 0; in < 4; in++)
+            if (FULL || (active & (1u << (im * 4 + in)))) dmma884(acc[im][in][0], acc[im][in][1], af[im], bf[in]);
       }
-#pragma unroll
-      for (int im = 0; im < 8; im++)
-#pragma unroll
-        for (int in = 0; in < 4; in++)
-          if (active & (1u << (im * 4 + in))) dmma884(acc[im][in][0], acc[im][in][1], af[im], bf[in]);
     }
-  }
+  };
+  if (active == 0xffffu)
+    main_loop(std::true_type{});
+  else
+    main_loop(std::false_type{});
   cp_async_wait<0>();
 
   const bool tri = (T.flags & TF_TRI) != 0;
   const double alpha = T.alpha, beta = T.beta;
+  // Epilogue: C = beta*C + alpha*acc.  The read-modify-write is done one row sub-tile (8 values per thread) at a
+  // time with all loads issued before the first store, so the global-load latency is paid once per group instead
+  // of once per element (the compiler cannot reorder loads across stores to the same array by itself).
 #pragma unroll
-  for (int im = 0; im < 8; im++) {
-    const int row = m0 + (im * 2 + wm) * 8 + lr;
-    if (row >= M) continue;
+  for (int im = 0; im < 4; im++) {
+    const int row = m0 + (im * 4 + wm) * 8 + lr;
+    double cv[4][2];
+    bool ok[4][2];
 #pragma unroll
-    for (int in = 0; in < 4; in++) {
-      if (!(active & (1u << (im * 4 + in)))) continue;
+    for (int in = 0; in < 4; in++)
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int col = n0 + (in * 4 + wn) * 8 + 2 * lc + h;
-        if (col < N && (!tri || row >= col)) {
-          double* p = C + row + (int64_t)col * ldc;
-          double v = alpha * acc[im][in][h];
-          if (beta != 0.0) v += beta * (*p);
-          *p = v;
-        }
+        const int col = n0 + (in * 2 + wn) * 8 + 2 * lc + h;
+        ok[in][h] = (active & (1u << (im * 4 + in))) && row < M && col < N && (!tri || row >= col);
+        cv[in][h] = 0.0;
+        if (ok[in][h] && beta != 0.0) cv[in][h] = C[row + (int64_t)col * ldc];
       }
-    }
+#pragma unroll
+    for (int in = 0; in < 4; in++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int col = n0 + (in * 2 + wn) * 8 + 2 * lc + h;
+        if (ok[in][h]) C[row + (int64_t)col * ldc] = beta * cv[in][h] + alpha * acc[im][in][h];
+      }
   }
 }
 
 // -------------------------------------------------------------------------------------------- POTRF ----
 // In-place Cholesky of an n x n (n <= 64) diagonal block; only the lower triangle is read and written.
+// The block sits in shared memory (identity padding up to 64).  Columns are processed in panels of 8: threads
+// 0..63 own one matrix row each and keep their 8 panel entries in registers (the 8x8 diagonal block is kept
+// symmetric-full so the pivot row broadcast yields l(k,c) directly), one rsqrt per column on the critical path;
+// the rank-8 trailing update then runs on all 128 threads.  Small code (no full unrolling): it has to run at
+// instruction-cache speed because it sits on the dependent chain of every blocked factorisation.
 // A non-positive or NaN pivot records (aux0 + j) in *info (minimum over all failures) and poisons the block.
 constexpr int P_LD = 65;
-__global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks, int ntasks, Arenas ar,
+__global__ void __launch_bounds__(128) k_potrf64(const Task* __restrict__ tasks, int ntasks, Arenas ar,
                                                  int* __restrict__ info) {
   __shared__ double S[64 * P_LD];
+  __shared__ double pr[8];
   const Task T = tasks[blockIdx.x];
   const int n = T.M, lda = T.lda;
   double* __restrict__ A = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
-  const int tid = threadIdx.x;
-  const int ti = tid & 63, tq = tid >> 6;  // thread = (row, column phase): no integer divisions in the hot loops
-  for (int j = tq; j < n; j += 4)
-    if (ti < n && ti >= j) S[j * P_LD + ti] = A[ti + (int64_t)j * lda];
-  for (int j = 0; j < n; j++) {
-    __syncthreads();
-    const double d = S[j * P_LD + j];
-    __syncthreads();
-    double ljj;
-    if (d > 0.0) {
-      ljj = sqrt(d);
-    } else {
-      ljj = nan("");
-      if (tid == 0) atomicMin(info, T.aux0 + j);
+  const int tid = threadIdx.x, i = tid & 63, half = tid >> 6;
+  {
+    double v[32];
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      const int k = half + 2 * u;
+      v[u] = (i == k) ? 1.0 : 0.0;
+      if (i < n && k <= i) v[u] = A[i + (int64_t)k * lda];
     }
-    const double inv = 1.0 / ljj;
-    if (tq == 0 && ti >= j && ti < n) S[j * P_LD + ti] = (ti == j) ? ljj : S[j * P_LD + ti] * inv;
-    __syncthreads();
-    if (ti < n) {
-      const double lij = S[j * P_LD + ti];
-      for (int k = j + 1 + tq; k <= ti; k += 4) S[k * P_LD + ti] -= lij * S[j * P_LD + k];
-    }
+#pragma unroll
+    for (int u = 0; u < 32; u++) S[(half + 2 * u) * P_LD + i] = v[u];
   }
   __syncthreads();
-  for (int j = tq; j < n; j += 4)
-    if (ti < n && ti >= j) A[ti + (int64_t)j * lda] = S[j * P_LD + ti];
+  bool bad = false;
+  for (int jb = 0; jb < 8; jb++) {
+    const int j0 = jb * 8;
+    if (j0 >= n) break;
+    double p[8];
+    if (half == 0) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const int col = j0 + c;
+        p[c] = (i >= col) ? S[col * P_LD + i] : S[i * P_LD + col];  // mirror inside the diagonal block / above it unused
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      if (half == 0 && i == j0 + c) {
+#pragma unroll
+        for (int c2 = c; c2 < 8; c2++) pr[c2] = p[c2];
+      }
+      __syncthreads();
+      if (half == 0) {
+        const double d = pr[c];
+        double dinv;
+        if (d > 0.0) {
+          dinv = rsqrt(d);
+        } else {
+          dinv = nan("");
+          if (i == j0 + c && j0 + c < n) bad = true;
+        }
+        const double lic = (i == j0 + c) ? d * dinv : p[c] * dinv;
+        p[c] = lic;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; c2++) p[c2] -= lic * (pr[c2] * dinv);
+      }
+      __syncthreads();
+    }
+    if (half == 0 && i >= j0) {
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        if (i >= j0 + c) S[(j0 + c) * P_LD + i] = p[c];
+    }
+    __syncthreads();
+    // rank-8 update of the trailing block: S(i,k) -= sum_c l(i,c) l(k,c), j0+8 <= k <= i; two threads per row
+    if (half == 1) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) p[c] = S[(j0 + c) * P_LD + i];
+    }
+    for (int k = j0 + 8 + half; k <= i; k += 2) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) acc += p[c] * S[(j0 + c) * P_LD + k];
+      S[k * P_LD + i] -= acc;
+    }
+    __syncthreads();
+  }
+  if (bad) atomicMin(info, T.aux0 + i);
+  {
+#pragma unroll 8
+    for (int u = 0; u < 32; u++) {
+      const int k = half + 2 * u;
+      if (i < n && k <= i) A[i + (int64_t)k * lda] = S[k * P_LD + i];
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------- TRSM ----
-// One CTA = TRSM_ROWS rows of X, one row per thread held in registers; the <=64x64 triangle sits in shared
-// memory padded to 64x64 with an identity so the substitution is fully unrolled.
+// One CTA = TRSM_ROWS rows of X, one row per thread; the <=64x64 triangle sits in shared memory padded to 64x64
+// with an identity.  The row is processed in 8-column blocks held in registers while the already solved part of
+// the row is parked in shared memory, so the code stays small (instruction-cache resident) and every inner
+// product is an unrolled 8x8 micro-kernel with broadcast reads of the triangle.
+constexpr int T_LDX = 65;
 template <bool TRANS>
 __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
-  __shared__ __align__(16) double Ls[64 * 64];
-  __shared__ double invd[64];
+  extern __shared__ __align__(16) double tsm[];
+  double* Ls = tsm;                 // 64 x 64, column-major
+  double* invd = Ls + 64 * 64;      // 64
+  double* Xs = invd + 64;           // TRSM_ROWS x T_LDX: row r of this CTA at Xs[r * T_LDX + c]
   const int tix = find_task(tasks, ntasks, blockIdx.x);
   const Task T = tasks[tix];
   const int M = T.M, N = T.N;
@@ -274,41 +356,78 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const Task* __restrict__ tas
   double* __restrict__ X = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
   const int ldl = T.ldb, ldx = T.ldc;
   const int tid = threadIdx.x;
-  for (int e = tid; e < 64 * 64; e += TRSM_ROWS) {
-    int r = e & 63, c = e >> 6;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < N && c < N && r >= c) v = L[r + (int64_t)c * ldl];
-    Ls[c * 64 + r] = v;
+  {
+    const int r = tid & 63, c0 = tid >> 6;
+    double v[32];
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      const int c = c0 + 2 * u;
+      v[u] = (r == c) ? 1.0 : 0.0;
+      if (r < N && c < N && r >= c) v[u] = L[r + (int64_t)c * ldl];
+    }
+#pragma unroll
+    for (int u = 0; u < 32; u++) Ls[(c0 + 2 * u) * 64 + r] = v[u];
+  }
+  const int row = (blockIdx.x - T.tile0) * TRSM_ROWS + tid;
+  const bool live = row < M;
+  double* xs = Xs + tid * T_LDX;
+  {
+#pragma unroll 16
+    for (int j = 0; j < 64; j++) xs[j] = (live && j < N) ? X[row + (int64_t)j * ldx] : 0.0;
   }
   __syncthreads();
   if (tid < 64) invd[tid] = 1.0 / Ls[tid * 64 + tid];
   __syncthreads();
-  const int row = (blockIdx.x - T.tile0) * TRSM_ROWS + tid;
-  if (row >= M) return;
-  double x[64];
-#pragma unroll
-  for (int j = 0; j < 64; j++) x[j] = (j < N) ? X[row + (int64_t)j * ldx] : 0.0;
   if (TRANS) {
-    // x L' = b  =>  x_j = (b_j - sum_{k<j} x_k L[j][k]) / L[j][j]; column-oriented elimination
+    // x L' = b:  blocks ascending.  x_J = (b_J - sum_{K<J} x_K L[J,K]') L[J,J]^{-T}
+    for (int jb = 0; jb < 8; jb++) {
+      const int j0 = jb * 8;
+      if (j0 >= N) break;
+      double xb[8];
 #pragma unroll
-    for (int j = 0; j < 64; j++) {
-      x[j] *= invd[j];
+      for (int c = 0; c < 8; c++) xb[c] = xs[j0 + c];
+      for (int k = 0; k < j0; k++) {
+        const double xk = xs[k];
 #pragma unroll
-      for (int k = j + 1; k < 64; k++) x[k] -= x[j] * Ls[j * 64 + k];
+        for (int c = 0; c < 8; c++) xb[c] -= xk * Ls[k * 64 + j0 + c];  // L[j0+c][k]
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        xb[c] *= invd[j0 + c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; c2++) xb[c2] -= xb[c] * Ls[(j0 + c) * 64 + j0 + c2];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) xs[j0 + c] = xb[c];
     }
   } else {
-    // x L = b   =>  x_c = (b_c - sum_{m>c} x_m L[m][c]) / L[c][c], c descending
+    // x L = b:  blocks descending.  x_J = (b_J - sum_{K>J} x_K L[K,J]) L[J,J]^{-1}
+    for (int jb = 7; jb >= 0; jb--) {
+      const int j0 = jb * 8;
+      if (j0 >= N) continue;
+      double xb[8];
 #pragma unroll
-    for (int c = 63; c >= 0; c--) {
-      x[c] *= invd[c];
+      for (int c = 0; c < 8; c++) xb[c] = xs[j0 + c];
+      for (int k = 63; k >= j0 + 8; k--) {
+        const double xk = xs[k];
 #pragma unroll
-      for (int m = 0; m < c; m++) x[m] -= x[c] * Ls[m * 64 + c];
+        for (int c = 0; c < 8; c++) xb[c] -= xk * Ls[(j0 + c) * 64 + k];  // L[k][j0+c]
+      }
+#pragma unroll
+      for (int c = 7; c >= 0; c--) {
+        xb[c] *= invd[j0 + c];
+#pragma unroll
+        for (int c2 = 0; c2 < c; c2++) xb[c2] -= xb[c] * Ls[(j0 + c2) * 64 + j0 + c];  // L[j0+c][j0+c2]
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) xs[j0 + c] = xb[c];
     }
   }
+  if (!live) return;
   const double sgn = (T.flags & TF_NEG) ? -1.0 : 1.0;
-#pragma unroll
+#pragma unroll 16
   for (int j = 0; j < 64; j++)
-    if (j < N) X[row + (int64_t)j * ldx] = sgn * x[j];
+    if (j < N) X[row + (int64_t)j * ldx] = sgn * xs[j];
 }
 
 // ------------------------------------------------------------------------------ multifrontal assembly ----
@@ -588,8 +707,9 @@ __global__ void k_scatter_values(const double* __restrict__ nzval, const int64_t
 }
 
 // ---------------------------------------------------------------------------------- host launchers ----
+static size_t trsm_smem() { return (size_t)(64 * 64 + 64 + TRSM_ROWS * T_LDX) * sizeof(double); }
 static size_t gemm_smem(bool ta, bool tb) {
-  size_t a = ta ? G_STAGE_T : G_STAGE_N, b = tb ? G_STAGE_T : G_STAGE_N;
+  size_t a = ta ? G_A_STAGE_T : G_A_STAGE_N, b = tb ? G_B_STAGE_T : G_B_STAGE_N;
   return (a + b) * G_STAGES * sizeof(double);
 }
 
@@ -606,6 +726,10 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)gemm_smem(true, false));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_trsm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_trsm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem());
   if (e != cudaSuccess) return e;
   const int small_smem = SMALL_FRONT_MAX * (SMALL_FRONT_MAX | 1) * (int)sizeof(double);
   e = cudaFuncSetAttribute(k_front_factor_small, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
@@ -632,13 +756,13 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       k_gemm<true, false><<<L.grid, 256, gemm_smem(true, false), st>>>(t, L.ntasks, ar);
       break;
     case LK_POTRF:
-      k_potrf64<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_info);
+      k_potrf64<<<L.grid, 128, 0, st>>>(t, L.ntasks, ar, aux.d_info);
       break;
     case LK_TRSM_RLT:
-      k_trsm<true><<<L.grid, TRSM_ROWS, 0, st>>>(t, L.ntasks, ar);
+      k_trsm<true><<<L.grid, TRSM_ROWS, trsm_smem(), st>>>(t, L.ntasks, ar);
       break;
     case LK_TRSM_RLN:
-      k_trsm<false><<<L.grid, TRSM_ROWS, 0, st>>>(t, L.ntasks, ar);
+      k_trsm<false><<<L.grid, TRSM_ROWS, trsm_smem(), st>>>(t, L.ntasks, ar);
       break;
     case LK_EXTEND_ADD:
       k_extend_add<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_relmap);

@@ -10,6 +10,10 @@ namespace gmrfb {
 
 namespace {
 
+// outer panel width of the two-level blocked POTRF/TRSM: wide enough that the left-looking GEMMs of a large
+// problem span a full wave of CTAs, narrow enough that small problems still advance in few launches
+inline int pick_nbo(int max_n) { return max_n <= 512 ? 128 : max_n <= 1536 ? 256 : 512; }
+
 inline int32_t arena_flags(int a, int b, int c) { return (a << TF_A_SHIFT) | (b << TF_B_SHIFT) | (c << TF_C_SHIFT); }
 
 double gemm_flops(int M, int N, int K, bool tri) {
@@ -68,6 +72,7 @@ struct FactorProb {
 static void plan_partial_factor_batch(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int nbo) {
   int max_s = 0;
   for (auto& p : probs) max_s = std::max(max_s, p.s);
+  if (nbo <= 0) nbo = pick_nbo(max_s);
   for (int j0 = 0; j0 < max_s; j0 += nbo) {
     for (int jj = j0; jj < std::min(j0 + nbo, max_s); jj += NB) {
       B.begin(LK_POTRF);
@@ -144,6 +149,7 @@ static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>
   int max_n = 0;
   for (auto& p : probs) max_n = std::max(max_n, p.n);
   if (max_n == 0) return;
+  if (nbo <= 0) nbo = pick_nbo(max_n);
   if (trans) {
     // ascending: X_J = (B_J - X_{<J} L[J,<J]') L_JJ^{-T}
     for (int o0 = 0; o0 < max_n; o0 += nbo) {
@@ -220,21 +226,67 @@ static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>
   }
 }
 
-constexpr int NBO = 128;
+
+
+// ---------------------------------------------------------------------- triangular inverse batch ----
+// W = L^{-1} (n x n lower) by recursive doubling: invert the 64x64 diagonal blocks, then merge neighbouring
+// inverted blocks  inv([A 0; B C]) = [A^{-1} 0; -C^{-1} B A^{-1}  C^{-1}]  level by level.  Every level is two
+// batched GEMM launches over all merges of all problems, so the dependent chain is 1 + 2 log2(n/64) launches
+// instead of ~3 n/64 for a substitution sweep.  W must be pre-set to the identity (zero strict upper triangle).
+struct TrtriProb {
+  int arenaL;
+  int64_t loff;
+  int ldl;
+  int arenaW;   // W and the scratch T live in the same arena
+  int64_t woff, toff;
+  int ldw;
+  int n;
+};
+
+static void plan_trtri_batch(PlanBuilder& B, Plan& P, const std::vector<TrtriProb>& probs) {
+  int max_n = 0;
+  for (auto& p : probs) max_n = std::max(max_n, p.n);
+  B.begin(LK_TRSM_RLN);
+  for (auto& p : probs)
+    for (int jj = 0; jj < p.n; jj += NB) {
+      int nb = std::min(NB, p.n - jj);
+      add_trsm(B, P, p.arenaL, p.loff + (int64_t)jj * p.ldl + jj, p.ldl, p.arenaW, p.woff + (int64_t)jj * p.ldw + jj,
+               p.ldw, nb, nb);
+    }
+  B.end();
+  for (int h = NB; h < max_n; h *= 2) {
+    B.begin(LK_GEMM_NN);  // T = B A^{-1}
+    for (auto& p : probs)
+      for (int j0 = 0; j0 + h < p.n; j0 += 2 * h) {
+        int j1 = j0 + h, hc = std::min(h, p.n - j1);
+        add_gemm(B, P, p.arenaL, p.loff + (int64_t)j0 * p.ldl + j1, p.ldl, p.arenaW, p.woff + (int64_t)j0 * p.ldw + j0,
+                 p.ldw, p.arenaW, p.toff + (int64_t)j0 * p.ldw + j1, p.ldw, hc, h, h, false, 1.0, 0.0);
+      }
+    B.end();
+    B.begin(LK_GEMM_NN);  // W_BA = -C^{-1} T
+    for (auto& p : probs)
+      for (int j0 = 0; j0 + h < p.n; j0 += 2 * h) {
+        int j1 = j0 + h, hc = std::min(h, p.n - j1);
+        add_gemm(B, P, p.arenaW, p.woff + (int64_t)j1 * p.ldw + j1, p.ldw, p.arenaW, p.toff + (int64_t)j0 * p.ldw + j1,
+                 p.ldw, p.arenaW, p.woff + (int64_t)j0 * p.ldw + j1, p.ldw, hc, h, hc, false, -1.0, 0.0);
+      }
+    B.end();
+  }
+}
 
 void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0) {
   std::vector<FactorProb> v{{arena, off, ld, n, n, col0}};
-  plan_partial_factor_batch(B, P, v, NBO);
+  plan_partial_factor_batch(B, P, v, 0);
 }
 void plan_trsm_rlt(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
                    int n, int ldx) {
   std::vector<TrsmProb> v{{arenaL, loff, ldl, arenaX, xoff, ldx, M, n}};
-  plan_trsm_batch(B, P, v, true, NBO);
+  plan_trsm_batch(B, P, v, true, 0);
 }
 void plan_trsm_rln(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
                    int n, int ldx, bool negate) {
   std::vector<TrsmProb> v{{arenaL, loff, ldl, arenaX, xoff, ldx, M, n}};
-  plan_trsm_batch(B, P, v, false, NBO);
+  plan_trsm_batch(B, P, v, false, 0);
   if (negate) {
     B.begin(LK_SCALE);
     Task t = make_task();
@@ -313,7 +365,7 @@ void build_factor_plan(const Symbolic& S, Plan& P) {
     std::vector<FactorProb> probs;
     probs.reserve(sn.size());
     for (int32_t s : sn) probs.push_back({AR_FRONT, S.foff[s], S.ld[s], S.front_order(s), S.ncols(s), S.sptr[s]});
-    plan_partial_factor_batch(B, P, probs, NBO);
+    plan_partial_factor_batch(B, P, probs, 0);
   }
 }
 
@@ -362,7 +414,7 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
     //   Z_CC = W'W - Y' Z_RC         (s x s, lower triangle)
     // W is used for the variances only (never for the factor or the solves), where its conditioning-dependent
     // error (~cond(L11) eps) is far inside the 1e-8 tolerance and cannot propagate to posterior means.
-    std::vector<int64_t> woff(sn.size());
+    std::vector<int64_t> woff(sn.size()), toff(sn.size());
     std::vector<int> ldw(sn.size());
     {
       int64_t off = 0;
@@ -370,6 +422,9 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
         int sc = S.ncols(sn[i]);
         ldw[i] = (sc + 1) & ~1;
         woff[i] = off;
+        off += (int64_t)ldw[i] * sc;
+        off = (off + 15) & ~(int64_t)15;
+        toff[i] = off;
         off += (int64_t)ldw[i] * sc;
         off = (off + 15) & ~(int64_t)15;
       }
@@ -408,12 +463,12 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
     }
     B.end();
     {
-      std::vector<TrsmProb> tp;
+      std::vector<TrtriProb> tp;
       for (size_t i = 0; i < sn.size(); i++) {
         int32_t s = sn[i];
-        tp.push_back({AR_FRONT, S.foff[s], S.ld[s], AR_WORK, woff[i], ldw[i], S.ncols(s), S.ncols(s)});
+        tp.push_back({AR_FRONT, S.foff[s], S.ld[s], AR_WORK, woff[i], toff[i], ldw[i], S.ncols(s)});
       }
-      plan_trsm_batch(B, P, tp, false, NBO);
+      plan_trtri_batch(B, P, tp);
     }
     B.begin(LK_GEMM_TT);  // Y' = W' L21'
     for (size_t i = 0; i < sn.size(); i++) {

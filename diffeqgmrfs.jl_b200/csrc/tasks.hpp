@@ -71,19 +71,23 @@ enum : int32_t {
 };
 
 // GEMM tile geometry used by both the plan builder (tile counts) and the kernels.
-constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16;
+#ifndef GMRFB_GEMM_BK
+#define GMRFB_GEMM_BK 16
+#endif
+constexpr int GEMM_BM = 128, GEMM_BN = 64, GEMM_BK = GMRFB_GEMM_BK;
 constexpr int NB = 64;           // panel width of the blocked POTRF/TRSM
 constexpr int TRSM_ROWS = 128;   // rows per CTA in the TRSM kernels
 constexpr int EA_TILE = 64;      // extend-add / gather tile edge
 constexpr int SMALL_FRONT_MAX = 160;  // fronts up to this order are processed by one CTA in shared memory
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-// number of 128x128 tiles of an M x N result; lower-trapezoidal results skip tiles above the diagonal
+// number of 128x64 tiles of an M x N result; lower-trapezoidal results skip tiles entirely above the diagonal
+// (tile (tm, tn) is needed iff its first column tn*64 <= last row tm*128+127, i.e. tn <= 2*tm + 1)
 inline int gemm_tiles(int M, int N, bool tri) {
   int tm = cdiv(M, GEMM_BM), tn = cdiv(N, GEMM_BN);
   if (!tri) return tm * tn;
   int t = 0;
-  for (int i = 0; i < tm; i++) t += (i + 1 < tn ? i + 1 : tn);
+  for (int i = 0; i < tm; i++) t += (2 * i + 2 < tn ? 2 * i + 2 : tn);
   return t;
 }
 
