@@ -6,7 +6,7 @@ dense block-tridiagonal Cholesky, as CUDA kernels behind the C ABI of include/gm
 reference's blueprint/GMRF interface on top of it; `workloads.py` generates the synthetic configurations.
 There is no CPU fallback: importing works anywhere, but every numeric call needs the built library and a GPU.
 """
-from . import _lib, workloads  # noqa: F401
+from . import _lib, dist, workloads  # noqa: F401
 from .solver import (  # noqa: F401
     CholeskyFactor, CholeskySolverBlueprint, Context, GMRF, GNCholeskySolverBlueprint, GaussNewtonOptimizer,
     PosteriorPrecision, RBMCStrategy, SparseMatrix, Symbolic, TakahashiStrategy, TridiagonalCholeskyFactor,

@@ -110,6 +110,15 @@ SIGNATURES = {
     "gmrfb_btd_logdet": (C.c_int32, [_P, _F64P]),
     "gmrfb_btd_selinv_diag": (C.c_int32, [_P, _F64P]),
     "gmrfb_btd_get_info": (C.c_int32, [_P, C.POINTER(BtdInfo)]),
+    "gmrfb_btd_dist_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _F64P, _F64P, C.POINTER(_P)]),
+    "gmrfb_btd_dist_iface_count": (C.c_int64, [_P]),
+    "gmrfb_btd_dist_get_iface": (C.c_int32, [_P, _P]),
+    "gmrfb_btd_dist_reduce": (C.c_int32, [_P, _P]),
+    "gmrfb_btd_dist_solve_count": (C.c_int64, [_P, C.c_int64]),
+    "gmrfb_btd_dist_solve_begin": (C.c_int32, [_P, _F64P, C.c_int64, C.c_int64, _P]),
+    "gmrfb_btd_dist_solve_end": (C.c_int32, [_P, _P, _F64P, C.c_int64, C.c_int64]),
+    "gmrfb_btd_dist_logdet": (C.c_int32, [_P, _F64P, _F64P]),
+    "gmrfb_btd_dist_destroy": (C.c_int32, [_P]),
 }
 
 _lib = None

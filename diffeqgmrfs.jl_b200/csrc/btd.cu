@@ -360,6 +360,41 @@ static gmrfb_status btd_build_solve_plans(gmrfb_btd* f, int nrhs, int ldr) {
   return GMRFB_OK;
 }
 
+// Run the forward and/or backward block sweeps of factor `f` on a device node-major buffer dXt (nrhs x b*N).
+static gmrfb_status btd_sweep(gmrfb_btd* f, bool fwd, bool bwd, double* dXt, int ldr, int nrhs) {
+  gmrfb_ctx* ctx = f->ctx;
+  gmrfb_status rc = btd_build_solve_plans(f, nrhs, ldr);
+  if (rc != GMRFB_OK) return rc;
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  const int64_t xstep = (int64_t)ldr * f->b;
+  if (fwd) {
+    for (int64_t i = 0; i < f->N; i++) {
+      Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, nullptr, nullptr}};
+      rc = run_plan(ctx, i == 0 ? f->fwd_first : f->fwd_step, ar, aux);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  if (bwd) {
+    for (int64_t i = f->N - 1; i >= 0; i--) {
+      Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, nullptr, nullptr}};
+      rc = run_plan(ctx, i == f->N - 1 ? f->bwd_last : f->bwd_step, ar, aux);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  return GMRFB_OK;
+}
+
+static gmrfb_status transpose_dev(gmrfb_ctx* ctx, const double* in, int64_t ldi, double* out, int64_t ldo, int64_t rows,
+                                  int64_t cols) {
+  dim3 tb(32, 8);
+  k_transpose_rect<<<dim3((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), tb, 0, ctx->stream>>>(in, ldi, out, ldo,
+                                                                                                          rows, cols);
+  GMRFB_CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  return GMRFB_OK;
+}
+
 extern "C" gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, int64_t ldx, int64_t nrhs) {
   if (!f || !X) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_solve: NULL argument");
   gmrfb_ctx* ctx = f->ctx;
@@ -369,37 +404,17 @@ extern "C" gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, i
   if (mode < GMRFB_BTD_SOLVE_A || mode > GMRFB_BTD_SOLVE_BWD) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_solve: bad mode");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   const int ldr = (int)((nrhs + 1) & ~(int64_t)1);
-  gmrfb_status rc = btd_build_solve_plans(f, (int)nrhs, ldr);
-  if (rc != GMRFB_OK) return rc;
   DevBuf<double> dX, dXt;
   GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs)));
   GMRFB_CU(ctx, dXt.alloc((size_t)((int64_t)ldr * n)));
   GMRFB_CU(ctx, cudaMemcpy2DAsync(dX.p, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), nrhs,
                                   cudaMemcpyHostToDevice, ctx->stream));
-  dim3 tb(32, 8);
-  k_transpose_rect<<<dim3((unsigned)((n + 31) / 32), (unsigned)((nrhs + 31) / 32)), tb, 0, ctx->stream>>>(dX.p, n, dXt.p, ldr, n, nrhs);
-  GMRFB_CU(ctx, cudaGetLastError());
-  ctx->launches++;
-  LaunchAux aux;
-  aux.d_info = ctx->d_info;
-  const int64_t xstep = (int64_t)ldr * f->b;
-  if (mode == GMRFB_BTD_SOLVE_A || mode == GMRFB_BTD_SOLVE_FWD) {
-    for (int64_t i = 0; i < f->N; i++) {
-      Arenas ar{{f->arena.p + i * f->slot, dXt.p + i * xstep, nullptr, nullptr}};
-      rc = run_plan(ctx, i == 0 ? f->fwd_first : f->fwd_step, ar, aux);
-      if (rc != GMRFB_OK) return rc;
-    }
-  }
-  if (mode == GMRFB_BTD_SOLVE_A || mode == GMRFB_BTD_SOLVE_BWD) {
-    for (int64_t i = f->N - 1; i >= 0; i--) {
-      Arenas ar{{f->arena.p + i * f->slot, dXt.p + i * xstep, nullptr, nullptr}};
-      rc = run_plan(ctx, i == f->N - 1 ? f->bwd_last : f->bwd_step, ar, aux);
-      if (rc != GMRFB_OK) return rc;
-    }
-  }
-  k_transpose_rect<<<dim3((unsigned)((nrhs + 31) / 32), (unsigned)((n + 31) / 32)), tb, 0, ctx->stream>>>(dXt.p, ldr, dX.p, n, nrhs, n);
-  GMRFB_CU(ctx, cudaGetLastError());
-  ctx->launches++;
+  gmrfb_status rc = transpose_dev(ctx, dX.p, n, dXt.p, ldr, n, nrhs);
+  if (rc != GMRFB_OK) return rc;
+  rc = btd_sweep(f, mode != GMRFB_BTD_SOLVE_BWD, mode != GMRFB_BTD_SOLVE_FWD, dXt.p, ldr, (int)nrhs);
+  if (rc != GMRFB_OK) return rc;
+  rc = transpose_dev(ctx, dXt.p, ldr, dX.p, n, nrhs, n);
+  if (rc != GMRFB_OK) return rc;
   GMRFB_CU(ctx, cudaMemcpy2DAsync(X, ldx * sizeof(double), dX.p, n * sizeof(double), n * sizeof(double), nrhs,
                                   cudaMemcpyDeviceToHost, ctx->stream));
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -508,5 +523,348 @@ extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
   }
   GMRFB_CU(ctx, cudaMemcpyAsync(var_out, dvar.p, f->b * f->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+// ======================================================================= time-sharded block tridiagonal ====
+// Rank r owns a contiguous slab of blocks.  Ranks 0..P-2 treat their last block as a *separator*; all other blocks
+// are interior.  With separators ordered last, the Cholesky factor is
+//      [ L_II        ]      L_II  = block-diagonal of the per-rank interior block-tridiagonal factors,
+//      [ L_SI   L_SS ]      L_SI  = A_SI L_II^{-T}: per rank one dense block V (own separator x last interior block)
+// and a *spike* W (previous rank's separator x every interior block), and L_SS L_SS' = S_hat, the (P-1)-block
+// tridiagonal Schur complement.  The only inter-rank exchange is an all-gather of three b x b blocks per rank
+// (factor) and two b x nrhs panels per rank (solve); it is performed by the host (torch.distributed / NCCL).
+struct gmrfb_btd_dist {
+  gmrfb_ctx* ctx = nullptr;
+  int rank = 0, P = 1;
+  int64_t b = 0, nloc = 0, ni = 0;  // ni = interior blocks
+  bool has_sep = false, has_spike = false;
+  int ld = 0;
+  gmrfb_btd* interior = nullptr;
+  gmrfb_btd* reduced = nullptr;
+  DevBuf<double> W;      // ni blocks of b x ld (spike), block i at W + i*ld*b
+  DevBuf<double> V;      // b x ld
+  DevBuf<double> iface;  // 3 blocks of b x b (ld = b): [Dsep - VV', Q, R]
+  DevBuf<double> Xt, Sx; // solve state: local node-major rhs; separator solutions
+  int solve_nrhs = 0, solve_ldr = 0;
+  bool reduced_ready = false;
+};
+
+namespace {
+
+// dst (b x b, ldd) = alpha * x (ldx) + beta * y (ldy)  (y may be NULL)
+__global__ void k_block_axpby(int64_t b, double alpha, const double* __restrict__ x, int64_t ldx, double beta,
+                              const double* __restrict__ y, int64_t ldy, double* __restrict__ dst, int64_t ldd) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b * b) return;
+  int64_t i = e % b, j = e / b;
+  double v = alpha * x[i + j * ldx];
+  if (y) v += beta * y[i + j * ldy];
+  dst[i + j * ldd] = v;
+}
+
+gmrfb_status block_axpby(gmrfb_ctx* ctx, int64_t b, double alpha, const double* x, int64_t ldx, double beta,
+                         const double* y, int64_t ldy, double* dst, int64_t ldd) {
+  k_block_axpby<<<(unsigned)((b * b + 255) / 256), 256, 0, ctx->stream>>>(b, alpha, x, ldx, beta, y, ldy, dst, ldd);
+  GMRFB_CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  return GMRFB_OK;
+}
+
+// one-off GEMM through the tile engine: C = beta C + alpha op(A) op(B), pointers given directly
+gmrfb_status gemm_once(gmrfb_ctx* ctx, int kind, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                       int M, int N, int K, bool tri, double alpha, double beta) {
+  Task t = make_task();
+  t.a = t.b = t.c = 0;
+  t.lda = lda;
+  t.ldb = ldb;
+  t.ldc = ldc;
+  t.M = M;
+  t.N = N;
+  t.K = K;
+  t.alpha = alpha;
+  t.beta = beta;
+  t.tile0 = 0;
+  t.flags = (0 << TF_A_SHIFT) | (1 << TF_B_SHIFT) | (2 << TF_C_SHIFT) | (tri ? TF_TRI : 0);
+  DevBuf<Task> dt;
+  std::vector<Task> ht{t};
+  GMRFB_CU(ctx, dt.upload(ht, ctx->stream));
+  Launch L{};
+  L.kind = kind;
+  L.task0 = 0;
+  L.ntasks = 1;
+  L.grid = gemm_tiles(M, N, tri);
+  Arenas ar{{const_cast<double*>(A), const_cast<double*>(B), C, nullptr}};
+  LaunchAux aux;
+  GMRFB_CU(ctx, run_launch(L, dt.p, ar, aux, ctx->stream));
+  ctx->launches++;
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // dt is released on return
+  return GMRFB_OK;
+}
+
+// X (M x b, ldx) <- X L^{-T} or X L^{-1} with the b x b factor L (ldl), blocked plan executed once
+gmrfb_status trsm_once(gmrfb_ctx* ctx, bool trans, const double* L, int ldl, double* X, int ldx, int M, int b) {
+  DevPlan P;
+  {
+    PlanBuilder B(P.host);
+    if (trans)
+      plan_trsm_rlt(B, P.host, 0, 0, ldl, 1, 0, M, b, ldx);
+    else
+      plan_trsm_rln(B, P.host, 0, 0, ldl, 1, 0, M, b, ldx, false);
+  }
+  GMRFB_CU(ctx, P.tasks.upload(P.host.tasks, ctx->stream));
+  Arenas ar{{const_cast<double*>(L), X, nullptr, nullptr}};
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  gmrfb_status rc = run_plan(ctx, P, ar, aux);
+  if (rc != GMRFB_OK) return rc;
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+}  // namespace
+
+extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int32_t nranks, int64_t b, int64_t nloc,
+                                              const double* D_local, const double* B_local, gmrfb_btd_dist** out) {
+  if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_create: ctx is NULL");
+  if (!out || !D_local || !B_local || rank < 0 || nranks < 1 || rank >= nranks || b <= 0)
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_dist_create: bad argument");
+  const bool has_sep = rank < nranks - 1;
+  if (nloc < (has_sep ? 2 : 1))
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_dist_create: every rank but the last needs at least 2 blocks");
+  *out = nullptr;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<gmrfb_btd_dist> h(new gmrfb_btd_dist());
+  h->ctx = ctx;
+  h->rank = rank;
+  h->P = nranks;
+  h->b = b;
+  h->nloc = nloc;
+  h->has_sep = has_sep;
+  h->has_spike = rank > 0;
+  h->ni = has_sep ? nloc - 1 : nloc;
+  // interior factor (blocks 0..ni-1); couplings inside the interior are B_local[:,:,1..ni-1]
+  gmrfb_status rc = gmrfb_btd_factor_dense(ctx, b, h->ni, D_local, h->ni > 1 ? B_local + b * b : nullptr, &h->interior);
+  if (rc != GMRFB_OK) {
+    if (h->interior) gmrfb_btd_destroy(h->interior);
+    return rc;
+  }
+  gmrfb_btd* F = h->interior;
+  const int ld = F->ld;
+  h->ld = ld;
+  const int64_t bs = (int64_t)ld * b;
+  const int ib = (int)b;
+  GMRFB_CU(ctx, h->iface.alloc((size_t)(3 * b * b)));
+  GMRFB_CU(ctx, cudaMemsetAsync(h->iface.p, 0, 3 * b * b * sizeof(double), ctx->stream));
+  DevBuf<double> tmp;
+  GMRFB_CU(ctx, tmp.alloc((size_t)bs));
+  if (h->has_spike) {
+    GMRFB_CU(ctx, h->W.alloc((size_t)(bs * h->ni)));
+    // W_1 = E_l' L_1^{-T},  E_l = B_local[:,:,0] (rows: first interior block, cols: previous separator)
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(tmp.p, ld * sizeof(double), B_local, b * sizeof(double), b * sizeof(double), b,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    rc = transpose_dev(ctx, tmp.p, ld, h->W.p, ld, b, b);
+    if (rc != GMRFB_OK) return rc;
+    rc = trsm_once(ctx, true, F->arena.p, ld, h->W.p, ld, ib, ib);
+    if (rc != GMRFB_OK) return rc;
+    for (int64_t i = 1; i < h->ni; i++) {
+      // W_i = -W_{i-1} C_i' ; W_i <- W_i L_i^{-T}
+      const double* Ci = F->arena.p + i * F->slot + bs;
+      rc = gemm_once(ctx, LK_GEMM_NT, h->W.p + (i - 1) * bs, ld, Ci, ld, h->W.p + i * bs, ld, ib, ib, ib, false, -1.0, 0.0);
+      if (rc != GMRFB_OK) return rc;
+      rc = trsm_once(ctx, true, F->arena.p + i * F->slot, ld, h->W.p + i * bs, ld, ib, ib);
+      if (rc != GMRFB_OK) return rc;
+    }
+    // Q = sum_i W_i W_i'  (lower triangle)
+    for (int64_t i = 0; i < h->ni; i++) {
+      rc = gemm_once(ctx, LK_GEMM_NT, h->W.p + i * bs, ld, h->W.p + i * bs, ld, h->iface.p + b * b, ib, ib, ib, ib, true, 1.0,
+                     i == 0 ? 0.0 : 1.0);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  if (h->has_sep) {
+    GMRFB_CU(ctx, h->V.alloc((size_t)bs));
+    // V = E_r L_ni^{-T},  E_r = B_local[:,:,nloc-1] (rows: separator, cols: last interior block)
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(h->V.p, ld * sizeof(double), B_local + (nloc - 1) * b * b, b * sizeof(double),
+                                    b * sizeof(double), b, cudaMemcpyHostToDevice, ctx->stream));
+    rc = trsm_once(ctx, true, F->arena.p + (h->ni - 1) * F->slot, ld, h->V.p, ld, ib, ib);
+    if (rc != GMRFB_OK) return rc;
+    // iface0 = D_sep - V V'
+    GMRFB_CU(ctx, cudaMemcpyAsync(h->iface.p, D_local + (nloc - 1) * b * b, b * b * sizeof(double), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    rc = gemm_once(ctx, LK_GEMM_NT, h->V.p, ld, h->V.p, ld, h->iface.p, ib, ib, ib, ib, true, -1.0, 1.0);
+    if (rc != GMRFB_OK) return rc;
+    if (h->has_spike) {
+      // R = V W_ni'  (block (S_r, S_{r-1}) of L_SI L_SI')
+      rc = gemm_once(ctx, LK_GEMM_NT, h->V.p, ld, h->W.p + (h->ni - 1) * bs, ld, h->iface.p + 2 * b * b, ib, ib, ib, ib, false,
+                     1.0, 0.0);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = h.release();
+  return GMRFB_OK;
+}
+
+extern "C" int64_t gmrfb_btd_dist_iface_count(const gmrfb_btd_dist* h) { return h ? 3 * h->b * h->b : 0; }
+
+extern "C" gmrfb_status gmrfb_btd_dist_get_iface(gmrfb_btd_dist* h, double* d_out) {
+  if (!h || !d_out) return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_get_iface: NULL argument");
+  GMRFB_CU(h->ctx, cudaSetDevice(h->ctx->device));
+  GMRFB_CU(h->ctx, cudaMemcpyAsync(d_out, h->iface.p, 3 * h->b * h->b * sizeof(double), cudaMemcpyDeviceToDevice,
+                                   h->ctx->stream));
+  GMRFB_CU(h->ctx, cudaStreamSynchronize(h->ctx->stream));
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_btd_dist_reduce(gmrfb_btd_dist* h, const double* d_all) {
+  if (!h || (h->P > 1 && !d_all)) return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_reduce: NULL argument");
+  gmrfb_ctx* ctx = h->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  if (h->P == 1) {
+    h->reduced_ready = true;
+    return GMRFB_OK;
+  }
+  const int64_t b = h->b, nb = h->P - 1, cnt = 3 * b * b;
+  std::unique_ptr<gmrfb_btd> R;
+  gmrfb_status rc = btd_alloc(ctx, b, nb, R);
+  if (rc != GMRFB_OK) return rc;
+  GMRFB_CU(ctx, cudaMemsetAsync(R->arena.p, 0, R->arena.n * sizeof(double), ctx->stream));
+  for (int64_t r = 0; r < nb; r++) {
+    // D_hat_r = iface0_r - Q_{r+1};   B_hat_r = -R_r (coupling with separator r-1)
+    rc = block_axpby(ctx, b, 1.0, d_all + r * cnt, b, -1.0, d_all + (r + 1) * cnt + b * b, b, R->arena.p + r * R->slot, R->ld);
+    if (rc != GMRFB_OK) return rc;
+    if (r > 0) {
+      rc = block_axpby(ctx, b, -1.0, d_all + r * cnt + 2 * b * b, b, 0.0, nullptr, 0,
+                       R->arena.p + r * R->slot + (int64_t)R->ld * b, R->ld);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  rc = btd_run_factor(R.get());
+  if (rc != GMRFB_OK) return rc;
+  if (h->reduced) gmrfb_btd_destroy(h->reduced);
+  h->reduced = R.release();
+  h->reduced_ready = true;
+  return GMRFB_OK;
+}
+
+extern "C" int64_t gmrfb_btd_dist_solve_count(const gmrfb_btd_dist* h, int64_t nrhs) {
+  if (!h) return 0;
+  const int64_t ldr = (nrhs + 1) & ~(int64_t)1;
+  return 2 * ldr * h->b;
+}
+
+// Phase 1: local forward elimination; d_send (device) receives [ (b_S - V y_last)' | (sum_i W_i y_i)' ], each ldr x b.
+extern "C" gmrfb_status gmrfb_btd_dist_solve_begin(gmrfb_btd_dist* h, const double* X_local, int64_t ldx, int64_t nrhs,
+                                                   double* d_send) {
+  if (!h || !X_local || (h->P > 1 && !d_send))
+    return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_solve_begin: NULL argument");
+  gmrfb_ctx* ctx = h->ctx;
+  if (!h->reduced_ready) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_dist_solve_begin: call gmrfb_btd_dist_reduce first");
+  const int64_t b = h->b, n = b * h->nloc;
+  if (ldx < n || nrhs <= 0 || nrhs > 4096) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_dist_solve_begin: bad ldx/nrhs");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int ldr = (int)((nrhs + 1) & ~(int64_t)1);
+  const int inr = (int)nrhs, ib = (int)b;
+  h->solve_nrhs = inr;
+  h->solve_ldr = ldr;
+  DevBuf<double> dX;
+  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs)));
+  GMRFB_CU(ctx, h->Xt.alloc((size_t)((int64_t)ldr * n)));
+  GMRFB_CU(ctx, cudaMemsetAsync(h->Xt.p, 0, h->Xt.n * sizeof(double), ctx->stream));
+  GMRFB_CU(ctx, cudaMemcpy2DAsync(dX.p, n * sizeof(double), X_local, ldx * sizeof(double), n * sizeof(double), nrhs,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+  gmrfb_status rc = transpose_dev(ctx, dX.p, n, h->Xt.p, ldr, n, nrhs);
+  if (rc != GMRFB_OK) return rc;
+  rc = btd_sweep(h->interior, true, false, h->Xt.p, ldr, inr);
+  if (rc != GMRFB_OK) return rc;
+  if (h->P == 1) return GMRFB_OK;
+  const int64_t xstep = (int64_t)ldr * b, bs = (int64_t)h->ld * b;
+  GMRFB_CU(ctx, cudaMemsetAsync(d_send, 0, 2 * xstep * sizeof(double), ctx->stream));
+  if (h->has_sep) {
+    // send0' = b_S' - y_last' V'
+    GMRFB_CU(ctx, cudaMemcpyAsync(d_send, h->Xt.p + h->ni * xstep, xstep * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = gemm_once(ctx, LK_GEMM_NT, h->Xt.p + (h->ni - 1) * xstep, ldr, h->V.p, h->ld, d_send, ldr, inr, ib, ib, false, -1.0, 1.0);
+    if (rc != GMRFB_OK) return rc;
+  }
+  if (h->has_spike) {
+    for (int64_t i = 0; i < h->ni; i++) {
+      rc = gemm_once(ctx, LK_GEMM_NT, h->Xt.p + i * xstep, ldr, h->W.p + i * bs, h->ld, d_send + xstep, ldr, inr, ib, ib, false,
+                     1.0, i == 0 ? 0.0 : 1.0);
+      if (rc != GMRFB_OK) return rc;
+    }
+  }
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+// Phase 2: reduced solve (redundant on every rank), local back-substitution, copy out this rank's rows.
+extern "C" gmrfb_status gmrfb_btd_dist_solve_end(gmrfb_btd_dist* h, const double* d_all, double* X_local, int64_t ldx,
+                                                 int64_t nrhs) {
+  if (!h || !X_local || (h->P > 1 && !d_all))
+    return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_solve_end: NULL argument");
+  gmrfb_ctx* ctx = h->ctx;
+  if (h->solve_nrhs != nrhs || !h->Xt.p) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_dist_solve_end: no matching solve_begin");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t b = h->b, n = b * h->nloc;
+  const int ldr = h->solve_ldr, inr = (int)nrhs, ib = (int)b;
+  const int64_t xstep = (int64_t)ldr * b, bs = (int64_t)h->ld * b;
+  gmrfb_status rc;
+  if (h->P > 1) {
+    const int64_t nb = h->P - 1, cnt = 2 * xstep;
+    GMRFB_CU(ctx, h->Sx.alloc((size_t)(xstep * nb)));
+    for (int64_t r = 0; r < nb; r++) {
+      // b_hat_r = send0_r - u_{r+1}   (treated as ldr x b blocks with leading dimension ldr)
+      GMRFB_CU(ctx, launch_axpby(xstep, 1.0, d_all + r * cnt, -1.0, d_all + (r + 1) * cnt + xstep, h->Sx.p + r * xstep, ctx->stream));
+      ctx->launches++;
+    }
+    rc = btd_sweep(h->reduced, true, true, h->Sx.p, ldr, inr);
+    if (rc != GMRFB_OK) return rc;
+    // y_i -= x_{S_{r-1}}' W_i  (all interior blocks);  y_last -= x_{S_r}' V
+    if (h->has_spike) {
+      for (int64_t i = 0; i < h->ni; i++) {
+        rc = gemm_once(ctx, LK_GEMM_NN, h->Sx.p + (h->rank - 1) * xstep, ldr, h->W.p + i * bs, h->ld, h->Xt.p + i * xstep, ldr,
+                       inr, ib, ib, false, -1.0, 1.0);
+        if (rc != GMRFB_OK) return rc;
+      }
+    }
+    if (h->has_sep) {
+      rc = gemm_once(ctx, LK_GEMM_NN, h->Sx.p + h->rank * xstep, ldr, h->V.p, h->ld, h->Xt.p + (h->ni - 1) * xstep, ldr, inr, ib,
+                     ib, false, -1.0, 1.0);
+      if (rc != GMRFB_OK) return rc;
+      GMRFB_CU(ctx, cudaMemcpyAsync(h->Xt.p + h->ni * xstep, h->Sx.p + h->rank * xstep, xstep * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  rc = btd_sweep(h->interior, false, true, h->Xt.p, ldr, inr);
+  if (rc != GMRFB_OK) return rc;
+  DevBuf<double> dX;
+  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs)));
+  rc = transpose_dev(ctx, h->Xt.p, ldr, dX.p, n, nrhs, n);
+  if (rc != GMRFB_OK) return rc;
+  GMRFB_CU(ctx, cudaMemcpy2DAsync(X_local, ldx * sizeof(double), dX.p, n * sizeof(double), n * sizeof(double), nrhs,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_btd_dist_logdet(gmrfb_btd_dist* h, double* local_part, double* reduced_part) {
+  if (!h || !local_part || !reduced_part)
+    return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_logdet: NULL argument");
+  if (!h->reduced_ready) return fail(h->ctx, GMRFB_ERR_STATE, "gmrfb_btd_dist_logdet: call gmrfb_btd_dist_reduce first");
+  gmrfb_status rc = gmrfb_btd_logdet(h->interior, local_part);
+  if (rc != GMRFB_OK) return rc;
+  *reduced_part = 0.0;
+  if (h->reduced) rc = gmrfb_btd_logdet(h->reduced, reduced_part);
+  return rc;
+}
+
+extern "C" gmrfb_status gmrfb_btd_dist_destroy(gmrfb_btd_dist* h) {
+  if (!h) return GMRFB_OK;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  if (h->interior) gmrfb_btd_destroy(h->interior);
+  if (h->reduced) gmrfb_btd_destroy(h->reduced);
+  delete h;
   return GMRFB_OK;
 }

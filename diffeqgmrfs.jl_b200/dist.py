@@ -1,0 +1,147 @@
+"""Time-sharded block-tridiagonal Cholesky across ranks (one process per GPU).
+
+The space-time precision of an implicit-Euler GMRF is block tridiagonal along the time axis
+(src/spdes/shallow_water.jl:219-230; the factor of src/tridiagonal_cholesky.jl:65-82).  Rank r owns a contiguous
+slab of time blocks; ranks 0..P-2 use their last block as a separator.  All dense work is local CUDA
+(libgmrfb, gmrfb_btd_dist_*); the only exchange is an all-gather of three b x b blocks per rank for the factor and
+two b x nrhs panels per rank for a solve, done here with torch.distributed (NCCL over NVLink on GPUs).
+
+`slab_bounds(N, P)` gives the block partition; `TimeShardedCholesky` runs the phases.  The phases are also exposed
+individually (`iface`, `reduce`, `solve_begin`, `solve_end`) so that P ranks can be driven from one process in
+tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib as B
+from .solver import Context, default_context
+
+
+def slab_bounds(n_blocks: int, world: int):
+    """Contiguous slabs [lo, hi) per rank, sizes as equal as possible (every rank but the last needs >= 2 blocks)."""
+    base, rem = divmod(n_blocks, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    if any(hi - lo < 2 for lo, hi in out[:-1]) or out[-1][1] - out[-1][0] < 1:
+        raise ValueError("too few time blocks for this many ranks")
+    return out
+
+
+def local_blocks(D, Bsub, lo, hi):
+    """Slice the global dense blocks (D[b,b,N], Bsub[b,b,N-1]) into the rank-local arrays of the C ABI."""
+    b = D.shape[0]
+    Dl = np.asfortranarray(D[:, :, lo:hi])
+    Bl = np.zeros((b, b, hi - lo), order="F")
+    for k in range(lo, hi):
+        if k > 0:
+            Bl[:, :, k - lo] = Bsub[:, :, k - 1]
+    return Dl, Bl
+
+
+class TimeShardedCholesky:
+    """One rank of the time-sharded factor.  `slab` may be a backend object implementing the four phases
+    (`iface`, `reduce`, `solve_begin`, `solve_end`, `logdet_parts`) on CPU tensors — used by the gloo tests to run
+    this orchestration code without a GPU; by default the phases are the CUDA library's."""
+
+    def __init__(self, D_local, B_local, rank: int, world: int, ctx: Context | None = None, group=None,
+                 auto_exchange: bool = True, slab=None):
+        import torch
+
+        self.torch = torch
+        self.rank, self.world, self.group = rank, world, group
+        self._slab = slab
+        if slab is not None:
+            self.b, self.nloc = slab.b, slab.nloc
+            if auto_exchange:
+                self.reduce(self._allgather(self.iface()))
+            return
+        self.ctx = ctx or default_context()
+        D_local = np.asfortranarray(D_local, dtype=np.float64)
+        B_local = np.asfortranarray(B_local, dtype=np.float64)
+        self.b, _, self.nloc = D_local.shape
+        h = C.c_void_p()
+        st = B.lib().gmrfb_btd_dist_create(self.ctx.h, rank, world, self.b, self.nloc, D_local.ctypes.data_as(B._F64P),
+                                           B_local.ctypes.data_as(B._F64P), C.byref(h))
+        B.check(st, self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_btd_dist_destroy, h)
+        self.dev = torch.device("cuda", self.ctx.device)
+        if auto_exchange:
+            self.reduce(self._allgather(self.iface()))
+
+    # ---- phases ----
+    def iface(self):
+        if self._slab is not None:
+            return self._slab.iface()
+        cnt = int(B.lib().gmrfb_btd_dist_iface_count(self.h))
+        send = self.torch.empty(cnt, dtype=self.torch.float64, device=self.dev)
+        B.check(B.lib().gmrfb_btd_dist_get_iface(self.h, C.c_void_p(send.data_ptr())), self.ctx.h)
+        return send
+
+    def reduce(self, gathered):
+        if self._slab is not None:
+            return self._slab.reduce(gathered)
+        ptr = C.c_void_p(gathered.data_ptr()) if gathered is not None else None
+        B.check(B.lib().gmrfb_btd_dist_reduce(self.h, ptr), self.ctx.h)
+
+    def solve_begin(self, X_local):
+        if self._slab is not None:
+            return self._slab.solve_begin(X_local)
+        X = np.asfortranarray(np.asarray(X_local, dtype=np.float64).reshape(self.b * self.nloc, -1))
+        self._nrhs = X.shape[1]
+        cnt = int(B.lib().gmrfb_btd_dist_solve_count(self.h, self._nrhs))
+        send = self.torch.zeros(cnt, dtype=self.torch.float64, device=self.dev)
+        B.check(B.lib().gmrfb_btd_dist_solve_begin(self.h, X.ctypes.data_as(B._F64P), X.shape[0], self._nrhs,
+                                                   C.c_void_p(send.data_ptr())), self.ctx.h)
+        return send
+
+    def solve_end(self, gathered):
+        if self._slab is not None:
+            return self._slab.solve_end(gathered)
+        n = self.b * self.nloc
+        X = np.empty((n, self._nrhs), order="F")
+        ptr = C.c_void_p(gathered.data_ptr()) if gathered is not None else None
+        B.check(B.lib().gmrfb_btd_dist_solve_end(self.h, ptr, X.ctypes.data_as(B._F64P), n, self._nrhs), self.ctx.h)
+        return X
+
+    # ---- collective wrappers ----
+    def _allgather(self, send):
+        if self.world == 1:
+            return send
+        import torch.distributed as dist
+
+        out = self.torch.empty(self.world * send.numel(), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(out, send, group=self.group)
+        return out
+
+    def solve(self, X_local):
+        """This rank's rows of A^{-1} X (intended semantics of ldiv, src/tridiagonal_cholesky.jl:54-63)."""
+        one = np.asarray(X_local).ndim == 1
+        X = self.solve_end(self._allgather(self.solve_begin(X_local)))
+        return X[:, 0].copy() if one else X
+
+    def logdet_parts(self):
+        if self._slab is not None:
+            return self._slab.logdet_parts()
+        loc, red = C.c_double(), C.c_double()
+        B.check(B.lib().gmrfb_btd_dist_logdet(self.h, C.byref(loc), C.byref(red)), self.ctx.h)
+        return loc.value, red.value
+
+    def logdet(self):
+        loc, red = self.logdet_parts()
+        total_local = loc
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dev = self.dev if self._slab is None else "cpu"
+            t = self.torch.tensor([loc], dtype=self.torch.float64, device=dev)
+            dist.all_reduce(t, group=self.group)
+            total_local = float(t.item())
+        return total_local + red

@@ -271,6 +271,35 @@ typedef struct gmrfb_btd_info {
 } gmrfb_btd_info;
 gmrfb_status gmrfb_btd_get_info(gmrfb_btd* f, gmrfb_btd_info* info);
 
+/* Time-sharded block-tridiagonal factor/solve across ranks (one process per GPU).  Rank r owns a contiguous slab
+ * of nloc blocks; ranks 0..P-2 use their last block as a separator.  All numeric work is local; the only exchange
+ * is an all-gather of three b-by-b blocks per rank (factor) and two b-by-nrhs panels per rank (solve), which the
+ * host performs between the phased calls below (torch.distributed / NCCL all_gather_into_tensor over NVLink in
+ * the Python host; NCCL.jl or MPI from Julia — see INTEGRATION.md).
+ *   D_local : b-by-b-by-nloc diagonal blocks of the slab
+ *   B_local : b-by-b-by-nloc, B_local[:,:,k] = block (slab block k, the block before it); ignored for k = 0 on rank 0 */
+typedef struct gmrfb_btd_dist gmrfb_btd_dist;
+gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int32_t nranks, int64_t b, int64_t nloc,
+                                   const double* D_local, const double* B_local, gmrfb_btd_dist** out);
+/* doubles each rank contributes to the factor exchange (3 b^2) */
+int64_t gmrfb_btd_dist_iface_count(const gmrfb_btd_dist* h);
+/* copy this rank's interface blocks into a caller-owned DEVICE buffer of iface_count doubles */
+gmrfb_status gmrfb_btd_dist_get_iface(gmrfb_btd_dist* h, double* d_out);
+/* d_all: the all-gathered interface blocks (DEVICE, rank-major, nranks * iface_count doubles): assembles and
+ * factorises the (P-1)-block reduced Schur system redundantly on every rank */
+gmrfb_status gmrfb_btd_dist_reduce(gmrfb_btd_dist* h, const double* d_all);
+/* doubles each rank contributes to the solve exchange for nrhs right-hand sides */
+int64_t gmrfb_btd_dist_solve_count(const gmrfb_btd_dist* h, int64_t nrhs);
+/* phase 1: X_local (b*nloc-by-nrhs, host) -> local forward elimination; fills d_send (DEVICE, solve_count doubles) */
+gmrfb_status gmrfb_btd_dist_solve_begin(gmrfb_btd_dist* h, const double* X_local, int64_t ldx, int64_t nrhs,
+                                        double* d_send);
+/* phase 2: d_all = all-gathered d_send of every rank (DEVICE); X_local <- this rank's rows of A^{-1} X */
+gmrfb_status gmrfb_btd_dist_solve_end(gmrfb_btd_dist* h, const double* d_all, double* X_local, int64_t ldx,
+                                      int64_t nrhs);
+/* log det A = sum over ranks of *local_part + *reduced_part (the reduced part is identical on every rank) */
+gmrfb_status gmrfb_btd_dist_logdet(gmrfb_btd_dist* h, double* local_part, double* reduced_part);
+gmrfb_status gmrfb_btd_dist_destroy(gmrfb_btd_dist* h);
+
 #ifdef __cplusplus
 }
 #endif
