@@ -1,0 +1,288 @@
+# GMRFB200.jl — thin `ccall` shim over libgmrfb (include/gmrfb.h).
+#
+# NOT EXECUTED IN THE BUILD CONTAINER (Julia is not installed there); kept trivially thin on purpose:
+# pointer passing, `GC.@preserve`, status -> exception.  The Python ctypes host
+# (`diffeqgmrfs.jl_b200/solver.py`) binds the same symbols with the same argument meaning and is what the
+# parity tests drive.  INTEGRATION.md shows how the reference's scripts select these types.
+#
+# Reference surface mirrored (file:line under timweiland/DiffEqGMRFs.jl):
+#   cholesky(Symmetric(A); perm, check)            scripts/solve_burger.jl:147, scripts/darcy/solve_darcy_fem.jl:93
+#   F \ b, F.PtL \ b, F.UP \ z, F.p, nnz(F), F.L    src/tridiagonal_cholesky.jl:20-22,39-41; scripts/darcy/solve_darcy_gmrf-fem.jl:169-170
+#   tridiagonal_cholesky / forward_solve / ...      src/tridiagonal_cholesky.jl:5-82
+#   CholeskySolverBlueprint(; var_strategy, perm)   scripts/darcy/solve_darcy_gmrf-fem.jl:100,174
+module GMRFB200
+
+using LinearAlgebra, SparseArrays
+
+export B200Context, B200Factor, b200_cholesky, b200_tridiagonal_cholesky, B200TridiagonalCholeskyFactor,
+       B200CholeskySolverBlueprint, B200GNCholeskySolverBlueprint, forward_solve, backward_solve, ldiv, ldiv!,
+       var_selinv, var_rbmc, logdet_factor, issuccess
+
+const libgmrfb = get(ENV, "GMRFB_LIB", joinpath(@__DIR__, "..", "diffeqgmrfs.jl_b200", "libgmrfb.so"))
+
+const GMRFB_OK = Int32(0)
+const GMRFB_ERR_NOT_SPD = Int32(2)
+const ORDER_GIVEN, ORDER_NATURAL, ORDER_ND = Int32(0), Int32(1), Int32(2)
+const SOLVE_A, SOLVE_PTL, SOLVE_UP, SOLVE_L, SOLVE_LT = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
+const BTD_SOLVE_A, BTD_SOLVE_FWD, BTD_SOLVE_BWD = Int32(0), Int32(1), Int32(2)
+
+struct GmrfbError <: Exception
+    status::Int32
+    msg::String
+end
+
+# mirrors gmrfb_analyze_opts
+struct AnalyzeOpts
+    ordering_kind::Int32
+    storage::Int32
+    base::Int32
+    coord_dim::Int32
+    coords::Ptr{Float64}
+    nd_leaf::Int32
+    relax_small::Int32
+    relax_zeros::Float64
+end
+
+# mirrors gmrfb_sym_info / gmrfb_fac_info / gmrfb_btd_info
+struct SymInfo
+    n::Int64; nnz_lower_A::Int64; nnz_L::Int64; nnz_L_stored::Int64; flops::Float64
+    nsuper::Int64; nlevels::Int64; max_front::Int64; front_bytes::Int64
+end
+struct FacInfo
+    status::Int32; fail_column::Int64; logdet::Float64; nnz_L::Int64
+end
+struct BtdInfo
+    b::Int64; nblocks::Int64; status::Int32; fail_block::Int64; flops::Float64
+end
+
+mutable struct B200Context
+    h::Ptr{Cvoid}
+    function B200Context(device::Integer = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        st = ccall((:gmrfb_ctx_create, libgmrfb), Int32, (Int32, Ref{Ptr{Cvoid}}), device, out)
+        st == GMRFB_OK || throw(GmrfbError(st, unsafe_string(ccall((:gmrfb_last_error, libgmrfb), Cstring, (Ptr{Cvoid},), C_NULL))))
+        ctx = new(out[])
+        finalizer(c -> ccall((:gmrfb_ctx_destroy, libgmrfb), Int32, (Ptr{Cvoid},), c.h), ctx)
+        return ctx
+    end
+end
+
+const _default_ctx = Ref{Union{Nothing,B200Context}}(nothing)
+default_context() = (_default_ctx[] === nothing && (_default_ctx[] = B200Context(0)); _default_ctx[]::B200Context)
+
+function check(ctx::B200Context, st::Int32)
+    st == GMRFB_OK && return
+    msg = unsafe_string(ccall((:gmrfb_last_error, libgmrfb), Cstring, (Ptr{Cvoid},), ctx.h))
+    st == GMRFB_ERR_NOT_SPD && throw(PosDefException(1))   # what stdlib `cholesky` throws with check=true
+    throw(GmrfbError(st, msg))
+end
+
+# ------------------------------------------------------------------------------------------ sparse factor --
+"Numeric supernodal factor with the CHOLMOD.Factor surface the reference touches (`.p`, `\\`, `.PtL`, `.UP`, `nnz`)."
+mutable struct B200Factor
+    ctx::B200Context
+    sym::Ptr{Cvoid}
+    fac::Ptr{Cvoid}
+    n::Int
+    p::Vector{Int64}          # 1-based, new -> old: identical to the `perm` passed in when one is given
+    success::Bool
+end
+
+function _destroy(F::B200Factor)
+    ccall((:gmrfb_fac_destroy, libgmrfb), Int32, (Ptr{Cvoid},), F.fac)
+    ccall((:gmrfb_sym_destroy, libgmrfb), Int32, (Ptr{Cvoid},), F.sym)
+end
+
+"""
+    b200_cholesky(A; perm=nothing, check=true, coords=nothing, ctx=default_context())
+
+Drop-in for `cholesky(Symmetric(A); perm, check)` on a `SparseMatrixCSC{Float64,Int64}` holding both triangles.
+Julia's 1-based `colptr`/`rowval`/`perm` are passed untouched (`base = 1`).
+"""
+function b200_cholesky(A::SparseMatrixCSC{Float64,Int64}; perm::Union{Nothing,Vector{Int64}} = nothing,
+                       check::Bool = true, coords::Union{Nothing,Matrix{Float64}} = nothing,
+                       ctx::B200Context = default_context())
+    n = size(A, 1)
+    cdim = coords === nothing ? Int32(0) : Int32(size(coords, 1))      # coords is dim x n (node-major in memory)
+    cptr = coords === nothing ? Ptr{Float64}(C_NULL) : pointer(coords)
+    opts = Ref(AnalyzeOpts(perm === nothing ? ORDER_ND : ORDER_GIVEN, Int32(0), Int32(1), cdim, cptr, 0, 0, 0.0))
+    sym = Ref{Ptr{Cvoid}}(C_NULL)
+    fac = Ref{Ptr{Cvoid}}(C_NULL)
+    pptr = perm === nothing ? Ptr{Int64}(C_NULL) : pointer(perm)
+    GC.@preserve A perm coords begin
+        check(ctx, ccall((:gmrfb_analyze, libgmrfb), Int32,
+                         (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{AnalyzeOpts}, Ref{Ptr{Cvoid}}),
+                         ctx.h, n, A.colptr, A.rowval, pptr, opts, sym))
+        check(ctx, ccall((:gmrfb_fac_create, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), sym[], fac))
+        p = Vector{Int64}(undef, n)
+        check(ctx, ccall((:gmrfb_sym_get, libgmrfb), Int32,
+                         (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+                         sym[], p, C_NULL, C_NULL, C_NULL, C_NULL))
+        F = B200Factor(ctx, sym[], fac[], n, p, false)
+        finalizer(_destroy, F)
+        refactorize!(F, A.nzval; check = check)
+        return F
+    end
+end
+
+"Numeric refactorisation on the analysed pattern (the Gauss-Newton loop, scripts/solve_burger.jl:171-180)."
+function refactorize!(F::B200Factor, nzval::Vector{Float64}; check::Bool = true)
+    st = GC.@preserve nzval ccall((:gmrfb_factorize, libgmrfb), Int32, (Ptr{Cvoid}, Ptr{Float64}), F.fac, nzval)
+    F.success = st == GMRFB_OK
+    (st == GMRFB_ERR_NOT_SPD && !check) && return F        # `check=false`: failure is a queryable flag
+    GMRFB200.check(F.ctx, st)
+    return F
+end
+
+LinearAlgebra.issuccess(F::B200Factor) = F.success
+
+function _info(F::B200Factor)
+    info = Ref(FacInfo(0, 0, 0.0, 0))
+    check(F.ctx, ccall((:gmrfb_fac_get_info, libgmrfb), Int32, (Ptr{Cvoid}, Ref{FacInfo}), F.fac, info))
+    return info[]
+end
+SparseArrays.nnz(F::B200Factor) = Int(_info(F).nnz_L)                  # scripts/darcy/solve_darcy_gmrf-fem.jl:170
+logdet_factor(F::B200Factor) = _info(F).logdet
+LinearAlgebra.logdet(F::B200Factor) = _info(F).logdet
+
+function _solve!(F::B200Factor, mode::Int32, X::StridedVecOrMat{Float64})
+    nrhs = size(X, 2)
+    ldx = X isa AbstractVector ? length(X) : stride(X, 2)
+    GC.@preserve X check(F.ctx, ccall((:gmrfb_solve, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int64),
+                                      F.fac, mode, X, ldx, nrhs))
+    return X
+end
+Base.:\(F::B200Factor, b::StridedVecOrMat{Float64}) = _solve!(F, SOLVE_A, copy(b))     # scripts/solve_burger.jl:148
+
+"`F.PtL \\ b` and `F.UP \\ z` (src/tridiagonal_cholesky.jl:20-22,39-41) as lazy views."
+struct FactorView
+    F::B200Factor
+    mode::Int32
+end
+Base.:\(V::FactorView, b::StridedVecOrMat{Float64}) = _solve!(V.F, V.mode, copy(b))
+function Base.getproperty(F::B200Factor, s::Symbol)
+    s === :PtL && return FactorView(F, SOLVE_PTL)
+    s === :UP && return FactorView(F, SOLVE_UP)
+    s === :L && return _sparse_L(F)                                    # scripts/burgers/solve_burgers_gmrf-collocation.jl:209
+    return getfield(F, s)
+end
+
+function _sparse_L(F::B200Factor)
+    n = getfield(F, :n); fac = getfield(F, :fac); ctx = getfield(F, :ctx)
+    colptr = Vector{Int64}(undef, n + 1)
+    check(ctx, ccall((:gmrfb_fac_get_L, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                     fac, 1, 1, colptr, C_NULL, C_NULL))
+    nz = colptr[end] - 1
+    rowval = Vector{Int64}(undef, nz); nzval = Vector{Float64}(undef, nz)
+    check(ctx, ccall((:gmrfb_fac_get_L, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                     fac, 1, 1, colptr, rowval, nzval))
+    return SparseMatrixCSC(n, n, colptr, rowval, nzval)
+end
+
+"x = mean + P' L^{-T} z for host-supplied standard normals z (`rand(rng, x)`, scripts/darcy/solve_darcy_gmrf-fem.jl:191)."
+function sample(F::B200Factor, Z::StridedVecOrMat{Float64}; mean::Union{Nothing,Vector{Float64}} = nothing)
+    X = similar(Z)
+    mptr = mean === nothing ? Ptr{Float64}(C_NULL) : pointer(mean)
+    GC.@preserve Z X mean check(F.ctx, ccall((:gmrfb_sample, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64),
+        F.fac, mptr, Z, size(Z, 1), X, size(X, 1), size(Z, 2)))
+    return X
+end
+
+"diag(Q^{-1}) by Takahashi selected inversion."
+function var_selinv(F::B200Factor)
+    v = Vector{Float64}(undef, F.n)
+    GC.@preserve v check(F.ctx, ccall((:gmrfb_var_selinv, libgmrfb), Int32, (Ptr{Cvoid}, Ptr{Float64}), F.fac, v))
+    return v
+end
+
+"RBMCStrategy(N) variances (scripts/darcy/solve_darcy_gmrf-fem.jl:100,174,192); Z = n x N standard normals."
+function var_rbmc(F::B200Factor, Q::SparseMatrixCSC{Float64,Int64}, Z::Matrix{Float64})
+    ctx = F.ctx
+    spm = Ref{Ptr{Cvoid}}(C_NULL)
+    v = Vector{Float64}(undef, F.n)
+    GC.@preserve Q Z v begin
+        check(ctx, ccall((:gmrfb_spm_create, libgmrfb), Int32,
+                         (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
+                         ctx.h, size(Q, 1), size(Q, 2), Q.colptr, Q.rowval, Q.nzval, 1, spm))
+        try
+            check(ctx, ccall((:gmrfb_var_rbmc, libgmrfb), Int32,
+                             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}),
+                             F.fac, spm[], Z, size(Z, 1), size(Z, 2), v))
+        finally
+            ccall((:gmrfb_spm_destroy, libgmrfb), Int32, (Ptr{Cvoid},), spm[])
+        end
+    end
+    return v
+end
+
+# --------------------------------------------------------------------------------- blueprints (GMRF.jl seam) --
+# GaussianMarkovRandomFields.jl constructs its solver from a blueprint via `construct_solver(bp, gmrf)`; a package
+# extension adds methods for these two types that build a `B200Factor` (see INTEGRATION.md for the glue).
+Base.@kwdef struct B200CholeskySolverBlueprint
+    var_strategy::Any = :takahashi          # or RBMCStrategy(N; rng) from GaussianMarkovRandomFields
+    perm::Union{Nothing,Vector{Int64}} = nothing
+end
+struct B200GNCholeskySolverBlueprint
+    perm::Union{Nothing,Vector{Int64}}
+end
+B200GNCholeskySolverBlueprint() = B200GNCholeskySolverBlueprint(nothing)
+
+# --------------------------------------------------------------------------- block-tridiagonal Cholesky --
+"Device-resident counterpart of `TridiagonalCholeskyFactor{T}` (src/tridiagonal_cholesky.jl:5-9)."
+mutable struct B200TridiagonalCholeskyFactor
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    N::Int          # total rows, as in the reference struct
+    b::Int
+    nblocks::Int
+end
+
+"`tridiagonal_cholesky(A::SparseMatrixCSC, N_blocks)` (src/tridiagonal_cholesky.jl:65-82)."
+function b200_tridiagonal_cholesky(A::SparseMatrixCSC{Float64,Int64}, N_blocks::Integer; ctx::B200Context = default_context())
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    st = GC.@preserve A ccall((:gmrfb_btd_factor, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Int64, Ref{Ptr{Cvoid}}),
+        ctx.h, size(A, 1), A.colptr, A.rowval, A.nzval, 1, N_blocks, out)
+    if st != GMRFB_OK && out[] != C_NULL
+        ccall((:gmrfb_btd_destroy, libgmrfb), Int32, (Ptr{Cvoid},), out[])
+    end
+    check(ctx, st)
+    F = B200TridiagonalCholeskyFactor(ctx, out[], size(A, 1), size(A, 1) ÷ N_blocks, N_blocks)
+    finalizer(f -> ccall((:gmrfb_btd_destroy, libgmrfb), Int32, (Ptr{Cvoid},), f.h), F)
+    return F
+end
+
+function _block(F::B200TridiagonalCholeskyFactor, i::Integer, which::Integer)
+    out = Matrix{Float64}(undef, F.b, F.b)
+    GC.@preserve out check(F.ctx, ccall((:gmrfb_btd_get_block, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64), F.h, i - 1, which, out, F.b))
+    return out
+end
+"`chos[i].L` and `Cs[i]` of the reference struct, copied out of device memory on demand."
+chos(F::B200TridiagonalCholeskyFactor) = [Cholesky(LowerTriangular(_block(F, i, 0))) for i in 1:F.nblocks]
+Cs(F::B200TridiagonalCholeskyFactor) = [_block(F, i, 1) for i in 1:F.nblocks-1]
+
+function _btd_solve(F::B200TridiagonalCholeskyFactor, mode::Int32, b::StridedVecOrMat{Float64})
+    n = F.b * F.nblocks
+    X = copy(b)
+    ldx = X isa AbstractVector ? length(X) : stride(X, 2)
+    GC.@preserve X check(F.ctx, ccall((:gmrfb_btd_solve, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int64),
+                                      F.h, mode, X, ldx, size(X, 2)))
+    return X
+end
+# intended semantics of src/tridiagonal_cholesky.jl:24-63 (flat vectors; defects T4/T5/T7 of SURVEY.md §8a not reproduced)
+forward_solve(F::B200TridiagonalCholeskyFactor, b) = _btd_solve(F, BTD_SOLVE_FWD, b)
+backward_solve(F::B200TridiagonalCholeskyFactor, b) = _btd_solve(F, BTD_SOLVE_BWD, b)
+forward_solve(F::B200Factor, b) = F.PtL \ b          # :39-41
+backward_solve(F::B200Factor, b) = F.UP \ b          # :20-22
+ldiv(F::B200TridiagonalCholeskyFactor, b) = _btd_solve(F, BTD_SOLVE_A, b)
+ldiv!(y, F::B200TridiagonalCholeskyFactor, b) = (y .= ldiv(F, b); y)
+
+function LinearAlgebra.logdet(F::B200TridiagonalCholeskyFactor)
+    out = Ref(0.0)
+    check(F.ctx, ccall((:gmrfb_btd_logdet, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Float64}), F.h, out))
+    return out[]
+end
+
+end # module

@@ -40,6 +40,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "sparse_chol.c")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _LIB_PATH, src, "-lm"])
+    build_supernodal(force)
     return _LIB_PATH
 
 
@@ -344,3 +345,129 @@ def btd_selinv_diag(F):
         S = Li.T @ H @ Li
         out[i * bs:(i + 1) * bs] = np.diag(S)
     return out
+
+
+# ------------------------------------------------------------------- supernodal CPU baseline (BLAS-3) --
+_SN_PATH = os.path.join(_HERE, "libsupernodal.so")
+_sn = None
+
+
+def _capsule_ptr(mod, name):
+    cap = mod.__pyx_capi__[name]
+    ctypes.pythonapi.PyCapsule_GetName.restype = ctypes.c_char_p
+    ctypes.pythonapi.PyCapsule_GetName.argtypes = [ctypes.py_object]
+    ctypes.pythonapi.PyCapsule_GetPointer.restype = ctypes.c_void_p
+    ctypes.pythonapi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+    return ctypes.pythonapi.PyCapsule_GetPointer(cap, ctypes.pythonapi.PyCapsule_GetName(cap))
+
+
+def build_supernodal(force: bool = False) -> str:
+    src = os.path.join(_HERE, "supernodal_chol.c")
+    if force or not os.path.exists(_SN_PATH) or os.path.getmtime(_SN_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _SN_PATH, src, "-lm"])
+    return _SN_PATH
+
+
+def _load_sn():
+    """libsupernodal.so with OpenBLAS/LAPACK entry points taken from scipy's Cython capsules."""
+    global _sn
+    if _sn is None:
+        import scipy.linalg.cython_blas as cb
+        import scipy.linalg.cython_lapack as cl
+
+        build_supernodal()
+        L = ctypes.CDLL(_SN_PATH)
+        i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+        L.sn_set_blas.argtypes = [ctypes.c_void_p] * 9
+        L.sn_set_blas(*[_capsule_ptr(cb, k) for k in ("dgemm", "dsyrk", "dtrsm", "dtrsv", "dgemv", "dsymm")],
+                      *[_capsule_ptr(cl, k) for k in ("dpotrf", "dtrtri", "dlauum")])
+        I = ctypes.c_int64
+        L.sn_factor.argtypes = [I, I, i64p, i64p, i64p, i64p, i64p, i64p, f64p, i64p, f64p]
+        L.sn_factor.restype = I
+        L.sn_solve.argtypes = [I, I, i64p, i64p, i64p, i64p, f64p, f64p, I, ctypes.c_int, ctypes.c_int]
+        L.sn_selinv.argtypes = [I, I, i64p, i64p, i64p, i64p, i64p, f64p, f64p]
+        L.sn_selinv.restype = I
+        _sn = L
+    return _sn
+
+
+class SupernodalCholesky:
+    """CPU supernodal multifrontal Cholesky with BLAS-3 supernodes (CHOLMOD's algorithm class; the timed CPU
+    baseline of bench.py).  The supernode partition is an input: ``perm_int`` (internal new->old, 0-based, an etree
+    postorder of the user's perm), ``sptr`` (first internal column of each supernode) and per-supernode row lists
+    (own columns first, then the below rows ascending) in the internal numbering."""
+
+    def __init__(self, A, perm_int, sptr, rows_list):
+        A = _csc(A)
+        self.n = n = A.shape[0]
+        self.perm = np.ascontiguousarray(perm_int, dtype=np.int64)
+        self.sptr = np.ascontiguousarray(sptr, dtype=np.int64)
+        self.ns = ns = len(self.sptr) - 1
+        self.rptr = np.zeros(ns + 1, np.int64)
+        np.cumsum([len(r) for r in rows_list], out=self.rptr[1:])
+        self.rows = np.ascontiguousarray(np.concatenate(rows_list) if ns else np.zeros(0), dtype=np.int64)
+        sc = np.diff(self.sptr)
+        d = np.diff(self.rptr)
+        snode = np.repeat(np.arange(ns, dtype=np.int64), sc)
+        self.sparent = np.full(ns, -1, np.int64)
+        has = d > sc
+        self.sparent[has] = snode[self.rows[(self.rptr[:-1] + sc)[has]]]
+        self.loff = np.zeros(ns + 1, np.int64)
+        np.cumsum(d * sc, out=self.loff[1:])
+        self.Lx = np.zeros(int(self.loff[-1]))
+        # tril(P A P') once, with the map from A's stored values to its entries (numeric refactorisations reuse it)
+        tag = sp.csc_matrix((np.arange(1, A.nnz + 1, dtype=np.float64), A.indices, A.indptr), shape=A.shape)
+        C = sp.tril(tag[self.perm][:, self.perm], format="csc")
+        C.sort_indices()
+        self._Cp = C.indptr.astype(np.int64)
+        self._Ci = C.indices.astype(np.int64)
+        self._vmap = (C.data - 1).astype(np.int64)
+        self.refactor(A)
+
+    def refactor(self, A):
+        """Numeric factorisation of a matrix with the analysed pattern (A: scipy sparse, or its CSC value array)."""
+        vals = _csc(A).data if sp.issparse(A) else np.asarray(A, dtype=np.float64)
+        Cx = np.ascontiguousarray(vals[self._vmap], dtype=np.float64)
+        rc = _load_sn().sn_factor(self.n, self.ns, self.sptr, self.rptr, self.rows, self.sparent, self._Cp, self._Ci, Cx,
+                                  self.loff, self.Lx)
+        if rc != 0:
+            raise np.linalg.LinAlgError(f"supernodal factorisation failed ({rc})")
+        return self
+
+    def _sweep(self, B, fwd, bwd, perm_in, perm_out):
+        B = np.asarray(B, dtype=np.float64)
+        one = B.ndim == 1
+        X = np.asfortranarray(B.reshape(self.n, -1).copy())
+        if perm_in:
+            X = np.asfortranarray(X[self.perm])
+        Xf = np.ascontiguousarray(X.T)  # rows = right-hand sides = column-major n x nrhs
+        _load_sn().sn_solve(self.n, self.ns, self.sptr, self.rptr, self.rows, self.loff, self.Lx, Xf, Xf.shape[0],
+                            int(fwd), int(bwd))
+        X = Xf.T
+        if perm_out:
+            out = np.empty_like(X)
+            out[self.perm] = X
+            X = out
+        return X[:, 0].copy() if one else np.array(X)
+
+    def solve(self, B):
+        return self._sweep(B, True, True, True, True)
+
+    def selinv_diag(self):
+        z = np.zeros(self.n)
+        rc = _load_sn().sn_selinv(self.n, self.ns, self.sptr, self.rptr, self.rows, self.sparent, self.loff, self.Lx, z)
+        if rc != 0:
+            raise MemoryError("sn_selinv failed")
+        out = np.empty(self.n)
+        out[self.perm] = z
+        return out
+
+    def logdet(self):
+        sc = np.diff(self.sptr)
+        d = np.diff(self.rptr)
+        tot = 0.0
+        for s in range(self.ns):
+            P = self.Lx[self.loff[s]:self.loff[s + 1]].reshape(sc[s], d[s])  # column-major d x sc == C-order sc x d
+            tot += float(np.sum(np.log(np.diag(P[:, :sc[s]]))))
+        return 2.0 * tot
