@@ -104,8 +104,8 @@ static const char* prof_name(int kind) {
     case LK_GEMM_TN: return "k_gemm<TN> (DMMA)";
     case LK_GEMM_TT: return "k_gemm<TT> (DMMA)";
     case LK_POTRF: return "k_potrf64";
-    case LK_TRSM_RLT: return "k_trsm<RLT>";
-    case LK_TRSM_RLN: return "k_trsm<RLN>";
+    case LK_TRSM_RLT: return "k_apply_inv<T>";
+    case LK_TRSM_RLN: return "k_apply_inv<N>";
     case LK_EXTEND_ADD: return "k_extend_add";
     case LK_GATHER_SYM: return "k_gather_sym";
     case LK_SET_IDENTITY: return "k_tile_op<identity>";
@@ -431,6 +431,7 @@ extern "C" gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out) {
   GMRFB_CU(ctx, f->partial.alloc((size_t)std::max<int64_t>(sym->partial_doubles, 1)));
   GMRFB_CU(ctx, f->bwork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
   GMRFB_CU(ctx, f->uvec.alloc((size_t)std::max<int64_t>(sym->uvec_rows, 1) * SOLVE_NRC));
+  GMRFB_CU(ctx, f->dinv.alloc((size_t)std::max<int64_t>(sym->factor_plan.host.dinv, 1)));
   *out = f.release();
   return GMRFB_OK;
 }
@@ -465,6 +466,7 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
   }
   ctx->launches++;
   Arenas ar{{fac->arena.p, nullptr, nullptr, nullptr}};
+  ar.dinv = fac->dinv.p;
   LaunchAux aux;
   aux.d_info = ctx->d_info;
   aux.d_relmap = sym->d_relmap.p;
@@ -774,7 +776,9 @@ static gmrfb_status selinv_run(gmrfb_fac* fac) {
   if (!fac->zarena.p) GMRFB_CU(ctx, fac->zarena.alloc(fac->arena.n));
   if (!fac->zdiag.p) GMRFB_CU(ctx, fac->zdiag.alloc((size_t)std::max<int64_t>(sym->S.n, 1)));
   if (!fac->zwork.p) GMRFB_CU(ctx, fac->zwork.alloc((size_t)std::max<int64_t>(sym->selinv_plan.host.scratch, 1)));
+  if ((int64_t)fac->dinv.n < sym->selinv_plan.host.dinv) GMRFB_CU(ctx, fac->dinv.alloc((size_t)sym->selinv_plan.host.dinv));
   Arenas ar{{fac->arena.p, fac->zarena.p, fac->zwork.p, nullptr}};
+  ar.dinv = fac->dinv.p;
   LaunchAux aux;
   aux.d_info = ctx->d_info;
   aux.d_relmap = sym->d_relmap.p;

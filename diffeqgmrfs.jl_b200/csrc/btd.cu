@@ -21,7 +21,7 @@ struct gmrfb_btd {
   int64_t b = 0, N = 0;
   int ld = 0;
   int64_t slot = 0;  // doubles per block slot
-  DevBuf<double> arena;
+  DevBuf<double> arena, dinv;  // dinv: scratch of inverted <=64x64 diagonal blocks
   DevPlan plan_first, plan_step;
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_block = -1;
@@ -88,6 +88,15 @@ gmrfb_status upload_plan(gmrfb_ctx* ctx, DevPlan& P) {
   return GMRFB_OK;
 }
 
+// grow the inverse-block scratch to what plan `P` needs (stream-ordered: earlier launches have been queued before)
+gmrfb_status ensure_dinv(gmrfb_btd* f, const Plan& P) {
+  if ((int64_t)f->dinv.n >= P.dinv) return GMRFB_OK;
+  gmrfb_ctx* ctx = f->ctx;
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  GMRFB_CU(ctx, f->dinv.alloc((size_t)P.dinv));
+  return GMRFB_OK;
+}
+
 gmrfb_status btd_alloc(gmrfb_ctx* ctx, int64_t b, int64_t N, std::unique_ptr<gmrfb_btd>& f) {
   if (b <= 0 || N <= 0) return fail(ctx, GMRFB_ERR_INVALID, "btd: block size and block count must be positive");
   if (b > 60000) return fail(ctx, GMRFB_ERR_INVALID, "btd: block size too large");
@@ -127,6 +136,8 @@ gmrfb_status btd_alloc(gmrfb_ctx* ctx, int64_t b, int64_t N, std::unique_ptr<gmr
   }
   gmrfb_status rc = upload_plan(ctx, f->plan_first);
   if (rc != GMRFB_OK) return rc;
+  if ((rc = ensure_dinv(f.get(), f->plan_first.host)) != GMRFB_OK) return rc;
+  if ((rc = ensure_dinv(f.get(), f->plan_step.host)) != GMRFB_OK) return rc;
   return upload_plan(ctx, f->plan_step);
 }
 
@@ -138,6 +149,7 @@ gmrfb_status btd_run_factor(gmrfb_btd* f) {
   aux.d_info = ctx->d_info;
   for (int64_t i = 0; i < f->N; i++) {
     Arenas ar{{f->arena.p + i * f->slot, nullptr, nullptr, nullptr}};
+    ar.dinv = f->dinv.p;
     gmrfb_status rc = run_plan(ctx, i == 0 ? f->plan_first : f->plan_step, ar, aux);
     if (rc != GMRFB_OK) return rc;
   }
@@ -356,6 +368,8 @@ static gmrfb_status btd_build_solve_plans(gmrfb_btd* f, int nrhs, int ldr) {
   if ((rc = upload_plan(ctx, f->fwd_step)) != GMRFB_OK) return rc;
   if ((rc = upload_plan(ctx, f->bwd_last)) != GMRFB_OK) return rc;
   if ((rc = upload_plan(ctx, f->bwd_step)) != GMRFB_OK) return rc;
+  for (DevPlan* dp : {&f->fwd_first, &f->fwd_step, &f->bwd_last, &f->bwd_step})
+    if ((rc = ensure_dinv(f, dp->host)) != GMRFB_OK) return rc;
   f->plan_nrhs = nrhs;
   return GMRFB_OK;
 }
@@ -371,6 +385,7 @@ static gmrfb_status btd_sweep(gmrfb_btd* f, bool fwd, bool bwd, double* dXt, int
   if (fwd) {
     for (int64_t i = 0; i < f->N; i++) {
       Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, nullptr, nullptr}};
+      ar.dinv = f->dinv.p;
       rc = run_plan(ctx, i == 0 ? f->fwd_first : f->fwd_step, ar, aux);
       if (rc != GMRFB_OK) return rc;
     }
@@ -378,6 +393,7 @@ static gmrfb_status btd_sweep(gmrfb_btd* f, bool fwd, bool bwd, double* dXt, int
   if (bwd) {
     for (int64_t i = f->N - 1; i >= 0; i--) {
       Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, nullptr, nullptr}};
+      ar.dinv = f->dinv.p;
       rc = run_plan(ctx, i == f->N - 1 ? f->bwd_last : f->bwd_step, ar, aux);
       if (rc != GMRFB_OK) return rc;
     }
@@ -501,6 +517,8 @@ extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
     gmrfb_status rc;
     if ((rc = upload_plan(ctx, f->sel_last)) != GMRFB_OK) return rc;
     if ((rc = upload_plan(ctx, f->sel_step)) != GMRFB_OK) return rc;
+    if ((rc = ensure_dinv(f, f->sel_last.host)) != GMRFB_OK) return rc;
+    if ((rc = ensure_dinv(f, f->sel_step.host)) != GMRFB_OK) return rc;
     f->sel_ready = true;
   }
   DevBuf<double> S0, S1, T, dvar;
@@ -514,6 +532,7 @@ extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
   double* cur = S1.p;
   for (int64_t i = f->N - 1; i >= 0; i--) {
     Arenas ar{{f->arena.p + i * f->slot, prev, T.p, cur}};
+    ar.dinv = f->dinv.p;
     gmrfb_status rc = run_plan(ctx, i == f->N - 1 ? f->sel_last : f->sel_step, ar, aux);
     if (rc != GMRFB_OK) return rc;
     k_diag_strided<<<(unsigned)((b + 255) / 256), 256, 0, ctx->stream>>>(cur, ld, b, dvar.p + i * f->b);
@@ -613,7 +632,10 @@ gmrfb_status trsm_once(gmrfb_ctx* ctx, bool trans, const double* L, int ldl, dou
       plan_trsm_rln(B, P.host, 0, 0, ldl, 1, 0, M, b, ldx, false);
   }
   GMRFB_CU(ctx, P.tasks.upload(P.host.tasks, ctx->stream));
+  DevBuf<double> dinv;
+  GMRFB_CU(ctx, dinv.alloc((size_t)std::max<int64_t>(P.host.dinv, 1)));
   Arenas ar{{const_cast<double*>(L), X, nullptr, nullptr}};
+  ar.dinv = dinv.p;
   LaunchAux aux;
   aux.d_info = ctx->d_info;
   gmrfb_status rc = run_plan(ctx, P, ar, aux);

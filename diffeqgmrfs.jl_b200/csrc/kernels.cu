@@ -4,8 +4,8 @@
 //                  mma.sync.aligned.m8n8k4.f64 — tcgen05 has no f64 kind; measured 37.1 TFLOP/s peak on B200,
 //                  profiles/r01_fp64_probe.txt).  Used for every SYRK/GEMM of the multifrontal factorisation,
 //                  selected inversion and the block-tridiagonal factor.
-//  k_potrf64       Cholesky of one <=64x64 diagonal block per CTA in shared memory.
-//  k_trsm_rlt/rln  X <- X L^{-T} / X L^{-1} with a <=64x64 triangle: one matrix row per thread in registers.
+//  k_potrf64       Cholesky + inverse of one <=64x64 diagonal block per CTA in shared memory (DMMA panel updates).
+//  k_apply_inv     X <- X L^{-T} / X L^{-1} as a DMMA product with the inverted <=64x64 triangle.
 //  k_extend_add, k_gather_sym, ...  index-mapped assembly kernels of the multifrontal method.
 //
 // No CPU fallback exists for any of these; the host only builds task lists (plan.cpp) and launches.
@@ -245,189 +245,243 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const Task* __restrict__ tasks,
 }
 
 // -------------------------------------------------------------------------------------------- POTRF ----
-// In-place Cholesky of an n x n (n <= 64) diagonal block; only the lower triangle is read and written.
-// The block sits in shared memory (identity padding up to 64).  Columns are processed in panels of 8: threads
-// 0..63 own one matrix row each and keep their 8 panel entries in registers (the 8x8 diagonal block is kept
-// symmetric-full so the pivot row broadcast yields l(k,c) directly), one rsqrt per column on the critical path;
-// the rank-8 trailing update then runs on all 128 threads.  Small code (no full unrolling): it has to run at
-// instruction-cache speed because it sits on the dependent chain of every blocked factorisation.
-// A non-positive or NaN pivot records (aux0 + j) in *info (minimum over all failures) and poisons the block.
-constexpr int P_LD = 65;
-__global__ void __launch_bounds__(128) k_potrf64(const Task* __restrict__ tasks, int ntasks, Arenas ar,
+// Cholesky AND inverse of an n x n (n <= 64) diagonal block, one CTA (8 warps) per block, everything in shared
+// memory (identity padding up to 64).  The block sits on the dependent chain of every blocked factorisation, so it is
+// organised for latency:
+//   factor : 8-column panels.  Threads 0..63 own one matrix row each; every one of them factors the 8x8 diagonal
+//            block of the panel redundantly in registers (no synchronisation inside a panel, one rsqrt per column)
+//            and solves its own row against it; the rank-8 trailing update then runs as 8x8 DMMA tiles on all warps.
+//            16 barriers per block instead of two per column.
+//   invert : W = L^{-1} by recursive doubling — the eight 8x8 diagonal blocks in registers, then three merge levels
+//            inv([A 0; B C]) = [A^{-1} 0; -C^{-1} B A^{-1}  C^{-1}], each two batched DMMA products.
+// The inverse turns every later "X L^{-T}" / "X L^{-1}" with this block into a tensor-core product (k_apply_inv).
+// Only <= 64x64 diagonal blocks are ever inverted; the error this adds is O(cond(L_jj) eps), as in blocked TRSMs of
+// dense GPU libraries.  Task: a/lda/M = block, b/ldb = destination of W (arena B bits, or ar.dinv when TF_B_DINV),
+// aux0 = global column for failure reports, TF_NOFACTOR = the block already holds L (invert only).
+constexpr int PLD = 68;  // leading dimension of the 64x64 smem matrices: = 4 (mod 16) => conflict-free fragment reads
+
+__device__ __forceinline__ double* task_b_ptr(const Task& T, const Arenas& ar) {
+  return ((T.flags & TF_B_DINV) ? ar.dinv : ar.p[(T.flags >> TF_B_SHIFT) & 3]) + T.b;
+}
+
+__global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks, int ntasks, Arenas ar,
                                                  int* __restrict__ info) {
-  __shared__ double S[64 * P_LD];
-  __shared__ double pr[8];
+  extern __shared__ __align__(16) double psm[];
+  double* S = psm;             // the block / its factor L, column-major S[c * PLD + r]
+  double* W = S + 64 * PLD;    // L^{-1}
+  double* Tm = W + 64 * PLD;   // scratch of the merge levels
   const Task T = tasks[blockIdx.x];
   const int n = T.M, lda = T.lda;
   double* __restrict__ A = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
-  const int tid = threadIdx.x, i = tid & 63, half = tid >> 6;
-  {
-    double v[32];
-#pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int k = half + 2 * u;
-      v[u] = (i == k) ? 1.0 : 0.0;
-      if (i < n && k <= i) v[u] = A[i + (int64_t)k * lda];
-    }
-#pragma unroll
-    for (int u = 0; u < 32; u++) S[(half + 2 * u) * P_LD + i] = v[u];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int i = e & 63, k = e >> 6;
+    double v = (i == k) ? 1.0 : 0.0;
+    if (i < n && k <= i) v = A[i + (int64_t)k * lda];
+    S[k * PLD + i] = v;
+    W[k * PLD + i] = 0.0;
   }
   __syncthreads();
-  bool bad = false;
-  for (int jb = 0; jb < 8; jb++) {
-    const int j0 = jb * 8;
-    if (j0 >= n) break;
-    double p[8];
-    if (half == 0) {
+  const int nb8 = (n + 7) >> 3;
+  if (!(T.flags & TF_NOFACTOR)) {
+    bool bad = false;
+    for (int p = 0; p < nb8; p++) {
+      const int j0 = p * 8;
+      const bool rowt = tid < 64 && tid >= j0;
+      double x[8];
+      if (rowt) {
+        const int i = tid;
+        double D[8][8], invd[8];
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const int col = j0 + c;
-        p[c] = (i >= col) ? S[col * P_LD + i] : S[i * P_LD + col];  // mirror inside the diagonal block / above it unused
-      }
-    }
+        for (int c = 0; c < 8; c++)
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-      if (half == 0 && i == j0 + c) {
+          for (int k = 0; k <= c; k++) D[c][k] = S[(j0 + k) * PLD + j0 + c];
 #pragma unroll
-        for (int c2 = c; c2 < 8; c2++) pr[c2] = p[c2];
-      }
-      __syncthreads();
-      if (half == 0) {
-        const double d = pr[c];
-        double dinv;
-        if (d > 0.0) {
-          dinv = rsqrt(d);
-        } else {
-          dinv = nan("");
-          if (i == j0 + c && j0 + c < n) bad = true;
+        for (int c = 0; c < 8; c++) {
+          double d = D[c][c];
+#pragma unroll
+          for (int k = 0; k < c; k++) d -= D[c][k] * D[c][k];
+          double r;
+          if (d > 0.0) {
+            r = rsqrt(d);
+          } else {
+            r = nan("");
+            if (i == j0 + c && i < n) bad = true;
+          }
+          invd[c] = r;
+          D[c][c] = d * r;
+#pragma unroll
+          for (int i2 = c + 1; i2 < 8; i2++) {
+            double v = D[i2][c];
+#pragma unroll
+            for (int k = 0; k < c; k++) v -= D[i2][k] * D[c][k];
+            D[i2][c] = v * r;
+          }
         }
-        const double lic = (i == j0 + c) ? d * dinv : p[c] * dinv;
-        p[c] = lic;
 #pragma unroll
-        for (int c2 = c + 1; c2 < 8; c2++) p[c2] -= lic * (pr[c2] * dinv);
+        for (int c = 0; c < 8; c++) x[c] = S[(j0 + c) * PLD + i];
+        const int ii = i - j0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          double v = x[c];
+#pragma unroll
+          for (int k = 0; k < c; k++) v -= x[k] * D[c][k];
+          // rows inside the diagonal block reproduce L's row for c <= ii (diagonal: d * rsqrt(d)); zero above it
+          x[c] = (c > ii) ? 0.0 : v * invd[c];
+        }
+      }
+      __syncthreads();  // every row thread has read the 8x8 diagonal block before its rows are overwritten
+      if (rowt) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) S[(j0 + c) * PLD + tid] = x[c];
+      }
+      __syncthreads();
+      const int first = p + 1, m = nb8 - first;
+      for (int t = warp; t < m * (m + 1) / 2; t += 8) {
+        int ti, tj;
+        tri_decode(t, ti, tj);
+        ti += first;
+        tj += first;
+        double* cp = S + (tj * 8 + 2 * lc) * PLD + ti * 8 + lr;
+        double c0 = cp[0], c1 = cp[PLD];
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+          const double a = -S[(j0 + 4 * kk + lc) * PLD + ti * 8 + lr];
+          const double b = S[(j0 + 4 * kk + lc) * PLD + tj * 8 + lr];
+          dmma884(c0, c1, a, b);
+        }
+        cp[0] = c0;
+        cp[PLD] = c1;
       }
       __syncthreads();
     }
-    if (half == 0 && i >= j0) {
+    if (bad) atomicMin(info, T.aux0 + tid);
+    for (int e = tid; e < 64 * 64; e += 256) {
+      const int i = e & 63, k = e >> 6;
+      if (i < n && k <= i) A[i + (int64_t)k * lda] = S[k * PLD + i];
+    }
+  }
+  // ---- W = L^{-1}: 8x8 diagonal blocks, one column per thread ----
+  if (tid < 64) {
+    const int bi = tid >> 3, cj = tid & 7, o = bi * 8;
+    double l[8][8], x[8];
 #pragma unroll
-      for (int c = 0; c < 8; c++)
-        if (i >= j0 + c) S[(j0 + c) * P_LD + i] = p[c];
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int k = 0; k <= r; k++) l[r][k] = S[(o + k) * PLD + o + r];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      double v = (r == cj) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; k++) v -= l[r][k] * x[k];
+      x[r] = v / l[r][r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) W[(o + cj) * PLD + o + r] = x[r];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int h = 8; h < 64; h *= 2) {
+    const int tp = h >> 3, tpp = tp * tp, ntile = (64 / (2 * h)) * tpp;
+    // T = L_BA W_AA
+    for (int t = warp; t < ntile; t += 8) {
+      const int q = t / tpp, rem = t - q * tpp, ti = rem / tp, tj = rem - ti * tp;
+      const int ao = q * 2 * h, co = ao + h;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k4 = 0; k4 < h; k4 += 4) {
+        const double a = S[(ao + k4 + lc) * PLD + co + ti * 8 + lr];
+        const double b = W[(ao + tj * 8 + lr) * PLD + ao + k4 + lc];
+        dmma884(c0, c1, a, b);
+      }
+      double* tp_ = Tm + (ao + tj * 8 + 2 * lc) * PLD + co + ti * 8 + lr;
+      tp_[0] = c0;
+      tp_[PLD] = c1;
     }
     __syncthreads();
-    // rank-8 update of the trailing block: S(i,k) -= sum_c l(i,c) l(k,c), j0+8 <= k <= i; two threads per row
-    if (half == 1) {
-#pragma unroll
-      for (int c = 0; c < 8; c++) p[c] = S[(j0 + c) * P_LD + i];
-    }
-    for (int k = j0 + 8 + half; k <= i; k += 2) {
-      double acc = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; c++) acc += p[c] * S[(j0 + c) * P_LD + k];
-      S[k * P_LD + i] -= acc;
+    // W_BA = -W_CC T
+    for (int t = warp; t < ntile; t += 8) {
+      const int q = t / tpp, rem = t - q * tpp, ti = rem / tp, tj = rem - ti * tp;
+      const int ao = q * 2 * h, co = ao + h;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k4 = 0; k4 < h; k4 += 4) {
+        const double a = -W[(co + k4 + lc) * PLD + co + ti * 8 + lr];
+        const double b = Tm[(ao + tj * 8 + lr) * PLD + co + k4 + lc];
+        dmma884(c0, c1, a, b);
+      }
+      double* wp = W + (ao + tj * 8 + 2 * lc) * PLD + co + ti * 8 + lr;
+      wp[0] = c0;
+      wp[PLD] = c1;
     }
     __syncthreads();
   }
-  if (bad) atomicMin(info, T.aux0 + i);
   {
-#pragma unroll 8
-    for (int u = 0; u < 32; u++) {
-      const int k = half + 2 * u;
-      if (i < n && k <= i) A[i + (int64_t)k * lda] = S[k * P_LD + i];
+    double* __restrict__ Wg = task_b_ptr(T, ar);
+    const int ldb = T.ldb;
+    const int nw = (T.flags & TF_B_DINV) ? 64 : n;  // scratch slots are full 64x64 (identity padded)
+    for (int e = tid; e < 64 * 64; e += 256) {
+      const int i = e & 63, k = e >> 6;
+      if (i < nw && k < nw) Wg[i + (int64_t)k * ldb] = W[k * PLD + i];
     }
   }
 }
 
-// --------------------------------------------------------------------------------------------- TRSM ----
-// One CTA = TRSM_ROWS rows of X, one row per thread; the <=64x64 triangle sits in shared memory padded to 64x64
-// with an identity.  The row is processed in 8-column blocks held in registers while the already solved part of
-// the row is parked in shared memory, so the code stays small (instruction-cache resident) and every inner
-// product is an unrolled 8x8 micro-kernel with broadcast reads of the triangle.
-constexpr int T_LDX = 65;
+// ------------------------------------------------------------------------------------- apply inverse ----
+// X (M x N, N <= 64) <- +-X W' (TRANS: "X L^{-T}") or +-X W (!TRANS: "X L^{-1}") with W = L^{-1} from k_potrf64.
+// One CTA = 128 rows, one warp = 16 rows: the A fragments are loaded straight from global memory (issued before W
+// is staged, so their latency overlaps), the product runs on DMMA, the result is written in place.
 template <bool TRANS>
-__global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
-  extern __shared__ __align__(16) double tsm[];
-  double* Ls = tsm;                 // 64 x 64, column-major
-  double* invd = Ls + 64 * 64;      // 64
-  double* Xs = invd + 64;           // TRSM_ROWS x T_LDX: row r of this CTA at Xs[r * T_LDX + c]
+__global__ void __launch_bounds__(256) k_apply_inv(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
+  __shared__ double Ws[64 * PLD];
   const int tix = find_task(tasks, ntasks, blockIdx.x);
   const Task T = tasks[tix];
   const int M = T.M, N = T.N;
-  const double* __restrict__ L = ar.p[(T.flags >> TF_B_SHIFT) & 3] + T.b;
+  const double* __restrict__ Wg = task_b_ptr(T, ar);
   double* __restrict__ X = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
-  const int ldl = T.ldb, ldx = T.ldc;
-  const int tid = threadIdx.x;
-  {
-    const int r = tid & 63, c0 = tid >> 6;
-    double v[32];
+  const int ldw = T.ldb, ldx = T.ldc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int row0 = (blockIdx.x - T.tile0) * TRSM_ROWS + warp * 16;
+  double a[2][16];
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int c = c0 + 2 * u;
-      v[u] = (r == c) ? 1.0 : 0.0;
-      if (r < N && c < N && r >= c) v[u] = L[r + (int64_t)c * ldl];
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      const int r = row0 + mt * 8 + lr, c = 4 * kk + lc;
+      a[mt][kk] = (r < M && c < N) ? X[r + (int64_t)c * ldx] : 0.0;
     }
-#pragma unroll
-    for (int u = 0; u < 32; u++) Ls[(c0 + 2 * u) * 64 + r] = v[u];
-  }
-  const int row = (blockIdx.x - T.tile0) * TRSM_ROWS + tid;
-  const bool live = row < M;
-  double* xs = Xs + tid * T_LDX;
-  {
-#pragma unroll 16
-    for (int j = 0; j < 64; j++) xs[j] = (live && j < N) ? X[row + (int64_t)j * ldx] : 0.0;
+  const int nw = (T.flags & TF_B_DINV) ? 64 : N;
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int i = e & 63, k = e >> 6;
+    Ws[k * PLD + i] = (i < nw && k < nw) ? Wg[i + (int64_t)k * ldw] : ((i == k) ? 1.0 : 0.0);
   }
   __syncthreads();
-  if (tid < 64) invd[tid] = 1.0 / Ls[tid * 64 + tid];
-  __syncthreads();
-  if (TRANS) {
-    // x L' = b:  blocks ascending.  x_J = (b_J - sum_{K<J} x_K L[J,K]') L[J,J]^{-T}
-    for (int jb = 0; jb < 8; jb++) {
-      const int j0 = jb * 8;
-      if (j0 >= N) break;
-      double xb[8];
+  if (row0 >= M) return;
+  double acc[2][8][2];
 #pragma unroll
-      for (int c = 0; c < 8; c++) xb[c] = xs[j0 + c];
-      for (int k = 0; k < j0; k++) {
-        const double xk = xs[k];
+  for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int c = 0; c < 8; c++) xb[c] -= xk * Ls[k * 64 + j0 + c];  // L[j0+c][k]
-      }
+    for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        xb[c] *= invd[j0 + c];
+  for (int kk = 0; kk < 16; kk++)
 #pragma unroll
-        for (int c2 = c + 1; c2 < 8; c2++) xb[c2] -= xb[c] * Ls[(j0 + c) * 64 + j0 + c2];
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c++) xs[j0 + c] = xb[c];
+    for (int nt = 0; nt < 8; nt++) {
+      // W is lower triangular: (X W')[:, n] needs k <= n, (X W)[:, n] needs k >= n
+      if (TRANS ? (kk > 2 * nt + 1) : (kk < 2 * nt)) continue;
+      const double b = TRANS ? Ws[(4 * kk + lc) * PLD + nt * 8 + lr] : Ws[(nt * 8 + lr) * PLD + 4 * kk + lc];
+      dmma884(acc[0][nt][0], acc[0][nt][1], a[0][kk], b);
+      dmma884(acc[1][nt][0], acc[1][nt][1], a[1][kk], b);
     }
-  } else {
-    // x L = b:  blocks descending.  x_J = (b_J - sum_{K>J} x_K L[K,J]) L[J,J]^{-1}
-    for (int jb = 7; jb >= 0; jb--) {
-      const int j0 = jb * 8;
-      if (j0 >= N) continue;
-      double xb[8];
-#pragma unroll
-      for (int c = 0; c < 8; c++) xb[c] = xs[j0 + c];
-      for (int k = 63; k >= j0 + 8; k--) {
-        const double xk = xs[k];
-#pragma unroll
-        for (int c = 0; c < 8; c++) xb[c] -= xk * Ls[(j0 + c) * 64 + k];  // L[k][j0+c]
-      }
-#pragma unroll
-      for (int c = 7; c >= 0; c--) {
-        xb[c] *= invd[j0 + c];
-#pragma unroll
-        for (int c2 = 0; c2 < c; c2++) xb[c2] -= xb[c] * Ls[(j0 + c2) * 64 + j0 + c];  // L[j0+c][j0+c2]
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c++) xs[j0 + c] = xb[c];
-    }
-  }
-  if (!live) return;
   const double sgn = (T.flags & TF_NEG) ? -1.0 : 1.0;
-#pragma unroll 16
-  for (int j = 0; j < 64; j++)
-    if (j < N) X[row + (int64_t)j * ldx] = sgn * xs[j];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int r = row0 + mt * 8 + lr, c = nt * 8 + 2 * lc + h;
+        if (r < M && c < N) X[r + (int64_t)c * ldx] = sgn * acc[mt][nt][h];
+      }
 }
 
 // ------------------------------------------------------------------------------ multifrontal assembly ----
@@ -502,13 +556,45 @@ __global__ void __launch_bounds__(256) k_gather_sym(const Task* __restrict__ tas
 
 // ------------------------------------------------------------------------ fused small-front kernels ----
 // Fronts of order d <= SMALL_FRONT_MAX are processed by ONE CTA entirely in shared memory (the front is staged
-// once, every operation of the multifrontal step runs on-chip, results are written once):
-//   factor : load the assembled panel, extend-add the children's update matrices (fixed order), partial
-//            Cholesky of the first s columns with the full trailing update, write L and the update matrix.
-//   selinv : gather Z_RR from the parent's inverse front, then the dense Takahashi recurrence column by column
-//            (Z_ij = (delta_ij / L_jj - sum_{k>j} L_kj Z_ik) / L_jj), write the inverse front and its diagonal.
+// once, every operation of the multifrontal step runs on-chip, results are written once).  Both kernels work in
+// 8-column panels: the 8x8 diagonal block is handled redundantly in registers by one thread per front row (no
+// barrier inside a panel), everything of rank 8 or higher runs as 8x8x4 DMMA tiles on all warps.
+//   factor : stage the assembled panel, extend-add the children's update matrices (fixed order), partial Cholesky
+//            of the first s columns with the full trailing update, write L and the update matrix.
+//   selinv : gather Z_RR from the parent's inverse front, then per panel J (right to left), with B = rows below J:
+//            Y = L_BJ L_JJ^{-1},  Z_BJ = -Z_BB Y,  Z_JJ = L_JJ^{-T} L_JJ^{-1} - Y' Z_BJ;  write the inverse front.
+// Shared layout: column-major with leading dimension ld = roundup(d, 8) + 4 (= 4 mod 8: conflict-free fragments).
 // Task encoding: aux0 = supernode index.
-__global__ void __launch_bounds__(256) k_front_factor_small(const Task* __restrict__ tasks, Arenas ar,
+__host__ __device__ __forceinline__ int sf_ld(int d) { return ((d + 7) & ~7) + 4; }
+
+// right-looking Cholesky of the 8x8 block in registers (lower part); invd[c] = 1 / L_cc.  Returns the first failing
+// column or 8.
+__device__ __forceinline__ int chol8(double (&D)[8][8], double (&invd)[8]) {
+  int bad = 8;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const double d = D[c][c];
+    double r;
+    if (d > 0.0) {
+      r = rsqrt(d);
+    } else {
+      r = nan("");
+      if (bad == 8) bad = c;
+    }
+    invd[c] = r;
+    D[c][c] = d * r;
+#pragma unroll
+    for (int i = c + 1; i < 8; i++) D[i][c] *= r;
+#pragma unroll
+    for (int j = c + 1; j < 8; j++)
+#pragma unroll
+      for (int i = j; i < 8; i++) D[i][j] -= D[i][c] * D[j][c];
+  }
+  return bad;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restrict__ tasks, Arenas ar,
                                                             const SnodeDesc* __restrict__ sd,
                                                             const int32_t* __restrict__ child_idx,
                                                             const int32_t* __restrict__ relmap,
@@ -517,12 +603,14 @@ __global__ void __launch_bounds__(256) k_front_factor_small(const Task* __restri
   __shared__ int32_t rel[SMALL_FRONT_MAX];
   const SnodeDesc D = sd[tasks[blockIdx.x].aux0];
   const int d = D.d, s = D.s, ldg = D.ld;
-  const int lds = d | 1;
+  const int dp = (d + 7) & ~7, lds = dp + 4;
+  double* Pb = S + (size_t)dp * lds;  // zero-padded copy of the current panel, 8 columns x lds
   double* __restrict__ F = ar.p[0] + D.foff;
-  const int tid = threadIdx.x, ti = tid & 63, tq = tid >> 6;
-  // stage: panel columns from the arena, update-matrix part starts from zero
-  for (int c = tq; c < d; c += 4)
-    for (int i = ti; i < d; i += 64) S[c * lds + i] = (c < s && i >= c) ? F[(int64_t)c * ldg + i] : 0.0;
+  const int tid = threadIdx.x, ti_ = tid & 63, tq = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  // stage: panel columns from the arena, update-matrix part and padding start from zero
+  for (int c = tq; c < dp; c += NT / 64)
+    for (int i = ti_; i < dp; i += 64) S[c * lds + i] = (c < s && i >= c && i < d) ? F[(int64_t)c * ldg + i] : 0.0;
   __syncthreads();
   for (int ci = 0; ci < D.nchild; ci++) {
     const SnodeDesc C = sd[child_idx[D.child0 + ci]];
@@ -530,110 +618,240 @@ __global__ void __launch_bounds__(256) k_front_factor_small(const Task* __restri
     const double* __restrict__ U = ar.p[0] + C.foff + (int64_t)C.s * C.ld + C.s;
     const int32_t* __restrict__ rl = relmap + C.rows_off + C.s;
     if (rc <= SMALL_FRONT_MAX) {
-      for (int i = tid; i < rc; i += 256) rel[i] = rl[i];
+      for (int i = tid; i < rc; i += NT) rel[i] = rl[i];
       __syncthreads();
-      for (int j = tq; j < rc; j += 4) {
+      for (int j = tq; j < rc; j += NT / 64) {
         const int pj = rel[j];
-        for (int i = j + ti - (j & 63) + ((ti < (j & 63)) ? 64 : 0); i < rc; i += 64)
+        for (int i = j + ti_ - (j & 63) + ((ti_ < (j & 63)) ? 64 : 0); i < rc; i += 64)
           S[pj * lds + rel[i]] += U[i + (int64_t)j * C.ld];
       }
     } else {
       // a child with a long boundary: its rows still all map inside this (small) front
-      for (int j = tq; j < rc; j += 4) {
+      for (int j = tq; j < rc; j += NT / 64) {
         const int pj = rl[j];
-        for (int i = j + ti - (j & 63) + ((ti < (j & 63)) ? 64 : 0); i < rc; i += 64)
+        for (int i = j + ti_ - (j & 63) + ((ti_ < (j & 63)) ? 64 : 0); i < rc; i += 64)
           S[pj * lds + rl[i]] += U[i + (int64_t)j * C.ld];
       }
     }
     __syncthreads();
   }
-  for (int j = 0; j < s; j++) {
-    const double dj = S[j * lds + j];
-    __syncthreads();
-    double ljj;
-    if (dj > 0.0) {
-      ljj = sqrt(dj);
-    } else {
-      ljj = nan("");
-      if (tid == 0) atomicMin(info, D.col0 + j);
+  for (int j0 = 0; j0 < s; j0 += 8) {
+    const int pw = min(8, s - j0);
+    const int i = j0 + tid;
+    const bool rowt = i < dp;
+    double x[8];
+    if (rowt) {
+      double Dg[8][8], invd[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int k = 0; k <= c; k++) Dg[c][k] = (c < pw) ? S[(j0 + k) * lds + j0 + c] : ((c == k) ? 1.0 : 0.0);
+      const int bad = chol8(Dg, invd);
+      if (bad < pw && tid == 0) atomicMin(info, D.col0 + j0 + bad);
+#pragma unroll
+      for (int c = 0; c < 8; c++) x[c] = (c < pw) ? S[(j0 + c) * lds + i] : 0.0;
+      const int ii = i - j0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        x[c] *= invd[c];
+#pragma unroll
+        for (int j = c + 1; j < 8; j++) x[j] -= x[c] * Dg[j][c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        if (c > ii) x[c] = 0.0;  // rows of the diagonal block: L's row up to the diagonal, zero above
     }
-    const double inv = 1.0 / ljj;
-    for (int i = j + tid; i < d; i += 256) S[j * lds + i] = (i == j) ? ljj : S[j * lds + i] * inv;
+    __syncthreads();  // all row threads have read the diagonal block
+    if (rowt) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (c < pw) S[(j0 + c) * lds + i] = x[c];
+        Pb[c * lds + i] = x[c];
+      }
+    }
     __syncthreads();
-    for (int k = j + 1 + tq; k < d; k += 4) {
-      const double lk = S[j * lds + k];
-      for (int i = k + ti - (k & 63) + ((ti < (k & 63)) ? 64 : 0); i < d; i += 64) S[k * lds + i] -= S[j * lds + i] * lk;
+    // trailing update S[i][k] -= sum_c P[i][c] P[k][c] for k >= j0 + pw, lower tiles
+    {
+      const int m0 = j0 + pw;  // first column that is updated
+      const int t0 = m0 >> 3, m = (dp >> 3) - t0;
+      for (int t = warp; t < m * (m + 1) / 2; t += NT / 32) {
+        int ti, tj;
+        tri_decode(t, ti, tj);
+        ti += t0;
+        tj += t0;
+        double* cp = S + (tj * 8 + 2 * lc) * lds + ti * 8 + lr;
+        double c0 = cp[0], c1 = cp[lds];
+        const bool kvalid = (tj * 8 + lr) >= m0;  // columns of the panel itself are not updated
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+          const double a = -Pb[(4 * kk + lc) * lds + ti * 8 + lr];
+          const double b = kvalid ? Pb[(4 * kk + lc) * lds + tj * 8 + lr] : 0.0;
+          dmma884(c0, c1, a, b);
+        }
+        cp[0] = c0;
+        cp[lds] = c1;
+      }
     }
     __syncthreads();
   }
-  for (int c = tq; c < d; c += 4)
-    for (int i = c + ti - (c & 63) + ((ti < (c & 63)) ? 64 : 0); i < d; i += 64) F[(int64_t)c * ldg + i] = S[c * lds + i];
+  for (int c = tq; c < d; c += NT / 64)
+    for (int i = c + ti_ - (c & 63) + ((ti_ < (c & 63)) ? 64 : 0); i < d; i += 64) F[(int64_t)c * ldg + i] = S[c * lds + i];
 }
 
-__global__ void __launch_bounds__(256) k_front_selinv_small(const Task* __restrict__ tasks, Arenas ar,
+template <int NT>
+__global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restrict__ tasks, Arenas ar,
                                                             const SnodeDesc* __restrict__ sd,
                                                             const int32_t* __restrict__ relmap,
                                                             const int32_t* __restrict__ sparent,
                                                             double* __restrict__ zdiag) {
   extern __shared__ __align__(16) double Z[];
-  __shared__ double lcol[SMALL_FRONT_MAX];
-  __shared__ double part[4][SMALL_FRONT_MAX];
   __shared__ int32_t rel[SMALL_FRONT_MAX];
-  __shared__ double red[8];
+  __shared__ double Wb[8][8];      // L_JJ^{-1} of the current panel
+  __shared__ double part[NT / 32][64];   // per-warp partial sums of Y' Z_BJ
   const int sidx = tasks[blockIdx.x].aux0;
   const SnodeDesc D = sd[sidx];
   const int d = D.d, s = D.s, r = d - s, ldg = D.ld;
-  const int lds = d | 1;
+  const int dp = (d + 7) & ~7, lds = dp + 4;
+  double* Lb = Z + (size_t)dp * lds;  // current panel of L (8 columns x lds, zero padded)
+  double* Yb = Lb + 8 * lds;          // Y = L_BJ L_JJ^{-1}   (rows outside B are zero)
   const double* __restrict__ L = ar.p[0] + D.foff;
   double* __restrict__ Zg = ar.p[1] + D.foff;
-  const int tid = threadIdx.x, ti = tid & 63, tq = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, ti_ = tid & 63, tq = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int c = tq; c < dp; c += NT / 64)
+    for (int i = ti_; i < dp; i += 64) Z[c * lds + i] = 0.0;
+  __syncthreads();
   if (r > 0) {
     const SnodeDesc P = sd[sparent[sidx]];
     const double* __restrict__ Zp = ar.p[1] + P.foff;
     const int32_t* __restrict__ rl = relmap + D.rows_off + s;
-    for (int i = tid; i < r; i += 256) rel[i] = rl[i];
+    for (int i = tid; i < r; i += NT) rel[i] = rl[i];
     __syncthreads();
-    for (int j = tq; j < r; j += 4) {
+    for (int j = tq; j < r; j += NT / 64) {
       const int64_t b = rel[j];
-      for (int i = ti; i < r; i += 64) {
+      for (int i = ti_; i < r; i += 64) {
         const int64_t a = rel[i];
         Z[(s + j) * lds + s + i] = (a >= b) ? Zp[a + b * P.ld] : Zp[b + a * P.ld];
       }
     }
   }
   __syncthreads();
-  for (int j = s - 1; j >= 0; j--) {
-    for (int i = j + tid; i < d; i += 256) lcol[i] = L[(int64_t)j * ldg + i];
-    __syncthreads();
-    const double inv = 1.0 / lcol[j];
-    // partial sums over k = j+1+tq, step 4, for every row i > j
-    for (int i = j + 1 + ti; i < d; i += 64) {
-      double acc = 0.0;
-      for (int k = j + 1 + tq; k < d; k += 4) acc += lcol[k] * Z[k * lds + i];
-      part[tq][i] = acc;
+  for (int j0 = ((s - 1) >> 3) << 3; j0 >= 0; j0 -= 8) {
+    const int pw = min(8, s - j0);
+    const int m0 = j0 + pw;  // B = [m0, d)
+    // panel of L into shared memory: Lb[c][i] = L[i][j0 + c], i >= j0 + c
+    for (int e = tid; e < 8 * dp; e += NT) {
+      const int c = e / dp, i = e - c * dp;
+      Lb[c * lds + i] = (c < pw && i >= j0 + c && i < d) ? L[(int64_t)(j0 + c) * ldg + i] : 0.0;
     }
     __syncthreads();
-    double dot = 0.0;
-    for (int i = j + 1 + tid; i < d; i += 256) {
-      const double z = -(((part[0][i] + part[1][i]) + part[2][i]) + part[3][i]) * inv;
-      Z[j * lds + i] = z;
-      Z[i * lds + j] = z;
-      dot += lcol[i] * z;
-    }
+    {
+      // every row thread inverts the (identity padded) 8x8 triangle redundantly, then forms its row of Y
+      const int i = m0 + tid;
+      if (i < dp || tid == 0) {
+        double l[8][8], w[8][8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (lane == 0) red[warp] = dot;
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+          for (int k = 0; k <= c; k++) l[c][k] = (c < pw) ? Lb[k * lds + j0 + c] : ((c == k) ? 1.0 : 0.0);
+        double invd[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) invd[c] = 1.0 / l[c][c];
+        // w = l^{-1}, column by column (forward substitution on the identity)
+#pragma unroll
+        for (int cj = 0; cj < 8; cj++) {
+#pragma unroll
+          for (int rr = 0; rr < 8; rr++) {
+            if (rr < cj) {
+              w[rr][cj] = 0.0;
+            } else {
+              double v = (rr == cj) ? 1.0 : 0.0;
+#pragma unroll
+              for (int k = cj; k < rr; k++) v -= l[rr][k] * w[k][cj];
+              w[rr][cj] = v * invd[rr];
+            }
+          }
+        }
+        if (tid == 0) {
+#pragma unroll
+          for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 8; b++) Wb[a][b] = w[a][b];
+        }
+        if (i < dp) {
+          double lrow[8], y[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) lrow[k] = Lb[k * lds + i];
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = c; k < 8; k++) v += lrow[k] * w[k][c];
+            y[c] = v;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c++) Yb[c * lds + i] = y[c];
+        }
+      }
+      // rows of the tile-aligned range below m0 do not belong to B
+      for (int e = tid; e < 8 * 8; e += NT) {
+        const int c = e >> 3, i = (m0 & ~7) + (e & 7);
+        if (i < m0) Yb[c * lds + i] = 0.0;
+      }
+    }
     __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < 8; w++) t += red[w];
-      Z[j * lds + j] = (inv - t) * inv;
+    // Z_BJ = -Z_BB Y (tiles of 8 rows), and the per-warp partial of Y' Z_BJ over the same rows
+    {
+      const int t0 = m0 >> 3, nt = (dp >> 3) - t0;
+      double p0 = 0.0, p1 = 0.0;
+      for (int t = warp; t < nt; t += NT / 32) {
+        const int row0 = (t0 + t) * 8;
+        double c0 = 0.0, c1 = 0.0;
+        for (int k4 = t0 * 8; k4 < dp; k4 += 4) {
+          const double a = -Z[(k4 + lc) * lds + row0 + lr];
+          const double b = Yb[lr * lds + k4 + lc];
+          dmma884(c0, c1, a, b);
+        }
+        const int gi = row0 + lr;
+        if (gi >= m0) {
+          // store both triangles: column j0 + c (rows in B) and row j0 + c
+          if (2 * lc < pw) {
+            Z[(j0 + 2 * lc) * lds + gi] = c0;
+            Z[gi * lds + j0 + 2 * lc] = c0;
+          }
+          if (2 * lc + 1 < pw) {
+            Z[(j0 + 2 * lc + 1) * lds + gi] = c1;
+            Z[gi * lds + j0 + 2 * lc + 1] = c1;
+          }
+        }
+        __syncwarp();
+        // partial (8x8) += Y_tile' Z_BJ_tile  (k = the 8 rows of this tile)
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+          const int kr = row0 + 4 * kk + lc;
+          const double a = Yb[lr * lds + kr];
+          const double b = (kr >= m0) ? Z[(j0 + lr) * lds + kr] : 0.0;
+          dmma884(p0, p1, a, b);
+        }
+      }
+      part[warp][lr * 8 + 2 * lc] = p0;
+      part[warp][lr * 8 + 2 * lc + 1] = p1;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      const int a = tid >> 3, b = tid & 7;  // Z_JJ[a][b] = (W'W)[a][b] - sum_w part[w][a][b]
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) v += Wb[k][a] * Wb[k][b];
+#pragma unroll
+      for (int w = 0; w < NT / 32; w++) v -= part[w][a * 8 + b];
+      if (a < pw && b < pw) Z[(j0 + b) * lds + j0 + a] = v;
     }
     __syncthreads();
   }
-  for (int c = tq; c < d; c += 4)
-    for (int i = c + ti - (c & 63) + ((ti < (c & 63)) ? 64 : 0); i < d; i += 64) Zg[(int64_t)c * ldg + i] = Z[c * lds + i];
-  for (int c = tid; c < s; c += 256) zdiag[D.col0 + c] = Z[c * lds + c];
+  for (int c = tq; c < d; c += NT / 64)
+    for (int i = c + ti_ - (c & 63) + ((ti_ < (c & 63)) ? 64 : 0); i < d; i += 64) Zg[(int64_t)c * ldg + i] = Z[c * lds + i];
+  for (int c = tid; c < s; c += NT) zdiag[D.col0 + c] = Z[c * lds + c];
 }
 
 // Simple element-wise task kernels: one CTA per 64x64 tile.
@@ -707,7 +925,7 @@ __global__ void k_scatter_values(const double* __restrict__ nzval, const int64_t
 }
 
 // ---------------------------------------------------------------------------------- host launchers ----
-static size_t trsm_smem() { return (size_t)(64 * 64 + 64 + TRSM_ROWS * T_LDX) * sizeof(double); }
+static size_t potrf_smem() { return (size_t)(3 * 64 * PLD) * sizeof(double); }
 static size_t gemm_smem(bool ta, bool tb) {
   size_t a = ta ? G_A_STAGE_T : G_A_STAGE_N, b = tb ? G_B_STAGE_T : G_B_STAGE_N;
   return (a + b) * G_STAGES * sizeof(double);
@@ -727,14 +945,16 @@ cudaError_t kernels_init() {
   e = cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)gemm_smem(true, false));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_trsm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem());
+  e = cudaFuncSetAttribute(k_potrf64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_trsm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem());
+  const int small_smem = small_front_smem(SMALL_FRONT_MAX);
+  e = cudaFuncSetAttribute(k_front_factor_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   if (e != cudaSuccess) return e;
-  const int small_smem = SMALL_FRONT_MAX * (SMALL_FRONT_MAX | 1) * (int)sizeof(double);
-  e = cudaFuncSetAttribute(k_front_factor_small, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+  e = cudaFuncSetAttribute(k_front_selinv_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_front_selinv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+  e = cudaFuncSetAttribute(k_front_factor_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_front_selinv_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   return e;
 }
 
@@ -756,13 +976,13 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       k_gemm<true, false><<<L.grid, 256, gemm_smem(true, false), st>>>(t, L.ntasks, ar);
       break;
     case LK_POTRF:
-      k_potrf64<<<L.grid, 128, 0, st>>>(t, L.ntasks, ar, aux.d_info);
+      k_potrf64<<<L.grid, 256, potrf_smem(), st>>>(t, L.ntasks, ar, aux.d_info);
       break;
     case LK_TRSM_RLT:
-      k_trsm<true><<<L.grid, TRSM_ROWS, trsm_smem(), st>>>(t, L.ntasks, ar);
+      k_apply_inv<true><<<L.grid, 256, 0, st>>>(t, L.ntasks, ar);
       break;
     case LK_TRSM_RLN:
-      k_trsm<false><<<L.grid, TRSM_ROWS, trsm_smem(), st>>>(t, L.ntasks, ar);
+      k_apply_inv<false><<<L.grid, 256, 0, st>>>(t, L.ntasks, ar);
       break;
     case LK_EXTEND_ADD:
       k_extend_add<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_relmap);
@@ -782,10 +1002,17 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       k_diag_out<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_out);
       break;
     case LK_FRONT_FACTOR_SMALL:
-      k_front_factor_small<<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_child_idx, aux.d_relmap, aux.d_info);
+      // fronts of order <= 104 need at most 104 row threads: 4-warp CTAs, more of them per SM
+      if (L.smem <= small_front_smem(104))
+        k_front_factor_small<128><<<L.grid, 128, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_child_idx, aux.d_relmap, aux.d_info);
+      else
+        k_front_factor_small<256><<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_child_idx, aux.d_relmap, aux.d_info);
       break;
     case LK_FRONT_SELINV_SMALL:
-      k_front_selinv_small<<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
+      if (L.smem <= small_front_smem(104))
+        k_front_selinv_small<128><<<L.grid, 128, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
+      else
+        k_front_selinv_small<256><<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
       break;
     default:
       return cudaErrorInvalidValue;

@@ -11,6 +11,7 @@ namespace gmrfb {
 // Up to four device arenas that Task offsets index into (selected by the TF_*_SHIFT bits of Task::flags).
 struct Arenas {
   double* p[4];
+  double* dinv = nullptr;  // scratch of inverted <=64x64 diagonal blocks (TF_B_DINV operands)
 };
 
 struct SnodeDesc;

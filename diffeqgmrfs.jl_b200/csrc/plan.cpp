@@ -42,18 +42,35 @@ void add_gemm(PlanBuilder& B, Plan& P, int aa, int64_t a, int lda, int ab, int64
   P.flops += gemm_flops(M, N, K, tri);
 }
 
-void add_trsm(PlanBuilder& B, Plan& P, int al, int64_t l, int ldl, int ax, int64_t x, int ldx, int M, int n) {
+// X (M x n) <- X W' / X W with W = L^{-1} held in inverse-block scratch slot `slot` (written by a POTRF task)
+void add_trsm(PlanBuilder& B, Plan& P, int64_t slot, int ax, int64_t x, int ldx, int M, int n) {
   if (M <= 0 || n <= 0) return;
   Task t = make_task();
-  t.b = l;
-  t.ldb = ldl;
+  t.b = slot * DINV_SLOT;
+  t.ldb = 64;
   t.c = x;
   t.ldc = ldx;
   t.M = M;
   t.N = n;
-  t.flags = arena_flags(0, al, ax);
+  t.flags = arena_flags(0, 0, ax) | TF_B_DINV;
   B.add(t, cdiv(M, TRSM_ROWS));
   P.flops += (double)M * n * n;
+  P.dinv = std::max(P.dinv, (slot + 1) * (int64_t)DINV_SLOT);
+}
+
+// Cholesky (unless nofactor) + inverse of the nb x nb block at (arena, off, ld); inverse into scratch slot `slot`
+void add_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int ld, int nb, int col0, int64_t slot, bool nofactor) {
+  Task t = make_task();
+  t.a = off;
+  t.lda = ld;
+  t.M = nb;
+  t.aux0 = col0;
+  t.b = slot * DINV_SLOT;
+  t.ldb = 64;
+  t.flags = arena_flags(arena, 0, 0) | TF_B_DINV | (nofactor ? TF_NOFACTOR : 0);
+  B.add(t, 1);
+  if (!nofactor) P.flops += (double)nb * nb * nb / 3.0;
+  P.dinv = std::max(P.dinv, (slot + 1) * (int64_t)DINV_SLOT);
 }
 
 }  // namespace
@@ -76,26 +93,24 @@ static void plan_partial_factor_batch(PlanBuilder& B, Plan& P, const std::vector
   for (int j0 = 0; j0 < max_s; j0 += nbo) {
     for (int jj = j0; jj < std::min(j0 + nbo, max_s); jj += NB) {
       B.begin(LK_POTRF);
-      for (auto& p : probs) {
-        if (jj >= p.s) continue;
-        int nb = std::min(NB, p.s - jj);
-        Task t = make_task();
-        t.a = p.off + (int64_t)jj * p.ld + jj;
-        t.lda = p.ld;
-        t.M = nb;
-        t.aux0 = p.col0 + jj;
-        t.flags = arena_flags(p.arena, 0, 0);
-        B.add(t, 1);
-        P.flops += (double)nb * nb * nb / 3.0;
+      {
+        int64_t slot = 0;
+        for (auto& p : probs) {
+          if (jj >= p.s) continue;
+          int nb = std::min(NB, p.s - jj);
+          add_potrf(B, P, p.arena, p.off + (int64_t)jj * p.ld + jj, p.ld, nb, p.col0 + jj, slot++, false);
+        }
       }
       B.end();
       B.begin(LK_TRSM_RLT);
-      for (auto& p : probs) {
-        if (jj >= p.s) continue;
-        int nb = std::min(NB, p.s - jj);
-        int row0 = jj + nb;
-        add_trsm(B, P, p.arena, p.off + (int64_t)jj * p.ld + jj, p.ld, p.arena, p.off + (int64_t)jj * p.ld + row0,
-                 p.ld, p.d - row0, nb);
+      {
+        int64_t slot = 0;
+        for (auto& p : probs) {
+          if (jj >= p.s) continue;
+          int nb = std::min(NB, p.s - jj);
+          int row0 = jj + nb;
+          add_trsm(B, P, slot++, p.arena, p.off + (int64_t)jj * p.ld + row0, p.ld, p.d - row0, nb);
+        }
       }
       B.end();
       B.begin(LK_GEMM_NT);
@@ -150,6 +165,19 @@ static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>
   for (auto& p : probs) max_n = std::max(max_n, p.n);
   if (max_n == 0) return;
   if (nbo <= 0) nbo = pick_nbo(max_n);
+  // invert every <=64x64 diagonal block of every L once (one launch, all blocks in parallel)
+  std::vector<int64_t> slot0(probs.size());
+  {
+    int64_t slot = 0;
+    B.begin(LK_POTRF);
+    for (size_t i = 0; i < probs.size(); i++) {
+      const auto& p = probs[i];
+      slot0[i] = slot;
+      for (int jj = 0; jj < p.n; jj += NB)
+        add_potrf(B, P, p.arenaL, p.loff + (int64_t)jj * p.ldl + jj, p.ldl, std::min(NB, p.n - jj), 0, slot++, true);
+    }
+    B.end();
+  }
   if (trans) {
     // ascending: X_J = (B_J - X_{<J} L[J,<J]') L_JJ^{-T}
     for (int o0 = 0; o0 < max_n; o0 += nbo) {
@@ -174,11 +202,11 @@ static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>
           B.end();
         }
         B.begin(LK_TRSM_RLT);
-        for (auto& p : probs) {
+        for (size_t i = 0; i < probs.size(); i++) {
+          const auto& p = probs[i];
           if (jj >= p.n) continue;
           int nb = std::min(NB, p.n - jj);
-          add_trsm(B, P, p.arenaL, p.loff + (int64_t)jj * p.ldl + jj, p.ldl, p.arenaX,
-                   p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
+          add_trsm(B, P, slot0[i] + jj / NB, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
         }
         B.end();
       }
@@ -214,11 +242,11 @@ static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>
         }
         B.end();
         B.begin(LK_TRSM_RLN);
-        for (auto& p : probs) {
+        for (size_t i = 0; i < probs.size(); i++) {
+          const auto& p = probs[i];
           if (jj >= p.n) continue;
           int nb = std::min(NB, p.n - jj);
-          add_trsm(B, P, p.arenaL, p.loff + (int64_t)jj * p.ldl + jj, p.ldl, p.arenaX,
-                   p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
+          add_trsm(B, P, slot0[i] + jj / NB, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
         }
         B.end();
       }
@@ -246,12 +274,19 @@ struct TrtriProb {
 static void plan_trtri_batch(PlanBuilder& B, Plan& P, const std::vector<TrtriProb>& probs) {
   int max_n = 0;
   for (auto& p : probs) max_n = std::max(max_n, p.n);
-  B.begin(LK_TRSM_RLN);
+  B.begin(LK_POTRF);  // invert-only: W_jj = L_jj^{-1} written straight into W's diagonal blocks
   for (auto& p : probs)
     for (int jj = 0; jj < p.n; jj += NB) {
       int nb = std::min(NB, p.n - jj);
-      add_trsm(B, P, p.arenaL, p.loff + (int64_t)jj * p.ldl + jj, p.ldl, p.arenaW, p.woff + (int64_t)jj * p.ldw + jj,
-               p.ldw, nb, nb);
+      Task t = make_task();
+      t.a = p.loff + (int64_t)jj * p.ldl + jj;
+      t.lda = p.ldl;
+      t.M = nb;
+      t.b = p.woff + (int64_t)jj * p.ldw + jj;
+      t.ldb = p.ldw;
+      t.flags = arena_flags(p.arenaL, p.arenaW, 0) | TF_NOFACTOR;
+      B.add(t, 1);
+      P.flops += (double)nb * nb * nb / 3.0;
     }
   B.end();
   for (int h = NB; h < max_n; h *= 2) {
@@ -309,17 +344,18 @@ void build_factor_plan(const Symbolic& S, Plan& P) {
     // small fronts: one fused shared-memory kernel launch per size class
     std::vector<int32_t> sn;
     {
-      const int classes[3] = {72, 104, SMALL_FRONT_MAX};
-      std::vector<int32_t> cls[3];
+      std::vector<int32_t> cls[SMALL_FRONT_NCLASS];
       for (int32_t s : all) {
         int d = S.front_order(s);
         if (d > SMALL_FRONT_MAX) {
           sn.push_back(s);
           continue;
         }
-        cls[d <= classes[0] ? 0 : d <= classes[1] ? 1 : 2].push_back(s);
+        int c = 0;
+        while (d > SMALL_FRONT_CLASSES[c]) c++;
+        cls[c].push_back(s);
       }
-      for (int c = 0; c < 3; c++) {
+      for (int c = 0; c < SMALL_FRONT_NCLASS; c++) {
         if (cls[c].empty()) continue;
         B.begin(LK_FRONT_FACTOR_SMALL);
         int maxd = 0;
@@ -332,7 +368,7 @@ void build_factor_plan(const Symbolic& S, Plan& P) {
           P.flops += sc * sc * sc / 3.0 + sc * sc * r + sc * r * (r + 1);
           B.add_bytes(8.0 * (d * sc + r * r));
         }
-        B.set_smem(maxd * (maxd | 1) * (int)sizeof(double));
+        B.set_smem(small_front_smem(maxd));
         B.end();
       }
     }
@@ -380,17 +416,18 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
     const auto& all = S.levels[lev].snodes;
     std::vector<int32_t> sn;
     {
-      const int classes[3] = {72, 104, SMALL_FRONT_MAX};
-      std::vector<int32_t> cls[3];
+      std::vector<int32_t> cls[SMALL_FRONT_NCLASS];
       for (int32_t s : all) {
         int d = S.front_order(s);
         if (d > SMALL_FRONT_MAX) {
           sn.push_back(s);
           continue;
         }
-        cls[d <= classes[0] ? 0 : d <= classes[1] ? 1 : 2].push_back(s);
+        int c = 0;
+        while (d > SMALL_FRONT_CLASSES[c]) c++;
+        cls[c].push_back(s);
       }
-      for (int c = 0; c < 3; c++) {
+      for (int c = 0; c < SMALL_FRONT_NCLASS; c++) {
         if (cls[c].empty()) continue;
         B.begin(LK_FRONT_SELINV_SMALL);
         int maxd = 0;
@@ -403,7 +440,7 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
           P.flops += 2.0 * (sc * r * r + sc * sc * r + sc * sc * sc / 3.0);
           B.add_bytes(8.0 * (d * sc + d * d / 2 + r * r));
         }
-        B.set_smem(maxd * (maxd | 1) * (int)sizeof(double));
+        B.set_smem(small_front_smem(maxd));
         B.end();
       }
     }

@@ -11,6 +11,7 @@ struct Plan {
   std::vector<Task> tasks;
   std::vector<Launch> launches;
   int64_t scratch = 0;  // doubles of scratch arena (AR_WORK) the plan needs
+  int64_t dinv = 0;     // doubles of inverse-block scratch (Arenas::dinv) the plan needs
   double flops = 0;  // floating-point operations of the GEMM/SYRK/TRSM/POTRF tasks (useful work, not tile padding)
 };
 

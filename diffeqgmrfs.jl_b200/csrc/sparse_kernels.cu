@@ -110,6 +110,15 @@ __global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ t
   const int r = d - s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* __restrict__ Fj = F + T.a;
+  // this thread's row of the block below the diagonal: all loads are issued first, so that their latency overlaps
+  // the (sequential) solve of the diagonal block
+  const int row = k0 + nb + chunk * FS_ROWS + tid;
+  double f[64];
+  if (row < d) {
+    const double* __restrict__ fr = Fj + row + (int64_t)k0 * ld;
+#pragma unroll
+    for (int c = 0; c < 64; c++) f[c] = (c < nb) ? fr[(int64_t)c * ld] : 0.0;
+  }
   for (int e = tid; e < nb * nb; e += FS_ROWS) {
     int i = e % nb, j = e / nb;
     if (i >= j) Ld[j * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + j) * ld];
@@ -144,27 +153,14 @@ __global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ t
     }
   }
   __syncthreads();
-  const int row = k0 + nb + chunk * FS_ROWS + tid;
   if (row >= d) return;
   double acc[NRC];
 #pragma unroll
   for (int q = 0; q < NRC; q++) acc[q] = 0.0;
-  const double* __restrict__ fr = Fj + row + (int64_t)k0 * ld;
-  int c = 0;
-  for (; c + 8 <= nb; c += 8) {
-    double f[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) f[u] = fr[(int64_t)(c + u) * ld];
+  for (int c = 0; c < 64; c++)
 #pragma unroll
-    for (int u = 0; u < 8; u++)
-#pragma unroll
-      for (int q = 0; q < NRC; q++) acc[q] += f[u] * yk[q][c + u];
-  }
-  for (; c < nb; c++) {
-    const double f = fr[(int64_t)c * ld];
-#pragma unroll
-    for (int q = 0; q < NRC; q++) acc[q] += f * yk[q][c];
-  }
+    for (int q = 0; q < NRC; q++) acc[q] += f[c] * yk[q][c];
   if (row < s) {
 #pragma unroll
     for (int q = 0; q < NRC; q++)
@@ -264,6 +260,15 @@ __global__ void __launch_bounds__(128) k_bwd_step(const Task* __restrict__ tasks
   const int nchunk = T.ldc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* __restrict__ Fj = F + T.a;
+  // update role (j < k): thread = (column cc of block j, row half hf) of L[k-rows, j-cols]; loads issued up front
+  const int cc = tid & 63, hf = tid >> 6;
+  const int r0 = hf * 32;
+  double f[32];
+  if (j != k) {
+    const double* __restrict__ fc = Fj + k0 + (int64_t)(j * 64 + cc) * ld;
+#pragma unroll
+    for (int u = 0; u < 32; u++) f[u] = (r0 + u < nb) ? fc[r0 + u] : 0.0;
+  }
   for (int e = tid; e < nb * nb; e += 128) {
     int i = e % nb, jj = e / nb;
     if (i >= jj) Ld[jj * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + jj) * ld];
@@ -304,18 +309,13 @@ __global__ void __launch_bounds__(128) k_bwd_step(const Task* __restrict__ tasks
   }
   __syncthreads();
   if (j == k) return;
-  // update block j (64 columns): thread = (column cc, row half)
-  const int cc = tid & 63, hf = tid >> 6;
-  const double* __restrict__ fc = Fj + k0 + (int64_t)(j * 64 + cc) * ld;
   double acc[NRC];
 #pragma unroll
   for (int q = 0; q < NRC; q++) acc[q] = 0.0;
-  const int r0 = hf * 32, r1 = min(nb, r0 + 32);
-  for (int rr = r0; rr < r1; rr++) {
-    const double f = fc[rr];
 #pragma unroll
-    for (int q = 0; q < NRC; q++) acc[q] += f * xk[q][rr];
-  }
+  for (int u = 0; u < 32; u++)
+#pragma unroll
+    for (int q = 0; q < NRC; q++) acc[q] += f[u] * xk[q][r0 + u];
   if (hf == 1) {
 #pragma unroll
     for (int q = 0; q < NRC; q++) half[cc][q] = acc[q];

@@ -18,6 +18,8 @@ enum : int32_t {
   TF_TRI = 1 << 8,  // C is lower-trapezoidal: tiles strictly above the diagonal are skipped, diagonal tiles masked
   TF_NEG = 1 << 9,  // kind-specific: negate result
   TF_KLOW = 1 << 10,  // GEMM with transposed A (K x M) that is lower triangular (zero for k < m): skip k < m0
+  TF_B_DINV = 1 << 11,    // operand b lives in the inverse-block scratch (Arenas::dinv), 64x64 slots with ld 64
+  TF_NOFACTOR = 1 << 12,  // POTRF task: the block already holds L, only its inverse is produced
 };
 
 struct alignas(16) Task {
@@ -34,9 +36,9 @@ enum LaunchKind : int32_t {
   LK_GEMM_NT = 0,     // C = beta C + alpha A B'        A: MxK, B: NxK
   LK_GEMM_NN = 1,     // C = beta C + alpha A B         A: MxK, B: KxN
   LK_GEMM_TN = 2,     // C = beta C + alpha A' B        A: KxM, B: KxN
-  LK_POTRF = 3,       // in-place Cholesky of an n<=64 diagonal block (a, lda, M=n); aux0 = global column
-  LK_TRSM_RLT = 4,    // X <- X L^{-T}   L: b (NxN, ldb), X: c (MxN, ldc), N<=64
-  LK_TRSM_RLN = 5,    // X <- X L^{-1}
+  LK_POTRF = 3,       // in-place Cholesky of an n<=64 diagonal block (a, lda, M=n) + its inverse W (b, ldb); aux0 = global column
+  LK_TRSM_RLT = 4,    // X <- X W' = X L^{-T}   W = L^{-1}: b (NxN, ldb), X: c (MxN, ldc), N<=64
+  LK_TRSM_RLN = 5,    // X <- X W  = X L^{-1}
   LK_EXTEND_ADD = 6,  // P[rel[i], rel[j]] += U[i,j] (i>=j): U: a (MxM, lda), P: c (ldc), rel at aux0
   LK_GATHER_SYM = 7,  // Zc[i,j] = Zp[rel[i], rel[j]] symmetric read: Zp: a (lda), Zc: c (MxM, ldc), rel at aux0
   LK_SET_IDENTITY = 8,  // c (MxM, ldc) <- I
@@ -76,11 +78,21 @@ enum : int32_t {
 #endif
 constexpr int GEMM_BM = 128, GEMM_BN = 64, GEMM_BK = GMRFB_GEMM_BK;
 constexpr int NB = 64;           // panel width of the blocked POTRF/TRSM
-constexpr int TRSM_ROWS = 128;   // rows per CTA in the TRSM kernels
+constexpr int TRSM_ROWS = 128;   // rows per CTA in the apply-inverse (TRSM) kernels
+constexpr int DINV_SLOT = 64 * 64;  // doubles per inverse-block scratch slot
 constexpr int EA_TILE = 64;      // extend-add / gather tile edge
-constexpr int SMALL_FRONT_MAX = 160;  // fronts up to this order are processed by one CTA in shared memory
+constexpr int SMALL_FRONT_MAX = 152;  // fronts up to this order are processed by one CTA in shared memory
+// size classes of the fused small-front launches (one launch per class and level; smaller classes => more CTAs/SM)
+constexpr int SMALL_FRONT_NCLASS = 5;
+constexpr int SMALL_FRONT_CLASSES[SMALL_FRONT_NCLASS] = {48, 72, 104, 128, SMALL_FRONT_MAX};
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// dynamic shared memory of the fused small-front kernels for a front of order d: the front (roundup(d,8) columns,
+// leading dimension roundup(d,8)+4) plus two 8-column panel buffers
+inline int small_front_smem(int d) {
+  const int dp = (d + 7) & ~7, ld = dp + 4;
+  return (dp + 16) * ld * (int)sizeof(double);
+}
 // number of 128x64 tiles of an M x N result; lower-trapezoidal results skip tiles entirely above the diagonal
 // (tile (tm, tn) is needed iff its first column tn*64 <= last row tm*128+127, i.e. tn <= 2*tm + 1)
 inline int gemm_tiles(int M, int N, bool tri) {
