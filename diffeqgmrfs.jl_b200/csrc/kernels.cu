@@ -59,6 +59,32 @@ __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
   tj = t - r * (r + 1) / 2;
 }
 
+// right-looking Cholesky of the 8x8 block in registers (lower part); invd[c] = 1 / L_cc.  Returns the first failing
+// column or 8.
+__device__ __forceinline__ int chol8(double (&D)[8][8], double (&invd)[8]) {
+  int bad = 8;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const double d = D[c][c];
+    double r;
+    if (d > 0.0) {
+      r = rsqrt(d);
+    } else {
+      r = nan("");
+      if (bad == 8) bad = c;
+    }
+    invd[c] = r;
+    D[c][c] = d * r;
+#pragma unroll
+    for (int i = c + 1; i < 8; i++) D[i][c] *= r;
+#pragma unroll
+    for (int j = c + 1; j < 8; j++)
+#pragma unroll
+      for (int i = j; i < 8; i++) D[i][j] -= D[i][c] * D[j][c];
+  }
+  return bad;
+}
+
 // --------------------------------------------------------------------------------------------- GEMM ----
 // C = beta*C + alpha*op(A)*op(B);  all column-major.
 //   TA=false: A is M x K (m contiguous)     TA=true: A is K x M (k contiguous), used as A'
@@ -275,12 +301,20 @@ __global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks,
   double* __restrict__ A = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  for (int e = tid; e < 64 * 64; e += 256) {
-    const int i = e & 63, k = e >> 6;
-    double v = (i == k) ? 1.0 : 0.0;
-    if (i < n && k <= i) v = A[i + (int64_t)k * lda];
-    S[k * PLD + i] = v;
-    W[k * PLD + i] = 0.0;
+  {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int e = tid + u * 256, i = e & 63, k = e >> 6;
+      v[u] = (i == k) ? 1.0 : 0.0;
+      if (i < n && k <= i) v[u] = A[i + (int64_t)k * lda];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int e = tid + u * 256, i = e & 63, k = e >> 6;
+      S[k * PLD + i] = v[u];
+      W[k * PLD + i] = 0.0;
+    }
   }
   __syncthreads();
   const int nb8 = (n + 7) >> 3;
@@ -298,38 +332,19 @@ __global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks,
 #pragma unroll
           for (int k = 0; k <= c; k++) D[c][k] = S[(j0 + k) * PLD + j0 + c];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          double d = D[c][c];
-#pragma unroll
-          for (int k = 0; k < c; k++) d -= D[c][k] * D[c][k];
-          double r;
-          if (d > 0.0) {
-            r = rsqrt(d);
-          } else {
-            r = nan("");
-            if (i == j0 + c && i < n) bad = true;
-          }
-          invd[c] = r;
-          D[c][c] = d * r;
-#pragma unroll
-          for (int i2 = c + 1; i2 < 8; i2++) {
-            double v = D[i2][c];
-#pragma unroll
-            for (int k = 0; k < c; k++) v -= D[i2][k] * D[c][k];
-            D[i2][c] = v * r;
-          }
-        }
-#pragma unroll
         for (int c = 0; c < 8; c++) x[c] = S[(j0 + c) * PLD + i];
+        const int badc = chol8(D, invd);
+        if (badc < 8 && i == j0 + badc && i < n) bad = true;
         const int ii = i - j0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          double v = x[c];
+          x[c] *= invd[c];
 #pragma unroll
-          for (int k = 0; k < c; k++) v -= x[k] * D[c][k];
-          // rows inside the diagonal block reproduce L's row for c <= ii (diagonal: d * rsqrt(d)); zero above it
-          x[c] = (c > ii) ? 0.0 : v * invd[c];
+          for (int j = c + 1; j < 8; j++) x[j] -= x[c] * D[j][c];
         }
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          if (c > ii) x[c] = 0.0;  // rows of the diagonal block: L's row up to the diagonal, zero above
       }
       __syncthreads();  // every row thread has read the 8x8 diagonal block before its rows are overwritten
       if (rowt) {
@@ -451,9 +466,19 @@ __global__ void __launch_bounds__(256) k_apply_inv(const Task* __restrict__ task
       a[mt][kk] = (r < M && c < N) ? X[r + (int64_t)c * ldx] : 0.0;
     }
   const int nw = (T.flags & TF_B_DINV) ? 64 : N;
-  for (int e = tid; e < 64 * 64; e += 256) {
-    const int i = e & 63, k = e >> 6;
-    Ws[k * PLD + i] = (i < nw && k < nw) ? Wg[i + (int64_t)k * ldw] : ((i == k) ? 1.0 : 0.0);
+  {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int e = tid + u * 256, i = e & 63, k = e >> 6;
+      // W is lower triangular: the strict upper part is never fetched
+      v[u] = (i < nw && k < nw && i >= k) ? Wg[i + (int64_t)k * ldw] : ((i == k) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int e = tid + u * 256, i = e & 63, k = e >> 6;
+      Ws[k * PLD + i] = v[u];
+    }
   }
   __syncthreads();
   if (row0 >= M) return;
@@ -567,32 +592,6 @@ __global__ void __launch_bounds__(256) k_gather_sym(const Task* __restrict__ tas
 // Task encoding: aux0 = supernode index.
 __host__ __device__ __forceinline__ int sf_ld(int d) { return ((d + 7) & ~7) + 4; }
 
-// right-looking Cholesky of the 8x8 block in registers (lower part); invd[c] = 1 / L_cc.  Returns the first failing
-// column or 8.
-__device__ __forceinline__ int chol8(double (&D)[8][8], double (&invd)[8]) {
-  int bad = 8;
-#pragma unroll
-  for (int c = 0; c < 8; c++) {
-    const double d = D[c][c];
-    double r;
-    if (d > 0.0) {
-      r = rsqrt(d);
-    } else {
-      r = nan("");
-      if (bad == 8) bad = c;
-    }
-    invd[c] = r;
-    D[c][c] = d * r;
-#pragma unroll
-    for (int i = c + 1; i < 8; i++) D[i][c] *= r;
-#pragma unroll
-    for (int j = c + 1; j < 8; j++)
-#pragma unroll
-      for (int i = j; i < 8; i++) D[i][j] -= D[i][c] * D[j][c];
-  }
-  return bad;
-}
-
 template <int NT>
 __global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restrict__ tasks, Arenas ar,
                                                             const SnodeDesc* __restrict__ sd,
@@ -608,29 +607,49 @@ __global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restric
   double* __restrict__ F = ar.p[0] + D.foff;
   const int tid = threadIdx.x, ti_ = tid & 63, tq = tid >> 6, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  // stage: panel columns from the arena, update-matrix part and padding start from zero
-  for (int c = tq; c < dp; c += NT / 64)
-    for (int i = ti_; i < dp; i += 64) S[c * lds + i] = (c < s && i >= c && i < d) ? F[(int64_t)c * ldg + i] : 0.0;
+  // stage: the update-matrix part and the padding start from zero, the panel columns come from the arena.  All
+  // global-memory loops of this kernel keep 8 independent loads per thread in flight (the kernel is latency bound).
+  for (int e = tid; e < dp * lds; e += NT) S[e] = 0.0;
+  __syncthreads();
+  for (int base = tid; base < s * dp; base += 8 * NT) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = base + u * NT, c = e / dp, i = e - c * dp;
+      v[u] = (e < s * dp && i >= c && i < d) ? F[(int64_t)c * ldg + i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = base + u * NT, c = e / dp, i = e - c * dp;
+      if (e < s * dp && i >= c && i < d) S[c * lds + i] = v[u];
+    }
+  }
   __syncthreads();
   for (int ci = 0; ci < D.nchild; ci++) {
     const SnodeDesc C = sd[child_idx[D.child0 + ci]];
     const int rc = C.d - C.s;
     const double* __restrict__ U = ar.p[0] + C.foff + (int64_t)C.s * C.ld + C.s;
     const int32_t* __restrict__ rl = relmap + C.rows_off + C.s;
-    if (rc <= SMALL_FRONT_MAX) {
+    const bool cached = rc <= SMALL_FRONT_MAX;  // else: a child with a long boundary (its rows still map into this front)
+    if (cached) {
       for (int i = tid; i < rc; i += NT) rel[i] = rl[i];
       __syncthreads();
-      for (int j = tq; j < rc; j += NT / 64) {
-        const int pj = rel[j];
-        for (int i = j + ti_ - (j & 63) + ((ti_ < (j & 63)) ? 64 : 0); i < rc; i += 64)
-          S[pj * lds + rel[i]] += U[i + (int64_t)j * C.ld];
+    }
+    const int32_t* __restrict__ rmap = cached ? rel : rl;
+    // lower triangle of the child's update matrix, visited as (row chunk of 64) x column
+    const int nrc64 = (rc + 63) >> 6;
+    const int total = nrc64 * rc;  // items: (j, chunk)
+    for (int base = tq; base < total; base += 8 * (NT / 64)) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int it = base + u * (NT / 64), j = it / nrc64, i = (it - j * nrc64) * 64 + ti_;
+        v[u] = (it < total && i >= j && i < rc) ? U[i + (int64_t)j * C.ld] : 0.0;
       }
-    } else {
-      // a child with a long boundary: its rows still all map inside this (small) front
-      for (int j = tq; j < rc; j += NT / 64) {
-        const int pj = rl[j];
-        for (int i = j + ti_ - (j & 63) + ((ti_ < (j & 63)) ? 64 : 0); i < rc; i += 64)
-          S[pj * lds + rl[i]] += U[i + (int64_t)j * C.ld];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int it = base + u * (NT / 64), j = it / nrc64, i = (it - j * nrc64) * 64 + ti_;
+        if (it < total && i >= j && i < rc) S[rmap[j] * lds + rmap[i]] += v[u];
       }
     }
     __syncthreads();
@@ -694,8 +713,10 @@ __global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restric
     }
     __syncthreads();
   }
-  for (int c = tq; c < d; c += NT / 64)
-    for (int i = c + ti_ - (c & 63) + ((ti_ < (c & 63)) ? 64 : 0); i < d; i += 64) F[(int64_t)c * ldg + i] = S[c * lds + i];
+  for (int e = tid; e < d * dp; e += NT) {
+    const int c = e / dp, i = e - c * dp;
+    if (i >= c && i < d) F[(int64_t)c * ldg + i] = S[c * lds + i];
+  }
 }
 
 template <int NT>
@@ -718,8 +739,7 @@ __global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restric
   double* __restrict__ Zg = ar.p[1] + D.foff;
   const int tid = threadIdx.x, ti_ = tid & 63, tq = tid >> 6, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  for (int c = tq; c < dp; c += NT / 64)
-    for (int i = ti_; i < dp; i += 64) Z[c * lds + i] = 0.0;
+  for (int e = tid; e < dp * lds; e += NT) Z[e] = 0.0;
   __syncthreads();
   if (r > 0) {
     const SnodeDesc P = sd[sparent[sidx]];
@@ -727,24 +747,48 @@ __global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restric
     const int32_t* __restrict__ rl = relmap + D.rows_off + s;
     for (int i = tid; i < r; i += NT) rel[i] = rl[i];
     __syncthreads();
-    for (int j = tq; j < r; j += NT / 64) {
-      const int64_t b = rel[j];
-      for (int i = ti_; i < r; i += 64) {
-        const int64_t a = rel[i];
-        Z[(s + j) * lds + s + i] = (a >= b) ? Zp[a + b * P.ld] : Zp[b + a * P.ld];
+    // Z_RR: lower triangle gathered from the parent's inverse front (8 independent loads in flight), mirrored
+    const int nr64 = (r + 63) >> 6, total = nr64 * r;
+    for (int base = tq; base < total; base += 8 * (NT / 64)) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int it = base + u * (NT / 64), j = it / nr64, i = (it - j * nr64) * 64 + ti_;
+        v[u] = (it < total && i >= j && i < r) ? Zp[(int64_t)rel[i] + (int64_t)rel[j] * P.ld] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int it = base + u * (NT / 64), j = it / nr64, i = (it - j * nr64) * 64 + ti_;
+        if (it < total && i >= j && i < r) {
+          Z[(s + j) * lds + s + i] = v[u];
+          Z[(s + i) * lds + s + j] = v[u];
+        }
       }
     }
   }
   __syncthreads();
+  // panel of L: Lb[c][i] = L[i][j0 + c], i >= j0 + c (8 * dp <= 8 * NT entries); the next panel is prefetched into
+  // registers while the current one is processed
+  double lnext[8];
+  auto load_panel = [&](int jp) {
+    const int pwp = min(8, s - jp);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = tid + u * NT, c = e / dp, i = e - c * dp;
+      lnext[u] = (jp >= 0 && e < 8 * dp && c < pwp && i >= jp + c && i < d) ? L[(int64_t)(jp + c) * ldg + i] : 0.0;
+    }
+  };
+  load_panel(((s - 1) >> 3) << 3);
   for (int j0 = ((s - 1) >> 3) << 3; j0 >= 0; j0 -= 8) {
     const int pw = min(8, s - j0);
     const int m0 = j0 + pw;  // B = [m0, d)
-    // panel of L into shared memory: Lb[c][i] = L[i][j0 + c], i >= j0 + c
-    for (int e = tid; e < 8 * dp; e += NT) {
-      const int c = e / dp, i = e - c * dp;
-      Lb[c * lds + i] = (c < pw && i >= j0 + c && i < d) ? L[(int64_t)(j0 + c) * ldg + i] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = tid + u * NT, c = e / dp, i = e - c * dp;
+      if (e < 8 * dp) Lb[c * lds + i] = lnext[u];
     }
     __syncthreads();
+    load_panel(j0 - 8);
     {
       // every row thread inverts the (identity padded) 8x8 triangle redundantly, then forms its row of Y
       const int i = m0 + tid;
@@ -849,8 +893,10 @@ __global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restric
     }
     __syncthreads();
   }
-  for (int c = tq; c < d; c += NT / 64)
-    for (int i = c + ti_ - (c & 63) + ((ti_ < (c & 63)) ? 64 : 0); i < d; i += 64) Zg[(int64_t)c * ldg + i] = Z[c * lds + i];
+  for (int e = tid; e < d * dp; e += NT) {
+    const int c = e / dp, i = e - c * dp;
+    if (i >= c && i < d) Zg[(int64_t)c * ldg + i] = Z[c * lds + i];
+  }
   for (int c = tid; c < s; c += NT) zdiag[D.col0 + c] = Z[c * lds + c];
 }
 
