@@ -206,7 +206,57 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm ----
+class Lane:
+    """One posterior problem in flight on the GPU: its own context (CUDA stream), factor handle and buffers."""
+
+    def __init__(self, pkg, torch, dev, local, nx, seed, perm=None):
+        self.prob = build_problem(nx, seed)
+        Qp = self.prob["Qpost"]
+        self.n = Qp.shape[0]
+        self.ctx = pkg.Context(local)
+        self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=dev)
+        # the first lane orders the pattern (library nested dissection); the others reuse its permutation, exactly as
+        # the reference passes `perm=p` for every further problem (scripts/darcy/solve_darcy_gmrf-fem.jl:169,174)
+        if perm is None:
+            self.sym = pkg.Symbolic(Qp, coords=self.prob["nodes"], ctx=self.ctx)
+        else:
+            self.sym = pkg.Symbolic(Qp, perm=perm, ctx=self.ctx)
+        self.fac = pkg.CholeskyFactor(self.sym)
+        self.nz_host = torch.from_numpy(np.ascontiguousarray(Qp.data)).pin_memory()
+        self.rhs_host = torch.from_numpy(np.ascontiguousarray(self.prob["rhs"])).pin_memory()
+        self.d_nz = self.nz_host.to(dev)
+        self.d_rhs = self.rhs_host.to(dev)
+        self.d_x = torch.empty_like(self.d_rhs)
+        self.d_var = torch.empty_like(self.d_rhs)
+        self.x_host = np.empty(self.n)
+        self.end = torch.cuda.Event(enable_timing=True)
+        self.torch, self.local = torch, local
+        self.xs = self.v = None
+
+    def steps_device(self, k):
+        """k posterior solves, everything resident in HBM: numeric factor + mean + selected-inversion variances."""
+        torch = self.torch
+        torch.cuda.set_device(self.local)
+        for _ in range(k):
+            with torch.cuda.stream(self.ext):
+                self.d_x.copy_(self.d_rhs, non_blocking=True)
+            self.fac.factorize_dev(self.d_nz.data_ptr())
+            self.fac.solve_dev(self.d_x.data_ptr(), 1)
+            self.fac.var_selinv_dev(self.d_var.data_ptr())
+
+    def steps_e2e(self, k):
+        """The same through the host C-ABI calls: pinned host inputs, host outputs (H2D/D2H inside)."""
+        self.torch.cuda.set_device(self.local)
+        for _ in range(k):
+            self.fac.factorize(self.nz_host.numpy())
+            self.x_host[:] = self.rhs_host.numpy()
+            self.xs = self.fac.solve(self.x_host)
+            self.v = self.fac.var_selinv()
+
+
 def run_gpu_arm(args):
+    import threading
+
     import torch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,53 +272,18 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     pkg = entry.load_pkg()
-    ctx = pkg.Context(local)
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     hbm_peak, fp64_peak, peak_src = load_peaks()
 
-    nx = args.nx
+    nx, B = args.nx, max(1, args.inflight)
     t_setup = time.perf_counter()
-    prob = build_problem(nx, rank)  # rank r solves problem r: independent problems, same pattern
-    Qp = prob["Qpost"]
-    n = Qp.shape[0]
-    sym = pkg.Symbolic(Qp, coords=prob["nodes"], ctx=ctx)
-    info = sym.info
-    fac = pkg.CholeskyFactor(sym)
+    # rank r, lane b solves problem r*B + b: independent posterior problems on one sparsity pattern
+    lanes = [Lane(pkg, torch, dev, local, nx, rank * B)]
+    for b in range(1, B):
+        lanes.append(Lane(pkg, torch, dev, local, nx, rank * B + b, perm=lanes[0].sym.p))
     t_setup = time.perf_counter() - t_setup
-
-    nz_host = torch.from_numpy(np.ascontiguousarray(Qp.data)).pin_memory()
-    rhs_host = torch.from_numpy(np.ascontiguousarray(prob["rhs"])).pin_memory()
-    d_nz = nz_host.to(dev)
-    d_rhs = rhs_host.to(dev)
-    d_x = torch.empty_like(d_rhs)
-    d_var = torch.empty_like(d_rhs)
+    L0 = lanes[0]
+    n, Qp, info = L0.n, L0.prob["Qpost"], L0.sym.info
     torch.cuda.synchronize()
-
-    def step_device():
-        with torch.cuda.stream(ext):
-            d_x.copy_(d_rhs)
-        fac.factorize_dev(d_nz.data_ptr())
-        fac.solve_dev(d_x.data_ptr(), 1)
-        fac.var_selinv_dev(d_var.data_ptr())
-
-    x_host = np.empty(n)
-    var_host = np.empty(n)
-
-    e2e_parts = {"factorize": 0.0, "solve": 0.0, "var": 0.0}
-
-    def step_e2e():
-        t0 = time.perf_counter()
-        fac.factorize(nz_host.numpy())
-        t1 = time.perf_counter()
-        x_host[:] = rhs_host.numpy()
-        xs = fac.solve(x_host)
-        t2 = time.perf_counter()
-        v = fac.var_selinv()
-        t3 = time.perf_counter()
-        e2e_parts["factorize"] += t1 - t0
-        e2e_parts["solve"] += t2 - t1
-        e2e_parts["var"] += t3 - t2
-        return xs, v
 
     def barrier():
         torch.cuda.synchronize()
@@ -276,58 +291,68 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+    def timed(which, k, use):
+        """Run k steps on each lane of `use` concurrently (one host thread per lane); device time from a start event
+        every lane's stream waits on to an end event that waits on every lane's stream."""
+        barrier()
+        cur = torch.cuda.current_stream()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for L in use:
+            L.ext.wait_event(e0)
+        th = [threading.Thread(target=getattr(L, which), args=(k,)) for L in use]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for L in use:
+            L.end.record(L.ext)
+            cur.wait_event(L.end)
+        e1.record(cur)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    timed("steps_device", args.warmup, lanes)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launch_count
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ext):
-        e0.record()
-    for _ in range(args.steps):
-        step_device()
-    with torch.cuda.stream(ext):
-        e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count - l0
+    l0 = sum(L.ctx.launch_count for L in lanes)
+    ms = timed("steps_device", args.steps, lanes)
+    launches = sum(L.ctx.launch_count for L in lanes) - l0
     clocks = sampler.stop() if rank == 0 else None
+    # latency of a single posterior solve with nothing else in flight
+    ms_single = timed("steps_device", args.steps, lanes[:1]) / args.steps
 
     # end-to-end through the host C-ABI calls (pinned host inputs, host outputs)
     ke = max(1, min(args.steps, 3))
-    step_e2e()
-    barrier()
-    with torch.cuda.stream(ext):
-        e0.record()
-    for _ in range(ke):
-        xs, v = step_e2e()
-    with torch.cuda.stream(ext):
-        e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1) / ke
-    print("e2e host-side split (s, incl. the untimed first call):", {k: round(v, 4) for k, v in e2e_parts.items()},
-          file=sys.stderr)
+    timed("steps_e2e", 1, lanes)
+    ms_e2e = timed("steps_e2e", ke, lanes) / ke
 
     if dist is not None:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_single], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_single = float(t[0]), float(t[1]), float(t[2])
 
-    # parity spot check of what was timed (size-independent property: residual of the mean, and var > 0)
-    mean = d_x.cpu().numpy()
-    resid = float(np.linalg.norm(Qp @ mean - prob["rhs"]) / np.linalg.norm(prob["rhs"]))
-    var = d_var.cpu().numpy()
-    ok = resid < 1e-9 and bool(np.all(var > 0)) and float(np.max(np.abs(xs - mean))) <= 1e-12 * float(np.max(np.abs(mean))) + 1e-300
+    # parity spot check of what was timed (size-independent property: residual of the mean, and var > 0), every lane
+    ok, resid, varpos = True, 0.0, True
+    for L in lanes:
+        mean = L.d_x.cpu().numpy()
+        r = float(np.linalg.norm(L.prob["Qpost"] @ mean - L.prob["rhs"]) / np.linalg.norm(L.prob["rhs"]))
+        var = L.d_var.cpu().numpy()
+        resid = max(resid, r)
+        varpos = varpos and bool(np.all(var > 0))
+        same = float(np.max(np.abs(L.xs - mean))) <= 1e-12 * float(np.max(np.abs(mean))) + 1e-300
+        same = same and float(np.max(np.abs(L.v - var))) <= 1e-12 * float(np.max(np.abs(var)))
+        ok = ok and r < 1e-9 and varpos and same
 
     # per-kernel profile of one more step (CUDA events around every launch on the library's stream)
     roofline = None
     prof_rows = []
     if rank == 0:
+        ctx = L0.ctx
         ctx.profile_begin()
-        step_device()
+        L0.steps_device(1)
         prof = ctx.profile_end()
         tot = sum(p["ms"] for p in prof)
         for p in sorted(prof, key=lambda q: -q["ms"]):
@@ -338,18 +363,21 @@ def run_gpu_arm(args):
                 row["gbs"] = round(p["bytes"] / p["ms"] * 1e-6, 1)
             prof_rows.append(row)
         top = max(prof, key=lambda q: q["ms"])
+        traffic = ncu_traffic(top["name"])
         if top["flops"] > 0 and "gemm" in top["name"]:
             ach = top["flops"] / top["ms"] * 1e-9
             roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": fp64_peak,
-                        "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                        "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_probe.json); "
-                                       "FP64 tensor (DMMA) issue peak 37.1 TFLOP/s",
+                                       "FP64 tensor (DMMA) issue peak 37.1 TFLOP/s; no f64 kind exists for tcgen05",
                         "launches_per_step": top["launches"], "ms_per_step": top["ms"],
-                        "flops_per_step": top["flops"]}
+                        "flops_per_step": top["flops"],
+                        "note": "achieved = algorithmic flops of all launches of this kernel in one posterior solve / "
+                                "their summed CUDA-event durations (profiled replay of the same step, one problem in flight)"}
         else:
             ach = top["bytes"] / top["ms"] * 1e-6 if top["ms"] > 0 else 0.0
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                        "frac": ach / hbm_peak, "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                         "launches_per_step": top["launches"], "ms_per_step": top["ms"]}
 
     if rank != 0:
@@ -362,23 +390,27 @@ def run_gpu_arm(args):
         cpu = cpu_baseline(nx)
     per_step = ms / args.steps
     line = {
-        "metric": METRIC, "value": world * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": world * B * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"config 4: 2-D Matern SPDE GMRF posterior, {nx}x{nx} P1 mesh (n={n}), numeric "
-                               "supernodal Cholesky + mean + selected-inversion variances per step",
+                               "supernodal Cholesky + mean + selected-inversion variances per posterior solve; "
+                               f"one step = one batch of {B} independent posterior problems per GPU (same pattern, "
+                               "different values; the reference's dataset loop), each on its own CUDA stream",
                    "n": n, "nnz_Q": int(Qp.nnz), "nnz_L": int(info.nnz_L), "factor_flops": info.flops,
                    "nsuper": int(info.nsuper), "levels": int(info.nlevels), "max_front": int(info.max_front),
                    "front_arena_gb": info.front_bytes / 1e9, "ordering": "library nested dissection (geometric)",
-                   "problems_per_gpu": 1, "l2_policy": "working set (front arena) >> 126 MB L2; no flush needed",
+                   "problems_per_gpu_in_flight": B, "solves_per_step": B,
+                   "single_solve_latency_ms": ms_single,
+                   "l2_policy": "working set (front arenas, 20 GB per problem) >> 126 MB L2; no flush needed",
                    "setup_s_outside_timing": round(t_setup, 2)},
-        "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(nz_host.numel() * 8 + n * 8), "d2h_bytes_per_step": int(2 * n * 8)},
+        "e2e": {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(B * (L0.nz_host.numel() * 8 + n * 8)), "d2h_bytes_per_step": int(B * 2 * n * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "kernel_profile": prof_rows,
-        "parity_check": {"mean_residual": resid, "var_positive": bool(np.all(var > 0)), "ok": bool(ok)},
+        "parity_check": {"mean_residual": resid, "var_positive": varpos, "ok": bool(ok)},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -386,6 +418,19 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
     if not ok:
         sys.exit("bench: parity spot check failed")
+
+
+def ncu_traffic(kernel_name):
+    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/r01_ncu_top_kernel.json), or None when no capture of that kernel is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_top_kernel.json")) as f:
+            d = json.load(f)
+        if d.get("kernel") and d["kernel"].split("<")[0] in kernel_name:
+            return d.get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    return None
 
 
 def main():
@@ -397,6 +442,8 @@ def main():
     ap.add_argument("--nx", type=int, default=1001, help="mesh nodes per side (1001 -> 1,002,001 nodes)")
     ap.add_argument("--nx-sample", dest="nx_sample", type=int, default=0, help="(unused; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3,
+                    help="independent posterior problems in flight per GPU (one CUDA stream each)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -10,10 +10,6 @@ namespace gmrfb {
 
 namespace {
 
-// outer panel width of the two-level blocked POTRF/TRSM: wide enough that the left-looking GEMMs of a large
-// problem span a full wave of CTAs, narrow enough that small problems still advance in few launches
-inline int pick_nbo(int max_n) { return max_n <= 512 ? 128 : max_n <= 1536 ? 256 : 512; }
-
 inline int32_t arena_flags(int a, int b, int c) { return (a << TF_A_SHIFT) | (b << TF_B_SHIFT) | (c << TF_C_SHIFT); }
 
 double gemm_flops(int M, int N, int K, bool tri) {
@@ -78,64 +74,63 @@ void add_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int ld, int nb, 
 // ------------------------------------------------------------------------ partial factorisation batch ----
 // Each problem is a d x d front (column-major, ld) whose first s columns are eliminated:
 //   [F11 .; F21 F22] -> L11 = chol(F11), L21 = F21 L11^{-T}, F22 <- F22 - L21 L21'.
-// Two-level blocking: outer panels of `nbo` columns (trailing updates with K = nbo), inner blocks of NB = 64
-// (POTRF in shared memory, TRSM by register substitution).  The F22 update is a single SYRK with K = s.
+// Recursive blocking down to NB = 64 wide blocks (POTRF + inverse in shared memory, TRSM as a DMMA product with the
+// inverse).  The F22 update is a single SYRK with K = s.
 struct FactorProb {
   int arena;
   int64_t off;
   int ld, d, s, col0;
 };
 
-static void plan_partial_factor_batch(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int nbo) {
-  int max_s = 0;
-  for (auto& p : probs) max_s = std::max(max_s, p.s);
-  if (nbo <= 0) nbo = pick_nbo(max_s);
-  for (int j0 = 0; j0 < max_s; j0 += nbo) {
-    for (int jj = j0; jj < std::min(j0 + nbo, max_s); jj += NB) {
-      B.begin(LK_POTRF);
-      {
-        int64_t slot = 0;
-        for (auto& p : probs) {
-          if (jj >= p.s) continue;
-          int nb = std::min(NB, p.s - jj);
-          add_potrf(B, P, p.arena, p.off + (int64_t)jj * p.ld + jj, p.ld, nb, p.col0 + jj, slot++, false);
-        }
-      }
-      B.end();
-      B.begin(LK_TRSM_RLT);
-      {
-        int64_t slot = 0;
-        for (auto& p : probs) {
-          if (jj >= p.s) continue;
-          int nb = std::min(NB, p.s - jj);
-          int row0 = jj + nb;
-          add_trsm(B, P, slot++, p.arena, p.off + (int64_t)jj * p.ld + row0, p.ld, p.d - row0, nb);
-        }
-      }
-      B.end();
-      B.begin(LK_GEMM_NT);
+// Recursive blocking: columns [j0, j1) of every front (all earlier updates applied) are factorised as
+//   factor [j0, jm);  trailing update of [jm, j1) with K = jm - j0;  factor [jm, j1)
+// with jm a multiple of NB near the middle, down to single NB-wide blocks (POTRF + apply-inverse).  Most of the
+// panel-update flops therefore run in GEMMs with K = width/2, width/4, ... instead of K = NB.
+static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int j0, int j1) {
+  if (j1 - j0 <= NB) {
+    B.begin(LK_POTRF);
+    {
+      int64_t slot = 0;
       for (auto& p : probs) {
-        if (jj >= p.s) continue;
-        int nb = std::min(NB, p.s - jj);
-        int c0 = jj + nb, c1 = std::min(j0 + nbo, p.s);
-        if (c1 <= c0) continue;
-        int64_t a = p.off + (int64_t)jj * p.ld + c0;
-        add_gemm(B, P, p.arena, a, p.ld, p.arena, a, p.ld, p.arena, p.off + (int64_t)c0 * p.ld + c0, p.ld,
-                 p.d - c0, c1 - c0, nb, true, -1.0, 1.0);
+        if (j0 >= p.s) continue;
+        int nb = std::min(NB, p.s - j0);
+        add_potrf(B, P, p.arena, p.off + (int64_t)j0 * p.ld + j0, p.ld, nb, p.col0 + j0, slot++, false);
       }
-      B.end();
-    }
-    B.begin(LK_GEMM_NT);
-    for (auto& p : probs) {
-      if (j0 >= p.s) continue;
-      int pe = std::min(j0 + nbo, p.s);
-      if (p.s <= pe) continue;
-      int64_t a = p.off + (int64_t)j0 * p.ld + pe;
-      add_gemm(B, P, p.arena, a, p.ld, p.arena, a, p.ld, p.arena, p.off + (int64_t)pe * p.ld + pe, p.ld, p.d - pe,
-               p.s - pe, pe - j0, true, -1.0, 1.0);
     }
     B.end();
+    B.begin(LK_TRSM_RLT);
+    {
+      int64_t slot = 0;
+      for (auto& p : probs) {
+        if (j0 >= p.s) continue;
+        int nb = std::min(NB, p.s - j0);
+        int row0 = j0 + nb;
+        add_trsm(B, P, slot++, p.arena, p.off + (int64_t)j0 * p.ld + row0, p.ld, p.d - row0, nb);
+      }
+    }
+    B.end();
+    return;
   }
+  const int nblk = (j1 - j0 + NB - 1) / NB;
+  const int jm = j0 + (nblk / 2) * NB;
+  plan_factor_cols(B, P, probs, j0, jm);
+  B.begin(LK_GEMM_NT);
+  for (auto& p : probs) {
+    if (jm >= p.s) continue;
+    int c1 = std::min(j1, p.s);
+    int64_t a = p.off + (int64_t)j0 * p.ld + jm;
+    add_gemm(B, P, p.arena, a, p.ld, p.arena, a, p.ld, p.arena, p.off + (int64_t)jm * p.ld + jm, p.ld, p.d - jm,
+             c1 - jm, jm - j0, true, -1.0, 1.0);
+  }
+  B.end();
+  plan_factor_cols(B, P, probs, jm, j1);
+}
+
+static void plan_partial_factor_batch(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int nbo) {
+  (void)nbo;
+  int max_s = 0;
+  for (auto& p : probs) max_s = std::max(max_s, p.s);
+  if (max_s > 0) plan_factor_cols(B, P, probs, 0, ((max_s + NB - 1) / NB) * NB);
   B.begin(LK_GEMM_NT);
   for (auto& p : probs) {
     int r = p.d - p.s;
@@ -160,11 +155,55 @@ struct TrsmProb {
   int M, n;
 };
 
+// Recursive over column ranges [j0, j1) (multiples of NB from 0, the same for every problem):
+//   trans : solve [j0, jm);  X[:, jm:j1] -= X[:, j0:jm] L[jm:j1, j0:jm]';  solve [jm, j1)
+//   !trans: solve [jm, j1);  X[:, j0:jm] -= X[:, jm:j1] L[jm:j1, j0:jm];   solve [j0, jm)
+// so the updates are GEMMs with K = width/2, width/4, ...; the leaves multiply by the inverted diagonal blocks.
+static void plan_trsm_cols(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>& probs,
+                           const std::vector<int64_t>& slot0, bool trans, int j0, int j1) {
+  if (j1 - j0 <= NB) {
+    B.begin(trans ? LK_TRSM_RLT : LK_TRSM_RLN);
+    for (size_t i = 0; i < probs.size(); i++) {
+      const auto& p = probs[i];
+      if (j0 >= p.n) continue;
+      int nb = std::min(NB, p.n - j0);
+      add_trsm(B, P, slot0[i] + j0 / NB, p.arenaX, p.xoff + (int64_t)j0 * p.ldx, p.ldx, p.M, nb);
+    }
+    B.end();
+    return;
+  }
+  const int nblk = (j1 - j0 + NB - 1) / NB;
+  const int jm = j0 + (nblk / 2) * NB;
+  if (trans) {
+    plan_trsm_cols(B, P, probs, slot0, trans, j0, jm);
+    B.begin(LK_GEMM_NT);
+    for (auto& p : probs) {
+      if (jm >= p.n) continue;
+      int c1 = std::min(j1, p.n);
+      add_gemm(B, P, p.arenaX, p.xoff + (int64_t)j0 * p.ldx, p.ldx, p.arenaL, p.loff + (int64_t)j0 * p.ldl + jm, p.ldl,
+               p.arenaX, p.xoff + (int64_t)jm * p.ldx, p.ldx, p.M, c1 - jm, jm - j0, false, -1.0, 1.0);
+    }
+    B.end();
+    plan_trsm_cols(B, P, probs, slot0, trans, jm, j1);
+  } else {
+    plan_trsm_cols(B, P, probs, slot0, trans, jm, j1);
+    B.begin(LK_GEMM_NN);
+    for (auto& p : probs) {
+      if (jm >= p.n) continue;
+      int c1 = std::min(j1, p.n);
+      add_gemm(B, P, p.arenaX, p.xoff + (int64_t)jm * p.ldx, p.ldx, p.arenaL, p.loff + (int64_t)j0 * p.ldl + jm, p.ldl,
+               p.arenaX, p.xoff + (int64_t)j0 * p.ldx, p.ldx, p.M, jm - j0, c1 - jm, false, -1.0, 1.0);
+    }
+    B.end();
+    plan_trsm_cols(B, P, probs, slot0, trans, j0, jm);
+  }
+}
+
 static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>& probs, bool trans, int nbo) {
+  (void)nbo;
   int max_n = 0;
   for (auto& p : probs) max_n = std::max(max_n, p.n);
   if (max_n == 0) return;
-  if (nbo <= 0) nbo = pick_nbo(max_n);
   // invert every <=64x64 diagonal block of every L once (one launch, all blocks in parallel)
   std::vector<int64_t> slot0(probs.size());
   {
@@ -178,83 +217,8 @@ static void plan_trsm_batch(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>
     }
     B.end();
   }
-  if (trans) {
-    // ascending: X_J = (B_J - X_{<J} L[J,<J]') L_JJ^{-T}
-    for (int o0 = 0; o0 < max_n; o0 += nbo) {
-      B.begin(LK_GEMM_NT);
-      for (auto& p : probs) {
-        if (o0 >= p.n || o0 == 0) continue;
-        int o1 = std::min(o0 + nbo, p.n);
-        add_gemm(B, P, p.arenaX, p.xoff, p.ldx, p.arenaL, p.loff + o0, p.ldl, p.arenaX,
-                 p.xoff + (int64_t)o0 * p.ldx, p.ldx, p.M, o1 - o0, o0, false, -1.0, 1.0);
-      }
-      B.end();
-      for (int jj = o0; jj < std::min(o0 + nbo, max_n); jj += NB) {
-        if (jj > o0) {
-          B.begin(LK_GEMM_NT);
-          for (auto& p : probs) {
-            if (jj >= p.n) continue;
-            int nb = std::min(NB, p.n - jj);
-            add_gemm(B, P, p.arenaX, p.xoff + (int64_t)o0 * p.ldx, p.ldx, p.arenaL,
-                     p.loff + (int64_t)o0 * p.ldl + jj, p.ldl, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M,
-                     nb, jj - o0, false, -1.0, 1.0);
-          }
-          B.end();
-        }
-        B.begin(LK_TRSM_RLT);
-        for (size_t i = 0; i < probs.size(); i++) {
-          const auto& p = probs[i];
-          if (jj >= p.n) continue;
-          int nb = std::min(NB, p.n - jj);
-          add_trsm(B, P, slot0[i] + jj / NB, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
-        }
-        B.end();
-      }
-    }
-  } else {
-    // descending: X_J = (B_J - X_{>J} L[>J,J]) L_JJ^{-1}.  Blocks are aligned to multiples of NB/nbo from 0 so
-    // that every problem sees the same block boundaries regardless of its n.
-    int nouter = cdiv(max_n, nbo);
-    for (int ob = nouter - 1; ob >= 0; ob--) {
-      int o0 = ob * nbo;
-      B.begin(LK_GEMM_NN);
-      for (auto& p : probs) {
-        if (o0 >= p.n) continue;
-        int o1 = std::min(o0 + nbo, p.n);
-        if (o1 >= p.n) continue;  // nothing to the right
-        add_gemm(B, P, p.arenaX, p.xoff + (int64_t)o1 * p.ldx, p.ldx, p.arenaL, p.loff + (int64_t)o0 * p.ldl + o1,
-                 p.ldl, p.arenaX, p.xoff + (int64_t)o0 * p.ldx, p.ldx, p.M, o1 - o0, p.n - o1, false, -1.0, 1.0);
-      }
-      B.end();
-      int ninner = nbo / NB;
-      for (int ib = ninner - 1; ib >= 0; ib--) {
-        int jj = o0 + ib * NB;
-        if (jj >= max_n) continue;
-        // update block jj with the already solved inner blocks to its right inside this outer block
-        B.begin(LK_GEMM_NN);
-        for (auto& p : probs) {
-          if (jj >= p.n) continue;
-          int nb = std::min(NB, p.n - jj);
-          int r0 = jj + nb, r1 = std::min(o0 + nbo, p.n);
-          if (r1 <= r0) continue;
-          add_gemm(B, P, p.arenaX, p.xoff + (int64_t)r0 * p.ldx, p.ldx, p.arenaL, p.loff + (int64_t)jj * p.ldl + r0,
-                   p.ldl, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb, r1 - r0, false, -1.0, 1.0);
-        }
-        B.end();
-        B.begin(LK_TRSM_RLN);
-        for (size_t i = 0; i < probs.size(); i++) {
-          const auto& p = probs[i];
-          if (jj >= p.n) continue;
-          int nb = std::min(NB, p.n - jj);
-          add_trsm(B, P, slot0[i] + jj / NB, p.arenaX, p.xoff + (int64_t)jj * p.ldx, p.ldx, p.M, nb);
-        }
-        B.end();
-      }
-    }
-  }
+  plan_trsm_cols(B, P, probs, slot0, trans, 0, ((max_n + NB - 1) / NB) * NB);
 }
-
-
 
 // ---------------------------------------------------------------------- triangular inverse batch ----
 // W = L^{-1} (n x n lower) by recursive doubling: invert the 64x64 diagonal blocks, then merge neighbouring
