@@ -128,7 +128,7 @@ gmrfb_status btd_alloc(gmrfb_ctx* ctx, int64_t b, int64_t N, std::unique_ptr<gmr
       t.alpha = -1.0;
       t.beta = 1.0;
       t.flags = TF_TRI;
-      B.add(t, gemm_tiles((int)b, (int)b, true));
+      B.add(t, gemm_tiles((int)b, (int)b, true, GCFG_BIG));
       P.flops += (double)b * b * (b + 1);
     }
     B.end();
@@ -334,7 +334,7 @@ static gmrfb_status btd_build_solve_plans(gmrfb_btd* f, int nrhs, int ldr) {
     t.alpha = -1.0;
     t.beta = 1.0;
     t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (1 << TF_C_SHIFT);
-    B.add(t, gemm_tiles(nrhs, b, false));
+    B.add(t, gemm_tiles(nrhs, b, false, GCFG_BIG));
     B.end();
     plan_trsm_rlt(B, P, 0, 0, f->ld, 1, 0, nrhs, b, ldr);
   }
@@ -359,7 +359,7 @@ static gmrfb_status btd_build_solve_plans(gmrfb_btd* f, int nrhs, int ldr) {
     t.alpha = -1.0;
     t.beta = 1.0;
     t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (1 << TF_C_SHIFT);
-    B.add(t, gemm_tiles(nrhs, b, false));
+    B.add(t, gemm_tiles(nrhs, b, false, GCFG_BIG));
     B.end();
     plan_trsm_rln(B, P, 0, 0, f->ld, 1, 0, nrhs, b, ldr, false);
   }
@@ -494,7 +494,7 @@ extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
       t.alpha = -1.0;
       t.beta = 0.0;
       t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (2 << TF_C_SHIFT);
-      B.add(t, gemm_tiles(b, b, false));
+      B.add(t, gemm_tiles(b, b, false, GCFG_BIG));
       B.end();
       ident(B);
       // H = I - C_{i+1}' T
@@ -510,7 +510,7 @@ extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
       u.alpha = -1.0;
       u.beta = 1.0;
       u.flags = (0 << TF_A_SHIFT) | (2 << TF_B_SHIFT) | (3 << TF_C_SHIFT);
-      B.add(u, gemm_tiles(b, b, false));
+      B.add(u, gemm_tiles(b, b, false, GCFG_BIG));
       B.end();
       tail(P, B);
     }
@@ -612,7 +612,8 @@ gmrfb_status gemm_once(gmrfb_ctx* ctx, int kind, const double* A, int lda, const
   L.kind = kind;
   L.task0 = 0;
   L.ntasks = 1;
-  L.grid = gemm_tiles(M, N, tri);
+  L.cfg = choose_gemm_cfg(gemm_tiles(M, N, tri, GCFG_BIG), 1);
+  L.grid = gemm_tiles(M, N, tri, L.cfg);
   Arenas ar{{const_cast<double*>(A), const_cast<double*>(B), C, nullptr}};
   LaunchAux aux;
   GMRFB_CU(ctx, run_launch(L, dt.p, ar, aux, ctx->stream));

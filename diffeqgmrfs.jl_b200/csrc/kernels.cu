@@ -1,7 +1,7 @@
 // Dense tile engine for sm_100a: grouped (batched, variable-size) FP64 kernels driven by Task lists.
 //
-//  k_gemm<TA,TB>   128x128x16 tiles, 3-stage cp.async pipeline, FP64 tensor cores (DMMA m8n8k4 via
-//                  mma.sync.aligned.m8n8k4.f64 — tcgen05 has no f64 kind; measured 37.1 TFLOP/s peak on B200,
+//  k_gemm2<TA,TB,CFG>  (gemm_engine.cuh) 128x64x16 / 64x64x16 tiles, cp.async pipeline, FP64 tensor cores (DMMA m8n8k4
+//                  via mma.sync.aligned.m8n8k4.f64 — tcgen05 has no f64 kind; measured 37.1 TFLOP/s peak on B200,
 //                  profiles/r01_fp64_probe.txt).  Used for every SYRK/GEMM of the multifrontal factorisation,
 //                  selected inversion and the block-tridiagonal factor.
 //  k_potrf64       Cholesky + inverse of one <=64x64 diagonal block per CTA in shared memory (DMMA panel updates).
@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <type_traits>
 
+#include "gemm_engine.cuh"
 #include "kernels.hpp"
 #include "sparse_kernels.hpp"
 #include "tasks.hpp"
@@ -86,189 +87,12 @@ __device__ __forceinline__ int chol8(double (&D)[8][8], double (&invd)[8]) {
 }
 
 // --------------------------------------------------------------------------------------------- GEMM ----
-// C = beta*C + alpha*op(A)*op(B);  all column-major.
-//   TA=false: A is M x K (m contiguous)     TA=true: A is K x M (k contiguous), used as A'
-//   TB=false: B is N x K (n contiguous), used as B'   TB=true: B is K x N (k contiguous)
-#ifndef GMRFB_GEMM_STAGES
-#define GMRFB_GEMM_STAGES 3
-#endif
-constexpr int G_STAGES = GMRFB_GEMM_STAGES;
-constexpr int G_LDNA = GEMM_BM + 4;  // A tile, [k][m] layout, +4 doubles: conflict-free 64-bit fragment loads
-constexpr int G_LDNB = GEMM_BN + 4;  // B tile, [k][n] layout
-constexpr int G_LDT = GEMM_BK + 4;   // [m][k] / [n][k] layouts
-constexpr int G_A_STAGE_N = GEMM_BK * G_LDNA, G_A_STAGE_T = GEMM_BM * G_LDT;
-constexpr int G_B_STAGE_N = GEMM_BK * G_LDNB, G_B_STAGE_T = GEMM_BN * G_LDT;
-
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(256, 2) k_gemm(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
-  extern __shared__ __align__(16) double smem[];
-  constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-  constexpr int A_STAGE = TA ? G_A_STAGE_T : G_A_STAGE_N;
-  constexpr int B_STAGE = TB ? G_B_STAGE_T : G_B_STAGE_N;
-  double* As = smem;
-  double* Bs = smem + G_STAGES * A_STAGE;
-
-  const int tix = find_task(tasks, ntasks, blockIdx.x);
-  const Task T = tasks[tix];
-  const int local = blockIdx.x - T.tile0;
-  const int M = T.M, N = T.N, K = T.K;
-  const int ntn = (N + BN - 1) / BN;
-  int tm, tn;
-  if (T.flags & TF_TRI) {
-    // row tile tm owns min(2*tm + 2, ntn) column tiles
-    int rem = local;
-    tm = 0;
-    for (;;) {
-      const int w = min(2 * tm + 2, ntn);
-      if (rem < w) break;
-      rem -= w;
-      tm++;
-    }
-    tn = rem;
-  } else {
-    tm = local / ntn;
-    tn = local % ntn;
-  }
-  const int m0 = tm * BM, n0 = tn * BN;
-  const double* __restrict__ A = ar.p[(T.flags >> TF_A_SHIFT) & 3] + T.a;
-  const double* __restrict__ B = ar.p[(T.flags >> TF_B_SHIFT) & 3] + T.b;
-  double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
-  const int lda = T.lda, ldb = T.ldb, ldc = T.ldc;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // Interleaved ownership of the 16 x 8 grid of 8x8 MMA sub-tiles: warp (wm, wn) owns row sub-tiles im*4 + wm and
-  // column sub-tiles in*2 + wn.  Sub-tiles outside the problem (or above the diagonal of a triangular result) are
-  // skipped with warp-uniform predicates, and the interleaving keeps the remaining work balanced across warps, so
-  // partially filled tiles (small fronts in a batched launch) cost only their useful 8x8 blocks of DMMA issue.
-  const int wm = warp & 3, wn = warp >> 2;
-  unsigned active = 0;
-#pragma unroll
-  for (int im = 0; im < 4; im++)
-#pragma unroll
-    for (int in = 0; in < 4; in++) {
-      const int r0 = m0 + (im * 4 + wm) * 8, c0 = n0 + (in * 2 + wn) * 8;
-      bool on = (r0 < M) && (c0 < N);
-      if ((T.flags & TF_TRI) && c0 > r0 + 7) on = false;
-      if (on) active |= 1u << (im * 4 + in);
-    }
-
-  auto load_stage = [&](int stage, int k0) {
-    double* as = As + stage * A_STAGE;
-    double* bs = Bs + stage * B_STAGE;
-#pragma unroll
-    for (int i = 0; i < (BM * BK) / 256; i++) {
-      int e = tid + i * 256;
-      if (!TA) {
-        int m = e & (BM - 1), kk = e >> 7;
-        int gm = m0 + m, gk = k0 + kk;
-        bool ok = (gm < M) && (gk < K);
-        cp_async8(as + kk * G_LDNA + m, ok ? A + gm + (int64_t)gk * lda : A, ok);
-      } else {
-        int kk = e & (BK - 1), m = e / BK;
-        int gm = m0 + m, gk = k0 + kk;
-        bool ok = (gm < M) && (gk < K);
-        cp_async8(as + m * G_LDT + kk, ok ? A + gk + (int64_t)gm * lda : A, ok);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < (BN * BK) / 256; i++) {
-      int e = tid + i * 256;
-      if (!TB) {
-        int n = e & (BN - 1), kk = e / BN;
-        int gn = n0 + n, gk = k0 + kk;
-        bool ok = (gn < N) && (gk < K);
-        cp_async8(bs + kk * G_LDNB + n, ok ? B + gn + (int64_t)gk * ldb : B, ok);
-      } else {
-        int kk = e & (BK - 1), n = e / BK;
-        int gn = n0 + n, gk = k0 + kk;
-        bool ok = (gn < N) && (gk < K);
-        cp_async8(bs + n * G_LDT + kk, ok ? B + gk + (int64_t)gn * ldb : B, ok);
-      }
-    }
-  };
-
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  const int nkt = (K + BK - 1) / BK;
-  const int kt0 = (TA && (T.flags & TF_KLOW)) ? min(m0 / BK, nkt) : 0;  // A' lower triangular: rows k < m0 are zero
-#pragma unroll
-  for (int s = 0; s < G_STAGES - 1; s++) {
-    if (kt0 + s < nkt) load_stage((kt0 + s) % G_STAGES, (kt0 + s) * BK);
-    cp_async_commit();
-  }
-  const int lr = lane >> 2, lc = lane & 3;
-  // Two instances of the main loop: full tiles run an unpredicated DMMA stream (no per-instruction predicate /
-  // reconvergence overhead); partially filled tiles skip inactive 8x8 sub-tiles with warp-uniform predicates.
-  auto main_loop = [&](auto full_tag) {
-    constexpr bool FULL = decltype(full_tag)::value;
-    for (int kt = kt0; kt < nkt; kt++) {
-      cp_async_wait<G_STAGES - 2>();
-      __syncthreads();
-      {
-        int nk = kt + G_STAGES - 1;
-        if (nk < nkt) load_stage(nk % G_STAGES, nk * BK);
-        cp_async_commit();
-      }
-      const double* as = As + (kt % G_STAGES) * A_STAGE;
-      const double* bs = Bs + (kt % G_STAGES) * B_STAGE;
-#pragma unroll
-      for (int kb = 0; kb < BK; kb += 4) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int im = 0; im < 4; im++) {
-          const int rr = (im * 4 + wm) * 8 + lr;
-          af[im] = TA ? as[rr * G_LDT + kb + lc] : as[(kb + lc) * G_LDNA + rr];
-        }
-#pragma unroll
-        for (int in = 0; in < 4; in++) {
-          const int cc = (in * 2 + wn) * 8 + lr;
-          bf[in] = TB ? bs[cc * G_LDT + kb + lc] : bs[(kb + lc) * G_LDNB + cc];
-        }
-#pragma unroll
-        for (int im = 0; im < 4; im++)
-#pragma unroll
-          for (int in = 0; in < 4; in++)
-            if (FULL || (active & (1u << (im * 4 + in)))) dmma884(acc[im][in][0], acc[im][in][1], af[im], bf[in]);
-      }
-    }
-  };
-  if (active == 0xffffu)
-    main_loop(std::true_type{});
-  else
-    main_loop(std::false_type{});
-  cp_async_wait<0>();
-
-  const bool tri = (T.flags & TF_TRI) != 0;
-  const double alpha = T.alpha, beta = T.beta;
-  // Epilogue: C = beta*C + alpha*acc.  The read-modify-write is done one row sub-tile (8 values per thread) at a
-  // time with all loads issued before the first store, so the global-load latency is paid once per group instead
-  // of once per element (the compiler cannot reorder loads across stores to the same array by itself).
-#pragma unroll
-  for (int im = 0; im < 4; im++) {
-    const int row = m0 + (im * 4 + wm) * 8 + lr;
-    double cv[4][2];
-    bool ok[4][2];
-#pragma unroll
-    for (int in = 0; in < 4; in++)
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int col = n0 + (in * 2 + wn) * 8 + 2 * lc + h;
-        ok[in][h] = (active & (1u << (im * 4 + in))) && row < M && col < N && (!tri || row >= col);
-        cv[in][h] = 0.0;
-        if (ok[in][h] && beta != 0.0) cv[in][h] = C[row + (int64_t)col * ldc];
-      }
-#pragma unroll
-    for (int in = 0; in < 4; in++)
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int col = n0 + (in * 2 + wn) * 8 + 2 * lc + h;
-        if (ok[in][h]) C[row + (int64_t)col * ldc] = beta * cv[in][h] + alpha * acc[im][in][h];
-      }
-  }
-}
+// The grouped DMMA GEMM engine lives in gemm_engine.cuh (k_gemm2<TA, TB, CFG>); two tile configurations are
+// instantiated and chosen per launch by the plan builder (Launch::cfg):
+//   GCFG_BIG   128x64 tiles, 8 warps, 3 stages, 2 CTAs/SM  - large, regular problems (33.5 TFLOP/s at n=4736, K=4096)
+//   GCFG_SMALL  64x64 tiles, 8 warps, 4 stages, 3 CTAs/SM  - launches with few or ragged tiles
+using GemmBig = GemmCfg<GEMM_TILE_M[GCFG_BIG], GEMM_TILE_N[GCFG_BIG], 4, 2, 16, 3, 2>;
+using GemmSmall = GemmCfg<GEMM_TILE_M[GCFG_SMALL], GEMM_TILE_N[GCFG_SMALL], 4, 2, 16, 4, 3>;
 
 // -------------------------------------------------------------------------------------------- POTRF ----
 // Cholesky AND inverse of an n x n (n <= 64) diagonal block, one CTA (8 warps) per block, everything in shared
@@ -972,25 +796,28 @@ __global__ void k_scatter_values(const double* __restrict__ nzval, const int64_t
 
 // ---------------------------------------------------------------------------------- host launchers ----
 static size_t potrf_smem() { return (size_t)(3 * 64 * PLD) * sizeof(double); }
-static size_t gemm_smem(bool ta, bool tb) {
-  size_t a = ta ? G_A_STAGE_T : G_A_STAGE_N, b = tb ? G_B_STAGE_T : G_B_STAGE_N;
-  return (a + b) * G_STAGES * sizeof(double);
+template <bool TA, bool TB, class CFG>
+static cudaError_t gemm_attr() {
+  return cudaFuncSetAttribute(k_gemm2<TA, TB, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM);
+}
+template <bool TA, bool TB>
+static void gemm_launch(const Launch& L, const Task* t, const Arenas& ar, cudaStream_t st) {
+  if (L.cfg == GCFG_SMALL)
+    k_gemm2<TA, TB, GemmSmall><<<L.grid, GemmSmall::NT, GemmSmall::SMEM, st>>>(t, L.ntasks, ar);
+  else
+    k_gemm2<TA, TB, GemmBig><<<L.grid, GemmBig::NT, GemmBig::SMEM, st>>>(t, L.ntasks, ar);
 }
 
 cudaError_t kernels_init() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)gemm_smem(false, false));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)gemm_smem(false, true));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)gemm_smem(true, true));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)gemm_smem(true, false));
-  if (e != cudaSuccess) return e;
+  if ((e = gemm_attr<false, false, GemmBig>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<false, true, GemmBig>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<true, true, GemmBig>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<true, false, GemmBig>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<false, false, GemmSmall>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<false, true, GemmSmall>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<true, true, GemmSmall>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<true, false, GemmSmall>()) != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_potrf64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem());
   if (e != cudaSuccess) return e;
   const int small_smem = small_front_smem(SMALL_FRONT_MAX);
@@ -1010,16 +837,16 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
   const Task* t = d_tasks + L.task0;
   switch (L.kind) {
     case LK_GEMM_NT:
-      k_gemm<false, false><<<L.grid, 256, gemm_smem(false, false), st>>>(t, L.ntasks, ar);
+      gemm_launch<false, false>(L, t, ar, st);
       break;
     case LK_GEMM_NN:
-      k_gemm<false, true><<<L.grid, 256, gemm_smem(false, true), st>>>(t, L.ntasks, ar);
+      gemm_launch<false, true>(L, t, ar, st);
       break;
     case LK_GEMM_TN:
-      k_gemm<true, true><<<L.grid, 256, gemm_smem(true, true), st>>>(t, L.ntasks, ar);
+      gemm_launch<true, true>(L, t, ar, st);
       break;
     case LK_GEMM_TT:
-      k_gemm<true, false><<<L.grid, 256, gemm_smem(true, false), st>>>(t, L.ntasks, ar);
+      gemm_launch<true, false>(L, t, ar, st);
       break;
     case LK_POTRF:
       k_potrf64<<<L.grid, 256, potrf_smem(), st>>>(t, L.ntasks, ar, aux.d_info);

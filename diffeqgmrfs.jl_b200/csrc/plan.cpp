@@ -5,8 +5,17 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace gmrfb {
+
+int gemm_big_min() {
+  static const int v = [] {
+    const char* e = std::getenv("GMRFB_GEMM_BIG_MIN");  // tuning aid: 0 = always 128x64 tiles, huge = always 64x64
+    return e ? std::atoi(e) : 128;
+  }();
+  return v;
+}
 
 namespace {
 
@@ -34,7 +43,7 @@ void add_gemm(PlanBuilder& B, Plan& P, int aa, int64_t a, int lda, int ab, int64
   t.alpha = alpha;
   t.beta = beta;
   t.flags = arena_flags(aa, ab, ac) | (tri ? TF_TRI : 0);
-  B.add(t, gemm_tiles(M, N, tri));
+  B.add(t, gemm_tiles(M, N, tri, GCFG_BIG));
   P.flops += gemm_flops(M, N, K, tri);
 }
 
@@ -489,7 +498,7 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
       t.alpha = 1.0;
       t.beta = 0.0;
       t.flags = arena_flags(AR_WORK, AR_FRONT, AR_ZINV) | TF_KLOW;
-      B.add(t, gemm_tiles(sc, r, false));
+      B.add(t, gemm_tiles(sc, r, false, GCFG_BIG));
       P.flops += (double)sc * sc * r;
     }
     B.end();
@@ -517,7 +526,7 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
       t.alpha = 1.0;
       t.beta = 0.0;
       t.flags = arena_flags(AR_WORK, AR_WORK, AR_ZINV) | TF_TRI | TF_KLOW;
-      B.add(t, gemm_tiles(sc, sc, true));
+      B.add(t, gemm_tiles(sc, sc, true, GCFG_BIG));
       P.flops += (double)sc * sc * sc / 3.0;
     }
     B.end();

@@ -26,6 +26,7 @@ class PlanBuilder {
     cur.grid = 0;
     cur.bytes = 0;
     cur.smem = 0;
+    cur.cfg = 0;
     flops0 = P.flops;
   }
   void add(Task t, int ctas) {
@@ -39,6 +40,16 @@ class PlanBuilder {
   void add_bytes(double b) { cur.bytes += b; }
   void end() {
     cur.flops = P.flops - flops0;
+    if (is_gemm_kind(cur.kind) && cur.ntasks > 0) {
+      // GEMM tasks were added with their GCFG_BIG tile counts; pick the launch's tile configuration and re-tile
+      cur.cfg = choose_gemm_cfg(cur.grid, cur.ntasks);
+      cur.grid = 0;
+      for (int32_t i = cur.task0; i < cur.task0 + cur.ntasks; i++) {
+        Task& t = P.tasks[i];
+        t.tile0 = cur.grid;
+        cur.grid += gemm_tiles(t.M, t.N, (t.flags & TF_TRI) != 0, cur.cfg);
+      }
+    }
     if (cur.ntasks > 0) P.launches.push_back(cur);
   }
 

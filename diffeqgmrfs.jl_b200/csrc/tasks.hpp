@@ -58,6 +58,7 @@ struct Launch {
   double flops;  // useful floating-point operations of this launch (0 for data-movement kernels)
   double bytes;  // algorithmic bytes of this launch (0 where not accounted)
   int32_t smem;  // dynamic shared memory of the launch (fused small-front kernels)
+  int32_t cfg;   // GEMM launches: tile configuration (GCFG_*), chosen by PlanBuilder::end()
 };
 
 // Profile slots for kernels that are not plan launches.
@@ -72,11 +73,10 @@ enum : int32_t {
   PK_MAX = 32
 };
 
-// GEMM tile geometry used by both the plan builder (tile counts) and the kernels.
-#ifndef GMRFB_GEMM_BK
-#define GMRFB_GEMM_BK 16
-#endif
-constexpr int GEMM_BM = 128, GEMM_BN = 64, GEMM_BK = GMRFB_GEMM_BK;
+// GEMM tile configurations shared by the plan builder (tile counts) and the kernels (gemm_engine.cuh).
+enum : int32_t { GCFG_BIG = 0, GCFG_SMALL = 1, GCFG_COUNT = 2 };
+constexpr int GEMM_TILE_M[GCFG_COUNT] = {128, 64};
+constexpr int GEMM_TILE_N[GCFG_COUNT] = {64, 64};
 constexpr int NB = 64;           // panel width of the blocked POTRF/TRSM
 constexpr int TRSM_ROWS = 128;   // rows per CTA in the apply-inverse (TRSM) kernels
 constexpr int DINV_SLOT = 64 * 64;  // doubles per inverse-block scratch slot
@@ -93,14 +93,29 @@ inline int small_front_smem(int d) {
   const int dp = (d + 7) & ~7, ld = dp + 4;
   return (dp + 16) * ld * (int)sizeof(double);
 }
-// number of 128x64 tiles of an M x N result; lower-trapezoidal results skip tiles entirely above the diagonal
-// (tile (tm, tn) is needed iff its first column tn*64 <= last row tm*128+127, i.e. tn <= 2*tm + 1)
-inline int gemm_tiles(int M, int N, bool tri) {
-  int tm = cdiv(M, GEMM_BM), tn = cdiv(N, GEMM_BN);
+// number of BM x BN tiles of an M x N result under tile configuration cfg; lower-trapezoidal results skip tiles
+// entirely above the diagonal (tile (tm, tn) is needed iff its first column tn*BN <= its last row tm*BM + BM - 1)
+inline int gemm_tiles(int M, int N, bool tri, int cfg) {
+  const int BM = GEMM_TILE_M[cfg], BN = GEMM_TILE_N[cfg];
+  const int tm = cdiv(M, BM), tn = cdiv(N, BN);
   if (!tri) return tm * tn;
   int t = 0;
-  for (int i = 0; i < tm; i++) t += (2 * i + 2 < tn ? 2 * i + 2 : tn);
+  for (int i = 0; i < tm; i++) {
+    const int w = (i * BM + BM - 1) / BN + 1;
+    t += w < tn ? w : tn;
+  }
   return t;
+}
+inline bool is_gemm_kind(int kind) {
+  return kind == LK_GEMM_NT || kind == LK_GEMM_NN || kind == LK_GEMM_TN || kind == LK_GEMM_TT;
+}
+// Tile configuration of a GEMM launch: 128x64 tiles when the launch consists of large regular problems (on average
+// at least gemm_big_min() 128x64 tiles per task, i.e. about 1024 x 1024 results), 64x64 tiles otherwise: batched
+// launches over many ragged fronts waste less of a small tile, and on the bench workload the small tile is never
+// slower below that size (gpurun sweep of GMRFB_GEMM_BIG_MIN, profiles/r01_gemm_engine.md).
+int gemm_big_min();
+inline int choose_gemm_cfg(int big_tiles, int ntasks) {
+  return (ntasks > 0 && big_tiles / ntasks >= gemm_big_min()) ? GCFG_BIG : GCFG_SMALL;
 }
 
 }  // namespace gmrfb

@@ -5,7 +5,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 timeout 600 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.txt 2>&1; echo "pytest rc=$?"; tail -15 $OUT/${TAG}_pytest.txt
 rm -f $OUT/${TAG}_dump.csv
-GMRFB_PROFILE_DUMP=$OUT/${TAG}_dump.csv timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+GMRFB_PROFILE_DUMP=$OUT/${TAG}_dump.csv timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --inflight 1 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
 python - <<PY
 import json
 d=json.load(open("$OUT/${TAG}_bench.json"))
