@@ -351,9 +351,15 @@ def run_gpu_arm(args):
     prof_rows = []
     if rank == 0:
         ctx = L0.ctx
+        # cudaProfilerStart/Stop bracket exactly this replayed step: `ncu --profile-from-start off` captures the
+        # launches of one posterior solve without any launch counting (no effect outside a profiler)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
         ctx.profile_begin()
         L0.steps_device(1)
         prof = ctx.profile_end()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
         tot = sum(p["ms"] for p in prof)
         for p in sorted(prof, key=lambda q: -q["ms"]):
             row = dict(name=p["name"], launches=p["launches"], ms=round(p["ms"], 3), share=round(p["ms"] / tot, 4))

@@ -42,16 +42,11 @@ __device__ __forceinline__ void ge_dmma(double& c0, double& c1, double a, double
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
 }
+// Task of CTA `cta`: launches with more than one task carry a CTA -> task map right after their tasks
+// (PlanBuilder::end in plan.hpp).
 __device__ __forceinline__ int ge_find_task(const Task* __restrict__ tasks, int ntasks, int cta) {
-  int lo = 0, hi = ntasks - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (tasks[mid].tile0 <= cta)
-      lo = mid;
-    else
-      hi = mid - 1;
-  }
-  return lo;
+  if (ntasks == 1) return 0;
+  return reinterpret_cast<const int32_t*>(tasks + ntasks)[cta];
 }
 
 template <int BM_, int BN_, int WARPS_M_, int WARPS_N_, int BK_, int STAGES_, int MINB_>

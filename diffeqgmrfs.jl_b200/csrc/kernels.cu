@@ -22,16 +22,11 @@
 namespace gmrfb {
 
 // ------------------------------------------------------------------------------------------ helpers ----
+// Task of CTA `cta`: launches with more than one task carry a CTA -> task map in the Task-sized slots that follow
+// their tasks (PlanBuilder::end), so the lookup is one load instead of a binary search over the tile0 prefix sums.
 __device__ __forceinline__ int find_task(const Task* __restrict__ tasks, int ntasks, int cta) {
-  int lo = 0, hi = ntasks - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (tasks[mid].tile0 <= cta)
-      lo = mid;
-    else
-      hi = mid - 1;
-  }
-  return lo;
+  if (ntasks == 1) return 0;
+  return reinterpret_cast<const int32_t*>(tasks + ntasks)[cta];
 }
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {

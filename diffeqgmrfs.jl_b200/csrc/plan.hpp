@@ -50,6 +50,19 @@ class PlanBuilder {
         cur.grid += gemm_tiles(t.M, t.N, (t.flags & TF_TRI) != 0, cur.cfg);
       }
     }
+    if (cur.ntasks > 1 && uses_cta_map(cur.kind)) {
+      // CTA -> task map of the launch, stored in Task-sized slots right after its tasks (kernels read
+      // reinterpret_cast<const int32_t*>(tasks + ntasks)[blockIdx.x] instead of searching the tile0 prefix sums)
+      const size_t nslots = ((size_t)cur.grid * sizeof(int32_t) + sizeof(Task) - 1) / sizeof(Task);
+      const size_t first = P.tasks.size();
+      P.tasks.resize(first + nslots, Task{});
+      int32_t* map = reinterpret_cast<int32_t*>(P.tasks.data() + first);
+      for (int32_t i = 0; i < cur.ntasks; i++) {
+        const int32_t lo = P.tasks[cur.task0 + i].tile0;
+        const int32_t hi = (i + 1 < cur.ntasks) ? P.tasks[cur.task0 + i + 1].tile0 : cur.grid;
+        for (int32_t c = lo; c < hi; c++) map[c] = i;
+      }
+    }
     if (cur.ntasks > 0) P.launches.push_back(cur);
   }
 

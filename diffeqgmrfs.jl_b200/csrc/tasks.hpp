@@ -106,6 +106,17 @@ inline int gemm_tiles(int M, int N, bool tri, int cfg) {
   }
   return t;
 }
+// launch kinds whose kernels serve several CTAs per task and look their task up through the CTA -> task map
+inline bool uses_cta_map(int kind) {
+  switch (kind) {
+    case LK_GEMM_NT: case LK_GEMM_NN: case LK_GEMM_TN: case LK_GEMM_TT: case LK_TRSM_RLT: case LK_TRSM_RLN:
+    case LK_EXTEND_ADD: case LK_GATHER_SYM: case LK_SET_IDENTITY: case LK_TRANSPOSE: case LK_SCALE:
+    case LK_DIAG_OUT: case LK_SYMMETRIZE:
+      return true;
+    default:
+      return false;
+  }
+}
 inline bool is_gemm_kind(int kind) {
   return kind == LK_GEMM_NT || kind == LK_GEMM_NN || kind == LK_GEMM_TN || kind == LK_GEMM_TT;
 }

@@ -7,14 +7,14 @@ OUT=gpurun_out
 mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.txt 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest_gpu.txt
 tail -3 $OUT/${TAG}_pytest_gpu.txt
-python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 2 --warmup 1 ${REF_ARGS:-} > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref rc=$?"
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+( time python bench.py --steps 5 --warmup 3 ) > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+( time python bench.py --impl reference --steps 2 --warmup 1 ${REF_ARGS:-} ) > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref rc=$?"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --inflight 1"
 $CMD > $OUT/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-10080} -c ${NCU_COUNT:-3400} --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-k_gemm} -s ${NCU_KSKIP:-1000} -c ${NCU_KCOUNT:-24} \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-k_gemm2} -s ${NCU_KSKIP:-100} -c ${NCU_KCOUNT:-24} \
     -f -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT | tail -20

@@ -94,12 +94,7 @@ int main() {
   k_fill<<<(unsigned)((nmax + 255) / 256), 256>>>(B, nmax, 2u);
   CK(cudaDeviceSynchronize());
   suite<GemmCfg<128, 64, 4, 2, 16, 3, 2>>("128x64 w4x2 k16 s3 b2", A, B, C, Cr);
-  suite<GemmCfg<128, 64, 4, 2, 16, 4, 2>>("128x64 w4x2 k16 s4 b2", A, B, C, Cr);
   suite<GemmCfg<128, 128, 4, 2, 16, 4, 1>>("128x128 w4x2 k16 s4 b1", A, B, C, Cr);
-  suite<GemmCfg<128, 128, 2, 4, 16, 4, 1>>("128x128 w2x4 k16 s4 b1", A, B, C, Cr);
-  suite<GemmCfg<128, 128, 4, 4, 16, 4, 1>>("128x128 w4x4 k16 s4 b1", A, B, C, Cr);
-  suite<GemmCfg<128, 128, 4, 4, 8, 6, 1>>("128x128 w4x4 k8 s6 b1", A, B, C, Cr);
-  suite<GemmCfg<64, 64, 2, 2, 16, 4, 4>>("64x64 w2x2 k16 s4 b4", A, B, C, Cr);
   suite<GemmCfg<64, 64, 4, 2, 16, 4, 3>>("64x64 w4x2 k16 s4 b3", A, B, C, Cr);
   return 0;
 }
