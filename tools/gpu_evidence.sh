@@ -14,7 +14,7 @@ $CMD > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-k_gemm2} -s ${NCU_KSKIP:-100} -c ${NCU_KCOUNT:-24} \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-k_gemm2} -s ${NCU_KSKIP:-100} -c ${NCU_KCOUNT:-10} \
     -f -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT | tail -20
