@@ -103,6 +103,8 @@ static const char* prof_name(int kind) {
     case LK_GEMM_NN: return "k_gemm<NN> (DMMA)";
     case LK_GEMM_TN: return "k_gemm<TN> (DMMA)";
     case LK_GEMM_TT: return "k_gemm<TT> (DMMA)";
+    case LK_SKINNY_NT: return "k_skinny_nt";
+    case LK_SKINNY_NN: return "k_skinny_nn";
     case LK_POTRF: return "k_potrf64";
     case LK_TRSM_RLT: return "k_apply_inv<T>";
     case LK_TRSM_RLN: return "k_apply_inv<N>";

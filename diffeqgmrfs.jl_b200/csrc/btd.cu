@@ -26,6 +26,13 @@ struct gmrfb_btd {
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_block = -1;
   bool factored = false;
+  // Solves apply W_i = L_i^{-1} (computed once per factorisation, on the first solve, by recursive doubling from the
+  // inverted 64x64 diagonal blocks): every block step of a sweep is then two GEMM launches whose cost is reading C_i
+  // and W_i once, instead of a chain of b/64 dependent substitution steps.
+  DevBuf<double> winv;  // N blocks of b x b (ld), strict upper triangles zero
+  DevBuf<double> skws;  // workspace of the skinny kernels (arrival counters + K-slice partial sums), passed as Arenas::dinv
+  bool winv_ready = false;
+  DevPlan plan_winv;
   // solve plans are built per nrhs on demand
   int plan_nrhs = -1;
   DevPlan fwd_first, fwd_step, bwd_last, bwd_step;
@@ -159,6 +166,7 @@ gmrfb_status btd_run_factor(gmrfb_btd* f) {
   f->status = GMRFB_OK;
   f->fail_block = -1;
   f->factored = true;
+  f->winv_ready = false;
   if (info != INT_MAX) {
     // locate the first block whose diagonal is poisoned
     std::vector<double> dg((size_t)(f->b * f->N));
@@ -300,104 +308,153 @@ extern "C" gmrfb_status gmrfb_btd_logdet(gmrfb_btd* f, double* logdet) {
 }
 
 // ---------------------------------------------------------------------------------------------- solve ----
-// Device RHS layout: Xt is nrhs x (b*N), leading dimension ldr; block i occupies columns [i*b, (i+1)*b).
-// Arena 0 = factor slots (moving base), arena 1 = Xt (moving base at block i).
+// Device RHS layout: node-major, nrhs x (b*N) with leading dimension ldr; block i occupies columns [i*b, (i+1)*b).
+// Two such buffers are used alternately (a GEMM cannot run in place):
+//   forward   U_i = X_i - Y_{i-1} C_i'          (in X),   Y_i = U_i W_i'   (into Y)
+//   backward  V_i = Y_i - X_{i+1} C_{i+1}       (in Y),   X_i = V_i W_i    (into X)
+// Arenas (all moving with the block): 0 = factor slot i, 1 = X block i, 2 = Y block i, 3 = W_i.
+static gmrfb_status btd_ensure_winv(gmrfb_btd* f) {
+  if (f->winv_ready) return GMRFB_OK;
+  gmrfb_ctx* ctx = f->ctx;
+  const int b = (int)f->b, ld = f->ld;
+  const int64_t bs = (int64_t)ld * b;
+  if (f->winv.n < (size_t)(bs * f->N)) GMRFB_CU(ctx, f->winv.alloc((size_t)(bs * f->N)));
+  GMRFB_CU(ctx, cudaMemsetAsync(f->winv.p, 0, (size_t)(bs * f->N) * sizeof(double), ctx->stream));
+  if (!f->plan_winv.ready) {
+    PlanBuilder B(f->plan_winv.host);
+    plan_trtri(B, f->plan_winv.host, 0, 0, ld, 1, 0, ld, 2, 0, b);
+    gmrfb_status rc = upload_plan(ctx, f->plan_winv);
+    if (rc != GMRFB_OK) return rc;
+    if ((rc = ensure_dinv(f, f->plan_winv.host)) != GMRFB_OK) return rc;
+  }
+  DevBuf<double> scratch;
+  GMRFB_CU(ctx, scratch.alloc((size_t)bs));
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  for (int64_t i = 0; i < f->N; i++) {
+    Arenas ar{{f->arena.p + i * f->slot, f->winv.p + i * bs, scratch.p, nullptr}};
+    ar.dinv = f->dinv.p;
+    gmrfb_status rc = run_plan(ctx, f->plan_winv, ar, aux);
+    if (rc != GMRFB_OK) return rc;
+  }
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // scratch is released on return
+  f->winv_ready = true;
+  return GMRFB_OK;
+}
+
+static void btd_add_solve_gemm(PlanBuilder& B, Plan& P, int kind, int aa, int64_t a, int ab, int64_t b, int ldb, int ac,
+                               int nrhs, int n, int ldr, double alpha, double beta, int32_t extra) {
+  // few right-hand sides: bandwidth-bound streaming kernels; otherwise the tile engine
+  const bool skinny = nrhs <= SKINNY_MAX_ROWS;
+  B.begin(skinny ? (kind == LK_GEMM_NT ? LK_SKINNY_NT : LK_SKINNY_NN) : kind);
+  Task t = make_task();
+  t.a = a;
+  t.lda = ldr;
+  t.b = b;
+  t.ldb = ldb;
+  t.c = 0;
+  t.ldc = ldr;
+  t.M = nrhs;
+  t.N = n;
+  t.K = n;
+  t.alpha = alpha;
+  t.beta = beta;
+  t.flags = (aa << TF_A_SHIFT) | (ab << TF_B_SHIFT) | (ac << TF_C_SHIFT) | extra;
+  if (!skinny) {
+    B.add(t, gemm_tiles(nrhs, n, false, GCFG_BIG));
+  } else if (kind == LK_GEMM_NT) {
+    t.aux0 = skinny_slices(n, n);
+    B.add(t, cdiv(n, SKINNY_ROWS) * t.aux0);
+    B.set_cfg(skinny_nr(nrhs));
+    P.dinv = std::max(P.dinv, skinny_workspace(nrhs, n, n));
+  } else {
+    B.add(t, cdiv(n, 8));
+    B.set_cfg(skinny_nr(nrhs));
+  }
+  // algorithmic bytes: the matrix operand once (a triangular W: its lower half)
+  B.add_bytes(8.0 * n * (double)n * ((extra & (TF_BUPP | TF_BLOW)) ? 0.5 : 1.0));
+  B.end();
+}
+
 static gmrfb_status btd_build_solve_plans(gmrfb_btd* f, int nrhs, int ldr) {
   if (f->plan_nrhs == nrhs) return GMRFB_OK;
   gmrfb_ctx* ctx = f->ctx;
-  const int b = (int)f->b;
-  const int64_t coff = (int64_t)f->ld * b;
-  const int64_t xstep = (int64_t)ldr * b;  // doubles between consecutive blocks of Xt
+  const int b = (int)f->b, ld = f->ld;
+  const int64_t coff = (int64_t)ld * b;
+  const int64_t xstep = (int64_t)ldr * b;  // doubles between consecutive blocks of a right-hand-side buffer
   for (DevPlan* dp : {&f->fwd_first, &f->fwd_step, &f->bwd_last, &f->bwd_step}) {
     dp->host = Plan();
     dp->tasks.release();
     dp->ready = false;
   }
-  {  // x_1 = b_1 L_1^{-T}
-    PlanBuilder B(f->fwd_first.host);
-    plan_trsm_rlt(B, f->fwd_first.host, 0, 0, f->ld, 1, 0, nrhs, b, ldr);
+  {  // Y_1 = X_1 W_1'
+    Plan& BP = f->fwd_first.host;
+    PlanBuilder B(BP);
+    btd_add_solve_gemm(B, BP, LK_GEMM_NT, 1, 0, 3, 0, ld, 2, nrhs, b, ldr, 1.0, 0.0, TF_BUPP);
   }
-  {  // x_i = (b_i - x_{i-1} C_i') L_i^{-T}
-    Plan& P = f->fwd_step.host;
-    PlanBuilder B(P);
-    B.begin(LK_GEMM_NT);
-    Task t = make_task();
-    t.a = -xstep;
-    t.lda = ldr;
-    t.b = coff;
-    t.ldb = f->ld;
-    t.c = 0;
-    t.ldc = ldr;
-    t.M = nrhs;
-    t.N = b;
-    t.K = b;
-    t.alpha = -1.0;
-    t.beta = 1.0;
-    t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (1 << TF_C_SHIFT);
-    B.add(t, gemm_tiles(nrhs, b, false, GCFG_BIG));
-    B.end();
-    plan_trsm_rlt(B, P, 0, 0, f->ld, 1, 0, nrhs, b, ldr);
+  {  // X_i -= Y_{i-1} C_i';  Y_i = X_i W_i'
+    Plan& BP = f->fwd_step.host;
+    PlanBuilder B(BP);
+    btd_add_solve_gemm(B, BP, LK_GEMM_NT, 2, -xstep, 0, coff, ld, 1, nrhs, b, ldr, -1.0, 1.0, 0);
+    btd_add_solve_gemm(B, BP, LK_GEMM_NT, 1, 0, 3, 0, ld, 2, nrhs, b, ldr, 1.0, 0.0, TF_BUPP);
   }
-  {  // x_N = b_N L_N^{-1}
-    PlanBuilder B(f->bwd_last.host);
-    plan_trsm_rln(B, f->bwd_last.host, 0, 0, f->ld, 1, 0, nrhs, b, ldr, false);
+  {  // X_N = Y_N W_N
+    Plan& BP = f->bwd_last.host;
+    PlanBuilder B(BP);
+    btd_add_solve_gemm(B, BP, LK_GEMM_NN, 2, 0, 3, 0, ld, 1, nrhs, b, ldr, 1.0, 0.0, TF_BLOW);
   }
-  {  // x_i = (b_i - x_{i+1} C_{i+1}) L_i^{-1}; C_{i+1} sits in the next slot
-    Plan& P = f->bwd_step.host;
-    PlanBuilder B(P);
-    B.begin(LK_GEMM_NN);
-    Task t = make_task();
-    t.a = xstep;
-    t.lda = ldr;
-    t.b = f->slot + coff;
-    t.ldb = f->ld;
-    t.c = 0;
-    t.ldc = ldr;
-    t.M = nrhs;
-    t.N = b;
-    t.K = b;
-    t.alpha = -1.0;
-    t.beta = 1.0;
-    t.flags = (1 << TF_A_SHIFT) | (0 << TF_B_SHIFT) | (1 << TF_C_SHIFT);
-    B.add(t, gemm_tiles(nrhs, b, false, GCFG_BIG));
-    B.end();
-    plan_trsm_rln(B, P, 0, 0, f->ld, 1, 0, nrhs, b, ldr, false);
+  {  // Y_i -= X_{i+1} C_{i+1} (C_{i+1} sits in the next slot);  X_i = Y_i W_i
+    Plan& BP = f->bwd_step.host;
+    PlanBuilder B(BP);
+    btd_add_solve_gemm(B, BP, LK_GEMM_NN, 1, xstep, 0, f->slot + coff, ld, 2, nrhs, b, ldr, -1.0, 1.0, 0);
+    btd_add_solve_gemm(B, BP, LK_GEMM_NN, 2, 0, 3, 0, ld, 1, nrhs, b, ldr, 1.0, 0.0, TF_BLOW);
   }
   gmrfb_status rc;
-  if ((rc = upload_plan(ctx, f->fwd_first)) != GMRFB_OK) return rc;
-  if ((rc = upload_plan(ctx, f->fwd_step)) != GMRFB_OK) return rc;
-  if ((rc = upload_plan(ctx, f->bwd_last)) != GMRFB_OK) return rc;
-  if ((rc = upload_plan(ctx, f->bwd_step)) != GMRFB_OK) return rc;
-  for (DevPlan* dp : {&f->fwd_first, &f->fwd_step, &f->bwd_last, &f->bwd_step})
-    if ((rc = ensure_dinv(f, dp->host)) != GMRFB_OK) return rc;
+  for (DevPlan* dp : {&f->fwd_first, &f->fwd_step, &f->bwd_last, &f->bwd_step}) {
+    if ((rc = upload_plan(ctx, *dp)) != GMRFB_OK) return rc;
+    if ((int64_t)f->skws.n < dp->host.dinv) {
+      GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+      GMRFB_CU(ctx, f->skws.alloc((size_t)dp->host.dinv));
+      // the arrival counters at the head of the workspace must start at zero (the kernels leave them at zero)
+      GMRFB_CU(ctx, cudaMemsetAsync(f->skws.p, 0, (size_t)dp->host.dinv * sizeof(double), ctx->stream));
+    }
+  }
   f->plan_nrhs = nrhs;
   return GMRFB_OK;
 }
 
-// Run the forward and/or backward block sweeps of factor `f` on a device node-major buffer dXt (nrhs x b*N).
+// Run the forward and/or backward block sweeps of factor `f` on a device node-major buffer dXt (nrhs x b*N), in place.
 static gmrfb_status btd_sweep(gmrfb_btd* f, bool fwd, bool bwd, double* dXt, int ldr, int nrhs) {
   gmrfb_ctx* ctx = f->ctx;
-  gmrfb_status rc = btd_build_solve_plans(f, nrhs, ldr);
+  gmrfb_status rc = btd_ensure_winv(f);
   if (rc != GMRFB_OK) return rc;
+  if ((rc = btd_build_solve_plans(f, nrhs, ldr)) != GMRFB_OK) return rc;
   LaunchAux aux;
   aux.d_info = ctx->d_info;
-  const int64_t xstep = (int64_t)ldr * f->b;
+  const int64_t xstep = (int64_t)ldr * f->b, bs = (int64_t)f->ld * f->b;
+  const size_t bytes = (size_t)(xstep * f->N) * sizeof(double);
+  DevBuf<double> Y;
+  GMRFB_CU(ctx, Y.alloc((size_t)(xstep * f->N)));
+  if (!fwd) GMRFB_CU(ctx, cudaMemcpyAsync(Y.p, dXt, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  auto arenas = [&](int64_t i) {
+    Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, Y.p + i * xstep, f->winv.p + i * bs}};
+    ar.dinv = f->skws.p;
+    return ar;
+  };
   if (fwd) {
     for (int64_t i = 0; i < f->N; i++) {
-      Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, nullptr, nullptr}};
-      ar.dinv = f->dinv.p;
-      rc = run_plan(ctx, i == 0 ? f->fwd_first : f->fwd_step, ar, aux);
+      rc = run_plan(ctx, i == 0 ? f->fwd_first : f->fwd_step, arenas(i), aux);
       if (rc != GMRFB_OK) return rc;
     }
+    if (!bwd) GMRFB_CU(ctx, cudaMemcpyAsync(dXt, Y.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   if (bwd) {
     for (int64_t i = f->N - 1; i >= 0; i--) {
-      Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, nullptr, nullptr}};
-      ar.dinv = f->dinv.p;
-      rc = run_plan(ctx, i == f->N - 1 ? f->bwd_last : f->bwd_step, ar, aux);
+      rc = run_plan(ctx, i == f->N - 1 ? f->bwd_last : f->bwd_step, arenas(i), aux);
       if (rc != GMRFB_OK) return rc;
     }
   }
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // Y is released on return
   return GMRFB_OK;
 }
 
@@ -622,29 +679,6 @@ gmrfb_status gemm_once(gmrfb_ctx* ctx, int kind, const double* A, int lda, const
   return GMRFB_OK;
 }
 
-// X (M x b, ldx) <- X L^{-T} or X L^{-1} with the b x b factor L (ldl), blocked plan executed once
-gmrfb_status trsm_once(gmrfb_ctx* ctx, bool trans, const double* L, int ldl, double* X, int ldx, int M, int b) {
-  DevPlan P;
-  {
-    PlanBuilder B(P.host);
-    if (trans)
-      plan_trsm_rlt(B, P.host, 0, 0, ldl, 1, 0, M, b, ldx);
-    else
-      plan_trsm_rln(B, P.host, 0, 0, ldl, 1, 0, M, b, ldx, false);
-  }
-  GMRFB_CU(ctx, P.tasks.upload(P.host.tasks, ctx->stream));
-  DevBuf<double> dinv;
-  GMRFB_CU(ctx, dinv.alloc((size_t)std::max<int64_t>(P.host.dinv, 1)));
-  Arenas ar{{const_cast<double*>(L), X, nullptr, nullptr}};
-  ar.dinv = dinv.p;
-  LaunchAux aux;
-  aux.d_info = ctx->d_info;
-  gmrfb_status rc = run_plan(ctx, P, ar, aux);
-  if (rc != GMRFB_OK) return rc;
-  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return GMRFB_OK;
-}
-
 }  // namespace
 
 extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int32_t nranks, int64_t b, int64_t nloc,
@@ -681,36 +715,69 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
   GMRFB_CU(ctx, cudaMemsetAsync(h->iface.p, 0, 3 * b * b * sizeof(double), ctx->stream));
   DevBuf<double> tmp;
   GMRFB_CU(ctx, tmp.alloc((size_t)bs));
+  // the couplings with the neighbouring separators are eliminated with W_i = L_i^{-1} of the interior blocks (the same
+  // inverses the solves use), so the whole spike recurrence is a replayed static plan of GEMMs without host round trips
+  if (h->has_spike || h->has_sep) {
+    rc = btd_ensure_winv(F);
+    if (rc != GMRFB_OK) return rc;
+  }
   if (h->has_spike) {
     GMRFB_CU(ctx, h->W.alloc((size_t)(bs * h->ni)));
-    // W_1 = E_l' L_1^{-T},  E_l = B_local[:,:,0] (rows: first interior block, cols: previous separator)
-    GMRFB_CU(ctx, cudaMemcpy2DAsync(tmp.p, ld * sizeof(double), B_local, b * sizeof(double), b * sizeof(double), b,
+    // scratch arena: [ T (b x b, ld) | E_l (b x b, ld) | Q (b x b, ld) ]
+    DevBuf<double> work;
+    GMRFB_CU(ctx, work.alloc((size_t)(3 * bs)));
+    GMRFB_CU(ctx, cudaMemsetAsync(work.p + 2 * bs, 0, (size_t)bs * sizeof(double), ctx->stream));
+    // E_l = B_local[:,:,0] (rows: first interior block, cols: previous separator)
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(work.p + bs, ld * sizeof(double), B_local, b * sizeof(double), b * sizeof(double), b,
                                     cudaMemcpyHostToDevice, ctx->stream));
-    rc = transpose_dev(ctx, tmp.p, ld, h->W.p, ld, b, b);
-    if (rc != GMRFB_OK) return rc;
-    rc = trsm_once(ctx, true, F->arena.p, ld, h->W.p, ld, ib, ib);
-    if (rc != GMRFB_OK) return rc;
-    for (int64_t i = 1; i < h->ni; i++) {
-      // W_i = -W_{i-1} C_i' ; W_i <- W_i L_i^{-T}
-      const double* Ci = F->arena.p + i * F->slot + bs;
-      rc = gemm_once(ctx, LK_GEMM_NT, h->W.p + (i - 1) * bs, ld, Ci, ld, h->W.p + i * bs, ld, ib, ib, ib, false, -1.0, 0.0);
-      if (rc != GMRFB_OK) return rc;
-      rc = trsm_once(ctx, true, F->arena.p + i * F->slot, ld, h->W.p + i * bs, ld, ib, ib);
-      if (rc != GMRFB_OK) return rc;
+    // arenas: 0 = factor slot i, 1 = spike block i (block i-1 at -bs), 2 = work, 3 = W_i = L_i^{-1}
+    auto gemm = [&](PlanBuilder& B, int kind, int aa, int64_t a, int ab, int64_t bo, int ac, int64_t c, bool tri, double alpha,
+                    double beta, int32_t extra) {
+      B.begin(kind);
+      Task t = make_task();
+      t.a = a;
+      t.b = bo;
+      t.c = c;
+      t.lda = t.ldb = t.ldc = ld;
+      t.M = t.N = t.K = ib;
+      t.alpha = alpha;
+      t.beta = beta;
+      t.flags = (aa << TF_A_SHIFT) | (ab << TF_B_SHIFT) | (ac << TF_C_SHIFT) | (tri ? TF_TRI : 0) | extra;
+      B.add(t, gemm_tiles(ib, ib, tri, GCFG_BIG));
+      B.end();
+    };
+    DevPlan first, step;
+    {  // S_1 = E_l' W_1';  Q = S_1 S_1'
+      PlanBuilder B(first.host);
+      gemm(B, LK_GEMM_TT, 2, bs, 3, 0, 1, 0, false, 1.0, 0.0, TF_BUPP);
+      gemm(B, LK_GEMM_NT, 1, 0, 1, 0, 2, 2 * bs, true, 1.0, 1.0, 0);
     }
-    // Q = sum_i W_i W_i'  (lower triangle)
+    {  // T = S_{i-1} C_i';  S_i = -T W_i';  Q += S_i S_i'
+      PlanBuilder B(step.host);
+      gemm(B, LK_GEMM_NT, 1, -bs, 0, bs, 2, 0, false, 1.0, 0.0, 0);
+      gemm(B, LK_GEMM_NT, 2, 0, 3, 0, 1, 0, false, -1.0, 0.0, TF_BUPP);
+      gemm(B, LK_GEMM_NT, 1, 0, 1, 0, 2, 2 * bs, true, 1.0, 1.0, 0);
+    }
+    if ((rc = upload_plan(ctx, first)) != GMRFB_OK) return rc;
+    if ((rc = upload_plan(ctx, step)) != GMRFB_OK) return rc;
+    LaunchAux aux;
+    aux.d_info = ctx->d_info;
     for (int64_t i = 0; i < h->ni; i++) {
-      rc = gemm_once(ctx, LK_GEMM_NT, h->W.p + i * bs, ld, h->W.p + i * bs, ld, h->iface.p + b * b, ib, ib, ib, ib, true, 1.0,
-                     i == 0 ? 0.0 : 1.0);
+      Arenas ar{{F->arena.p + i * F->slot, h->W.p + i * bs, work.p, F->winv.p + i * bs}};
+      rc = run_plan(ctx, i == 0 ? first : step, ar, aux);
       if (rc != GMRFB_OK) return rc;
     }
+    // Q (lower triangle) -> iface block 1 (ld = b)
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(h->iface.p + b * b, b * sizeof(double), work.p + 2 * bs, ld * sizeof(double),
+                                    b * sizeof(double), b, cudaMemcpyDeviceToDevice, ctx->stream));
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // work and the plans are released here
   }
   if (h->has_sep) {
     GMRFB_CU(ctx, h->V.alloc((size_t)bs));
     // V = E_r L_ni^{-T},  E_r = B_local[:,:,nloc-1] (rows: separator, cols: last interior block)
-    GMRFB_CU(ctx, cudaMemcpy2DAsync(h->V.p, ld * sizeof(double), B_local + (nloc - 1) * b * b, b * sizeof(double),
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(tmp.p, ld * sizeof(double), B_local + (nloc - 1) * b * b, b * sizeof(double),
                                     b * sizeof(double), b, cudaMemcpyHostToDevice, ctx->stream));
-    rc = trsm_once(ctx, true, F->arena.p + (h->ni - 1) * F->slot, ld, h->V.p, ld, ib, ib);
+    rc = gemm_once(ctx, LK_GEMM_NT, tmp.p, ld, F->winv.p + (h->ni - 1) * bs, ld, h->V.p, ld, ib, ib, ib, false, 1.0, 0.0);
     if (rc != GMRFB_OK) return rc;
     // iface0 = D_sep - V V'
     GMRFB_CU(ctx, cudaMemcpyAsync(h->iface.p, D_local + (nloc - 1) * b * b, b * b * sizeof(double), cudaMemcpyHostToDevice,

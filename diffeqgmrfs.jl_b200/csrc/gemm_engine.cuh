@@ -153,8 +153,11 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) k_gemm2(const Task* __rest
   const unsigned a_dst = (unsigned)__cvta_generic_to_shared(As + a_k * LDA + a_m);
   const unsigned b_dst = (unsigned)__cvta_generic_to_shared(Bs + b_k * LDB + b_n);
 
-  const int nkt = (K + BK - 1) / BK;
-  const int kt0 = (TA && (T.flags & TF_KLOW)) ? min(m0 / BK, nkt) : 0;  // A' lower triangular: rows k < m0 are zero
+  // reduction range in BK steps; triangular operands (flags) shorten it per tile
+  int nkt = (K + BK - 1) / BK;
+  int kt0 = (TA && (T.flags & TF_KLOW)) ? min(m0 / BK, nkt) : 0;  // A' lower triangular: rows k < m0 are zero
+  if (TB && (T.flags & TF_BLOW)) kt0 = max(kt0, min(n0 / BK, nkt));           // B (K x N) lower: k < n0 is zero
+  if (!TB && (T.flags & TF_BUPP)) nkt = min(nkt, (n0 + BN + BK - 1) / BK);    // B (N x K) lower: k >= n0 + BN is zero
   // sources of the thread's first copy at k-iteration kt0
   const double* a_src = TA ? A + (kt0 * BK + a_k) + (int64_t)(m0 + a_m) * lda : A + (m0 + a_m) + (int64_t)(kt0 * BK + a_k) * lda;
   const double* b_src = TB ? B + (kt0 * BK + b_k) + (int64_t)(n0 + b_n) * ldb : B + (n0 + b_n) + (int64_t)(kt0 * BK + b_k) * ldb;

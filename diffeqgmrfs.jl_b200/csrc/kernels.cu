@@ -16,6 +16,7 @@
 
 #include "gemm_engine.cuh"
 #include "kernels.hpp"
+#include "skinny_kernels.cuh"
 #include "sparse_kernels.hpp"
 #include "tasks.hpp"
 
@@ -842,6 +843,22 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       break;
     case LK_GEMM_TT:
       gemm_launch<true, false>(L, t, ar, st);
+      break;
+    case LK_SKINNY_NT:
+      switch (L.cfg) {
+        case 1: k_skinny_nt<1><<<L.grid, SK_ROWS, 0, st>>>(t, ar); break;
+        case 2: k_skinny_nt<2><<<L.grid, SK_ROWS, 0, st>>>(t, ar); break;
+        case 4: k_skinny_nt<4><<<L.grid, SK_ROWS, 0, st>>>(t, ar); break;
+        default: k_skinny_nt<8><<<L.grid, SK_ROWS, 0, st>>>(t, ar); break;
+      }
+      break;
+    case LK_SKINNY_NN:
+      switch (L.cfg) {
+        case 1: k_skinny_nn<1><<<L.grid, 256, 0, st>>>(t, ar); break;
+        case 2: k_skinny_nn<2><<<L.grid, 256, 0, st>>>(t, ar); break;
+        case 4: k_skinny_nn<4><<<L.grid, 256, 0, st>>>(t, ar); break;
+        default: k_skinny_nn<8><<<L.grid, 256, 0, st>>>(t, ar); break;
+      }
       break;
     case LK_POTRF:
       k_potrf64<<<L.grid, 256, potrf_smem(), st>>>(t, L.ntasks, ar, aux.d_info);

@@ -238,10 +238,11 @@ struct TrtriProb {
   int arenaL;
   int64_t loff;
   int ldl;
-  int arenaW;   // W and the scratch T live in the same arena
+  int arenaW;   // W and the scratch T live in the same arena unless arenaT >= 0
   int64_t woff, toff;
   int ldw;
   int n;
+  int arenaT = -1;
 };
 
 static void plan_trtri_batch(PlanBuilder& B, Plan& P, const std::vector<TrtriProb>& probs) {
@@ -268,20 +269,28 @@ static void plan_trtri_batch(PlanBuilder& B, Plan& P, const std::vector<TrtriPro
       for (int j0 = 0; j0 + h < p.n; j0 += 2 * h) {
         int j1 = j0 + h, hc = std::min(h, p.n - j1);
         add_gemm(B, P, p.arenaL, p.loff + (int64_t)j0 * p.ldl + j1, p.ldl, p.arenaW, p.woff + (int64_t)j0 * p.ldw + j0,
-                 p.ldw, p.arenaW, p.toff + (int64_t)j0 * p.ldw + j1, p.ldw, hc, h, h, false, 1.0, 0.0);
+                 p.ldw, p.arenaT >= 0 ? p.arenaT : p.arenaW, p.toff + (int64_t)j0 * p.ldw + j1, p.ldw, hc, h, h, false,
+                 1.0, 0.0);
       }
     B.end();
     B.begin(LK_GEMM_NN);  // W_BA = -C^{-1} T
     for (auto& p : probs)
       for (int j0 = 0; j0 + h < p.n; j0 += 2 * h) {
         int j1 = j0 + h, hc = std::min(h, p.n - j1);
-        add_gemm(B, P, p.arenaW, p.woff + (int64_t)j1 * p.ldw + j1, p.ldw, p.arenaW, p.toff + (int64_t)j0 * p.ldw + j1,
-                 p.ldw, p.arenaW, p.woff + (int64_t)j0 * p.ldw + j1, p.ldw, hc, h, hc, false, -1.0, 0.0);
+        add_gemm(B, P, p.arenaW, p.woff + (int64_t)j1 * p.ldw + j1, p.ldw, p.arenaT >= 0 ? p.arenaT : p.arenaW,
+                 p.toff + (int64_t)j0 * p.ldw + j1, p.ldw, p.arenaW, p.woff + (int64_t)j0 * p.ldw + j1, p.ldw, hc, h, hc,
+                 false, -1.0, 0.0);
       }
     B.end();
   }
 }
 
+void plan_trtri(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaW, int64_t woff, int ldw, int arenaT,
+                int64_t toff, int n) {
+  TrtriProb p{arenaL, loff, ldl, arenaW, woff, toff, ldw, n};
+  p.arenaT = arenaT;
+  plan_trtri_batch(B, P, std::vector<TrtriProb>{p});
+}
 void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0) {
   std::vector<FactorProb> v{{arena, off, ld, n, n, col0}};
   plan_partial_factor_batch(B, P, v, 0);

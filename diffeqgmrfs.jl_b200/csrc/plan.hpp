@@ -37,6 +37,7 @@ class PlanBuilder {
     cur.grid += ctas;
   }
   void set_smem(int bytes) { cur.smem = bytes; }
+  void set_cfg(int cfg) { cur.cfg = cfg; }
   void add_bytes(double b) { cur.bytes += b; }
   void end() {
     cur.flops = P.flops - flops0;
@@ -91,6 +92,10 @@ void build_selinv_plan(const Symbolic& S, Plan& P);
 // Dense building blocks shared with the block-tridiagonal path (offsets relative to a moving base).
 //  blocked in-place Cholesky of the n x n matrix at `off` (ld), reporting failures at column col0 + j
 void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0);
+//  W (n x n at woff, ldw; its strict upper triangle must already be zero) <- L^{-1} by recursive doubling; T is an
+//  n x n scratch (ldw) in arena arenaT
+void plan_trtri(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaW, int64_t woff, int ldw, int arenaT,
+                int64_t toff, int n);
 //  X (M x n at xoff, ldx) <- X L^{-T}, L n x n lower at loff (ldl); left-looking blocked
 void plan_trsm_rlt(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
                    int n, int ldx);

@@ -20,6 +20,8 @@ enum : int32_t {
   TF_KLOW = 1 << 10,  // GEMM with transposed A (K x M) that is lower triangular (zero for k < m): skip k < m0
   TF_B_DINV = 1 << 11,    // operand b lives in the inverse-block scratch (Arenas::dinv), 64x64 slots with ld 64
   TF_NOFACTOR = 1 << 12,  // POTRF task: the block already holds L, only its inverse is produced
+  TF_BLOW = 1 << 13,  // GEMM, B stored K x N (TB) and lower triangular (zero for k < n): skip k < n0
+  TF_BUPP = 1 << 14,  // GEMM, B stored N x K (!TB) and lower triangular (zero for k > n): skip k >= n0 + BN
 };
 
 struct alignas(16) Task {
@@ -49,6 +51,8 @@ enum LaunchKind : int32_t {
   LK_FRONT_FACTOR_SMALL = 13,  // fused shared-memory factorisation of one small front per CTA (aux0 = supernode)
   LK_FRONT_SELINV_SMALL = 14,  // fused shared-memory selected inversion of one small front per CTA
   LK_GEMM_TT = 15,             // C = beta C + alpha A' B'       A: KxM, B: NxK
+  LK_SKINNY_NT = 16,           // M <= 8 rows: C = beta C + alpha A B', bandwidth-bound streaming of B (skinny_kernels.cuh)
+  LK_SKINNY_NN = 17,           // M <= 8 rows: C = beta C + alpha A B
 };
 
 struct Launch {
@@ -87,6 +91,18 @@ constexpr int SMALL_FRONT_NCLASS = 5;
 constexpr int SMALL_FRONT_CLASSES[SMALL_FRONT_NCLASS] = {48, 72, 104, 128, SMALL_FRONT_MAX};
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// skinny products (skinny_kernels.cuh): rows of B per CTA, K slices of the nt variant, workspace doubles
+constexpr int SKINNY_ROWS = 256, SKINNY_MAX_ROWS = 8, SKINNY_WS_HEAD = 512;
+inline int skinny_nr(int m) { return m <= 1 ? 1 : m <= 2 ? 2 : m <= 4 ? 4 : 8; }
+inline int skinny_slices(int N, int K) {
+  const int chunks = cdiv(N, SKINNY_ROWS);
+  int ks = 592 / chunks;  // about four CTAs per SM in flight
+  ks = ks < K / 64 ? ks : K / 64;
+  return ks < 1 ? 1 : ks > 32 ? 32 : ks;
+}
+inline int64_t skinny_workspace(int m, int N, int K) {
+  return SKINNY_WS_HEAD + (int64_t)skinny_slices(N, K) * skinny_nr(m) * N;
+}
 // dynamic shared memory of the fused small-front kernels for a front of order d: the front (roundup(d,8) columns,
 // leading dimension roundup(d,8)+4) plus two 8-column panel buffers
 inline int small_front_smem(int d) {

@@ -9,7 +9,7 @@ def rel(a, b):
     return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
 
 
-@pytest.mark.parametrize("b,N", [(1, 1), (1, 5), (7, 3), (64, 4), (65, 3), (130, 5), (257, 3), (400, 2)])
+@pytest.mark.parametrize("b,N", [(1, 1), (1, 5), (7, 3), (64, 4), (65, 3), (130, 5), (257, 3), (400, 2), (600, 3)])
 def test_btd_dense_blocks(pkg, orc, ctx, W, b, N):
     D, Bs = W.random_btd(b, N, seed=b * 31 + N)
     A = W.btd_to_sparse(D, Bs)
@@ -22,7 +22,9 @@ def test_btd_dense_blocks(pkg, orc, ctx, W, b, N):
         if i > 0:
             assert rel(Cs[i - 1], Fo.Cs[i - 1]) < 1e-12
     rng = np.random.default_rng(b + N)
-    for nrhs in (1, 3):
+    # 1..8 right-hand sides take the bandwidth-bound streaming kernels (one template instance per 1/2/4/8), more
+    # than 8 the tile engine
+    for nrhs in (1, 2, 3, 5, 8, 11):
         rhs = rng.standard_normal((b * N, nrhs))
         want_f = np.stack([orc.btd_forward_solve(Fo, rhs[:, k]) for k in range(nrhs)], 1)
         want_b = np.stack([orc.btd_backward_solve(Fo, rhs[:, k]) for k in range(nrhs)], 1)
