@@ -116,6 +116,13 @@ class SparseMatrix:
     def values_dev(self) -> int:
         return int(B.lib().gmrfb_spm_values_dev(self.h) or 0)
 
+    def values_host(self):
+        """The nonzero values only (the pattern of a fixed-pattern result is fetched once by its owner)."""
+        _, _, z = self.dims()
+        nz = np.empty(z, np.float64)
+        B.check(B.lib().gmrfb_spm_get(self.h, 0, None, None, nz.ctypes.data_as(B._F64P)), self.ctx.h)
+        return nz
+
     def matvec(self, x, trans=False, alpha=1.0, beta=0.0, y=None):
         m, n, _ = self.dims()
         x, xp = B.f64(x)
@@ -387,6 +394,20 @@ class CholeskySolverBlueprint:
         self.perm = perm
         self.coords = coords
         self.ctx = ctx
+        self._sym_cache = None  # (indptr, indices, Symbolic) of the last pattern analysed through this blueprint
+
+    def symbolic_for(self, Q) -> "Symbolic":
+        """Symbolic analysis for Q's pattern.  A blueprint that is reused over a dataset loop (the reference passes
+        ``perm=p`` for exactly that, scripts/darcy/solve_darcy_gmrf-fem.jl:169-174) keeps the analysis of the last
+        pattern, so further matrices with the same pattern only pay the numeric factorisation."""
+        c = self._sym_cache
+        if c is not None and ((c[0] is Q.indptr and c[1] is Q.indices) or (
+                c[0].size == Q.indptr.size and c[1].size == Q.indices.size
+                and np.array_equal(c[0], Q.indptr) and np.array_equal(c[1], Q.indices))):
+            return c[2]
+        sym = Symbolic(Q, perm=self.perm, coords=self.coords, ctx=self.ctx)
+        self._sym_cache = (Q.indptr, Q.indices, sym)  # pattern arrays are treated as immutable
+        return sym
 
 
 class GNCholeskySolverBlueprint(CholeskySolverBlueprint):
@@ -409,12 +430,15 @@ class _Ref:
 class CholeskySolver:
     """What ``x.solver_ref[]`` points to: holds ``precision_chol`` (with ``.p``, ``.L``, ``nnz``)."""
 
-    def __init__(self, gmrf, blueprint: CholeskySolverBlueprint, symbolic: Symbolic | None = None):
+    def __init__(self, gmrf, blueprint: CholeskySolverBlueprint, symbolic: Symbolic | None = None, values_dev: int = 0):
         self.gmrf = gmrf
         self.blueprint = blueprint
         Q = gmrf.precision
-        sym = symbolic or Symbolic(Q, perm=blueprint.perm, coords=blueprint.coords, ctx=blueprint.ctx)
-        self.precision_chol = CholeskyFactor(sym).factorize(Q.data)
+        sym = symbolic or blueprint.symbolic_for(Q)
+        if values_dev:  # the values already sit in device memory (fixed-pattern assembly): no host round trip
+            self.precision_chol = CholeskyFactor(sym).factorize_dev(values_dev)
+        else:
+            self.precision_chol = CholeskyFactor(sym).factorize(Q.data)
         self._mean = None
         self._var = None
 
@@ -447,13 +471,14 @@ class GMRF:
     """``GMRF(mean, precision, solver_blueprint)`` (_research/elliptic_chen24.jl:166).  ``information`` carries
     the lazy right-hand side of a conditioned GMRF: mean = prior_mean + Q^{-1} information."""
 
-    def __init__(self, mean, precision, solver_blueprint=None, information=None, _symbolic=None):
+    def __init__(self, mean, precision, solver_blueprint=None, information=None, _symbolic=None, _values_dev=0):
         self.precision = _csc(precision)
         self.n = self.precision.shape[0]
         self.prior_mean = np.asarray(mean, dtype=np.float64)
         self.information = information
         bp = solver_blueprint or CholeskySolverBlueprint()
-        self.solver_ref = _Ref(CholeskySolver(self, bp, _symbolic))
+        self.solver_ref = _Ref(CholeskySolver(self, bp, _symbolic, _values_dev))
+        self._cond_ws = None
 
     def __len__(self):
         return self.n
@@ -488,22 +513,52 @@ def sqmahal(x: GMRF, v):
     return SparseMatrix(x.precision, ctx=ch.ctx).sqmahal(v, mu=mean(x))
 
 
+class _ConditioningWorkspace:
+    """Device-resident state of ``condition_on_observations`` for one prior and one observation pattern: Q and A on
+    the device, the fixed-pattern plan for Q + A' Q_eps A and the pattern of its result.  A dataset loop (same mesh,
+    new coefficients: scripts/darcy/solve_darcy_gmrf-fem.jl:210) then only uploads A's values per problem."""
+
+    def __init__(self, x, A, ctx):
+        self.A_indptr, self.A_indices, self.shape = A.indptr, A.indices, A.shape
+        self.Qd = SparseMatrix(x.precision, ctx=ctx)
+        self.Ad = SparseMatrix(A, ctx=ctx)
+        self.plan = PosteriorPrecision(self.Qd, self.Ad)
+        self.pattern = None  # (indptr, indices) of the posterior precision, fetched with the first result
+
+    def matches(self, A):
+        return A.shape == self.shape and A.indptr.size == self.A_indptr.size and A.indices.size == self.A_indices.size \
+            and np.array_equal(A.indptr, self.A_indptr) and np.array_equal(A.indices, self.A_indices)
+
+
 def condition_on_observations(x: GMRF, A, Q_eps, y, solver_blueprint=None) -> GMRF:
     """``condition_on_observations(x, A, Q_eps, y; solver_blueprint)``
     (scripts/darcy/solve_darcy_gmrf-fem.jl:165-167,188-189): posterior precision Q + A'Q_eps A (device
-    SpGEMM on a fixed pattern), posterior mean mu + Qpost^{-1} A'Q_eps (y - A mu)."""
+    SpGEMM on a fixed pattern), posterior mean mu + Qpost^{-1} A'Q_eps (y - A mu).  The values of the posterior
+    precision go from the assembly kernel straight into the numeric factorisation; the host copy that
+    ``precision_map`` returns is downloaded once per call."""
     bp = solver_blueprint or x.solver_ref.value.blueprint
     ctx = x.solver_ref.value.precision_chol.ctx
     A = _csc(A)
     mu = mean(x)
-    Qd = SparseMatrix(x.precision, ctx=ctx)
-    Ad = SparseMatrix(A, ctx=ctx)
-    plan = PosteriorPrecision(Qd, Ad)
-    Qpost = plan.compute(Q_eps).to_scipy()
+    ws = x._cond_ws
+    if ws is None or not ws.matches(A):
+        ws = x._cond_ws = _ConditioningWorkspace(x, A, ctx)
+    else:
+        ws.Ad.set_values(A.data)
+    Apost = ws.plan.compute(Q_eps)
+    if ws.pattern is None:
+        P = Apost.to_scipy()
+        ws.pattern = (P.indptr, P.indices)
+        vals = P.data
+    else:
+        vals = Apost.values_host()
+    Qpost = sp.csc_matrix((vals, ws.pattern[1], ws.pattern[0]), shape=x.precision.shape)
+    Qpost.has_sorted_indices = True
+    Qpost.has_canonical_format = True
     w = np.broadcast_to(np.asarray(Q_eps, dtype=np.float64), (A.shape[0],))
-    resid = np.asarray(y, dtype=np.float64) - Ad.matvec(mu)
-    info = Ad.matvec(w * resid, trans=True)
-    return GMRF(mu, Qpost, bp, information=info)
+    resid = np.asarray(y, dtype=np.float64) - ws.Ad.matvec(mu)
+    info = ws.Ad.matvec(w * resid, trans=True)
+    return GMRF(mu, Qpost, bp, information=info, _values_dev=Apost.values_dev())
 
 
 # ------------------------------------------------------------------------------------------ Gauss-Newton --

@@ -200,3 +200,114 @@ def burgers_like_problem(nx: int = 64, seed: int = 0, dt: float = 0.01, nu: floa
     mu = np.concatenate([u0, u0])
     y = np.zeros(nx)
     return dict(Q=Q, f_and_J=f_and_J, f=f, y=y, mu=mu, n=2 * nx)
+
+
+# ----------------------------------------------------------------------------- configs 1-3 at full size ----
+def elliptic_problem(nx: int = 201, corr_range: float = 0.1, seed: int = 0):
+    """Config 1 of BASELINE.json (_research/elliptic_chen24.jl:118-171): nonlinear elliptic PDE  -lap u + u^3 = g  on
+    the unit square, GMRF prior (Matern, range 0.1, smoothness 1), Dirichlet data as point observations of the
+    boundary nodes, Gauss-Newton on the collocation residual.  P1 stand-in for the P2 Ferrite assembly on the same
+    grid (nx = 201 => n = 40 401 as N_el_xy = 100 with P2).  Manufactured solution as in :60-67.
+    Returns dict(Q, nodes, A_bnd, y_bnd, f_and_J, y, u_true, n)."""
+    nodes, tris = structured_mesh(nx, nx, seed=seed)
+    m, K = p1_mass_stiffness(nodes, tris)
+    Q = matern_precision(nodes, tris, corr_range)
+    x, y = nodes[:, 0], nodes[:, 1]
+    u_true = np.sin(np.pi * x) * np.sin(np.pi * y) + 2.0 * np.sin(4 * np.pi * x) * np.sin(4 * np.pi * y)
+    g = K @ u_true + m * u_true**3  # discrete right-hand side of the manufactured solution
+    bnd = np.flatnonzero((x == 0) | (x == 1) | (y == 0) | (y == 1))
+    A_bnd = sp.csc_matrix((np.ones(bnd.size), (np.arange(bnd.size), bnd)), shape=(bnd.size, nodes.shape[0]))
+    Kc = K.tocsc()
+    Kc.sort_indices()
+    diag_pos = np.array([Kc.indptr[j] + np.searchsorted(Kc.indices[Kc.indptr[j]:Kc.indptr[j + 1]], j)
+                         for j in range(Kc.shape[0])])
+
+    def f_and_J(u):
+        J = Kc.copy()  # fixed pattern: the cubic term only touches the diagonal (lumped mass)
+        J.data[diag_pos] += 3.0 * m * u**2
+        return Kc @ u + m * u**3, J
+
+    return dict(Q=Q, nodes=nodes, A_bnd=A_bnd, y_bnd=u_true[bnd], f_and_J=f_and_J, y=g, u_true=u_true,
+                n=nodes.shape[0])
+
+
+def burgers_spacetime(nx: int = 4095, nt: int = 201, dt: float = 0.01, nu: float = 0.01, tau: float = 1.0,
+                      q_ic: float = 1e8, seed: int = 0):
+    """Config 2 of BASELINE.json (scripts/solve_burger.jl): 1-D periodic viscous Burgers in space-time.  Prior: implicit
+    Euler diffusion state-space model (block-tridiagonal precision, block size b = nx, N = nt blocks; ingredients of
+    src/spdes/shallow_water.jl:198-228) conditioned on the initial condition at step 1 with Q_eps = 1e8 (:98).
+    Observation model of the Gauss-Newton loop: collocation residual of every step with the tangent of :127-134,
+        f(w)_t = M (u_{t+1} - u_t) + dt M (u_{t+1} .* D u_{t+1}) + dt nu K u_{t+1},      y = 0.
+    Unknown w is time-major (block t = rows [t nx, (t+1) nx)).  Returns dict(Q, mu, f_and_J, y, coords, b, N, u0)."""
+    rng = np.random.default_rng(seed)
+    h = 1.0 / nx
+    I = sp.identity(nx, format="csc")
+    S = sp.csc_matrix((np.ones(nx), (np.arange(nx), (np.arange(nx) + 1) % nx)), shape=(nx, nx))
+    D1 = ((S - S.T) / (2 * h)).tocsc()
+    Kx = ((2 * I - S - S.T) / h).tocsc()
+    M = (h * I).tocsc()
+    G = (M + dt * nu * Kx).tocsc()
+    kappa = 8.0
+    K0 = (kappa**2 * M + Kx).tocsc()
+    Q0 = (K0.T @ K0 / h).tocsc()
+    binv = 1.0 / (dt * tau**2) / h
+    GtG, MM, off = binv * (G.T @ G), binv * (M.T @ M), -binv * (G.T @ M)
+    Tdiag = sp.identity(nt, format="csc")
+    first = sp.csc_matrix(([1.0], ([0], [0])), shape=(nt, nt))
+    last = sp.csc_matrix(([1.0], ([nt - 1], [nt - 1])), shape=(nt, nt))
+    sub = sp.csc_matrix((np.ones(nt - 1), (np.arange(1, nt), np.arange(nt - 1))), shape=(nt, nt))
+    Q = (sp.kron(first, Q0 + q_ic * I) + sp.kron(Tdiag - first, GtG) + sp.kron(Tdiag - last, MM) + sp.kron(sub, off)
+         + sp.kron(sub.T, off.T)).tocsc()
+    Q.sort_indices()
+    xs = np.arange(nx) * h
+    u0 = np.zeros(nx)
+    for k in range(1, 5):  # smooth random Fourier series
+        u0 += rng.standard_normal() / k * np.sin(2 * np.pi * k * xs) + rng.standard_normal() / k * np.cos(2 * np.pi * k * xs)
+    mu = np.tile(u0, nt)
+    # residual operator pieces: rows = steps 1..nt-1
+    Enext = sp.csc_matrix((np.ones(nt - 1), (np.arange(nt - 1), np.arange(1, nt))), shape=(nt - 1, nt))
+    Eprev = sp.csc_matrix((np.ones(nt - 1), (np.arange(nt - 1), np.arange(nt - 1))), shape=(nt - 1, nt))
+    A_next = sp.kron(Enext, I).tocsc()
+    L_static = (sp.kron(Enext, G) - sp.kron(Eprev, M)).tocsc()
+    Dn = sp.kron(Enext, D1).tocsc()
+    P = (abs(L_static) + abs(A_next) + abs(Dn)).tocsc()
+    P.data[:] = 0.0
+
+    def f_and_J(w):
+        un, dun = A_next @ w, Dn @ w
+        fx = L_static @ w + dt * h * un * dun
+        J = (L_static + dt * h * (sp.diags(dun) @ A_next + sp.diags(un) @ Dn) + P).tocsc()
+        J.sort_indices()
+        return fx, J
+
+    tt, xx = np.meshgrid(np.arange(nt) / max(nt - 1, 1), xs, indexing="ij")
+    coords = np.stack([xx.ravel(), tt.ravel()], axis=1)
+    return dict(Q=Q, mu=mu, f_and_J=f_and_J, y=np.zeros(nx * (nt - 1)), coords=coords, b=nx, N=nt, u0=u0)
+
+
+def darcy_problem(nx: int = 601, seed: int = 0, q_eps: float = 1e8):
+    """Config 3 of BASELINE.json (scripts/darcy/solve_darcy_gmrf-fem.jl): Darcy flow  -div(a grad u) = 1  with a
+    piecewise-constant two-level coefficient (3 / 12) looked up by nearest index on a 241 x 241 grid
+    (src/datasets/darcy.jl:30-34, src/problems/darcy.jl:39) — here thresholded from a seeded smooth random field since
+    the dataset is not shipped.  Prior: Matern with range 1/sqrt(300) (:97-98); observation operator A = stiffness of
+    the coefficient, y = load vector, Q_eps = 1e8.  Returns dict(Q, A, y, q_eps, nodes, coeff_grid)."""
+    rng = np.random.default_rng(seed)
+    nodes, tris = structured_mesh(nx, nx, seed=0)  # one mesh (one pattern) for every problem of the dataset loop
+    g = 241
+    kx = np.fft.fftfreq(g)[:, None]
+    ky = np.fft.fftfreq(g)[None, :]
+    spec = np.exp(-((kx**2 + ky**2) * (g / 6.0) ** 2))
+    field = np.real(np.fft.ifft2(np.fft.fft2(rng.standard_normal((g, g))) * spec))
+    coeff_grid = np.where(field > 0, 12.0, 3.0)
+    cent = nodes[tris].mean(axis=1)
+    ij = np.clip(np.rint(cent * (g - 1)).astype(int), 0, g - 1)
+    coeff = coeff_grid[ij[:, 1], ij[:, 0]]
+    m, A = p1_mass_stiffness(nodes, tris, coeff=coeff)
+    # homogeneous Dirichlet rows on the boundary (the reference applies them through Ferrite's constraint handler)
+    x, yy = nodes[:, 0], nodes[:, 1]
+    bnd = ((x == 0) | (x == 1) | (yy == 0) | (yy == 1)).astype(np.float64)
+    A = (sp.diags(1.0 - bnd) @ A + sp.diags(bnd)).tocsc()
+    A.sort_indices()
+    y = m * (1.0 - bnd)
+    Q = matern_precision(nodes, tris, 1.0 / np.sqrt(300.0))
+    return dict(Q=Q, A=A, y=y, q_eps=q_eps, nodes=nodes, coeff_grid=coeff_grid)
