@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "gemm_engine.cuh"
@@ -821,10 +823,25 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_front_selinv_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_front_factor_small<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_front_selinv_small<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_front_factor_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_front_selinv_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   return e;
+}
+
+// threads per CTA of the fused small-front kernels for a launch with `smem` bytes of dynamic shared memory
+// (GMRFB_SF_THREADS="t72,t104,tbig" overrides the defaults; tuning aid)
+static int small_front_threads(int smem) {
+  static int cfg[3] = {0, 0, 0};
+  if (cfg[0] == 0) {
+    cfg[0] = 128, cfg[1] = 256, cfg[2] = 512;
+    if (const char* e = std::getenv("GMRFB_SF_THREADS")) std::sscanf(e, "%d,%d,%d", &cfg[0], &cfg[1], &cfg[2]);
+  }
+  return smem <= small_front_smem(72) ? cfg[0] : smem <= small_front_smem(104) ? cfg[1] : cfg[2];
 }
 
 cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, const LaunchAux& aux,
@@ -886,19 +903,28 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
     case LK_DIAG_OUT:
       k_diag_out<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_out);
       break;
-    case LK_FRONT_FACTOR_SMALL:
-      // fronts of order <= 104 need at most 104 row threads: 4-warp CTAs, more of them per SM
-      if (L.smem <= small_front_smem(104))
+    case LK_FRONT_FACTOR_SMALL: {
+      // CTA width by size class: the kernels are latency bound (global loads of the children's update matrices), so
+      // the classes that fit only one or two CTAs per SM get more threads = more loads in flight per SM
+      const int nt = small_front_threads(L.smem);
+      if (nt == 128)
         k_front_factor_small<128><<<L.grid, 128, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_child_idx, aux.d_relmap, aux.d_info);
-      else
+      else if (nt == 256)
         k_front_factor_small<256><<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_child_idx, aux.d_relmap, aux.d_info);
-      break;
-    case LK_FRONT_SELINV_SMALL:
-      if (L.smem <= small_front_smem(104))
-        k_front_selinv_small<128><<<L.grid, 128, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
       else
-        k_front_selinv_small<256><<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
+        k_front_factor_small<512><<<L.grid, 512, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_child_idx, aux.d_relmap, aux.d_info);
       break;
+    }
+    case LK_FRONT_SELINV_SMALL: {
+      const int nt = small_front_threads(L.smem);
+      if (nt == 128)
+        k_front_selinv_small<128><<<L.grid, 128, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
+      else if (nt == 256)
+        k_front_selinv_small<256><<<L.grid, 256, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
+      else
+        k_front_selinv_small<512><<<L.grid, 512, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
+      break;
+    }
     default:
       return cudaErrorInvalidValue;
   }
