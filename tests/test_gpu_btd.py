@@ -113,3 +113,20 @@ def test_time_sharded_emulated_ranks(pkg, orc, ctx, W, b, N, P):
         tot += loc.value
         red = rd.value
     assert abs(tot + red - orc.btd_logdet(Fo)) < 1e-9 * max(1.0, abs(orc.btd_logdet(Fo)))
+
+
+def test_btd_solve_ill_conditioned_residual(pkg, orc, ctx, W):
+    """The solves apply W_i = L_i^{-1} with one refinement step against L_i: on an ill-conditioned chain (Burgers
+    posterior, Q_eps = 1e8) the residual must stay at the level of the substitution-based oracle."""
+    P = W.burgers_spacetime(96, 7)
+    fx, J = P["f_and_J"](P["mu"])
+    A = (P["Q"] + 1e8 * (J.T @ J)).tocsc()
+    A.sort_indices()
+    F = pkg.tridiagonal_cholesky(A, 7, ctx=ctx)
+    Fo = orc.tridiagonal_cholesky(A, 7)
+    rhs = np.random.default_rng(5).standard_normal((A.shape[0], 3))
+    x = pkg.ldiv(F, rhs)
+    xo = np.stack([orc.btd_ldiv(Fo, rhs[:, k]) for k in range(3)], 1)
+    res = np.linalg.norm(A @ x - rhs) / np.linalg.norm(rhs)
+    res_o = np.linalg.norm(A @ xo - rhs) / np.linalg.norm(rhs)
+    assert res < 10 * res_o + 1e-13

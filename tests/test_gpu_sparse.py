@@ -247,3 +247,30 @@ def test_gauss_newton(pkg, orc, ctx, W):
         steps += 1
     assert steps == gno.n_steps and steps >= 2
     assert rel(xg, x) < 1e-9
+
+
+def test_dataset_loop_reuses_workspace(pkg, orc, ctx, W):
+    """The Darcy dataset loop (scripts/darcy/solve_darcy_gmrf-fem.jl:210): one prior, one mesh, a new coefficient
+    field per problem.  Later calls of condition_on_observations reuse the device matrices, the fixed-pattern plan and
+    the symbolic analysis and only upload A's values; every posterior must still match the oracle and earlier
+    posteriors must stay valid (each owns its factor)."""
+    P0 = W.darcy_problem(17, seed=0, q_eps=1e4)
+    n = P0["Q"].shape[0]
+    x = pkg.GMRF(np.zeros(n), P0["Q"], pkg.CholeskySolverBlueprint(coords=P0["nodes"], ctx=ctx))
+    first = pkg.condition_on_observations(x, P0["A"], P0["q_eps"], P0["y"])
+    p = first.solver_ref[()].precision_chol.p
+    bp = pkg.CholeskySolverBlueprint(perm=p, ctx=ctx)
+    posts = []
+    for k in range(3):
+        Pk = W.darcy_problem(17, seed=k, q_eps=1e4)
+        posts.append((Pk, pkg.condition_on_observations(x, Pk["A"], Pk["q_eps"], Pk["y"], solver_blueprint=bp)))
+    assert x._cond_ws is not None and bp._sym_cache is not None
+    syms = {id(xc.solver_ref[()].precision_chol.sym) for _, xc in posts}
+    assert len(syms) == 1  # one symbolic analysis for the whole loop
+    for Pk, xc in posts:  # checked after the loop: earlier posteriors were not overwritten by later ones
+        Qp = orc.posterior_precision(Pk["Q"], Pk["A"], Pk["q_eps"])
+        ref = orc.SparseCholesky(Qp, p)
+        mref = orc.posterior_mean(ref, Pk["Q"], Pk["A"], Pk["q_eps"], Pk["y"], np.zeros(n))
+        assert abs(pkg.precision_map(xc) - Qp).max() < 1e-12 * abs(Qp).max()
+        assert rel(pkg.mean(xc), mref) < 1e-9
+        assert rel(pkg.var(xc), ref.selinv_diag()) < TOL_VAR

@@ -1,6 +1,7 @@
 #!/bin/bash
+# Throughput against the number of independent posterior problems in flight per GPU.
 OUT=gpurun_out; mkdir -p $OUT
-for B in 1 2 3 4; do
+for B in ${@:-1 2 3 4 5 6}; do
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline --inflight $B > $OUT/inflight_$B.json 2> $OUT/inflight_$B.err; echo "B=$B rc=$?"
   python - <<PY
 import json
