@@ -209,11 +209,11 @@ extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_
   if (rc != GMRFB_OK) return rc;
   for (int64_t i = 0; i < nblocks; i++) {
     GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot, f->ld * sizeof(double), D + i * b * b, b * sizeof(double),
-                                    b * sizeof(double), b, cudaMemcpyHostToDevice, ctx->stream));
+                                    b * sizeof(double), b, cudaMemcpyDefault, ctx->stream));
     if (i > 0)
       GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot + (int64_t)f->ld * b, f->ld * sizeof(double),
                                       Bsub + (i - 1) * b * b, b * sizeof(double), b * sizeof(double), b,
-                                      cudaMemcpyHostToDevice, ctx->stream));
+                                      cudaMemcpyDefault, ctx->stream));
   }
   rc = btd_run_factor(f.get());
   *out = f.release();  // the handle is returned even when not SPD so that get_info can report the block
@@ -756,7 +756,7 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
     GMRFB_CU(ctx, cudaMemsetAsync(work.p + 2 * bs, 0, (size_t)bs * sizeof(double), ctx->stream));
     // E_l = B_local[:,:,0] (rows: first interior block, cols: previous separator)
     GMRFB_CU(ctx, cudaMemcpy2DAsync(work.p + bs, ld * sizeof(double), B_local, b * sizeof(double), b * sizeof(double), b,
-                                    cudaMemcpyHostToDevice, ctx->stream));
+                                    cudaMemcpyDefault, ctx->stream));
     // arenas: 0 = factor slot i, 1 = spike block i (block i-1 at -bs), 2 = work, 3 = W_i = L_i^{-1}
     auto gemm = [&](PlanBuilder& B, int kind, int aa, int64_t a, int ab, int64_t bo, int ac, int64_t c, bool tri, double alpha,
                     double beta, int32_t extra) {
@@ -803,11 +803,11 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
     GMRFB_CU(ctx, h->V.alloc((size_t)bs));
     // V = E_r L_ni^{-T},  E_r = B_local[:,:,nloc-1] (rows: separator, cols: last interior block)
     GMRFB_CU(ctx, cudaMemcpy2DAsync(tmp.p, ld * sizeof(double), B_local + (nloc - 1) * b * b, b * sizeof(double),
-                                    b * sizeof(double), b, cudaMemcpyHostToDevice, ctx->stream));
+                                    b * sizeof(double), b, cudaMemcpyDefault, ctx->stream));
     rc = gemm_once(ctx, LK_GEMM_NT, tmp.p, ld, F->winv.p + (h->ni - 1) * bs, ld, h->V.p, ld, ib, ib, ib, false, 1.0, 0.0);
     if (rc != GMRFB_OK) return rc;
     // iface0 = D_sep - V V'
-    GMRFB_CU(ctx, cudaMemcpyAsync(h->iface.p, D_local + (nloc - 1) * b * b, b * b * sizeof(double), cudaMemcpyHostToDevice,
+    GMRFB_CU(ctx, cudaMemcpyAsync(h->iface.p, D_local + (nloc - 1) * b * b, b * b * sizeof(double), cudaMemcpyDefault,
                                   ctx->stream));
     rc = gemm_once(ctx, LK_GEMM_NT, h->V.p, ld, h->V.p, ld, h->iface.p, ib, ib, ib, ib, true, -1.0, 1.0);
     if (rc != GMRFB_OK) return rc;

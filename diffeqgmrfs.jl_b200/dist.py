@@ -63,12 +63,20 @@ class TimeShardedCholesky:
                 self.reduce(self._allgather(self.iface()))
             return
         self.ctx = ctx or default_context()
-        D_local = np.asfortranarray(D_local, dtype=np.float64)
-        B_local = np.asfortranarray(B_local, dtype=np.float64)
-        self.b, _, self.nloc = D_local.shape
+        if torch.is_tensor(D_local):
+            # device-resident blocks: CUDA float64 tensors of shape (nloc, b, b), C-contiguous, element [k, j, i] =
+            # entry (i, j) of block k (each block column-major) - the memory layout of the NumPy form below
+            assert D_local.is_cuda and B_local.is_cuda and D_local.is_contiguous() and B_local.is_contiguous()
+            assert D_local.dtype == torch.float64 and B_local.dtype == torch.float64
+            self.nloc, self.b, _ = D_local.shape
+            dp, bp = C.cast(C.c_void_p(D_local.data_ptr()), B._F64P), C.cast(C.c_void_p(B_local.data_ptr()), B._F64P)
+        else:
+            D_local = np.asfortranarray(D_local, dtype=np.float64)
+            B_local = np.asfortranarray(B_local, dtype=np.float64)
+            self.b, _, self.nloc = D_local.shape
+            dp, bp = D_local.ctypes.data_as(B._F64P), B_local.ctypes.data_as(B._F64P)
         h = C.c_void_p()
-        st = B.lib().gmrfb_btd_dist_create(self.ctx.h, rank, world, self.b, self.nloc, D_local.ctypes.data_as(B._F64P),
-                                           B_local.ctypes.data_as(B._F64P), C.byref(h))
+        st = B.lib().gmrfb_btd_dist_create(self.ctx.h, rank, world, self.b, self.nloc, dp, bp, C.byref(h))
         B.check(st, self.ctx.h)
         self.h = h
         self._fin = weakref.finalize(self, B.lib().gmrfb_btd_dist_destroy, h)

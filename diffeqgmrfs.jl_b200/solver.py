@@ -703,16 +703,24 @@ def tridiagonal_cholesky(A, N_blocks, ctx=None) -> TridiagonalCholeskyFactor:
 
 
 def tridiagonal_cholesky_dense(D, Bsub, ctx=None) -> TridiagonalCholeskyFactor:
-    """Dense-block entry: D[b,b,N] diagonal blocks, Bsub[b,b,N-1] sub-diagonal blocks (Fortran order)."""
+    """Dense-block entry: D[b,b,N] diagonal blocks, Bsub[b,b,N-1] sub-diagonal blocks (Fortran order), or the same
+    memory as CUDA float64 tensors of shape (N, b, b) / (N-1, b, b) (element [k, j, i] = entry (i, j) of block k)."""
     ctx = ctx or default_context()
-    D = np.asfortranarray(D, dtype=np.float64)
-    b, _, N = D.shape
-    Bp = None
-    if N > 1:
-        Bsub = np.asfortranarray(Bsub, dtype=np.float64)
-        Bp = Bsub.ctypes.data_as(B._F64P)
+    if hasattr(D, "data_ptr"):  # device-resident blocks (torch CUDA tensors)
+        assert D.is_cuda and D.is_contiguous() and str(D.dtype) == "torch.float64"
+        N, b, _ = D.shape
+        Dp = C.cast(C.c_void_p(D.data_ptr()), B._F64P)
+        Bp = C.cast(C.c_void_p(Bsub.data_ptr()), B._F64P) if N > 1 else None
+    else:
+        D = np.asfortranarray(D, dtype=np.float64)
+        b, _, N = D.shape
+        Dp = D.ctypes.data_as(B._F64P)
+        Bp = None
+        if N > 1:
+            Bsub = np.asfortranarray(Bsub, dtype=np.float64)
+            Bp = Bsub.ctypes.data_as(B._F64P)
     h = C.c_void_p()
-    st = B.lib().gmrfb_btd_factor_dense(ctx.h, b, N, D.ctypes.data_as(B._F64P), Bp, C.byref(h))
+    st = B.lib().gmrfb_btd_factor_dense(ctx.h, b, N, Dp, Bp, C.byref(h))
     if st != B.OK and h.value:
         B.lib().gmrfb_btd_destroy(h)
     B.check(st, ctx.h)

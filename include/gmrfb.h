@@ -277,7 +277,8 @@ gmrfb_status gmrfb_btd_get_info(gmrfb_btd* f, gmrfb_btd_info* info);
  * host performs between the phased calls below (torch.distributed / NCCL all_gather_into_tensor over NVLink in
  * the Python host; NCCL.jl or MPI from Julia — see INTEGRATION.md).
  *   D_local : b-by-b-by-nloc diagonal blocks of the slab
- *   B_local : b-by-b-by-nloc, B_local[:,:,k] = block (slab block k, the block before it); ignored for k = 0 on rank 0 */
+ *   B_local : b-by-b-by-nloc, B_local[:,:,k] = block (slab block k, the block before it); ignored for k = 0 on rank 0
+ * D_local / B_local (and D / Bsub of gmrfb_btd_factor_dense) may be host or device pointers (unified addressing). */
 typedef struct gmrfb_btd_dist gmrfb_btd_dist;
 gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int32_t nranks, int64_t b, int64_t nloc,
                                    const double* D_local, const double* B_local, gmrfb_btd_dist** out);

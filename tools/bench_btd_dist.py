@@ -41,8 +41,10 @@ Dblk = R @ R.T + 2.0 * np.eye(b)
 Bblk = 0.4 * R
 lo, hi = pkg.dist.slab_bounds(N, world)[rank]
 nloc = hi - lo
-Dl = np.asfortranarray(np.repeat(Dblk[:, :, None], nloc, axis=2))
-Bl = np.asfortranarray(np.repeat(Bblk[:, :, None], nloc, axis=2))
+# device-resident slab (element [k, j, i] = entry (i, j) of block k): the factor timing below is GPU work only
+dev = torch.device("cuda", local)
+Dl = torch.from_numpy(np.ascontiguousarray(Dblk.T)).to(dev).unsqueeze(0).repeat(nloc, 1, 1).contiguous()
+Bl = torch.from_numpy(np.ascontiguousarray(Bblk.T)).to(dev).unsqueeze(0).repeat(nloc, 1, 1).contiguous()
 rhs = np.random.default_rng(1).standard_normal((b * N, args.nrhs))
 
 
@@ -64,11 +66,35 @@ def timed(fn):
     return out, float(dt.item())
 
 
+phases = {}
 for rep in range(2):
-    ts, t_fac = timed(lambda: pkg.dist.TimeShardedCholesky(Dl, Bl, rank, world, ctx=ctx))
+    sync()
+    if rep == 1:
+        ctx.profile_begin()  # CUDA events around every launch: GPU time of the local phase without allocations
+    t0 = time.perf_counter()
+    ts = pkg.dist.TimeShardedCholesky(Dl, Bl, rank, world, ctx=ctx, auto_exchange=False)  # local factor + spikes
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    kern_ms = sum(p["ms"] for p in ctx.profile_end()) if rep == 1 else 0.0
+    send = ts.iface()
+    gathered = ts._allgather(send)                                                        # 3 b^2 doubles per rank
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    ts.reduce(gathered)                                                                   # reduced (P-1)-block chain
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    tt = torch.tensor([t3 - t0, t1 - t0, t2 - t1, t3 - t2, kern_ms * 1e-3], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_fac = float(tt[0])
+    phases = {"local_factor_and_spikes_s": float(tt[1]), "local_kernels_s": float(tt[4]), "exchange_s": float(tt[2]),
+              "reduced_system_s": float(tt[3]),
+              "note": "wall times, max over ranks; local phase = kernels + device allocations of the slab's factor, "
+                      "inverse and spike buffers (several GB per rank: concurrent cudaMalloc/cudaFree of the ranks "
+                      "serialise in the driver)"}
     x, t_sol = timed(lambda: ts.solve(rhs[lo * b:hi * b]))
     if rep == 0:
-        del ts
+        del ts, send, gathered
 # residual of this rank's rows: needs neighbours' solution rows -> gather the full solution (small: b*N*nrhs)
 xt = torch.from_numpy(np.ascontiguousarray(x)).to(f"cuda:{local}")
 if world > 1:
@@ -92,8 +118,8 @@ if world > 1:
 logdet = ts.logdet()
 seq = None
 if args.seq and rank == 0:
-    Dall = np.asfortranarray(np.repeat(Dblk[:, :, None], N, axis=2))
-    Ball = np.asfortranarray(np.repeat(Bblk[:, :, None], N - 1, axis=2))
+    Dall = torch.from_numpy(np.ascontiguousarray(Dblk.T)).to(dev).unsqueeze(0).repeat(N, 1, 1).contiguous()
+    Ball = torch.from_numpy(np.ascontiguousarray(Bblk.T)).to(dev).unsqueeze(0).repeat(max(N - 1, 1), 1, 1).contiguous()
     for rep in range(2):
         torch.cuda.synchronize()
         t = time.perf_counter()
@@ -106,7 +132,7 @@ if args.seq and rank == 0:
 if rank == 0:
     flops_seq = (N - 1) * 7.0 / 3.0 * b**3 + b**3 / 3.0
     print(json.dumps({"b": b, "N": N, "world": world, "nrhs": args.nrhs, "factor_s": t_fac, "solve_s": t_sol,
-                      "factor_incl_h2d": True, "seq_equiv_tflops": flops_seq / t_fac * 1e-12,
+                      "factor_incl_h2d": False, "factor_phases": phases, "seq_equiv_tflops": flops_seq / t_fac * 1e-12,
                       "max_rel_residual": float(rt.item()), "logdet": logdet, "sequential": seq}), flush=True)
 if world > 1:
     dist.barrier()
