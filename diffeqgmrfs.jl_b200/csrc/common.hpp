@@ -4,6 +4,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -54,25 +56,113 @@ inline gmrfb_status fail(gmrfb_ctx* ctx, gmrfb_status code, const std::string& m
     }                                                                                                \
   } while (0)
 
+// Cache of released device allocations.  Handles of this library own several GB of fronts / factor blocks each, and a
+// loop that creates and destroys them (one posterior per dataset problem, one time-sharded factor per rank) otherwise
+// pays cudaMalloc + cudaFree of those GB every iteration - and concurrent processes on one node serialise in the
+// driver on them (profiles/r01_multi_gpu.md).  Released buffers of >= 1 MB are kept (after the same device
+// synchronisation cudaFree implies) and handed to the next allocation of (nearly) the same size on the same device.
+// GMRFB_POOL=0 disables the cache, GMRFB_POOL_MAX_GB bounds it (default 64).
+class DevPool {
+ public:
+  static DevPool& get() {
+    static DevPool P;
+    return P;
+  }
+  cudaError_t alloc(void** out, size_t bytes, size_t* cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (enabled_ && bytes >= kMin) {
+      std::lock_guard<std::mutex> lk(mu_);
+      int best = -1;
+      for (int i = 0; i < (int)free_.size(); i++)
+        if (free_[i].dev == dev && free_[i].bytes >= bytes && free_[i].bytes <= bytes + bytes / 8 &&
+            (best < 0 || free_[i].bytes < free_[best].bytes))
+          best = i;
+      if (best >= 0) {
+        *out = free_[best].p;
+        *cap = free_[best].bytes;
+        cached_ -= free_[best].bytes;
+        free_.erase(free_.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached memory back and retry once
+      cudaGetLastError();
+      trim(0);
+      e = cudaMalloc(out, bytes);
+    }
+    *cap = bytes;
+    return e;
+  }
+  void release(void* p, size_t cap) {
+    if (!enabled_ || cap < kMin) {
+      cudaFree(p);
+      return;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceSynchronize();  // what cudaFree would have done: no kernel still uses the buffer when it is reused
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      free_.push_back({p, cap, dev});
+      cached_ += cap;
+    }
+    trim(max_bytes_);
+  }
+  // free cached buffers (oldest first) until at most `keep` bytes remain cached
+  void trim(size_t keep) {
+    std::lock_guard<std::mutex> lk(mu_);
+    while (cached_ > keep && !free_.empty()) {
+      cudaFree(free_.front().p);
+      cached_ -= free_.front().bytes;
+      free_.erase(free_.begin());
+    }
+  }
+
+ private:
+  DevPool() {
+    const char* e = std::getenv("GMRFB_POOL");
+    enabled_ = !(e && e[0] == '0');
+    const char* m = std::getenv("GMRFB_POOL_MAX_GB");
+    max_bytes_ = (size_t)((m ? std::atof(m) : 64.0) * 1e9);
+  }
+  static constexpr size_t kMin = (size_t)1 << 20;
+  struct Ent {
+    void* p;
+    size_t bytes;
+    int dev;
+  };
+  std::mutex mu_;
+  std::vector<Ent> free_;
+  size_t cached_ = 0, max_bytes_ = 0;
+  bool enabled_ = true;
+};
+
 // Owning device buffer.
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  size_t cap = 0;  // bytes of the underlying allocation (>= n * sizeof(T) when it came from the cache)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) DevPool::get().release(p, cap);
     p = nullptr;
     n = 0;
+    cap = 0;
   }
   cudaError_t alloc(size_t count) {
     release();
     if (count == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-    if (e == cudaSuccess) n = count;
+    cudaError_t e = DevPool::get().alloc((void**)&p, count * sizeof(T), &cap);
+    if (e == cudaSuccess)
+      n = count;
+    else
+      p = nullptr;
     return e;
   }
   cudaError_t upload(const std::vector<T>& h, cudaStream_t st) {

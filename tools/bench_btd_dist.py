@@ -74,8 +74,12 @@ for rep in range(2):
     t0 = time.perf_counter()
     ts = pkg.dist.TimeShardedCholesky(Dl, Bl, rank, world, ctx=ctx, auto_exchange=False)  # local factor + spikes
     torch.cuda.synchronize()
-    t1 = time.perf_counter()
+    t1l = time.perf_counter()
     kern_ms = sum(p["ms"] for p in ctx.profile_end()) if rep == 1 else 0.0
+    if world > 1:
+        dist.barrier()  # so that the exchange timer below does not include waiting for the slowest rank's local phase
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
     send = ts.iface()
     gathered = ts._allgather(send)                                                        # 3 b^2 doubles per rank
     torch.cuda.synchronize()
@@ -83,7 +87,7 @@ for rep in range(2):
     ts.reduce(gathered)                                                                   # reduced (P-1)-block chain
     torch.cuda.synchronize()
     t3 = time.perf_counter()
-    tt = torch.tensor([t3 - t0, t1 - t0, t2 - t1, t3 - t2, kern_ms * 1e-3], device=f"cuda:{local}", dtype=torch.float64)
+    tt = torch.tensor([t3 - t0, t1l - t0, t2 - t1, t3 - t2, kern_ms * 1e-3], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_fac = float(tt[0])
