@@ -881,8 +881,9 @@ extern "C" gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const
   GMRFB_CU(ctx, dvar.alloc((size_t)std::max<int64_t>(n, 1)));
   for (int64_t c0 = 0; c0 < nsamp; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nsamp - c0);
+    // Z may be a host or a device pointer (unified addressing): normals drawn on the device need no PCIe round trip
     GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
-                                    n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
+                                    n * sizeof(double), nr, cudaMemcpyDefault, ctx->stream));
     GMRFB_CU(ctx, launch_perm_gather(fac->bwork.p, n, fac->ywork.p, n, sym->d_post.p, n, nr, ctx->stream));
     ctx->launches++;
     gmrfb_status rc = sweep_bwd(fac, fac->ywork.p, fac->xwork.p, nr);

@@ -351,10 +351,16 @@ class CholeskyFactor:
         B.check(B.lib().gmrfb_var_selinv_dev(self.h, C.c_void_p(dptr)), self.ctx.h)
 
     def var_rbmc(self, Q: SparseMatrix, Z):
-        Zf = np.asfortranarray(np.asarray(Z, dtype=np.float64).reshape(self.sym.n, -1))
+        """Z: n x nsamp standard normals - a NumPy array (any order) or a CUDA float64 tensor of shape (nsamp, n)
+        (one sample per contiguous row, i.e. the column-major n x nsamp matrix the C ABI expects)."""
         out = np.empty(self.sym.n)
-        B.check(B.lib().gmrfb_var_rbmc(self.h, Q.h, Zf.ctypes.data_as(B._F64P), self.sym.n, Zf.shape[1],
-                                       out.ctypes.data_as(B._F64P)), self.ctx.h)
+        if hasattr(Z, "data_ptr"):
+            assert Z.is_cuda and Z.is_contiguous() and Z.shape[1] == self.sym.n and str(Z.dtype) == "torch.float64"
+            zp, ns = C.cast(C.c_void_p(Z.data_ptr()), B._F64P), Z.shape[0]
+        else:
+            Zf = np.asfortranarray(np.asarray(Z, dtype=np.float64).reshape(self.sym.n, -1))
+            zp, ns = Zf.ctypes.data_as(B._F64P), Zf.shape[1]
+        B.check(B.lib().gmrfb_var_rbmc(self.h, Q.h, zp, self.sym.n, ns, out.ctypes.data_as(B._F64P)), self.ctx.h)
         return out
 
     def selinv_entries(self, rows, cols):
@@ -375,11 +381,20 @@ def cholesky(A, perm=None, check=True, ctx=None, coords=None) -> CholeskyFactor:
 
 # ------------------------------------------------------------------------------- blueprints and the GMRF --
 class RBMCStrategy:
-    """``RBMCStrategy(N; rng)`` (scripts/darcy/solve_darcy_gmrf-fem.jl:100)."""
+    """``RBMCStrategy(N; rng)`` (scripts/darcy/solve_darcy_gmrf-fem.jl:100).  With an ``rng`` the normals come from
+    that host generator (reproducible against the oracle); without one they are drawn on the device."""
 
     def __init__(self, n_samples: int, rng=None):
         self.n_samples = int(n_samples)
-        self.rng = rng if rng is not None else np.random.default_rng()
+        self.rng = rng
+
+    def normals(self, n, device_index):
+        """n x n_samples standard normals in the layout ``CholeskyFactor.var_rbmc`` takes."""
+        if self.rng is None:
+            import torch
+
+            return torch.randn((self.n_samples, n), dtype=torch.float64, device=torch.device("cuda", device_index))
+        return self.rng.standard_normal((self.n_samples, n)).T  # column-major n x n_samples without a copy
 
 
 class TakahashiStrategy:
@@ -455,7 +470,7 @@ class CholeskySolver:
         if self._var is None:
             vs = self.blueprint.var_strategy
             if isinstance(vs, RBMCStrategy):
-                Z = vs.rng.standard_normal((self.gmrf.n, vs.n_samples))
+                Z = vs.normals(self.gmrf.n, self.precision_chol.ctx.device)
                 Qd = SparseMatrix(self.gmrf.precision, ctx=self.precision_chol.ctx)
                 self._var = self.precision_chol.var_rbmc(Qd, Z)
             else:

@@ -197,7 +197,8 @@ gmrfb_status gmrfb_var_selinv(gmrfb_fac* fac, double* var_out);
 gmrfb_status gmrfb_var_selinv_dev(gmrfb_fac* fac, double* d_var_out);
 /* Rao-Blackwellised Monte-Carlo variances, RBMCStrategy(N) (scripts/darcy/solve_darcy_gmrf-fem.jl:100,174,192):
  *   var_i = 1/Q_ii + mean_k ( Σ_{j != i} Q_ij x_j^(k) )^2 / Q_ii^2,   x^(k) = P' L^{-T} z^(k).
- * Q is the precision the factor was computed from; Z is n-by-nsamp standard normals supplied by the host. */
+ * Q is the precision the factor was computed from; Z is n-by-nsamp standard normals supplied by the caller (host or
+ * device memory: the caller owns the random stream, as the reference threads its MersenneTwister through). */
 gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
                             int64_t nsamp, double* var_out);
 /* Selected entries of Q^{-1}: for each k, out[k] = (Q^{-1})[rows[k], cols[k]] (`base`-based indices in

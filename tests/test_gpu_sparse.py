@@ -210,8 +210,12 @@ def test_gmrf_interface(pkg, orc, ctx, problems):
     mref = orc.posterior_mean(ref, Q, A, qe, y, np.zeros(n))
     assert rel(pkg.mean(xc), mref) < TOL_SOLVE and rel(pkg.mean(xc2), mref) < TOL_SOLVE
     assert rel(pkg.std(xc), np.sqrt(ref.selinv_diag())) < TOL_VAR
-    Z = np.random.default_rng(7).standard_normal((n, 50))
+    Z = np.random.default_rng(7).standard_normal((50, n)).T  # the host mirror draws one sample per contiguous row
     assert rel(pkg.std(xc2), np.sqrt(orc.rbmc_variance(ref, Qp, Z))) < 1e-9
+    # without an rng the normals are drawn on the device: a Monte-Carlo estimate of the exact (Takahashi) variances
+    bp3 = pkg.CholeskySolverBlueprint(var_strategy=pkg.RBMCStrategy(4000), perm=p, ctx=ctx)
+    xc3 = pkg.condition_on_observations(x, A, qe, y, solver_blueprint=bp3)
+    assert np.max(np.abs(pkg.var(xc3) - ref.selinv_diag()) / ref.selinv_diag()) < 0.15
     z = np.random.default_rng(11).standard_normal(n)
     s = pkg.rand(np.random.default_rng(11), xc)
     assert rel(s, mref + ref.solve_UP(z)) < TOL_SOLVE
