@@ -280,3 +280,9 @@ extern "C" gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps
   if (Qpost) *Qpost = &plan->out;
   return GMRFB_OK;
 }
+
+extern "C" gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_spm** Qpost) {
+  if (!plan || !Qpost) return fail(plan ? plan->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_postprec_result: NULL argument");
+  *Qpost = &plan->out;
+  return GMRFB_OK;
+}

@@ -647,6 +647,89 @@ def optimize(gno: GaussNewtonOptimizer):
     return gno.xk
 
 
+class DeviceGaussNewton:
+    """Gauss-Newton with the whole iteration on the device (gmrfb_gn_*) for a bilinear collocation residual
+    ``f(w) = L w + c (A w).*(D w)`` - the Burgers residual of scripts/solve_burger.jl:127-134 with L = A1 - A0 - dt nu D2,
+    A = A1, c = dt.  Same update, objective and stopping rule as ``GaussNewtonOptimizer`` / ``optimize``
+    (scripts/solve_burger.jl:143-180), but residual, tangent, ``Q + noise J'J``, refactorisation and solve never leave
+    the GPU; fields read afterwards as in scripts/burgers/solve_burgers_gmrf-fem.jl:184-188: ``xk``, ``Jk``, ``Q_mat``,
+    ``obj_history``, ``n_steps``."""
+
+    def __init__(self, mu, Q, L, A, D, c, noise, y, x0, solver_bp=None, max_steps=20, rel_tol=1e-4):
+        self.bp = solver_bp or GNCholeskySolverBlueprint()
+        self.ctx = self.bp.ctx or default_context()
+        Q = _csc(Q)
+        L, A, D = _csc(L), _csc(A), _csc(D)
+        if not (L.shape == A.shape == D.shape) or L.shape[1] != Q.shape[0]:
+            raise ValueError("L, A, D must share one shape (m x n) with n = size of Q")
+        m, n = L.shape
+        U = (abs(L) + abs(A) + abs(D)).tocsc()  # union pattern
+        U.sort_indices()
+        ucol = np.repeat(np.arange(n, dtype=np.int64), np.diff(U.indptr))
+        ukey = ucol * m + U.indices
+
+        def aligned(M):
+            mcol = np.repeat(np.arange(n, dtype=np.int64), np.diff(M.indptr))
+            pos = np.searchsorted(ukey, mcol * m + M.indices)
+            out = np.zeros(U.nnz)
+            out[pos] = M.data
+            return out
+
+        self._Qd = SparseMatrix(Q, ctx=self.ctx)
+        self.xk = np.ascontiguousarray(x0, dtype=np.float64).copy()
+        self.max_steps, self.rel_tol = int(max_steps), float(rel_tol)
+        self._pattern = (U.indptr.astype(np.int64), U.indices.astype(np.int64), (m, n))
+        opts = B.AnalyzeOpts()
+        opts.ordering_kind = B.ORDER_ND
+        opts.storage = B.STORAGE_FULL
+        opts.base = 0
+        self._coords = None
+        if self.bp.coords is not None:
+            self._coords = np.ascontiguousarray(self.bp.coords, dtype=np.float64)
+            opts.coord_dim = self._coords.shape[1]
+            opts.coords = self._coords.ctypes.data_as(B._F64P)
+        pp = None
+        if self.bp.perm is not None:
+            _, pp = B.i64(self.bp.perm)
+        _, cp = B.i64(self._pattern[0])
+        _, ri = B.i64(self._pattern[1])
+        _, lp = B.f64(aligned(L))
+        _, ap = B.f64(aligned(A))
+        _, dp = B.f64(aligned(D))
+        _, yp = B.f64(y)
+        _, mp = B.f64(mu)
+        h = C.c_void_p()
+        B.check(B.lib().gmrfb_gn_create(self.ctx.h, self._Qd.h, m, cp, ri, lp, ap, dp, 0, float(c), float(noise), yp, mp, pp,
+                                        C.byref(opts), C.byref(h)), self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_gn_destroy, h)
+        self.obj_history, self.n_steps = [], 0
+
+    def optimize(self):
+        hist = np.zeros(self.max_steps + 1)
+        steps = C.c_int32()
+        B.check(B.lib().gmrfb_gn_optimize(self.h, self.xk.ctypes.data_as(B._F64P), self.max_steps, self.rel_tol,
+                                          C.byref(steps), hist.ctypes.data_as(B._F64P)), self.ctx.h)
+        self.n_steps = steps.value
+        self.obj_history = hist[: self.n_steps + 1].tolist()
+        return self.xk
+
+    def _view(self, which):
+        out = [C.c_void_p() for _ in range(4)]
+        B.check(B.lib().gmrfb_gn_get(self.h, *(C.byref(o) for o in out)), self.ctx.h)
+        return out[which]
+
+    @property
+    def Jk(self):
+        """Tangent at the last linearisation point."""
+        return SparseMatrix(None, ctx=self.ctx, _handle=self._view(2), _owner=self).to_scipy()
+
+    @property
+    def Q_mat(self):
+        """Q + noise J_k' J_k of the last step (the posterior precision the reference builds at :184-186)."""
+        return SparseMatrix(None, ctx=self.ctx, _handle=self._view(3), _owner=self).to_scipy()
+
+
 # ------------------------------------------------------------------------------- block tridiagonal factor --
 class _DenseChol:
     """Stand-in for LinearAlgebra.Cholesky: ``.L`` is the lower factor."""

@@ -282,7 +282,9 @@ def burgers_spacetime(nx: int = 4095, nt: int = 201, dt: float = 0.01, nu: float
 
     tt, xx = np.meshgrid(np.arange(nt) / max(nt - 1, 1), xs, indexing="ij")
     coords = np.stack([xx.ravel(), tt.ravel()], axis=1)
-    return dict(Q=Q, mu=mu, f_and_J=f_and_J, y=np.zeros(nx * (nt - 1)), coords=coords, b=nx, N=nt, u0=u0)
+    # the same residual in the bilinear form f(w) = L w + c (A w).*(D w) the device Gauss-Newton driver takes
+    return dict(Q=Q, mu=mu, f_and_J=f_and_J, y=np.zeros(nx * (nt - 1)), coords=coords, b=nx, N=nt, u0=u0,
+                L=L_static, A=A_next, D=Dn, c=dt * h)
 
 
 def darcy_problem(nx: int = 601, seed: int = 0, q_eps: float = 1e8):

@@ -235,8 +235,37 @@ gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps_scalar, co
 gmrfb_status gmrfb_spm_dims(const gmrfb_spm* A, int64_t* m, int64_t* n, int64_t* nnz);
 gmrfb_status gmrfb_spm_get(const gmrfb_spm* A, int32_t base, int64_t* colptr, int64_t* rowval,
                            double* nzval);
+/* The plan's result matrix (pattern fixed at creation, values of the last gmrfb_postprec_compute); owned by the plan. */
+gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_spm** Qpost);
 /* Device pointer to the matrix values (for gmrfb_factorize_dev). */
 const double* gmrfb_spm_values_dev(const gmrfb_spm* A);
+
+/* ------------------------------------------- Gauss-Newton on the device ------ */
+/* The explicit loop of scripts/solve_burger.jl:143-180 (packaged as GaussNewtonOptimizer / optimize in
+ * scripts/burgers/solve_burgers_gmrf-fem.jl:172-182) for a bilinear collocation residual
+ *     f(w) = L w + c (A w) .* (D w),        J(w) = L + c (diag(D w) A + diag(A w) D),
+ * of which the Burgers residual f = A1 w - A0 w + dt (A1 w).*(D w) - dt nu D2 w (:127-134) is the instance
+ * L = A1 - A0 - dt nu D2, A = A1, c = dt.  Per iteration, all on the device: residual and tangent, the
+ * fixed-pattern assembly Q + noise J'J (:145), numeric refactorisation on the pattern analysed once, the solve
+ * x+ = (Q + noise J'J)^{-1} (Q mu + noise J'(J x + y - f)) (:146-148) and the objective
+ * (mu-x)'Q(mu-x) + noise |y-f|^2; the loop stops when its relative change is <= rel_tol or after max_steps (:171-180).
+ *   colptr/rowval : CSC union pattern of L, A, D (m-by-n, n = size of Q); lval/aval/dval are aligned to it (zeros where
+ *                   a matrix has no entry)
+ *   perm          : fill-reducing permutation to reuse (`opts->base`-based), or NULL to order by `opts` (may be NULL) */
+typedef struct gmrfb_gn gmrfb_gn;
+gmrfb_status gmrfb_gn_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, int64_t m, const int64_t* colptr,
+                             const int64_t* rowval, const double* lval, const double* aval, const double* dval,
+                             int32_t base, double c, double noise, const double* y, const double* mu,
+                             const int64_t* perm, const gmrfb_analyze_opts* opts, gmrfb_gn** out);
+/* x: in = starting point x0, out = final iterate; obj_hist (max_steps + 1 doubles, may be NULL) receives the objective
+ * at x0 and after every step; *steps = iterations taken. */
+gmrfb_status gmrfb_gn_optimize(gmrfb_gn* gn, double* x, int32_t max_steps, double rel_tol, int32_t* steps,
+                               double* obj_hist);
+/* Borrowed views of the optimiser's state after gmrfb_gn_optimize: the factor of the last Q + noise J'J (for
+ * mean / sample / variance calls), its symbolic analysis, the last tangent J_k and the assembled matrix
+ * (`Jₖ`, `Q_mat` in scripts/burgers/solve_burgers_gmrf-fem.jl:184-188).  Any of the outputs may be NULL. */
+gmrfb_status gmrfb_gn_get(gmrfb_gn* gn, gmrfb_fac** fac, gmrfb_sym** sym, const gmrfb_spm** J, const gmrfb_spm** Qpost);
+gmrfb_status gmrfb_gn_destroy(gmrfb_gn* gn);
 
 /* ------------------------------------------- block-tridiagonal Cholesky ------ */
 /* Replaces src/tridiagonal_cholesky.jl:

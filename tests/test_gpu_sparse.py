@@ -278,3 +278,31 @@ def test_dataset_loop_reuses_workspace(pkg, orc, ctx, W):
         assert abs(pkg.precision_map(xc) - Qp).max() < 1e-12 * abs(Qp).max()
         assert rel(pkg.mean(xc), mref) < 1e-9
         assert rel(pkg.var(xc), ref.selinv_diag()) < TOL_VAR
+
+
+def test_device_gauss_newton_matches_host_loop(pkg, orc, ctx, W):
+    """gmrfb_gn_*: the whole Gauss-Newton iteration of scripts/solve_burger.jl:143-180 on the device for the bilinear
+    Burgers residual, against (a) the host-driven GaussNewtonOptimizer and (b) the oracle's restated loop."""
+    P = W.burgers_spacetime(24, 6)
+    noise = 1e4
+    n = P["Q"].shape[0]
+    pat = orc.posterior_precision(P["Q"], P["f_and_J"](P["mu"])[1], noise)
+    p0 = pkg.Symbolic(pat, host_only=True).p
+    dgn = pkg.DeviceGaussNewton(P["mu"], P["Q"], P["L"], P["A"], P["D"], P["c"], noise, P["y"], P["mu"],
+                                solver_bp=pkg.GNCholeskySolverBlueprint(p0, ctx=ctx))
+    xd = dgn.optimize()
+    gno = pkg.GaussNewtonOptimizer(P["mu"], P["Q"], P["f_and_J"], noise, P["y"], P["mu"],
+                                   solver_bp=pkg.GNCholeskySolverBlueprint(p0, ctx=ctx))
+    xh = pkg.optimize(gno)
+    assert dgn.n_steps == gno.n_steps and dgn.n_steps >= 2
+    assert rel(xd, xh) < 1e-10
+    assert rel(np.array(dgn.obj_history[1:]), np.array(gno.obj_history)) < 1e-10
+    # oracle loop
+    x, Qx = P["mu"].copy(), P["Q"] @ P["mu"]
+    for _ in range(dgn.n_steps):
+        fx, J = P["f_and_J"](x)
+        x = orc.gauss_newton_step(P["Q"], J, noise, x, Qx, P["y"] - fx, p0)
+    assert rel(xd, x) < 1e-9
+    # state read after the loop: tangent and posterior precision of the last linearisation
+    assert abs(dgn.Q_mat - gno.Q_mat).max() < 1e-10 * abs(gno.Q_mat).max()
+    assert abs(dgn.Jk - gno.Jk).max() < 1e-12 * abs(gno.Jk).max()
