@@ -239,6 +239,68 @@ mutable struct B200TridiagonalCholeskyFactor
 end
 
 "`tridiagonal_cholesky(A::SparseMatrixCSC, N_blocks)` (src/tridiagonal_cholesky.jl:65-82)."
+# ---------------------------------------------------------------------------------------------------------------
+# Gauss-Newton on the device (gmrfb_gn_*): the loop of scripts/solve_burger.jl:143-180 for a bilinear collocation
+# residual f(w) = L w + c (A w).*(D w)  (Burgers, :127-134: L = A1 - A0 - dt*nu*D2, A = A1, c = dt).
+mutable struct B200GaussNewton
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    Q::Ptr{Cvoid}        # device copy of the prior precision (owned)
+    n::Int
+    obj_history::Vector{Float64}
+    n_steps::Int
+end
+
+function _union_pattern(Ms::SparseMatrixCSC{Float64,Int64}...)
+    U = sum(M -> SparseMatrixCSC(M.m, M.n, M.colptr, M.rowval, ones(length(M.nzval))), Ms)  # structural union
+    vals = map(Ms) do M
+        v = zeros(nnz(U))
+        for j in 1:M.n, p in nzrange(M, j)
+            q = searchsortedfirst(view(U.rowval, nzrange(U, j)), M.rowval[p]) + first(nzrange(U, j)) - 1
+            v[q] = M.nzval[p]
+        end
+        v
+    end
+    return U, vals
+end
+
+function b200_gauss_newton(mu::Vector{Float64}, Q::SparseMatrixCSC{Float64,Int64}, L::SparseMatrixCSC{Float64,Int64},
+                           A::SparseMatrixCSC{Float64,Int64}, D::SparseMatrixCSC{Float64,Int64}, c::Real, noise::Real,
+                           y::Vector{Float64}; perm::Union{Nothing,Vector{Int64}} = nothing,
+                           ctx::B200Context = default_context())
+    U, (lv, av, dv) = _union_pattern(L, A, D)
+    qh = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve Q check(ctx, ccall((:gmrfb_spm_create, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, size(Q, 1), size(Q, 2), Q.colptr, Q.rowval, Q.nzval, 1, qh))
+    opts = Ref(AnalyzeOpts(perm === nothing ? ORDER_ND : ORDER_GIVEN, 0, 1, 0, C_NULL, 0, 0, 0.0))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve U lv av dv y mu perm check(ctx, ccall((:gmrfb_gn_create, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64,
+         Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ref{AnalyzeOpts}, Ref{Ptr{Cvoid}}),
+        ctx.h, qh[], size(U, 1), U.colptr, U.rowval, lv, av, dv, 1, Float64(c), Float64(noise), y, mu,
+        perm === nothing ? C_NULL : pointer(perm), opts, out))
+    gn = B200GaussNewton(ctx, out[], qh[], size(Q, 1), Float64[], 0)
+    finalizer(gn) do g
+        ccall((:gmrfb_gn_destroy, libgmrfb), Int32, (Ptr{Cvoid},), g.h)
+        ccall((:gmrfb_spm_destroy, libgmrfb), Int32, (Ptr{Cvoid},), g.Q)
+    end
+    return gn
+end
+
+"`optimize(gno)` of scripts/burgers/solve_burgers_gmrf-fem.jl:182 - returns the final iterate."
+function optimize!(gn::B200GaussNewton, x0::Vector{Float64}; max_steps::Integer = 20, rel_tol::Real = 1e-4)
+    x = copy(x0)
+    hist = zeros(max_steps + 1)
+    steps = Ref{Int32}(0)
+    GC.@preserve x hist check(gn.ctx, ccall((:gmrfb_gn_optimize, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ref{Int32}, Ptr{Float64}),
+        gn.h, x, Int32(max_steps), Float64(rel_tol), steps, hist))
+    gn.n_steps = steps[]
+    gn.obj_history = hist[1:steps[]+1]
+    return x
+end
+
 function b200_tridiagonal_cholesky(A::SparseMatrixCSC{Float64,Int64}, N_blocks::Integer; ctx::B200Context = default_context())
     out = Ref{Ptr{Cvoid}}(C_NULL)
     st = GC.@preserve A ccall((:gmrfb_btd_factor, libgmrfb), Int32,
