@@ -8,7 +8,9 @@
 // with the Burgers collocation residual  f(w) = A1 w - A0 w + dt (A1 w).*(D w) - dt nu D2 w.  That residual is an
 // instance of
 //     f(w) = L w + c (A w) .* (D w),      J(w) = L + c (diag(D w) A + diag(A w) D),
-// with sparse L, A, D of one shape.  The caller passes the union pattern of L, A, D in CSC form with three aligned value
+// with sparse L, A, D of one shape; an optional elementwise cubic term e .* w.^3 (square systems: the elliptic problem
+// -lap u + u^3 = g of _research/elliptic_chen24.jl:231-285 with lumped mass, L = stiffness, e = mass) adds
+// diag(3 e w^2) to the tangent.  The caller passes the union pattern of L, A, D in CSC form with three aligned value
 // arrays; everything else happens here without leaving the device: residual and tangent (one row-wise and one
 // entry-wise kernel), the fixed-pattern assembly Q + noise J'J, the numeric refactorisation on the analysed pattern,
 // the solve, the objective (one scalar per iteration crosses PCIe, for the stopping rule).
@@ -32,6 +34,8 @@ struct gmrfb_gn {
   int64_t m = 0, n = 0, nnz = 0;
   double c = 0, noise = 0;
   DevBuf<double> lval, aval, dval;        // aligned to J's CSC positions
+  DevBuf<double> cubic;                   // optional e (length n = m): f += e .* w.^3
+  DevBuf<int64_t> diagpos;                // CSC position of J[i,i] (cubic term)
   DevBuf<double> y, mu, qmu, x, aw, dw, r, t, rhs, d, qd;
   int32_t steps = 0;
 };
@@ -42,8 +46,9 @@ namespace {
 __global__ void k_gn_residual(int64_t m, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                               const int64_t* __restrict__ tmap, const double* __restrict__ lval,
                               const double* __restrict__ aval, const double* __restrict__ dval, double c,
-                              const double* __restrict__ w, const double* __restrict__ y, double* __restrict__ aw,
-                              double* __restrict__ dw, double* __restrict__ r) {
+                              const double* __restrict__ w, const double* __restrict__ y,
+                              const double* __restrict__ cubic, double* __restrict__ aw, double* __restrict__ dw,
+                              double* __restrict__ r) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   double sl = 0.0, sa = 0.0, sd = 0.0;
@@ -56,7 +61,16 @@ __global__ void k_gn_residual(int64_t m, const int64_t* __restrict__ rowptr, con
   }
   aw[i] = sa;
   dw[i] = sd;
-  r[i] = y[i] - (sl + c * sa * sd);
+  double f = sl + c * sa * sd;
+  if (cubic) f += cubic[i] * w[i] * w[i] * w[i];
+  r[i] = y[i] - f;
+}
+
+// J[i,i] += 3 e_i w_i^2
+__global__ void k_gn_cubic_diag(int64_t n, const int64_t* __restrict__ diagpos, const double* __restrict__ cubic,
+                                const double* __restrict__ w, double* __restrict__ jval) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) jval[diagpos[i]] += 3.0 * cubic[i] * w[i] * w[i];
 }
 
 // entries of the tangent in CSC order: J = L + c (diag(D w) A + diag(A w) D)
@@ -83,7 +97,7 @@ gmrfb_status gn_eval(gmrfb_gn* g, double* obj) {
   cudaStream_t st = ctx->stream;
   const gmrfb_spm* J = g->J;
   k_gn_residual<<<blocks(g->m), 256, 0, st>>>(g->m, J->d_rowptr.p, J->d_colidx.p, J->d_tmap.p, g->lval.p, g->aval.p,
-                                              g->dval.p, g->c, g->x.p, g->y.p, g->aw.p, g->dw.p, g->r.p);
+                                              g->dval.p, g->c, g->x.p, g->y.p, g->cubic.p, g->aw.p, g->dw.p, g->r.p);
   GMRFB_CU(ctx, cudaGetLastError());
   // objective = (mu - x)' Q (mu - x) + noise * r'r
   GMRFB_CU(ctx, launch_axpby(g->n, 1.0, g->mu.p, -1.0, g->x.p, g->d.p, st));
@@ -106,6 +120,11 @@ gmrfb_status gn_step(gmrfb_gn* g) {
   k_gn_tangent<<<blocks(g->nnz), 256, 0, st>>>(g->nnz, J->d_rowidx.p, g->lval.p, g->aval.p, g->dval.p, g->c, g->aw.p,
                                                g->dw.p, J->d_val.p);
   GMRFB_CU(ctx, cudaGetLastError());
+  if (g->cubic.p) {
+    k_gn_cubic_diag<<<blocks(g->n), 256, 0, st>>>(g->n, g->diagpos.p, g->cubic.p, g->x.p, J->d_val.p);
+    GMRFB_CU(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
   GMRFB_CU(ctx, launch_gather_values(J->d_val.p, J->d_tmap.p, J->nnz, J->d_tval.p, st));
   // t = J x + r ;  rhs = Q mu + noise * J' t
   GMRFB_CU(ctx, launch_spmv_rows(g->m, J->d_rowptr.p, J->d_colidx.p, J->d_tval.p, g->x.p, g->t.p, 1.0, 0.0, st));
@@ -126,9 +145,9 @@ gmrfb_status gn_step(gmrfb_gn* g) {
 
 extern "C" gmrfb_status gmrfb_gn_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, int64_t m, const int64_t* colptr,
                                         const int64_t* rowval, const double* lval, const double* aval,
-                                        const double* dval, int32_t base, double c, double noise, const double* y,
-                                        const double* mu, const int64_t* perm, const gmrfb_analyze_opts* opts,
-                                        gmrfb_gn** out) {
+                                        const double* dval, const double* cubic, int32_t base, double c, double noise,
+                                        const double* y, const double* mu, const int64_t* perm,
+                                        const gmrfb_analyze_opts* opts, gmrfb_gn** out) {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_gn_create: ctx is NULL");
   if (!Q || !colptr || !rowval || !lval || !aval || !dval || !y || !mu || !out || m <= 0 || Q->m != Q->n)
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_gn_create: bad argument");
@@ -157,6 +176,17 @@ extern "C" gmrfb_status gmrfb_gn_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, int6
   if (up(g->lval, lval, g->nnz) != cudaSuccess || up(g->aval, aval, g->nnz) != cudaSuccess ||
       up(g->dval, dval, g->nnz) != cudaSuccess || up(g->y, y, m) != cudaSuccess || up(g->mu, mu, g->n) != cudaSuccess)
     return cleanup(fail(ctx, GMRFB_ERR_ALLOC, "gmrfb_gn_create: device allocation failed"));
+  if (cubic) {
+    if (m != g->n) return cleanup(fail(ctx, GMRFB_ERR_INVALID, "gmrfb_gn_create: the cubic term needs a square system"));
+    std::vector<int64_t> dp((size_t)g->n, -1);
+    for (int64_t j = 0; j < g->n; j++)
+      for (int64_t p = g->J->colptr[j]; p < g->J->colptr[j + 1]; p++)
+        if (g->J->rowidx[p] == j) dp[j] = p;
+    for (int64_t j = 0; j < g->n; j++)
+      if (dp[j] < 0) return cleanup(fail(ctx, GMRFB_ERR_INVALID, "gmrfb_gn_create: the pattern must hold the diagonal for the cubic term"));
+    if (up(g->cubic, cubic, g->n) != cudaSuccess || g->diagpos.upload(dp, st) != cudaSuccess)
+      return cleanup(fail(ctx, GMRFB_ERR_ALLOC, "gmrfb_gn_create: device allocation failed"));
+  }
   for (DevBuf<double>* b : {&g->qmu, &g->x, &g->rhs, &g->d, &g->qd})
     if (b->alloc((size_t)g->n) != cudaSuccess) return cleanup(fail(ctx, GMRFB_ERR_ALLOC, "gmrfb_gn_create: device allocation failed"));
   for (DevBuf<double>* b : {&g->aw, &g->dw, &g->r, &g->t})

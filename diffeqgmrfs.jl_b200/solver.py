@@ -655,15 +655,21 @@ class DeviceGaussNewton:
     the GPU; fields read afterwards as in scripts/burgers/solve_burgers_gmrf-fem.jl:184-188: ``xk``, ``Jk``, ``Q_mat``,
     ``obj_history``, ``n_steps``."""
 
-    def __init__(self, mu, Q, L, A, D, c, noise, y, x0, solver_bp=None, max_steps=20, rel_tol=1e-4):
+    def __init__(self, mu, Q, L, A, D, c, noise, y, x0, solver_bp=None, max_steps=20, rel_tol=1e-4, cubic=None):
+        """``cubic``: optional vector e adding ``e .* w.^3`` to the residual (the elliptic problem of
+        _research/elliptic_chen24.jl: L = stiffness, e = lumped mass, A = D = 0)."""
         self.bp = solver_bp or GNCholeskySolverBlueprint()
         self.ctx = self.bp.ctx or default_context()
         Q = _csc(Q)
-        L, A, D = _csc(L), _csc(A), _csc(D)
+        L = _csc(L)
+        A = _csc(A) if A is not None else sp.csc_matrix(L.shape)
+        D = _csc(D) if D is not None else sp.csc_matrix(L.shape)
         if not (L.shape == A.shape == D.shape) or L.shape[1] != Q.shape[0]:
             raise ValueError("L, A, D must share one shape (m x n) with n = size of Q")
         m, n = L.shape
         U = (abs(L) + abs(A) + abs(D)).tocsc()  # union pattern
+        if cubic is not None:
+            U = (U + sp.identity(n, format="csc")).tocsc()  # the cubic term lives on the diagonal
         U.sort_indices()
         ucol = np.repeat(np.arange(n, dtype=np.int64), np.diff(U.indptr))
         ukey = ucol * m + U.indices
@@ -698,8 +704,11 @@ class DeviceGaussNewton:
         _, dp = B.f64(aligned(D))
         _, yp = B.f64(y)
         _, mp = B.f64(mu)
+        ep = None
+        if cubic is not None:
+            _, ep = B.f64(cubic)
         h = C.c_void_p()
-        B.check(B.lib().gmrfb_gn_create(self.ctx.h, self._Qd.h, m, cp, ri, lp, ap, dp, 0, float(c), float(noise), yp, mp, pp,
+        B.check(B.lib().gmrfb_gn_create(self.ctx.h, self._Qd.h, m, cp, ri, lp, ap, dp, ep, 0, float(c), float(noise), yp, mp, pp,
                                         C.byref(opts), C.byref(h)), self.ctx.h)
         self.h = h
         self._fin = weakref.finalize(self, B.lib().gmrfb_gn_destroy, h)

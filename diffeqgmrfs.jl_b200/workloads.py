@@ -227,8 +227,9 @@ def elliptic_problem(nx: int = 201, corr_range: float = 0.1, seed: int = 0):
         J.data[diag_pos] += 3.0 * m * u**2
         return Kc @ u + m * u**3, J
 
+    # K and m: the same residual as f(u) = K u + m .* u.^3 for the device Gauss-Newton driver
     return dict(Q=Q, nodes=nodes, A_bnd=A_bnd, y_bnd=u_true[bnd], f_and_J=f_and_J, y=g, u_true=u_true,
-                n=nodes.shape[0])
+                n=nodes.shape[0], K=Kc, m=m)
 
 
 def burgers_spacetime(nx: int = 4095, nt: int = 201, dt: float = 0.01, nu: float = 0.01, tau: float = 1.0,

@@ -249,13 +249,17 @@ const double* gmrfb_spm_values_dev(const gmrfb_spm* A);
  * fixed-pattern assembly Q + noise J'J (:145), numeric refactorisation on the pattern analysed once, the solve
  * x+ = (Q + noise J'J)^{-1} (Q mu + noise J'(J x + y - f)) (:146-148) and the objective
  * (mu-x)'Q(mu-x) + noise |y-f|^2; the loop stops when its relative change is <= rel_tol or after max_steps (:171-180).
+ * An optional elementwise cubic term, f += e .* w.^3 (J += diag(3 e w.^2); square systems whose pattern holds the
+ * diagonal), covers the elliptic problem -lap u + u^3 = g of _research/elliptic_chen24.jl:231-285 (L = stiffness,
+ * e = lumped mass).
  *   colptr/rowval : CSC union pattern of L, A, D (m-by-n, n = size of Q); lval/aval/dval are aligned to it (zeros where
  *                   a matrix has no entry)
+ *   cubic         : e (length n) or NULL
  *   perm          : fill-reducing permutation to reuse (`opts->base`-based), or NULL to order by `opts` (may be NULL) */
 typedef struct gmrfb_gn gmrfb_gn;
 gmrfb_status gmrfb_gn_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, int64_t m, const int64_t* colptr,
                              const int64_t* rowval, const double* lval, const double* aval, const double* dval,
-                             int32_t base, double c, double noise, const double* y, const double* mu,
+                             const double* cubic, int32_t base, double c, double noise, const double* y, const double* mu,
                              const int64_t* perm, const gmrfb_analyze_opts* opts, gmrfb_gn** out);
 /* x: in = starting point x0, out = final iterate; obj_hist (max_steps + 1 doubles, may be NULL) receives the objective
  * at x0 and after every step; *steps = iterations taken. */

@@ -276,9 +276,10 @@ function b200_gauss_newton(mu::Vector{Float64}, Q::SparseMatrixCSC{Float64,Int64
     opts = Ref(AnalyzeOpts(perm === nothing ? ORDER_ND : ORDER_GIVEN, 0, 1, 0, C_NULL, 0, 0, 0.0))
     out = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve U lv av dv y mu perm check(ctx, ccall((:gmrfb_gn_create, libgmrfb), Int32,
-        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64,
-         Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ref{AnalyzeOpts}, Ref{Ptr{Cvoid}}),
-        ctx.h, qh[], size(U, 1), U.colptr, U.rowval, lv, av, dv, 1, Float64(c), Float64(noise), y, mu,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
+         Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ref{AnalyzeOpts}, Ref{Ptr{Cvoid}}),
+        ctx.h, qh[], size(U, 1), U.colptr, U.rowval, lv, av, dv, C_NULL #= cubic term e, if any =#, 1, Float64(c),
+        Float64(noise), y, mu,
         perm === nothing ? C_NULL : pointer(perm), opts, out))
     gn = B200GaussNewton(ctx, out[], qh[], size(Q, 1), Float64[], 0)
     finalizer(gn) do g

@@ -306,3 +306,23 @@ def test_device_gauss_newton_matches_host_loop(pkg, orc, ctx, W):
     # state read after the loop: tangent and posterior precision of the last linearisation
     assert abs(dgn.Q_mat - gno.Q_mat).max() < 1e-10 * abs(gno.Q_mat).max()
     assert abs(dgn.Jk - gno.Jk).max() < 1e-12 * abs(gno.Jk).max()
+
+
+def test_device_gauss_newton_cubic_term(pkg, orc, ctx, W):
+    """The elliptic problem -lap u + u^3 = g (_research/elliptic_chen24.jl): f(u) = K u + m .* u.^3 through the cubic
+    term of gmrfb_gn_*, against the host-driven optimiser on the same prior."""
+    P = W.elliptic_problem(15)
+    n = P["n"]
+    Qc = (P["Q"] + 1e6 * (P["A_bnd"].T @ P["A_bnd"])).tocsc()  # prior conditioned on the boundary data
+    mu = np.zeros(n)
+    noise = 1e10
+    p0 = pkg.Symbolic(orc.posterior_precision(Qc, P["f_and_J"](mu)[1], noise), host_only=True).p
+    dgn = pkg.DeviceGaussNewton(mu, Qc, P["K"], None, None, 0.0, noise, P["y"], mu, cubic=P["m"],
+                                solver_bp=pkg.GNCholeskySolverBlueprint(p0, ctx=ctx), max_steps=10, rel_tol=1e-8)
+    xd = dgn.optimize()
+    gno = pkg.GaussNewtonOptimizer(mu, Qc, P["f_and_J"], noise, P["y"], mu,
+                                   solver_bp=pkg.GNCholeskySolverBlueprint(p0, ctx=ctx), max_steps=10, rel_tol=1e-8)
+    xh = pkg.optimize(gno)
+    assert dgn.n_steps == gno.n_steps and dgn.n_steps >= 2
+    assert rel(xd, xh) < 1e-9
+    assert rel(xd, P["u_true"]) < 1e-2  # the collocation solution of the manufactured problem

@@ -103,6 +103,18 @@ def config1():
     gno, out["Optimization_s"] = timed(run_gn, warm=True)
     out["gn_steps"] = gno.n_steps
     out["rel_err_vs_manufactured"] = rel(gno.xk, P["u_true"])
+
+    def run_dgn():  # the same loop with residual and tangent on the device (cubic term of gmrfb_gn_*)
+        d = pkg.DeviceGaussNewton(mu_c, pkg.precision_map(xc), P["K"], None, None, 0.0, noise, P["y"], mu_c, cubic=P["m"],
+                                  solver_bp=pkg.GNCholeskySolverBlueprint(perm=p), max_steps=10, rel_tol=1e-5)
+        t0 = time.perf_counter()
+        d.optimize()
+        ctx.sync()
+        return d, time.perf_counter() - t0
+
+    run_dgn()
+    dgn, t_opt = run_dgn()
+    out["device_gn"] = {"steps": dgn.n_steps, "optimize_s": t_opt, "rel_diff_vs_host_driven_loop": rel(dgn.xk, gno.xk)}
     Qf = gno.Q_mat
     xf = pkg.GMRF(gno.xk, Qf, pkg.CholeskySolverBlueprint(var_strategy=pkg.RBMCStrategy(50, rng=np.random.default_rng(0)), perm=p))
     _, out["Std dev (RBMC 50)_s"] = timed(lambda: pkg.std(pkg.GMRF(gno.xk, Qf, pkg.CholeskySolverBlueprint(
