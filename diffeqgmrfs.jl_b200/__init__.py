@@ -10,8 +10,8 @@ from . import _lib, dist, workloads  # noqa: F401
 from .solver import (  # noqa: F401
     CholeskyFactor, CholeskySolverBlueprint, Context, DeviceGaussNewton, GMRF, GNCholeskySolverBlueprint, GaussNewtonOptimizer,
     PosteriorPrecision, RBMCStrategy, SparseMatrix, Symbolic, TakahashiStrategy, TridiagonalCholeskyFactor,
-    backward_solve, cholesky, condition_on_observations, default_context, forward_solve, ldiv, ldiv_, mean,
-    optimize, precision_map, rand, sqmahal, std, to_matrix, tridiagonal_cholesky, tridiagonal_cholesky_dense, var,
+    backward_solve, cholesky, condition_on_observations, default_context, forward_solve, ldiv, ldiv_, mean, metrics,
+    optimize, precision_map, rand, sqmahal, std, to_matrix, tridiagonal_cholesky, tridiagonal_cholesky_dense, tridiagonal_cholesky_ssm, var,
 )
 from ._lib import GmrfbError, NotPositiveDefinite  # noqa: F401
 

@@ -99,6 +99,7 @@ SIGNATURES = {
     "gmrfb_postprec_create": (C.c_int32, [_P, _P, _P, C.POINTER(_P)]),
     "gmrfb_postprec_destroy": (C.c_int32, [_P]),
     "gmrfb_postprec_compute": (C.c_int32, [_P, C.c_double, _F64P, C.POINTER(_P)]),
+    "gmrfb_metrics": (C.c_int32, [_P, _P, _F64P, _F64P, C.c_int64, _F64P]),
     "gmrfb_postprec_result": (C.c_int32, [_P, C.POINTER(_P)]),
     "gmrfb_gn_create": (C.c_int32, [_P, _P, C.c_int64, _I64P, _I64P, _F64P, _F64P, _F64P, _F64P, C.c_int32, C.c_double, C.c_double,
                                     _F64P, _F64P, _I64P, C.POINTER(AnalyzeOpts), C.POINTER(_P)]),
@@ -110,6 +111,7 @@ SIGNATURES = {
     "gmrfb_spm_values_dev": (_P, [_P]),
     "gmrfb_btd_factor": (C.c_int32, [_P, C.c_int64, _I64P, _I64P, _F64P, C.c_int32, C.c_int64, C.POINTER(_P)]),
     "gmrfb_btd_factor_dense": (C.c_int32, [_P, C.c_int64, C.c_int64, _F64P, _F64P, C.POINTER(_P)]),
+    "gmrfb_btd_factor_ssm": (C.c_int32, [_P, C.c_int64, C.c_int64, _F64P, _F64P, _F64P, _F64P, C.POINTER(_P)]),
     "gmrfb_btd_destroy": (C.c_int32, [_P]),
     "gmrfb_btd_get_block": (C.c_int32, [_P, C.c_int64, C.c_int32, _F64P, C.c_int64]),
     "gmrfb_btd_solve": (C.c_int32, [_P, C.c_int32, _F64P, C.c_int64, C.c_int64]),

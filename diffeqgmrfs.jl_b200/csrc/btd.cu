@@ -220,6 +220,42 @@ extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_
   return rc;
 }
 
+// Block-tridiagonal precision of a constant-mesh implicit-Euler state-space model built directly in block form
+// (ingredients of src/spdes/shallow_water.jl:198-228): with G = M + dt K and noise precision q,
+//   D_1 = Q_0 + q M'M,   D_t = q (G'G + M'M) (1 < t < N),   D_N = q G'G,   B_t = -q G'M  (every sub-diagonal block),
+// so four b-by-b blocks describe the whole N-block matrix: the arena is filled on the device from them, without the
+// N-block host array of gmrfb_btd_factor_dense or the sparse -> dense gather of src/tridiagonal_cholesky.jl:73,76.
+extern "C" gmrfb_status gmrfb_btd_factor_ssm(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D_first,
+                                             const double* D_mid, const double* D_last, const double* B_sub,
+                                             gmrfb_btd** out) {
+  if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor_ssm: ctx is NULL");
+  if (!out || !D_first || (nblocks > 1 && (!D_last || !B_sub)) || (nblocks > 2 && !D_mid))
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_factor_ssm: NULL argument");
+  *out = nullptr;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<gmrfb_btd> f;
+  gmrfb_status rc = btd_alloc(ctx, b, nblocks, f);
+  if (rc != GMRFB_OK) return rc;
+  // stage the distinct blocks once in device memory, then replicate device-to-device
+  DevBuf<double> stage;
+  GMRFB_CU(ctx, stage.alloc((size_t)(4 * b * b)));
+  const double* src[4] = {D_first, D_mid, D_last, B_sub};
+  for (int k = 0; k < 4; k++)
+    if (src[k]) GMRFB_CU(ctx, cudaMemcpyAsync(stage.p + k * b * b, src[k], b * b * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  for (int64_t i = 0; i < nblocks; i++) {
+    const int which = (i == 0) ? 0 : (i == nblocks - 1 ? 2 : 1);
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot, f->ld * sizeof(double), stage.p + which * b * b,
+                                    b * sizeof(double), b * sizeof(double), b, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (i > 0)
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot + (int64_t)f->ld * b, f->ld * sizeof(double),
+                                      stage.p + 3 * b * b, b * sizeof(double), b * sizeof(double), b,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  rc = btd_run_factor(f.get());  // synchronises the stream: `stage` may be released afterwards
+  *out = f.release();
+  return rc;
+}
+
 extern "C" gmrfb_status gmrfb_btd_factor(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
                                          const double* nzval, int32_t base, int64_t nblocks, gmrfb_btd** out) {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor: ctx is NULL");

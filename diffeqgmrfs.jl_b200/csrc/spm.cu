@@ -286,3 +286,92 @@ extern "C" gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_
   *Qpost = &plan->out;
   return GMRFB_OK;
 }
+
+// ------------------------------------------------------------------------------- evaluation metrics ----
+// src/metrics.jl:3-13 on the device: pred = E x (or x), then
+//   rmse = sqrt(mean((pred - truth).^2)),  max_err = max |pred - truth|,  rel_err = |pred - truth| / |truth|.
+namespace {
+
+constexpr int MET_BLOCKS = 512;
+
+// per-block partials in a fixed order (bit-reproducible): [sum (p-t)^2, max |p-t|, sum t^2]
+__global__ void __launch_bounds__(256) k_metrics_partial(int64_t n, const double* __restrict__ pred,
+                                                         const double* __restrict__ truth, double* __restrict__ part) {
+  __shared__ double sh[3][8];
+  double s2 = 0.0, mx = 0.0, t2 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const double d = pred[i] - truth[i], t = truth[i];
+    s2 += d * d;
+    mx = fmax(mx, fabs(d));
+    t2 += t * t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[0][warp] = s2;
+    sh[1][warp] = mx;
+    sh[2][warp] = t2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int w = 0; w < 8; w++) {
+      a += sh[0][w];
+      b = fmax(b, sh[1][w]);
+      c += sh[2][w];
+    }
+    part[3 * blockIdx.x] = a;
+    part[3 * blockIdx.x + 1] = b;
+    part[3 * blockIdx.x + 2] = c;
+  }
+}
+
+__global__ void k_metrics_final(int nb, int64_t n, const double* __restrict__ part, double* __restrict__ out) {
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int k = 0; k < nb; k++) {
+    a += part[3 * k];
+    b = fmax(b, part[3 * k + 1]);
+    c += part[3 * k + 2];
+  }
+  out[0] = sqrt(a / (double)n);
+  out[1] = b;
+  out[2] = sqrt(a) / sqrt(c);
+}
+
+}  // namespace
+
+extern "C" gmrfb_status gmrfb_metrics(gmrfb_ctx* ctx, const gmrfb_spm* E, const double* x, const double* truth,
+                                      int64_t ntruth, double* out3) {
+  if (!ctx || !x || !truth || !out3 || ntruth <= 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_metrics: bad argument");
+  if (E && E->m != ntruth) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_metrics: E has the wrong number of rows");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int64_t nx = E ? E->n : ntruth;
+  DevBuf<double> dx, dt, dp, part;
+  GMRFB_CU(ctx, dx.alloc((size_t)nx));
+  GMRFB_CU(ctx, dt.alloc((size_t)ntruth));
+  GMRFB_CU(ctx, part.alloc(3 * MET_BLOCKS + 3));
+  GMRFB_CU(ctx, cudaMemcpyAsync(dx.p, x, nx * sizeof(double), cudaMemcpyDefault, st));
+  GMRFB_CU(ctx, cudaMemcpyAsync(dt.p, truth, ntruth * sizeof(double), cudaMemcpyDefault, st));
+  const double* pred = dx.p;
+  if (E) {
+    GMRFB_CU(ctx, dp.alloc((size_t)ntruth));
+    GMRFB_CU(ctx, launch_spmv_rows(E->m, E->d_rowptr.p, E->d_colidx.p, E->d_tval.p, dx.p, dp.p, 1.0, 0.0, st));
+    ctx->launches++;
+    pred = dp.p;
+  }
+  const int nb = (int)std::min<int64_t>(MET_BLOCKS, (ntruth + 255) / 256);
+  k_metrics_partial<<<nb, 256, 0, st>>>(ntruth, pred, dt.p, part.p);
+  GMRFB_CU(ctx, cudaGetLastError());
+  k_metrics_final<<<1, 1, 0, st>>>(nb, ntruth, part.p, part.p + 3 * MET_BLOCKS);
+  GMRFB_CU(ctx, cudaGetLastError());
+  ctx->launches += 2;
+  GMRFB_CU(ctx, cudaMemcpyAsync(out3, part.p + 3 * MET_BLOCKS, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GMRFB_CU(ctx, cudaStreamSynchronize(st));
+  return GMRFB_OK;
+}

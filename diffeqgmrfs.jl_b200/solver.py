@@ -647,6 +647,17 @@ def optimize(gno: GaussNewtonOptimizer):
     return gno.xk
 
 
+def metrics(pred_or_x, truth, E: SparseMatrix | None = None, ctx=None):
+    """``rmse``, ``max_err``, ``rel_err`` (src/metrics.jl:3-13) on the device; with ``E`` the prediction is ``E * x``
+    (scripts/darcy/solve_darcy_gmrf-fem.jl:190-196)."""
+    ctx = ctx or (E.ctx if E is not None else default_context())
+    _, xp = B.f64(pred_or_x)
+    t, tp = B.f64(truth)
+    out = (C.c_double * 3)()
+    B.check(B.lib().gmrfb_metrics(ctx.h, E.h if E is not None else None, xp, tp, t.size, out), ctx.h)
+    return out[0], out[1], out[2]
+
+
 class DeviceGaussNewton:
     """Gauss-Newton with the whole iteration on the device (gmrfb_gn_*) for a bilinear collocation residual
     ``f(w) = L w + c (A w).*(D w)`` - the Burgers residual of scripts/solve_burger.jl:127-134 with L = A1 - A0 - dt nu D2,
@@ -832,6 +843,21 @@ def tridiagonal_cholesky_dense(D, Bsub, ctx=None) -> TridiagonalCholeskyFactor:
         B.lib().gmrfb_btd_destroy(h)
     B.check(st, ctx.h)
     return TridiagonalCholeskyFactor(h, ctx, b * N, b, N)
+
+
+def tridiagonal_cholesky_ssm(D_first, D_mid, D_last, B_sub, N_blocks, ctx=None) -> TridiagonalCholeskyFactor:
+    """Block-tridiagonal factor of a constant-mesh implicit-Euler state-space prior given by its four distinct blocks
+    (gmrfb_btd_factor_ssm; ingredients of src/spdes/shallow_water.jl:198-228)."""
+    ctx = ctx or default_context()
+    blocks = [np.asfortranarray(M, dtype=np.float64) if M is not None else None for M in (D_first, D_mid, D_last, B_sub)]
+    b = blocks[0].shape[0]
+    ptrs = [M.ctypes.data_as(B._F64P) if M is not None else None for M in blocks]
+    h = C.c_void_p()
+    st = B.lib().gmrfb_btd_factor_ssm(ctx.h, b, int(N_blocks), *ptrs, C.byref(h))
+    if st != B.OK and h.value:
+        B.lib().gmrfb_btd_destroy(h)
+    B.check(st, ctx.h)
+    return TridiagonalCholeskyFactor(h, ctx, b * int(N_blocks), b, int(N_blocks))
 
 
 def forward_solve(L, b):

@@ -240,6 +240,12 @@ gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_spm** Qpost
 /* Device pointer to the matrix values (for gmrfb_factorize_dev). */
 const double* gmrfb_spm_values_dev(const gmrfb_spm* A);
 
+/* Evaluation metrics of src/metrics.jl:3-13 on the device: pred = E x (E = evaluation matrix, e.g. the 241 x 241 grid
+ * of scripts/darcy/solve_darcy_gmrf-fem.jl:86-89,190-196; NULL: pred = x), out3 = { rmse, max_err, rel_err } of pred
+ * against `truth` (ntruth values).  x and truth may be host or device pointers. */
+gmrfb_status gmrfb_metrics(gmrfb_ctx* ctx, const gmrfb_spm* E, const double* x, const double* truth, int64_t ntruth,
+                           double* out3);
+
 /* ------------------------------------------- Gauss-Newton on the device ------ */
 /* The explicit loop of scripts/solve_burger.jl:143-180 (packaged as GaussNewtonOptimizer / optimize in
  * scripts/burgers/solve_burgers_gmrf-fem.jl:172-182) for a bilinear collocation residual
@@ -285,6 +291,11 @@ gmrfb_status gmrfb_btd_factor(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, 
  * (B[:,:,k] = block (k+2, k+1) of A, 1-based), both column-major and contiguous. */
 gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D,
                                     const double* B, gmrfb_btd** out);
+/* Constant-mesh implicit-Euler state-space prior built directly in block form (ingredients of
+ * src/spdes/shallow_water.jl:198-228): the N-block matrix has diagonal blocks D_first, D_mid (blocks 2..N-1), D_last and
+ * one sub-diagonal block B_sub everywhere.  Four b-by-b column-major blocks (host or device) instead of N. */
+gmrfb_status gmrfb_btd_factor_ssm(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D_first,
+                                  const double* D_mid, const double* D_last, const double* B_sub, gmrfb_btd** out);
 gmrfb_status gmrfb_btd_destroy(gmrfb_btd* f);
 enum { GMRFB_BTD_BLOCK_L = 0, GMRFB_BTD_BLOCK_C = 1 };
 /* Copy block i (0-based) out: which = L -> `chos[i+1].L` (b-by-b lower, upper zeroed);

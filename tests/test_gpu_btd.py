@@ -130,3 +130,15 @@ def test_btd_solve_ill_conditioned_residual(pkg, orc, ctx, W):
     res = np.linalg.norm(A @ x - rhs) / np.linalg.norm(rhs)
     res_o = np.linalg.norm(A @ xo - rhs) / np.linalg.norm(rhs)
     assert res < 10 * res_o + 1e-13
+
+
+def test_btd_ssm_blocks_match_dense_entry(pkg, orc, ctx, W):
+    """gmrfb_btd_factor_ssm: the implicit-Euler heat prior (config 5 in miniature) from its four distinct blocks."""
+    hs = W.heat_spacetime(7, 6, dt=1e-2)
+    D, Bs, N = hs["D"], hs["B"], hs["N"]
+    assert all(np.array_equal(D[:, :, t], D[:, :, 1]) for t in range(1, N - 1))
+    F = pkg.tridiagonal_cholesky_ssm(D[:, :, 0], D[:, :, 1], D[:, :, N - 1], Bs[:, :, 0], N, ctx=ctx)
+    Fo = orc.tridiagonal_cholesky(hs["A"], N)
+    rhs = np.random.default_rng(3).standard_normal(hs["A"].shape[0])
+    assert rel(pkg.ldiv(F, rhs), orc.btd_ldiv(Fo, rhs)) < 1e-10
+    assert abs(F.logdet() - orc.btd_logdet(Fo)) < 1e-10 * abs(orc.btd_logdet(Fo))

@@ -326,3 +326,18 @@ def test_device_gauss_newton_cubic_term(pkg, orc, ctx, W):
     assert dgn.n_steps == gno.n_steps and dgn.n_steps >= 2
     assert rel(xd, xh) < 1e-9
     assert rel(xd, P["u_true"]) < 1e-2  # the collocation solution of the manufactured problem
+
+
+def test_metrics_on_device(pkg, orc, ctx):
+    """src/metrics.jl:3-13 (rmse, max_err, rel_err), with and without an evaluation matrix."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(0)
+    n, m = 5000, 1777
+    x, truth = rng.standard_normal(n), rng.standard_normal(m)
+    E = sp.random(m, n, density=0.002, random_state=1, format="csc")
+    got = pkg.metrics(x, truth, E=pkg.SparseMatrix(E, ctx=ctx))
+    want = orc.metrics(E @ x, truth)
+    assert np.allclose(got, want, rtol=1e-12)
+    t2 = x + 1e-3 * rng.standard_normal(n)
+    assert np.allclose(pkg.metrics(x, t2, ctx=ctx), orc.metrics(x, t2), rtol=1e-12)
