@@ -121,6 +121,8 @@ static const char* prof_name(int kind) {
     case PK_BWD_LEVEL: return "k_bwd_step";
     case PK_FWD_ASM: return "k_fwd_assemble";
     case PK_BWD_RPART: return "k_bwd_rpart";
+    case PK_FWD_SMALL: return "k_fwd_small";
+    case PK_BWD_SMALL: return "k_bwd_small";
     case PK_SCATTER: return "k_scatter_values";
     case PK_MEMSET: return "memset(front arena)";
     case PK_PERM: return "k_perm_gather/scatter";
@@ -308,6 +310,28 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
   }
   GMRFB_CU(ctx, sym->d_level_lists.upload(lists, st));
   // ---- solve schedule ----
+  auto solve_small = [&](int32_t s) { return S.front_order(s) <= SOLVE_SMALL_MAX; };
+  {
+    std::vector<int32_t> sl;
+    sym->small_off.clear(), sym->small_cnt.clear(), sym->big_off.clear(), sym->big_cnt.clear(), sym->small_bytes.clear();
+    for (auto& L : S.levels) {
+      double sb = 0;
+      sym->small_off.push_back((int32_t)sl.size());
+      for (int32_t s : L.snodes)
+        if (solve_small(s)) {
+          sl.push_back(s);
+          const double d = S.front_order(s), sc = S.ncols(s);
+          sb += 8.0 * (sc * d - sc * (sc - 1) / 2);
+        }
+      sym->small_cnt.push_back((int32_t)sl.size() - sym->small_off.back());
+      sym->small_bytes.push_back(sb);
+      sym->big_off.push_back((int32_t)sl.size());
+      for (int32_t s : L.snodes)
+        if (!solve_small(s)) sl.push_back(s);
+      sym->big_cnt.push_back((int32_t)sl.size() - sym->big_off.back());
+    }
+    GMRFB_CU(ctx, sym->d_solve_lists.upload(sl, st));
+  }
   {
     std::vector<Task> tasks;
     sym->solve_levels.assign(S.levels.size(), gmrfb_sym::SolveLevel());
@@ -340,7 +364,8 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
       const auto& sn = S.levels[l].snodes;
       auto& SL = sym->solve_levels[l];
       int maxs = 0;
-      for (int32_t s : sn) maxs = std::max(maxs, S.ncols(s));
+      for (int32_t s : sn)
+        if (!solve_small(s)) maxs = std::max(maxs, S.ncols(s));
       int nsteps = cdiv(maxs, 64);
       for (int k = 0; k < nsteps; k++) {
         Launch Lf{};
@@ -350,7 +375,7 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
         // forward step k: CTAs over the rows below block k (at least one CTA to solve and publish the block)
         for (int32_t s : sn) {
           int sc = S.ncols(s), d = S.front_order(s);
-          if (k * 64 >= sc) continue;
+          if (k * 64 >= sc || solve_small(s)) continue;
           int nb = std::min(64, sc - k * 64);
           Task t = base_task(s, k);
           t.tile0 = Lf.grid;
@@ -367,7 +392,7 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
         Lb.task0 = (int32_t)tasks.size();
         for (int32_t s : sn) {
           int sc = S.ncols(s);
-          if (k * 64 >= sc) continue;
+          if (k * 64 >= sc || solve_small(s)) continue;
           int nb = std::min(64, sc - k * 64);
           Task t = base_task(s, k);
           t.tile0 = Lb.grid;
@@ -385,7 +410,7 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
       Lr.task0 = (int32_t)tasks.size();
       for (int32_t s : sn) {
         int sc = S.ncols(s), d = S.front_order(s), r = d - sc;
-        if (r <= 0) continue;
+        if (r <= 0 || solve_small(s)) continue;
         Task t = base_task(s, 0);
         t.tile0 = Lr.grid;
         tasks.push_back(t);
@@ -611,15 +636,16 @@ gmrfb_status sweep_fwd(gmrfb_fac* fac, double* w, double* y, int nr) {
   const int64_t n = sym->S.n;
   const int nlev = (int)sym->S.levels.size();
   for (int l = 0; l < nlev; l++) {
-    int cnt = sym->level_off[l + 1] - sym->level_off[l];
-    if (l > 0) {
-      ProfScope ps(ctx, PK_FWD_ASM, 0, sym->level_vec_bytes[l] * nr, cnt, cnt);
-      GMRFB_CU(ctx, launch_fwd_assemble(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt,
-                                        sym->d_child_idx.p, sym->d_relmap.p, w, n, fac->uvec.p, ctx->stream));
+    if (sym->small_cnt[l] > 0) {  // fused: children's contributions, substitution and update vector by one warp each
+      ProfScope ps(ctx, PK_FWD_SMALL, 0, sym->small_bytes[l], sym->small_cnt[l], sym->small_cnt[l]);
+      GMRFB_CU(ctx, launch_fwd_small(sym->d_snodes.p, sym->d_solve_lists.p + sym->small_off[l], sym->small_cnt[l],
+                                     sym->d_child_idx.p, sym->d_relmap.p, fac->arena.p, w, y, n, fac->uvec.p, nr, ctx->stream));
       ctx->launches++;
-    } else {
-      // leaves have no children: their update vectors start from zero
-      GMRFB_CU(ctx, launch_fwd_assemble(sym->d_snodes.p, sym->d_level_lists.p + sym->level_off[l], cnt,
+    }
+    if (sym->big_cnt[l] > 0) {
+      // leaves have no children: the same kernel just zeroes their update vectors
+      ProfScope ps(ctx, PK_FWD_ASM, 0, 0, sym->big_cnt[l], sym->big_cnt[l]);
+      GMRFB_CU(ctx, launch_fwd_assemble(sym->d_snodes.p, sym->d_solve_lists.p + sym->big_off[l], sym->big_cnt[l],
                                         sym->d_child_idx.p, sym->d_relmap.p, w, n, fac->uvec.p, ctx->stream));
       ctx->launches++;
     }
@@ -651,6 +677,12 @@ gmrfb_status sweep_bwd(gmrfb_fac* fac, double* t, double* xs, int nr) {
       ProfScope ps(ctx, PK_BWD_LEVEL, L.flops * nr, L.bytes, L.grid, L.ntasks);
       GMRFB_CU(ctx, launch_bwd_step(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, t, xs, n,
                                     fac->partial.p, nr, ctx->stream));
+      ctx->launches++;
+    }
+    if (sym->small_cnt[l] > 0) {
+      ProfScope ps(ctx, PK_BWD_SMALL, 0, sym->small_bytes[l], sym->small_cnt[l], sym->small_cnt[l]);
+      GMRFB_CU(ctx, launch_bwd_small(sym->d_snodes.p, sym->d_solve_lists.p + sym->small_off[l], sym->small_cnt[l],
+                                     sym->d_rows.p, fac->arena.p, t, xs, n, nr, ctx->stream));
       ctx->launches++;
     }
   }

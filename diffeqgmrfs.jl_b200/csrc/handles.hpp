@@ -12,6 +12,11 @@ struct gmrfb_sym {
   gmrfb::DevBuf<int32_t> d_relmap, d_rows, d_perm, d_post, d_child_idx, d_level_lists, d_sparent;
   gmrfb::DevBuf<gmrfb::SnodeDesc> d_snodes;
   std::vector<int32_t> level_off, level_maxd;
+  // solves: per level, the supernodes solved by the fused one-warp kernels (fronts of order <= SOLVE_SMALL_MAX) and the
+  // others (assemble / block-step / R-part launches); offsets into d_solve_lists
+  gmrfb::DevBuf<int32_t> d_solve_lists;
+  std::vector<int32_t> small_off, small_cnt, big_off, big_cnt;
+  std::vector<double> small_bytes;
   std::vector<double> level_bytes, level_vec_bytes, level_flops;  // algorithmic work of one solve sweep per level
   int64_t uvec_rows = 0;
   gmrfb::DevPlan factor_plan, selinv_plan;

@@ -172,6 +172,169 @@ __global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ t
   }
 }
 
+// ------------------------------------------------------------------ fused solves of small supernodes ----
+// Supernodes whose front has order d <= SOLVE_SMALL_MAX (the large majority: 31 of 38 thousand on the 1M-node mesh,
+// a quarter of the factor's bytes) are solved by ONE WARP each, the whole panel [L11; L21] streamed once, column
+// by column, with the working vector (x_J on top of u_J) in shared memory:
+//   forward : v = [x_J; 0] + contributions of the children's update vectors (fixed order);
+//             for c = 0..s-1:  y_c = v_c / L_cc,  v_i -= L_ic y_c (i > c);      u_J = v[s..d)
+//   backward: v = [t_J; x[rows of R]];
+//             for c = s-1..0:  x_c = (v_c - sum_{i>c} L_ic v_i) / L_cc
+// This replaces, for these supernodes, the assemble / block-step / R-part launches, whose CTAs spent their time on a
+// 64-step substitution executed by one of their four warps.  Column c+1 is loaded while column c is applied.
+constexpr int SS_ROWS = (SOLVE_SMALL_MAX + 31) / 32;  // front rows per lane
+constexpr int SS_WARPS = 4;
+
+template <int NRC>
+__global__ void __launch_bounds__(32 * SS_WARPS) k_fwd_small(const SnodeDesc* __restrict__ sd,
+                                                             const int32_t* __restrict__ list, int count,
+                                                             const int32_t* __restrict__ child_idx,
+                                                             const int32_t* __restrict__ relmap,
+                                                             const double* __restrict__ F, double* __restrict__ w,
+                                                             double* __restrict__ ysol, int64_t ldx,
+                                                             double* __restrict__ uvec, int nr) {
+  __shared__ double sv[SS_WARPS][NRC][SOLVE_SMALL_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * SS_WARPS + warp;
+  if (idx >= count) return;
+  const SnodeDesc D = sd[list[idx]];
+  const int d = D.d, s = D.s, r = d - s, ld = D.ld;
+  const double* __restrict__ Fj = F + D.foff;
+  double(*v)[SOLVE_SMALL_MAX] = sv[warp];
+  // first column's values are requested before anything else
+  double lnext[SS_ROWS];
+#pragma unroll
+  for (int t = 0; t < SS_ROWS; t++) {
+    const int i = lane + 32 * t;
+    lnext[t] = (i < d) ? Fj[i] : 0.0;
+  }
+  for (int i = lane; i < d; i += 32)
+#pragma unroll
+    for (int q = 0; q < NRC; q++) v[q][i] = (i < s && q < nr) ? w[D.col0 + i + q * ldx] : 0.0;
+  __syncwarp();
+  for (int ci = 0; ci < D.nchild; ci++) {
+    const SnodeDesc C = sd[child_idx[D.child0 + ci]];
+    const int rc = C.d - C.s;
+    const double* __restrict__ uc = uvec + C.uoff * NRC;
+    const int32_t* __restrict__ rel = relmap + C.rows_off + C.s;
+    for (int i = lane; i < rc; i += 32) {
+      const int p = rel[i];  // distinct rows of this front: no two lanes hit the same entry
+#pragma unroll
+      for (int q = 0; q < NRC; q++) v[q][p] += uc[i + q * rc];
+    }
+    __syncwarp();
+  }
+  for (int c = 0; c < s; c++) {
+    double lcur[SS_ROWS];
+#pragma unroll
+    for (int t = 0; t < SS_ROWS; t++) lcur[t] = lnext[t];
+    if (c + 1 < s) {
+      const double* __restrict__ fc = Fj + (int64_t)(c + 1) * ld;
+#pragma unroll
+      for (int t = 0; t < SS_ROWS; t++) {
+        const int i = lane + 32 * t;
+        lnext[t] = (i > c && i < d) ? fc[i] : 0.0;
+      }
+    }
+    double diag = 0.0;  // L_cc sits in slot c / 32 of lane c % 32 (select chain: no dynamic register indexing)
+#pragma unroll
+    for (int t = 0; t < SS_ROWS; t++)
+      if (t == (c >> 5)) diag = lcur[t];
+    const double inv = 1.0 / __shfl_sync(0xffffffffu, diag, c & 31);
+    double yc[NRC];
+#pragma unroll
+    for (int q = 0; q < NRC; q++) yc[q] = v[q][c] * inv;
+#pragma unroll
+    for (int t = 0; t < SS_ROWS; t++) {
+      const int i = lane + 32 * t;
+      if (i > c && i < d)
+#pragma unroll
+        for (int q = 0; q < NRC; q++) v[q][i] -= lcur[t] * yc[q];
+    }
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < NRC; q++)
+        if (q < nr) ysol[D.col0 + c + q * ldx] = yc[q];
+    __syncwarp();
+  }
+  double* __restrict__ uj = uvec + D.uoff * NRC;
+  for (int i = lane; i < r; i += 32)
+#pragma unroll
+    for (int q = 0; q < NRC; q++) uj[i + q * r] = v[q][s + i];
+}
+
+template <int NRC>
+__global__ void __launch_bounds__(32 * SS_WARPS) k_bwd_small(const SnodeDesc* __restrict__ sd,
+                                                             const int32_t* __restrict__ list, int count,
+                                                             const int32_t* __restrict__ rows,
+                                                             const double* __restrict__ F, const double* __restrict__ tv,
+                                                             double* __restrict__ xsol, int64_t ldx, int nr) {
+  __shared__ double sv[SS_WARPS][NRC][SOLVE_SMALL_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * SS_WARPS + warp;
+  if (idx >= count) return;
+  const SnodeDesc D = sd[list[idx]];
+  const int d = D.d, s = D.s, ld = D.ld;
+  const double* __restrict__ Fj = F + D.foff;
+  const int32_t* __restrict__ rw = rows + D.rows_off;
+  double(*v)[SOLVE_SMALL_MAX] = sv[warp];
+  double lnext[SS_ROWS];
+  {
+    const double* __restrict__ fc = Fj + (int64_t)(s - 1) * ld;
+#pragma unroll
+    for (int t = 0; t < SS_ROWS; t++) {
+      const int i = lane + 32 * t;
+      lnext[t] = (i >= s - 1 && i < d) ? fc[i] : 0.0;
+    }
+  }
+  for (int i = lane; i < d; i += 32) {
+    const int64_t g = (i < s) ? (int64_t)D.col0 + i : (int64_t)rw[i];
+#pragma unroll
+    for (int q = 0; q < NRC; q++) v[q][i] = (q < nr) ? (i < s ? tv[g + q * ldx] : xsol[g + q * ldx]) : 0.0;
+  }
+  __syncwarp();
+  for (int c = s - 1; c >= 0; c--) {
+    double lcur[SS_ROWS];
+#pragma unroll
+    for (int t = 0; t < SS_ROWS; t++) lcur[t] = lnext[t];
+    if (c > 0) {
+      const double* __restrict__ fc = Fj + (int64_t)(c - 1) * ld;
+#pragma unroll
+      for (int t = 0; t < SS_ROWS; t++) {
+        const int i = lane + 32 * t;
+        lnext[t] = (i >= c - 1 && i < d) ? fc[i] : 0.0;
+      }
+    }
+    double dot[NRC];
+#pragma unroll
+    for (int q = 0; q < NRC; q++) dot[q] = 0.0;
+#pragma unroll
+    for (int t = 0; t < SS_ROWS; t++) {
+      const int i = lane + 32 * t;
+      if (i > c && i < d)
+#pragma unroll
+        for (int q = 0; q < NRC; q++) dot[q] += lcur[t] * v[q][i];
+    }
+#pragma unroll
+    for (int q = 0; q < NRC; q++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
+    double diag = 0.0;
+#pragma unroll
+    for (int t = 0; t < SS_ROWS; t++)
+      if (t == (c >> 5)) diag = lcur[t];
+    const double inv = 1.0 / __shfl_sync(0xffffffffu, diag, c & 31);
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < NRC; q++) v[q][c] = (v[q][c] - dot[q]) * inv;
+    __syncwarp();
+  }
+  for (int i = lane; i < s; i += 32)
+#pragma unroll
+    for (int q = 0; q < NRC; q++)
+      if (q < nr) xsol[D.col0 + i + q * ldx] = v[q][i];
+}
+
 // Backward, R part: partial[chunk][c][q] = sum_{rows of the chunk} L21[row, c] * x[rows[row]][q] for the 64 columns
 // of block kb.  One CTA = 64 columns x BR_ROWS rows; fixed-order reductions (shuffle tree, then warps in order).
 template <int NRC>
@@ -467,6 +630,21 @@ cudaError_t launch_fwd_assemble(const SnodeDesc* sd, const int32_t* list, int co
                                 const int32_t* relmap, double* x, int64_t ldx, double* uvec, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   k_fwd_assemble<SOLVE_NRC><<<count, 256, 0, st>>>(sd, list, child_idx, relmap, x, ldx, uvec);
+  return cudaGetLastError();
+}
+cudaError_t launch_fwd_small(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* child_idx,
+                             const int32_t* relmap, const double* F, double* w, double* ysol, int64_t ldx, double* uvec,
+                             int nr, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  k_fwd_small<SOLVE_NRC><<<(count + SS_WARPS - 1) / SS_WARPS, 32 * SS_WARPS, 0, st>>>(sd, list, count, child_idx, relmap, F, w,
+                                                                                        ysol, ldx, uvec, nr);
+  return cudaGetLastError();
+}
+cudaError_t launch_bwd_small(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* rows, const double* F,
+                             const double* t, double* xsol, int64_t ldx, int nr, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  k_bwd_small<SOLVE_NRC><<<(count + SS_WARPS - 1) / SS_WARPS, 32 * SS_WARPS, 0, st>>>(sd, list, count, rows, F, t, xsol, ldx,
+                                                                                        nr);
   return cudaGetLastError();
 }
 cudaError_t launch_fwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* w, double* ysol,

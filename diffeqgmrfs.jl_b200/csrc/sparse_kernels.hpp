@@ -18,6 +18,7 @@ struct SnodeDesc {
 };
 
 cudaError_t sparse_kernels_init();
+constexpr int SOLVE_SMALL_MAX = 160;  // supernodes with fronts up to this order are solved by one warp each (fused)
 constexpr int SOLVE_FS_ROWS = 128;  // rows per CTA of the forward block step
 constexpr int SOLVE_BR_ROWS = 512;  // rows per CTA of the backward R-part reduction
 cudaError_t launch_perm_gather(const double* src, int64_t lds, double* dst, int64_t ldd, const int32_t* perm,
@@ -27,6 +28,11 @@ cudaError_t launch_perm_scatter(const double* src, int64_t lds, double* dst, int
 cudaError_t launch_perm_scatter_nodemajor(const double* src, int64_t lds, double* dst, int64_t ldk,
                                           const int32_t* perm, int64_t n, int k0, int nr, cudaStream_t st);
 struct Task;
+cudaError_t launch_fwd_small(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* child_idx,
+                             const int32_t* relmap, const double* F, double* w, double* ysol, int64_t ldx, double* uvec,
+                             int nr, cudaStream_t st);
+cudaError_t launch_bwd_small(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* rows, const double* F,
+                             const double* t, double* xsol, int64_t ldx, int nr, cudaStream_t st);
 cudaError_t launch_fwd_assemble(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* child_idx,
                                 const int32_t* relmap, double* x, int64_t ldx, double* uvec, cudaStream_t st);
 cudaError_t launch_fwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* w, double* ysol,

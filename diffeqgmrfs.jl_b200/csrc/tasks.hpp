@@ -74,6 +74,8 @@ enum : int32_t {
   PK_PERM = 24,
   PK_FWD_ASM = 25,
   PK_BWD_RPART = 26,
+  PK_FWD_SMALL = 27,
+  PK_BWD_SMALL = 28,
   PK_MAX = 32
 };
 
