@@ -309,6 +309,8 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
     sym->level_maxd.push_back(md);
   }
   GMRFB_CU(ctx, sym->d_level_lists.upload(lists, st));
+  // the factor plan comes first: the solve tasks refer to the inverse-block slots it keeps
+  build_factor_plan(S, sym->factor_plan.host);
   // ---- solve schedule ----
   auto solve_small = [&](int32_t s) { return S.front_order(s) <= SOLVE_SMALL_MAX; };
   {
@@ -358,6 +360,11 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
       t.ldc = nchunk[s];
       t.aux0 = (int32_t)(S.rptr[s] & 0xffffffff);
       t.aux1 = (int32_t)(S.rptr[s] >> 32);
+      // offset (in doubles) of the supernode's kept inverse blocks, carried in the bits of `alpha`; -1 = none
+      const int64_t ws = sym->factor_plan.host.winv_slot[s];
+      const int64_t woff = ws >= 0 ? ws * (int64_t)DINV_SLOT : -1;
+      static_assert(sizeof(double) == sizeof(int64_t), "bit cast");
+      std::memcpy(&t.alpha, &woff, sizeof(double));
       return t;
     };
     for (size_t l = 0; l < S.levels.size(); l++) {
@@ -423,7 +430,6 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
     }
     GMRFB_CU(ctx, sym->d_solve_tasks.upload(tasks, st));
   }
-  build_factor_plan(S, sym->factor_plan.host);
   GMRFB_CU(ctx, sym->factor_plan.tasks.upload(sym->factor_plan.host.tasks, st));
   sym->factor_plan.ready = true;
   sym->dev_ready = true;
@@ -652,7 +658,7 @@ gmrfb_status sweep_fwd(gmrfb_fac* fac, double* w, double* y, int nr) {
     for (const Launch& L : sym->solve_levels[l].fwd_steps) {
       ProfScope ps(ctx, PK_FWD_LEVEL, L.flops * nr, L.bytes, L.grid, L.ntasks);
       GMRFB_CU(ctx, launch_fwd_step(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, w, y, n,
-                                    fac->uvec.p, nr, ctx->stream));
+                                    fac->uvec.p, nr, fac->dinv.p, ctx->stream));
       ctx->launches++;
     }
   }
@@ -676,7 +682,7 @@ gmrfb_status sweep_bwd(gmrfb_fac* fac, double* t, double* xs, int nr) {
       const Launch& L = SL.bwd_steps[k];
       ProfScope ps(ctx, PK_BWD_LEVEL, L.flops * nr, L.bytes, L.grid, L.ntasks);
       GMRFB_CU(ctx, launch_bwd_step(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, t, xs, n,
-                                    fac->partial.p, nr, ctx->stream));
+                                    fac->partial.p, nr, fac->dinv.p, ctx->stream));
       ctx->launches++;
     }
     if (sym->small_cnt[l] > 0) {
@@ -810,9 +816,11 @@ static gmrfb_status selinv_run(gmrfb_fac* fac) {
   if (!fac->zarena.p) GMRFB_CU(ctx, fac->zarena.alloc(fac->arena.n));
   if (!fac->zdiag.p) GMRFB_CU(ctx, fac->zdiag.alloc((size_t)std::max<int64_t>(sym->S.n, 1)));
   if (!fac->zwork.p) GMRFB_CU(ctx, fac->zwork.alloc((size_t)std::max<int64_t>(sym->selinv_plan.host.scratch, 1)));
-  if ((int64_t)fac->dinv.n < sym->selinv_plan.host.dinv) GMRFB_CU(ctx, fac->dinv.alloc((size_t)sym->selinv_plan.host.dinv));
+  // the selected inversion has its own inverse-block scratch: fac->dinv keeps the factor's inverses for the solves
+  if ((int64_t)fac->dinv_sel.n < sym->selinv_plan.host.dinv)
+    GMRFB_CU(ctx, fac->dinv_sel.alloc((size_t)std::max<int64_t>(sym->selinv_plan.host.dinv, 1)));
   Arenas ar{{fac->arena.p, fac->zarena.p, fac->zwork.p, nullptr}};
-  ar.dinv = fac->dinv.p;
+  ar.dinv = fac->dinv_sel.p;
   LaunchAux aux;
   aux.d_info = ctx->d_info;
   aux.d_relmap = sym->d_relmap.p;

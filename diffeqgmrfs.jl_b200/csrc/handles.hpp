@@ -33,7 +33,7 @@ struct gmrfb_sym {
 struct gmrfb_fac {
   gmrfb_ctx* ctx = nullptr;
   gmrfb_sym* sym = nullptr;
-  gmrfb::DevBuf<double> arena, zarena, zwork, zdiag, nzval, xwork, ywork, bwork, owork, uvec, partial, dinv;
+  gmrfb::DevBuf<double> arena, zarena, zwork, zdiag, nzval, xwork, ywork, bwork, owork, uvec, partial, dinv, dinv_sel;
   bool factored = false, z_valid = false, logdet_valid = false;
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_column = -1;

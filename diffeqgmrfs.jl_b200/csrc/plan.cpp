@@ -89,6 +89,8 @@ struct FactorProb {
   int arena;
   int64_t off;
   int ld, d, s, col0;
+  int64_t slot0 = -1;  // >= 0: the inverses of this front's 64x64 diagonal blocks are kept in slots slot0 + j/64
+                       // (the solves apply them); -1: transient scratch slots, reused by the next panel step
 };
 
 // Recursive blocking: columns [j0, j1) of every front (all earlier updates applied) are factorised as
@@ -103,7 +105,8 @@ static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorPr
       for (auto& p : probs) {
         if (j0 >= p.s) continue;
         int nb = std::min(NB, p.s - j0);
-        add_potrf(B, P, p.arena, p.off + (int64_t)j0 * p.ld + j0, p.ld, nb, p.col0 + j0, slot++, false);
+        add_potrf(B, P, p.arena, p.off + (int64_t)j0 * p.ld + j0, p.ld, nb, p.col0 + j0,
+                  p.slot0 >= 0 ? p.slot0 + j0 / NB : slot++, false);
       }
     }
     B.end();
@@ -114,7 +117,8 @@ static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorPr
         if (j0 >= p.s) continue;
         int nb = std::min(NB, p.s - j0);
         int row0 = j0 + nb;
-        add_trsm(B, P, slot++, p.arena, p.off + (int64_t)j0 * p.ld + row0, p.ld, p.d - row0, nb);
+        add_trsm(B, P, p.slot0 >= 0 ? p.slot0 + j0 / NB : slot++, p.arena, p.off + (int64_t)j0 * p.ld + row0, p.ld,
+                 p.d - row0, nb);
       }
     }
     B.end();
@@ -321,6 +325,8 @@ void plan_trsm_rln(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, i
 // ------------------------------------------------------------------------------------ sparse factor ----
 void build_factor_plan(const Symbolic& S, Plan& P) {
   PlanBuilder B(P);
+  P.winv_slot.assign(S.nsuper, -1);
+  P.kept_slots = 0;
   for (size_t lev = 0; lev < S.levels.size(); lev++) {
     const auto& all = S.levels[lev].snodes;
     // small fronts: one fused shared-memory kernel launch per size class
@@ -380,9 +386,16 @@ void build_factor_plan(const Symbolic& S, Plan& P) {
       B.end();
     }
     // 2. partial factorisation of every front of the level
+    // the inverses of the 64x64 diagonal blocks are kept (one slot each) for the triangular solves
     std::vector<FactorProb> probs;
     probs.reserve(sn.size());
-    for (int32_t s : sn) probs.push_back({AR_FRONT, S.foff[s], S.ld[s], S.front_order(s), S.ncols(s), S.sptr[s]});
+    for (int32_t s : sn) {
+      FactorProb fp{AR_FRONT, S.foff[s], S.ld[s], S.front_order(s), S.ncols(s), S.sptr[s]};
+      fp.slot0 = P.kept_slots;
+      P.winv_slot[s] = P.kept_slots;
+      P.kept_slots += cdiv(S.ncols(s), NB);
+      probs.push_back(fp);
+    }
     plan_partial_factor_batch(B, P, probs, 0);
   }
 }

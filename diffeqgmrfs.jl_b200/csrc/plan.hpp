@@ -13,6 +13,10 @@ struct Plan {
   int64_t scratch = 0;  // doubles of scratch arena (AR_WORK) the plan needs
   int64_t dinv = 0;     // doubles of inverse-block scratch (Arenas::dinv) the plan needs
   double flops = 0;  // floating-point operations of the GEMM/SYRK/TRSM/POTRF tasks (useful work, not tile padding)
+  // sparse factor plan: first kept inverse-block slot of every supernode factored by the blocked path (-1: none; the
+  // fused small-front kernels keep no inverses), and the number of kept slots
+  std::vector<int64_t> winv_slot;
+  int64_t kept_slots = 0;
 };
 
 // Incremental builder: open a launch, append tasks with their CTA counts, close it (empty launches vanish).

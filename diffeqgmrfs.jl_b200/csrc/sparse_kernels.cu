@@ -97,7 +97,8 @@ template <int NRC>
 __global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ tasks, int ntasks,
                                                       const double* __restrict__ F, double* __restrict__ x,
                                                       double* __restrict__ ysol, int64_t ldx,
-                                                      double* __restrict__ uvec, int nr) {
+                                                      double* __restrict__ uvec, int nr,
+                                                      const double* __restrict__ dinv) {
   __shared__ double Ld[64 * DLD];
   __shared__ double invd[64];
   __shared__ double yk[NRC][64];
@@ -119,6 +120,44 @@ __global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ t
 #pragma unroll
     for (int c = 0; c < 64; c++) f[c] = (c < nb) ? fr[(int64_t)c * ld] : 0.0;
   }
+  // the factorisation kept W_kk = L_kk^{-1} of this diagonal block (task field alpha): y_k = W_kk x_k is a parallel
+  // product instead of a 64-step substitution chain
+  const int64_t woff = __double_as_longlong(T.alpha);
+  if (woff >= 0) {
+    const double* __restrict__ Wk = dinv + woff + (int64_t)T.K * DINV_SLOT;  // nb x nb, leading dimension 64
+    for (int e = tid; e < 64 * 64; e += FS_ROWS) {
+      const int i = e & 63, j = e >> 6;
+      Ld[j * DLD + i] = (i < nb && j <= i) ? Wk[i + j * 64] : 0.0;
+    }
+    for (int e = tid; e < NRC * 64; e += FS_ROWS) {
+      const int q = e >> 6, j = e & 63;
+      yk[q][j] = (q < nr && j < nb) ? x[col0 + k0 + j + q * ldx] : 0.0;  // x_k staged; overwritten by y_k below
+    }
+    __syncthreads();
+    double part[NRC];
+#pragma unroll
+    for (int q = 0; q < NRC; q++) part[q] = 0.0;
+    const int i = tid & 63, j0 = (tid >> 6) * 32;
+    for (int j = j0; j < j0 + 32; j++) {
+      const double wv = Ld[j * DLD + i];
+#pragma unroll
+      for (int q = 0; q < NRC; q++) part[q] += wv * yk[q][j];
+    }
+    __syncthreads();  // all reads of x_k done
+    if (tid >= 64)
+#pragma unroll
+      for (int q = 0; q < NRC; q++) Ld[q * DLD + i] = part[q];  // upper halves parked in Ld (free now)
+    __syncthreads();
+    if (tid < 64) {
+#pragma unroll
+      for (int q = 0; q < NRC; q++) {
+        const double yv = part[q] + Ld[q * DLD + i];
+        yk[q][i] = yv;
+        if (chunk == 0 && q < nr && i < nb) ysol[col0 + k0 + i + q * ldx] = yv;
+      }
+    }
+    __syncthreads();
+  } else {
   for (int e = tid; e < nb * nb; e += FS_ROWS) {
     int i = e % nb, j = e / nb;
     if (i >= j) Ld[j * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + j) * ld];
@@ -153,6 +192,7 @@ __global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ t
     }
   }
   __syncthreads();
+  }
   if (row >= d) return;
   double acc[NRC];
 #pragma unroll
@@ -409,7 +449,8 @@ template <int NRC>
 __global__ void __launch_bounds__(128) k_bwd_step(const Task* __restrict__ tasks, int ntasks,
                                                   const double* __restrict__ F, double* __restrict__ x,
                                                   double* __restrict__ xsol, int64_t ldx,
-                                                  const double* __restrict__ partial, int nr) {
+                                                  const double* __restrict__ partial, int nr,
+                                                  const double* __restrict__ dinv) {
   __shared__ double Ld[64 * DLD];
   __shared__ double invd[64];
   __shared__ double xk[NRC][64];
@@ -432,6 +473,50 @@ __global__ void __launch_bounds__(128) k_bwd_step(const Task* __restrict__ tasks
 #pragma unroll
     for (int u = 0; u < 32; u++) f[u] = (r0 + u < nb) ? fc[r0 + u] : 0.0;
   }
+  const int64_t woff = __double_as_longlong(T.alpha);
+  if (woff >= 0) {
+    // x_k = W_kk' t_k with the stored inverse of the diagonal block (see k_fwd_step)
+    const double* __restrict__ Wk = dinv + woff + (int64_t)k * DINV_SLOT;
+    for (int e = tid; e < 64 * 64; e += 128) {
+      const int i = e & 63, jj = e >> 6;
+      Ld[jj * DLD + i] = (i < nb && jj <= i) ? Wk[i + jj * 64] : 0.0;
+    }
+    // t_k = x_k - sum over the R-part chunks (fixed order)
+    for (int e = tid; e < NRC * 64; e += 128) {
+      const int q = e >> 6, i = e & 63;
+      double v = 0.0;
+      if (q < nr && i < nb) {
+        v = x[col0 + k0 + i + q * ldx];
+        const double* __restrict__ pj = partial + T.c;
+        for (int ch = 0; ch < nchunk; ch++) v -= pj[(int64_t)ch * s * NRC + (int64_t)(k0 + i) * NRC + q];
+      }
+      xk[q][i] = v;
+    }
+    __syncthreads();
+    double part[NRC];
+#pragma unroll
+    for (int q = 0; q < NRC; q++) part[q] = 0.0;
+    const int jc = tid & 63, i0 = (tid >> 6) * 32;
+    for (int i = i0; i < i0 + 32; i++) {
+      const double wv = Ld[jc * DLD + i];  // W[i, jc]: column jc of W, conflict-free through the padding
+#pragma unroll
+      for (int q = 0; q < NRC; q++) part[q] += wv * xk[q][i];
+    }
+    __syncthreads();
+    if (tid >= 64)
+#pragma unroll
+      for (int q = 0; q < NRC; q++) half[jc][q] = part[q];
+    __syncthreads();
+    if (tid < 64) {
+#pragma unroll
+      for (int q = 0; q < NRC; q++) {
+        const double xv = part[q] + half[jc][q];
+        xk[q][jc] = xv;
+        if (j == k && q < nr && jc < nb) xsol[col0 + k0 + jc + q * ldx] = xv;
+      }
+    }
+    __syncthreads();
+  } else {
   for (int e = tid; e < nb * nb; e += 128) {
     int i = e % nb, jj = e / nb;
     if (i >= jj) Ld[jj * DLD + i] = Fj[(k0 + i) + (int64_t)(k0 + jj) * ld];
@@ -471,6 +556,7 @@ __global__ void __launch_bounds__(128) k_bwd_step(const Task* __restrict__ tasks
     }
   }
   __syncthreads();
+  }
   if (j == k) return;
   double acc[NRC];
 #pragma unroll
@@ -648,9 +734,9 @@ cudaError_t launch_bwd_small(const SnodeDesc* sd, const int32_t* list, int count
   return cudaGetLastError();
 }
 cudaError_t launch_fwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* w, double* ysol,
-                            int64_t ldx, double* uvec, int nr, cudaStream_t st) {
+                            int64_t ldx, double* uvec, int nr, const double* dinv, cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
-  k_fwd_step<SOLVE_NRC><<<grid, FS_ROWS, 0, st>>>(tasks, ntasks, F, w, ysol, ldx, uvec, nr);
+  k_fwd_step<SOLVE_NRC><<<grid, FS_ROWS, 0, st>>>(tasks, ntasks, F, w, ysol, ldx, uvec, nr, dinv);
   return cudaGetLastError();
 }
 cudaError_t launch_bwd_rpart(const Task* tasks, int ntasks, int grid, const double* F, const int32_t* rows,
@@ -660,9 +746,9 @@ cudaError_t launch_bwd_rpart(const Task* tasks, int ntasks, int grid, const doub
   return cudaGetLastError();
 }
 cudaError_t launch_bwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* t, double* xsol,
-                            int64_t ldx, const double* partial, int nr, cudaStream_t st) {
+                            int64_t ldx, const double* partial, int nr, const double* dinv, cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
-  k_bwd_step<SOLVE_NRC><<<grid, 128, 0, st>>>(tasks, ntasks, F, t, xsol, ldx, partial, nr);
+  k_bwd_step<SOLVE_NRC><<<grid, 128, 0, st>>>(tasks, ntasks, F, t, xsol, ldx, partial, nr, dinv);
   return cudaGetLastError();
 }
 

@@ -35,12 +35,13 @@ cudaError_t launch_bwd_small(const SnodeDesc* sd, const int32_t* list, int count
                              const double* t, double* xsol, int64_t ldx, int nr, cudaStream_t st);
 cudaError_t launch_fwd_assemble(const SnodeDesc* sd, const int32_t* list, int count, const int32_t* child_idx,
                                 const int32_t* relmap, double* x, int64_t ldx, double* uvec, cudaStream_t st);
+// dinv: the factor's stored inverses of 64x64 diagonal blocks (tasks whose `alpha` holds an offset >= 0 use them)
 cudaError_t launch_fwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* w, double* ysol,
-                            int64_t ldx, double* uvec, int nr, cudaStream_t st);
+                            int64_t ldx, double* uvec, int nr, const double* dinv, cudaStream_t st);
 cudaError_t launch_bwd_rpart(const Task* tasks, int ntasks, int grid, const double* F, const int32_t* rows,
                              const double* x, int64_t ldx, double* partial, int nr, cudaStream_t st);
 cudaError_t launch_bwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* t, double* xsol,
-                            int64_t ldx, const double* partial, int nr, cudaStream_t st);
+                            int64_t ldx, const double* partial, int nr, const double* dinv, cudaStream_t st);
 cudaError_t launch_spmv_rows(int64_t nrows, const int64_t* ptr, const int32_t* idx, const double* val,
                              const double* x, double* y, double alpha, double beta, cudaStream_t st);
 cudaError_t launch_rbmc(int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, const double* X,
