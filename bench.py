@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--nx", type=int, default=1001, help="mesh nodes per side (1001 -> 1,002,001 nodes)")
     ap.add_argument("--nx-sample", dest="nx_sample", type=int, default=0, help="(unused; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=4,
                     help="independent posterior problems in flight per GPU (one CUDA stream each)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -88,9 +88,15 @@ __device__ __forceinline__ int chol8(double (&D)[8][8], double (&invd)[8]) {
 // The grouped DMMA GEMM engine lives in gemm_engine.cuh (k_gemm2<TA, TB, CFG>); two tile configurations are
 // instantiated and chosen per launch by the plan builder (Launch::cfg):
 //   GCFG_BIG   128x64 tiles, 8 warps, 3 stages, 2 CTAs/SM  - large, regular problems (33.5 TFLOP/s at n=4736, K=4096)
-//   GCFG_SMALL  64x64 tiles, 8 warps, 4 stages, 3 CTAs/SM  - launches with few or ragged tiles
+//   GCFG_SMALL  64x64 tiles, 8 warps, 2 stages, 3 CTAs/SM  - launches with few or ragged tiles
+// Two stages, not more: on batched launches over ragged fronts (K = 30 ... 600) the 2-stage pipeline is 6-18 % faster
+// than the 4-stage one and no slower at K = 4096 (35 KB instead of 70 KB of shared memory per CTA leaves the L1 to the
+// read-modify-write of the C tiles; tools/probe/gemm_batched_probe.cu, profiles/r01_gemm_batched_probe.md).
+#ifndef GMRFB_SMALL_STAGES
+#define GMRFB_SMALL_STAGES 2
+#endif
 using GemmBig = GemmCfg<GEMM_TILE_M[GCFG_BIG], GEMM_TILE_N[GCFG_BIG], 4, 2, 16, 3, 2>;
-using GemmSmall = GemmCfg<GEMM_TILE_M[GCFG_SMALL], GEMM_TILE_N[GCFG_SMALL], 4, 2, 16, 4, 3>;
+using GemmSmall = GemmCfg<GEMM_TILE_M[GCFG_SMALL], GEMM_TILE_N[GCFG_SMALL], 4, 2, 16, GMRFB_SMALL_STAGES, 3>;
 
 // -------------------------------------------------------------------------------------------- POTRF ----
 // Cholesky AND inverse of an n x n (n <= 64) diagonal block, one CTA (8 warps) per block, everything in shared

@@ -12,7 +12,7 @@ namespace gmrfb {
 int gemm_big_min() {
   static const int v = [] {
     const char* e = std::getenv("GMRFB_GEMM_BIG_MIN");  // tuning aid: 0 = always 128x64 tiles, huge = always 64x64
-    return e ? std::atoi(e) : 128;
+    return e ? std::atoi(e) : (1 << 30);
   }();
   return v;
 }

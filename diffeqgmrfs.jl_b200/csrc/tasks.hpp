@@ -138,10 +138,10 @@ inline bool uses_cta_map(int kind) {
 inline bool is_gemm_kind(int kind) {
   return kind == LK_GEMM_NT || kind == LK_GEMM_NN || kind == LK_GEMM_TN || kind == LK_GEMM_TT;
 }
-// Tile configuration of a GEMM launch: 128x64 tiles when the launch consists of large regular problems (on average
-// at least gemm_big_min() 128x64 tiles per task, i.e. about 1024 x 1024 results), 64x64 tiles otherwise: batched
-// launches over many ragged fronts waste less of a small tile, and on the bench workload the small tile is never
-// slower below that size (gpurun sweep of GMRFB_GEMM_BIG_MIN, profiles/r01_gemm_engine.md).
+// Tile configuration of a GEMM launch.  With the 2-stage 64x64 configuration the small tile is at least as fast as the
+// 128x64 one on every launch of the bench workload (batched ragged fronts: 7-12 % faster; one 4736^2 x 4096 product:
+// 33.4 against 33.5 TFLOP/s; profiles/r01_gemm_batched_probe.md), so the 128x64 configuration is only chosen when
+// GMRFB_GEMM_BIG_MIN asks for it (launches averaging at least that many 128x64 tiles per task); default: never.
 int gemm_big_min();
 inline int choose_gemm_cfg(int big_tiles, int ntasks) {
   return (ntasks > 0 && big_tiles / ntasks >= gemm_big_min()) ? GCFG_BIG : GCFG_SMALL;
