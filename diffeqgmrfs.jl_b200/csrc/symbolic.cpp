@@ -8,6 +8,8 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -433,7 +435,7 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
     std::iota(S.perm_user.begin(), S.perm_user.end(), 0);
   } else if (opt.ordering_kind == 2) {
     if (opt.coords && (opt.coord_dim < 1 || opt.coord_dim > 3)) return "coord_dim must be 1..3";
-    nested_dissection(n, xadj, adj, opt.nd_leaf, opt.coords ? opt.coord_dim : 0, opt.coords, S.perm_user);
+    nested_dissection(n, xadj, adj, opt.nd_leaf > 0 ? opt.nd_leaf : (std::getenv("GMRFB_ND_LEAF") ? std::atoi(std::getenv("GMRFB_ND_LEAF")) : 0), opt.coords ? opt.coord_dim : 0, opt.coords, S.perm_user);
   } else {
     return "unknown ordering kind";
   }
@@ -514,8 +516,16 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
   };
   std::vector<SN> sn;
   sn.reserve(n / 2 + 1);
-  const int relax_small = opt.relax_small > 0 ? opt.relax_small : 16;
-  const double relax_zeros = opt.relax_zeros > 0 ? opt.relax_zeros : 0.0;  // 0 => tiered default below
+  // tuning aids (only when the caller leaves the options at their defaults): GMRFB_RELAX_SMALL, GMRFB_RELAX_ZEROS,
+  // GMRFB_RELAX_TIERS="z32,z64,z128,zbig" (zero fractions of the tiered default rule)
+  auto env_num = [](const char* name, double dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atof(e) : dflt;
+  };
+  const int relax_small = opt.relax_small > 0 ? opt.relax_small : (int)env_num("GMRFB_RELAX_SMALL", 16);
+  const double relax_zeros = opt.relax_zeros > 0 ? opt.relax_zeros : env_num("GMRFB_RELAX_ZEROS", 0.0);  // 0 => tiered rule
+  double tier32 = 0.5, tier64 = 0.3, tier128 = 0.05, tierbig = 0.05;  // tier64: B200 sweep, profiles/r01_amalgamation_sweep.md
+  if (const char* e = std::getenv("GMRFB_RELAX_TIERS")) std::sscanf(e, "%lf,%lf,%lf,%lf", &tier32, &tier64, &tier128, &tierbig);
   auto trapezoid = [](int64_t s, int64_t d) { return s * d - s * (s - 1) / 2; };
   for (int32_t k = 0; k < n;) {
     int32_t f = k;
@@ -541,11 +551,13 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
       else if (relax_zeros > 0)
         merge = zfrac <= relax_zeros;
       else if (s_new <= 32)
-        merge = zfrac <= 0.5;
+        merge = zfrac <= tier32;
       else if (s_new <= 64)
-        merge = zfrac <= 0.15;
+        merge = zfrac <= tier64;
+      else if (s_new <= 128)
+        merge = zfrac <= tier128;
       else
-        merge = zfrac <= 0.05;
+        merge = zfrac <= tierbig;
       if (!merge) break;
       cur.first = c.first;
       cur.true_nnz = truen;
