@@ -400,6 +400,327 @@ static std::string build_adjacency(int64_t n, const int64_t* colptr, const int64
   return "";
 }
 
+// ------------------------------------------------------------------------------- approximate minimum degree ----
+// Approximate minimum degree ordering on the quotient graph (Amestoy, Davis & Duff, SIAM J. Matrix Anal. Appl. 17
+// (1996) 886-905), restated from the paper: elements absorb the eliminated variables' adjacency, external degrees
+// are bounded by  d_i <- min(n - k, d_i + |L_p \ i|, |A_i \ i| + |L_p \ i| + sum_{e in E_i \ p} |L_e \ L_p|)
+// with the |L_e \ L_p| obtained in one pass by the timestamp trick, indistinguishable variables are merged into
+// supervariables (hash buckets), variables whose adjacency is covered by the new element are mass-eliminated and
+// elements that became subsets of it are absorbed (aggressive absorption).  No dense-row handling: GMRF precision
+// matrices have bounded row degree.  This is the reordering the reference gets from CHOLMOD's default `cholesky(A)`
+// call (no `perm`); ties are broken by this implementation's list order, not SuiteSparse's.
+namespace {
+
+struct AmdWork {
+  int32_t n;
+  std::vector<int32_t> iw;             // adjacency storage: for a variable its elements then its variables; for an element its variables
+  std::vector<int64_t> pe;             // start of node i's list in iw, or -1 when the node is dead (absorbed)
+  std::vector<int32_t> len, elen;      // list length; number of leading elements (variables only)
+  std::vector<int32_t> nv;             // supervariable size (0: absorbed variable; negative: currently in L_p)
+  std::vector<int32_t> degree;         // approximate external degree (variables) / |L_e| (elements)
+  std::vector<int32_t> parent;         // absorbed node -> node that absorbed it
+  std::vector<char> is_elem;
+  std::vector<int64_t> w;              // timestamps
+  std::vector<int32_t> head, next, last;  // degree lists
+  int64_t pfree = 0;
+
+  // compact the live lists to the front of iw (no list is being scanned when this runs)
+  void collect() {
+    for (int32_t i = 0; i < n; i++) {
+      if (pe[i] >= 0 && len[i] > 0) {
+        const int64_t p = pe[i];
+        pe[i] = iw[p];       // save the first entry
+        iw[p] = -(i + 1);    // mark the head of i's list
+      } else if (pe[i] >= 0) {
+        pe[i] = -2;  // live node with an empty list: re-pointed below
+      }
+    }
+    int64_t dst = 0, src = 0;
+    while (src < pfree) {
+      const int32_t v = iw[src++];
+      if (v < 0) {
+        const int32_t i = -v - 1;
+        iw[dst] = (int32_t)pe[i];
+        pe[i] = dst++;
+        for (int32_t k = 1; k < len[i]; k++) iw[dst++] = iw[src++];
+      }
+    }
+    for (int32_t i = 0; i < n; i++)
+      if (pe[i] == -2) pe[i] = dst;
+    pfree = dst;
+  }
+  void list_remove(int32_t i) {
+    const int32_t d = degree[i];
+    if (last[i] >= 0) next[last[i]] = next[i]; else head[d] = next[i];
+    if (next[i] >= 0) last[next[i]] = last[i];
+  }
+  void list_insert(int32_t i, int32_t d) {
+    next[i] = head[d];
+    last[i] = -1;
+    if (head[d] >= 0) last[head[d]] = i;
+    head[d] = i;
+  }
+};
+
+}  // namespace
+
+void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
+               std::vector<int32_t>& perm) {
+  perm.assign(n, 0);
+  if (n == 0) return;
+  AmdWork W;
+  W.n = n;
+  const int64_t nnz = xadj[n];
+  W.iw.resize((size_t)(nnz + nnz / 4 + 2 * (int64_t)n + 16));
+  W.pe.resize(n); W.len.resize(n); W.elen.assign(n, 0); W.nv.assign(n, 1); W.degree.resize(n);
+  W.parent.assign(n, -1); W.is_elem.assign(n, 0); W.w.assign(n, 1);
+  W.head.assign(n + 1, -1); W.next.assign(n, -1); W.last.assign(n, -1);
+  std::copy(adj.begin(), adj.end(), W.iw.begin());
+  W.pfree = nnz;
+  std::vector<int32_t> pivots;  // elimination sequence of the pivot (super)variables
+  pivots.reserve(n);
+  int32_t nel = 0;
+  for (int32_t i = 0; i < n; i++) {
+    W.pe[i] = xadj[i];
+    W.len[i] = (int32_t)(xadj[i + 1] - xadj[i]);
+    W.degree[i] = W.len[i];
+  }
+  for (int32_t i = 0; i < n; i++) {
+    if (W.degree[i] == 0) {  // isolated vertex: eliminate at once
+      W.is_elem[i] = 1; W.w[i] = 0; W.pe[i] = -1; W.elen[i] = -1;
+      pivots.push_back(i);
+      nel++;
+    } else {
+      W.list_insert(i, W.degree[i]);
+    }
+  }
+  int64_t wflg = 2;
+  int32_t mindeg = 1;
+  std::vector<int32_t> lme;         // the new element's variable list
+  std::vector<int32_t> keep_e, keep_v;
+  std::vector<int32_t> hhead(n, -1), hnext(n, -1), hval(n, 0), used;  // hash buckets of this pivot
+  auto& iw = W.iw; auto& pe = W.pe; auto& len = W.len; auto& elen = W.elen; auto& nv = W.nv; auto& degree = W.degree;
+  auto& w = W.w;
+
+  while (nel < n) {
+    while (mindeg <= n && W.head[mindeg] < 0) mindeg++;
+    const int32_t me = W.head[mindeg];
+    W.list_remove(me);
+    const int32_t elenme = elen[me];
+    int32_t nvpiv = nv[me];
+    nel += nvpiv;
+    nv[me] = -nvpiv;
+    int32_t degme = 0;
+    // ---- L_me = (A_me  U  union of L_e, e in E_me) \ me ----
+    lme.clear();
+    auto take = [&](int32_t i) {
+      const int32_t nvi = nv[i];
+      if (nvi > 0) {
+        degme += nvi;
+        nv[i] = -nvi;
+        lme.push_back(i);
+        W.list_remove(i);
+      }
+    };
+    {
+      const int64_t p0 = pe[me];
+      for (int32_t k = 0; k < elenme; k++) {
+        const int32_t e = iw[p0 + k];
+        if (pe[e] < 0) continue;
+        const int64_t pj = pe[e];
+        for (int32_t t = 0; t < len[e]; t++) take(iw[pj + t]);
+        pe[e] = -1;  // element e is absorbed into me
+        W.parent[e] = me;
+        w[e] = 0;
+      }
+      for (int32_t k = elenme; k < len[me]; k++) take(iw[p0 + k]);
+    }
+    // store L_me (me's old list and the absorbed elements' lists are garbage now)
+    pe[me] = -1;
+    if (W.pfree + (int64_t)lme.size() > (int64_t)iw.size()) W.collect();
+    if (W.pfree + (int64_t)lme.size() > (int64_t)iw.size()) iw.resize((size_t)(W.pfree + lme.size() + n));
+    const int64_t pme1 = W.pfree;
+    std::copy(lme.begin(), lme.end(), iw.begin() + pme1);
+    W.pfree += (int64_t)lme.size();
+    pe[me] = pme1;
+    len[me] = (int32_t)lme.size();
+    W.is_elem[me] = 1;
+    degree[me] = degme;
+    elen[me] = -1;
+    pivots.push_back(me);
+    const int64_t pme2 = pme1 + len[me];
+    // timestamps must stay below overflow: w values are at most wflg + n
+    if (wflg > ((int64_t)1 << 60)) {
+      for (int32_t i = 0; i < n; i++) if (w[i] != 0) w[i] = 1;
+      wflg = 2;
+    }
+    // ---- scan 1: w[e] - wflg = |L_e \ L_me| for every element e adjacent to a variable of L_me ----
+    int64_t wmax = wflg;
+    for (int64_t p = pme1; p < pme2; p++) {
+      const int32_t i = iw[p];
+      const int32_t eln = elen[i];
+      if (eln <= 0) continue;
+      const int32_t nvi = -nv[i];
+      const int64_t wnvi = wflg - nvi;
+      const int64_t pi = pe[i];
+      for (int32_t k = 0; k < eln; k++) {
+        const int32_t e = iw[pi + k];
+        const int64_t we = w[e];
+        if (we >= wflg) w[e] = we - nvi;
+        else if (we != 0) {
+          w[e] = degree[e] + wnvi;
+          if (w[e] > wmax) wmax = w[e];
+        }
+      }
+    }
+    // ---- scan 2: degree update, list pruning, hashing ----
+    used.clear();
+    for (int64_t p = pme1; p < pme2; p++) {
+      const int32_t i = iw[p];
+      const int64_t p1 = pe[i];
+      const int64_t p2 = p1 + elen[i];
+      int64_t pn;
+      uint32_t hash = 0;
+      int64_t deg = 0;
+      // the pruned list gets me in front, so the survivors are gathered in a scratch first
+      keep_e.clear(); keep_v.clear();
+      for (int64_t q = p1; q < p2; q++) {
+        const int32_t e = iw[q];
+        const int64_t we = w[e];
+        if (we == 0) continue;  // absorbed earlier
+        const int64_t dext = we - wflg;
+        if (dext > 0) {
+          deg += dext;
+          keep_e.push_back(e);
+          hash += (uint32_t)e;
+        } else {  // L_e is a subset of L_me: aggressive absorption
+          pe[e] = -1;
+          W.parent[e] = me;
+          w[e] = 0;
+        }
+      }
+      const int64_t pend = p1 + len[i];
+      for (int64_t q = p2; q < pend; q++) {
+        const int32_t j = iw[q];
+        const int32_t nvj = nv[j];
+        if (nvj > 0) {  // live and outside L_me
+          deg += nvj;
+          keep_v.push_back(j);
+          hash += (uint32_t)j;
+        }
+      }
+      if (keep_e.empty() && keep_v.empty()) {
+        // mass elimination: i's adjacency is me alone
+        pe[i] = -1;
+        W.parent[i] = me;
+        const int32_t nvi = -nv[i];
+        degme -= nvi;
+        nvpiv += nvi;
+        nel += nvi;
+        nv[i] = 0;
+        elen[i] = -1;
+        continue;
+      }
+      degree[i] = (int32_t)std::min<int64_t>(degree[i], deg);
+      // new list: me, surviving elements, surviving variables (never longer than the old list: the variables of
+      // L_me that i was adjacent to, or at least one absorbed element, made room - otherwise append at pfree)
+      const int64_t newlen = 1 + (int64_t)keep_e.size() + (int64_t)keep_v.size();
+      int64_t base = p1;
+      if (newlen > len[i]) {  // cannot happen (me or an absorbed element always frees a slot); kept as a guard
+        if (W.pfree + newlen > (int64_t)iw.size()) iw.resize((size_t)(W.pfree + newlen + n));
+        base = W.pfree;
+        W.pfree += newlen;
+        pe[i] = base;
+      }
+      pn = base;
+      iw[pn++] = me;
+      for (int32_t e : keep_e) iw[pn++] = e;
+      for (int32_t j : keep_v) iw[pn++] = j;
+      elen[i] = 1 + (int32_t)keep_e.size();
+      len[i] = (int32_t)newlen;
+      const int32_t hb = (int32_t)(hash % (uint32_t)n);
+      hval[i] = (int32_t)hash;
+      if (hhead[hb] < 0) used.push_back(hb);
+      hnext[i] = hhead[hb];
+      hhead[hb] = i;
+    }
+    degree[me] = degme;
+    wflg = wmax + 1;  // every timestamp handed out in scan 1 is now in the past
+    // ---- supervariable detection inside each hash bucket ----
+    for (int32_t hb : used) {
+      for (int32_t i = hhead[hb]; i >= 0; i = hnext[i]) {
+        if (nv[i] == 0 || hnext[i] < 0) continue;
+        // mark i's list
+        wflg++;
+        const int64_t pi = pe[i];
+        for (int32_t k = 1; k < len[i]; k++) w[iw[pi + k]] = (w[iw[pi + k]] == 0 ? 0 : wflg);
+        int32_t prev = i;
+        for (int32_t j = hnext[i]; j >= 0; j = hnext[j]) {
+          bool same = nv[j] != 0 && hval[j] == hval[i] && len[j] == len[i] && elen[j] == elen[i];
+          if (same) {
+            const int64_t pj = pe[j];
+            for (int32_t k = 1; k < len[j] && same; k++) same = (w[iw[pj + k]] == wflg);
+          }
+          if (same) {  // j is indistinguishable from i
+            pe[j] = -1;
+            W.parent[j] = i;
+            nv[i] += nv[j];  // both negative: sizes add
+            nv[j] = 0;
+            elen[j] = -1;
+            hnext[prev] = hnext[j];
+          } else {
+            prev = j;
+          }
+        }
+      }
+      hhead[hb] = -1;
+    }
+    wflg += 2;
+    // ---- finalise the new element and the degrees of its variables ----
+    int64_t p = pme1;
+    const int32_t nleft = n - nel;
+    for (int64_t q = pme1; q < pme2; q++) {
+      const int32_t i = iw[q];
+      const int32_t nvi = -nv[i];
+      if (nvi <= 0) continue;  // absorbed above
+      nv[i] = nvi;
+      int64_t deg = (int64_t)degree[i] + degme - nvi;
+      deg = std::min<int64_t>(deg, nleft - nvi);
+      if (deg < 1) deg = 1;  // only possible for the last variables; keeps list 0 free for nothing special
+      if (deg > n) deg = n;
+      degree[i] = (int32_t)deg;
+      W.list_insert(i, (int32_t)deg);
+      if (deg < mindeg) mindeg = (int32_t)deg;
+      iw[p++] = i;
+    }
+    nv[me] = nvpiv;
+    len[me] = (int32_t)(p - pme1);
+    if (len[me] == 0) {
+      pe[me] = -1;
+      w[me] = 0;
+    }
+    // make sure the timestamp of the new element is a live one
+    if (len[me] > 0) w[me] = 1;
+  }
+  // ---- ordering: pivots in elimination order, each followed by the variables absorbed into it ----
+  std::vector<int32_t> rep(n, -1);
+  std::vector<int32_t> cnt_head(n, -1), cnt_next(n, -1);
+  std::vector<char> is_pivot(n, 0);
+  for (int32_t v : pivots) is_pivot[v] = 1;
+  for (int32_t i = n - 1; i >= 0; i--) {
+    if (is_pivot[i]) continue;
+    int32_t r = i;
+    while (!is_pivot[r]) r = W.parent[r];  // variables are absorbed by variables that end up as pivots or by pivots
+    cnt_next[i] = cnt_head[r];
+    cnt_head[r] = i;
+  }
+  int32_t k = 0;
+  for (int32_t v : pivots) {
+    perm[k++] = v;
+    for (int32_t i = cnt_head[v]; i >= 0; i = cnt_next[i]) perm[k++] = i;
+  }
+}
+
 std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* rowval, const int64_t* perm_in,
                             const AnalyzeOptions& opt, Symbolic& S) {
   if (n64 < 0 || n64 > (int64_t)2000000000) return "n out of range";
@@ -436,6 +757,8 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
   } else if (opt.ordering_kind == 2) {
     if (opt.coords && (opt.coord_dim < 1 || opt.coord_dim > 3)) return "coord_dim must be 1..3";
     nested_dissection(n, xadj, adj, opt.nd_leaf > 0 ? opt.nd_leaf : (std::getenv("GMRFB_ND_LEAF") ? std::atoi(std::getenv("GMRFB_ND_LEAF")) : 0), opt.coords ? opt.coord_dim : 0, opt.coords, S.perm_user);
+  } else if (opt.ordering_kind == 3) {
+    amd_order(n, xadj, adj, S.perm_user);
   } else {
     return "unknown ordering kind";
   }

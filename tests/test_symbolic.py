@@ -82,3 +82,67 @@ def test_invalid_inputs(pkg):
         pkg.Symbolic(A, perm=np.array([0, 1, 1, 3]), host_only=True)  # not a permutation
     with pytest.raises(ValueError):
         pkg.Symbolic(sp.csc_matrix(np.ones((3, 4))), host_only=True)
+
+
+# ------------------------------------------------------------------------ approximate minimum degree ----
+def _brute_force_min_degree_fill(A):
+    """Exact minimum-degree elimination on the dense pattern (ties: smallest index); returns nnz(L)."""
+    n = A.shape[0]
+    adj = [set(np.nonzero(A[:, j].toarray().ravel())[0].tolist()) - {j} for j in range(n)]
+    alive = set(range(n))
+    nnz = 0
+    while alive:
+        v = min(alive, key=lambda i: (len(adj[i]), i))
+        nb = adj[v]
+        nnz += len(nb) + 1
+        for u in nb:
+            adj[u] |= nb
+            adj[u] -= {u, v}
+        alive.remove(v)
+    return nnz
+
+
+@pytest.mark.parametrize("nx", [2, 5, 13, 40])
+def test_amd_ordering_mesh(pkg, orc, W, nx):
+    """ORDER_AMD (what `cholesky(A)` without `perm` asks CHOLMOD for): a valid permutation whose etree / column counts
+    match the oracle's symbolic analysis of the same permutation."""
+    prob = W.matern_posterior(nx, obs_frac=0.2, corr_range=0.3)
+    _check(pkg, orc, prob["Qpost"], ordering="amd")
+
+
+def test_amd_edge_patterns(pkg, orc):
+    _check(pkg, orc, sp.identity(1, format="csc"), ordering="amd")
+    _check(pkg, orc, sp.identity(50, format="csc"), ordering="amd")
+    blocks = [sp.csc_matrix(np.ones((7, 7))), sp.identity(3), sp.csc_matrix(np.ones((20, 20)))]
+    sym = _check(pkg, orc, sp.block_diag(blocks, format="csc"), ordering="amd")
+    assert sym.info.nnz_L == 7 * 8 // 2 + 3 + 20 * 21 // 2  # cliques stay cliques: no fill
+    n = 30
+    A = sp.lil_matrix((n, n))
+    A.setdiag(1.0)
+    A[0, :] = 1.0
+    A[:, 0] = 1.0  # arrow pointing the wrong way: the natural ordering fills completely, minimum degree not at all
+    sym = _check(pkg, orc, A.tocsc(), ordering="amd")
+    assert sym.info.nnz_L == 2 * n - 1
+    chain = sp.diags([np.ones(99), np.ones(100), np.ones(99)], [-1, 0, 1], format="csc")
+    sym = _check(pkg, orc, chain, ordering="amd")
+    assert sym.info.nnz_L == 199  # a tree has a perfect elimination ordering and minimum degree finds it
+    R = sp.random(200, 200, density=0.02, random_state=1, format="csc")
+    _check(pkg, orc, (R + R.T + sp.identity(200)).tocsc(), ordering="amd")
+
+
+def test_amd_fill_quality(pkg, W):
+    """Fill of the approximate-degree ordering stays close to exact minimum degree on small problems and beats the
+    natural ordering by a wide margin on a mesh."""
+    rng = np.random.default_rng(3)
+    for n, dens in ((40, 0.08), (80, 0.05), (120, 0.03)):
+        R = sp.random(n, n, density=dens, random_state=int(rng.integers(1 << 30)), format="csc")
+        A = (R + R.T + sp.identity(n)).tocsc()
+        amd = pkg.Symbolic(A, host_only=True, ordering="amd").info.nnz_L
+        exact = _brute_force_min_degree_fill(A)
+        assert amd <= 1.25 * exact + 10, (n, amd, exact)
+    prob = W.matern_posterior(60, obs_frac=0.1, corr_range=0.2)
+    amd = pkg.Symbolic(prob["Qpost"], host_only=True, ordering="amd").info
+    nat = pkg.Symbolic(prob["Qpost"], host_only=True, ordering="natural").info
+    nd = pkg.Symbolic(prob["Qpost"], host_only=True).info
+    assert amd.flops < 0.5 * nat.flops
+    assert amd.nnz_L < 1.3 * nd.nnz_L

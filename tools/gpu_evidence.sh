@@ -14,7 +14,11 @@ $CMD > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-k_gemm2} -s ${NCU_KSKIP:-100} -c ${NCU_KCOUNT:-10} \
+# DRAM traffic of every GEMM launch of the same step (one pass, three metrics): roofline.traffic of the bench line
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off \
+    -k regex:k_gemm2 --csv --log-file $OUT/${TAG}_gemm_traffic.csv $CMD > $OUT/${TAG}_ncu_traffic.log 2>&1
+echo "ncu traffic rc=$?"
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-k_gemm2} -s ${NCU_KSKIP:-193} -c ${NCU_KCOUNT:-15} \
     -f -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT | tail -20
