@@ -209,7 +209,7 @@ def run_reference_arm(args):
 class Lane:
     """One posterior problem in flight on the GPU: its own context (CUDA stream), factor handle and buffers."""
 
-    def __init__(self, pkg, torch, dev, local, nx, seed, perm=None):
+    def __init__(self, pkg, torch, dev, local, nx, seed, perm=None, ordering="nd"):
         self.prob = build_problem(nx, seed)
         Qp = self.prob["Qpost"]
         self.n = Qp.shape[0]
@@ -218,7 +218,8 @@ class Lane:
         # the first lane orders the pattern (library nested dissection); the others reuse its permutation, exactly as
         # the reference passes `perm=p` for every further problem (scripts/darcy/solve_darcy_gmrf-fem.jl:169,174)
         if perm is None:
-            self.sym = pkg.Symbolic(Qp, coords=self.prob["nodes"], ctx=self.ctx)
+            self.sym = pkg.Symbolic(Qp, coords=self.prob["nodes"] if ordering == "nd" else None, ordering=ordering,
+                                    ctx=self.ctx)
         else:
             self.sym = pkg.Symbolic(Qp, perm=perm, ctx=self.ctx)
         self.fac = pkg.CholeskyFactor(self.sym)
@@ -277,7 +278,7 @@ def run_gpu_arm(args):
     nx, B = args.nx, max(1, args.inflight)
     t_setup = time.perf_counter()
     # rank r, lane b solves problem r*B + b: independent posterior problems on one sparsity pattern
-    lanes = [Lane(pkg, torch, dev, local, nx, rank * B)]
+    lanes = [Lane(pkg, torch, dev, local, nx, rank * B, ordering=args.ordering)]
     for b in range(1, B):
         lanes.append(Lane(pkg, torch, dev, local, nx, rank * B + b, perm=lanes[0].sym.p))
     t_setup = time.perf_counter() - t_setup
@@ -405,7 +406,8 @@ def run_gpu_arm(args):
                                "different values; the reference's dataset loop), each on its own CUDA stream",
                    "n": n, "nnz_Q": int(Qp.nnz), "nnz_L": int(info.nnz_L), "factor_flops": info.flops,
                    "nsuper": int(info.nsuper), "levels": int(info.nlevels), "max_front": int(info.max_front),
-                   "front_arena_gb": info.front_bytes / 1e9, "ordering": "library nested dissection (geometric)",
+                   "front_arena_gb": info.front_bytes / 1e9, "ordering": ("library nested dissection (geometric)" if args.ordering == "nd"
+                                else "library approximate minimum degree"),
                    "problems_per_gpu_in_flight": B, "solves_per_step": B,
                    "single_solve_latency_ms": ms_single,
                    "l2_policy": "working set (front arenas, 20 GB per problem) >> 126 MB L2; no flush needed",
@@ -427,16 +429,17 @@ def run_gpu_arm(args):
 
 
 def ncu_traffic(kernel_name):
-    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/r01_ncu_top_kernel.json), or None when no capture of that kernel is committed."""
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel, averaged over all its
+    launches of one posterior solve, from the committed ncu pass over the same bench step
+    (profiles/r01_gemm_traffic.json, written by tools/summarize_traffic.py from tools/gpu_evidence.sh); None when
+    no capture of that kernel is committed."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_top_kernel.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
             d = json.load(f)
-        if d.get("kernel") and d["kernel"].split("<")[0] in kernel_name:
-            return d.get("dram_bytes_per_launch")
+        e = d["kernels"].get(kernel_name)
+        return e["bytes_per_launch"] if e else None
     except Exception:  # noqa: BLE001
-        pass
-    return None
+        return None
 
 
 def main():
@@ -448,6 +451,8 @@ def main():
     ap.add_argument("--nx", type=int, default=1001, help="mesh nodes per side (1001 -> 1,002,001 nodes)")
     ap.add_argument("--nx-sample", dest="nx_sample", type=int, default=0, help="(unused; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ordering", choices=["nd", "amd"], default="nd",
+                    help="fill-reducing ordering computed once by the library and reused as perm=p (default: nested dissection)")
     ap.add_argument("--inflight", type=int, default=4,
                     help="independent posterior problems in flight per GPU (one CUDA stream each)")
     args = ap.parse_args()

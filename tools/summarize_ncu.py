@@ -65,9 +65,15 @@ def full(src, dst, pattern=None):
             c = col(m)
             if c is not None:
                 try:
-                    rec[k] = float(r[c].replace(",", ""))
+                    v = float(r[c].replace(",", ""))
                 except ValueError:
-                    pass
+                    continue
+                u = rows[1][c] if len(rows[1]) > c else ""  # ncu picks one unit per column
+                if k == "duration_us":
+                    v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
+                elif k.endswith("_MB"):
+                    v *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
+                rec[k] = v
         recs.append(rec)
     # the capture of the launch with the longest duration represents the kernel's steady state
     top = max(recs, key=lambda q: q.get("duration_us", 0))
