@@ -153,3 +153,72 @@ class TimeShardedCholesky:
             dist.all_reduce(t, group=self.group)
             total_local = float(t.item())
         return total_local + red
+
+
+# ------------------------------------------------------------------- sample-sharded RBMC variances / samples --
+# SURVEY.md §8(e), row "multi-RHS samples / RBMC": every rank holds the same factor (factorised redundantly: one
+# numeric factorisation is cheaper than shipping 8 nnz(L) bytes), the N sample columns are split across ranks, and the
+# only exchange is one all-reduce of an n-vector.  The Rao-Blackwellised estimator is an average over samples,
+#   var_i = 1/Q_ii + mean_k t_ik^2 / Q_ii^2,
+# so the global estimate is the sample-count-weighted average of the per-rank estimates: no new device code is needed,
+# each rank calls gmrfb_var_rbmc on its columns (scripts/darcy/solve_darcy_gmrf-fem.jl:192, RBMCStrategy(50)).
+def sample_bounds(n_samples: int, world: int):
+    """Contiguous sample-column ranges [lo, hi) per rank, sizes as equal as possible (ranks may be empty)."""
+    base, rem = divmod(n_samples, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def rbmc_variance_sharded(factor, Q, Z, rank: int, world: int, group=None, device=None):
+    """RBMC marginal variances with the sample columns of ``Z`` (n x N, the same array on every rank: the reference
+    threads one seeded generator through ``RBMCStrategy(N; rng)``) split across ranks.  ``factor`` needs a
+    ``var_rbmc(Q, Z_cols)`` method (``CholeskyFactor``; a NumPy stand-in in the gloo tests).  Returns the full n-vector
+    on every rank; with ``world == 1`` it is exactly ``factor.var_rbmc(Q, Z)``."""
+    import torch
+
+    Z = np.asarray(Z)
+    n, N = Z.shape
+    lo, hi = sample_bounds(N, world)[rank]
+    part = np.zeros(n)
+    if hi > lo:
+        part = np.asarray(factor.var_rbmc(Q, np.asfortranarray(Z[:, lo:hi]))) * ((hi - lo) / N)
+    if world == 1:
+        return part
+    import torch.distributed as dist
+
+    t = torch.from_numpy(part)
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def rand_sharded(factor, Z, rank: int, world: int, mean=None, gather=False, group=None, device=None):
+    """Posterior samples mean + P' L^{-T} z for this rank's columns of ``Z`` (n x N); no collective unless
+    ``gather`` asks for all N columns on every rank (scripts/darcy/solve_darcy_gmrf-fem.jl:191 in a sample loop)."""
+    import torch
+
+    Z = np.asarray(Z)
+    n, N = Z.shape
+    bounds = sample_bounds(N, world)
+    lo, hi = bounds[rank]
+    X = np.zeros((n, 0))
+    if hi > lo:
+        X = np.asarray(factor.sample(np.asfortranarray(Z[:, lo:hi]), mean=mean)).reshape(n, hi - lo)
+    if not gather or world == 1:
+        return X
+    import torch.distributed as dist
+
+    # ragged column counts: gather equal-sized (padded) panels and trim
+    cmax = max(h - l for l, h in bounds)
+    mine = torch.zeros((cmax, n), dtype=torch.float64)
+    mine[:hi - lo] = torch.from_numpy(np.ascontiguousarray(X.T))
+    if device is not None:
+        mine = mine.to(device)
+    parts = [torch.empty_like(mine) for _ in bounds]
+    dist.all_gather(parts, mine, group=group)
+    return torch.cat([p[:h - l] for p, (l, h) in zip(parts, bounds)]).cpu().numpy().T

@@ -165,6 +165,66 @@ def test_time_sharded_orchestration_gloo(tmp_path, world, b, N):
         assert err < 1e-10 and lerr < 1e-12, (r, err, lerr)
 
 
+class NumpyFactor:
+    """CPU stand-in with the two methods the sample-sharded helpers call (restated RBMC / sampling of the oracle)."""
+
+    def __init__(self, orc, Q, perm):
+        self.orc, self.Q = orc, Q
+        self.chol = orc.SparseCholesky(Q, perm)
+
+    def var_rbmc(self, Q, Z):
+        return self.orc.rbmc_variance(self.chol, Q, Z)
+
+    def sample(self, Z, mean=None):
+        X = self.chol.solve_UP(Z)
+        return X if mean is None else X + np.asarray(mean)[:, None]
+
+
+def _worker_rbmc(rank, world, port, nsamp, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+
+    pkg = g.load_pkg()
+    orc = g.load_oracle()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob = pkg.workloads.matern_posterior(9, obs_frac=0.3, corr_range=0.3)
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    perm = np.random.default_rng(5).permutation(n)
+    fac = NumpyFactor(orc, Q, perm)
+    Z = np.random.default_rng(11).standard_normal((n, nsamp))  # the same seeded stream on every rank
+    var = pkg.dist.rbmc_variance_sharded(fac, Q, Z, rank, world)
+    want = orc.rbmc_variance(fac.chol, Q, Z)
+    mean = np.linspace(0.0, 1.0, n)
+    X = pkg.dist.rand_sharded(fac, Z, rank, world, mean=mean, gather=True)
+    Xw = fac.sample(Z, mean=mean)
+    lo, hi = pkg.dist.sample_bounds(nsamp, world)[rank]
+    Xl = pkg.dist.rand_sharded(fac, Z, rank, world, mean=mean)
+    e1 = float(np.max(np.abs(var - want) / want))
+    e2 = float(np.max(np.abs(X - Xw)))
+    e3 = float(np.max(np.abs(Xl - Xw[:, lo:hi]))) if hi > lo else 0.0
+    with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+        f.write(f"{e1} {e2} {e3}\n")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nsamp", [(2, 7), (3, 2)])
+def test_sample_sharded_rbmc_gloo(tmp_path, world, nsamp):
+    """sample columns split across ranks (ragged, and one rank empty in the second case), one
+    all-reduce of the n-vector; the result must equal the single-process estimate over all columns."""
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker_rbmc, args=(world, _free_port(), nsamp, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        e1, e2, e3 = map(float, open(tmp_path / f"rank{r}.txt").read().split())
+        assert e1 < 1e-12 and e2 < 1e-13 and e3 < 1e-13, (r, e1, e2, e3)
+
+
 def test_slab_bounds(pkg=None):
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
@@ -174,3 +234,5 @@ def test_slab_bounds(pkg=None):
     assert d.slab_bounds(1024, 8)[-1] == (896, 1024)
     with pytest.raises(ValueError):
         d.slab_bounds(3, 3)
+    assert d.sample_bounds(50, 8) == [(0, 7), (7, 14), (14, 20), (20, 26), (26, 32), (32, 38), (38, 44), (44, 50)]
+    assert d.sample_bounds(2, 3) == [(0, 1), (1, 2), (2, 2)]

@@ -159,6 +159,34 @@ def test_rbmc_matches_oracle_same_z(pkg, orc, ctx, problems):
     np.testing.assert_allclose(v, vref, rtol=1e-9)
 
 
+def test_rbmc_and_samples_sharded_over_emulated_ranks(pkg, orc, ctx, problems):
+    """SURVEY.md 8(e) row 2 through the C ABI: each (emulated) rank factorises redundantly and handles its share of the
+    50 sample columns; the sample-count-weighted sum of the per-rank estimates (what the all-reduce of
+    dist.rbmc_variance_sharded adds up) equals the single-GPU estimate and the oracle's."""
+    prob = problems[24]
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    sym = pkg.Symbolic(Q, ctx=ctx)
+    Qd = pkg.SparseMatrix(Q, ctx=ctx)
+    Z = np.random.default_rng(5).standard_normal((n, 50))
+    world = 8
+    bounds = pkg.dist.sample_bounds(50, world)
+    acc = np.zeros(n)
+    cols = []
+    for r in range(world):
+        fac = pkg.CholeskyFactor(sym).factorize(Q.data)  # one factor per rank
+        lo, hi = bounds[r]
+        acc += fac.var_rbmc(Qd, np.asfortranarray(Z[:, lo:hi])) * ((hi - lo) / 50)
+        cols.append(pkg.dist.rand_sharded(fac, Z, r, world, mean=prob["rhs"]))
+    one = pkg.dist.rbmc_variance_sharded(pkg.CholeskyFactor(sym).factorize(Q.data), Qd, Z, 0, 1)
+    ref = orc.SparseCholesky(Q, sym.p)
+    np.testing.assert_allclose(acc, one, rtol=1e-12)
+    np.testing.assert_allclose(acc, orc.rbmc_variance(ref, Q, Z), rtol=1e-9)
+    X = np.hstack(cols)
+    Xref = ref.solve_UP(Z) + prob["rhs"][:, None]
+    assert np.max(np.abs(X - Xref)) <= 1e-10 * np.max(np.abs(Xref))
+
+
 def test_spmv_sqmahal_postprec(pkg, orc, ctx, problems):
     prob = problems[24]
     Q, A = prob["Q"], prob["A"]

@@ -5,8 +5,8 @@ NS=${1:-"1 2"}; TAG=${2:-mg}; CFGS=${3:-"2048x128 4096x64"}
 OUT=gpurun_out; mkdir -p $OUT
 for N in $NS; do
   if [ "$N" = "1" ]; then TR="python"; else TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"; fi
-  timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err; echo "bench N=$N rc=$?"
-  python - <<PY
+  [ -n "${SKIP_BENCH:-}" ] || timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err; echo "bench N=$N rc=$?"
+  [ -n "${SKIP_BENCH:-}" ] || python - <<PY
 import json
 for l in open("$OUT/${TAG}_bench_n$N.json"):
     if l.startswith("{"):
