@@ -57,7 +57,12 @@ extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) {
   if (prop.major < 10)
     return fail(nullptr, GMRFB_ERR_CUDA, "gmrfb_ctx_create: device is not sm_100-class; libgmrfb is built for sm_100a only");
   c->sm_count = prop.multiProcessorCount;
-  GMRFB_CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // the context's stream gets the highest priority so that a second, default-priority lane (ctx->stream2: GPU-filling
+  // GEMMs of the time-sharded factor) cannot starve the small dependent kernels queued here: the CTA dispatcher serves
+  // pending blocks of higher-priority streams first whenever an SM frees resources
+  int prio_least = 0, prio_greatest = 0;
+  GMRFB_CU(nullptr, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  GMRFB_CU(nullptr, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
   GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_info, sizeof(int)));
   GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_scalar, 16 * sizeof(double)));
   GMRFB_CU(nullptr, kernels_init());
@@ -72,6 +77,11 @@ extern "C" gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d_info) cudaFree(ctx->d_info);
   if (ctx->d_scalar) cudaFree(ctx->d_scalar);
+  if (ctx->stream2) {
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamDestroy(ctx->stream2);
+  }
+  if (ctx->ev_lane) cudaEventDestroy(ctx->ev_lane);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return GMRFB_OK;

@@ -8,6 +8,7 @@
 // right-sided GEMM/TRSM of the same kernels that factorise.
 #include <algorithm>
 #include <climits>
+#include <functional>
 #include <cmath>
 #include <memory>
 
@@ -38,6 +39,9 @@ struct gmrfb_btd {
   DevPlan fwd_first, fwd_step, bwd_last, bwd_step;
   DevPlan sel_last, sel_step;
   bool sel_ready = false;
+  // called by btd_run_factor after the launches of block i have been queued (time-sharded factor: queues W_i and the
+  // spike step of block i on a second stream while the dependent chain of block i + 1 runs on the first)
+  std::function<gmrfb_status(int64_t)> after_block;
 };
 
 namespace {
@@ -167,6 +171,7 @@ gmrfb_status btd_run_factor(gmrfb_btd* f) {
     ar.dinv = f->dinv.p;
     gmrfb_status rc = run_plan(ctx, i == 0 ? f->plan_first : f->plan_step, ar, aux);
     if (rc != GMRFB_OK) return rc;
+    if (f->after_block && (rc = f->after_block(i)) != GMRFB_OK) return rc;
   }
   int info = 0;
   GMRFB_CU(ctx, cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -198,6 +203,21 @@ gmrfb_status btd_run_factor(gmrfb_btd* f) {
 
 }  // namespace
 
+// copy the dense input blocks (host or device memory, column-major b x b) into the factor's slots
+static gmrfb_status btd_load_dense(gmrfb_btd* f, const double* D, const double* Bsub) {
+  gmrfb_ctx* ctx = f->ctx;
+  const int64_t b = f->b;
+  for (int64_t i = 0; i < f->N; i++) {
+    GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot, f->ld * sizeof(double), D + i * b * b, b * sizeof(double),
+                                    b * sizeof(double), b, cudaMemcpyDefault, ctx->stream));
+    if (i > 0)
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot + (int64_t)f->ld * b, f->ld * sizeof(double),
+                                      Bsub + (i - 1) * b * b, b * sizeof(double), b * sizeof(double), b,
+                                      cudaMemcpyDefault, ctx->stream));
+  }
+  return GMRFB_OK;
+}
+
 extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D,
                                                const double* Bsub, gmrfb_btd** out) {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor_dense: ctx is NULL");
@@ -207,14 +227,7 @@ extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_
   std::unique_ptr<gmrfb_btd> f;
   gmrfb_status rc = btd_alloc(ctx, b, nblocks, f);
   if (rc != GMRFB_OK) return rc;
-  for (int64_t i = 0; i < nblocks; i++) {
-    GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot, f->ld * sizeof(double), D + i * b * b, b * sizeof(double),
-                                    b * sizeof(double), b, cudaMemcpyDefault, ctx->stream));
-    if (i > 0)
-      GMRFB_CU(ctx, cudaMemcpy2DAsync(f->arena.p + i * f->slot + (int64_t)f->ld * b, f->ld * sizeof(double),
-                                      Bsub + (i - 1) * b * b, b * sizeof(double), b * sizeof(double), b,
-                                      cudaMemcpyDefault, ctx->stream));
-  }
+  if ((rc = btd_load_dense(f.get(), D, Bsub)) != GMRFB_OK) return rc;
   rc = btd_run_factor(f.get());
   *out = f.release();  // the handle is returned even when not SPD so that get_info can report the block
   return rc;
@@ -357,8 +370,8 @@ extern "C" gmrfb_status gmrfb_btd_logdet(gmrfb_btd* f, double* logdet) {
 //   forward   U_i = X_i - Y_{i-1} C_i'          (in X),   Y_i = U_i L_i^{-T}   (into Y; X_i is consumed as scratch)
 //   backward  V_i = Y_i - X_{i+1} C_{i+1}       (in Y),   X_i = V_i L_i^{-1}   (into X; Y_i is consumed as scratch)
 // Arenas (all moving with the block): 0 = factor slot i, 1 = X block i, 2 = Y block i, 3 = W_i.
-static gmrfb_status btd_ensure_winv(gmrfb_btd* f) {
-  if (f->winv_ready) return GMRFB_OK;
+// allocate and clear W, build the recursive-doubling plan (stream-ordered on ctx->stream)
+static gmrfb_status btd_prepare_winv(gmrfb_btd* f) {
   gmrfb_ctx* ctx = f->ctx;
   const int b = (int)f->b, ld = f->ld;
   const int64_t bs = (int64_t)ld * b;
@@ -371,21 +384,33 @@ static gmrfb_status btd_ensure_winv(gmrfb_btd* f) {
     if (rc != GMRFB_OK) return rc;
     if ((rc = ensure_dinv(f, f->plan_winv.host)) != GMRFB_OK) return rc;
   }
-  DevBuf<double> scratch;
-  GMRFB_CU(ctx, scratch.alloc((size_t)bs));
+  return GMRFB_OK;
+}
+// W_i = L_i^{-1} of block i on ctx->stream (scratch: b x b, ld)
+static gmrfb_status btd_winv_block(gmrfb_btd* f, int64_t i, double* scratch) {
+  gmrfb_ctx* ctx = f->ctx;
+  const int b = (int)f->b, ld = f->ld;
+  const int64_t bs = (int64_t)ld * b;
+  if (b > 1) {
+    k_zero_upper<<<dim3((unsigned)((b + 255) / 256), (unsigned)b), 256, 0, ctx->stream>>>(f->arena.p + i * f->slot, ld, b);
+    GMRFB_CU(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
   LaunchAux aux;
   aux.d_info = ctx->d_info;
-  for (int64_t i = 0; i < f->N; i++) {
-    if (b > 1) {
-      k_zero_upper<<<dim3((unsigned)((b + 255) / 256), (unsigned)b), 256, 0, ctx->stream>>>(f->arena.p + i * f->slot, ld, b);
-      GMRFB_CU(ctx, cudaGetLastError());
-      ctx->launches++;
-    }
-    Arenas ar{{f->arena.p + i * f->slot, f->winv.p + i * bs, scratch.p, nullptr}};
-    ar.dinv = f->dinv.p;
-    gmrfb_status rc = run_plan(ctx, f->plan_winv, ar, aux);
-    if (rc != GMRFB_OK) return rc;
-  }
+  Arenas ar{{f->arena.p + i * f->slot, f->winv.p + i * bs, scratch, nullptr}};
+  ar.dinv = f->dinv.p;
+  return run_plan(ctx, f->plan_winv, ar, aux);
+}
+static gmrfb_status btd_ensure_winv(gmrfb_btd* f) {
+  if (f->winv_ready) return GMRFB_OK;
+  gmrfb_ctx* ctx = f->ctx;
+  gmrfb_status rc = btd_prepare_winv(f);
+  if (rc != GMRFB_OK) return rc;
+  DevBuf<double> scratch;
+  GMRFB_CU(ctx, scratch.alloc((size_t)((int64_t)f->ld * f->b)));
+  for (int64_t i = 0; i < f->N; i++)
+    if ((rc = btd_winv_block(f, i, scratch.p)) != GMRFB_OK) return rc;
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // scratch is released on return
   f->winv_ready = true;
   return GMRFB_OK;
@@ -687,6 +712,10 @@ struct gmrfb_btd_dist {
   DevBuf<double> Xt, Sx; // solve state: local node-major rhs; separator solutions
   int solve_nrhs = 0, solve_ldr = 0;
   bool reduced_ready = false;
+  ~gmrfb_btd_dist() {  // also runs on the error paths of gmrfb_btd_dist_create
+    if (interior) gmrfb_btd_destroy(interior);
+    if (reduced) gmrfb_btd_destroy(reduced);
+  }
 };
 
 namespace {
@@ -764,10 +793,16 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
   h->has_spike = rank > 0;
   h->ni = has_sep ? nloc - 1 : nloc;
   // interior factor (blocks 0..ni-1); couplings inside the interior are B_local[:,:,1..ni-1]
-  gmrfb_status rc = gmrfb_btd_factor_dense(ctx, b, h->ni, D_local, h->ni > 1 ? B_local + b * b : nullptr, &h->interior);
-  if (rc != GMRFB_OK) {
-    if (h->interior) gmrfb_btd_destroy(h->interior);
-    return rc;
+  const bool lanes = (h->has_spike || h->has_sep) && !getenv("GMRFB_BTD_DIST_SERIAL");
+  gmrfb_status rc;
+  if (!lanes) {
+    rc = gmrfb_btd_factor_dense(ctx, b, h->ni, D_local, h->ni > 1 ? B_local + b * b : nullptr, &h->interior);
+    if (rc != GMRFB_OK) return rc;
+  } else {
+    std::unique_ptr<gmrfb_btd> f;
+    if ((rc = btd_alloc(ctx, b, h->ni, f)) != GMRFB_OK) return rc;
+    h->interior = f.release();
+    if ((rc = btd_load_dense(h->interior, D_local, h->ni > 1 ? B_local + b * b : nullptr)) != GMRFB_OK) return rc;
   }
   gmrfb_btd* F = h->interior;
   const int ld = F->ld;
@@ -778,16 +813,29 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
   GMRFB_CU(ctx, cudaMemsetAsync(h->iface.p, 0, 3 * b * b * sizeof(double), ctx->stream));
   DevBuf<double> tmp;
   GMRFB_CU(ctx, tmp.alloc((size_t)bs));
-  // the couplings with the neighbouring separators are eliminated with W_i = L_i^{-1} of the interior blocks (the same
-  // inverses the solves use), so the whole spike recurrence is a replayed static plan of GEMMs without host round trips
-  if (h->has_spike || h->has_sep) {
+  // The couplings with the neighbouring separators are eliminated with W_i = L_i^{-1} of the interior blocks (the same
+  // inverses the solves use), so the whole spike recurrence is a replayed static plan of GEMMs without host round trips.
+  // Two lanes: the factor of block i + 1 (a dependent chain of 64-column steps that leaves most SMs idle) runs on
+  // ctx->stream while W_i and the spike step of block i (large GEMMs) run on ctx->stream2; the only ordering between
+  // the lanes is "block i factored" (one event).  GMRFB_BTD_DIST_SERIAL=1 restores the one-stream order (A/B runs).
+  DevBuf<double> work, wscratch;
+  DevPlan first, step;
+  if (lanes) {
+    if ((rc = btd_prepare_winv(F)) != GMRFB_OK) return rc;
+    GMRFB_CU(ctx, wscratch.alloc((size_t)bs));
+    if (!ctx->stream2) {
+      int prio_least = 0, prio_greatest = 0;
+      GMRFB_CU(ctx, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+      GMRFB_CU(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_least));
+    }
+    if (!ctx->ev_lane) GMRFB_CU(ctx, cudaEventCreateWithFlags(&ctx->ev_lane, cudaEventDisableTiming));
+  } else if (h->has_spike || h->has_sep) {
     rc = btd_ensure_winv(F);
     if (rc != GMRFB_OK) return rc;
   }
   if (h->has_spike) {
     GMRFB_CU(ctx, h->W.alloc((size_t)(bs * h->ni)));
     // scratch arena: [ T (b x b, ld) | E_l (b x b, ld) | Q (b x b, ld) ]
-    DevBuf<double> work;
     GMRFB_CU(ctx, work.alloc((size_t)(3 * bs)));
     GMRFB_CU(ctx, cudaMemsetAsync(work.p + 2 * bs, 0, (size_t)bs * sizeof(double), ctx->stream));
     // E_l = B_local[:,:,0] (rows: first interior block, cols: previous separator)
@@ -809,7 +857,6 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
       B.add(t, gemm_tiles(ib, ib, tri, GCFG_BIG));
       B.end();
     };
-    DevPlan first, step;
     {  // S_1 = E_l' W_1';  Q = S_1 S_1'
       PlanBuilder B(first.host);
       gemm(B, LK_GEMM_TT, 2, bs, 3, 0, 1, 0, false, 1.0, 0.0, TF_BUPP);
@@ -823,17 +870,40 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
     }
     if ((rc = upload_plan(ctx, first)) != GMRFB_OK) return rc;
     if ((rc = upload_plan(ctx, step)) != GMRFB_OK) return rc;
-    LaunchAux aux;
-    aux.d_info = ctx->d_info;
-    for (int64_t i = 0; i < h->ni; i++) {
-      Arenas ar{{F->arena.p + i * F->slot, h->W.p + i * bs, work.p, F->winv.p + i * bs}};
-      rc = run_plan(ctx, i == 0 ? first : step, ar, aux);
-      if (rc != GMRFB_OK) return rc;
-    }
+  }
+  LaunchAux aux;
+  aux.d_info = ctx->d_info;
+  auto spike_step = [&](int64_t i) -> gmrfb_status {
+    Arenas ar{{F->arena.p + i * F->slot, h->W.p + i * bs, work.p, F->winv.p + i * bs}};
+    return run_plan(ctx, i == 0 ? first : step, ar, aux);
+  };
+  if (lanes) {
+    // everything queued so far on ctx->stream (input copies, memsets, plan uploads) precedes the first event
+    F->after_block = [&](int64_t i) -> gmrfb_status {
+      GMRFB_CU(ctx, cudaEventRecord(ctx->ev_lane, ctx->stream));
+      std::swap(ctx->stream, ctx->stream2);  // queue on the second lane
+      gmrfb_status r = GMRFB_OK;
+      cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_lane, 0);
+      if (e != cudaSuccess) r = fail(ctx, GMRFB_ERR_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e));
+      if (r == GMRFB_OK) r = btd_winv_block(F, i, wscratch.p);
+      if (r == GMRFB_OK && h->has_spike) r = spike_step(i);
+      std::swap(ctx->stream, ctx->stream2);
+      return r;
+    };
+    rc = btd_run_factor(F);  // synchronises ctx->stream and reports a non-SPD block
+    F->after_block = nullptr;
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream2));
+    if (rc != GMRFB_OK) return rc;
+    F->winv_ready = true;
+  } else if (h->has_spike) {
+    for (int64_t i = 0; i < h->ni; i++)
+      if ((rc = spike_step(i)) != GMRFB_OK) return rc;
+  }
+  if (h->has_spike) {
     // Q (lower triangle) -> iface block 1 (ld = b)
     GMRFB_CU(ctx, cudaMemcpy2DAsync(h->iface.p + b * b, b * sizeof(double), work.p + 2 * bs, ld * sizeof(double),
                                     b * sizeof(double), b, cudaMemcpyDeviceToDevice, ctx->stream));
-    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // work and the plans are released here
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // work and the plans are released at the end of this function
   }
   if (h->has_sep) {
     GMRFB_CU(ctx, h->V.alloc((size_t)bs));
@@ -1016,8 +1086,6 @@ extern "C" gmrfb_status gmrfb_btd_dist_destroy(gmrfb_btd_dist* h) {
   if (!h) return GMRFB_OK;
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
-  if (h->interior) gmrfb_btd_destroy(h->interior);
-  if (h->reduced) gmrfb_btd_destroy(h->reduced);
   delete h;
   return GMRFB_OK;
 }

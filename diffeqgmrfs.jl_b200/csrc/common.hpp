@@ -18,6 +18,10 @@
 struct gmrfb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // second stream + event for two-lane schedules (created on first use; the time-sharded block-tridiagonal factor
+  // runs its GPU-filling spike GEMMs there while the latency-bound chain of the next block runs on `stream`)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_lane = nullptr;
   std::string err;
   int64_t launches = 0;
   int* d_info = nullptr;       // POTRF failure column
