@@ -46,7 +46,7 @@ __global__ void k_ref(const Task* tasks, int TA, int TB, const double* A, const 
 template <class CFG>
 const char* cfg_name() {
   static char buf[64];
-  snprintf(buf, sizeof buf, "%dx%d/w%dx%d/s%d/b%d", CFG::BM, CFG::BN, CFG::WARPS_M, CFG::WARPS_N, CFG::STAGES, CFG::MINB);
+  snprintf(buf, sizeof buf, "%dx%dx%d/w%dx%d/s%d/b%d", CFG::BM, CFG::BN, CFG::BK, CFG::WARPS_M, CFG::WARPS_N, CFG::STAGES, CFG::MINB);
   return buf;
 }
 
@@ -180,7 +180,7 @@ int main() {
   k_fill<<<(unsigned)((buf.na + 255) / 256), 256>>>(buf.A, buf.na, 1u);
   CK(cudaMemset(buf.C, 0, buf.nc * 8));
   CK(cudaDeviceSynchronize());
-  using Small = GemmCfg<64, 64, 4, 2, 16, 4, 3>;
+  using Small = GemmCfg<64, 64, 4, 2, 16, 2, 3>;
   using Big = GemmCfg<128, 64, 4, 2, 16, 3, 2>;
   {
     Bufs small = buf; small.nc = (size_t)8 << 20;
@@ -202,25 +202,17 @@ int main() {
   workload<false, true, CFG>("zrr108", buf, 108, 600, 214, 600, false, 60);
   SHORTK(Small)
 #ifdef PROBE_EXTRA_CFGS
-  using S2 = GemmCfg<64, 64, 4, 2, 16, 2, 3>;
-  using S5 = GemmCfg<64, 64, 4, 2, 16, 3, 3>;
-  using S6 = GemmCfg<64, 64, 4, 2, 32, 2, 3>;
-  using S7 = GemmCfg<64, 64, 4, 2, 8, 3, 3>;
-  using S8 = GemmCfg<64, 64, 4, 2, 8, 2, 3>;
-  using B2 = GemmCfg<128, 64, 4, 2, 16, 2, 2>;
-  SHORTK(S2)
-  SHORTK(S5)
-  SHORTK(S6)
-  SHORTK(S7)
-  SHORTK(S8)
-  workload<false, false, S2>("syrk16", buf, 16, 1800, 1800, 450, true, 100);
-  workload<false, false, S5>("syrk16", buf, 16, 1800, 1800, 450, true, 100);
-  workload<false, false, B2>("syrk16", buf, 16, 1800, 1800, 450, true, 100);
+  using S9 = GemmCfg<64, 64, 4, 2, 16, 2, 4>;   // 64-register cap: 4 CTAs/SM
+  using S10 = GemmCfg<64, 64, 2, 2, 16, 2, 4>;  // 4 warps, 32x32 warp tiles, 4 CTAs/SM
+  using S11 = GemmCfg<64, 64, 2, 2, 16, 2, 5>;
+  using S12 = GemmCfg<64, 64, 4, 2, 8, 3, 3>;   // BK = 8
+  SHORTK(S9)
+  SHORTK(S10)
+  SHORTK(S11)
+  SHORTK(S12)
+  workload<false, false, S10>("syrk16", buf, 16, 1800, 1800, 450, true, 100);
+  workload<false, false, S10>("big1", buf, 1, 4736, 4736, 4096, false, 0);
   workload<false, false, Small>("big1", buf, 1, 4736, 4736, 4096, false, 0);
-  workload<false, false, S2>("big1", buf, 1, 4736, 4736, 4096, false, 0);
-  workload<false, false, S5>("big1", buf, 1, 4736, 4736, 4096, false, 0);
-  workload<false, false, Big>("big1", buf, 1, 4736, 4736, 4096, false, 0);
-  workload<false, false, B2>("big1", buf, 1, 4736, 4736, 4096, false, 0);
 #endif
   workload<false, false, Big>("syrk64", buf, 64, 1000, 1000, 256, true, 100);
   workload<false, false, Small>("syrk16", buf, 16, 1800, 1800, 450, true, 100);
