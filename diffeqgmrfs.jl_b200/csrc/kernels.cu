@@ -88,15 +88,18 @@ __device__ __forceinline__ int chol8(double (&D)[8][8], double (&invd)[8]) {
 // The grouped DMMA GEMM engine lives in gemm_engine.cuh (k_gemm2<TA, TB, CFG>); two tile configurations are
 // instantiated and chosen per launch by the plan builder (Launch::cfg):
 //   GCFG_BIG   128x64 tiles, 8 warps, 3 stages, 2 CTAs/SM  - large, regular problems (33.5 TFLOP/s at n=4736, K=4096)
-//   GCFG_SMALL  64x64 tiles, 8 warps, 2 stages, 3 CTAs/SM  - launches with few or ragged tiles
-// Two stages, not more: on batched launches over ragged fronts (K = 30 ... 600) the 2-stage pipeline is 6-18 % faster
-// than the 4-stage one and no slower at K = 4096 (35 KB instead of 70 KB of shared memory per CTA leaves the L1 to the
-// read-modify-write of the C tiles; tools/probe/gemm_batched_probe.cu, profiles/r01_gemm_batched_probe.md).
-#ifndef GMRFB_SMALL_STAGES
-#define GMRFB_SMALL_STAGES 2
-#endif
+//   GCFG_SMALL  64x64 tiles, 2 stages, in two warp layouts chosen at launch time by the grid size:
+//                 4 warps (32x32 warp tiles) at 4 CTAs/SM for launches of at least GEMM_W4_MIN_GRID CTAs,
+//                 8 warps (16x32 warp tiles) at 3 CTAs/SM below (few CTAs: more warps per tile hide latency better)
+// Measured with tools/probe/gemm_batched_probe.cu (profiles/r01_gemm_batched_probe.md): on batched launches over ragged
+// fronts (K = 30 ... 600) two stages are 6-18 % faster than four (35 KB instead of 70 KB of shared memory per CTA leaves
+// the L1 to the read-modify-write of the C tiles); four warps with 32x32 warp tiles (one LDS.128 pair feeds 16 DMMAs
+// instead of 8) at 4 CTAs/SM add another 2-4 % on large grids and reach 35.1 TFLOP/s on one 4736^2 x 4096 product
+// (8 warps: 33.5; cuBLAS DGEMM: 35.5).  The 128x64 configuration is only used on request (GMRFB_GEMM_BIG_MIN).
 using GemmBig = GemmCfg<GEMM_TILE_M[GCFG_BIG], GEMM_TILE_N[GCFG_BIG], 4, 2, 16, 3, 2>;
-using GemmSmall = GemmCfg<GEMM_TILE_M[GCFG_SMALL], GEMM_TILE_N[GCFG_SMALL], 4, 2, 16, GMRFB_SMALL_STAGES, 3>;
+using GemmSmall = GemmCfg<GEMM_TILE_M[GCFG_SMALL], GEMM_TILE_N[GCFG_SMALL], 4, 2, 16, 2, 3>;
+using GemmSmall4 = GemmCfg<GEMM_TILE_M[GCFG_SMALL], GEMM_TILE_N[GCFG_SMALL], 2, 2, 16, 2, 4>;
+constexpr int GEMM_W4_MIN_GRID = 1184;  // two full waves of the 4-warp layout (148 SMs x 4 CTAs x 2)
 
 // -------------------------------------------------------------------------------------------- POTRF ----
 // Cholesky AND inverse of an n x n (n <= 64) diagonal block, one CTA (8 warps) per block, everything in shared
@@ -806,7 +809,9 @@ static cudaError_t gemm_attr() {
 }
 template <bool TA, bool TB>
 static void gemm_launch(const Launch& L, const Task* t, const Arenas& ar, cudaStream_t st) {
-  if (L.cfg == GCFG_SMALL)
+  if (L.cfg == GCFG_SMALL && L.grid >= GEMM_W4_MIN_GRID)
+    k_gemm2<TA, TB, GemmSmall4><<<L.grid, GemmSmall4::NT, GemmSmall4::SMEM, st>>>(t, L.ntasks, ar);
+  else if (L.cfg == GCFG_SMALL)
     k_gemm2<TA, TB, GemmSmall><<<L.grid, GemmSmall::NT, GemmSmall::SMEM, st>>>(t, L.ntasks, ar);
   else
     k_gemm2<TA, TB, GemmBig><<<L.grid, GemmBig::NT, GemmBig::SMEM, st>>>(t, L.ntasks, ar);
@@ -822,6 +827,10 @@ cudaError_t kernels_init() {
   if ((e = gemm_attr<false, true, GemmSmall>()) != cudaSuccess) return e;
   if ((e = gemm_attr<true, true, GemmSmall>()) != cudaSuccess) return e;
   if ((e = gemm_attr<true, false, GemmSmall>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<false, false, GemmSmall4>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<false, true, GemmSmall4>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<true, true, GemmSmall4>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<true, false, GemmSmall4>()) != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_potrf64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem());
   if (e != cudaSuccess) return e;
   const int small_smem = small_front_smem(SMALL_FRONT_MAX);

@@ -180,7 +180,7 @@ int main() {
   k_fill<<<(unsigned)((buf.na + 255) / 256), 256>>>(buf.A, buf.na, 1u);
   CK(cudaMemset(buf.C, 0, buf.nc * 8));
   CK(cudaDeviceSynchronize());
-  using Small = GemmCfg<64, 64, 4, 2, 16, 2, 3>;
+  using Small = GemmCfg<64, 64, 2, 2, 16, 2, 4>;  // the library's configuration
   using Big = GemmCfg<128, 64, 4, 2, 16, 3, 2>;
   {
     Bufs small = buf; small.nc = (size_t)8 << 20;
