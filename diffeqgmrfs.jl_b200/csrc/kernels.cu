@@ -368,10 +368,24 @@ __global__ void __launch_bounds__(256) k_extend_add(const Task* __restrict__ tas
   const int i = i0 + li;
   if (i >= M) return;
   const int64_t pr = ri[li];
-  for (int lj = tid >> 6; lj < EA_TILE; lj += 4) {
-    const int j = j0 + lj;
-    if (j > i || j >= M) continue;
-    P[pr + (int64_t)rj[lj] * T.ldc] += U[i + (int64_t)j * T.lda];
+  // 16 columns per thread: all loads of a batch of 8 are issued before the first store (the kernel is bound by the
+  // latency of the indexed read-modify-write, not by arithmetic)
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    double u[8], pv[8];
+    double* pp[8];
+    bool ok[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int lj = (tid >> 6) + 4 * (8 * h + q), j = j0 + lj;
+      ok[q] = j <= i && j < M;
+      pp[q] = P + pr + (int64_t)rj[lj] * T.ldc;
+      u[q] = ok[q] ? U[i + (int64_t)j * T.lda] : 0.0;
+      pv[q] = ok[q] ? *pp[q] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (ok[q]) *pp[q] = pv[q] + u[q];
   }
 }
 
@@ -401,12 +415,20 @@ __global__ void __launch_bounds__(256) k_gather_sym(const Task* __restrict__ tas
   const int i = i0 + li;
   if (i >= M) return;
   const int64_t a = ri[li];
-  for (int lj = tid >> 6; lj < EA_TILE; lj += 4) {
-    const int j = j0 + lj;
-    if (j >= M) continue;
-    const int64_t b = rj[lj];
-    const double v = (a >= b) ? Zp[a + b * T.lda] : Zp[b + a * T.lda];
-    Zc[i + (int64_t)j * T.ldc] = v;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {  // 8 gathered loads in flight per thread before the first store
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int lj = (tid >> 6) + 4 * (8 * h + q);
+      const int64_t b = rj[lj];
+      v[q] = (j0 + lj < M) ? ((a >= b) ? Zp[a + b * T.lda] : Zp[b + a * T.lda]) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int j = j0 + (tid >> 6) + 4 * (8 * h + q);
+      if (j < M) Zc[i + (int64_t)j * T.ldc] = v[q];
+    }
   }
 }
 
