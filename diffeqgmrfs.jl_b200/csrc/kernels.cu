@@ -370,21 +370,24 @@ __global__ void __launch_bounds__(256) k_extend_add(const Task* __restrict__ tas
   const int64_t pr = ri[li];
   // 16 columns per thread: all loads of a batch of 8 are issued before the first store (the kernel is bound by the
   // latency of the indexed read-modify-write, not by arithmetic)
+#ifndef EA_BATCH
+#define EA_BATCH 8
+#endif
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    double u[8], pv[8];
-    double* pp[8];
-    bool ok[8];
+  for (int h = 0; h < 16 / EA_BATCH; h++) {
+    double u[EA_BATCH], pv[EA_BATCH];
+    double* pp[EA_BATCH];
+    bool ok[EA_BATCH];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int lj = (tid >> 6) + 4 * (8 * h + q), j = j0 + lj;
+    for (int q = 0; q < EA_BATCH; q++) {
+      const int lj = (tid >> 6) + 4 * (EA_BATCH * h + q), j = j0 + lj;
       ok[q] = j <= i && j < M;
       pp[q] = P + pr + (int64_t)rj[lj] * T.ldc;
       u[q] = ok[q] ? U[i + (int64_t)j * T.lda] : 0.0;
       pv[q] = ok[q] ? *pp[q] : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < EA_BATCH; q++)
       if (ok[q]) *pp[q] = pv[q] + u[q];
   }
 }
@@ -416,17 +419,17 @@ __global__ void __launch_bounds__(256) k_gather_sym(const Task* __restrict__ tas
   if (i >= M) return;
   const int64_t a = ri[li];
 #pragma unroll
-  for (int h = 0; h < 2; h++) {  // 8 gathered loads in flight per thread before the first store
-    double v[8];
+  for (int h = 0; h < 16 / EA_BATCH; h++) {  // EA_BATCH gathered loads in flight per thread before the first store
+    double v[EA_BATCH];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int lj = (tid >> 6) + 4 * (8 * h + q);
+    for (int q = 0; q < EA_BATCH; q++) {
+      const int lj = (tid >> 6) + 4 * (EA_BATCH * h + q);
       const int64_t b = rj[lj];
       v[q] = (j0 + lj < M) ? ((a >= b) ? Zp[a + b * T.lda] : Zp[b + a * T.lda]) : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int j = j0 + (tid >> 6) + 4 * (8 * h + q);
+    for (int q = 0; q < EA_BATCH; q++) {
+      const int j = j0 + (tid >> 6) + 4 * (EA_BATCH * h + q);
       if (j < M) Zc[i + (int64_t)j * T.ldc] = v[q];
     }
   }
