@@ -94,18 +94,21 @@ function _destroy(F::B200Factor)
 end
 
 """
-    b200_cholesky(A; perm=nothing, check=true, coords=nothing, ctx=default_context())
+    b200_cholesky(A; perm=nothing, check=true, coords=nothing, ordering=:nd, ctx=default_context())
 
 Drop-in for `cholesky(Symmetric(A); perm, check)` on a `SparseMatrixCSC{Float64,Int64}` holding both triangles.
-Julia's 1-based `colptr`/`rowval`/`perm` are passed untouched (`base = 1`).
+Julia's 1-based `colptr`/`rowval`/`perm` are passed untouched (`base = 1`).  Without `perm` the library orders the
+matrix itself: `ordering = :nd` (nested dissection, geometric when `coords` is given; the faster factor on the GPU) or
+`ordering = :amd` (approximate minimum degree, the kind of ordering `cholesky(A)` gets from CHOLMOD).
 """
 function b200_cholesky(A::SparseMatrixCSC{Float64,Int64}; perm::Union{Nothing,Vector{Int64}} = nothing,
                        check::Bool = true, coords::Union{Nothing,Matrix{Float64}} = nothing,
-                       ctx::B200Context = default_context())
+                       ordering::Symbol = :nd, ctx::B200Context = default_context())
     n = size(A, 1)
     cdim = coords === nothing ? Int32(0) : Int32(size(coords, 1))      # coords is dim x n (node-major in memory)
     cptr = coords === nothing ? Ptr{Float64}(C_NULL) : pointer(coords)
-    opts = Ref(AnalyzeOpts(perm === nothing ? ORDER_ND : ORDER_GIVEN, Int32(0), Int32(1), cdim, cptr, 0, 0, 0.0))
+    kind = perm !== nothing ? ORDER_GIVEN : ordering === :amd ? ORDER_AMD : ORDER_ND
+    opts = Ref(AnalyzeOpts(kind, Int32(0), Int32(1), cdim, cptr, 0, 0, 0.0))
     sym = Ref{Ptr{Cvoid}}(C_NULL)
     fac = Ref{Ptr{Cvoid}}(C_NULL)
     pptr = perm === nothing ? Ptr{Int64}(C_NULL) : pointer(perm)
