@@ -371,11 +371,12 @@ class CholeskyFactor:
         return out
 
 
-def cholesky(A, perm=None, check=True, ctx=None, coords=None) -> CholeskyFactor:
+def cholesky(A, perm=None, check=True, ctx=None, coords=None, ordering="nd") -> CholeskyFactor:
     """``cholesky(Symmetric(A); perm=perm, check=check)`` (scripts/solve_burger.jl:147,
-    scripts/darcy/solve_darcy_fem.jl:93).  ``perm`` is 0-based here."""
+    scripts/darcy/solve_darcy_fem.jl:93).  ``perm`` is 0-based here; without it the library orders the matrix
+    (``ordering="nd"`` nested dissection, ``"amd"`` approximate minimum degree, ``"natural"``)."""
     A = _csc(A)
-    sym = Symbolic(A, perm=perm, ctx=ctx, coords=coords)
+    sym = Symbolic(A, perm=perm, ctx=ctx, coords=coords, ordering=ordering)
     return CholeskyFactor(sym).factorize(A.data, check=check)
 
 

@@ -23,7 +23,7 @@ def problems(W):
 
 
 @pytest.mark.parametrize("nx", [7, 24, 61, 130])
-@pytest.mark.parametrize("mode", ["nd", "geo", "given"])
+@pytest.mark.parametrize("mode", ["nd", "geo", "given", "amd"])
 def test_factor_solve_sample(pkg, orc, ctx, problems, nx, mode):
     prob = problems[nx]
     Q = prob["Qpost"]
@@ -33,6 +33,9 @@ def test_factor_solve_sample(pkg, orc, ctx, problems, nx, mode):
         sym = pkg.Symbolic(Q, ctx=ctx)
     elif mode == "geo":
         sym = pkg.Symbolic(Q, ctx=ctx, coords=prob["nodes"])
+    elif mode == "amd":
+        # approximate minimum degree: a deep, unbalanced supernodal tree (many levels with few fronts each)
+        sym = pkg.Symbolic(Q, ctx=ctx, ordering="amd")
     else:
         # "perm = p reused" path of the reference: ordering from a first analysis, then ORDER_GIVEN
         p0 = pkg.Symbolic(Q, host_only=True).p
@@ -73,8 +76,17 @@ def test_factor_values(pkg, orc, ctx, problems, nx):
 
 @pytest.mark.parametrize("nx", [7, 24, 61, 130])
 def test_selected_inversion(pkg, orc, ctx, problems, nx):
+    _selected_inversion(pkg, orc, ctx, problems, nx, "nd")
+
+
+@pytest.mark.parametrize("nx", [24, 130])
+def test_selected_inversion_amd_ordering(pkg, orc, ctx, problems, nx):
+    _selected_inversion(pkg, orc, ctx, problems, nx, "amd")
+
+
+def _selected_inversion(pkg, orc, ctx, problems, nx, ordering):
     Q = problems[nx]["Qpost"]
-    sym = pkg.Symbolic(Q, ctx=ctx)
+    sym = pkg.Symbolic(Q, ctx=ctx, ordering=ordering)
     fac = pkg.CholeskyFactor(sym).factorize(Q.data)
     v = fac.var_selinv()
     ref = orc.SparseCholesky(Q, sym.p)
