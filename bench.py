@@ -218,8 +218,8 @@ class Lane:
         # the first lane orders the pattern (library nested dissection); the others reuse its permutation, exactly as
         # the reference passes `perm=p` for every further problem (scripts/darcy/solve_darcy_gmrf-fem.jl:169,174)
         if perm is None:
-            self.sym = pkg.Symbolic(Qp, coords=self.prob["nodes"] if ordering == "nd" else None, ordering=ordering,
-                                    ctx=self.ctx)
+            self.sym = pkg.Symbolic(Qp, coords=self.prob["nodes"] if ordering == "nd" else None,
+                                    ordering={"ndgraph": "nd"}.get(ordering, ordering), ctx=self.ctx)
         else:
             self.sym = pkg.Symbolic(Qp, perm=perm, ctx=self.ctx)
         self.fac = pkg.CholeskyFactor(self.sym)
@@ -406,8 +406,10 @@ def run_gpu_arm(args):
                                "different values; the reference's dataset loop), each on its own CUDA stream",
                    "n": n, "nnz_Q": int(Qp.nnz), "nnz_L": int(info.nnz_L), "factor_flops": info.flops,
                    "nsuper": int(info.nsuper), "levels": int(info.nlevels), "max_front": int(info.max_front),
-                   "front_arena_gb": info.front_bytes / 1e9, "ordering": ("library nested dissection (geometric)" if args.ordering == "nd"
-                                else "library approximate minimum degree"),
+                   "front_arena_gb": info.front_bytes / 1e9, "ordering": {"nd": "library nested dissection (geometric)",
+                                "ndgraph": "library nested dissection (graph bisection, no coordinates)",
+                                "nd_amd": "library nested dissection (graph) with halo-AMD leaves",
+                                "amd": "library approximate minimum degree"}[args.ordering],
                    "problems_per_gpu_in_flight": B, "solves_per_step": B,
                    "single_solve_latency_ms": ms_single,
                    "l2_policy": "working set (front arenas, 20 GB per problem) >> 126 MB L2; no flush needed",
@@ -451,8 +453,9 @@ def main():
     ap.add_argument("--nx", type=int, default=1001, help="mesh nodes per side (1001 -> 1,002,001 nodes)")
     ap.add_argument("--nx-sample", dest="nx_sample", type=int, default=0, help="(unused; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ordering", choices=["nd", "amd"], default="nd",
-                    help="fill-reducing ordering computed once by the library and reused as perm=p (default: nested dissection)")
+    ap.add_argument("--ordering", choices=["nd", "ndgraph", "nd_amd", "amd"], default="nd",
+                    help="fill-reducing ordering computed once by the library and reused as perm=p (default: geometric "
+                         "nested dissection, the configuration every committed profile was measured with)")
     ap.add_argument("--inflight", type=int, default=4,
                     help="independent posterior problems in flight per GPU (one CUDA stream each)")
     args = ap.parse_args()

@@ -169,15 +169,15 @@ struct NDWork {
 }  // namespace
 
 void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
-                       int leaf, int coord_dim, const double* coords, std::vector<int32_t>& perm) {
+                       int leaf, int coord_dim, const double* coords, std::vector<int32_t>& perm, bool amd_leaves) {
   NDWork W(n, xadj, adj);
-  W.leaf = leaf > 0 ? leaf : 24;
+  W.leaf = leaf > 0 ? leaf : (amd_leaves ? 200 : 24);
   W.coord_dim = coord_dim;
   W.coords = coords;
   struct Range {
     int32_t lo, hi;
   };
-  std::vector<Range> todo;
+  std::vector<Range> todo, leaves;  // leaves: ranges that are not split further
   todo.push_back({0, n});
   std::vector<int32_t> side;  // scratch: 0 = A, 1 = B, 2 = S for vertices of the current range (by position)
   std::vector<int32_t> tmp;
@@ -185,7 +185,10 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
     Range r = todo.back();
     todo.pop_back();
     int32_t m = r.hi - r.lo;
-    if (m <= W.leaf) continue;  // leaf: keep the order it inherited (BFS order of the parent bisection)
+    if (m <= W.leaf) {  // leaf: keeps the order it inherited (BFS order of the parent bisection) unless amd_leaves
+      leaves.push_back(r);
+      continue;
+    }
     int32_t lab = W.next_label++;
     for (int32_t k = r.lo; k < r.hi; k++) W.label[W.verts[k]] = lab;
     // --- choose a bipartition A0 | B of the range; mark with stamp: in A0 <=> inA[v] ---
@@ -290,7 +293,10 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
       }
       if (!split_done) {
         // connected: q holds the BFS order from `root`, levels in W.lvl, nl levels
-        if (nl < 3) continue;  // (near-)clique: no useful separator, treat as leaf
+        if (nl < 3) {  // (near-)clique: no useful separator, treat as leaf
+          leaves.push_back(r);
+          continue;
+        }
         // smallest level index mcut with |levels <= mcut| >= m/2, but keep at least one level on each side
         std::vector<int32_t> cnt(nl, 0);
         for (int32_t v : q) cnt[W.lvl[v]]++;
@@ -335,7 +341,10 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
     for (int32_t k = 0; k < m; k++) na += (side[k] == 0), nb += (side[k] == 1), ns += (side[k] == 2);
     if (nb == 0 || na == 0) {
       // degenerate split (everything on one side): accept as leaf to guarantee progress
-      if (ns == 0 || na + nb == 0) continue;
+      if (ns == 0 || na + nb == 0) {
+        leaves.push_back(r);
+        continue;
+      }
     }
     int32_t pa = 0, pb = na, ps = na + nb;
     for (int32_t k = 0; k < m; k++) {
@@ -352,6 +361,52 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
     for (int32_t k = na + nb; k < m; k++) W.label[W.verts[r.lo + k]] = -1;
     if (nb > 0) todo.push_back({r.lo + na, r.lo + na + nb});
     if (na > 0) todo.push_back({r.lo, r.lo + na});
+  }
+  if (amd_leaves) {
+    // Halo-AMD inside every leaf subdomain: the leaf's vertices are ordered by approximate minimum degree on the leaf's
+    // subgraph extended by its halo (the neighbours outside the leaf: separator vertices of the enclosing dissections,
+    // all eliminated after the leaf), so fill against the separators is accounted for in the degrees.
+    std::vector<int32_t> loc(n, -1), lperm, ladj, halo, order;
+    std::vector<int64_t> lxadj;
+    std::vector<std::vector<int32_t>> hadj;
+    for (const Range& r : leaves) {
+      const int32_t m = r.hi - r.lo;
+      if (m < 3) continue;
+      for (int32_t k = 0; k < m; k++) loc[W.verts[r.lo + k]] = k;
+      halo.clear();
+      for (int32_t k = 0; k < m; k++) {
+        const int32_t v = W.verts[r.lo + k];
+        for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+          const int32_t u = adj[p];
+          if (loc[u] < 0) {
+            loc[u] = m + (int32_t)halo.size();
+            halo.push_back(u);
+          }
+        }
+      }
+      const int32_t nl = m + (int32_t)halo.size();
+      hadj.assign(halo.size(), std::vector<int32_t>());
+      lxadj.assign(nl + 1, 0);
+      ladj.clear();
+      for (int32_t k = 0; k < m; k++) {
+        const int32_t v = W.verts[r.lo + k];
+        for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) {
+          const int32_t lu = loc[adj[p]];
+          ladj.push_back(lu);
+          if (lu >= m) hadj[lu - m].push_back(k);
+        }
+        lxadj[k + 1] = (int64_t)ladj.size();
+      }
+      for (size_t h = 0; h < halo.size(); h++) {  // halo rows: their neighbours inside the leaf (symmetric graph)
+        ladj.insert(ladj.end(), hadj[h].begin(), hadj[h].end());
+        lxadj[m + h + 1] = (int64_t)ladj.size();
+      }
+      amd_order(nl, lxadj, ladj, lperm, m);
+      order.assign(W.verts.begin() + r.lo, W.verts.begin() + r.hi);
+      for (int32_t k = 0; k < m; k++) W.verts[r.lo + k] = order[lperm[k]];
+      for (int32_t v : order) loc[v] = -1;
+      for (int32_t u : halo) loc[u] = -1;
+    }
   }
   perm = W.verts;
 }
@@ -464,10 +519,14 @@ struct AmdWork {
 
 }  // namespace
 
+// Vertices nfree .. n-1 (if any) are a HALO: they take part in the quotient graph (so the degrees of the free vertices
+// next to them are right) but are never eliminated, merged or reported - the "halo-AMD" used to order the leaf
+// subdomains of a nested dissection, whose halo is the surrounding separators (eliminated later).
 void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
-               std::vector<int32_t>& perm) {
-  perm.assign(n, 0);
-  if (n == 0) return;
+               std::vector<int32_t>& perm, int32_t nfree) {
+  if (nfree < 0 || nfree > n) nfree = n;
+  perm.assign(nfree, 0);
+  if (nfree == 0) return;
   AmdWork W;
   W.n = n;
   const int64_t nnz = xadj[n];
@@ -486,6 +545,7 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
     W.degree[i] = W.len[i];
   }
   for (int32_t i = 0; i < n; i++) {
+    if (i >= nfree) continue;  // halo vertices are never candidates
     if (W.degree[i] == 0) {  // isolated vertex: eliminate at once
       W.is_elem[i] = 1; W.w[i] = 0; W.pe[i] = -1; W.elen[i] = -1;
       pivots.push_back(i);
@@ -502,7 +562,7 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
   auto& iw = W.iw; auto& pe = W.pe; auto& len = W.len; auto& elen = W.elen; auto& nv = W.nv; auto& degree = W.degree;
   auto& w = W.w;
 
-  while (nel < n) {
+  while (nel < nfree) {
     while (mindeg <= n && W.head[mindeg] < 0) mindeg++;
     const int32_t me = W.head[mindeg];
     W.list_remove(me);
@@ -519,7 +579,7 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
         degme += nvi;
         nv[i] = -nvi;
         lme.push_back(i);
-        W.list_remove(i);
+        if (i < nfree) W.list_remove(i);
       }
     };
     {
@@ -609,7 +669,7 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
           hash += (uint32_t)j;
         }
       }
-      if (keep_e.empty() && keep_v.empty()) {
+      if (keep_e.empty() && keep_v.empty() && i < nfree) {
         // mass elimination: i's adjacency is me alone
         pe[i] = -1;
         W.parent[i] = me;
@@ -621,7 +681,7 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
         elen[i] = -1;
         continue;
       }
-      degree[i] = (int32_t)std::min<int64_t>(degree[i], deg);
+      if (i < nfree) degree[i] = (int32_t)std::min<int64_t>(degree[i], deg);
       // new list: me, surviving elements, surviving variables (never longer than the old list: the variables of
       // L_me that i was adjacent to, or at least one absorbed element, made room - otherwise append at pfree)
       const int64_t newlen = 1 + (int64_t)keep_e.size() + (int64_t)keep_v.size();
@@ -638,6 +698,7 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
       for (int32_t j : keep_v) iw[pn++] = j;
       elen[i] = 1 + (int32_t)keep_e.size();
       len[i] = (int32_t)newlen;
+      if (i >= nfree) continue;  // halo: list kept consistent, no degree, no supervariable detection
       const int32_t hb = (int32_t)(hash % (uint32_t)n);
       hval[i] = (int32_t)hash;
       if (hhead[hb] < 0) used.push_back(hb);
@@ -678,12 +739,16 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
     wflg += 2;
     // ---- finalise the new element and the degrees of its variables ----
     int64_t p = pme1;
-    const int32_t nleft = n - nel;
+    const int32_t nleft = (nfree - nel) + (n - nfree);
     for (int64_t q = pme1; q < pme2; q++) {
       const int32_t i = iw[q];
       const int32_t nvi = -nv[i];
       if (nvi <= 0) continue;  // absorbed above
       nv[i] = nvi;
+      if (i >= nfree) {  // halo member of the new element
+        iw[p++] = i;
+        continue;
+      }
       int64_t deg = (int64_t)degree[i] + degme - nvi;
       deg = std::min<int64_t>(deg, nleft - nvi);
       if (deg < 1) deg = 1;  // only possible for the last variables; keeps list 0 free for nothing special
@@ -707,7 +772,7 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
   std::vector<int32_t> cnt_head(n, -1), cnt_next(n, -1);
   std::vector<char> is_pivot(n, 0);
   for (int32_t v : pivots) is_pivot[v] = 1;
-  for (int32_t i = n - 1; i >= 0; i--) {
+  for (int32_t i = nfree - 1; i >= 0; i--) {
     if (is_pivot[i]) continue;
     int32_t r = i;
     while (!is_pivot[r]) r = W.parent[r];  // variables are absorbed by variables that end up as pivots or by pivots
@@ -756,9 +821,12 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
     std::iota(S.perm_user.begin(), S.perm_user.end(), 0);
   } else if (opt.ordering_kind == 2) {
     if (opt.coords && (opt.coord_dim < 1 || opt.coord_dim > 3)) return "coord_dim must be 1..3";
-    nested_dissection(n, xadj, adj, opt.nd_leaf > 0 ? opt.nd_leaf : (std::getenv("GMRFB_ND_LEAF") ? std::atoi(std::getenv("GMRFB_ND_LEAF")) : 0), opt.coords ? opt.coord_dim : 0, opt.coords, S.perm_user);
+    nested_dissection(n, xadj, adj, opt.nd_leaf > 0 ? opt.nd_leaf : (std::getenv("GMRFB_ND_LEAF") ? std::atoi(std::getenv("GMRFB_ND_LEAF")) : 0), opt.coords ? opt.coord_dim : 0, opt.coords, S.perm_user, false);
   } else if (opt.ordering_kind == 3) {
     amd_order(n, xadj, adj, S.perm_user);
+  } else if (opt.ordering_kind == 4) {
+    if (opt.coords && (opt.coord_dim < 1 || opt.coord_dim > 3)) return "coord_dim must be 1..3";
+    nested_dissection(n, xadj, adj, opt.nd_leaf > 0 ? opt.nd_leaf : (std::getenv("GMRFB_ND_LEAF") ? std::atoi(std::getenv("GMRFB_ND_LEAF")) : 0), opt.coords ? opt.coord_dim : 0, opt.coords, S.perm_user, true);
   } else {
     return "unknown ordering kind";
   }

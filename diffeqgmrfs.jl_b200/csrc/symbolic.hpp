@@ -82,8 +82,10 @@ void postorder_tree(int32_t n, const std::vector<int32_t>& parent, std::vector<i
 void column_counts(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
                    const std::vector<int32_t>& parent, const std::vector<int32_t>& post,
                    std::vector<int32_t>& colcount);
-void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj, std::vector<int32_t>& perm);
+void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj, std::vector<int32_t>& perm,
+               int32_t nfree = -1);  // vertices >= nfree: halo (never eliminated); -1: none
 void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
-                       int leaf, int coord_dim, const double* coords, std::vector<int32_t>& perm);
+                       int leaf, int coord_dim, const double* coords, std::vector<int32_t>& perm,
+                       bool amd_leaves = false);  // amd_leaves: halo-AMD inside the leaf subdomains (default leaf 200)
 
 }  // namespace gmrfb

@@ -179,7 +179,7 @@ class Symbolic:
         if perm is not None:
             opts.ordering_kind = B.ORDER_GIVEN
         else:
-            opts.ordering_kind = {"nd": B.ORDER_ND, "natural": B.ORDER_NATURAL, "amd": B.ORDER_AMD}[ordering]
+            opts.ordering_kind = {"nd": B.ORDER_ND, "natural": B.ORDER_NATURAL, "amd": B.ORDER_AMD, "nd_amd": B.ORDER_ND_AMD}[ordering]
         opts.storage = storage
         opts.base = 0
         self._coords = None

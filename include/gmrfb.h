@@ -91,8 +91,10 @@ enum { /* ordering_kind */
   GMRFB_ORDER_GIVEN = 0,   /* use `perm` exactly (Julia `perm=p`): the factor's .p equals perm */
   GMRFB_ORDER_NATURAL = 1, /* identity */
   GMRFB_ORDER_ND = 2,      /* library's nested dissection (graph BFS bisection; coordinates if supplied) */
-  GMRFB_ORDER_AMD = 3      /* approximate minimum degree on the quotient graph (Amestoy-Davis-Duff): what the
+  GMRFB_ORDER_AMD = 3,     /* approximate minimum degree on the quotient graph (Amestoy-Davis-Duff): what the
                               reference's `cholesky(A)` without `perm` asks CHOLMOD for; ties are this library's */
+  GMRFB_ORDER_ND_AMD = 4   /* nested dissection down to leaves of nd_leaf (default 200) vertices, each leaf ordered by
+                              halo-AMD (minimum degree aware of the surrounding separators)                          */
 };
 enum { /* storage */
   GMRFB_STORAGE_FULL = 0,  /* both triangles stored (Julia Symmetric(sparse) of an assembled matrix) */

@@ -146,3 +146,26 @@ def test_amd_fill_quality(pkg, W):
     nd = pkg.Symbolic(prob["Qpost"], host_only=True).info
     assert amd.flops < 0.5 * nat.flops
     assert amd.nnz_L < 1.3 * nd.nnz_L
+
+
+# ------------------------------------------------- nested dissection with halo-AMD leaves (ORDER_ND_AMD) ----
+@pytest.mark.parametrize("nx", [5, 13, 40, 70])
+def test_nd_amd_ordering_mesh(pkg, orc, W, nx):
+    prob = W.matern_posterior(nx, obs_frac=0.2, corr_range=0.3)
+    _check(pkg, orc, prob["Qpost"], ordering="nd_amd")
+    _check(pkg, orc, prob["Qpost"], ordering="nd_amd", coords=prob["nodes"])
+    _check(pkg, orc, prob["Qpost"], ordering="nd_amd", nd_leaf=30)  # several leaves with halos even on small meshes
+
+
+def test_nd_amd_edge_patterns_and_fill(pkg, orc, W):
+    _check(pkg, orc, sp.identity(1, format="csc"), ordering="nd_amd")
+    _check(pkg, orc, sp.identity(50, format="csc"), ordering="nd_amd")
+    blocks = [sp.csc_matrix(np.ones((7, 7))), sp.identity(3), sp.csc_matrix(np.ones((20, 20)))]
+    _check(pkg, orc, sp.block_diag(blocks, format="csc"), ordering="nd_amd", nd_leaf=8)
+    R = sp.random(300, 300, density=0.02, random_state=2, format="csc")
+    _check(pkg, orc, (R + R.T + sp.identity(300)).tocsc(), ordering="nd_amd", nd_leaf=40)
+    # ordering the leaves by minimum degree must not lose against leaves left in BFS order
+    prob = W.matern_posterior(90, obs_frac=0.1, corr_range=0.2)
+    nd = pkg.Symbolic(prob["Qpost"], host_only=True, nd_leaf=200).info
+    nda = pkg.Symbolic(prob["Qpost"], host_only=True, ordering="nd_amd", nd_leaf=200).info
+    assert nda.nnz_L <= nd.nnz_L and nda.flops <= nd.flops
