@@ -310,6 +310,20 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
         }
         if (mcut >= nl - 1) mcut = nl - 2;
         if (mcut < 1) mcut = 1;
+        // tuning aid GMRFB_ND_BALANCE=f (0 < f < 0.5, default off): among the levels whose cut leaves at least a
+        // fraction f of the vertices on either side, take the narrowest one instead of the median level
+        static const double balance = std::getenv("GMRFB_ND_BALANCE") ? std::atof(std::getenv("GMRFB_ND_BALANCE")) : 0.0;
+        if (balance > 0.0 && balance < 0.5) {
+          int64_t below = 0;
+          int32_t best = mcut;
+          for (int l = 0; l < nl - 1; l++) {
+            // cutting at level l: A = levels < l, S subset of level l, B = levels > l
+            const int64_t above = (int64_t)m - below - cnt[l];
+            if (l >= 1 && (double)below >= balance * m && (double)above >= balance * m && cnt[l] < cnt[best]) best = l;
+            below += cnt[l];
+          }
+          mcut = best;
+        }
         tmp.assign(q.begin(), q.end());
         for (int32_t k = 0; k < m; k++) {
           int32_t v = tmp[k];
