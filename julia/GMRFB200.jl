@@ -22,7 +22,7 @@ const libgmrfb = get(ENV, "GMRFB_LIB", joinpath(@__DIR__, "..", "diffeqgmrfs.jl_
 
 const GMRFB_OK = Int32(0)
 const GMRFB_ERR_NOT_SPD = Int32(2)
-const ORDER_GIVEN, ORDER_NATURAL, ORDER_ND, ORDER_AMD = Int32(0), Int32(1), Int32(2), Int32(3)
+const ORDER_GIVEN, ORDER_NATURAL, ORDER_ND, ORDER_AMD, ORDER_ND_AMD = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
 const SOLVE_A, SOLVE_PTL, SOLVE_UP, SOLVE_L, SOLVE_LT = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
 const BTD_SOLVE_A, BTD_SOLVE_FWD, BTD_SOLVE_BWD = Int32(0), Int32(1), Int32(2)
 
