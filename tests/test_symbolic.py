@@ -169,3 +169,42 @@ def test_nd_amd_edge_patterns_and_fill(pkg, orc, W):
     nd = pkg.Symbolic(prob["Qpost"], host_only=True, nd_leaf=200).info
     nda = pkg.Symbolic(prob["Qpost"], host_only=True, ordering="nd_amd", nd_leaf=200).info
     assert nda.nnz_L <= nd.nnz_L and nda.flops <= nd.flops
+
+
+# ------------------------------------------------------------- separator refinement of the nested dissection ----
+def test_nd_regular_coordinates_with_ties(pkg, orc, W):
+    """Structured meshes: whole grid lines share a coordinate; the cut is snapped to a gap between distinct values."""
+    for nx in (5, 13, 40):
+        prob = W.matern_posterior(nx, obs_frac=0.2, corr_range=0.3)
+        g = np.linspace(0.0, 1.0, nx)
+        X, Y = np.meshgrid(g, g)
+        _check(pkg, orc, prob["Qpost"], coords=np.column_stack([X.ravel(), Y.ravel()]))
+        _check(pkg, orc, prob["Qpost"], coords=np.column_stack([X.ravel(), np.zeros(nx * nx)]))  # degenerate axis
+
+
+def test_vertex_cover_separators_reduce_fill():
+    """GMRFB_ND_COVER is read once per process, so the two variants run in subprocesses: on a jittered mesh the
+    minimum-vertex-cover separators must need clearly fewer flops than the plain boundary layers, for the geometric
+    and no more for the graph dissection."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json; sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as g\n"
+        "pkg = g.load_pkg(); prob = pkg.workloads.matern_posterior(90, obs_frac=0.1, corr_range=0.2)\n"
+        "geo = pkg.Symbolic(prob['Qpost'], host_only=True, coords=prob['nodes']).info\n"
+        "gra = pkg.Symbolic(prob['Qpost'], host_only=True).info\n"
+        "print(json.dumps([geo.flops, geo.nnz_L, gra.flops, gra.nnz_L]))\n" % root
+    )
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, GMRFB_ND_COVER=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr
+        out[flag] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["1"][0] < 0.9 * out["0"][0] and out["1"][1] < out["0"][1]  # geometric: at least 10 % fewer flops
+    assert out["1"][2] <= 1.02 * out["0"][2]                               # graph: no worse
