@@ -4,6 +4,9 @@
 //  - column counts: Gilbert, Ng & Peyton (1994) skeleton-leaf / least-common-ancestor scheme;
 //  - nested dissection: George & Liu automatic ND (BFS level-structure bisection from a pseudo-peripheral
 //    vertex) with a boundary-layer vertex separator; coordinate bisection when node coordinates are supplied;
+//    separators refined to a minimum vertex cover of the cut edges (Liu 1989 / Pothen & Fan 1990: Hopcroft-Karp
+//    maximum matching + Koenig's theorem); optional halo-AMD ordering of the leaf subdomains;
+//  - approximate minimum degree: Amestoy, Davis & Duff (1996) on the quotient graph, with an optional halo;
 //  - relaxed supernode amalgamation in the spirit of CHOLMOD's nrelax/zrelax rule, tuned for wide GPU fronts.
 #include "symbolic.hpp"
 
