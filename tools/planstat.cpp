@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
     for (int ph = 0; ph < 2; ph++) {
       Plan P; if (ph == 0) build_factor_plan(S, P); else build_selinv_plan(S, P);
       std::map<int, std::pair<int, double>> by;  // kind -> (launches, flops)
-      double kb[6] = {0, 0, 0, 0, 0, 0}, tiles = 0; int chain = 0, small_grid = 0;
+      double kb[6] = {0, 0, 0, 0, 0, 0}, tiles = 0, model_ns = 0; int chain = 0, small_grid = 0;
       for (auto& L : P.launches) {
         by[L.kind].first++; by[L.kind].second += L.flops;
         if (L.grid < 148) small_grid++;
@@ -38,10 +38,14 @@ int main(int argc, char** argv) {
             double fl = tri ? (double)T.K * ((double)std::min(T.M, T.N) * (std::min(T.M, T.N) + 1) + 2.0 * (T.M - std::min(T.M, T.N)) * std::min(T.M, T.N)) : 2.0 * T.M * T.N * T.K;
             int b = T.K <= 32 ? 0 : T.K <= 64 ? 1 : T.K <= 128 ? 2 : T.K <= 256 ? 3 : T.K <= 512 ? 4 : 5;
             kb[b] += fl;
+            // per-tile cost of the 2-stage 64x64 engine fitted to tools/probe/gemm_batched_probe.cu on B200
+            // (K = 29 ... 4096: 19, 25, 34, 74, 124, 1003 ns per tile, GPU-wide): 12 ns + 0.243 ns * K
+            model_ns += gemm_tiles(T.M, T.N, tri, GCFG_SMALL) * (12.0 + 0.243 * T.K);
           }
         }
       }
       printf("  %s plan: %zu launches (%d with grid < 148, %d POTRF steps), flops %.4g, GEMM tiles %.0f\n", ph == 0 ? "factor" : "selinv", P.launches.size(), small_grid, chain, P.flops, tiles);
+      printf("    GEMM time predicted by the per-tile model (saturated GPU, no launch latency): %.1f ms\n", model_ns * 1e-6);
       printf("    GEMM GFLOP by K: <=32 %.1f | <=64 %.1f | <=128 %.1f | <=256 %.1f | <=512 %.1f | >512 %.1f\n", kb[0] / 1e9, kb[1] / 1e9, kb[2] / 1e9, kb[3] / 1e9, kb[4] / 1e9, kb[5] / 1e9);
       for (auto& kv : by) printf("    kind %2d: %4d launches %.4g flops\n", kv.first, kv.second.first, kv.second.second);
     }
