@@ -684,6 +684,44 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
   if (nfree < 0 || nfree > n) nfree = n;
   perm.assign(nfree, 0);
   if (nfree == 0) return;
+  // Dense rows (degree above max(16, 10 sqrt(n)), the SuiteSparse AMD rule) are taken out and ordered last: a vertex
+  // adjacent to nearly everything is rescanned at every one of its neighbours' eliminations (quadratic time) and ends
+  // up in the last front whatever the order.
+  {
+    const double thresh = std::max(16.0, 10.0 * std::sqrt((double)n));
+    std::vector<int32_t> dense;
+    for (int32_t i = 0; i < nfree; i++)
+      if ((double)(xadj[i + 1] - xadj[i]) > thresh) dense.push_back(i);
+    if (!dense.empty() && (int32_t)dense.size() < nfree) {
+      std::vector<int32_t> newid(n, -1), oldid;
+      std::vector<char> isd(n, 0);
+      for (int32_t d : dense) isd[d] = 1;
+      for (int32_t i = 0; i < n; i++)
+        if (!isd[i]) {
+          newid[i] = (int32_t)oldid.size();
+          oldid.push_back(i);
+        }
+      const int32_t n2 = (int32_t)oldid.size(), nfree2 = nfree - (int32_t)dense.size();
+      std::vector<int64_t> x2(n2 + 1, 0);
+      std::vector<int32_t> a2;
+      a2.reserve(adj.size());
+      for (int32_t k = 0; k < n2; k++) {
+        const int32_t i = oldid[k];
+        for (int64_t p = xadj[i]; p < xadj[i + 1]; p++)
+          if (!isd[adj[p]]) a2.push_back(newid[adj[p]]);
+        x2[k + 1] = (int64_t)a2.size();
+      }
+      std::vector<int32_t> p2;
+      amd_order(n2, x2, a2, p2, nfree2);  // no vertex of the reduced graph exceeds the threshold of the original n
+      std::stable_sort(dense.begin(), dense.end(), [&](int32_t a, int32_t b) {
+        return (xadj[a + 1] - xadj[a]) < (xadj[b + 1] - xadj[b]);
+      });
+      int32_t k = 0;
+      for (int32_t v : p2) perm[k++] = oldid[v];
+      for (int32_t d : dense) perm[k++] = d;
+      return;
+    }
+  }
   AmdWork W;
   W.n = n;
   const int64_t nnz = xadj[n];

@@ -208,3 +208,30 @@ def test_vertex_cover_separators_reduce_fill():
         out[flag] = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["1"][0] < 0.9 * out["0"][0] and out["1"][1] < out["0"][1]  # geometric: at least 10 % fewer flops
     assert out["1"][2] <= 1.02 * out["0"][2]                               # graph: no worse
+
+
+def test_amd_dense_rows_are_ordered_last(pkg, orc):
+    """A vertex adjacent to (nearly) everything is removed before the minimum-degree elimination and ordered last
+    (SuiteSparse AMD's dense-row rule): no quadratic rescans, and the arrow matrix still factors without fill."""
+    import time
+
+    n = 30000
+    rows = np.concatenate([np.zeros(n - 1, int), np.arange(1, n)])
+    cols = np.concatenate([np.arange(1, n), np.zeros(n - 1, int)])
+    A = (sp.coo_matrix((np.ones(2 * (n - 1)), (rows, cols)), shape=(n, n)) + sp.identity(n) * n).tocsc()
+    t0 = time.time()
+    sym = pkg.Symbolic(A, host_only=True, ordering="amd")
+    assert time.time() - t0 < 5.0
+    assert sym.info.nnz_L == 2 * n - 1 and sym.p[-1] == 0
+    # a hub on top of a mesh: same etree / counts as the oracle, hub last
+    m = 40
+    T = sp.diags([np.ones(m - 1), np.ones(m - 1)], [-1, 1])
+    G = sp.kron(sp.identity(m), T) + sp.kron(T, sp.identity(m))
+    N = m * m + 1
+    H = sp.lil_matrix((N, N))
+    H[:m * m, :m * m] = G
+    H[m * m, :m * m] = 1.0
+    H[:m * m, m * m] = 1.0
+    H.setdiag(10.0)
+    sym = _check(pkg, orc, H.tocsc(), ordering="amd")
+    assert sym.p[-1] == m * m
