@@ -406,7 +406,8 @@ def run_gpu_arm(args):
                                "different values; the reference's dataset loop), each on its own CUDA stream",
                    "n": n, "nnz_Q": int(Qp.nnz), "nnz_L": int(info.nnz_L), "factor_flops": info.flops,
                    "nsuper": int(info.nsuper), "levels": int(info.nlevels), "max_front": int(info.max_front),
-                   "front_arena_gb": info.front_bytes / 1e9, "ordering": {"nd": "library nested dissection (geometric)",
+                   "front_arena_gb": info.front_bytes / 1e9, "ordering": {"nd": "library nested dissection (geometric, minimum-vertex-cover separators"
+                                      + (")" if os.environ.get("GMRFB_ND_COVER", "1") != "0" else " off: plain boundary layers)"),
                                 "ndgraph": "library nested dissection (graph bisection, no coordinates)",
                                 "nd_amd": "library nested dissection (graph) with halo-AMD leaves",
                                 "amd": "library approximate minimum degree"}[args.ordering],
