@@ -11,7 +11,7 @@ from .solver import (  # noqa: F401
     CholeskyFactor, CholeskySolverBlueprint, Context, DeviceGaussNewton, GMRF, GNCholeskySolverBlueprint, GaussNewtonOptimizer,
     PosteriorPrecision, RBMCStrategy, SparseMatrix, Symbolic, TakahashiStrategy, TridiagonalCholeskyFactor,
     backward_solve, cholesky, condition_on_observations, default_context, forward_solve, ldiv, ldiv_, mean, metrics,
-    optimize, precision_map, rand, sqmahal, std, to_matrix, tridiagonal_cholesky, tridiagonal_cholesky_dense, tridiagonal_cholesky_ssm, var,
+    optimize, pool_trim, precision_map, rand, sqmahal, std, to_matrix, tridiagonal_cholesky, tridiagonal_cholesky_dense, tridiagonal_cholesky_ssm, var,
 )
 from ._lib import GmrfbError, NotPositiveDefinite  # noqa: F401
 

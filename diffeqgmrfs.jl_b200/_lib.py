@@ -86,6 +86,8 @@ SIGNATURES = {
     "gmrfb_fac_get_L": (C.c_int32, [_P, C.c_int32, C.c_int32, _I64P, _I64P, _F64P]),
     "gmrfb_solve": (C.c_int32, [_P, C.c_int32, _F64P, C.c_int64, C.c_int64]),
     "gmrfb_solve_dev": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, C.c_int64]),
+    "gmrfb_solve_refined": (C.c_int32, [_P, _P, _F64P, C.c_int64, C.c_int64, C.c_int32, _F64P]),
+    "gmrfb_pool_trim": (C.c_int32, [C.c_int64, _I64P]),
     "gmrfb_sample": (C.c_int32, [_P, _F64P, _F64P, C.c_int64, _F64P, C.c_int64, C.c_int64]),
     "gmrfb_var_selinv": (C.c_int32, [_P, _F64P]),
     "gmrfb_var_selinv_dev": (C.c_int32, [_P, _P]),

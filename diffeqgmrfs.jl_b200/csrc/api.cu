@@ -67,7 +67,14 @@ extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) {
   GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_scalar, 16 * sizeof(double)));
   GMRFB_CU(nullptr, kernels_init());
   GMRFB_CU(nullptr, sparse_kernels_init());
+  DevPool::get().ctx_created();
   *out = c.release();
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_pool_trim(int64_t keep_bytes, int64_t* cached_bytes_out) {
+  DevPool::get().trim(keep_bytes > 0 ? (size_t)keep_bytes : 0);
+  if (cached_bytes_out) *cached_bytes_out = (int64_t)DevPool::get().cached();
   return GMRFB_OK;
 }
 
@@ -84,6 +91,7 @@ extern "C" gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx) {
   if (ctx->ev_lane) cudaEventDestroy(ctx->ev_lane);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  DevPool::get().ctx_destroyed();
   return GMRFB_OK;
 }
 
@@ -136,6 +144,11 @@ static const char* prof_name(int kind) {
     case PK_SCATTER: return "k_scatter_values";
     case PK_MEMSET: return "memset(front arena)";
     case PK_PERM: return "k_perm_gather/scatter";
+    case PK_PERM_MR: return "k_mr_perm_in/out";
+    case LK_MR_FWD_SMALL: return "k_mr_fwd_small";
+    case LK_MR_BWD_SMALL: return "k_mr_bwd_small";
+    case LK_MR_ASSEMBLE: return "k_mr_assemble";
+    case LK_MR_GATHER: return "k_mr_gather";
   }
   return "other";
 }
@@ -705,6 +718,64 @@ gmrfb_status sweep_bwd(gmrfb_fac* fac, double* t, double* xs, int nr) {
   return GMRFB_OK;
 }
 
+
+// ---- panel (multi-right-hand-side) sweeps: solve_mr.cu + build_solve_mr_plans ----
+gmrfb_status sym_get_mr(gmrfb_sym* sym, int nr, gmrfb_sym::MrPlans** out) {
+  gmrfb_ctx* ctx = sym->ctx;
+  auto it = sym->mr_plans.find(nr);
+  if (it == sym->mr_plans.end()) {
+    if (sym->mr_plans.size() >= 8) {  // bounded cache of panel widths; queued launches may still read the old task lists
+      GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+      sym->mr_plans.clear();
+    }
+    std::unique_ptr<gmrfb_sym::MrPlans> mp(new gmrfb_sym::MrPlans());
+    mp->nr = nr;
+    mp->ldk = (nr + 7) & ~7;
+    build_solve_mr_plans(sym->S, sym->factor_plan.host.winv_slot, nr, mp->ldk, mp->fwd.host, mp->bwd.host);
+    GMRFB_CU(ctx, mp->fwd.tasks.upload(mp->fwd.host.tasks, ctx->stream));
+    GMRFB_CU(ctx, mp->bwd.tasks.upload(mp->bwd.host.tasks, ctx->stream));
+    mp->fwd.ready = mp->bwd.ready = true;
+    it = sym->mr_plans.emplace(nr, std::move(mp)).first;
+  }
+  *out = it->second.get();
+  return GMRFB_OK;
+}
+
+gmrfb_status fac_ensure_mr(gmrfb_fac* fac, bool staging) {
+  gmrfb_ctx* ctx = fac->ctx;
+  const int64_t n = std::max<int64_t>(fac->sym->S.n, 1);
+  if (!fac->mr_x.p) GMRFB_CU(ctx, fac->mr_x.alloc((size_t)n * MR_MAX));
+  if (!fac->mr_u.p) GMRFB_CU(ctx, fac->mr_u.alloc((size_t)std::max<int64_t>(fac->sym->uvec_rows, 1) * MR_MAX));
+  if (staging && !fac->mr_io.p) GMRFB_CU(ctx, fac->mr_io.alloc((size_t)n * MR_MAX));
+  return GMRFB_OK;
+}
+
+// The panel fac->mr_x (nr x n, node-major, internal ordering) through L^{-1} and / or L^{-T}, in place.
+gmrfb_status sweep_panel(gmrfb_fac* fac, bool fwd, bool bwd, int nr) {
+  gmrfb_sym* sym = fac->sym;
+  gmrfb_sym::MrPlans* mp = nullptr;
+  gmrfb_status rc = sym_get_mr(sym, nr, &mp);
+  if (rc != GMRFB_OK) return rc;
+  Arenas ar{{fac->arena.p, fac->mr_x.p, fac->mr_u.p, nullptr}};
+  ar.dinv = fac->dinv.p;
+  LaunchAux aux;
+  aux.d_relmap = sym->d_relmap.p;
+  aux.d_snodes = sym->d_snodes.p;
+  aux.d_child_idx = sym->d_child_idx.p;
+  aux.d_rows = sym->d_rows.p;
+  aux.nr = nr;
+  aux.ldk = mp->ldk;
+  if (fwd) rc = run_plan(fac->ctx, mp->fwd, ar, aux);
+  if (rc == GMRFB_OK && bwd) rc = run_plan(fac->ctx, mp->bwd, ar, aux);
+  return rc;
+}
+
+// split nrhs right-hand sides into the fewest, equally wide panels of at most MR_MAX columns
+inline int64_t panel_width(int64_t nrhs) {
+  const int64_t chunks = (nrhs + MR_MAX - 1) / MR_MAX;
+  return (nrhs + chunks - 1) / chunks;
+}
+
 struct ModeSpec {
   bool fwd, bwd;
   bool in_perm;   // gather input through perm (original ordering) instead of post (perm ordering)
@@ -729,6 +800,30 @@ gmrfb_status solve_device(gmrfb_fac* fac, int mode, const double* d_in, int64_t 
   const int64_t n = sym->S.n;
   ModeSpec m;
   if (!mode_spec(mode, m)) return fail(ctx, GMRFB_ERR_INVALID, "unknown solve mode");
+  if (nrhs > SOLVE_NRC) {
+    // batches: one sweep over L per panel of up to MR_MAX right-hand sides
+    gmrfb_status rc = fac_ensure_mr(fac, false);
+    if (rc != GMRFB_OK) return rc;
+    const int64_t pw = panel_width(nrhs);
+    for (int64_t c0 = 0; c0 < nrhs; c0 += pw) {
+      const int nr = (int)std::min<int64_t>(pw, nrhs - c0), ldk = (nr + 7) & ~7;
+      {
+        ProfScope ps(ctx, PK_PERM_MR, 0, 16.0 * n * nr);
+        GMRFB_CU(ctx, launch_mr_perm_in(d_in + c0 * ldin, ldin, fac->mr_x.p, ldk, m.in_perm ? sym->d_perm.p : sym->d_post.p, n,
+                                        nr, ctx->stream));
+      }
+      ctx->launches++;
+      rc = sweep_panel(fac, m.fwd, m.bwd, nr);
+      if (rc != GMRFB_OK) return rc;
+      {
+        ProfScope ps(ctx, PK_PERM_MR, 0, 16.0 * n * nr);
+        GMRFB_CU(ctx, launch_mr_perm_out(fac->mr_x.p, ldk, d_out + c0 * ldout, ldout,
+                                         m.out_perm ? sym->d_perm.p : sym->d_post.p, n, nr, d_mean, ctx->stream));
+      }
+      ctx->launches++;
+    }
+    return GMRFB_OK;
+  }
   for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
     // fwd: xwork -> ywork;  bwd: ywork -> xwork
@@ -759,6 +854,8 @@ extern "C" gmrfb_status gmrfb_solve_dev(gmrfb_fac* fac, int32_t mode, double* d_
   // in-place: stage each chunk through bwork so gather/scatter never alias
   gmrfb_ctx* ctx = fac->ctx;
   const int64_t n = fac->sym->S.n;
+  if (nrhs > SOLVE_NRC)  // panel path: the gather into the panel finishes before the scatter back starts
+    return solve_device(fac, mode, d_X, ldx, d_X, ldx, nrhs, nullptr);
   for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
     GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), d_X + c0 * ldx, ldx * sizeof(double),
@@ -777,6 +874,22 @@ extern "C" gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int
   if (ldx < n || nrhs < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_solve: bad ldx/nrhs");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   DevBuf<double>& out = fac->owork;  // persistent staging: no cudaMalloc/cudaFree on the solve path
+  if (nrhs > SOLVE_NRC) {
+    gmrfb_status rc = fac_ensure_mr(fac, true);
+    if (rc != GMRFB_OK) return rc;
+    const int64_t pw = panel_width(nrhs);
+    for (int64_t c0 = 0; c0 < nrhs; c0 += pw) {
+      const int64_t nr = std::min<int64_t>(pw, nrhs - c0);
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->mr_io.p, n * sizeof(double), X + c0 * ldx, ldx * sizeof(double),
+                                      n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
+      rc = solve_device(fac, mode, fac->mr_io.p, n, fac->mr_io.p, n, nr, nullptr);
+      if (rc != GMRFB_OK) return rc;
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(X + c0 * ldx, ldx * sizeof(double), fac->mr_io.p, n * sizeof(double),
+                                      n * sizeof(double), nr, cudaMemcpyDeviceToHost, ctx->stream));
+      GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GMRFB_OK;
+  }
   for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
     GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), X + c0 * ldx, ldx * sizeof(double),
@@ -790,6 +903,60 @@ extern "C" gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int
   return GMRFB_OK;
 }
 
+extern "C" gmrfb_status gmrfb_solve_refined(gmrfb_fac* fac, const gmrfb_spm* Q, double* X, int64_t ldx, int64_t nrhs,
+                                            int32_t max_iter, double* resid_out) {
+  if (!fac || !Q || !X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_solve_refined: NULL argument");
+  if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_solve_refined: no successful factorisation");
+  gmrfb_ctx* ctx = fac->ctx;
+  gmrfb_sym* sym = fac->sym;
+  const int64_t n = sym->S.n;
+  if (Q->m != n || Q->n != n) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_solve_refined: Q has the wrong shape");
+  if (ldx < n || nrhs < 0 || max_iter < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_solve_refined: bad ldx/nrhs/max_iter");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // workspaces (n doubles each, original ordering): b, x, r / correction, best iterate
+  if (fac->refine_ws.n < (size_t)(4 * std::max<int64_t>(n, 1))) GMRFB_CU(ctx, fac->refine_ws.alloc((size_t)(4 * std::max<int64_t>(n, 1))));
+  double *db = fac->refine_ws.p, *dx = db + n, *dr = dx + n, *dbest = dr + n;
+  auto dot_host = [&](const double* a, double* out) -> gmrfb_status {
+    GMRFB_CU(ctx, launch_dot(a, a, n, ctx->d_scalar, st));
+    ctx->launches++;
+    GMRFB_CU(ctx, cudaMemcpyAsync(out, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, st));
+    GMRFB_CU(ctx, cudaStreamSynchronize(st));
+    return GMRFB_OK;
+  };
+  for (int64_t c = 0; c < nrhs; c++) {
+    GMRFB_CU(ctx, cudaMemcpyAsync(db, X + c * ldx, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    double bb = 0;
+    gmrfb_status rc = dot_host(db, &bb);
+    if (rc != GMRFB_OK) return rc;
+    rc = solve_device(fac, GMRFB_SOLVE_A, db, n, dx, n, 1, nullptr);
+    if (rc != GMRFB_OK) return rc;
+    double best = -1.0;
+    for (int it = 0;; it++) {
+      // r = b - Q x   (Q symmetric: its CSC columns double as rows)
+      GMRFB_CU(ctx, cudaMemcpyAsync(dr, db, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      GMRFB_CU(ctx, launch_spmv_rows(n, Q->d_colptr.p, Q->d_rowidx.p, Q->d_val.p, dx, dr, -1.0, 1.0, st));
+      ctx->launches++;
+      double rr = 0;
+      rc = dot_host(dr, &rr);
+      if (rc != GMRFB_OK) return rc;
+      const double res = bb > 0 ? std::sqrt(rr / bb) : std::sqrt(rr);
+      if (best >= 0 && !(res < best)) break;  // no further progress: keep the previous iterate
+      best = res;
+      GMRFB_CU(ctx, cudaMemcpyAsync(dbest, dx, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if (it >= max_iter || res == 0.0) break;
+      rc = solve_device(fac, GMRFB_SOLVE_A, dr, n, dr, n, 1, nullptr);  // correction, in place
+      if (rc != GMRFB_OK) return rc;
+      GMRFB_CU(ctx, launch_axpby(n, 1.0, dx, 1.0, dr, dx, st));
+      ctx->launches++;
+    }
+    if (resid_out) resid_out[c] = best;
+    GMRFB_CU(ctx, cudaMemcpyAsync(X + c * ldx, dbest, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GMRFB_CU(ctx, cudaStreamSynchronize(st));
+  }
+  return GMRFB_OK;
+}
+
 extern "C" gmrfb_status gmrfb_sample(gmrfb_fac* fac, const double* mean, const double* Z, int64_t ldz, double* X,
                                      int64_t ldx, int64_t nrhs) {
   if (!fac || !Z || !X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sample: NULL argument");
@@ -799,16 +966,32 @@ extern "C" gmrfb_status gmrfb_sample(gmrfb_fac* fac, const double* mean, const d
   if (ldz < n || ldx < n || nrhs < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_sample: bad leading dimension");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   DevBuf<double>& out = fac->owork;
-  DevBuf<double> dmean;
-  if (mean) {
-    GMRFB_CU(ctx, dmean.alloc((size_t)std::max<int64_t>(n, 1)));
-    GMRFB_CU(ctx, cudaMemcpyAsync(dmean.p, mean, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (mean) {  // persistent in the handle: no allocation (and no device-wide synchronisation of a release) per call
+    if (!fac->meanbuf.p) GMRFB_CU(ctx, fac->meanbuf.alloc((size_t)std::max<int64_t>(n, 1)));
+    GMRFB_CU(ctx, cudaMemcpyAsync(fac->meanbuf.p, mean, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const double* dmean = mean ? fac->meanbuf.p : nullptr;
+  if (nrhs > SOLVE_NRC) {
+    gmrfb_status rc = fac_ensure_mr(fac, true);
+    if (rc != GMRFB_OK) return rc;
+    const int64_t pw = panel_width(nrhs);
+    for (int64_t c0 = 0; c0 < nrhs; c0 += pw) {
+      const int64_t nr = std::min<int64_t>(pw, nrhs - c0);
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->mr_io.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
+                                      n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
+      rc = solve_device(fac, GMRFB_SOLVE_UP, fac->mr_io.p, n, fac->mr_io.p, n, nr, dmean);
+      if (rc != GMRFB_OK) return rc;
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(X + c0 * ldx, ldx * sizeof(double), fac->mr_io.p, n * sizeof(double),
+                                      n * sizeof(double), nr, cudaMemcpyDeviceToHost, ctx->stream));
+      GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GMRFB_OK;
   }
   for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
     GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
                                     n * sizeof(double), nr, cudaMemcpyHostToDevice, ctx->stream));
-    gmrfb_status rc = solve_device(fac, GMRFB_SOLVE_UP, fac->bwork.p, n, out.p, n, nr, mean ? dmean.p : nullptr);
+    gmrfb_status rc = solve_device(fac, GMRFB_SOLVE_UP, fac->bwork.p, n, out.p, n, nr, dmean);
     if (rc != GMRFB_OK) return rc;
     GMRFB_CU(ctx, cudaMemcpy2DAsync(X + c0 * ldx, ldx * sizeof(double), out.p, n * sizeof(double), n * sizeof(double), nr,
                                     cudaMemcpyDeviceToHost, ctx->stream));
@@ -926,12 +1109,36 @@ extern "C" gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const
   if (ldz < n || nsamp <= 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_var_rbmc: bad ldz/nsamp");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   const int64_t ldk = (nsamp + 3) & ~(int64_t)3;
-  DevBuf<double> Xs, dvar;
-  GMRFB_CU(ctx, Xs.alloc((size_t)ldk * std::max<int64_t>(n, 1)));
-  GMRFB_CU(ctx, dvar.alloc((size_t)std::max<int64_t>(n, 1)));
+  // sample panel (node-major, original ordering) and result: persistent in the handle, grown on demand
+  if ((int64_t)fac->rbmc_x.n < ldk * std::max<int64_t>(n, 1)) GMRFB_CU(ctx, fac->rbmc_x.alloc((size_t)ldk * std::max<int64_t>(n, 1)));
+  DevBuf<double>& Xs = fac->rbmc_x;
+  DevBuf<double>& dvar = fac->owork;
+  if (nsamp > SOLVE_NRC) {
+    // all samples of a panel in one backward sweep over L (RBMCStrategy(50): one sweep instead of 13)
+    gmrfb_status rc = fac_ensure_mr(fac, true);
+    if (rc != GMRFB_OK) return rc;
+    const int64_t pw = panel_width(nsamp);
+    for (int64_t c0 = 0; c0 < nsamp; c0 += pw) {
+      const int nr = (int)std::min<int64_t>(pw, nsamp - c0), lk = (nr + 7) & ~7;
+      // Z may be a host or a device pointer (unified addressing): normals drawn on the device need no PCIe round trip
+      GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->mr_io.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
+                                      n * sizeof(double), nr, cudaMemcpyDefault, ctx->stream));
+      {
+        ProfScope ps(ctx, PK_PERM_MR, 0, 16.0 * n * nr);
+        GMRFB_CU(ctx, launch_mr_perm_in(fac->mr_io.p, n, fac->mr_x.p, lk, sym->d_post.p, n, nr, ctx->stream));
+      }
+      ctx->launches++;
+      rc = sweep_panel(fac, false, true, nr);
+      if (rc != GMRFB_OK) return rc;
+      {
+        ProfScope ps(ctx, PK_PERM_MR, 0, 16.0 * n * nr);
+        GMRFB_CU(ctx, launch_mr_perm_nodemajor(fac->mr_x.p, lk, Xs.p, ldk, sym->d_perm.p, n, (int)c0, nr, ctx->stream));
+      }
+      ctx->launches++;
+    }
+  } else
   for (int64_t c0 = 0; c0 < nsamp; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nsamp - c0);
-    // Z may be a host or a device pointer (unified addressing): normals drawn on the device need no PCIe round trip
     GMRFB_CU(ctx, cudaMemcpy2DAsync(fac->bwork.p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
                                     n * sizeof(double), nr, cudaMemcpyDefault, ctx->stream));
     GMRFB_CU(ctx, launch_perm_gather(fac->bwork.p, n, fac->ywork.p, n, sym->d_post.p, n, nr, ctx->stream));

@@ -522,7 +522,7 @@ static gmrfb_status btd_sweep(gmrfb_btd* f, bool fwd, bool bwd, double* dXt, int
   const int64_t xstep = (int64_t)ldr * f->b, bs = (int64_t)f->ld * f->b;
   const size_t bytes = (size_t)(xstep * f->N) * sizeof(double);
   DevBuf<double> Y;
-  GMRFB_CU(ctx, Y.alloc((size_t)(xstep * f->N)));
+  GMRFB_CU(ctx, Y.alloc((size_t)(xstep * f->N), ctx->stream));
   if (!fwd) GMRFB_CU(ctx, cudaMemcpyAsync(Y.p, dXt, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   auto arenas = [&](int64_t i) {
     Arenas ar{{f->arena.p + i * f->slot, dXt + i * xstep, Y.p + i * xstep, f->winv.p + i * bs}};
@@ -566,8 +566,8 @@ extern "C" gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, i
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   const int ldr = (int)((nrhs + 1) & ~(int64_t)1);
   DevBuf<double> dX, dXt;
-  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs)));
-  GMRFB_CU(ctx, dXt.alloc((size_t)((int64_t)ldr * n)));
+  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs), ctx->stream));
+  GMRFB_CU(ctx, dXt.alloc((size_t)((int64_t)ldr * n), ctx->stream));
   GMRFB_CU(ctx, cudaMemcpy2DAsync(dX.p, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), nrhs,
                                   cudaMemcpyHostToDevice, ctx->stream));
   gmrfb_status rc = transpose_dev(ctx, dX.p, n, dXt.p, ldr, n, nrhs);
@@ -992,7 +992,7 @@ extern "C" gmrfb_status gmrfb_btd_dist_solve_begin(gmrfb_btd_dist* h, const doub
   h->solve_nrhs = inr;
   h->solve_ldr = ldr;
   DevBuf<double> dX;
-  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs)));
+  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs), ctx->stream));
   GMRFB_CU(ctx, h->Xt.alloc((size_t)((int64_t)ldr * n)));
   GMRFB_CU(ctx, cudaMemsetAsync(h->Xt.p, 0, h->Xt.n * sizeof(double), ctx->stream));
   GMRFB_CU(ctx, cudaMemcpy2DAsync(dX.p, n * sizeof(double), X_local, ldx * sizeof(double), n * sizeof(double), nrhs,
@@ -1062,7 +1062,7 @@ extern "C" gmrfb_status gmrfb_btd_dist_solve_end(gmrfb_btd_dist* h, const double
   rc = btd_sweep(h->interior, false, true, h->Xt.p, ldr, inr);
   if (rc != GMRFB_OK) return rc;
   DevBuf<double> dX;
-  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs)));
+  GMRFB_CU(ctx, dX.alloc((size_t)(n * nrhs), ctx->stream));
   rc = transpose_dev(ctx, h->Xt.p, ldr, dX.p, n, nrhs, n);
   if (rc != GMRFB_OK) return rc;
   GMRFB_CU(ctx, cudaMemcpy2DAsync(X_local, ldx * sizeof(double), dX.p, n * sizeof(double), n * sizeof(double), nrhs,

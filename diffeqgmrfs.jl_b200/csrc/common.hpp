@@ -65,28 +65,40 @@ inline gmrfb_status fail(gmrfb_ctx* ctx, gmrfb_status code, const std::string& m
 // pays cudaMalloc + cudaFree of those GB every iteration - and concurrent processes on one node serialise in the
 // driver on them (profiles/r01_multi_gpu.md).  Released buffers of >= 1 MB are kept (after the same device
 // synchronisation cudaFree implies) and handed to the next allocation of (nearly) the same size on the same device.
-// GMRFB_POOL=0 disables the cache, GMRFB_POOL_MAX_GB bounds it (default 64).
+// GMRFB_POOL=0 disables the cache, GMRFB_POOL_MAX_GB bounds it (default 24); gmrfb_pool_trim and the
+// destruction of the last context give the cached memory back to the driver.
 class DevPool {
  public:
   static DevPool& get() {
     static DevPool P;
     return P;
   }
-  cudaError_t alloc(void** out, size_t bytes, size_t* cap) {
+  // `st`: the stream the buffer will be used on first (nullptr: unknown).  A cached buffer that was released with work
+  // still queued on its stream carries an event; the new user waits for it (stream-ordered if `st` is known).
+  cudaError_t alloc(void** out, size_t bytes, size_t* cap, cudaStream_t st = nullptr) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (enabled_ && bytes >= kMin) {
-      std::lock_guard<std::mutex> lk(mu_);
+      std::unique_lock<std::mutex> lk(mu_);
       int best = -1;
       for (int i = 0; i < (int)free_.size(); i++)
         if (free_[i].dev == dev && free_[i].bytes >= bytes && free_[i].bytes <= bytes + bytes / 8 &&
             (best < 0 || free_[i].bytes < free_[best].bytes))
           best = i;
       if (best >= 0) {
-        *out = free_[best].p;
-        *cap = free_[best].bytes;
-        cached_ -= free_[best].bytes;
+        const Ent e = free_[best];
+        cached_ -= e.bytes;
         free_.erase(free_.begin() + best);
+        lk.unlock();
+        if (e.ev) {
+          if (st)
+            cudaStreamWaitEvent(st, e.ev, 0);
+          else
+            cudaEventSynchronize(e.ev);
+          cudaEventDestroy(e.ev);
+        }
+        *out = e.p;
+        *cap = e.bytes;
         return cudaSuccess;
       }
     }
@@ -99,25 +111,53 @@ class DevPool {
     *cap = bytes;
     return e;
   }
-  void release(void* p, size_t cap) {
+  // `st`: the only stream that may still have work queued on the buffer (temporaries of one API call); the release is
+  // then an event record instead of a device-wide synchronisation.  nullptr: unknown users => synchronise the device
+  // (what cudaFree would have done).
+  void release(void* p, size_t cap, cudaStream_t st = nullptr) {
     if (!enabled_ || cap < kMin) {
       cudaFree(p);
       return;
     }
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceSynchronize();  // what cudaFree would have done: no kernel still uses the buffer when it is reused
+    cudaEvent_t ev = nullptr;
+    if (st && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+      if (cudaEventRecord(ev, st) != cudaSuccess) {
+        cudaEventDestroy(ev);
+        ev = nullptr;
+      }
+    }
+    if (!ev) cudaDeviceSynchronize();
     {
       std::lock_guard<std::mutex> lk(mu_);
-      free_.push_back({p, cap, dev});
+      free_.push_back({p, cap, dev, ev});
       cached_ += cap;
     }
     trim(max_bytes_);
+  }
+  size_t cached() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return cached_;
+  }
+  // live contexts of the process: the last one to go trims the cache
+  void ctx_created() {
+    std::lock_guard<std::mutex> lk(mu_);
+    live_ctx_++;
+  }
+  void ctx_destroyed() {
+    bool last;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      last = --live_ctx_ <= 0;
+    }
+    if (last) trim(0);
   }
   // free cached buffers (oldest first) until at most `keep` bytes remain cached
   void trim(size_t keep) {
     std::lock_guard<std::mutex> lk(mu_);
     while (cached_ > keep && !free_.empty()) {
+      if (free_.front().ev) cudaEventDestroy(free_.front().ev);  // cudaFree waits for the device anyway
       cudaFree(free_.front().p);
       cached_ -= free_.front().bytes;
       free_.erase(free_.begin());
@@ -129,17 +169,19 @@ class DevPool {
     const char* e = std::getenv("GMRFB_POOL");
     enabled_ = !(e && e[0] == '0');
     const char* m = std::getenv("GMRFB_POOL_MAX_GB");
-    max_bytes_ = (size_t)((m ? std::atof(m) : 64.0) * 1e9);
+    max_bytes_ = (size_t)((m ? std::atof(m) : 24.0) * 1e9);
   }
   static constexpr size_t kMin = (size_t)1 << 20;
   struct Ent {
     void* p;
     size_t bytes;
     int dev;
+    cudaEvent_t ev;  // recorded on the releasing stream, or nullptr (device was synchronised)
   };
   std::mutex mu_;
   std::vector<Ent> free_;
   size_t cached_ = 0, max_bytes_ = 0;
+  int live_ctx_ = 0;
   bool enabled_ = true;
 };
 
@@ -149,20 +191,24 @@ struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   size_t cap = 0;  // bytes of the underlying allocation (>= n * sizeof(T) when it came from the cache)
+  cudaStream_t st = nullptr;  // set for temporaries of one API call: the only stream that uses the buffer
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) DevPool::get().release(p, cap);
+    if (p) DevPool::get().release(p, cap, st);
     p = nullptr;
     n = 0;
     cap = 0;
   }
-  cudaError_t alloc(size_t count) {
+  // stream != nullptr marks a temporary that is only ever used on that stream (stream-ordered reuse, no device-wide
+  // synchronisation when it is released)
+  cudaError_t alloc(size_t count, cudaStream_t stream = nullptr) {
     release();
+    st = stream;
     if (count == 0) return cudaSuccess;
-    cudaError_t e = DevPool::get().alloc((void**)&p, count * sizeof(T), &cap);
+    cudaError_t e = DevPool::get().alloc((void**)&p, count * sizeof(T), &cap, stream);
     if (e == cudaSuccess)
       n = count;
     else

@@ -1,5 +1,7 @@
 // Opaque handle definitions behind include/gmrfb.h.
 #pragma once
+#include <map>
+#include <memory>
 #include <vector>
 
 #include "common.hpp"
@@ -28,12 +30,21 @@ struct gmrfb_sym {
   std::vector<SolveLevel> solve_levels;
   gmrfb::DevBuf<gmrfb::Task> d_solve_tasks;
   int64_t partial_doubles = 0;
+  // panel (multi-right-hand-side) sweeps, one pair of plans per panel width (built on first use)
+  struct MrPlans {
+    gmrfb::DevPlan fwd, bwd;
+    int nr = 0, ldk = 0;
+  };
+  std::map<int, std::unique_ptr<MrPlans>> mr_plans;
 };
 
 struct gmrfb_fac {
   gmrfb_ctx* ctx = nullptr;
   gmrfb_sym* sym = nullptr;
   gmrfb::DevBuf<double> arena, zarena, zwork, zdiag, nzval, xwork, ywork, bwork, owork, uvec, partial, dinv, dinv_sel;
+  // panel solves: node-major panel X (MR_MAX x n), update panels U (MR_MAX x sum of r_J), column-major staging (n x MR_MAX)
+  gmrfb::DevBuf<double> mr_x, mr_u, mr_io;
+  gmrfb::DevBuf<double> meanbuf, rbmc_x, refine_ws;  // persistent workspaces of gmrfb_sample / gmrfb_var_rbmc
   bool factored = false, z_valid = false, logdet_valid = false;
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_column = -1;

@@ -870,7 +870,8 @@ cudaError_t kernels_init() {
   e = cudaFuncSetAttribute(k_front_factor_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_front_selinv_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
-  return e;
+  if (e != cudaSuccess) return e;
+  return mr_kernels_init();
 }
 
 // threads per CTA of the fused small-front kernels for a launch with `smem` bytes of dynamic shared memory
@@ -965,6 +966,11 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
         k_front_selinv_small<512><<<L.grid, 512, L.smem, st>>>(t, ar, aux.d_snodes, aux.d_relmap, aux.d_sparent, aux.d_out);
       break;
     }
+    case LK_MR_FWD_SMALL:
+    case LK_MR_BWD_SMALL:
+    case LK_MR_ASSEMBLE:
+    case LK_MR_GATHER:
+      return run_mr_launch(L, t, ar, aux, st);
     default:
       return cudaErrorInvalidValue;
   }

@@ -576,4 +576,125 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
   }
 }
 
+// ------------------------------------------------------------------------------- panel solves ----
+// Sweeps over L for a node-major panel of nr right-hand sides (solve_mr.cu): arena 0 = fronts, arena 1 = the panel X
+// (nr x n, leading dimension ldk), arena 2 = the update panels U_J (nr x r_J at uoff_J * ldk), inverse-block operands =
+// the inverses the factorisation kept (winv_slot).  One plan per panel width.
+void build_solve_mr_plans(const Symbolic& S, const std::vector<int64_t>& winv_slot, int nr, int ldk, Plan& fwd, Plan& bwd) {
+  std::vector<int64_t> uoff(S.nsuper, 0);
+  {
+    int64_t uo = 0;
+    for (int32_t s = 0; s < S.nsuper; s++) {
+      uoff[s] = uo;
+      uo += S.front_order(s) - S.ncols(s);
+    }
+  }
+  auto trap_bytes = [&](int32_t s) {
+    const double d = S.front_order(s), sc = S.ncols(s);
+    return 8.0 * (sc * d - sc * (sc - 1) / 2);
+  };
+  auto split = [&](const std::vector<int32_t>& all, std::vector<int32_t> (&cls)[SMALL_FRONT_NCLASS], std::vector<int32_t>& big) {
+    for (int32_t s : all) {
+      const int d = S.front_order(s);
+      if (d > SMALL_FRONT_MAX) {
+        big.push_back(s);
+        continue;
+      }
+      int c = 0;
+      while (d > SMALL_FRONT_CLASSES[c]) c++;
+      cls[c].push_back(s);
+    }
+  };
+  auto small_launches = [&](PlanBuilder& B, Plan& P, int kind, std::vector<int32_t> (&cls)[SMALL_FRONT_NCLASS]) {
+    for (int c = 0; c < SMALL_FRONT_NCLASS; c++) {
+      if (cls[c].empty()) continue;
+      B.begin(kind);
+      int maxd = 0;
+      for (int32_t s : cls[c]) {
+        Task t = make_task();
+        t.aux0 = s;
+        B.add(t, 1);
+        maxd = std::max(maxd, S.front_order(s));
+        B.add_bytes(trap_bytes(s));
+        const double d = S.front_order(s), sc = S.ncols(s);
+        P.flops += 2.0 * nr * (sc * d - sc * (sc - 1) / 2);
+      }
+      B.set_smem(maxd);  // largest front order of the launch (the kernels size their shared memory from it)
+      B.end();
+    }
+  };
+  auto trsm_probs = [&](const std::vector<int32_t>& big, std::vector<int64_t>& slot0) {
+    std::vector<TrsmProb> tp;
+    slot0.clear();
+    for (int32_t s : big) {
+      tp.push_back({AR_FRONT, S.foff[s], S.ld[s], 1, (int64_t)S.sptr[s] * ldk, ldk, nr, S.ncols(s)});
+      slot0.push_back(winv_slot[s]);
+    }
+    return tp;
+  };
+  {  // ---- forward: leaves to root ----
+    PlanBuilder B(fwd);
+    for (size_t lev = 0; lev < S.levels.size(); lev++) {
+      std::vector<int32_t> cls[SMALL_FRONT_NCLASS], big;
+      split(S.levels[lev].snodes, cls, big);
+      small_launches(B, fwd, LK_MR_FWD_SMALL, cls);
+      if (big.empty()) continue;
+      B.begin(LK_MR_ASSEMBLE);
+      for (int32_t s : big) {
+        Task t = make_task();
+        t.aux0 = s;
+        B.add(t, 1);
+      }
+      B.end();
+      std::vector<int64_t> slot0;
+      std::vector<TrsmProb> tp = trsm_probs(big, slot0);
+      int max_n = 0;
+      for (auto& p : tp) max_n = std::max(max_n, p.n);
+      plan_trsm_cols(B, fwd, tp, slot0, true, 0, ((max_n + NB - 1) / NB) * NB);
+      B.begin(LK_GEMM_NT);  // U_J -= X_J L21'
+      for (int32_t s : big) {
+        const int sc = S.ncols(s), r = S.front_order(s) - sc;
+        if (r <= 0) continue;
+        add_gemm(B, fwd, 1, (int64_t)S.sptr[s] * ldk, ldk, AR_FRONT, S.foff[s] + sc, S.ld[s], 2, uoff[s] * ldk, ldk, nr, r, sc,
+                 false, -1.0, 1.0);
+        B.add_bytes(8.0 * (double)r * sc);
+      }
+      B.end();
+    }
+  }
+  {  // ---- backward: root to leaves ----
+    PlanBuilder B(bwd);
+    for (int lev = (int)S.levels.size() - 1; lev >= 0; lev--) {
+      std::vector<int32_t> cls[SMALL_FRONT_NCLASS], big;
+      split(S.levels[lev].snodes, cls, big);
+      if (!big.empty()) {
+        B.begin(LK_MR_GATHER);
+        for (int32_t s : big) {
+          const int r = S.front_order(s) - S.ncols(s);
+          if (r <= 0) continue;
+          Task t = make_task();
+          t.aux0 = s;
+          B.add(t, cdiv(r, 64));
+        }
+        B.end();
+        B.begin(LK_GEMM_NN);  // X_J -= U_J L21
+        for (int32_t s : big) {
+          const int sc = S.ncols(s), r = S.front_order(s) - sc;
+          if (r <= 0) continue;
+          add_gemm(B, bwd, 2, uoff[s] * ldk, ldk, AR_FRONT, S.foff[s] + sc, S.ld[s], 1, (int64_t)S.sptr[s] * ldk, ldk, nr, sc, r,
+                   false, -1.0, 1.0);
+          B.add_bytes(8.0 * (double)r * sc);
+        }
+        B.end();
+        std::vector<int64_t> slot0;
+        std::vector<TrsmProb> tp = trsm_probs(big, slot0);
+        int max_n = 0;
+        for (auto& p : tp) max_n = std::max(max_n, p.n);
+        plan_trsm_cols(B, bwd, tp, slot0, false, 0, ((max_n + NB - 1) / NB) * NB);
+      }
+      small_launches(B, bwd, LK_MR_BWD_SMALL, cls);
+    }
+  }
+}
+
 }  // namespace gmrfb

@@ -93,6 +93,10 @@ void build_factor_plan(const Symbolic& S, Plan& P);
 // DIAG_OUT tasks write diag(Z) by internal column index.
 void build_selinv_plan(const Symbolic& S, Plan& P);
 
+// Panel (multi-right-hand-side) forward / backward sweeps for nr right-hand sides held node-major with leading dimension
+// ldk (solve_mr.cu); winv_slot = Plan::winv_slot of the factor plan (kept inverses of the 64 x 64 diagonal blocks).
+void build_solve_mr_plans(const Symbolic& S, const std::vector<int64_t>& winv_slot, int nr, int ldk, Plan& fwd, Plan& bwd);
+
 // Dense building blocks shared with the block-tridiagonal path (offsets relative to a moving base).
 //  blocked in-place Cholesky of the n x n matrix at `off` (ld), reporting failures at column col0 + j
 void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0);

@@ -6,7 +6,8 @@
 
 namespace gmrfb {
 
-constexpr int SOLVE_NRC = 4;  // right-hand sides processed per pass of the level-scheduled solves
+constexpr int SOLVE_NRC = 4;  // right-hand sides processed per pass of the level-scheduled solves (batches of up to 4)
+constexpr int MR_MAX = 64;    // right-hand sides per pass of the panel solves (larger batches, solve_mr.cu)
 
 // Per-supernode record used by the solve kernels (device copy of the symbolic structure).
 struct SnodeDesc {

@@ -139,8 +139,8 @@ extern "C" gmrfb_status gmrfb_spmv(const gmrfb_spm* A, int32_t trans, double alp
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   const int64_t nx = trans ? A->m : A->n, ny = trans ? A->n : A->m;
   DevBuf<double> dx, dy;
-  GMRFB_CU(ctx, dx.alloc((size_t)std::max<int64_t>(nx, 1)));
-  GMRFB_CU(ctx, dy.alloc((size_t)std::max<int64_t>(ny, 1)));
+  GMRFB_CU(ctx, dx.alloc((size_t)std::max<int64_t>(nx, 1), ctx->stream));
+  GMRFB_CU(ctx, dy.alloc((size_t)std::max<int64_t>(ny, 1), ctx->stream));
   GMRFB_CU(ctx, cudaMemcpyAsync(dx.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (beta != 0.0) GMRFB_CU(ctx, cudaMemcpyAsync(dy.p, y, ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (trans)  // y_j = sum over column j of A: the CSC arrays are the rows of A'
@@ -160,12 +160,12 @@ extern "C" gmrfb_status gmrfb_sqmahal(const gmrfb_spm* Q, const double* mu, cons
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   const int64_t n = Q->n;
   DevBuf<double> dv, dmu, dd, dt;
-  GMRFB_CU(ctx, dv.alloc((size_t)std::max<int64_t>(n, 1)));
-  GMRFB_CU(ctx, dd.alloc((size_t)std::max<int64_t>(n, 1)));
-  GMRFB_CU(ctx, dt.alloc((size_t)std::max<int64_t>(n, 1)));
+  GMRFB_CU(ctx, dv.alloc((size_t)std::max<int64_t>(n, 1), ctx->stream));
+  GMRFB_CU(ctx, dd.alloc((size_t)std::max<int64_t>(n, 1), ctx->stream));
+  GMRFB_CU(ctx, dt.alloc((size_t)std::max<int64_t>(n, 1), ctx->stream));
   GMRFB_CU(ctx, cudaMemcpyAsync(dv.p, v, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (mu) {
-    GMRFB_CU(ctx, dmu.alloc((size_t)std::max<int64_t>(n, 1)));
+    GMRFB_CU(ctx, dmu.alloc((size_t)std::max<int64_t>(n, 1), ctx->stream));
     GMRFB_CU(ctx, cudaMemcpyAsync(dmu.p, mu, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   GMRFB_CU(ctx, launch_axpby(n, 1.0, dv.p, -1.0, mu ? dmu.p : nullptr, dd.p, ctx->stream));
@@ -353,14 +353,14 @@ extern "C" gmrfb_status gmrfb_metrics(gmrfb_ctx* ctx, const gmrfb_spm* E, const 
   cudaStream_t st = ctx->stream;
   const int64_t nx = E ? E->n : ntruth;
   DevBuf<double> dx, dt, dp, part;
-  GMRFB_CU(ctx, dx.alloc((size_t)nx));
-  GMRFB_CU(ctx, dt.alloc((size_t)ntruth));
-  GMRFB_CU(ctx, part.alloc(3 * MET_BLOCKS + 3));
+  GMRFB_CU(ctx, dx.alloc((size_t)nx, ctx->stream));
+  GMRFB_CU(ctx, dt.alloc((size_t)ntruth, ctx->stream));
+  GMRFB_CU(ctx, part.alloc(3 * MET_BLOCKS + 3, ctx->stream));
   GMRFB_CU(ctx, cudaMemcpyAsync(dx.p, x, nx * sizeof(double), cudaMemcpyDefault, st));
   GMRFB_CU(ctx, cudaMemcpyAsync(dt.p, truth, ntruth * sizeof(double), cudaMemcpyDefault, st));
   const double* pred = dx.p;
   if (E) {
-    GMRFB_CU(ctx, dp.alloc((size_t)ntruth));
+    GMRFB_CU(ctx, dp.alloc((size_t)ntruth, ctx->stream));
     GMRFB_CU(ctx, launch_spmv_rows(E->m, E->d_rowptr.p, E->d_colidx.p, E->d_tval.p, dx.p, dp.p, 1.0, 0.0, st));
     ctx->launches++;
     pred = dp.p;

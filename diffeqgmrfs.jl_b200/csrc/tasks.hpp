@@ -53,6 +53,12 @@ enum LaunchKind : int32_t {
   LK_GEMM_TT = 15,             // C = beta C + alpha A' B'       A: KxM, B: NxK
   LK_SKINNY_NT = 16,           // M <= 8 rows: C = beta C + alpha A B', bandwidth-bound streaming of B (skinny_kernels.cuh)
   LK_SKINNY_NN = 17,           // M <= 8 rows: C = beta C + alpha A B
+  // panel (multi-right-hand-side) triangular solves, solve_mr.cu: the right-hand sides are a node-major panel
+  // X (nr x n, leading dimension ldk) in arena 1, the supernodes' update panels U_J (nr x r_J) in arena 2
+  LK_MR_FWD_SMALL = 32,  // forward substitution of one small supernode per CTA (aux0 = supernode)
+  LK_MR_BWD_SMALL = 33,  // backward substitution of one small supernode per CTA
+  LK_MR_ASSEMBLE = 34,   // X[:, C_J] += / U_J = children's update panels (aux0 = supernode; CTA = 8 right-hand sides)
+  LK_MR_GATHER = 35,     // U_J <- X[:, below rows of J] (aux0 = supernode; CTA = 64 rows)
 };
 
 struct Launch {
@@ -76,7 +82,8 @@ enum : int32_t {
   PK_BWD_RPART = 26,
   PK_FWD_SMALL = 27,
   PK_BWD_SMALL = 28,
-  PK_MAX = 32
+  PK_PERM_MR = 29,
+  PK_MAX = 40
 };
 
 // GEMM tile configurations shared by the plan builder (tile counts) and the kernels (gemm_engine.cuh).
@@ -129,7 +136,7 @@ inline bool uses_cta_map(int kind) {
   switch (kind) {
     case LK_GEMM_NT: case LK_GEMM_NN: case LK_GEMM_TN: case LK_GEMM_TT: case LK_TRSM_RLT: case LK_TRSM_RLN:
     case LK_EXTEND_ADD: case LK_GATHER_SYM: case LK_SET_IDENTITY: case LK_TRANSPOSE: case LK_SCALE:
-    case LK_DIAG_OUT: case LK_SYMMETRIZE:
+    case LK_DIAG_OUT: case LK_SYMMETRIZE: case LK_MR_GATHER:
       return true;
     default:
       return false;

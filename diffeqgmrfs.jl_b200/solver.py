@@ -40,9 +40,9 @@ class Context:
 
     def profile_end(self):
         """-> list of dicts(name, kind, launches, ms, flops, bytes), one per kernel kind."""
-        ent = (B.ProfileEntry * 32)()
+        ent = (B.ProfileEntry * 64)()
         cnt = C.c_int32()
-        B.check(B.lib().gmrfb_ctx_profile_end(self.h, ent, 32, C.byref(cnt)), self.h)
+        B.check(B.lib().gmrfb_ctx_profile_end(self.h, ent, 64, C.byref(cnt)), self.h)
         return [dict(name=e.name.decode(), kind=e.kind, launches=e.launches, ms=e.ms, flops=e.flops, bytes=e.bytes)
                 for e in ent[:cnt.value]]
 
@@ -53,6 +53,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(B.lib().gmrfb_ctx_launch_count(self.h))
+
+
+def pool_trim(keep_bytes: int = 0) -> int:
+    """Give cached device buffers back to the driver (gmrfb_pool_trim); returns the bytes still cached."""
+    out = C.c_int64()
+    B.check(B.lib().gmrfb_pool_trim(int(keep_bytes), C.byref(out)), None)
+    return out.value
 
 
 _default_ctx = None
@@ -312,8 +319,21 @@ class CholeskyFactor:
         B.check(B.lib().gmrfb_solve(self.h, mode, X.ctypes.data_as(B._F64P), self.sym.n, X.shape[1]), self.ctx.h)
         return X[:, 0].copy() if one else X
 
-    def solve(self, b):
-        return self._solve(B.SOLVE_A, b)
+    def solve(self, b, refine: "SparseMatrix | None" = None, max_iter: int = 1, return_residual=False):
+        """``F \\ b``.  With ``refine=Q`` (the precision as a device matrix) up to ``max_iter`` steps of iterative
+        refinement x += F \\ (b - Q x) follow the factor solve (gmrfb_solve_refined): for precisions with a large
+        conditioning term (Q_eps = 1e8, scripts/solve_burger.jl:98,140) one step brings the residual down to that of
+        a backward-stable substitution."""
+        if refine is None:
+            return self._solve(B.SOLVE_A, b)
+        b = np.asarray(b, dtype=np.float64)
+        one = b.ndim == 1
+        X = np.asfortranarray(b.reshape(self.sym.n, -1).copy(order="F"))
+        res = np.empty(X.shape[1])
+        B.check(B.lib().gmrfb_solve_refined(self.h, refine.h, X.ctypes.data_as(B._F64P), self.sym.n, X.shape[1],
+                                            int(max_iter), res.ctypes.data_as(B._F64P)), self.ctx.h)
+        out = X[:, 0].copy() if one else X
+        return (out, res) if return_residual else out
 
     def PtL_solve(self, b):
         return self._solve(B.SOLVE_PTL, b)
@@ -790,8 +810,13 @@ class TridiagonalCholeskyFactor:
     def _solve(self, mode, b):
         b = np.asarray(b, dtype=np.float64)
         n = self.b * self.nblocks
+        if b.shape[0] != n:
+            # the factor covers N_blocks * (size(A, 1) ÷ N_blocks) rows (src/tridiagonal_cholesky.jl:66); the reference's
+            # chunked solves fail on any other length (`make_chunks` puts the remainder rows into the last chunk)
+            raise ValueError(f"right-hand side has {b.shape[0]} rows, the block factor covers {n} "
+                             f"({self.nblocks} blocks of {self.b})")
         one = b.ndim == 1
-        X = np.asfortranarray(b.reshape(b.shape[0], -1)[:n].copy(order="F"))
+        X = np.asfortranarray(b.reshape(n, -1).copy(order="F"))
         B.check(B.lib().gmrfb_btd_solve(self.h, mode, X.ctypes.data_as(B._F64P), n, X.shape[1]), self.ctx.h)
         return X[:, 0].copy() if one else X
 
@@ -829,6 +854,9 @@ def tridiagonal_cholesky_dense(D, Bsub, ctx=None) -> TridiagonalCholeskyFactor:
         assert D.is_cuda and D.is_contiguous() and str(D.dtype) == "torch.float64"
         N, b, _ = D.shape
         Dp = C.cast(C.c_void_p(D.data_ptr()), B._F64P)
+        if N > 1:
+            assert Bsub.is_cuda and Bsub.is_contiguous() and str(Bsub.dtype) == "torch.float64" \
+                and tuple(Bsub.shape) == (N - 1, b, b) and Bsub.device == D.device
         Bp = C.cast(C.c_void_p(Bsub.data_ptr()), B._F64P) if N > 1 else None
     else:
         D = np.asfortranarray(D, dtype=np.float64)

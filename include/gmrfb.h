@@ -67,6 +67,13 @@ uint64_t gmrfb_ctx_stream(gmrfb_ctx* ctx);
 /* Number of kernels this library has launched through `ctx` since creation (for benchmarks). */
 int64_t gmrfb_ctx_launch_count(gmrfb_ctx* ctx);
 
+/* The library caches released device buffers of >= 1 MB (a dataset loop that creates and destroys multi-GB factor handles
+ * would otherwise pay cudaMalloc/cudaFree every iteration).  gmrfb_pool_trim frees cached buffers until at most
+ * keep_bytes remain cached (0: everything) and reports what is still cached; destroying the last context trims the
+ * cache completely, so a co-resident allocator (torch, CUDA.jl) gets the memory back.  GMRFB_POOL=0 disables the
+ * cache, GMRFB_POOL_MAX_GB bounds it (default 24). */
+gmrfb_status gmrfb_pool_trim(int64_t keep_bytes, int64_t* cached_bytes_out);
+
 /* Per-kernel profiling for benchmarks: between profile_begin and profile_end every kernel launched through
  * `ctx` is bracketed by CUDA events on the context's stream; profile_end synchronises and returns one entry
  * per kernel kind with its launch count, summed device time and the algorithmic flops / bytes of those launches
@@ -188,6 +195,15 @@ enum { GMRFB_SOLVE_A = 0, GMRFB_SOLVE_PTL = 1, GMRFB_SOLVE_UP = 2, GMRFB_SOLVE_L
 gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int64_t ldx, int64_t nrhs);
 /* Device-pointer variant: d_X is n-by-nrhs column-major on the context's device. */
 gmrfb_status gmrfb_solve_dev(gmrfb_fac* fac, int32_t mode, double* d_X, int64_t ldx, int64_t nrhs);
+
+/* `F \ b` with iterative refinement against the matrix the factor was computed from:
+ *   x_0 = Q^{-1} b (factor solve);  repeat up to max_iter times:  r = b - Q x,  x <- x + Q^{-1} r
+ * (stops early when the relative residual ||r|| / ||b|| no longer decreases; the iterate with the smallest residual is
+ * returned).  For precisions with a large conditioning term such as Q_eps = 1e8 (scripts/solve_burger.jl:98,140) one
+ * step brings the residual of the solve down to that of a backward-stable substitution.  Q: the precision as a device
+ * matrix (full symmetric storage); resid_out (nrhs doubles, may be NULL) receives the final relative residuals. */
+gmrfb_status gmrfb_solve_refined(gmrfb_fac* fac, const gmrfb_spm* Q, double* X, int64_t ldx, int64_t nrhs,
+                                 int32_t max_iter, double* resid_out);
 
 /* Samples  X[:,k] = mean + P' L^{-T} Z[:,k]  — `rand(rng, x)` (scripts/darcy/solve_darcy_gmrf-fem.jl:191).
  * The host supplies the standard normals Z (n-by-nrhs) so "same seed" means "same z"; mean may be NULL. */

@@ -70,7 +70,7 @@ end
 const _default_ctx = Ref{Union{Nothing,B200Context}}(nothing)
 default_context() = (_default_ctx[] === nothing && (_default_ctx[] = B200Context(0)); _default_ctx[]::B200Context)
 
-function check(ctx::B200Context, st::Int32)
+function _check(ctx::B200Context, st::Int32)
     st == GMRFB_OK && return
     msg = unsafe_string(ccall((:gmrfb_last_error, libgmrfb), Cstring, (Ptr{Cvoid},), ctx.h))
     st == GMRFB_ERR_NOT_SPD && throw(PosDefException(1))   # what stdlib `cholesky` throws with check=true
@@ -113,12 +113,12 @@ function b200_cholesky(A::SparseMatrixCSC{Float64,Int64}; perm::Union{Nothing,Ve
     fac = Ref{Ptr{Cvoid}}(C_NULL)
     pptr = perm === nothing ? Ptr{Int64}(C_NULL) : pointer(perm)
     GC.@preserve A perm coords begin
-        check(ctx, ccall((:gmrfb_analyze, libgmrfb), Int32,
+        _check(ctx, ccall((:gmrfb_analyze, libgmrfb), Int32,
                          (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{AnalyzeOpts}, Ref{Ptr{Cvoid}}),
                          ctx.h, n, A.colptr, A.rowval, pptr, opts, sym))
-        check(ctx, ccall((:gmrfb_fac_create, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), sym[], fac))
+        _check(ctx, ccall((:gmrfb_fac_create, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), sym[], fac))
         p = Vector{Int64}(undef, n)
-        check(ctx, ccall((:gmrfb_sym_get, libgmrfb), Int32,
+        _check(ctx, ccall((:gmrfb_sym_get, libgmrfb), Int32,
                          (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
                          sym[], p, C_NULL, C_NULL, C_NULL, C_NULL))
         F = B200Factor(ctx, sym[], fac[], n, p, false)
@@ -133,7 +133,7 @@ function refactorize!(F::B200Factor, nzval::Vector{Float64}; check::Bool = true)
     st = GC.@preserve nzval ccall((:gmrfb_factorize, libgmrfb), Int32, (Ptr{Cvoid}, Ptr{Float64}), F.fac, nzval)
     F.success = st == GMRFB_OK
     (st == GMRFB_ERR_NOT_SPD && !check) && return F        # `check=false`: failure is a queryable flag
-    GMRFB200.check(F.ctx, st)
+    _check(F.ctx, st)
     return F
 end
 
@@ -141,7 +141,7 @@ LinearAlgebra.issuccess(F::B200Factor) = F.success
 
 function _info(F::B200Factor)
     info = Ref(FacInfo(0, 0, 0.0, 0))
-    check(F.ctx, ccall((:gmrfb_fac_get_info, libgmrfb), Int32, (Ptr{Cvoid}, Ref{FacInfo}), F.fac, info))
+    _check(F.ctx, ccall((:gmrfb_fac_get_info, libgmrfb), Int32, (Ptr{Cvoid}, Ref{FacInfo}), F.fac, info))
     return info[]
 end
 SparseArrays.nnz(F::B200Factor) = Int(_info(F).nnz_L)                  # scripts/darcy/solve_darcy_gmrf-fem.jl:170
@@ -151,7 +151,7 @@ LinearAlgebra.logdet(F::B200Factor) = _info(F).logdet
 function _solve!(F::B200Factor, mode::Int32, X::StridedVecOrMat{Float64})
     nrhs = size(X, 2)
     ldx = X isa AbstractVector ? length(X) : stride(X, 2)
-    GC.@preserve X check(F.ctx, ccall((:gmrfb_solve, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int64),
+    GC.@preserve X _check(F.ctx, ccall((:gmrfb_solve, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int64),
                                       F.fac, mode, X, ldx, nrhs))
     return X
 end
@@ -173,11 +173,11 @@ end
 function _sparse_L(F::B200Factor)
     n = getfield(F, :n); fac = getfield(F, :fac); ctx = getfield(F, :ctx)
     colptr = Vector{Int64}(undef, n + 1)
-    check(ctx, ccall((:gmrfb_fac_get_L, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+    _check(ctx, ccall((:gmrfb_fac_get_L, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
                      fac, 1, 1, colptr, C_NULL, C_NULL))
     nz = colptr[end] - 1
     rowval = Vector{Int64}(undef, nz); nzval = Vector{Float64}(undef, nz)
-    check(ctx, ccall((:gmrfb_fac_get_L, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+    _check(ctx, ccall((:gmrfb_fac_get_L, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
                      fac, 1, 1, colptr, rowval, nzval))
     return SparseMatrixCSC(n, n, colptr, rowval, nzval)
 end
@@ -186,7 +186,7 @@ end
 function sample(F::B200Factor, Z::StridedVecOrMat{Float64}; mean::Union{Nothing,Vector{Float64}} = nothing)
     X = similar(Z)
     mptr = mean === nothing ? Ptr{Float64}(C_NULL) : pointer(mean)
-    GC.@preserve Z X mean check(F.ctx, ccall((:gmrfb_sample, libgmrfb), Int32,
+    GC.@preserve Z X mean _check(F.ctx, ccall((:gmrfb_sample, libgmrfb), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64),
         F.fac, mptr, Z, size(Z, 1), X, size(X, 1), size(Z, 2)))
     return X
@@ -195,7 +195,7 @@ end
 "diag(Q^{-1}) by Takahashi selected inversion."
 function var_selinv(F::B200Factor)
     v = Vector{Float64}(undef, F.n)
-    GC.@preserve v check(F.ctx, ccall((:gmrfb_var_selinv, libgmrfb), Int32, (Ptr{Cvoid}, Ptr{Float64}), F.fac, v))
+    GC.@preserve v _check(F.ctx, ccall((:gmrfb_var_selinv, libgmrfb), Int32, (Ptr{Cvoid}, Ptr{Float64}), F.fac, v))
     return v
 end
 
@@ -205,11 +205,11 @@ function var_rbmc(F::B200Factor, Q::SparseMatrixCSC{Float64,Int64}, Z::Matrix{Fl
     spm = Ref{Ptr{Cvoid}}(C_NULL)
     v = Vector{Float64}(undef, F.n)
     GC.@preserve Q Z v begin
-        check(ctx, ccall((:gmrfb_spm_create, libgmrfb), Int32,
+        _check(ctx, ccall((:gmrfb_spm_create, libgmrfb), Int32,
                          (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
                          ctx.h, size(Q, 1), size(Q, 2), Q.colptr, Q.rowval, Q.nzval, 1, spm))
         try
-            check(ctx, ccall((:gmrfb_var_rbmc, libgmrfb), Int32,
+            _check(ctx, ccall((:gmrfb_var_rbmc, libgmrfb), Int32,
                              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}),
                              F.fac, spm[], Z, size(Z, 1), size(Z, 2), v))
         finally
@@ -273,12 +273,12 @@ function b200_gauss_newton(mu::Vector{Float64}, Q::SparseMatrixCSC{Float64,Int64
                            ctx::B200Context = default_context())
     U, (lv, av, dv) = _union_pattern(L, A, D)
     qh = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve Q check(ctx, ccall((:gmrfb_spm_create, libgmrfb), Int32,
+    GC.@preserve Q _check(ctx, ccall((:gmrfb_spm_create, libgmrfb), Int32,
         (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
         ctx.h, size(Q, 1), size(Q, 2), Q.colptr, Q.rowval, Q.nzval, 1, qh))
     opts = Ref(AnalyzeOpts(perm === nothing ? ORDER_ND : ORDER_GIVEN, 0, 1, 0, C_NULL, 0, 0, 0.0))
     out = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve U lv av dv y mu perm check(ctx, ccall((:gmrfb_gn_create, libgmrfb), Int32,
+    GC.@preserve U lv av dv y mu perm _check(ctx, ccall((:gmrfb_gn_create, libgmrfb), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
          Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ref{AnalyzeOpts}, Ref{Ptr{Cvoid}}),
         ctx.h, qh[], size(U, 1), U.colptr, U.rowval, lv, av, dv, C_NULL #= cubic term e, if any =#, 1, Float64(c),
@@ -297,7 +297,7 @@ function optimize!(gn::B200GaussNewton, x0::Vector{Float64}; max_steps::Integer 
     x = copy(x0)
     hist = zeros(max_steps + 1)
     steps = Ref{Int32}(0)
-    GC.@preserve x hist check(gn.ctx, ccall((:gmrfb_gn_optimize, libgmrfb), Int32,
+    GC.@preserve x hist _check(gn.ctx, ccall((:gmrfb_gn_optimize, libgmrfb), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ref{Int32}, Ptr{Float64}),
         gn.h, x, Int32(max_steps), Float64(rel_tol), steps, hist))
     gn.n_steps = steps[]
@@ -313,7 +313,7 @@ function b200_tridiagonal_cholesky(A::SparseMatrixCSC{Float64,Int64}, N_blocks::
     if st != GMRFB_OK && out[] != C_NULL
         ccall((:gmrfb_btd_destroy, libgmrfb), Int32, (Ptr{Cvoid},), out[])
     end
-    check(ctx, st)
+    _check(ctx, st)
     F = B200TridiagonalCholeskyFactor(ctx, out[], size(A, 1), size(A, 1) ÷ N_blocks, N_blocks)
     finalizer(f -> ccall((:gmrfb_btd_destroy, libgmrfb), Int32, (Ptr{Cvoid},), f.h), F)
     return F
@@ -321,7 +321,7 @@ end
 
 function _block(F::B200TridiagonalCholeskyFactor, i::Integer, which::Integer)
     out = Matrix{Float64}(undef, F.b, F.b)
-    GC.@preserve out check(F.ctx, ccall((:gmrfb_btd_get_block, libgmrfb), Int32,
+    GC.@preserve out _check(F.ctx, ccall((:gmrfb_btd_get_block, libgmrfb), Int32,
         (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64), F.h, i - 1, which, out, F.b))
     return out
 end
@@ -333,7 +333,7 @@ function _btd_solve(F::B200TridiagonalCholeskyFactor, mode::Int32, b::StridedVec
     n = F.b * F.nblocks
     X = copy(b)
     ldx = X isa AbstractVector ? length(X) : stride(X, 2)
-    GC.@preserve X check(F.ctx, ccall((:gmrfb_btd_solve, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int64),
+    GC.@preserve X _check(F.ctx, ccall((:gmrfb_btd_solve, libgmrfb), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int64),
                                       F.h, mode, X, ldx, size(X, 2)))
     return X
 end
@@ -347,7 +347,7 @@ ldiv!(y, F::B200TridiagonalCholeskyFactor, b) = (y .= ldiv(F, b); y)
 
 function LinearAlgebra.logdet(F::B200TridiagonalCholeskyFactor)
     out = Ref(0.0)
-    check(F.ctx, ccall((:gmrfb_btd_logdet, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Float64}), F.h, out))
+    _check(F.ctx, ccall((:gmrfb_btd_logdet, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Float64}), F.h, out))
     return out[]
 end
 
