@@ -7,15 +7,18 @@ One *step* = one posterior solve of BASELINE config 4 (synthetic 2-D Matern SPDE
 with `perm=p`) + posterior mean (forward + backward solve) + marginal variances by Takahashi selected inversion.
 
     python bench.py --gpus N --steps K --warmup W          # product arm (CUDA, one process per GPU)
-    python bench.py --impl reference ...                    # CPU arm: the oracle port on the host cores
+    python bench.py --impl reference ...                    # CPU arm: the oracle port on all host cores
 
 `value`   : whole-job solves/s with the precision values and right-hand side resident in HBM (device entry points).
 `e2e`     : the same metric through the host C-ABI calls (pinned host buffers, H2D/D2H inside the timed region).
 `roofline`: the dominant kernel of the step, timed with CUDA events inside this run (profiled replay of the same
             step), against the measured FP64 tensor peak (cuBLAS DGEMM, profiles/r01_fp64_probe.json) or the
-            measured HBM copy bandwidth (MEASURED_PEAKS.json).
+            measured HBM copy bandwidth (MEASURED_PEAKS.json); every `kernel_profile` row carries its own fraction.
 N > 1     : independent posterior problems (the reference's dataset loop, scripts/darcy/solve_darcy_gmrf-fem.jl:210)
-            are sharded one per rank — no data-path collective; weak scaling.
+            are sharded one per rank — no data-path collective; weak scaling.  The two multi-GPU paths that do
+            exchange data are measured after the timed region and reported as extra keys of the same line:
+            `btd_dist` (time-sharded block-tridiagonal factor + 8-RHS solve, Schur split over NCCL) and
+            `rbmc_sharded` (sample-sharded RBMC-64 variances, one all-reduce).
 """
 from __future__ import annotations
 
@@ -37,6 +40,8 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "GMRF posterior (mean+marginal var) solves/sec"
 UNIT = "solves/s"
 FP64_PEAK_TFLOPS_FALLBACK = 35.5  # cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_fp64_probe.json)
+OBS_FRAC, Q_EPS, CORR_RANGE = 0.1, 1e2, 0.05
+TOL_MEAN_VS_CPU, TOL_VAR_VS_CPU = 1e-10, 1e-8  # north-star tolerances, gated at N = 1 on the 1M-node problem
 
 
 def load_peaks():
@@ -112,31 +117,51 @@ class ClockSampler:
 
 
 def build_problem(nx, seed):
-    pkg = entry.load_pkg()
-    prob = pkg.workloads.matern_posterior(nx, obs_frac=0.1, q_eps=1e2, corr_range=0.05, seed=seed)
-    return prob
+    pkg = entry.load_pkg()  # workload generator only (NumPy / SciPy; loads no native library)
+    return pkg.workloads.matern_posterior(nx, obs_frac=OBS_FRAC, q_eps=Q_EPS, corr_range=CORR_RANGE, seed=seed)
+
+
+def workload_config(nx, n, nnz_q):
+    """The `config` object — identical in both arms (what the workload is; nothing arm-specific)."""
+    return {"workload": f"config 4: synthetic 2-D Matern SPDE GMRF posterior on a {nx}x{nx} P1 mesh (n={n}), "
+                        f"{int(OBS_FRAC * 100)} % of the nodes observed with Q_eps={Q_EPS:g}; one posterior solve = numeric "
+                        "supernodal Cholesky (symbolic analysis reused) + posterior mean + marginal variances by "
+                        "Takahashi selected inversion",
+            "n": int(n), "nnz_Q": int(nnz_q), "obs_frac": OBS_FRAC, "q_eps": Q_EPS, "corr_range": CORR_RANGE,
+            "l2_policy": "working set (front arenas, > 8 GB per problem) >> 126 MB L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm ----
+def set_blas_threads():
+    """All host cores for the CPU arm, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)."""
+    want = os.cpu_count() or 1
+    got = want
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=want)  # stays in force for the process
+        got = max([p.get("num_threads", 1) for p in threadpool_info()] or [want])
+    except Exception:  # noqa: BLE001
+        pass
+    return got
+
+
 class CpuPosterior:
     """The reference path on the host cores: supernodal multifrontal Cholesky with BLAS-3 supernodes
     (oracle/supernodal_chol.c, CHOLMOD's algorithm class; OpenBLAS through scipy, all host threads) on the SAME
-    workload, ordering and supernode partition as the GPU arm.  One step = numeric factorisation (symbolic reused,
-    as `perm=p` does in the reference) + posterior mean (forward + backward sweep) + Takahashi variances."""
+    workload.  Ordering (geometric nested dissection with minimum-vertex-cover separators) and supernodal symbolic
+    analysis are the oracle's own (oracle/gmrf_oracle.py, oracle/sn_symbolic.c): nothing of the product library is
+    loaded.  One step = numeric factorisation (symbolic reused, as `perm=p` does in the reference) + posterior mean
+    (forward + backward sweep) + Takahashi variances."""
 
     def __init__(self, nx, seed=0):
-        pkg = entry.load_pkg()
         orc = entry.load_oracle()
+        self.threads = set_blas_threads()
         self.prob = build_problem(nx, seed)
         Qp = self.prob["Qpost"]
-        sym = pkg.Symbolic(Qp, coords=self.prob["nodes"], host_only=True)  # integer analysis only, no GPU involved
-        p, ipost = sym.p, sym.ipost
-        perm_int = np.empty(len(p), np.int64)
-        perm_int[ipost] = p
-        sptr = sym.super_ptr
-        rows = [sym.super_rows(s) for s in range(len(sptr) - 1)]
-        self.info = sym.info
-        self.F = orc.SupernodalCholesky(Qp, perm_int, sptr, rows)
+        t = time.perf_counter()
+        self.F = orc.SupernodalCholesky.analyze(Qp, coords=self.prob["nodes"])
+        self.setup_s = time.perf_counter() - t
         self.n = Qp.shape[0]
 
     def step(self):
@@ -150,27 +175,19 @@ class CpuPosterior:
         return dict(factor_s=t1 - t0, solve_s=t2 - t1, selinv_s=t3 - t2, total_s=t3 - t0), x, v
 
 
-def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-
-        return max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count() or 1])
-    except Exception:  # noqa: BLE001
-        return os.cpu_count() or 1
-
-
-def cpu_sample_desc(nx, s):
+def cpu_sample_desc(nx, s, F):
     return (f"full workload: one posterior solve of the {nx}x{nx} mesh (n={nx * nx}) by oracle/supernodal_chol.c "
-            f"(supernodal multifrontal, OpenBLAS): factor {s['factor_s']:.2f}s, solves {s['solve_s']:.2f}s, "
-            f"selinv {s['selinv_s']:.2f}s; a restatement of CHOLMOD's supernodal algorithm class, not CHOLMOD")
+            f"(supernodal multifrontal, OpenBLAS) with the oracle's own nested-dissection ordering (nnz(L)={F.nnz_L}, "
+            f"{F.flops:.3e} flops): factor {s['factor_s']:.2f}s, solves {s['solve_s']:.2f}s, selinv {s['selinv_s']:.2f}s; "
+            "a restatement of CHOLMOD's supernodal algorithm class, not CHOLMOD")
 
 
 def cpu_baseline(nx):
     cp = CpuPosterior(nx)
     cp.step()  # warm-up call, as the reference does before each timed call
-    s, _, _ = cp.step()
-    return {"value": 1.0 / s["total_s"], "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-            "sample": cpu_sample_desc(nx, s), "sample_seconds": s["total_s"]}
+    s, x, v = cp.step()
+    return {"value": 1.0 / s["total_s"], "unit": UNIT, "cores": cp.threads, "kind": "port",
+            "sample": cpu_sample_desc(nx, s, cp.F), "sample_seconds": s["total_s"]}, x, v
 
 
 def run_reference_arm(args):
@@ -191,13 +208,14 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": 1.0 / per, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config 4: 2-D Matern SPDE GMRF posterior, {nx}x{nx} P1 mesh (n={nx * nx}), "
-                               "numeric supernodal Cholesky + mean + selected-inversion variances per step",
-                   "n": nx * nx, "nnz_L": int(cp.info.nnz_L), "factor_flops": cp.info.flops,
+        "config": workload_config(nx, cp.n, cp.prob["Qpost"].nnz),
+        "detail": {"nnz_L": int(cp.F.nnz_L), "factor_flops": cp.F.flops, "setup_s_outside_timing": round(cp.setup_s, 2),
+                   "cpu_scope": "the whole host: one posterior problem at a time on all host cores, whatever --gpus says "
+                                "(the CPU box does not grow with the number of GPUs)",
                    "note": "CPU arm = oracle port on the host cores (CHOLMOD/Julia are not installed in this image); "
-                           "full workload per step, no sampling"},
-        "cpu_baseline": {"value": 1.0 / per, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                         "sample": cpu_sample_desc(nx, last)},
+                           "full workload per step, no sampling; no product code or library is loaded"},
+        "cpu_baseline": {"value": 1.0 / per, "unit": UNIT, "cores": cp.threads, "kind": "port",
+                         "sample": cpu_sample_desc(nx, last, cp.F)},
         "e2e": {"value": 1.0 / per, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "parity_check": {"mean_residual": resid, "var_positive": bool(np.all(v > 0))},
@@ -279,6 +297,7 @@ def run_gpu_arm(args):
     t_setup = time.perf_counter()
     # rank r, lane b solves problem r*B + b: independent posterior problems on one sparsity pattern
     lanes = [Lane(pkg, torch, dev, local, nx, rank * B, ordering=args.ordering)]
+    t_analyze = time.perf_counter() - t_setup
     for b in range(1, B):
         lanes.append(Lane(pkg, torch, dev, local, nx, rank * B + b, perm=lanes[0].sym.p))
     t_setup = time.perf_counter() - t_setup
@@ -325,10 +344,9 @@ def run_gpu_arm(args):
     # latency of a single posterior solve with nothing else in flight
     ms_single = timed("steps_device", args.steps, lanes[:1]) / args.steps
 
-    # end-to-end through the host C-ABI calls (pinned host inputs, host outputs)
-    ke = max(1, min(args.steps, 3))
+    # end-to-end through the host C-ABI calls (pinned host inputs, host outputs): the same number of steps
     timed("steps_e2e", 1, lanes)
-    ms_e2e = timed("steps_e2e", ke, lanes) / ke
+    ms_e2e = timed("steps_e2e", args.steps, lanes) / args.steps
 
     if dist is not None:
         t = torch.tensor([ms, ms_e2e, ms_single], device=dev, dtype=torch.float64)
@@ -346,6 +364,7 @@ def run_gpu_arm(args):
         same = float(np.max(np.abs(L.xs - mean))) <= 1e-12 * float(np.max(np.abs(mean))) + 1e-300
         same = same and float(np.max(np.abs(L.v - var))) <= 1e-12 * float(np.max(np.abs(var)))
         ok = ok and r < 1e-9 and varpos and same
+    gpu_mean0, gpu_var0 = L0.d_x.cpu().numpy(), L0.d_var.cpu().numpy()
 
     # per-kernel profile of one more step (CUDA events around every launch on the library's stream)
     roofline = None
@@ -368,81 +387,300 @@ def run_gpu_arm(args):
                 row["tflops"] = round(p["flops"] / p["ms"] * 1e-9, 3)
             if p["bytes"] > 0 and p["ms"] > 0:
                 row["gbs"] = round(p["bytes"] / p["ms"] * 1e-6, 1)
+            # the kernel's own roofline fraction: tensor peak for the DMMA kernels, HBM peak for the streaming ones
+            if "tflops" in row and ("gemm" in p["name"] or "apply_inv" in p["name"] or "potrf" in p["name"]):
+                row["bound"], row["frac"] = "tensor", round(row["tflops"] / fp64_peak, 4)
+            elif "gbs" in row:
+                row["bound"], row["frac"] = "hbm", round(row["gbs"] / hbm_peak, 4)
             prof_rows.append(row)
         top = max(prof, key=lambda q: q["ms"])
-        traffic = ncu_traffic(top["name"])
+        traffic, traffic_note = ncu_traffic(top["name"], nx, args.ordering, int(top["launches"]))
         if top["flops"] > 0 and "gemm" in top["name"]:
             ach = top["flops"] / top["ms"] * 1e-9
             roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": fp64_peak,
-                        "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
+                        "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic, "traffic_source": traffic_note,
                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_probe.json); "
                                        "FP64 tensor (DMMA) issue peak 37.1 TFLOP/s; no f64 kind exists for tcgen05",
                         "launches_per_step": top["launches"], "ms_per_step": top["ms"],
                         "flops_per_step": top["flops"],
+                        "whole_step_frac": (sum(p["flops"] for p in prof) / (ms / args.steps / B) * 1e-9) / fp64_peak,
                         "note": "achieved = algorithmic flops of all launches of this kernel in one posterior solve / "
-                                "their summed CUDA-event durations (profiled replay of the same step, one problem in flight)"}
+                                "their summed CUDA-event durations (profiled replay of the same step, one problem in "
+                                "flight); whole_step_frac = all flops of a solve / the timed per-solve time / peak"}
         else:
             ach = top["bytes"] / top["ms"] * 1e-6 if top["ms"] > 0 else 0.0
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                        "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_note,
+                        "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                         "launches_per_step": top["launches"], "ms_per_step": top["ms"]}
+
+    # ---- the multi-GPU paths that exchange data (and, at N = 1, their one-GPU versions), outside the timed region ----
+    extras = {}
+    if not args.skip_extras:
+        try:
+            extras["rbmc_sharded"] = bench_rbmc_sharded(pkg, torch, dist, L0, rank, world, dev)
+        except Exception as e:  # noqa: BLE001
+            extras["rbmc_sharded"] = {"error": f"{type(e).__name__}: {e}"}
+    del lanes, L0, L  # the factor arenas (tens of GB) go back to the pool, then to the driver
+    import gc
+
+    gc.collect()
+    pkg.pool_trim(0)
+    torch.cuda.empty_cache()
+    if not args.skip_extras:
+        try:
+            extras["btd_dist"] = bench_btd_dist(pkg, torch, dist, rank, world, local, args.btd_b, args.btd_blocks, fp64_peak)
+        except Exception as e:  # noqa: BLE001
+            extras["btd_dist"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    cpu = None
+    cpu, parity_cpu = None, {}
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(nx)
+        cpu, x_cpu, v_cpu = cpu_baseline(nx)
+        # the 1M-node headline against the CPU port on the identical problem (problem 0): north-star tolerances
+        parity_cpu = {"mean_rel_vs_cpu": float(np.linalg.norm(gpu_mean0 - x_cpu) / np.linalg.norm(x_cpu)),
+                      "var_max_rel_vs_cpu": float(np.max(np.abs(gpu_var0 - v_cpu) / np.abs(v_cpu))),
+                      "tol_mean": TOL_MEAN_VS_CPU, "tol_var": TOL_VAR_VS_CPU}
+        ok = ok and parity_cpu["mean_rel_vs_cpu"] < TOL_MEAN_VS_CPU and parity_cpu["var_max_rel_vs_cpu"] < TOL_VAR_VS_CPU
     per_step = ms / args.steps
     line = {
         "metric": METRIC, "value": world * B * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config 4: 2-D Matern SPDE GMRF posterior, {nx}x{nx} P1 mesh (n={n}), numeric "
-                               "supernodal Cholesky + mean + selected-inversion variances per posterior solve; "
-                               f"one step = one batch of {B} independent posterior problems per GPU (same pattern, "
-                               "different values; the reference's dataset loop), each on its own CUDA stream",
-                   "n": n, "nnz_Q": int(Qp.nnz), "nnz_L": int(info.nnz_L), "factor_flops": info.flops,
+        "config": workload_config(nx, n, Qp.nnz),
+        "detail": {"step": f"one step = one batch of {B} independent posterior problems per GPU (same pattern, different "
+                           "values; the reference's dataset loop), each on its own CUDA stream",
+                   "nnz_L": int(info.nnz_L), "factor_flops": info.flops,
                    "nsuper": int(info.nsuper), "levels": int(info.nlevels), "max_front": int(info.max_front),
-                   "front_arena_gb": info.front_bytes / 1e9, "ordering": {"nd": "library nested dissection (geometric, minimum-vertex-cover separators"
+                   "front_arena_gb": info.front_bytes / 1e9,
+                   "ordering": {"nd": "library nested dissection (geometric, minimum-vertex-cover separators"
                                       + (")" if os.environ.get("GMRFB_ND_COVER", "1") != "0" else " off: plain boundary layers)"),
                                 "ndgraph": "library nested dissection (graph bisection, no coordinates)",
                                 "nd_amd": "library nested dissection (graph) with halo-AMD leaves",
                                 "amd": "library approximate minimum degree"}[args.ordering],
                    "problems_per_gpu_in_flight": B, "solves_per_step": B,
                    "single_solve_latency_ms": ms_single,
-                   "l2_policy": "working set (front arenas, 20 GB per problem) >> 126 MB L2; no flush needed",
-                   "setup_s_outside_timing": round(t_setup, 2)},
-        "e2e": {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(B * (L0.nz_host.numel() * 8 + n * 8)), "d2h_bytes_per_step": int(B * 2 * n * 8)},
+                   "analyze_s": round(t_analyze, 2), "setup_s_outside_timing": round(t_setup, 2)},
+        "e2e": {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "steps": args.steps,
+                "h2d_bytes_per_step": int(B * (Qp.nnz * 8 + n * 8)), "d2h_bytes_per_step": int(B * 2 * n * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "kernel_profile": prof_rows,
-        "parity_check": {"mean_residual": resid, "var_positive": varpos, "ok": bool(ok)},
+        "parity_check": {"mean_residual": resid, "var_positive": varpos, **parity_cpu, "ok": bool(ok)},
         "cpu_baseline": cpu,
+        **extras,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     if not ok:
-        sys.exit("bench: parity spot check failed")
+        sys.exit("bench: parity check failed")
 
 
-def ncu_traffic(kernel_name):
+def bench_rbmc_sharded(pkg, torch, dist, L0, rank, world, dev, nsamp=64):
+    """Sample-sharded RBMC-64 on the bench problem (RBMCStrategy(N) of
+    scripts/darcy/solve_darcy_gmrf-fem.jl:100,174): every rank holds the factor, takes its share of the sample columns
+    (drawn from one seeded stream, identical on every rank) and the estimates are combined by ONE all-reduce of an
+    n-vector over NCCL.  Reported: the sharded time (CUDA events, max over ranks), the one-GPU time of all 64 columns on
+    the same factor, and the exchange."""
+    n = L0.n
+    Qd = pkg.SparseMatrix(L0.prob["Qpost"], ctx=L0.ctx)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    Z = torch.randn((nsamp, n), dtype=torch.float64, device=dev, generator=g)  # same on every rank
+    lo, hi = pkg.dist.sample_bounds(nsamp, world)[rank]
+
+    def one_gpu():
+        return L0.fac.var_rbmc(Qd, Z)
+
+    def sharded():
+        part = np.zeros(n)
+        if hi > lo:
+            part = L0.fac.var_rbmc(Qd, Z[lo:hi].contiguous()) * ((hi - lo) / nsamp)
+        t = torch.from_numpy(part).to(dev)
+        t0 = time.perf_counter()
+        if dist is not None:
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        return t.cpu().numpy(), time.perf_counter() - t0
+
+    def wall(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        torch.cuda.synchronize()
+        return out, (time.perf_counter() - t0) / reps
+
+    v1, t1 = wall(one_gpu)
+    (vs, t_ex), ts = wall(sharded)
+    tt = torch.tensor([t1, ts, t_ex], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return {"what": f"RBMC-{nsamp} marginal variances of the bench problem (n={n}), sample columns split over the ranks, "
+                    "one all-reduce of an n-vector; host-timed calls through the C ABI incl. the D2H of the result",
+            "nsamp": nsamp, "one_gpu_ms": float(tt[0]) * 1e3, "sharded_ms": float(tt[1]) * 1e3,
+            "allreduce_ms": float(tt[2]) * 1e3, "speedup_vs_1gpu": float(tt[0] / tt[1]),
+            "max_rel_diff_vs_1gpu": float(np.max(np.abs(vs - v1) / np.abs(v1))),
+            "limiter": "every backward sweep is a chain of ~17 tree levels of small launches whose length does not "
+                       "shrink with the panel width; the factor (not timed here) is computed redundantly per rank"}
+
+
+def bench_btd_dist(pkg, torch, dist, rank, world, local, b, nblocks, fp64_peak, nrhs=8):
+    """Time-sharded block-tridiagonal factor + 8-RHS solve at fixed size (strong scaling; SURVEY.md §8e row 3,
+    src/tridiagonal_cholesky.jl:65-82 across ranks): local interior factor + spikes, one all-gather of three b x b
+    blocks per rank over NCCL, reduced (P-1)-block Schur system, local back-substitution.  At N = 1 this is the
+    sequential chain.  Rank 0 also factors the whole chain on its own GPU for `speedup_vs_1gpu`."""
+    dev = torch.device("cuda", local)
+    ctx = pkg.Context(local)
+    rng = np.random.default_rng(0)
+    R = rng.standard_normal((b, b)) / np.sqrt(b)
+    Dblk = R @ R.T + 2.0 * np.eye(b)
+    Bblk = 0.4 * R
+    Dt = torch.from_numpy(np.ascontiguousarray(Dblk.T)).to(dev)
+    Bt = torch.from_numpy(np.ascontiguousarray(Bblk.T)).to(dev)
+    flops_seq = (nblocks - 1) * 7.0 / 3.0 * b**3 + b**3 / 3.0
+    rhs = np.random.default_rng(1).standard_normal((b * nblocks, nrhs))
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    out = {"what": f"block-tridiagonal Cholesky, b={b} x {nblocks} blocks (n={b * nblocks}), FP64, device-resident blocks, "
+                   f"{nrhs} right-hand sides; strong scaling over the ranks", "b": b, "n_blocks": nblocks, "nrhs": nrhs,
+           "seq_flops": flops_seq}
+    seq = None
+    if world == 1 or rank == 0:
+        # the sequential chain on one GPU (the 1-GPU reference of the speed-up); the chain repeats one diagonal and one
+        # sub-diagonal block, so it is handed over as four blocks (gmrfb_btd_factor_ssm) instead of N copies
+        ts = []
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            F = pkg.tridiagonal_cholesky_ssm(Dblk, Dblk, Dblk, Bblk, nblocks, ctx=ctx)
+            ctx.sync()
+            ts.append(time.perf_counter() - t)
+            if rep == 0:
+                del F
+        pkg.ldiv(F, rhs)  # first solve builds the block inverses
+        t = time.perf_counter()
+        x = pkg.ldiv(F, rhs)
+        t_sol = time.perf_counter() - t
+        res = _btd_residual(Dblk, Bblk, x, rhs, 0, nblocks, b)
+        seq = {"factor_s": ts[1], "solve_s": t_sol, "tflops": flops_seq / ts[1] * 1e-12,
+               "frac_of_dgemm_peak": flops_seq / ts[1] * 1e-12 / fp64_peak, "max_rel_residual": res}
+        del F
+        import gc
+
+        gc.collect()
+        pkg.pool_trim(0)
+        torch.cuda.empty_cache()
+    out["sequential_1gpu"] = seq
+    if world == 1:
+        return out
+    lo, hi = pkg.dist.slab_bounds(nblocks, world)[rank]
+    nloc = hi - lo
+    Dl = Dt.unsqueeze(0).expand(nloc, b, b).contiguous()
+    Bl = Bt.unsqueeze(0).expand(nloc, b, b).contiguous()
+    best = None
+    for rep in range(2):
+        sync()
+        t0 = time.perf_counter()
+        ts_ = pkg.dist.TimeShardedCholesky(Dl, Bl, rank, world, ctx=ctx, auto_exchange=False)  # local factor + spikes
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t1b = time.perf_counter()
+        gathered = ts_._allgather(ts_.iface())  # 3 b^2 doubles per rank, NCCL all-gather
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        ts_.reduce(gathered)  # reduced (P-1)-block chain, redundantly on every rank
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        fac_s, loc_s, ex_s, red_s = maxr([(t1 - t0) + (t3 - t1b), t1 - t0, t2 - t1b, t3 - t2])
+        sync()
+        t = time.perf_counter()
+        x = ts_.solve(rhs[lo * b:hi * b])
+        torch.cuda.synchronize()
+        (sol_s,) = maxr([time.perf_counter() - t])
+        best = dict(factor_s=fac_s, local_s=loc_s, exchange_s=ex_s, reduced_s=red_s, solve_s=sol_s)
+        if rep == 0:
+            del ts_, gathered
+    # residual of this rank's rows needs the neighbours' solution rows: gather the solution (small)
+    xt = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    sizes = [(h - l) * b for l, h in pkg.dist.slab_bounds(nblocks, world)]
+    parts = [torch.empty((s, nrhs), dtype=torch.float64, device=dev) for s in sizes]
+    dist.all_gather(parts, xt)
+    xfull = torch.cat(parts).cpu().numpy()
+    (res,) = maxr([_btd_residual(Dblk, Bblk, xfull, rhs, lo, hi, b)])
+    local_flops = ((19.0 if rank > 0 else 7.0) / 3.0) * b**3 * nloc
+    (lt,) = maxr([local_flops / best["local_s"] * 1e-12])
+    out.update(best)
+    out.update({"max_rel_residual": res, "seq_equiv_tflops": flops_seq / best["factor_s"] * 1e-12,
+                "local_tflops_per_gpu": lt,
+                "limiter": "the Schur split trades flops for parallelism: every rank but the first does 19/3 b^3 flops "
+                           "per block (factor + spike recurrence through W_i = L_i^-1) instead of 7/3 b^3, so P ranks "
+                           "finish in about (19/7)/P of the sequential time; exchange and reduced system are small"})
+    if rank == 0 and seq is not None:
+        out["speedup_vs_1gpu"] = seq["factor_s"] / best["factor_s"]
+        out["solve_speedup_vs_1gpu"] = seq["solve_s"] / best["solve_s"]
+    return out
+
+
+def _btd_residual(Dblk, Bblk, xfull, rhs, lo, hi, b):
+    """Largest relative residual over a sample of (at most ~16) block rows of [lo, hi) incl. the first and the last."""
+    res, N = 0.0, xfull.shape[0] // b
+    pick = sorted(set(list(range(lo, hi, max(1, (hi - lo) // 14))) + [lo, hi - 1]))
+    for k in pick:
+        r = Dblk @ xfull[k * b:(k + 1) * b]
+        if k > 0:
+            r += Bblk @ xfull[(k - 1) * b:k * b]
+        if k < N - 1:
+            r += Bblk.T @ xfull[(k + 1) * b:(k + 2) * b]
+        res = max(res, float(np.linalg.norm(r - rhs[k * b:(k + 1) * b]) / np.linalg.norm(rhs[k * b:(k + 1) * b])))
+    return res
+
+
+def ncu_traffic(kernel_name, nx, ordering, launches):
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel, averaged over all its
-    launches of one posterior solve, from the committed ncu pass over the same bench step
-    (profiles/r01_gemm_traffic.json, written by tools/summarize_traffic.py from tools/gpu_evidence.sh); None when
-    no capture of that kernel is committed."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
-            d = json.load(f)
-        e = d["kernels"].get(kernel_name)
-        return e["bytes_per_launch"] if e else None
-    except Exception:  # noqa: BLE001
-        return None
+    launches of one posterior solve, from the committed ncu pass over the same bench step (profiles/r02_gemm_traffic.json,
+    written by tools/summarize_traffic.py from tools/gpu_evidence.sh).  The capture records its own configuration; the
+    number is only reported when mesh size, ordering, vertex-cover setting and the kernel's launch count per solve all
+    match this run — otherwise None (a stale capture is not a measurement of this run)."""
+    for tag in ("r02", "r01"):
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{tag}_gemm_traffic.json")) as f:
+                d = json.load(f)
+            e = d["kernels"].get(kernel_name)
+            cfg = d.get("config", {})
+            if not e:
+                continue
+            same = (cfg.get("nx") == nx and cfg.get("ordering") == ordering
+                    and str(cfg.get("nd_cover", "1")) == os.environ.get("GMRFB_ND_COVER", "1")
+                    and int(e.get("launches", -1)) == launches)
+            if same:
+                return e["bytes_per_launch"], f"profiles/{tag}_gemm_traffic.json (same nx, ordering and launch count)"
+        except Exception:  # noqa: BLE001
+            continue
+    return None, "no committed ncu capture matches this run's configuration"
 
 
 def main():
@@ -452,11 +690,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=1001, help="mesh nodes per side (1001 -> 1,002,001 nodes)")
-    ap.add_argument("--nx-sample", dest="nx_sample", type=int, default=0, help="(unused; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the btd_dist / rbmc_sharded measurements")
+    ap.add_argument("--btd-b", dest="btd_b", type=int, default=4096)
+    ap.add_argument("--btd-blocks", dest="btd_blocks", type=int, default=256,
+                    help="time blocks of the strong-scaling block-tridiagonal measurement (256 x b=4096: 69 GB of factor, "
+                         "fits one GPU so that the 1-GPU chain is measured by the same run)")
     ap.add_argument("--ordering", choices=["nd", "ndgraph", "nd_amd", "amd"], default="nd",
                     help="fill-reducing ordering computed once by the library and reused as perm=p (default: geometric "
-                         "nested dissection, the configuration every committed profile was measured with)")
+                         "nested dissection with minimum-vertex-cover separators)")
     ap.add_argument("--inflight", type=int, default=4,
                     help="independent posterior problems in flight per GPU (one CUDA stream each)")
     args = ap.parse_args()

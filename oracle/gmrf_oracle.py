@@ -362,9 +362,9 @@ def _capsule_ptr(mod, name):
 
 
 def build_supernodal(force: bool = False) -> str:
-    src = os.path.join(_HERE, "supernodal_chol.c")
-    if force or not os.path.exists(_SN_PATH) or os.path.getmtime(_SN_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _SN_PATH, src, "-lm"])
+    srcs = [os.path.join(_HERE, "supernodal_chol.c"), os.path.join(_HERE, "sn_symbolic.c")]
+    if force or not os.path.exists(_SN_PATH) or os.path.getmtime(_SN_PATH) < max(os.path.getmtime(x) for x in srcs):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _SN_PATH, *srcs, "-lm"])
     return _SN_PATH
 
 
@@ -388,8 +388,141 @@ def _load_sn():
         L.sn_solve.argtypes = [I, I, i64p, i64p, i64p, i64p, f64p, f64p, I, ctypes.c_int, ctypes.c_int]
         L.sn_selinv.argtypes = [I, I, i64p, i64p, i64p, i64p, i64p, f64p, f64p]
         L.sn_selinv.restype = I
+        L.orc_sn_symbolic.argtypes = [I, i64p, i64p, i64p, i64p]
+        L.orc_sn_symbolic.restype = I
+        L.orc_sn_symbolic_nrows.restype = I
+        L.orc_sn_symbolic_nnzL.restype = I
+        L.orc_sn_symbolic_flops.restype = ctypes.c_double
+        L.orc_sn_symbolic_fetch.argtypes = [i64p, i64p, i64p]
         _sn = L
     return _sn
+
+
+def _min_vertex_cover(u, v):
+    """Minimum vertex cover of the bipartite graph with edges (u[k], v[k]) (u: left labels, v: right labels)."""
+    from scipy.sparse.csgraph import maximum_bipartite_matching
+
+    if u.size == 0:
+        return np.zeros(0, np.int64)
+    Lset, li = np.unique(u, return_inverse=True)
+    Rset, ri = np.unique(v, return_inverse=True)
+    B = sp.csr_matrix((np.ones(li.size, np.int8), (li, ri)), shape=(Lset.size, Rset.size))
+    B.sum_duplicates()
+    match_l = maximum_bipartite_matching(B, perm_type="column")  # for every left vertex its right partner or -1
+    match_r = np.full(Rset.size, -1, np.int64)
+    ok = match_l >= 0
+    match_r[match_l[ok]] = np.flatnonzero(ok)
+    # alternating reachability from the unmatched left vertices: left -> right along any edge, right -> left along
+    # matching edges
+    vis_l = np.zeros(Lset.size, bool)
+    vis_r = np.zeros(Rset.size, bool)
+    frontier = np.flatnonzero(~ok)
+    vis_l[frontier] = True
+    indptr, indices = B.indptr, B.indices
+    while frontier.size:
+        cnt = indptr[frontier + 1] - indptr[frontier]
+        if cnt.sum() == 0:
+            break
+        pos = np.repeat(indptr[frontier], cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+        nr = np.unique(indices[pos])
+        nr = nr[~vis_r[nr]]
+        vis_r[nr] = True
+        nl = match_r[nr]
+        nl = nl[nl >= 0]
+        nl = nl[~vis_l[nl]]
+        vis_l[nl] = True
+        frontier = nl
+    return np.concatenate([Lset[~vis_l], Rset[vis_r]]).astype(np.int64)
+
+
+def nested_dissection(A, coords, leaf: int = 64):
+    """Geometric nested dissection (new->old permutation) for the CPU baseline, independent of the product's
+    orderings: level-synchronous recursive coordinate bisection at the median of the wider axis; the separator of a
+    cut is a minimum vertex cover of the cut edges (maximum bipartite matching + Koenig).  Leaf regions first, then the
+    separators from the deepest level up to the top one (the kind of ordering CHOLMOD obtains from METIS when the
+    reference calls `cholesky(A)` on a mesh matrix)."""
+    A = _csc(A)
+    n = A.shape[0]
+    coords = np.asarray(coords, dtype=np.float64)
+    C = A.tocoo()
+    ei, ej = C.row[C.row != C.col], C.col[C.row != C.col]
+    region = np.zeros(n, np.int64)      # current region of every vertex still inside a region
+    sep_level = np.full(n, -1, np.int64)  # level at which a vertex became a separator vertex (-1: none yet)
+    active = np.ones(n, bool)
+    level = 0
+    while True:
+        idx = np.flatnonzero(active)
+        if idx.size == 0:
+            break
+        reg = region[idx]
+        sizes = np.bincount(reg)
+        big = sizes[reg] > leaf
+        if not big.any():
+            break
+        idx, reg = idx[big], reg[big]
+        # wider axis per region, median split
+        nreg = int(reg.max()) + 1
+        ext = np.zeros((nreg, coords.shape[1]))
+        for a in range(coords.shape[1]):
+            lo = np.full(nreg, np.inf)
+            hi = np.full(nreg, -np.inf)
+            np.minimum.at(lo, reg, coords[idx, a])
+            np.maximum.at(hi, reg, coords[idx, a])
+            ext[:, a] = hi - lo
+        axis = np.argmax(ext, axis=1)
+        key = coords[idx, axis[reg]]
+        order = np.lexsort((key, reg))
+        ridx, rreg = idx[order], reg[order]
+        start = np.flatnonzero(np.r_[True, rreg[1:] != rreg[:-1]])
+        cnt = np.diff(np.r_[start, rreg.size])
+        rank = np.arange(rreg.size) - np.repeat(start, cnt)
+        side = np.zeros(n, np.int8)  # 1: low half, 2: high half (of a region being split at this level)
+        low = rank < np.repeat(cnt // 2, cnt)
+        side[ridx[low]] = 1
+        side[ridx[~low]] = 2
+        # separator: a minimum vertex cover of the cut edges (low side <-> high side inside one region), by maximum
+        # bipartite matching + Koenig's theorem; all regions of the level at once (their cut graphs are disjoint)
+        m = (side[ei] == 1) & (side[ej] == 2) & (region[ei] == region[ej]) & active[ei] & active[ej]
+        sep = _min_vertex_cover(ei[m], ej[m])
+        sep_level[sep] = level
+        active[sep] = False
+        side[sep] = 0
+        # children regions: 2 * region + (0 | 1) for the vertices of split regions; unsplit regions become inactive leaves
+        split = side > 0
+        region[split] = 2 * region[split] + (side[split] == 2)
+        small = active & ~split & (sep_level < 0)
+        small_idx = np.flatnonzero(small)
+        # leaves keep their region id but must not collide with the renumbered ones: tag them with the level
+        region[small_idx] = -(region[small_idx] * 64 + level) - 1
+        active[small_idx] = False
+        # compress region ids of the active vertices
+        act = np.flatnonzero(active)
+        if act.size:
+            _, region[act] = np.unique(region[act], return_inverse=True)
+        level += 1
+    # elimination order: leaves (grouped by region), then separators by descending level (grouped by coordinates order)
+    lvl_key = np.where(sep_level < 0, level + 1, sep_level)
+    perm = np.lexsort((region, -lvl_key))
+    return perm.astype(np.int64)
+
+
+def supernodal_symbolic(A, perm):
+    """Postordered permutation, supernode partition and supernodal row structures for `perm` (oracle/sn_symbolic.c):
+    -> dict(perm_int, sptr, rptr, rows, nnz_L, flops)."""
+    L = _load_sn()
+    A = _csc(A)
+    n = A.shape[0]
+    Ap, Ai = A.indptr.astype(np.int64), A.indices.astype(np.int64)
+    perm = np.ascontiguousarray(perm, dtype=np.int64)
+    perm_int = np.empty(n, np.int64)
+    ns = L.orc_sn_symbolic(n, Ap, Ai, perm, perm_int)
+    if ns < 0:
+        raise MemoryError(f"orc_sn_symbolic failed ({ns})")
+    sptr, rptr = np.empty(ns + 1, np.int64), np.empty(ns + 1, np.int64)
+    rows = np.empty(max(int(L.orc_sn_symbolic_nrows()), 1), np.int64)
+    nnzL, flops = int(L.orc_sn_symbolic_nnzL()), float(L.orc_sn_symbolic_flops())
+    L.orc_sn_symbolic_fetch(sptr, rptr, rows)
+    return dict(perm_int=perm_int, sptr=sptr, rptr=rptr, rows=rows[: int(rptr[-1])], nnz_L=nnzL, flops=flops)
 
 
 class SupernodalCholesky:
@@ -398,15 +531,20 @@ class SupernodalCholesky:
     postorder of the user's perm), ``sptr`` (first internal column of each supernode) and per-supernode row lists
     (own columns first, then the below rows ascending) in the internal numbering."""
 
-    def __init__(self, A, perm_int, sptr, rows_list):
+    def __init__(self, A, perm_int, sptr, rows_list, rptr=None):
+        """``rows_list``: per-supernode row lists, or (with ``rptr``) the flat row array of `supernodal_symbolic`."""
         A = _csc(A)
         self.n = n = A.shape[0]
         self.perm = np.ascontiguousarray(perm_int, dtype=np.int64)
         self.sptr = np.ascontiguousarray(sptr, dtype=np.int64)
         self.ns = ns = len(self.sptr) - 1
-        self.rptr = np.zeros(ns + 1, np.int64)
-        np.cumsum([len(r) for r in rows_list], out=self.rptr[1:])
-        self.rows = np.ascontiguousarray(np.concatenate(rows_list) if ns else np.zeros(0), dtype=np.int64)
+        if rptr is not None:
+            self.rptr = np.ascontiguousarray(rptr, dtype=np.int64)
+            self.rows = np.ascontiguousarray(rows_list, dtype=np.int64)
+        else:
+            self.rptr = np.zeros(ns + 1, np.int64)
+            np.cumsum([len(r) for r in rows_list], out=self.rptr[1:])
+            self.rows = np.ascontiguousarray(np.concatenate(rows_list) if ns else np.zeros(0), dtype=np.int64)
         sc = np.diff(self.sptr)
         d = np.diff(self.rptr)
         snode = np.repeat(np.arange(ns, dtype=np.int64), sc)
@@ -462,6 +600,17 @@ class SupernodalCholesky:
         out = np.empty(self.n)
         out[self.perm] = z
         return out
+
+    @classmethod
+    def analyze(cls, A, coords=None, perm=None, leaf=64):
+        """Order (own nested dissection, or a given perm), analyse (oracle/sn_symbolic.c) and factorise: the CPU
+        baseline path without any of the product's host code."""
+        if perm is None:
+            perm = nested_dissection(A, coords, leaf)
+        sy = supernodal_symbolic(A, perm)
+        F = cls(A, sy["perm_int"], sy["sptr"], sy["rows"], rptr=sy["rptr"])
+        F.nnz_L, F.flops = sy["nnz_L"], sy["flops"]
+        return F
 
     def logdet(self):
         sc = np.diff(self.sptr)

@@ -104,3 +104,48 @@ def test_posterior_and_gauss_newton_restatement(orc, W):
     x1 = orc.gauss_newton_step(prob["Q"], A, prob["q_eps"], x0, prob["Q"] @ np.zeros(n), prob["y"] - A @ x0,
                                np.arange(n))
     np.testing.assert_allclose(x1, ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("nx", [9, 40, 97])
+def test_oracle_ordering_and_supernodal_symbolic(orc, pkg, W, nx):
+    """The CPU baseline's own analysis (oracle/sn_symbolic.c + the NumPy nested dissection): a valid permutation; column
+    counts / nnz(L) / flops equal to the scalar oracle's and, bit-exactly, to the product's host analysis of the same
+    permutation (two independent implementations of the same integer algorithms); supernodes that tile the columns,
+    contain their children's rows, and factor to the scalar oracle's numbers."""
+    prob = W.matern_posterior(nx, obs_frac=0.2, corr_range=0.15, seed=nx)
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    p = orc.nested_dissection(Q, prob["nodes"], leaf=16)
+    assert np.array_equal(np.sort(p), np.arange(n))
+    sy = orc.supernodal_symbolic(Q, p)
+    ref = orc.SparseCholesky(Q, sy["perm_int"])
+    assert sy["nnz_L"] == ref.nnz == int(ref.colcount.sum())
+    assert np.all(ref.parent[:-1] > np.arange(n - 1)) or n == 1  # postordered: parents follow their children
+    sym = pkg.Symbolic(Q, perm=p, host_only=True)
+    assert sym.info.nnz_L == sy["nnz_L"] and sym.info.flops == sy["flops"]
+    sptr, rptr, rows = sy["sptr"], sy["rptr"], sy["rows"]
+    assert sptr[0] == 0 and sptr[-1] == n and np.all(np.diff(sptr) > 0)
+    Lpat = ref.L().tocsc()
+    for s in range(len(sptr) - 1):
+        r = rows[rptr[s]:rptr[s + 1]]
+        w = sptr[s + 1] - sptr[s]
+        assert np.array_equal(r[:w], np.arange(sptr[s], sptr[s + 1])) and np.all(np.diff(r[w:]) > 0)
+        # the structure of every column of the supernode is contained in the supernode's row list
+        for j in range(sptr[s], sptr[s + 1]):
+            assert set(Lpat.indices[Lpat.indptr[j]:Lpat.indptr[j + 1]]) <= set(r.tolist())
+    F = orc.SupernodalCholesky.analyze(Q, perm=p)
+    b = np.random.default_rng(0).standard_normal(n)
+    assert np.linalg.norm(F.solve(b) - orc.SparseCholesky(Q, p).solve(b)) < 1e-11 * np.linalg.norm(b)
+    np.testing.assert_allclose(F.selinv_diag(), orc.SparseCholesky(Q, p).selinv_diag(), rtol=1e-9)
+
+
+def test_oracle_nd_separators_separate(orc, W):
+    """After removing the top separator (the last vertices of the ordering that form one etree chain) the mesh falls
+    apart: a structural check of the vertex-cover separators, via the fill they produce against a random ordering."""
+    prob = W.matern_posterior(60, obs_frac=0.2, corr_range=0.15, seed=1)
+    Q = prob["Qpost"]
+    p = orc.nested_dissection(Q, prob["nodes"], leaf=32)
+    nd = orc.supernodal_symbolic(Q, p)["nnz_L"]
+    rnd = orc.supernodal_symbolic(Q, np.random.default_rng(0).permutation(Q.shape[0]))["nnz_L"]
+    nat = orc.supernodal_symbolic(Q, np.arange(Q.shape[0]))["nnz_L"]
+    assert nd < 0.65 * nat and nd < 0.2 * rnd  # 60 x 60 mesh: banded (natural) fill is n^1.5, nested dissection n log n
