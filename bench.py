@@ -35,6 +35,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# a dedicated benchmark process: let the library's buffer cache hold the largest factor (the strong-scaling block-
+# tridiagonal measurement re-creates a 69 GB arena); read once when the library makes its first device allocation
+os.environ.setdefault("GMRFB_POOL_MAX_GB", "150")
 import __graft_entry__ as entry  # noqa: E402
 
 METRIC = "GMRF posterior (mean+marginal var) solves/sec"
@@ -573,7 +576,7 @@ def bench_btd_dist(pkg, torch, dist, rank, world, local, b, nblocks, fp64_peak, 
         for rep in range(2):
             torch.cuda.synchronize()
             t = time.perf_counter()
-            F = pkg.tridiagonal_cholesky_ssm(Dblk, Dblk, Dblk, Bblk, nblocks, ctx=ctx)
+            F = pkg.tridiagonal_cholesky_ssm(Dt, Dt, Dt, Bt, nblocks, ctx=ctx)
             ctx.sync()
             ts.append(time.perf_counter() - t)
             if rep == 0:

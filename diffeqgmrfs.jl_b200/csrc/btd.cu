@@ -8,6 +8,7 @@
 // right-sided GEMM/TRSM of the same kernels that factorise.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <functional>
 #include <cmath>
 #include <memory>
@@ -24,6 +25,16 @@ struct gmrfb_btd {
   int64_t slot = 0;  // doubles per block slot
   DevBuf<double> arena, dinv;  // dinv: scratch of inverted <=64x64 diagonal blocks
   DevPlan plan_first, plan_step;
+  // look-ahead schedule (default for b >= 512): C_{i+1} = B_{i+1} L_i^{-T} is queued on a second stream and follows the
+  // POTRF of block i panel by panel (one event per 64-column panel), so the two latency-bound chains overlap; the
+  // inverses of L_i's diagonal blocks are kept in one of two alternating slot sets instead of being recomputed
+  DevPlan la_potrf, la_trsm, la_syrk;
+  DevBuf<double> la_dinv;  // 2 sets of ceil(b / 64) inverse-block slots
+  std::vector<cudaEvent_t> la_ev[2];   // [set][j]: panel j of L_i is final (set = i & 1)
+  std::vector<cudaEvent_t> la_cev[2];  // [set][j]: column block j of C_i is final
+  cudaEvent_t la_done = nullptr;
+  cudaStream_t la_stream = nullptr, la_stream2 = nullptr;  // TRSM lane, SYRK lane
+  bool lookahead = false;
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_block = -1;
   bool factored = false;
@@ -157,7 +168,77 @@ gmrfb_status btd_alloc(gmrfb_ctx* ctx, int64_t b, int64_t N, std::unique_ptr<gmr
   if (rc != GMRFB_OK) return rc;
   if ((rc = ensure_dinv(f.get(), f->plan_first.host)) != GMRFB_OK) return rc;
   if ((rc = ensure_dinv(f.get(), f->plan_step.host)) != GMRFB_OK) return rc;
-  return upload_plan(ctx, f->plan_step);
+  if ((rc = upload_plan(ctx, f->plan_step)) != GMRFB_OK) return rc;
+  {
+    const char* e = getenv("GMRFB_BTD_LOOKAHEAD");
+    f->lookahead = e ? (e[0] != '0') : (b >= 512 && N > 1);
+  }
+  if (f->lookahead) {
+    const int64_t coff = (int64_t)f->ld * b;
+    {
+      PlanBuilder B(f->la_potrf.host);
+      plan_potrf_events(B, f->la_potrf.host, 0, 0, (int)b, f->ld, 0);
+    }
+    {
+      PlanBuilder B(f->la_trsm.host);
+      plan_trsm_rlt_events(B, f->la_trsm.host, 0, -f->slot, f->ld, 0, coff, (int)b, (int)b, f->ld);
+    }
+    {
+      // D_{i+1} -= C C' accumulated over K chunks of LA_SYRK_K columns of C, each launch waiting for the last column
+      // block of its chunk: the rank-k updates follow the TRSM as its columns become final
+      Plan& P = f->la_syrk.host;
+      PlanBuilder B(P);
+      const int LA_SYRK_K = 512;
+      for (int c0 = 0; c0 < (int)b; c0 += LA_SYRK_K) {
+        const int kc = std::min(LA_SYRK_K, (int)b - c0);
+        B.begin(LK_GEMM_NT);
+        B.set_wait((c0 + kc - 1) / NB);
+        Task t = make_task();
+        t.a = coff + (int64_t)c0 * f->ld;
+        t.b = t.a;
+        t.c = 0;
+        t.lda = t.ldb = t.ldc = f->ld;
+        t.M = t.N = (int)b;
+        t.K = kc;
+        t.alpha = -1.0;
+        t.beta = 1.0;
+        t.flags = TF_TRI;
+        B.add(t, gemm_tiles((int)b, (int)b, true, GCFG_BIG));
+        P.flops += (double)kc * b * (b + 1);
+        B.end();
+      }
+    }
+    if ((rc = upload_plan(ctx, f->la_potrf)) != GMRFB_OK) return rc;
+    if ((rc = upload_plan(ctx, f->la_trsm)) != GMRFB_OK) return rc;
+    if ((rc = upload_plan(ctx, f->la_syrk)) != GMRFB_OK) return rc;
+    const int nblk = cdiv((int)b, NB);
+    GMRFB_CU(ctx, f->la_dinv.alloc((size_t)2 * nblk * DINV_SLOT));
+    for (int set = 0; set < 2; set++) {
+      f->la_ev[set].resize(nblk);
+      f->la_cev[set].resize(nblk);
+      for (auto& ev : f->la_ev[set]) GMRFB_CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      for (auto& ev : f->la_cev[set]) GMRFB_CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    GMRFB_CU(ctx, cudaEventCreateWithFlags(&f->la_done, cudaEventDisableTiming));
+    int prio_least = 0, prio_greatest = 0;
+    GMRFB_CU(ctx, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    GMRFB_CU(ctx, cudaStreamCreateWithPriority(&f->la_stream, cudaStreamNonBlocking, prio_least));
+    GMRFB_CU(ctx, cudaStreamCreateWithPriority(&f->la_stream2, cudaStreamNonBlocking, prio_least));
+  }
+  return GMRFB_OK;
+}
+
+// one plan on `st`, honouring the per-launch events of a look-ahead schedule
+gmrfb_status run_plan_events(gmrfb_ctx* ctx, const DevPlan& P, const Arenas& ar, const LaunchAux& aux, cudaStream_t st,
+                             const std::vector<cudaEvent_t>* wait_evs, const std::vector<cudaEvent_t>* rec_evs) {
+  for (const Launch& L : P.host.launches) {
+    if (L.wait_ev >= 0 && wait_evs) GMRFB_CU(ctx, cudaStreamWaitEvent(st, (*wait_evs)[L.wait_ev], 0));
+    cudaError_t e = run_launch(L, P.tasks.p, ar, aux, st);
+    if (e != cudaSuccess) return fail(ctx, GMRFB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+    ctx->launches++;
+    if (L.rec_ev >= 0 && rec_evs) GMRFB_CU(ctx, cudaEventRecord((*rec_evs)[L.rec_ev], st));
+  }
+  return GMRFB_OK;
 }
 
 gmrfb_status btd_run_factor(gmrfb_btd* f) {
@@ -166,6 +247,34 @@ gmrfb_status btd_run_factor(gmrfb_btd* f) {
   GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   LaunchAux aux;
   aux.d_info = ctx->d_info;
+  if (f->lookahead && !f->after_block && !ctx->profiling) {
+    // stream 1 (ctx->stream, highest priority): POTRF_i, recording one event per finished 64-column panel of L_i
+    // la_stream :  TRSM_{i+1} (C_{i+1} = B_{i+1} L_i^{-T}), every leaf waiting for the panel of L_i it reads and recording
+    //              one event per finished column block of C_{i+1}
+    // la_stream2:  SYRK_{i+1} (D_{i+1} -= C_{i+1} C_{i+1}') as rank-512 updates, each waiting for its columns of C_{i+1}
+    // => the two latency-bound chains and the GPU-filling rank-k updates overlap; POTRF_{i+1} waits for the last update
+    const int64_t setsz = (int64_t)cdiv((int)f->b, NB) * DINV_SLOT;
+    GMRFB_CU(ctx, cudaEventRecord(f->la_done, ctx->stream));
+    GMRFB_CU(ctx, cudaStreamWaitEvent(f->la_stream, f->la_done, 0));  // the input blocks are in place
+    GMRFB_CU(ctx, cudaStreamWaitEvent(f->la_stream2, f->la_done, 0));
+    for (int64_t i = 0; i < f->N; i++) {
+      const int set = (int)(i & 1);
+      Arenas ar{{f->arena.p + i * f->slot, nullptr, nullptr, nullptr}};
+      gmrfb_status rc;
+      if (i > 0) {
+        ar.dinv = f->la_dinv.p + (int64_t)(1 - set) * setsz;  // inverses kept by POTRF_{i-1}
+        rc = run_plan_events(ctx, f->la_trsm, ar, aux, f->la_stream, &f->la_ev[1 - set], &f->la_cev[set]);
+        if (rc != GMRFB_OK) return rc;
+        rc = run_plan_events(ctx, f->la_syrk, ar, aux, f->la_stream2, &f->la_cev[set], nullptr);
+        if (rc != GMRFB_OK) return rc;
+        GMRFB_CU(ctx, cudaEventRecord(f->la_done, f->la_stream2));
+        GMRFB_CU(ctx, cudaStreamWaitEvent(ctx->stream, f->la_done, 0));
+      }
+      ar.dinv = f->la_dinv.p + (int64_t)set * setsz;
+      rc = run_plan_events(ctx, f->la_potrf, ar, aux, ctx->stream, nullptr, &f->la_ev[set]);
+      if (rc != GMRFB_OK) return rc;
+    }
+  } else
   for (int64_t i = 0; i < f->N; i++) {
     Arenas ar{{f->arena.p + i * f->slot, nullptr, nullptr, nullptr}};
     ar.dinv = f->dinv.p;
@@ -304,6 +413,16 @@ extern "C" gmrfb_status gmrfb_btd_destroy(gmrfb_btd* f) {
   if (!f) return GMRFB_OK;
   cudaSetDevice(f->ctx->device);
   cudaStreamSynchronize(f->ctx->stream);
+  for (cudaStream_t st : {f->la_stream, f->la_stream2})
+    if (st) {
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+    }
+  for (int set = 0; set < 2; set++) {
+    for (auto ev : f->la_ev[set]) cudaEventDestroy(ev);
+    for (auto ev : f->la_cev[set]) cudaEventDestroy(ev);
+  }
+  if (f->la_done) cudaEventDestroy(f->la_done);
   delete f;
   return GMRFB_OK;
 }

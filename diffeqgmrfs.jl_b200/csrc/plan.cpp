@@ -97,8 +97,14 @@ struct FactorProb {
 //   factor [j0, jm);  trailing update of [jm, j1) with K = jm - j0;  factor [jm, j1)
 // with jm a multiple of NB near the middle, down to single NB-wide blocks (POTRF + apply-inverse).  Most of the
 // panel-update flops therefore run in GEMMs with K = width/2, width/4, ... instead of K = NB.
-static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int j0, int j1) {
+static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int j0, int j1,
+                             bool events = false) {
   if (j1 - j0 <= NB) {
+    // with events: column block j0 / NB of L is final after the apply-inverse launch of this leaf (or after the POTRF
+    // launch when no rows lie below the block)
+    bool rows_below = false;
+    for (auto& p : probs)
+      if (j0 < p.s && p.d - (j0 + std::min(NB, p.s - j0)) > 0) rows_below = true;
     B.begin(LK_POTRF);
     {
       int64_t slot = 0;
@@ -109,8 +115,10 @@ static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorPr
                   p.slot0 >= 0 ? p.slot0 + j0 / NB : slot++, false);
       }
     }
+    if (events && !rows_below) B.set_record(j0 / NB);
     B.end();
     B.begin(LK_TRSM_RLT);
+    if (events && rows_below) B.set_record(j0 / NB);
     {
       int64_t slot = 0;
       for (auto& p : probs) {
@@ -126,7 +134,7 @@ static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorPr
   }
   const int nblk = (j1 - j0 + NB - 1) / NB;
   const int jm = j0 + (nblk / 2) * NB;
-  plan_factor_cols(B, P, probs, j0, jm);
+  plan_factor_cols(B, P, probs, j0, jm, events);
   B.begin(LK_GEMM_NT);
   for (auto& p : probs) {
     if (jm >= p.s) continue;
@@ -136,7 +144,7 @@ static void plan_factor_cols(PlanBuilder& B, Plan& P, const std::vector<FactorPr
              c1 - jm, jm - j0, true, -1.0, 1.0);
   }
   B.end();
-  plan_factor_cols(B, P, probs, jm, j1);
+  plan_factor_cols(B, P, probs, jm, j1, events);
 }
 
 static void plan_partial_factor_batch(PlanBuilder& B, Plan& P, const std::vector<FactorProb>& probs, int nbo) {
@@ -173,9 +181,13 @@ struct TrsmProb {
 //   !trans: solve [jm, j1);  X[:, j0:jm] -= X[:, jm:j1] L[jm:j1, j0:jm];   solve [j0, jm)
 // so the updates are GEMMs with K = width/2, width/4, ...; the leaves multiply by the inverted diagonal blocks.
 static void plan_trsm_cols(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>& probs,
-                           const std::vector<int64_t>& slot0, bool trans, int j0, int j1) {
+                           const std::vector<int64_t>& slot0, bool trans, int j0, int j1, bool events = false) {
   if (j1 - j0 <= NB) {
     B.begin(trans ? LK_TRSM_RLT : LK_TRSM_RLN);
+    if (events) {  // wait for panel j of L; afterwards column block j of X is final
+      B.set_wait(j0 / NB);
+      B.set_record(j0 / NB);
+    }
     for (size_t i = 0; i < probs.size(); i++) {
       const auto& p = probs[i];
       if (j0 >= p.n) continue;
@@ -188,7 +200,7 @@ static void plan_trsm_cols(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>&
   const int nblk = (j1 - j0 + NB - 1) / NB;
   const int jm = j0 + (nblk / 2) * NB;
   if (trans) {
-    plan_trsm_cols(B, P, probs, slot0, trans, j0, jm);
+    plan_trsm_cols(B, P, probs, slot0, trans, j0, jm, events);
     B.begin(LK_GEMM_NT);
     for (auto& p : probs) {
       if (jm >= p.n) continue;
@@ -197,7 +209,7 @@ static void plan_trsm_cols(PlanBuilder& B, Plan& P, const std::vector<TrsmProb>&
                p.arenaX, p.xoff + (int64_t)jm * p.ldx, p.ldx, p.M, c1 - jm, jm - j0, false, -1.0, 1.0);
     }
     B.end();
-    plan_trsm_cols(B, P, probs, slot0, trans, jm, j1);
+    plan_trsm_cols(B, P, probs, slot0, trans, jm, j1, events);
   } else {
     plan_trsm_cols(B, P, probs, slot0, trans, jm, j1);
     B.begin(LK_GEMM_NN);
@@ -294,6 +306,18 @@ void plan_trtri(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int 
   TrtriProb p{arenaL, loff, ldl, arenaW, woff, toff, ldw, n};
   p.arenaT = arenaT;
   plan_trtri_batch(B, P, std::vector<TrtriProb>{p});
+}
+void plan_potrf_events(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0) {
+  FactorProb fp{arena, off, ld, n, n, col0};
+  fp.slot0 = 0;  // kept: slot j holds the inverse of diagonal block j until the next factorisation with this slot set
+  std::vector<FactorProb> v{fp};
+  if (n > 0) plan_factor_cols(B, P, v, 0, ((n + NB - 1) / NB) * NB, true);
+}
+void plan_trsm_rlt_events(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
+                          int n, int ldx) {
+  std::vector<TrsmProb> v{{arenaL, loff, ldl, arenaX, xoff, ldx, M, n}};
+  std::vector<int64_t> slot0{0};
+  if (n > 0) plan_trsm_cols(B, P, v, slot0, true, 0, ((n + NB - 1) / NB) * NB, true);
 }
 void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0) {
   std::vector<FactorProb> v{{arena, off, ld, n, n, col0}};

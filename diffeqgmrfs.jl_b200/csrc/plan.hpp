@@ -31,6 +31,7 @@ class PlanBuilder {
     cur.bytes = 0;
     cur.smem = 0;
     cur.cfg = 0;
+    cur.wait_ev = cur.rec_ev = -1;
     flops0 = P.flops;
   }
   void add(Task t, int ctas) {
@@ -41,6 +42,9 @@ class PlanBuilder {
     cur.grid += ctas;
   }
   void set_smem(int bytes) { cur.smem = bytes; }
+  void set_wait(int ev) { cur.wait_ev = (int16_t)ev; }
+  void set_record(int ev) { cur.rec_ev = (int16_t)ev; }
+  int open_tasks() const { return cur.ntasks; }
   void set_cfg(int cfg) { cur.cfg = cfg; }
   void add_bytes(double b) { cur.bytes += b; }
   void end() {
@@ -104,6 +108,14 @@ void plan_potrf(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, 
 //  n x n scratch (ldw) in arena arenaT
 void plan_trtri(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaW, int64_t woff, int ldw, int arenaT,
                 int64_t toff, int n);
+//  the same with per-panel events for look-ahead (column block j = columns [64 j, 64 j + 64)): the inverses of the
+//  diagonal blocks are kept in inverse-block slots 0, 1, ... (slot j = block j); every leaf of plan_potrf_events records
+//  event j once column block j of L is final, every leaf of plan_trsm_rlt_events waits for event j before it reads
+//  block row j of L and slot j (it inverts nothing itself) and records event j (of a second event array) once column
+//  block j of X is final
+void plan_potrf_events(PlanBuilder& B, Plan& P, int arena, int64_t off, int n, int ld, int col0);
+void plan_trsm_rlt_events(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
+                          int n, int ldx);
 //  X (M x n at xoff, ldx) <- X L^{-T}, L n x n lower at loff (ldl); left-looking blocked
 void plan_trsm_rlt(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaX, int64_t xoff, int M,
                    int n, int ldx);

@@ -69,6 +69,9 @@ struct Launch {
   double bytes;  // algorithmic bytes of this launch (0 where not accounted)
   int32_t smem;  // dynamic shared memory of the launch (fused small-front kernels)
   int32_t cfg;   // GEMM launches: tile configuration (GCFG_*), chosen by PlanBuilder::end()
+  // look-ahead schedules (block-tridiagonal factor): before the launch its stream waits for event `wait_ev`, after it
+  // the stream records event `rec_ev` (indices into the caller's event array; -1 = none)
+  int16_t wait_ev = -1, rec_ev = -1;
 };
 
 // Profile slots for kernels that are not plan launches.

@@ -878,9 +878,17 @@ def tridiagonal_cholesky_ssm(D_first, D_mid, D_last, B_sub, N_blocks, ctx=None) 
     """Block-tridiagonal factor of a constant-mesh implicit-Euler state-space prior given by its four distinct blocks
     (gmrfb_btd_factor_ssm; ingredients of src/spdes/shallow_water.jl:198-228)."""
     ctx = ctx or default_context()
-    blocks = [np.asfortranarray(M, dtype=np.float64) if M is not None else None for M in (D_first, D_mid, D_last, B_sub)]
-    b = blocks[0].shape[0]
-    ptrs = [M.ctypes.data_as(B._F64P) if M is not None else None for M in blocks]
+    if hasattr(D_first, "data_ptr"):
+        # device-resident blocks: CUDA float64 tensors of shape (b, b), element [j, i] = entry (i, j) (column-major)
+        blocks = [D_first, D_mid, D_last, B_sub]
+        for M in blocks:
+            assert M is None or (M.is_cuda and M.is_contiguous() and str(M.dtype) == "torch.float64")
+        b = blocks[0].shape[0]
+        ptrs = [C.cast(C.c_void_p(M.data_ptr()), B._F64P) if M is not None else None for M in blocks]
+    else:
+        blocks = [np.asfortranarray(M, dtype=np.float64) if M is not None else None for M in (D_first, D_mid, D_last, B_sub)]
+        b = blocks[0].shape[0]
+        ptrs = [M.ctypes.data_as(B._F64P) if M is not None else None for M in blocks]
     h = C.c_void_p()
     st = B.lib().gmrfb_btd_factor_ssm(ctx.h, b, int(N_blocks), *ptrs, C.byref(h))
     if st != B.OK and h.value:
