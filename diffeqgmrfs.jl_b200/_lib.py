@@ -103,6 +103,12 @@ SIGNATURES = {
     "gmrfb_postprec_compute": (C.c_int32, [_P, C.c_double, _F64P, C.POINTER(_P)]),
     "gmrfb_metrics": (C.c_int32, [_P, _P, _F64P, _F64P, C.c_int64, _F64P]),
     "gmrfb_postprec_result": (C.c_int32, [_P, C.POINTER(_P)]),
+    "gmrfb_fem_create": (C.c_int32, [_P, C.c_int64, _F64P, C.c_int64, _I64P, C.c_int32, C.POINTER(_P)]),
+    "gmrfb_fem_destroy": (C.c_int32, [_P]),
+    "gmrfb_fem_get_mass": (C.c_int32, [_P, _F64P]),
+    "gmrfb_fem_set_coeff_grid": (C.c_int32, [_P, C.c_int64, _F64P, C.c_int64, _F64P]),
+    "gmrfb_fem_assemble": (C.c_int32, [_P, _P, _P, C.POINTER(_P)]),
+    "gmrfb_fem_matern_precision": (C.c_int32, [_P, C.c_double, C.c_double, _P, C.c_double, C.POINTER(_P)]),
     "gmrfb_gn_create": (C.c_int32, [_P, _P, C.c_int64, _I64P, _I64P, _F64P, _F64P, _F64P, _F64P, C.c_int32, C.c_double, C.c_double,
                                     _F64P, _F64P, _I64P, C.POINTER(AnalyzeOpts), C.POINTER(_P)]),
     "gmrfb_gn_optimize": (C.c_int32, [_P, _F64P, C.c_int32, C.c_double, C.POINTER(C.c_int32), _F64P]),

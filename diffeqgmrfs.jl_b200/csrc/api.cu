@@ -145,6 +145,7 @@ static const char* prof_name(int kind) {
     case PK_MEMSET: return "memset(front arena)";
     case PK_PERM: return "k_perm_gather/scatter";
     case PK_PERM_MR: return "k_mr_perm_in/out";
+    case PK_FEM: return "k_fem_assemble";
     case LK_MR_FWD_SMALL: return "k_mr_fwd_small";
     case LK_MR_BWD_SMALL: return "k_mr_bwd_small";
     case LK_MR_ASSEMBLE: return "k_mr_assemble";

@@ -63,3 +63,9 @@ struct gmrfb_spm {
   gmrfb::DevBuf<double> d_val, d_tval;
   bool owned_by_plan = false;
 };
+
+namespace gmrfb {
+// fill `M` (host pattern copy + device CSC / row-wise arrays) from a base-`base` CSC pattern; nzval may be NULL (spm.cu)
+gmrfb_status spm_build(gmrfb_ctx* ctx, gmrfb_spm* M, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                       const double* nzval, int base);
+}  // namespace gmrfb

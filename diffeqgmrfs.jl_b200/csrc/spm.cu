@@ -20,7 +20,7 @@ struct gmrfb_postprec {
   int64_t nprod = 0;
 };
 
-static gmrfb_status spm_build(gmrfb_ctx* ctx, gmrfb_spm* M, int64_t m, int64_t n, const int64_t* colptr,
+gmrfb_status gmrfb::spm_build(gmrfb_ctx* ctx, gmrfb_spm* M, int64_t m, int64_t n, const int64_t* colptr,
                               const int64_t* rowval, const double* nzval, int base) {
   M->ctx = ctx;
   M->m = m;
@@ -269,8 +269,8 @@ extern "C" gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps
   if (!plan) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_postprec_compute: NULL plan");
   gmrfb_ctx* ctx = plan->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
-  if (qeps_diag)
-    GMRFB_CU(ctx, cudaMemcpyAsync(plan->d_w.p, qeps_diag, plan->A->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (qeps_diag)  // host or device pointer (unified addressing)
+    GMRFB_CU(ctx, cudaMemcpyAsync(plan->d_w.p, qeps_diag, plan->A->m * sizeof(double), cudaMemcpyDefault, ctx->stream));
   GMRFB_CU(ctx, launch_postprec(plan->out.nnz, plan->d_qsrc.p, plan->Q->d_val.p, plan->d_pptr.p, plan->d_prow.p,
                                 plan->d_pa.p, plan->d_pb.p, plan->A->d_val.p, qeps_diag ? plan->d_w.p : nullptr,
                                 qeps_scalar, plan->out.d_val.p, ctx->stream));

@@ -86,6 +86,7 @@ enum : int32_t {
   PK_FWD_SMALL = 27,
   PK_BWD_SMALL = 28,
   PK_PERM_MR = 29,
+  PK_FEM = 30,
   PK_MAX = 40
 };
 

@@ -169,6 +169,76 @@ class PosteriorPrecision:
         return SparseMatrix(None, ctx=self.ctx, _handle=out, _owner=self)
 
 
+class FEMP1:
+    """P1 finite-element assembly on the device (gmrfb_fem): the Darcy stiffness of a new coefficient field
+    (``assemble_darcy_diff_matrix``, src/problems/darcy.jl:5-63, with the nearest-index coefficient lookup of
+    src/datasets/darcy.jl:30-34) and the Matern prior ``ratio * K' Mt^-1 K`` (src/spdes/shallow_water.jl:177-194), on a
+    pattern analysed once per mesh.  ``nodes``: n x 2, ``tris``: T x 3 (0-based)."""
+
+    def __init__(self, nodes, tris, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self._nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        tris, tp = B.i64(np.ascontiguousarray(tris).reshape(-1))
+        self.n = self._nodes.shape[0]
+        h = C.c_void_p()
+        B.check(B.lib().gmrfb_fem_create(self.ctx.h, self.n, self._nodes.ctypes.data_as(B._F64P), tris.size // 3, tp, 0,
+                                         C.byref(h)), self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_fem_destroy, h)
+        self._presc_keep = None
+
+    @property
+    def mass(self):
+        """Lumped mass vector = load vector of f = 1."""
+        out = np.empty(self.n)
+        B.check(B.lib().gmrfb_fem_get_mass(self.h, out.ctypes.data_as(B._F64P)), self.ctx.h)
+        return out
+
+    def set_coeff_grid(self, x_coords, y_coords):
+        x, xp = B.f64(x_coords)
+        y, yp = B.f64(y_coords)
+        B.check(B.lib().gmrfb_fem_set_coeff_grid(self.h, x.size, xp, y.size, yp), self.ctx.h)
+        self._grid = (x.size, y.size)
+
+    def _presc(self, prescribed):
+        if prescribed is None:
+            return None
+        self._presc_keep = np.ascontiguousarray(np.asarray(prescribed) != 0, dtype=np.uint8)
+        assert self._presc_keep.size == self.n
+        return C.c_void_p(self._presc_keep.ctypes.data)
+
+    def assemble(self, coeff_grid=None, prescribed=None) -> SparseMatrix:
+        """Stiffness matrix of the coefficient grid ``coeff_grid[iy, ix]`` (NumPy, shape (gy, gx): element (iy, ix) is
+        ``coeff_mat[ix, iy]`` of the reference's column-major array) or a CUDA float64 tensor of the same layout; rows
+        of ``prescribed`` dofs become identity rows.  The returned device matrix is owned by this object (fixed
+        pattern, values of the last call)."""
+        cp = None
+        if coeff_grid is not None:
+            if hasattr(coeff_grid, "data_ptr"):
+                assert coeff_grid.is_cuda and coeff_grid.is_contiguous() and str(coeff_grid.dtype) == "torch.float64"
+                assert tuple(coeff_grid.shape) == (self._grid[1], self._grid[0])
+                cp = C.c_void_p(coeff_grid.data_ptr())
+                self._coeff_keep = coeff_grid
+            else:
+                self._coeff_keep = np.ascontiguousarray(coeff_grid, dtype=np.float64)
+                assert self._coeff_keep.shape == (self._grid[1], self._grid[0])
+                cp = C.c_void_p(self._coeff_keep.ctypes.data)
+        out = C.c_void_p()
+        B.check(B.lib().gmrfb_fem_assemble(self.h, cp, self._presc(prescribed), C.byref(out)), self.ctx.h)
+        M = SparseMatrix(None, ctx=self.ctx, _handle=out, _owner=self)
+        M.shape = (self.n, self.n)
+        return M
+
+    def matern_precision(self, kappa, ratio, prescribed=None, prescribed_mass=1e-2) -> SparseMatrix:
+        """``ratio * K' Mt^-1 K`` with ``K = kappa^2 Mt + G`` (device matrix owned by this object)."""
+        out = C.c_void_p()
+        B.check(B.lib().gmrfb_fem_matern_precision(self.h, float(kappa), float(ratio), self._presc(prescribed),
+                                                   float(prescribed_mass), C.byref(out)), self.ctx.h)
+        M = SparseMatrix(None, ctx=self.ctx, _handle=out, _owner=self)
+        M.shape = (self.n, self.n)
+        return M
+
+
 # ------------------------------------------------------------------------------------ symbolic + numeric --
 class Symbolic:
     """Symbolic analysis of one sparsity pattern (gmrfb_sym).  ``perm`` is 0-based new->old (Julia's
@@ -555,13 +625,22 @@ class _ConditioningWorkspace:
     new coefficients: scripts/darcy/solve_darcy_gmrf-fem.jl:210) then only uploads A's values per problem."""
 
     def __init__(self, x, A, ctx):
-        self.A_indptr, self.A_indices, self.shape = A.indptr, A.indices, A.shape
         self.Qd = SparseMatrix(x.precision, ctx=ctx)
-        self.Ad = SparseMatrix(A, ctx=ctx)
+        if isinstance(A, SparseMatrix):  # assembled on the device (FEMP1.assemble): no upload, now or later
+            self.Ad, self.dev_handle = A, A.h.value
+            self.shape = tuple(A.dims()[:2])
+            self.A_indptr = self.A_indices = None
+        else:
+            self.A_indptr, self.A_indices, self.shape = A.indptr, A.indices, A.shape
+            self.Ad, self.dev_handle = SparseMatrix(A, ctx=ctx), None
         self.plan = PosteriorPrecision(self.Qd, self.Ad)
         self.pattern = None  # (indptr, indices) of the posterior precision, fetched with the first result
 
     def matches(self, A):
+        if isinstance(A, SparseMatrix):
+            return self.dev_handle is not None and A.h.value == self.dev_handle
+        if self.dev_handle is not None:
+            return False
         return A.shape == self.shape and A.indptr.size == self.A_indptr.size and A.indices.size == self.A_indices.size \
             and np.array_equal(A.indptr, self.A_indptr) and np.array_equal(A.indices, self.A_indices)
 
@@ -574,12 +653,14 @@ def condition_on_observations(x: GMRF, A, Q_eps, y, solver_blueprint=None) -> GM
     ``precision_map`` returns is downloaded once per call."""
     bp = solver_blueprint or x.solver_ref.value.blueprint
     ctx = x.solver_ref.value.precision_chol.ctx
-    A = _csc(A)
+    on_device = isinstance(A, SparseMatrix)  # e.g. the stiffness matrix straight from FEMP1.assemble
+    if not on_device:
+        A = _csc(A)
     mu = mean(x)
     ws = x._cond_ws
     if ws is None or not ws.matches(A):
         ws = x._cond_ws = _ConditioningWorkspace(x, A, ctx)
-    else:
+    elif not on_device:
         ws.Ad.set_values(A.data)
     Apost = ws.plan.compute(Q_eps)
     if ws.pattern is None:
@@ -591,7 +672,7 @@ def condition_on_observations(x: GMRF, A, Q_eps, y, solver_blueprint=None) -> GM
     Qpost = sp.csc_matrix((vals, ws.pattern[1], ws.pattern[0]), shape=x.precision.shape)
     Qpost.has_sorted_indices = True
     Qpost.has_canonical_format = True
-    w = np.broadcast_to(np.asarray(Q_eps, dtype=np.float64), (A.shape[0],))
+    w = np.broadcast_to(np.asarray(Q_eps, dtype=np.float64), (ws.shape[0],))
     resid = np.asarray(y, dtype=np.float64) - ws.Ad.matvec(mu)
     info = ws.Ad.matvec(w * resid, trans=True)
     return GMRF(mu, Qpost, bp, information=info, _values_dev=Apost.values_dev())

@@ -266,6 +266,37 @@ const double* gmrfb_spm_values_dev(const gmrfb_spm* A);
 gmrfb_status gmrfb_metrics(gmrfb_ctx* ctx, const gmrfb_spm* E, const double* x, const double* truth, int64_t ntruth,
                            double* out3);
 
+/* ------------------------------------------- P1 finite-element assembly ------ */
+/* The two matrices the reference rebuilds inside its hot loops, assembled on the device on a fixed pattern:
+ *   assemble_darcy_diff_matrix(disc, x_coords, y_coords, coeff_mat)   src/problems/darcy.jl:5-63  -> gmrfb_fem_assemble
+ *       (called per problem of the dataset loop through form_observations, scripts/darcy/solve_darcy_gmrf-fem.jl:104-137,178;
+ *        the coefficient of an element is coeff_mat[get_xy_idcs(quadrature point)], src/datasets/darcy.jl:30-34)
+ *   Q_matern = ratio * K_matern' * Mt^-1 * K_matern,  K_matern = kappa^2 Mt + G    src/spdes/shallow_water.jl:177-194
+ *                                                                               -> gmrfb_fem_matern_precision
+ * for linear (P1) triangles with the one-point rule (exact for piecewise-constant coefficients and P1 gradients).
+ *   nodes : nnodes x 2 coordinates, node-major;  tris : ntri x 3 vertex indices (`base`-based), element-major.
+ * The mesh is analysed once (pattern, element -> nonzero gather lists); every later call is a few kernels. */
+typedef struct gmrfb_fem gmrfb_fem;
+gmrfb_status gmrfb_fem_create(gmrfb_ctx* ctx, int64_t nnodes, const double* nodes, int64_t ntri, const int64_t* tris,
+                              int32_t base, gmrfb_fem** out);
+gmrfb_status gmrfb_fem_destroy(gmrfb_fem* fem);
+/* lumped mass vector (integral of every hat function), nnodes doubles: the load vector of f = 1 (`fe[i] += beta * du * dOmega`
+ * with beta = 1, src/problems/darcy.jl:46) */
+gmrfb_status gmrfb_fem_get_mass(gmrfb_fem* fem, double* mass_out);
+/* coefficient grid axes: gx values x_coords, gy values y_coords; element -> grid cell by nearest index per axis */
+gmrfb_status gmrfb_fem_set_coeff_grid(gmrfb_fem* fem, int64_t gx, const double* x_coords, int64_t gy,
+                                      const double* y_coords);
+/* G = sum_T coeff(T) K_T.  coeff_grid: gx*gy doubles, entry ix + iy*gx = coeff_mat[ix, iy] (host or device memory), or
+ * NULL for a unit coefficient; prescribed: nnodes bytes (non-zero = Dirichlet dof: its row becomes an identity row) or
+ * NULL.  *G_out is a matrix owned by the handle (fixed pattern; values of the last call): hand it to
+ * gmrfb_postprec_create once, then every gmrfb_fem_assemble + gmrfb_postprec_compute pair re-uses the plan. */
+gmrfb_status gmrfb_fem_assemble(gmrfb_fem* fem, const double* coeff_grid, const uint8_t* prescribed,
+                                const gmrfb_spm** G_out);
+/* Q = ratio * K' Mt^-1 K with K = kappa^2 Mt + G (unit coefficient) and lumped Mt; for prescribed dofs (optional mask)
+ * Mt_ii = prescribed_mass and G_ii = 1 as in src/spdes/shallow_water.jl:178-181.  *Q_out is owned by the handle. */
+gmrfb_status gmrfb_fem_matern_precision(gmrfb_fem* fem, double kappa, double ratio, const uint8_t* prescribed,
+                                        double prescribed_mass, const gmrfb_spm** Q_out);
+
 /* ------------------------------------------- Gauss-Newton on the device ------ */
 /* The explicit loop of scripts/solve_burger.jl:143-180 (packaged as GaussNewtonOptimizer / optimize in
  * scripts/burgers/solve_burgers_gmrf-fem.jl:172-182) for a bilinear collocation residual
