@@ -77,6 +77,7 @@ SIGNATURES = {
     "gmrfb_sym_get_info": (C.c_int32, [_P, C.POINTER(SymInfo)]),
     "gmrfb_sym_get": (C.c_int32, [_P, _I64P, _I64P, _I64P, _I64P, _I64P]),
     "gmrfb_sym_get_super_rows": (C.c_int32, [_P, C.c_int64, _I64P, C.c_int64, _I64P]),
+    "gmrfb_sym_get_maps": (C.c_int32, [_P, _I64P, _I64P, _I64P, _I64P]),
     "gmrfb_fac_create": (C.c_int32, [_P, C.POINTER(_P)]),
     "gmrfb_fac_destroy": (C.c_int32, [_P]),
     "gmrfb_factorize": (C.c_int32, [_P, _F64P]),

@@ -220,7 +220,15 @@ extern "C" gmrfb_status gmrfb_analyze(gmrfb_ctx* ctx, int64_t n, const int64_t* 
   }
   std::unique_ptr<gmrfb_sym> s(new gmrfb_sym());
   s->ctx = ctx;
-  std::string err = analyze_pattern(n, colptr, rowval, perm, o, s->S);
+  // with a context the data-parallel phases of the analysis run on its device (symbolic_gpu.cu); GMRFB_SYM_HOST=1 forces
+  // the host loops (the two paths are bit-identical, tests/test_symbolic.py)
+  std::unique_ptr<SymDevice> dev;
+  const char* force_host = getenv("GMRFB_SYM_HOST");
+  if (ctx && !(force_host && force_host[0] == '1')) {
+    GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+    dev.reset(new SymDevice((void*)ctx->stream));
+  }
+  std::string err = analyze_pattern(n, colptr, rowval, perm, o, s->S, dev.get());
   if (!err.empty()) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_analyze: " + err);
   *out = s.release();
   return GMRFB_OK;
@@ -273,6 +281,18 @@ extern "C" gmrfb_status gmrfb_sym_get_super_rows(const gmrfb_sym* sym, int64_t s
   if (nrows) *nrows = cnt;
   if (rows)
     for (int64_t k = 0; k < std::min(cnt, cap); k++) rows[k] = S.rows[S.rptr[s] + k] + S.base;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_sym_get_maps(const gmrfb_sym* sym, int64_t* amap, int64_t* relmap, int64_t* nnz_out,
+                                           int64_t* total_rows_out) {
+  if (!sym) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get_maps: sym is NULL");
+  const Symbolic& S = sym->S;
+  if (nnz_out) *nnz_out = (int64_t)S.amap.size();
+  if (total_rows_out) *total_rows_out = (int64_t)S.relmap.size();
+  if (amap) std::copy(S.amap.begin(), S.amap.end(), amap);
+  if (relmap)
+    for (size_t k = 0; k < S.relmap.size(); k++) relmap[k] = S.relmap[k];
   return GMRFB_OK;
 }
 

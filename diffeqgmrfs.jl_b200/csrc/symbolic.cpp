@@ -11,6 +11,8 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -981,8 +983,21 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
   }
 }
 
+// GMRFB_SYM_TIMING=1: wall time of every phase of the analysis on stderr (tuning aid)
+struct PhaseTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTimer() : on(std::getenv("GMRFB_SYM_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[gmrfb analyze] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* rowval, const int64_t* perm_in,
-                            const AnalyzeOptions& opt, Symbolic& S) {
+                            const AnalyzeOptions& opt, Symbolic& S, SymDevice* dev) {
   if (n64 < 0 || n64 > (int64_t)2000000000) return "n out of range";
   if (!colptr || (n64 > 0 && !rowval)) return "null pattern";
   if (opt.base != 0 && opt.base != 1) return "base must be 0 or 1";
@@ -998,8 +1013,20 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
 
   std::vector<int64_t> xadj;
   std::vector<int32_t> adj;
-  std::string err = build_adjacency(n, colptr, rowval, base, xadj, adj);
-  if (!err.empty()) return err;
+  PhaseTimer pt;
+  std::string err;
+  bool on_dev = false;
+  if (dev && opt.storage == 0) {
+    // structurally symmetric input with both triangles stored: validated and turned into the adjacency on the GPU
+    err = dev->adjacency(n, colptr, rowval, base, xadj, adj, on_dev);
+    if (!err.empty()) return err;
+  }
+  if (!on_dev) {
+    dev = nullptr;  // LOWER / UPPER storage or an unsymmetric pattern: the whole analysis takes the host path
+    err = build_adjacency(n, colptr, rowval, base, xadj, adj);
+    if (!err.empty()) return err;
+  }
+  pt.lap(on_dev ? "adjacency (GPU)" : "adjacency");
 
   // ---- ordering ----
   S.perm_user.resize(n);
@@ -1026,20 +1053,27 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
     return "unknown ordering kind";
   }
 
+  pt.lap("ordering");
   // ---- permuted adjacency (perm_user ordering) ----
   std::vector<int32_t> ipu(n);
   for (int32_t k = 0; k < n; k++) ipu[S.perm_user[k]] = k;
   std::vector<int64_t> pxadj(n + 1, 0);
   std::vector<int32_t> padj(adj.size());
-  for (int32_t k = 0; k < n; k++) pxadj[k + 1] = pxadj[k] + (xadj[S.perm_user[k] + 1] - xadj[S.perm_user[k]]);
-  for (int32_t k = 0; k < n; k++) {
-    int32_t v = S.perm_user[k];
-    int64_t o = pxadj[k];
-    for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) padj[o++] = ipu[adj[p]];
-    std::sort(padj.begin() + pxadj[k], padj.begin() + pxadj[k + 1]);
+  if (dev) {
+    err = dev->permuted_adjacency(S.perm_user, ipu, pxadj, padj);
+    if (!err.empty()) return err;
+  } else {
+    for (int32_t k = 0; k < n; k++) pxadj[k + 1] = pxadj[k] + (xadj[S.perm_user[k] + 1] - xadj[S.perm_user[k]]);
+    for (int32_t k = 0; k < n; k++) {
+      int32_t v = S.perm_user[k];
+      int64_t o = pxadj[k];
+      for (int64_t p = xadj[v]; p < xadj[v + 1]; p++) padj[o++] = ipu[adj[p]];
+      std::sort(padj.begin() + pxadj[k], padj.begin() + pxadj[k + 1]);
+    }
   }
   S.nnz_lower_A = (int64_t)adj.size() / 2 + n;
 
+  pt.lap("permuted adjacency");
   // ---- etree, postorder, column counts in the perm_user ordering ----
   etree_lower(n, pxadj, padj, S.parent_user);
   postorder_tree(n, S.parent_user, S.post);
@@ -1051,6 +1085,7 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
     S.flops += (double)S.colcount_user[j] * (double)S.colcount_user[j];
   }
 
+  pt.lap("etree + postorder + colcounts");
   // ---- internal (postordered) numbering ----
   S.ipost.resize(n);
   S.perm.resize(n);
@@ -1070,7 +1105,10 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
   // internal adjacency (needed for the supernode row structures): neighbours above each column
   std::vector<int64_t> ixadj(n + 1, 0);
   std::vector<int32_t> iadj;  // for internal column k: sorted internal neighbours i > k
-  {
+  if (dev) {
+    err = dev->internal_adjacency(S.post, S.ipost, ixadj, iadj);
+    if (!err.empty()) return err;
+  } else {
     std::vector<int64_t> cnt(n + 1, 0);
     for (int32_t k = 0; k < n; k++) {
       int32_t ku = S.post[k];
@@ -1091,6 +1129,7 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
     }
   }
 
+  pt.lap("internal numbering/adjacency");
   // ---- fundamental supernodes ----
   std::vector<int32_t> nchild(n, 0);
   for (int32_t k = 0; k < n; k++)
@@ -1178,6 +1217,7 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
       if (S.sparent[s] >= 0) S.child_idx[fillp[S.sparent[s]]++] = s;
   }
 
+  pt.lap("supernodes");
   // ---- row structures (bottom-up union) ----
   S.rptr.assign(S.nsuper + 1, 0);
   S.rows.clear();
@@ -1218,6 +1258,7 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
         return "internal error: column counts disagree with the supernodal row structure";
     }
   }
+  pt.lap("row structures");
   // ---- relmap, layout, levels ----
   S.relmap.assign(S.rows.size(), -1);
   S.ld.resize(S.nsuper);
@@ -1236,15 +1277,16 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
     S.nnzL_stored += trapezoid(sc, d);
     int32_t p = S.sparent[s];
     if (p >= 0) {
-      // positions of s's below-rows inside the parent's (sorted) row list
+      // positions of s's below-rows inside the parent's (sorted) row list (with `dev`: k_relmap, below)
       int64_t q = S.rptr[p];
       const int64_t qe = S.rptr[p + 1];
-      for (int64_t k = S.rptr[s] + sc; k < S.rptr[s + 1]; k++) {
-        int32_t i = S.rows[k];
-        while (q < qe && S.rows[q] < i) q++;
-        if (q >= qe || S.rows[q] != i) return "internal error: child row missing from parent front";
-        S.relmap[k] = (int32_t)(q - S.rptr[p]);
-      }
+      if (!dev)
+        for (int64_t k = S.rptr[s] + sc; k < S.rptr[s + 1]; k++) {
+          int32_t i = S.rows[k];
+          while (q < qe && S.rows[q] < i) q++;
+          if (q >= qe || S.rows[q] != i) return "internal error: child row missing from parent front";
+          S.relmap[k] = (int32_t)(q - S.rptr[p]);
+        }
       S.level[p] = std::max(S.level[p], S.level[s] + 1);
     }
   }
@@ -1253,7 +1295,13 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
   S.levels.assign(nlev, Level());
   for (int32_t s = 0; s < S.nsuper; s++) S.levels[S.level[s]].snodes.push_back(s);
 
+  pt.lap("relmap + layout + levels");
   // ---- scatter map of the user's stored entries into the frontal arena ----
+  if (dev) {
+    err = dev->maps(S);  // relmap + amap on the GPU
+    pt.lap("relmap + amap (GPU)");
+    return err;
+  }
   S.amap.assign(S.nnzA, -1);
   for (int64_t c = 0; c < n; c++) {
     int32_t jc = S.iperm[c];
@@ -1284,6 +1332,7 @@ std::string analyze_pattern(int64_t n64, const int64_t* colptr, const int64_t* r
       S.amap[p] = S.foff[s] + (int64_t)(j - f) * S.ld[s] + lr;
     }
   }
+  pt.lap("amap");
   return "";
 }
 

@@ -71,9 +71,36 @@ struct Symbolic {
   int ncols(int32_t s) const { return sptr[s + 1] - sptr[s]; }
 };
 
-// Returns "" on success, else an error message.  colptr/rowval are `base`-based 64-bit CSC.
+// CUDA implementations of the data-parallel phases of the analysis (symbolic_gpu.cu): pattern validation + symmetric
+// adjacency, permuted / internal adjacency, relmap and amap.  Every method returns "" on success; results are
+// bit-identical to the host loops of analyze_pattern.
+class SymDevice {
+ public:
+  explicit SymDevice(void* cuda_stream);
+  ~SymDevice();
+  SymDevice(const SymDevice&) = delete;
+  SymDevice& operator=(const SymDevice&) = delete;
+  // handled = false: the pattern is malformed or not structurally symmetric (the host path deals with it)
+  std::string adjacency(int64_t n, const int64_t* colptr, const int64_t* rowval, int base, std::vector<int64_t>& xadj,
+                        std::vector<int32_t>& adj, bool& handled);
+  std::string permuted_adjacency(const std::vector<int32_t>& perm_user, const std::vector<int32_t>& ipu,
+                                 std::vector<int64_t>& pxadj, std::vector<int32_t>& padj);
+  std::string internal_adjacency(const std::vector<int32_t>& post, const std::vector<int32_t>& ipost,
+                                 std::vector<int64_t>& ixadj, std::vector<int32_t>& iadj);
+  std::string maps(Symbolic& S);  // S.relmap and S.amap from S.rows / S.sptr / S.foff / ...
+  struct Impl;
+  struct Perm;
+
+ private:
+  Impl* im = nullptr;
+  Perm* pm = nullptr;
+};
+
+// Returns "" on success, else an error message.  colptr/rowval are `base`-based 64-bit CSC.  With `dev` the
+// data-parallel phases run as CUDA kernels (the ordering, the elimination tree, the column counts, the supernode
+// partition and the bottom-up row structures are sequential graph algorithms and stay on the host).
 std::string analyze_pattern(int64_t n, const int64_t* colptr, const int64_t* rowval, const int64_t* perm,
-                            const AnalyzeOptions& opt, Symbolic& S);
+                            const AnalyzeOptions& opt, Symbolic& S, SymDevice* dev = nullptr);
 
 // Pieces exposed for tests.
 void etree_lower(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,

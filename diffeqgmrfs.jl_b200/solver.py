@@ -303,6 +303,15 @@ class Symbolic:
     super_ptr = property(lambda self: self._get()["super_ptr"])
     ipost = property(lambda self: self._get()["ipost"])
 
+    def maps(self):
+        """(amap, relmap) of the analysis (gmrfb_sym_get_maps; diagnostic: GPU vs host analysis, bit for bit)."""
+        na, nr = C.c_int64(), C.c_int64()
+        B.check(B.lib().gmrfb_sym_get_maps(self.h, None, None, C.byref(na), C.byref(nr)), None)
+        amap, relmap = np.empty(na.value, np.int64), np.empty(nr.value, np.int64)
+        B.check(B.lib().gmrfb_sym_get_maps(self.h, amap.ctypes.data_as(B._I64P), relmap.ctypes.data_as(B._I64P), None, None),
+                None)
+        return amap, relmap
+
     def super_rows(self, s):
         cnt = C.c_int64()
         B.check(B.lib().gmrfb_sym_get_super_rows(self.h, s, None, 0, C.byref(cnt)), None)

@@ -130,6 +130,34 @@ def heat_spacetime(nx: int, n_steps: int, dt: float = 1e-3, diffusivity: float =
     return dict(A=A, D=np.asfortranarray(D), B=np.asfortranarray(Bsub), b=b, N=N, nodes=nodes)
 
 
+def heat_spacetime_sparse(nx: int, n_steps: int, dt: float = 1e-3, diffusivity: float = 1.0, tau: float = 1.0,
+                          corr_range: float = 0.2, seed: int = 0):
+    """Config 5 without dense blocks: the same implicit-Euler heat space-time precision as `heat_spacetime`
+    (src/spdes/shallow_water.jl:198-230), assembled only as a sparse matrix (time-major unknowns, block t = rows
+    [t b, (t+1) b)), with 3-D coordinates (x, y, t h) for nested dissection in space-time (h = mesh width, so that a
+    time step is as long as a mesh edge).  Returns dict(A, coords, b, N, nodes)."""
+    nodes, tris = structured_mesh(nx, nx, seed=seed)
+    m, Kst = p1_mass_stiffness(nodes, tris)
+    M = sp.diags(m).tocsc()
+    G = (M + dt * diffusivity * Kst).tocsc()
+    Q0 = matern_precision(nodes, tris, corr_range)
+    binv = 1.0 / (dt * tau**2)
+    GtG = (binv * (G.T @ G)).tocsc()
+    MM = (binv * (M.T @ M)).tocsc()
+    off = (-binv * (G.T @ M)).tocsc()  # block (t+1, t)
+    b, N = nodes.shape[0], n_steps
+    T = sp.identity(N, format="csc")
+    first = sp.csc_matrix(([1.0], ([0], [0])), shape=(N, N))
+    last = sp.csc_matrix(([1.0], ([N - 1], [N - 1])), shape=(N, N))
+    sub = sp.csc_matrix((np.ones(N - 1), (np.arange(1, N), np.arange(N - 1))), shape=(N, N))
+    A = (sp.kron(first, Q0) + sp.kron(T - first, GtG) + sp.kron(T - last, MM) + sp.kron(sub, off)
+         + sp.kron(sub.T, off.T)).tocsc()
+    A.sort_indices()
+    h = 1.0 / (nx - 1)
+    coords = np.column_stack([np.tile(nodes[:, 0], N), np.tile(nodes[:, 1], N), np.repeat(np.arange(N) * h, b)])
+    return dict(A=A, coords=coords, b=b, N=N, nodes=nodes)
+
+
 def random_btd(b: int, N: int, seed: int = 0, coupling: float = 0.4):
     """Generic SPD block-tridiagonal test matrix with dense blocks (diagonally dominant by construction)."""
     rng = np.random.default_rng(seed)

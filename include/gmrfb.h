@@ -155,6 +155,13 @@ gmrfb_status gmrfb_sym_get(const gmrfb_sym* sym, int64_t* perm, int64_t* parent,
 gmrfb_status gmrfb_sym_get_super_rows(const gmrfb_sym* sym, int64_t s, int64_t* rows, int64_t cap,
                                       int64_t* nrows);
 
+/* Index maps of the analysis (diagnostic / test entry point: the GPU and the host implementation of the analysis are
+ * compared bit for bit through it).  amap[nnz]: arena slot of every stored matrix entry (-1: mirrored triangle);
+ * relmap[total_rows]: for every below-row of every front its position in the parent's front (-1 for a front's own
+ * columns and for roots); total_rows = sum of the front orders.  Call with NULL pointers to get the sizes. */
+gmrfb_status gmrfb_sym_get_maps(const gmrfb_sym* sym, int64_t* amap, int64_t* relmap, int64_t* nnz_out,
+                                int64_t* total_rows_out);
+
 /* ------------------------------------------------- numeric factorisation ---- */
 /* Replaces the numeric half of `cholesky(A; perm, check=false)` (scripts/solve_burger.jl:147) and the
  * factorisation inside condition_on_observations / GaussNewtonOptimizer for CholeskySolverBlueprint,

@@ -175,3 +175,19 @@ def test_btd_b2048_six_blocks(pkg, orc, ctx, W):
     np.testing.assert_allclose(F.selinv_diag(), orc.btd_selinv_diag(Fo), rtol=TOL_VAR)
     with pytest.raises(ValueError):
         pkg.ldiv(F, np.zeros(b * N + 3))
+
+
+def test_spacetime_sparse_path_matches_block_tridiagonal(pkg, ctx, W):
+    """Config 5's precision (implicit-Euler heat space-time GMRF, src/spdes/shallow_water.jl:198-230) through both
+    paths: the sparse supernodal factor under nested dissection in space-time (3-D coordinates) and the dense
+    block-tridiagonal factor of src/tridiagonal_cholesky.jl:65-82 — same means, same marginal variances, same logdet."""
+    st = W.heat_spacetime_sparse(24, 6)
+    A, n = st["A"], st["A"].shape[0]
+    F = pkg.tridiagonal_cholesky(A, st["N"], ctx=ctx)
+    fac = pkg.cholesky(A, coords=st["coords"], ctx=ctx)
+    rhs = np.random.default_rng(0).standard_normal((n, 3))
+    xb, xs = pkg.ldiv(F, rhs), fac.solve(rhs)
+    assert rel(xs, xb) < 1e-9
+    assert np.linalg.norm(A @ xs - rhs) < 1e-10 * np.linalg.norm(rhs)
+    np.testing.assert_allclose(fac.var_selinv(), F.selinv_diag(), rtol=1e-8)
+    assert abs(fac.logdet() - F.logdet()) < 1e-10 * abs(F.logdet())
