@@ -93,6 +93,7 @@ SIGNATURES = {
     "gmrfb_var_selinv": (C.c_int32, [_P, _F64P]),
     "gmrfb_var_selinv_dev": (C.c_int32, [_P, _P]),
     "gmrfb_var_rbmc": (C.c_int32, [_P, _P, _F64P, C.c_int64, C.c_int64, _F64P]),
+    "gmrfb_var_rbmc_dev": (C.c_int32, [_P, _P, _F64P, C.c_int64, C.c_int64, _P]),
     "gmrfb_selinv_entries": (C.c_int32, [_P, C.c_int32, C.c_int64, _I64P, _I64P, _F64P]),
     "gmrfb_spm_create": (C.c_int32, [_P, C.c_int64, C.c_int64, _I64P, _I64P, _F64P, C.c_int32, C.POINTER(_P)]),
     "gmrfb_spm_set_values": (C.c_int32, [_P, _F64P]),

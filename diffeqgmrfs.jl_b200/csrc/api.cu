@@ -1119,8 +1119,20 @@ extern "C" gmrfb_status gmrfb_selinv_entries(gmrfb_fac* fac, int32_t base, int64
   return GMRFB_OK;
 }
 
+static gmrfb_status var_rbmc_core(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz, int64_t nsamp,
+                                  double* var_out, bool out_on_device);
+
 extern "C" gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
                                        int64_t nsamp, double* var_out) {
+  return var_rbmc_core(fac, Q, Z, ldz, nsamp, var_out, false);
+}
+extern "C" gmrfb_status gmrfb_var_rbmc_dev(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
+                                           int64_t nsamp, double* d_var_out) {
+  return var_rbmc_core(fac, Q, Z, ldz, nsamp, d_var_out, true);
+}
+
+static gmrfb_status var_rbmc_core(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz, int64_t nsamp,
+                                  double* var_out, bool out_on_device) {
   if (!fac || !Q || !Z || !var_out) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_var_rbmc: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_var_rbmc: no successful factorisation");
   gmrfb_ctx* ctx = fac->ctx;
@@ -1170,9 +1182,12 @@ extern "C" gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const
     ctx->launches++;
   }
   // Q is symmetric: its CSC columns double as rows
-  GMRFB_CU(ctx, launch_rbmc(n, Q->d_colptr.p, Q->d_rowidx.p, Q->d_val.p, Xs.p, ldk, (int)nsamp, dvar.p, ctx->stream));
+  GMRFB_CU(ctx, launch_rbmc(n, Q->d_colptr.p, Q->d_rowidx.p, Q->d_val.p, Xs.p, ldk, (int)nsamp,
+                            out_on_device ? var_out : dvar.p, ctx->stream));
   ctx->launches++;
-  GMRFB_CU(ctx, cudaMemcpyAsync(var_out, dvar.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!out_on_device) {
+    GMRFB_CU(ctx, cudaMemcpyAsync(var_out, dvar.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return GMRFB_OK;
 }

@@ -620,8 +620,8 @@ static std::string build_adjacency(int64_t n, const int64_t* colptr, const int64
 // are bounded by  d_i <- min(n - k, d_i + |L_p \ i|, |A_i \ i| + |L_p \ i| + sum_{e in E_i \ p} |L_e \ L_p|)
 // with the |L_e \ L_p| obtained in one pass by the timestamp trick, indistinguishable variables are merged into
 // supervariables (hash buckets), variables whose adjacency is covered by the new element are mass-eliminated and
-// elements that became subsets of it are absorbed (aggressive absorption).  No dense-row handling: GMRF precision
-// matrices have bounded row degree.  This is the reordering the reference gets from CHOLMOD's default `cholesky(A)`
+// elements that became subsets of it are absorbed (aggressive absorption).  Dense rows (degree above
+// max(16, 10 sqrt(n)), SuiteSparse's rule) are detected ONCE, removed and ordered last (amd_order below).  This is the reordering the reference gets from CHOLMOD's default `cholesky(A)`
 // call (no `perm`); ties are broken by this implementation's list order, not SuiteSparse's.
 namespace {
 
@@ -681,15 +681,23 @@ struct AmdWork {
 // Vertices nfree .. n-1 (if any) are a HALO: they take part in the quotient graph (so the degrees of the free vertices
 // next to them are right) but are never eliminated, merged or reported - the "halo-AMD" used to order the leaf
 // subdomains of a nested dissection, whose halo is the surrounding separators (eliminated later).
+static void amd_order_impl(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
+                           std::vector<int32_t>& perm, int32_t nfree, bool detect_dense);
+
 void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
                std::vector<int32_t>& perm, int32_t nfree) {
+  amd_order_impl(n, xadj, adj, perm, nfree, true);
+}
+
+static void amd_order_impl(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
+                           std::vector<int32_t>& perm, int32_t nfree, bool detect_dense) {
   if (nfree < 0 || nfree > n) nfree = n;
   perm.assign(nfree, 0);
   if (nfree == 0) return;
   // Dense rows (degree above max(16, 10 sqrt(n)), the SuiteSparse AMD rule) are taken out and ordered last: a vertex
   // adjacent to nearly everything is rescanned at every one of its neighbours' eliminations (quadratic time) and ends
   // up in the last front whatever the order.
-  {
+  if (detect_dense) {
     const double thresh = std::max(16.0, 10.0 * std::sqrt((double)n));
     std::vector<int32_t> dense;
     for (int32_t i = 0; i < nfree; i++)
@@ -714,7 +722,9 @@ void amd_order(int32_t n, const std::vector<int64_t>& xadj, const std::vector<in
         x2[k + 1] = (int64_t)a2.size();
       }
       std::vector<int32_t> p2;
-      amd_order(n2, x2, a2, p2, nfree2);  // no vertex of the reduced graph exceeds the threshold of the original n
+      // dense detection runs once, against the threshold of the original n: the reduced graph is ordered as it is (a
+      // recursive re-detection with the smaller n2 would peel further vertices level after level)
+      amd_order_impl(n2, x2, a2, p2, nfree2, false);
       std::stable_sort(dense.begin(), dense.end(), [&](int32_t a, int32_t b) {
         return (xadj[a + 1] - xadj[a]) < (xadj[b + 1] - xadj[b]);
       });

@@ -68,6 +68,7 @@ class TimeShardedCholesky:
             # entry (i, j) of block k (each block column-major) - the memory layout of the NumPy form below
             assert D_local.is_cuda and B_local.is_cuda and D_local.is_contiguous() and B_local.is_contiguous()
             assert D_local.dtype == torch.float64 and B_local.dtype == torch.float64
+            torch.cuda.current_stream(D_local.device).synchronize()  # the blocks may still be in the making on torch's stream
             self.nloc, self.b, _ = D_local.shape
             dp, bp = C.cast(C.c_void_p(D_local.data_ptr()), B._F64P), C.cast(C.c_void_p(B_local.data_ptr()), B._F64P)
         else:
@@ -90,12 +91,14 @@ class TimeShardedCholesky:
             return self._slab.iface()
         cnt = int(B.lib().gmrfb_btd_dist_iface_count(self.h))
         send = self.torch.empty(cnt, dtype=self.torch.float64, device=self.dev)
+        self._sync_torch()
         B.check(B.lib().gmrfb_btd_dist_get_iface(self.h, C.c_void_p(send.data_ptr())), self.ctx.h)
         return send
 
     def reduce(self, gathered):
         if self._slab is not None:
             return self._slab.reduce(gathered)
+        self._sync_torch()
         ptr = C.c_void_p(gathered.data_ptr()) if gathered is not None else None
         B.check(B.lib().gmrfb_btd_dist_reduce(self.h, ptr), self.ctx.h)
 
@@ -105,7 +108,10 @@ class TimeShardedCholesky:
         X = np.asfortranarray(np.asarray(X_local, dtype=np.float64).reshape(self.b * self.nloc, -1))
         self._nrhs = X.shape[1]
         cnt = int(B.lib().gmrfb_btd_dist_solve_count(self.h, self._nrhs))
-        send = self.torch.zeros(cnt, dtype=self.torch.float64, device=self.dev)
+        # torch.empty, not zeros: a fill kernel queued on torch's stream is NOT ordered against the library's own
+        # (non-blocking) stream and could land after the library has written the buffer; the library clears it itself
+        send = self.torch.empty(max(cnt, 1), dtype=self.torch.float64, device=self.dev)[:cnt]
+        self._sync_torch()
         B.check(B.lib().gmrfb_btd_dist_solve_begin(self.h, X.ctypes.data_as(B._F64P), X.shape[0], self._nrhs,
                                                    C.c_void_p(send.data_ptr())), self.ctx.h)
         return send
@@ -113,6 +119,7 @@ class TimeShardedCholesky:
     def solve_end(self, gathered):
         if self._slab is not None:
             return self._slab.solve_end(gathered)
+        self._sync_torch()
         n = self.b * self.nloc
         X = np.empty((n, self._nrhs), order="F")
         ptr = C.c_void_p(gathered.data_ptr()) if gathered is not None else None
@@ -120,6 +127,13 @@ class TimeShardedCholesky:
         return X
 
     # ---- collective wrappers ----
+    def _sync_torch(self):
+        """The library runs on its own non-blocking CUDA stream: work torch (or NCCL) has queued on ITS stream for a buffer
+        that is about to be handed to the library must have finished first.  (The other direction is covered by the C ABI:
+        every call returns with its outputs complete.)"""
+        if self._slab is None:
+            self.torch.cuda.current_stream(self.dev).synchronize()
+
     def _allgather(self, send):
         if self.world == 1:
             return send
@@ -127,6 +141,8 @@ class TimeShardedCholesky:
 
         out = self.torch.empty(self.world * send.numel(), dtype=send.dtype, device=send.device)
         dist.all_gather_into_tensor(out, send, group=self.group)
+        # the collective is ordered on torch's current stream only: wait for it before the library reads `out`
+        self._sync_torch()
         return out
 
     def solve(self, X_local):

@@ -72,6 +72,14 @@ def default_context() -> Context:
     return _default_ctx
 
 
+def _torch_ready(t):
+    """A CUDA tensor about to be handed to the library: the library runs on its own non-blocking stream, which is not
+    ordered against torch's, so whatever torch has queued to produce the tensor must have finished first."""
+    import torch
+
+    torch.cuda.current_stream(t.device).synchronize()
+
+
 def _csc(A):
     A = sp.csc_matrix(A)
     if not A.has_sorted_indices:
@@ -217,6 +225,7 @@ class FEMP1:
             if hasattr(coeff_grid, "data_ptr"):
                 assert coeff_grid.is_cuda and coeff_grid.is_contiguous() and str(coeff_grid.dtype) == "torch.float64"
                 assert tuple(coeff_grid.shape) == (self._grid[1], self._grid[0])
+                _torch_ready(coeff_grid)
                 cp = C.c_void_p(coeff_grid.data_ptr())
                 self._coeff_keep = coeff_grid
             else:
@@ -455,12 +464,21 @@ class CholeskyFactor:
         out = np.empty(self.sym.n)
         if hasattr(Z, "data_ptr"):
             assert Z.is_cuda and Z.is_contiguous() and Z.shape[1] == self.sym.n and str(Z.dtype) == "torch.float64"
+            _torch_ready(Z)
             zp, ns = C.cast(C.c_void_p(Z.data_ptr()), B._F64P), Z.shape[0]
         else:
             Zf = np.asfortranarray(np.asarray(Z, dtype=np.float64).reshape(self.sym.n, -1))
             zp, ns = Zf.ctypes.data_as(B._F64P), Zf.shape[1]
         B.check(B.lib().gmrfb_var_rbmc(self.h, Q.h, zp, self.sym.n, ns, out.ctypes.data_as(B._F64P)), self.ctx.h)
         return out
+
+    def var_rbmc_dev(self, Q: SparseMatrix, Z, out_dptr: int):
+        """RBMC variances of the CUDA tensor ``Z`` (nsamp, n) written to device memory at ``out_dptr`` (n doubles);
+        queued on the context's stream (no synchronisation, no host copy)."""
+        assert Z.is_cuda and Z.is_contiguous() and Z.shape[1] == self.sym.n and str(Z.dtype) == "torch.float64"
+        _torch_ready(Z)
+        zp = C.cast(C.c_void_p(Z.data_ptr()), B._F64P)
+        B.check(B.lib().gmrfb_var_rbmc_dev(self.h, Q.h, zp, self.sym.n, Z.shape[0], C.c_void_p(out_dptr)), self.ctx.h)
 
     def selinv_entries(self, rows, cols):
         rows, rp = B.i64(rows)
@@ -942,6 +960,7 @@ def tridiagonal_cholesky_dense(D, Bsub, ctx=None) -> TridiagonalCholeskyFactor:
     ctx = ctx or default_context()
     if hasattr(D, "data_ptr"):  # device-resident blocks (torch CUDA tensors)
         assert D.is_cuda and D.is_contiguous() and str(D.dtype) == "torch.float64"
+        _torch_ready(D)
         N, b, _ = D.shape
         Dp = C.cast(C.c_void_p(D.data_ptr()), B._F64P)
         if N > 1:
@@ -973,6 +992,7 @@ def tridiagonal_cholesky_ssm(D_first, D_mid, D_last, B_sub, N_blocks, ctx=None) 
         blocks = [D_first, D_mid, D_last, B_sub]
         for M in blocks:
             assert M is None or (M.is_cuda and M.is_contiguous() and str(M.dtype) == "torch.float64")
+        _torch_ready(blocks[0])
         b = blocks[0].shape[0]
         ptrs = [C.cast(C.c_void_p(M.data_ptr()), B._F64P) if M is not None else None for M in blocks]
     else:

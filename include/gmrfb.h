@@ -228,6 +228,10 @@ gmrfb_status gmrfb_var_selinv_dev(gmrfb_fac* fac, double* d_var_out);
  * device memory: the caller owns the random stream, as the reference threads its MersenneTwister through). */
 gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
                             int64_t nsamp, double* var_out);
+/* Same with the result left in device memory (n doubles; queued on the context's stream, not synchronised): the
+ * sample-sharded estimate of several GPUs is then combined by one all-reduce without a host round trip. */
+gmrfb_status gmrfb_var_rbmc_dev(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz, int64_t nsamp,
+                                double* d_var_out);
 /* Selected entries of Q^{-1}: for each k, out[k] = (Q^{-1})[rows[k], cols[k]] (`base`-based indices in
  * the original ordering).  Entries outside the filled pattern of L + L' yield GMRFB_ERR_INVALID. */
 gmrfb_status gmrfb_selinv_entries(gmrfb_fac* fac, int32_t base, int64_t count, const int64_t* rows,
