@@ -64,6 +64,13 @@ extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) {
   GMRFB_CU(nullptr, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   GMRFB_CU(nullptr, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
   GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_info, sizeof(int)));
+  GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_info_init, sizeof(int)));
+  {
+    const int big = INT_MAX;
+    GMRFB_CU(nullptr, cudaMemcpy(c->d_info_init, &big, sizeof(int), cudaMemcpyHostToDevice));
+    const char* g = getenv("GMRFB_GRAPHS");
+    c->use_graphs = !(g && g[0] == '0');
+  }
   GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_scalar, 16 * sizeof(double)));
   GMRFB_CU(nullptr, kernels_init());
   GMRFB_CU(nullptr, sparse_kernels_init());
@@ -83,6 +90,7 @@ extern "C" gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d_info) cudaFree(ctx->d_info);
+  if (ctx->d_info_init) cudaFree(ctx->d_info_init);
   if (ctx->d_scalar) cudaFree(ctx->d_scalar);
   if (ctx->stream2) {
     cudaStreamSynchronize(ctx->stream2);
@@ -531,26 +539,29 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
   fac->factored = false;
   fac->z_valid = false;
   fac->logdet_valid = false;
-  {
-    ProfScope ps(ctx, PK_MEMSET, 0, (double)fac->arena.n * sizeof(double));
-    GMRFB_CU(ctx, cudaMemsetAsync(fac->arena.p, 0, fac->arena.n * sizeof(double), st));
-  }
-  const int big = INT_MAX;
-  GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, st));
-  {
-    ProfScope ps(ctx, PK_SCATTER, 0, (double)S.nnzA * 16.0 + (double)S.nnz_lower_A * 8.0);
-    GMRFB_CU(ctx, launch_scatter_values(d_nzval, sym->d_amap.p, S.nnzA, fac->arena.p, st));
-  }
-  ctx->launches++;
-  Arenas ar{{fac->arena.p, nullptr, nullptr, nullptr}};
-  ar.dinv = fac->dinv.p;
-  LaunchAux aux;
-  aux.d_info = ctx->d_info;
-  aux.d_relmap = sym->d_relmap.p;
-  aux.d_snodes = sym->d_snodes.p;
-  aux.d_child_idx = sym->d_child_idx.p;
-  aux.d_sparent = sym->d_sparent.p;
-  gmrfb_status rc = run_plan(ctx, sym->factor_plan, ar, aux);
+  auto body = [&]() -> gmrfb_status {
+    {
+      ProfScope ps(ctx, PK_MEMSET, 0, (double)fac->arena.n * sizeof(double));
+      GMRFB_CU(ctx, cudaMemsetAsync(fac->arena.p, 0, fac->arena.n * sizeof(double), st));
+    }
+    GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, ctx->d_info_init, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    {
+      ProfScope ps(ctx, PK_SCATTER, 0, (double)S.nnzA * 16.0 + (double)S.nnz_lower_A * 8.0);
+      GMRFB_CU(ctx, launch_scatter_values(d_nzval, sym->d_amap.p, S.nnzA, fac->arena.p, st));
+    }
+    ctx->launches++;
+    Arenas ar{{fac->arena.p, nullptr, nullptr, nullptr}};
+    ar.dinv = fac->dinv.p;
+    LaunchAux aux;
+    aux.d_info = ctx->d_info;
+    aux.d_relmap = sym->d_relmap.p;
+    aux.d_snodes = sym->d_snodes.p;
+    aux.d_child_idx = sym->d_child_idx.p;
+    aux.d_sparent = sym->d_sparent.p;
+    return run_plan(ctx, sym->factor_plan, ar, aux);
+  };
+  gmrfb_status rc = run_graphed(ctx, fac->graphs, graph_key({1, (uint64_t)(uintptr_t)d_nzval, (uint64_t)(uintptr_t)fac->arena.p,
+                                                             (uint64_t)(uintptr_t)fac->dinv.p}), body);
   if (rc != GMRFB_OK) return rc;
   int info = 0;
   GMRFB_CU(ctx, cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -786,9 +797,16 @@ gmrfb_status sweep_panel(gmrfb_fac* fac, bool fwd, bool bwd, int nr) {
   aux.d_rows = sym->d_rows.p;
   aux.nr = nr;
   aux.ldk = mp->ldk;
-  if (fwd) rc = run_plan(fac->ctx, mp->fwd, ar, aux);
-  if (rc == GMRFB_OK && bwd) rc = run_plan(fac->ctx, mp->bwd, ar, aux);
-  return rc;
+  auto body = [&]() -> gmrfb_status {
+    gmrfb_status r = GMRFB_OK;
+    if (fwd) r = run_plan(fac->ctx, mp->fwd, ar, aux);
+    if (r == GMRFB_OK && bwd) r = run_plan(fac->ctx, mp->bwd, ar, aux);
+    return r;
+  };
+  return run_graphed(fac->ctx, fac->graphs,
+                     graph_key({3, (uint64_t)nr, (uint64_t)fwd, (uint64_t)bwd, (uint64_t)(uintptr_t)fac->mr_x.p,
+                                (uint64_t)(uintptr_t)fac->mr_u.p, (uint64_t)(uintptr_t)fac->arena.p,
+                                (uint64_t)(uintptr_t)mp->fwd.tasks.p}), body);
 }
 
 // split nrhs right-hand sides into the fewest, equally wide panels of at most MR_MAX columns
@@ -847,20 +865,28 @@ gmrfb_status solve_device(gmrfb_fac* fac, int mode, const double* d_in, int64_t 
   }
   for (int64_t c0 = 0; c0 < nrhs; c0 += SOLVE_NRC) {
     int nr = (int)std::min<int64_t>(SOLVE_NRC, nrhs - c0);
-    // fwd: xwork -> ywork;  bwd: ywork -> xwork
-    double* first = m.fwd ? fac->xwork.p : fac->ywork.p;
-    GMRFB_CU(ctx, launch_perm_gather(d_in + c0 * ldin, ldin, first, n, m.in_perm ? sym->d_perm.p : sym->d_post.p, n, nr,
-                                     ctx->stream));
-    ctx->launches++;
-    gmrfb_status rc = GMRFB_OK;
-    if (m.fwd) rc = sweep_fwd(fac, fac->xwork.p, fac->ywork.p, nr);
+    auto body = [&]() -> gmrfb_status {
+      // fwd: xwork -> ywork;  bwd: ywork -> xwork
+      double* first = m.fwd ? fac->xwork.p : fac->ywork.p;
+      GMRFB_CU(ctx, launch_perm_gather(d_in + c0 * ldin, ldin, first, n, m.in_perm ? sym->d_perm.p : sym->d_post.p, n, nr,
+                                       ctx->stream));
+      ctx->launches++;
+      gmrfb_status rc = GMRFB_OK;
+      if (m.fwd) rc = sweep_fwd(fac, fac->xwork.p, fac->ywork.p, nr);
+      if (rc != GMRFB_OK) return rc;
+      if (m.bwd) rc = sweep_bwd(fac, fac->ywork.p, fac->xwork.p, nr);
+      if (rc != GMRFB_OK) return rc;
+      const double* result = m.bwd ? fac->xwork.p : fac->ywork.p;
+      GMRFB_CU(ctx, launch_perm_scatter(result, n, d_out + c0 * ldout, ldout, m.out_perm ? sym->d_perm.p : sym->d_post.p,
+                                        n, nr, d_mean, ctx->stream));
+      ctx->launches++;
+      return GMRFB_OK;
+    };
+    gmrfb_status rc = run_graphed(ctx, fac->graphs,
+                                  graph_key({2, (uint64_t)mode, (uint64_t)(uintptr_t)(d_in + c0 * ldin), (uint64_t)ldin,
+                                             (uint64_t)(uintptr_t)(d_out + c0 * ldout), (uint64_t)ldout, (uint64_t)nr,
+                                             (uint64_t)(uintptr_t)d_mean, (uint64_t)(uintptr_t)fac->arena.p}), body);
     if (rc != GMRFB_OK) return rc;
-    if (m.bwd) rc = sweep_bwd(fac, fac->ywork.p, fac->xwork.p, nr);
-    if (rc != GMRFB_OK) return rc;
-    const double* result = m.bwd ? fac->xwork.p : fac->ywork.p;
-    GMRFB_CU(ctx, launch_perm_scatter(result, n, d_out + c0 * ldout, ldout, m.out_perm ? sym->d_perm.p : sym->d_post.p,
-                                      n, nr, d_mean, ctx->stream));
-    ctx->launches++;
   }
   return GMRFB_OK;
 }
@@ -1042,7 +1068,11 @@ static gmrfb_status selinv_run(gmrfb_fac* fac) {
   aux.d_snodes = sym->d_snodes.p;
   aux.d_child_idx = sym->d_child_idx.p;
   aux.d_sparent = sym->d_sparent.p;
-  rc = run_plan(ctx, sym->selinv_plan, ar, aux);
+  rc = run_graphed(ctx, fac->graphs,
+                   graph_key({4, (uint64_t)(uintptr_t)fac->arena.p, (uint64_t)(uintptr_t)fac->zarena.p,
+                              (uint64_t)(uintptr_t)fac->zwork.p, (uint64_t)(uintptr_t)fac->zdiag.p,
+                              (uint64_t)(uintptr_t)fac->dinv_sel.p}),
+                   [&]() -> gmrfb_status { return run_plan(ctx, sym->selinv_plan, ar, aux); });
   if (rc != GMRFB_OK) return rc;
   fac->z_valid = true;
   return GMRFB_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <initializer_list>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -25,7 +26,9 @@ struct gmrfb_ctx {
   std::string err;
   int64_t launches = 0;
   int* d_info = nullptr;       // POTRF failure column
+  int* d_info_init = nullptr;  // device constant INT_MAX (d_info is reset by a device-to-device copy: graph-capturable)
   double* d_scalar = nullptr;  // small device scratch (reductions)
+  bool use_graphs = true;      // replay the static launch lists as CUDA graphs (GMRFB_GRAPHS=0 disables)
   int sm_count = 0;
   // optional per-kernel profiling (CUDA events around every launch)
   bool profiling = false;
@@ -257,5 +260,80 @@ struct ProfScope {
 
 // Execute every launch of a plan on the context's stream.
 gmrfb_status run_plan(gmrfb_ctx* ctx, const DevPlan& P, const Arenas& ar, const LaunchAux& aux);
+
+// The numeric phases are static launch lists (hundreds of small dependent kernels for the top of the elimination tree):
+// the first execution of a phase with a given set of buffers is captured into a CUDA graph, later executions replay the
+// graph with one launch call (no per-kernel host work, back-to-back scheduling on the device).  `key` identifies
+// everything baked into the captured kernel arguments (buffer addresses, sizes, modes); a different key re-captures.
+// Profiling (per-launch events) bypasses the graphs.
+struct GraphCache {
+  struct Ent {
+    uint64_t key = 0;
+    cudaGraphExec_t exec = nullptr;
+    int64_t nodes = 0;  // kernels of the graph (for the launch counter)
+    uint64_t stamp = 0;
+  };
+  std::vector<Ent> ents;
+  uint64_t clock = 0;
+  ~GraphCache() { clear(); }
+  void clear() {
+    for (auto& e : ents)
+      if (e.exec) cudaGraphExecDestroy(e.exec);
+    ents.clear();
+  }
+};
+inline uint64_t graph_key(std::initializer_list<uint64_t> parts) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (uint64_t v : parts) {
+    h ^= v;
+    h *= 0x100000001b3ull;
+    h ^= h >> 29;
+  }
+  return h ? h : 1;
+}
+template <class Body>
+gmrfb_status run_graphed(gmrfb_ctx* ctx, GraphCache& gc, uint64_t key, Body&& body) {
+  if (!ctx->use_graphs || ctx->profiling) return body();
+  for (auto& e : gc.ents)
+    if (e.key == key && e.exec) {
+      e.stamp = ++gc.clock;
+      GMRFB_CU(ctx, cudaGraphLaunch(e.exec, ctx->stream));
+      ctx->launches += e.nodes;
+      return GMRFB_OK;
+    }
+  const int64_t l0 = ctx->launches;
+  GMRFB_CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  gmrfb_status rc = body();
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != GMRFB_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    return fail(ctx, GMRFB_ERR_CUDA, std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce));
+  }
+  GraphCache::Ent e;
+  ce = cudaGraphInstantiate(&e.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, GMRFB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+  }
+  e.key = key;
+  e.nodes = ctx->launches - l0;
+  e.stamp = ++gc.clock;
+  if (gc.ents.size() >= 12) {  // bounded: drop the least recently used graph
+    size_t lru = 0;
+    for (size_t i = 1; i < gc.ents.size(); i++)
+      if (gc.ents[i].stamp < gc.ents[lru].stamp) lru = i;
+    cudaGraphExecDestroy(gc.ents[lru].exec);
+    gc.ents.erase(gc.ents.begin() + lru);
+  }
+  gc.ents.push_back(e);
+  GMRFB_CU(ctx, cudaGraphLaunch(e.exec, ctx->stream));
+  return GMRFB_OK;
+}
 
 }  // namespace gmrfb

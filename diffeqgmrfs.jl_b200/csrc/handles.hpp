@@ -45,6 +45,7 @@ struct gmrfb_fac {
   // panel solves: node-major panel X (MR_MAX x n), update panels U (MR_MAX x sum of r_J), column-major staging (n x MR_MAX)
   gmrfb::DevBuf<double> mr_x, mr_u, mr_io;
   gmrfb::DevBuf<double> meanbuf, rbmc_x, refine_ws;  // persistent workspaces of gmrfb_sample / gmrfb_var_rbmc
+  gmrfb::GraphCache graphs;  // captured numeric phases of this factor (factorisation, sweeps, selected inversion)
   bool factored = false, z_valid = false, logdet_valid = false;
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_column = -1;
