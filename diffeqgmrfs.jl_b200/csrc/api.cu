@@ -70,6 +70,8 @@ extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) {
     GMRFB_CU(nullptr, cudaMemcpy(c->d_info_init, &big, sizeof(int), cudaMemcpyHostToDevice));
     const char* g = getenv("GMRFB_GRAPHS");
     c->use_graphs = !(g && g[0] == '0');
+    const char* po = getenv("GMRFB_POISON");
+    c->poison = po && po[0] == '1';
   }
   GMRFB_CU(nullptr, cudaMalloc((void**)&c->d_scalar, 16 * sizeof(double)));
   GMRFB_CU(nullptr, kernels_init());
@@ -158,6 +160,7 @@ static const char* prof_name(int kind) {
     case LK_MR_BWD_SMALL: return "k_mr_bwd_small";
     case LK_MR_ASSEMBLE: return "k_mr_assemble";
     case LK_MR_GATHER: return "k_mr_gather";
+    case LK_ZERO_FRONT: return "k_zero_front";
   }
   return "other";
 }
@@ -484,6 +487,9 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
   }
   GMRFB_CU(ctx, sym->factor_plan.tasks.upload(sym->factor_plan.host.tasks, st));
   sym->factor_plan.ready = true;
+  build_zero_plan(S, sym->zero_plan.host);
+  GMRFB_CU(ctx, sym->zero_plan.tasks.upload(sym->zero_plan.host.tasks, st));
+  sym->zero_plan.ready = true;
   sym->dev_ready = true;
   return GMRFB_OK;
 }
@@ -540,11 +546,15 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
   fac->z_valid = false;
   fac->logdet_valid = false;
   auto body = [&]() -> gmrfb_status {
-    {
-      ProfScope ps(ctx, PK_MEMSET, 0, (double)fac->arena.n * sizeof(double));
-      GMRFB_CU(ctx, cudaMemsetAsync(fac->arena.p, 0, fac->arena.n * sizeof(double), st));
-    }
+    // (the plan's first launch clears the parts of the fronts that are accumulated into; GMRFB_POISON=1 fills the whole
+    //  arena with NaNs first — a debugging aid that proves nothing outside the cleared parts is ever read)
+    if (ctx->poison) GMRFB_CU(ctx, cudaMemsetAsync(fac->arena.p, 0xff, fac->arena.n * sizeof(double), st));
     GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, ctx->d_info_init, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    {
+      Arenas zar{{fac->arena.p, nullptr, nullptr, nullptr}};
+      gmrfb_status zrc = run_plan(ctx, sym->zero_plan, zar, LaunchAux());
+      if (zrc != GMRFB_OK) return zrc;
+    }
     {
       ProfScope ps(ctx, PK_SCATTER, 0, (double)S.nnzA * 16.0 + (double)S.nnz_lower_A * 8.0);
       GMRFB_CU(ctx, launch_scatter_values(d_nzval, sym->d_amap.p, S.nnzA, fac->arena.p, st));

@@ -28,6 +28,7 @@ struct gmrfb_ctx {
   int* d_info = nullptr;       // POTRF failure column
   int* d_info_init = nullptr;  // device constant INT_MAX (d_info is reset by a device-to-device copy: graph-capturable)
   double* d_scalar = nullptr;  // small device scratch (reductions)
+  bool poison = false;         // GMRFB_POISON=1: NaN-fill the frontal arena before every factorisation (debug)
   bool use_graphs = true;      // replay the static launch lists as CUDA graphs (GMRFB_GRAPHS=0 disables)
   int sm_count = 0;
   // optional per-kernel profiling (CUDA events around every launch)

@@ -21,7 +21,7 @@ struct gmrfb_sym {
   std::vector<double> small_bytes;
   std::vector<double> level_bytes, level_vec_bytes, level_flops;  // algorithmic work of one solve sweep per level
   int64_t uvec_rows = 0;
-  gmrfb::DevPlan factor_plan, selinv_plan;
+  gmrfb::DevPlan factor_plan, selinv_plan, zero_plan;
   // solve schedule: per level, one launch per 64-column block step
   struct SolveLevel {
     std::vector<gmrfb::Launch> fwd_steps, bwd_steps;

@@ -782,6 +782,39 @@ __global__ void __launch_bounds__(256) k_tile_op(const Task* __restrict__ tasks,
   }
 }
 
+// c (M x N) <- 0, one CTA per 64 x 64 tile; with TF_TRI only the tiles that meet the lower triangle.  The numeric
+// factorisation clears exactly what it accumulates into (the lower triangles of the large fronts, the panels of the
+// small ones) instead of the whole frontal arena: 3.5 GB instead of 8.3 GB on the 1M-node mesh.
+__global__ void __launch_bounds__(256) k_zero_front(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
+  const int tix = find_task(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int M = T.M, N = T.N;
+  const int local = blockIdx.x - T.tile0;
+  int ti, tj;
+  if (T.flags & TF_TRI) {
+    tri_decode(local, ti, tj);
+  } else {
+    const int ntm = (M + 63) / 64;
+    ti = local % ntm;
+    tj = local / ntm;
+  }
+  double* __restrict__ C = ar.p[(T.flags >> TF_C_SHIFT) & 3] + T.c;
+  // fronts start on 128-byte boundaries and have even leading dimensions: row pairs are 16-byte aligned
+  const int i = ti * 64 + 2 * (threadIdx.x & 31);
+  if (i >= M) return;
+  const bool pair = i + 1 < M;
+#pragma unroll 8
+  for (int lj = threadIdx.x >> 5; lj < 64; lj += 8) {
+    const int j = tj * 64 + lj;
+    if (j >= N) break;
+    double* p = C + i + (int64_t)j * T.ldc;
+    if (pair)
+      *reinterpret_cast<double2*>(p) = make_double2(0.0, 0.0);
+    else
+      *p = 0.0;
+  }
+}
+
 // In-place transpose of a square M x M matrix: one CTA per 32x32 tile pair of the lower triangle.
 __global__ void __launch_bounds__(256) k_transpose(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
   __shared__ double sa[32][33], sb[32][33];
@@ -943,6 +976,9 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       break;
     case LK_DIAG_OUT:
       k_diag_out<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_out);
+      break;
+    case LK_ZERO_FRONT:
+      k_zero_front<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar);
       break;
     case LK_FRONT_FACTOR_SMALL: {
       // CTA width by size class: the kernels are latency bound (global loads of the children's update matrices), so

@@ -17,6 +17,14 @@ int gemm_big_min() {
   return v;
 }
 
+bool gemm_lpt_order() {
+  static const bool v = [] {
+    const char* e = std::getenv("GMRFB_GEMM_LPT");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 namespace {
 
 inline int32_t arena_flags(int a, int b, int c) { return (a << TF_A_SHIFT) | (b << TF_B_SHIFT) | (c << TF_C_SHIFT); }
@@ -347,6 +355,34 @@ void plan_trsm_rln(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, i
 }
 
 // ------------------------------------------------------------------------------------ sparse factor ----
+// Clears what the factorisation accumulates into, before the matrix values are scattered into the fronts: the panel of
+// every small front (the fused kernel keeps the rest of the front in shared memory and writes it in full) and the
+// lower triangle of every large front.
+void build_zero_plan(const Symbolic& S, Plan& P) {
+  PlanBuilder B(P);
+  B.begin(LK_ZERO_FRONT);
+  for (int32_t s = 0; s < S.nsuper; s++) {
+    const int d = S.front_order(s), sc = S.ncols(s);
+    Task t = make_task();
+    t.c = S.foff[s];
+    t.ldc = S.ld[s];
+    t.M = d;
+    t.flags = arena_flags(0, 0, AR_FRONT);
+    if (d <= SMALL_FRONT_MAX) {
+      t.N = sc;
+      B.add(t, cdiv(d, 64) * cdiv(sc, 64));
+      B.add_bytes(8.0 * d * sc);
+    } else {
+      t.N = d;
+      t.flags |= TF_TRI;
+      const int nt = cdiv(d, 64);
+      B.add(t, nt * (nt + 1) / 2);
+      B.add_bytes(8.0 * 64 * 64 * (nt * (nt + 1) / 2));
+    }
+  }
+  B.end();
+}
+
 void build_factor_plan(const Symbolic& S, Plan& P) {
   PlanBuilder B(P);
   P.winv_slot.assign(S.nsuper, -1);

@@ -1,5 +1,6 @@
 // Host-side plan builders: compile a symbolic structure into static launch/task lists for the tile engine.
 #pragma once
+#include <algorithm>
 #include <vector>
 
 #include "symbolic.hpp"
@@ -50,6 +51,11 @@ class PlanBuilder {
   void end() {
     cur.flops = P.flops - flops0;
     if (is_gemm_kind(cur.kind) && cur.ntasks > 0) {
+      // longest tiles first (K descending): the CTAs of a launch are dispatched in index order, so the last, partially
+      // filled wave is made of the shortest tiles (the tasks of one launch are independent: any order is valid)
+      if (cur.ntasks > 1 && gemm_lpt_order())
+        std::stable_sort(P.tasks.begin() + cur.task0, P.tasks.begin() + cur.task0 + cur.ntasks,
+                         [](const Task& a, const Task& b) { return a.K > b.K; });
       // GEMM tasks were added with their GCFG_BIG tile counts; pick the launch's tile configuration and re-tile
       cur.cfg = choose_gemm_cfg(cur.grid, cur.ntasks);
       cur.grid = 0;
@@ -91,6 +97,8 @@ inline Task make_task() {
 // Arena indices used by the sparse plans.
 enum { AR_FRONT = 0, AR_ZINV = 1, AR_WORK = 2 };
 
+// One launch that clears the parts of the frontal arena the factorisation accumulates into (runs before the scatter).
+void build_zero_plan(const Symbolic& S, Plan& P);
 // Multifrontal numeric factorisation of every front, level by level (arena 0 = frontal arena).
 void build_factor_plan(const Symbolic& S, Plan& P);
 // Takahashi selected inversion, top-down (arena 0 = factor fronts, arena 1 = inverse fronts);

@@ -59,6 +59,7 @@ enum LaunchKind : int32_t {
   LK_MR_BWD_SMALL = 33,  // backward substitution of one small supernode per CTA
   LK_MR_ASSEMBLE = 34,   // X[:, C_J] += / U_J = children's update panels (aux0 = supernode; CTA = 8 right-hand sides)
   LK_MR_GATHER = 35,     // U_J <- X[:, below rows of J] (aux0 = supernode; CTA = 64 rows)
+  LK_ZERO_FRONT = 36,    // c (M x N, ldc) <- 0 by 64 x 64 tiles; TF_TRI: only the tiles of the lower triangle (N = M)
 };
 
 struct Launch {
@@ -140,7 +141,7 @@ inline bool uses_cta_map(int kind) {
   switch (kind) {
     case LK_GEMM_NT: case LK_GEMM_NN: case LK_GEMM_TN: case LK_GEMM_TT: case LK_TRSM_RLT: case LK_TRSM_RLN:
     case LK_EXTEND_ADD: case LK_GATHER_SYM: case LK_SET_IDENTITY: case LK_TRANSPOSE: case LK_SCALE:
-    case LK_DIAG_OUT: case LK_SYMMETRIZE: case LK_MR_GATHER:
+    case LK_DIAG_OUT: case LK_SYMMETRIZE: case LK_MR_GATHER: case LK_ZERO_FRONT:
       return true;
     default:
       return false;
@@ -154,6 +155,7 @@ inline bool is_gemm_kind(int kind) {
 // 33.4 against 33.5 TFLOP/s; profiles/r01_gemm_batched_probe.md), so the 128x64 configuration is only chosen when
 // GMRFB_GEMM_BIG_MIN asks for it (launches averaging at least that many 128x64 tiles per task); default: never.
 int gemm_big_min();
+bool gemm_lpt_order();  // GMRFB_GEMM_LPT=0 keeps the tasks of a GEMM launch in supernode order (A/B aid)
 inline int choose_gemm_cfg(int big_tiles, int ntasks) {
   return (ntasks > 0 && big_tiles / ntasks >= gemm_big_min()) ? GCFG_BIG : GCFG_SMALL;
 }
