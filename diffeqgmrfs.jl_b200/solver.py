@@ -563,9 +563,11 @@ class _Ref:
 class CholeskySolver:
     """What ``x.solver_ref[]`` points to: holds ``precision_chol`` (with ``.p``, ``.L``, ``nnz``)."""
 
-    def __init__(self, gmrf, blueprint: CholeskySolverBlueprint, symbolic: Symbolic | None = None, values_dev: int = 0):
+    def __init__(self, gmrf, blueprint: CholeskySolverBlueprint, symbolic: Symbolic | None = None, values_dev: int = 0,
+                 precision_dev: "SparseMatrix | None" = None):
         self.gmrf = gmrf
         self.blueprint = blueprint
+        self._precision_dev = precision_dev  # the precision as a device matrix, when the caller already has one
         Q = gmrf.precision
         sym = symbolic or blueprint.symbolic_for(Q)
         if values_dev:  # the values already sit in device memory (fixed-pattern assembly): no host round trip
@@ -589,7 +591,11 @@ class CholeskySolver:
             vs = self.blueprint.var_strategy
             if isinstance(vs, RBMCStrategy):
                 Z = vs.normals(self.gmrf.n, self.precision_chol.ctx.device)
-                Qd = SparseMatrix(self.gmrf.precision, ctx=self.precision_chol.ctx)
+                # the posterior precision assembled on the device is used where it lies (no upload, no row-wise copy)
+                # (only while it still holds THIS posterior: a later conditioning on the same prior overwrites its values)
+                pd = self._precision_dev
+                Qd = pd[0] if (pd is not None and pd[1].generation == pd[2]) else \
+                    SparseMatrix(self.gmrf.precision, ctx=self.precision_chol.ctx)
                 self._var = self.precision_chol.var_rbmc(Qd, Z)
             else:
                 self._var = self.precision_chol.var_selinv()
@@ -604,13 +610,14 @@ class GMRF:
     """``GMRF(mean, precision, solver_blueprint)`` (_research/elliptic_chen24.jl:166).  ``information`` carries
     the lazy right-hand side of a conditioned GMRF: mean = prior_mean + Q^{-1} information."""
 
-    def __init__(self, mean, precision, solver_blueprint=None, information=None, _symbolic=None, _values_dev=0):
+    def __init__(self, mean, precision, solver_blueprint=None, information=None, _symbolic=None, _values_dev=0,
+                 _precision_dev=None):
         self.precision = _csc(precision)
         self.n = self.precision.shape[0]
         self.prior_mean = np.asarray(mean, dtype=np.float64)
         self.information = information
         bp = solver_blueprint or CholeskySolverBlueprint()
-        self.solver_ref = _Ref(CholeskySolver(self, bp, _symbolic, _values_dev))
+        self.solver_ref = _Ref(CholeskySolver(self, bp, _symbolic, _values_dev, _precision_dev))
         self._cond_ws = None
 
     def __len__(self):
@@ -662,6 +669,7 @@ class _ConditioningWorkspace:
             self.Ad, self.dev_handle = SparseMatrix(A, ctx=ctx), None
         self.plan = PosteriorPrecision(self.Qd, self.Ad)
         self.pattern = None  # (indptr, indices) of the posterior precision, fetched with the first result
+        self.generation = 0  # bumped by every numeric assembly: the plan's result matrix is overwritten in place
 
     def matches(self, A):
         if isinstance(A, SparseMatrix):
@@ -690,6 +698,7 @@ def condition_on_observations(x: GMRF, A, Q_eps, y, solver_blueprint=None) -> GM
     elif not on_device:
         ws.Ad.set_values(A.data)
     Apost = ws.plan.compute(Q_eps)
+    ws.generation += 1
     if ws.pattern is None:
         P = Apost.to_scipy()
         ws.pattern = (P.indptr, P.indices)
@@ -702,7 +711,8 @@ def condition_on_observations(x: GMRF, A, Q_eps, y, solver_blueprint=None) -> GM
     w = np.broadcast_to(np.asarray(Q_eps, dtype=np.float64), (ws.shape[0],))
     resid = np.asarray(y, dtype=np.float64) - ws.Ad.matvec(mu)
     info = ws.Ad.matvec(w * resid, trans=True)
-    return GMRF(mu, Qpost, bp, information=info, _values_dev=Apost.values_dev())
+    return GMRF(mu, Qpost, bp, information=info, _values_dev=Apost.values_dev(),
+                _precision_dev=(Apost, ws, ws.generation))
 
 
 # ------------------------------------------------------------------------------------------ Gauss-Newton --
