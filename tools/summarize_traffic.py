@@ -1,11 +1,11 @@
 """Summarise `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv` of the GEMM launches
 of one bench step into profiles/<name>.json: per kernel instantiation the launches, DRAM bytes and time; bench.py
 reads `bytes_per_launch` of the dominant kernel as `roofline.traffic`.
-Usage: python tools/summarize_traffic.py gpurun_out/<tag>_gemm_traffic.csv profiles/r01_gemm_traffic.json"""
+Usage: python tools/summarize_traffic.py gpurun_out/<tag>_gemm_traffic.csv profiles/r02_gemm_traffic.json [nx ordering nd_cover]\n(the configuration of the capture is recorded; bench.py reports the traffic only for a run with the same configuration and launch count)"""
 import csv, json, re, sys
 
 
-def main(src, dst):
+def main(src, dst, nx=1001, ordering="nd", nd_cover="1"):
     lines = open(src, errors="replace").read().splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
     per = {}
@@ -23,7 +23,10 @@ def main(src, dst):
             e["dram_write_bytes"] += val * scale
         elif metric == "gpu__time_duration.sum":
             e["time_ms"] += val * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)
-    out = {"source": src, "kernels": {}}
+    out = {"source": src, "config": {"nx": int(nx), "ordering": ordering, "nd_cover": str(nd_cover),
+                                    "command": "python bench.py --steps 1 --warmup 3 --no-cpu-baseline --skip-extras --inflight 1 "
+                                               "(profiled replay of one posterior solve, cudaProfilerStart/Stop window)"},
+           "kernels": {}}
     for k, e in per.items():
         n = len(e["launches"])
         tot = e["dram_read_bytes"] + e["dram_write_bytes"]
@@ -34,4 +37,4 @@ def main(src, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:])
