@@ -58,6 +58,21 @@ __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
   tj = t - r * (r + 1) / 2;
 }
 
+// advance a lower-triangular tile index (ti, tj) by `step` tiles in row-major order of the triangle (0,0), (1,0), (1,1), ...
+// (the per-tile sqrt-based decode cost more than the two DMMAs of a rank-8 tile update: ncu, profiles/r02_small_front_lines.md)
+__device__ __forceinline__ void tri_advance(int& ti, int& tj, int step) {
+  tj += step;
+  while (tj > ti) {
+    tj -= ti + 1;
+    ti++;
+  }
+}
+// x / n for 0 <= x < 65536 and 1 <= n < 65536 through a multiplication by ceil(2^32 / n): the staging loops of the fused
+// small-front kernels index (column, row) pairs by a flat counter, and an integer division per element was a tenth of
+// their issue slots
+__device__ __forceinline__ uint32_t div_magic(uint32_t n) { return n <= 1 ? 0u : (uint32_t)((0x100000000ull + n - 1) / n); }
+__device__ __forceinline__ int fast_div(int x, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)x, magic) : x; }
+
 // right-looking Cholesky of the 8x8 block in registers (lower part); invd[c] = 1 / L_cc.  Returns the first failing
 // column or 8.
 __device__ __forceinline__ int chol8(double (&D)[8][8], double (&invd)[8]) {
@@ -184,11 +199,10 @@ __global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks,
       }
       __syncthreads();
       const int first = p + 1, m = nb8 - first;
-      for (int t = warp; t < m * (m + 1) / 2; t += 8) {
-        int ti, tj;
-        tri_decode(t, ti, tj);
-        ti += first;
-        tj += first;
+      int ti0 = 0, tj0 = 0;
+      tri_advance(ti0, tj0, warp);
+      for (; ti0 < m; tri_advance(ti0, tj0, 8)) {
+        const int ti = ti0 + first, tj = tj0 + first;
         double* cp = S + (tj * 8 + 2 * lc) * PLD + ti * 8 + lr;
         double c0 = cp[0], c1 = cp[PLD];
 #pragma unroll
@@ -466,17 +480,18 @@ __global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restric
   // stage: the update-matrix part and the padding start from zero, the panel columns come from the arena.  All
   // global-memory loops of this kernel keep 8 independent loads per thread in flight (the kernel is latency bound).
   for (int e = tid; e < dp * lds; e += NT) S[e] = 0.0;
+  const uint32_t mdp = div_magic((uint32_t)dp);
   __syncthreads();
   for (int base = tid; base < s * dp; base += 8 * NT) {
     double v[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      const int e = base + u * NT, c = e / dp, i = e - c * dp;
+      const int e = base + u * NT, c = fast_div(e, mdp), i = e - c * dp;
       v[u] = (e < s * dp && i >= c && i < d) ? F[(int64_t)c * ldg + i] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      const int e = base + u * NT, c = e / dp, i = e - c * dp;
+      const int e = base + u * NT, c = fast_div(e, mdp), i = e - c * dp;
       if (e < s * dp && i >= c && i < d) S[c * lds + i] = v[u];
     }
   }
@@ -495,16 +510,18 @@ __global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restric
     // lower triangle of the child's update matrix, visited as (row chunk of 64) x column
     const int nrc64 = (rc + 63) >> 6;
     const int total = nrc64 * rc;  // items: (j, chunk)
+    const bool fastd = total < 65536;
+    const uint32_t mrc = div_magic((uint32_t)nrc64);
     for (int base = tq; base < total; base += 8 * (NT / 64)) {
       double v[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int it = base + u * (NT / 64), j = it / nrc64, i = (it - j * nrc64) * 64 + ti_;
+        const int it = base + u * (NT / 64), j = fastd ? fast_div(it, mrc) : it / nrc64, i = (it - j * nrc64) * 64 + ti_;
         v[u] = (it < total && i >= j && i < rc) ? U[i + (int64_t)j * C.ld] : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int it = base + u * (NT / 64), j = it / nrc64, i = (it - j * nrc64) * 64 + ti_;
+        const int it = base + u * (NT / 64), j = fastd ? fast_div(it, mrc) : it / nrc64, i = (it - j * nrc64) * 64 + ti_;
         if (it < total && i >= j && i < rc) S[rmap[j] * lds + rmap[i]] += v[u];
       }
     }
@@ -549,11 +566,10 @@ __global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restric
     {
       const int m0 = j0 + pw;  // first column that is updated
       const int t0 = m0 >> 3, m = (dp >> 3) - t0;
-      for (int t = warp; t < m * (m + 1) / 2; t += NT / 32) {
-        int ti, tj;
-        tri_decode(t, ti, tj);
-        ti += t0;
-        tj += t0;
+      int ti0 = 0, tj0 = 0;
+      tri_advance(ti0, tj0, warp);
+      for (; ti0 < m; tri_advance(ti0, tj0, NT / 32)) {
+        const int ti = ti0 + t0, tj = tj0 + t0;
         double* cp = S + (tj * 8 + 2 * lc) * lds + ti * 8 + lr;
         double c0 = cp[0], c1 = cp[lds];
         const bool kvalid = (tj * 8 + lr) >= m0;  // columns of the panel itself are not updated
@@ -570,7 +586,7 @@ __global__ void __launch_bounds__(NT) k_front_factor_small(const Task* __restric
     __syncthreads();
   }
   for (int e = tid; e < d * dp; e += NT) {
-    const int c = e / dp, i = e - c * dp;
+    const int c = fast_div(e, mdp), i = e - c * dp;
     if (i >= c && i < d) F[(int64_t)c * ldg + i] = S[c * lds + i];
   }
 }
@@ -605,16 +621,17 @@ __global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restric
     __syncthreads();
     // Z_RR: lower triangle gathered from the parent's inverse front (8 independent loads in flight), mirrored
     const int nr64 = (r + 63) >> 6, total = nr64 * r;
+    const uint32_t mr64 = div_magic((uint32_t)nr64);
     for (int base = tq; base < total; base += 8 * (NT / 64)) {
       double v[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int it = base + u * (NT / 64), j = it / nr64, i = (it - j * nr64) * 64 + ti_;
+        const int it = base + u * (NT / 64), j = fast_div(it, mr64), i = (it - j * nr64) * 64 + ti_;
         v[u] = (it < total && i >= j && i < r) ? Zp[(int64_t)rel[i] + (int64_t)rel[j] * P.ld] : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int it = base + u * (NT / 64), j = it / nr64, i = (it - j * nr64) * 64 + ti_;
+        const int it = base + u * (NT / 64), j = fast_div(it, mr64), i = (it - j * nr64) * 64 + ti_;
         if (it < total && i >= j && i < r) {
           Z[(s + j) * lds + s + i] = v[u];
           Z[(s + i) * lds + s + j] = v[u];
@@ -626,11 +643,12 @@ __global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restric
   // panel of L: Lb[c][i] = L[i][j0 + c], i >= j0 + c (8 * dp <= 8 * NT entries); the next panel is prefetched into
   // registers while the current one is processed
   double lnext[8];
+  const uint32_t mdp = div_magic((uint32_t)dp);
   auto load_panel = [&](int jp) {
     const int pwp = min(8, s - jp);
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      const int e = tid + u * NT, c = e / dp, i = e - c * dp;
+      const int e = tid + u * NT, c = fast_div(e, mdp), i = e - c * dp;
       lnext[u] = (jp >= 0 && e < 8 * dp && c < pwp && i >= jp + c && i < d) ? L[(int64_t)(jp + c) * ldg + i] : 0.0;
     }
   };
@@ -640,7 +658,7 @@ __global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restric
     const int m0 = j0 + pw;  // B = [m0, d)
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      const int e = tid + u * NT, c = e / dp, i = e - c * dp;
+      const int e = tid + u * NT, c = fast_div(e, mdp), i = e - c * dp;
       if (e < 8 * dp) Lb[c * lds + i] = lnext[u];
     }
     __syncthreads();
@@ -750,7 +768,7 @@ __global__ void __launch_bounds__(NT) k_front_selinv_small(const Task* __restric
     __syncthreads();
   }
   for (int e = tid; e < d * dp; e += NT) {
-    const int c = e / dp, i = e - c * dp;
+    const int c = fast_div(e, mdp), i = e - c * dp;
     if (i >= c && i < d) Zg[(int64_t)c * ldg + i] = Z[c * lds + i];
   }
   for (int c = tid; c < s; c += NT) zdiag[D.col0 + c] = Z[c * lds + c];
