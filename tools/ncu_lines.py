@@ -20,34 +20,40 @@ h = rows[0]
 names = [(r[h.index("ID")], r[h.index("Kernel Name")], r[h.index("gpu__time_duration.sum")], r[h.index("Grid Size")]) for r in rows[2:]]
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
                      text=True).stdout
-blocks, cur = [], None
+launches, cur, fpath = [], None, None
 for r in csv.reader(src.splitlines()):
     if not r:
         continue
+    if r[0] == "File Path":
+        fpath = r[1]
+        continue
     if r[0] == "Function Name":
-        cur = {"name": r[1], "rows": [], "hdr": None}
-        blocks.append(cur)
+        # one section per (launch, source file): a file seen before in the current group starts the next launch
+        if cur is None or cur["name"] != r[1] or fpath in cur["files"]:
+            cur = {"name": r[1], "files": set(), "rows": []}
+            launches.append(cur)
+        cur["files"].add(fpath)
+        cur["file"], cur["hdr"] = fpath.split("/")[-1], None
     elif r[0] == "Line No" and cur is not None:
         cur["hdr"] = r
-    elif cur is not None and cur["hdr"] is not None and r[0] not in ("File Path",):
-        cur["rows"].append(r)
-for k, b in enumerate(blocks):
+    elif cur is not None and cur.get("hdr") is not None:
+        cur["rows"].append((cur["file"], cur["hdr"], r))
+for k, b in enumerate(launches):
     if not re.search(pat, b["name"]):
         continue
-    hd = b["hdr"]
-    i_line, i_src, i_samp = 0, 1, hd.index("# Samples")
-    agg, text = defaultdict(int), {}
-    for r in b["rows"]:
+    agg, text, last = defaultdict(int), {}, None
+    for fname, hd, r in b["rows"]:
         try:
-            s = int(r[i_samp])
+            s = int(r[hd.index("# Samples")])
         except (ValueError, IndexError):
             continue
-        if r[i_line] not in ("", "-"):
-            last = r[i_line]
-            text[last] = r[i_src]
-        agg[last] += s
+        if r[0] not in ("", "-"):
+            last = (fname, r[0])
+            text[last] = r[1]
+        if last is not None:
+            agg[last] += s
     tot = sum(agg.values()) or 1
     meta = names[k] if k < len(names) else ("?", b["name"], "?", "?")
     print(f"== launch {meta[0]}: {re.sub(r'[(].*', '', b['name'])} grid {meta[3]} duration {meta[2]} samples {tot}")
-    for line, s in sorted(agg.items(), key=lambda kv: -kv[1])[:topn]:
-        print(f"   {100 * s / tot:5.1f}%  L{line:>5}: {text.get(line, '')[:110].strip()}")
+    for (fname, line), s in sorted(agg.items(), key=lambda kv: -kv[1])[:topn]:
+        print(f"   {100 * s / tot:5.1f}%  {fname}:{line:>5}: {text.get((fname, line), '')[:100].strip()}")
