@@ -247,7 +247,7 @@ gmrfb_status btd_run_factor(gmrfb_btd* f) {
   GMRFB_CU(ctx, cudaMemcpyAsync(ctx->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   LaunchAux aux;
   aux.d_info = ctx->d_info;
-  if (f->lookahead && !f->after_block && !ctx->profiling) {
+  if (f->lookahead && !ctx->profiling) {
     // stream 1 (ctx->stream, highest priority): POTRF_i, recording one event per finished 64-column panel of L_i
     // la_stream :  TRSM_{i+1} (C_{i+1} = B_{i+1} L_i^{-T}), every leaf waiting for the panel of L_i it reads and recording
     //              one event per finished column block of C_{i+1}
@@ -273,6 +273,8 @@ gmrfb_status btd_run_factor(gmrfb_btd* f) {
       ar.dinv = f->la_dinv.p + (int64_t)set * setsz;
       rc = run_plan_events(ctx, f->la_potrf, ar, aux, ctx->stream, nullptr, &f->la_ev[set]);
       if (rc != GMRFB_OK) return rc;
+      // time-sharded factor: W_i = L_i^-1 and the spike step of block i are queued on a further lane behind POTRF_i
+      if (f->after_block && (rc = f->after_block(i)) != GMRFB_OK) return rc;
     }
   } else
   for (int64_t i = 0; i < f->N; i++) {

@@ -21,15 +21,25 @@ from . import _lib as B
 from .solver import Context, default_context
 
 
-def slab_bounds(n_blocks: int, world: int):
-    """Contiguous slabs [lo, hi) per rank, sizes as equal as possible (every rank but the last needs >= 2 blocks)."""
-    base, rem = divmod(n_blocks, world)
+def slab_bounds(n_blocks: int, world: int, first_weight: float = 1.0):
+    """Contiguous slabs [lo, hi) per rank (every rank but the last needs >= 2 blocks).  With ``first_weight`` = 1 the
+    sizes are as equal as possible.  Rank 0 has no spike to eliminate — it does 7/3 b^3 flops per block where the other
+    ranks do 19/3 b^3 — so a ``first_weight`` > 1 gives it that many times the blocks of the others and balances the local
+    phases (flop ratio 19/7 = 2.7; measured time ratio per block at b = 4096 on B200: 2.15, which is what bench.py uses)."""
+    if world == 1:
+        return [(0, n_blocks)]
+    if first_weight == 1.0:
+        base, rem = divmod(n_blocks, world)
+        sizes = [base + (1 if r < rem else 0) for r in range(world)]
+    else:
+        per = n_blocks / (first_weight + world - 1)
+        sizes = [max(2, int(round(per))) for _ in range(world)]
+        sizes[0] = n_blocks - sum(sizes[1:])
     out, lo = [], 0
     for r in range(world):
-        hi = lo + base + (1 if r < rem else 0)
-        out.append((lo, hi))
-        lo = hi
-    if any(hi - lo < 2 for lo, hi in out[:-1]) or out[-1][1] - out[-1][0] < 1:
+        out.append((lo, lo + sizes[r]))
+        lo += sizes[r]
+    if any(hi - lo < 2 for lo, hi in out[:-1]) or out[-1][1] - out[-1][0] < 1 or out[-1][1] != n_blocks:
         raise ValueError("too few time blocks for this many ranks")
     return out
 

@@ -234,5 +234,14 @@ def test_slab_bounds(pkg=None):
     assert d.slab_bounds(1024, 8)[-1] == (896, 1024)
     with pytest.raises(ValueError):
         d.slab_bounds(3, 3)
+    # load-balanced split: rank 0 (no spike: 7/3 b^3 per block instead of 19/3) takes 19/7 times the blocks of the others
+    for n, w in ((256, 2), (256, 8), (64, 4), (16, 3)):
+        bb = d.slab_bounds(n, w, first_weight=19.0 / 7.0)
+        sizes = [hi - lo for lo, hi in bb]
+        assert bb[0][0] == 0 and bb[-1][1] == n and all(a[1] == b[0] for a, b in zip(bb, bb[1:]))
+        assert min(sizes) >= 2 and sizes[0] == max(sizes) and max(sizes[1:]) - min(sizes[1:]) == 0
+        if n >= 64:
+            assert abs(sizes[0] / sizes[1] - 19.0 / 7.0) < 0.5
+    assert d.slab_bounds(5, 1, first_weight=3.0) == [(0, 5)]
     assert d.sample_bounds(50, 8) == [(0, 7), (7, 14), (14, 20), (20, 26), (26, 32), (32, 38), (38, 44), (44, 50)]
     assert d.sample_bounds(2, 3) == [(0, 1), (1, 2), (2, 2)]
