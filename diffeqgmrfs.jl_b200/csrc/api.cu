@@ -570,8 +570,7 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
     aux.d_sparent = sym->d_sparent.p;
     return run_plan(ctx, sym->factor_plan, ar, aux);
   };
-  gmrfb_status rc = run_graphed(ctx, fac->graphs, graph_key({1, (uint64_t)(uintptr_t)d_nzval, (uint64_t)(uintptr_t)fac->arena.p,
-                                                             (uint64_t)(uintptr_t)fac->dinv.p}), body);
+  gmrfb_status rc = run_graphed(ctx, sym->graphs, graph_key({1, (uint64_t)(uintptr_t)d_nzval, fac->buffers_key()}), body);
   if (rc != GMRFB_OK) return rc;
   int info = 0;
   GMRFB_CU(ctx, cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -813,9 +812,8 @@ gmrfb_status sweep_panel(gmrfb_fac* fac, bool fwd, bool bwd, int nr) {
     if (r == GMRFB_OK && bwd) r = run_plan(fac->ctx, mp->bwd, ar, aux);
     return r;
   };
-  return run_graphed(fac->ctx, fac->graphs,
-                     graph_key({3, (uint64_t)nr, (uint64_t)fwd, (uint64_t)bwd, (uint64_t)(uintptr_t)fac->mr_x.p,
-                                (uint64_t)(uintptr_t)fac->mr_u.p, (uint64_t)(uintptr_t)fac->arena.p,
+  return run_graphed(fac->ctx, sym->graphs,
+                     graph_key({3, (uint64_t)nr, (uint64_t)fwd, (uint64_t)bwd, fac->buffers_key(),
                                 (uint64_t)(uintptr_t)mp->fwd.tasks.p}), body);
 }
 
@@ -892,10 +890,10 @@ gmrfb_status solve_device(gmrfb_fac* fac, int mode, const double* d_in, int64_t 
       ctx->launches++;
       return GMRFB_OK;
     };
-    gmrfb_status rc = run_graphed(ctx, fac->graphs,
+    gmrfb_status rc = run_graphed(ctx, sym->graphs,
                                   graph_key({2, (uint64_t)mode, (uint64_t)(uintptr_t)(d_in + c0 * ldin), (uint64_t)ldin,
                                              (uint64_t)(uintptr_t)(d_out + c0 * ldout), (uint64_t)ldout, (uint64_t)nr,
-                                             (uint64_t)(uintptr_t)d_mean, (uint64_t)(uintptr_t)fac->arena.p}), body);
+                                             (uint64_t)(uintptr_t)d_mean, fac->buffers_key()}), body);
     if (rc != GMRFB_OK) return rc;
   }
   return GMRFB_OK;
@@ -1078,10 +1076,7 @@ static gmrfb_status selinv_run(gmrfb_fac* fac) {
   aux.d_snodes = sym->d_snodes.p;
   aux.d_child_idx = sym->d_child_idx.p;
   aux.d_sparent = sym->d_sparent.p;
-  rc = run_graphed(ctx, fac->graphs,
-                   graph_key({4, (uint64_t)(uintptr_t)fac->arena.p, (uint64_t)(uintptr_t)fac->zarena.p,
-                              (uint64_t)(uintptr_t)fac->zwork.p, (uint64_t)(uintptr_t)fac->zdiag.p,
-                              (uint64_t)(uintptr_t)fac->dinv_sel.p}),
+  rc = run_graphed(ctx, sym->graphs, graph_key({4, fac->buffers_key()}),
                    [&]() -> gmrfb_status { return run_plan(ctx, sym->selinv_plan, ar, aux); });
   if (rc != GMRFB_OK) return rc;
   fac->z_valid = true;

@@ -266,7 +266,9 @@ gmrfb_status run_plan(gmrfb_ctx* ctx, const DevPlan& P, const Arenas& ar, const 
 // the first execution of a phase with a given set of buffers is captured into a CUDA graph, later executions replay the
 // graph with one launch call (no per-kernel host work, back-to-back scheduling on the device).  `key` identifies
 // everything baked into the captured kernel arguments (buffer addresses, sizes, modes); a different key re-captures.
-// Profiling (per-launch events) bypasses the graphs.
+// The cache belongs to the symbolic handle and is shared by its factors: a new factor that the buffer pool hands the
+// same device buffers (the dataset loop) replays the graphs of its predecessor.  Profiling (per-launch events) bypasses
+// the graphs.
 struct GraphCache {
   struct Ent {
     uint64_t key = 0;
@@ -275,6 +277,9 @@ struct GraphCache {
     uint64_t stamp = 0;
   };
   std::vector<Ent> ents;
+  std::vector<uint64_t> seen;  // keys executed once without a graph: a phase is captured on its SECOND execution, so that
+                               // one-shot factors (a dataset loop that creates a factor per problem) never pay capture +
+                               // instantiation for nothing
   uint64_t clock = 0;
   ~GraphCache() { clear(); }
   void clear() {
@@ -302,6 +307,15 @@ gmrfb_status run_graphed(gmrfb_ctx* ctx, GraphCache& gc, uint64_t key, Body&& bo
       ctx->launches += e.nodes;
       return GMRFB_OK;
     }
+  {
+    bool second = false;
+    for (uint64_t k : gc.seen) second = second || k == key;
+    if (!second) {
+      if (gc.seen.size() >= 64) gc.seen.erase(gc.seen.begin());
+      gc.seen.push_back(key);
+      return body();
+    }
+  }
   const int64_t l0 = ctx->launches;
   GMRFB_CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
   gmrfb_status rc = body();

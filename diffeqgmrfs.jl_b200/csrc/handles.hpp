@@ -36,16 +36,26 @@ struct gmrfb_sym {
     int nr = 0, ldk = 0;
   };
   std::map<int, std::unique_ptr<MrPlans>> mr_plans;
+  // captured numeric phases (factorisation, sweeps, selected inversion) of the factors of this pattern, keyed by every
+  // device buffer the kernels were captured with
+  gmrfb::GraphCache graphs;
 };
 
 struct gmrfb_fac {
   gmrfb_ctx* ctx = nullptr;
   gmrfb_sym* sym = nullptr;
+  // hash of the addresses of every device buffer of this factor (part of every graph key)
+  uint64_t buffers_key() const {
+    return gmrfb::graph_key({(uint64_t)(uintptr_t)arena.p, (uint64_t)(uintptr_t)zarena.p, (uint64_t)(uintptr_t)zwork.p,
+                             (uint64_t)(uintptr_t)zdiag.p, (uint64_t)(uintptr_t)nzval.p, (uint64_t)(uintptr_t)xwork.p,
+                             (uint64_t)(uintptr_t)ywork.p, (uint64_t)(uintptr_t)bwork.p, (uint64_t)(uintptr_t)owork.p,
+                             (uint64_t)(uintptr_t)uvec.p, (uint64_t)(uintptr_t)partial.p, (uint64_t)(uintptr_t)dinv.p,
+                             (uint64_t)(uintptr_t)dinv_sel.p, (uint64_t)(uintptr_t)mr_x.p, (uint64_t)(uintptr_t)mr_u.p});
+  }
   gmrfb::DevBuf<double> arena, zarena, zwork, zdiag, nzval, xwork, ywork, bwork, owork, uvec, partial, dinv, dinv_sel;
   // panel solves: node-major panel X (MR_MAX x n), update panels U (MR_MAX x sum of r_J), column-major staging (n x MR_MAX)
   gmrfb::DevBuf<double> mr_x, mr_u, mr_io;
   gmrfb::DevBuf<double> meanbuf, rbmc_x, refine_ws;  // persistent workspaces of gmrfb_sample / gmrfb_var_rbmc
-  gmrfb::GraphCache graphs;  // captured numeric phases of this factor (factorisation, sweeps, selected inversion)
   bool factored = false, z_valid = false, logdet_valid = false;
   int32_t status = GMRFB_ERR_STATE;
   int64_t fail_column = -1;

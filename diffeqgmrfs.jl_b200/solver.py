@@ -565,7 +565,10 @@ class CholeskySolver:
 
     def __init__(self, gmrf, blueprint: CholeskySolverBlueprint, symbolic: Symbolic | None = None, values_dev: int = 0,
                  precision_dev: "SparseMatrix | None" = None):
-        self.gmrf = gmrf
+        # no back-reference to the GMRF: a GMRF <-> solver cycle would leave the factor's GBs of device memory to the
+        # cyclic garbage collector instead of freeing them (into the buffer pool) when the GMRF goes out of scope
+        self.n, self._Q = gmrf.n, gmrf.precision
+        self._prior_mean, self._information = gmrf.prior_mean, gmrf.information
         self.blueprint = blueprint
         self._precision_dev = precision_dev  # the precision as a device matrix, when the caller already has one
         Q = gmrf.precision
@@ -579,30 +582,29 @@ class CholeskySolver:
 
     def compute_mean(self):
         if self._mean is None:
-            g = self.gmrf
-            if g.information is None:
-                self._mean = g.prior_mean
+            if self._information is None:
+                self._mean = self._prior_mean
             else:
-                self._mean = g.prior_mean + self.precision_chol.solve(g.information)
+                self._mean = self._prior_mean + self.precision_chol.solve(self._information)
         return self._mean
 
     def compute_variance(self):
         if self._var is None:
             vs = self.blueprint.var_strategy
             if isinstance(vs, RBMCStrategy):
-                Z = vs.normals(self.gmrf.n, self.precision_chol.ctx.device)
+                Z = vs.normals(self.n, self.precision_chol.ctx.device)
                 # the posterior precision assembled on the device is used where it lies (no upload, no row-wise copy)
                 # (only while it still holds THIS posterior: a later conditioning on the same prior overwrites its values)
                 pd = self._precision_dev
                 Qd = pd[0] if (pd is not None and pd[1].generation == pd[2]) else \
-                    SparseMatrix(self.gmrf.precision, ctx=self.precision_chol.ctx)
+                    SparseMatrix(self._Q, ctx=self.precision_chol.ctx)
                 self._var = self.precision_chol.var_rbmc(Qd, Z)
             else:
                 self._var = self.precision_chol.var_selinv()
         return self._var
 
     def compute_rand(self, rng):
-        z = rng.standard_normal(self.gmrf.n)
+        z = rng.standard_normal(self.n)
         return self.precision_chol.sample(z, mean=self.compute_mean())
 
 

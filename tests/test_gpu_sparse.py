@@ -320,6 +320,41 @@ def test_dataset_loop_reuses_workspace(pkg, orc, ctx, W):
         assert rel(pkg.var(xc), ref.selinv_diag()) < TOL_VAR
 
 
+def test_dataset_loop_frees_factors_and_replays_graphs(pkg, orc, ctx, W):
+    """The dataset loop as the reference script writes it (``x_k = condition_on_observations(...)`` rebinding one
+    name): the factor of the previous problem is released by reference counting alone (no GMRF <-> solver cycle left
+    to the cyclic collector), its buffers come back from the pool for the next factor, and that factor replays the
+    CUDA graphs captured for its predecessor (cache shared through the symbolic handle, keyed by every buffer
+    address).  Every posterior must still match the oracle - a stale pointer in a replayed graph would show here."""
+    import gc
+    import weakref
+    P0 = W.darcy_problem(23, seed=0, q_eps=1e4)
+    n = P0["Q"].shape[0]
+    x = pkg.GMRF(np.zeros(n), P0["Q"], pkg.CholeskySolverBlueprint(coords=P0["nodes"], ctx=ctx))
+    first = pkg.condition_on_observations(x, P0["A"], P0["q_eps"], P0["y"])
+    p = first.solver_ref[()].precision_chol.p
+    bp = pkg.CholeskySolverBlueprint(var_strategy=pkg.RBMCStrategy(600, rng=np.random.default_rng(5)), perm=p, ctx=ctx)
+    gc.collect()
+    gc.disable()
+    try:
+        xk, prev = None, None
+        for k in range(7):
+            Pk = W.darcy_problem(23, seed=k, q_eps=1e4)
+            xk = pkg.condition_on_observations(x, Pk["A"], Pk["q_eps"], Pk["y"], solver_blueprint=bp)
+            if prev is not None:
+                assert prev() is None  # the previous factor went with its GMRF, without the cyclic collector
+            prev = weakref.ref(xk.solver_ref[()].precision_chol)
+            Qp = orc.posterior_precision(Pk["Q"], Pk["A"], Pk["q_eps"])
+            ref = orc.SparseCholesky(Qp, p)
+            mref = orc.posterior_mean(ref, Pk["Q"], Pk["A"], Pk["q_eps"], Pk["y"], np.zeros(n))
+            assert rel(pkg.mean(xk), mref) < 1e-9
+            vref = ref.selinv_diag()
+            assert np.median(np.abs(pkg.var(xk) - vref) / vref) < 0.1  # RBMC-600 (panel sweeps, graphed)
+            assert rel(xk.solver_ref[()].precision_chol.var_selinv(), vref) < TOL_VAR
+    finally:
+        gc.enable()
+
+
 def test_device_gauss_newton_matches_host_loop(pkg, orc, ctx, W):
     """gmrfb_gn_*: the whole Gauss-Newton iteration of scripts/solve_burger.jl:143-180 on the device for the bilinear
     Burgers residual, against (a) the host-driven GaussNewtonOptimizer and (b) the oracle's restated loop."""
