@@ -111,6 +111,12 @@ SIGNATURES = {
     "gmrfb_fem_set_coeff_grid": (C.c_int32, [_P, C.c_int64, _F64P, C.c_int64, _F64P]),
     "gmrfb_fem_assemble": (C.c_int32, [_P, _P, _P, C.POINTER(_P)]),
     "gmrfb_fem_matern_precision": (C.c_int32, [_P, C.c_double, C.c_double, _P, C.c_double, C.POINTER(_P)]),
+    "gmrfb_fem_assemble_cubic": (C.c_int32, [_P, _P, C.c_int32, C.c_double, _P, C.POINTER(_P), _P]),
+    "gmrfb_fem1d_create": (C.c_int32, [_P, C.c_int64, C.c_int64, _I64P, _F64P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "gmrfb_fem1d_destroy": (C.c_int32, [_P]),
+    "gmrfb_fem1d_mass_stiffness": (C.c_int32, [_P, C.c_int32, _P, C.POINTER(_P), C.POINTER(_P)]),
+    "gmrfb_fem1d_advection": (C.c_int32, [_P, _P, _P, C.POINTER(_P), _P]),
+    "gmrfb_fem1d_spacetime_tangent": (C.c_int32, [_P, C.c_int64, C.c_double, C.c_double, _P, _P, C.POINTER(_P), _P]),
     "gmrfb_gn_create": (C.c_int32, [_P, _P, C.c_int64, _I64P, _I64P, _F64P, _F64P, _F64P, _F64P, C.c_int32, C.c_double, C.c_double,
                                     _F64P, _F64P, _I64P, C.POINTER(AnalyzeOpts), C.POINTER(_P)]),
     "gmrfb_gn_optimize": (C.c_int32, [_P, _F64P, C.c_int32, C.c_double, C.POINTER(C.c_int32), _F64P]),

@@ -2,7 +2,10 @@
 //   * the Darcy stiffness G(a) = sum_T a_T K_T of a new coefficient field for every problem of the dataset loop
 //     (src/problems/darcy.jl:5-63 assemble_darcy_diff_matrix; coefficient looked up by nearest grid index,
 //     src/datasets/darcy.jl:30-34; called from form_observations in scripts/darcy/solve_darcy_gmrf-fem.jl:104-137,178);
-//   * the Matern prior precision Q = ratio * K' Mt^-1 K, K = kappa^2 Mt + G (src/spdes/shallow_water.jl:177-194).
+//   * the Matern prior precision Q = ratio * K' Mt^-1 K, K = kappa^2 Mt + G (src/spdes/shallow_water.jl:177-194);
+//   * the Gauss-Newton tangent of the cubic reaction term, J = s G + 3 int u^2 phi_i phi_j and
+//     f = s G u + int u^3 phi_i, by quadrature of the current iterate (_research/elliptic_chen24.jl:180-285
+//     assemble_J_diff_and_f / assemble_J_cube / f_and_J), reassembled at every Gauss-Newton step.
 // The mesh is analysed once on the host (pattern of the stiffness matrix, the list of element entries that fall on
 // every nonzero, the grid cell of every element); every assembly is then one gather kernel over the nonzeros —
 // deterministic (fixed summation order), no atomics — writing straight into a device matrix that the posterior-
@@ -13,6 +16,7 @@
 #include <numeric>
 
 #include "common.hpp"
+#include "fem_pattern.hpp"
 #include "handles.hpp"
 
 using namespace gmrfb;
@@ -28,6 +32,7 @@ struct gmrfb_fem {
   gmrfb_spm G;  // stiffness pattern (n x n, full symmetric storage), values of the last assembly
   gmrfb_spm K;  // same pattern: kappa^2 Mt + G of the last Matern call
   gmrfb_spm Z;  // empty n x n matrix (the "Q" of the posterior-precision plan that forms K' W K)
+  gmrfb_spm J;  // same pattern: tangent of the last gmrfb_fem_assemble_cubic call
   bool G_built = false, K_built = false;
   DevBuf<double> d_kloc;   // nt x 9: geometric element matrices (unit coefficient), entry t * 9 + 3 i + j
   DevBuf<double> d_area;   // nt
@@ -39,6 +44,10 @@ struct gmrfb_fem {
   DevBuf<double> d_coeff;  // staged coefficient grid
   DevBuf<uint8_t> d_presc; // nn: prescribed (Dirichlet) dofs of the last call
   DevBuf<double> d_w;      // nn: ratio / Mt
+  DevBuf<int32_t> d_tris;  // 3 nt: vertices of every element
+  DevBuf<double> d_u, d_f; // nn: staged iterate / residual of the cubic tangent
+  DevBuf<double> d_quad;   // 4 nq: barycentric quadrature points and weights of the last requested degree
+  int quad_degree = 0, nq = 0;
   std::vector<double> centroid;  // 2 nt (host): element centroids = the quadrature points of the P1 rule
   std::vector<double> mass;      // nn (host copy)
   int64_t ncell = 0;
@@ -121,6 +130,85 @@ __global__ void k_fem_matern_k(int64_t nn, const int64_t* __restrict__ diag, con
   w[i] = ratio / mt;
 }
 
+// Tangent of the cubic term (_research/elliptic_chen24.jl:231-278) fused with s * stiffness (:180-228), one thread per
+// nonzero: J[k] = sum over the element entries (t, i, j) on k of  s K_t[i, j] + 3 |t| sum_q w_q l_i(q) l_j(q) u_q^2,
+// u_q = sum_k u[v_k] l_k(q); rows of prescribed dofs are skipped (stay zero) as the reference's `continue` does.
+__global__ void k_fem_cubic_J(int64_t nnz, const int64_t* __restrict__ cptr, const int32_t* __restrict__ cidx,
+                              const double* __restrict__ kloc, const double* __restrict__ area,
+                              const int32_t* __restrict__ tris, const double* __restrict__ u,
+                              const int32_t* __restrict__ rowidx, const uint8_t* __restrict__ presc, double s,
+                              const double* __restrict__ quad, int nq, double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  if (presc && presc[rowidx[k]]) {
+    out[k] = 0.0;
+    return;
+  }
+  double v = 0.0;
+  for (int64_t p = cptr[k]; p < cptr[k + 1]; p++) {
+    const int32_t e = cidx[p];
+    const int32_t t = e / 9, i = (e % 9) / 3, j = e % 3;
+    const double w0 = u[tris[3 * t]], w1 = u[tris[3 * t + 1]], w2 = u[tris[3 * t + 2]];
+    double acc = 0.0;
+    for (int q = 0; q < nq; q++) {
+      const double* l = quad + 4 * q;
+      const double uq = l[0] * w0 + l[1] * w1 + l[2] * w2;
+      acc += l[3] * l[i] * l[j] * uq * uq;
+    }
+    v += s * kloc[e] + 3.0 * area[t] * acc;
+  }
+  out[k] = v;
+}
+
+// f[i] = sum over the elements t at node i (local index a) of  s sum_j K_t[a, j] u_j + |t| sum_q w_q l_a(q) u_q^3
+// (gathered through the diagonal's contribution list: one entry per element at i); prescribed rows stay zero
+__global__ void k_fem_cubic_f(int64_t nn, const int64_t* __restrict__ diag, const int64_t* __restrict__ cptr,
+                              const int32_t* __restrict__ cidx, const double* __restrict__ kloc,
+                              const double* __restrict__ area, const int32_t* __restrict__ tris,
+                              const double* __restrict__ u, const uint8_t* __restrict__ presc, double s,
+                              const double* __restrict__ quad, int nq, double* __restrict__ f) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  if (presc && presc[i]) {
+    f[i] = 0.0;
+    return;
+  }
+  const int64_t k = diag[i];
+  double v = 0.0;
+  for (int64_t p = cptr[k]; p < cptr[k + 1]; p++) {
+    const int32_t e = cidx[p];
+    const int32_t t = e / 9, a = e % 3;
+    const double w0 = u[tris[3 * t]], w1 = u[tris[3 * t + 1]], w2 = u[tris[3 * t + 2]];
+    double acc = 0.0;
+    for (int q = 0; q < nq; q++) {
+      const double* l = quad + 4 * q;
+      const double uq = l[0] * w0 + l[1] * w1 + l[2] * w2;
+      acc += l[3] * l[a] * uq * uq * uq;
+    }
+    const double* kr = kloc + 9 * (int64_t)t + 3 * a;
+    v += s * (kr[0] * w0 + kr[1] * w1 + kr[2] * w2) + area[t] * acc;
+  }
+  f[i] = v;
+}
+
+// symmetric triangle rules exact to degree 1, 2 (3 interior points: QuadratureRule{RefTriangle}(2)) and 4 (6 points);
+// rows: barycentric coordinates l0, l1, l2 and the weight (weights sum to 1: d Omega = weight * area)
+std::vector<double> tri_rule(int degree) {
+  if (degree == 1) return {1.0 / 3, 1.0 / 3, 1.0 / 3, 1.0};
+  if (degree == 2) {
+    const double a = 1.0 / 6, b = 2.0 / 3, w = 1.0 / 3;
+    return {b, a, a, w, a, b, a, w, a, a, b, w};
+  }
+  std::vector<double> r;
+  const double as[2] = {0.445948490915965, 0.091576213509771}, ws[2] = {0.223381589678011, 0.109951743655322};
+  for (int g = 0; g < 2; g++) {
+    const double a = as[g], b = 1.0 - 2.0 * a, w = ws[g];
+    const double rows[12] = {b, a, a, w, a, b, a, w, a, a, b, w};
+    r.insert(r.end(), rows, rows + 12);
+  }
+  return r;
+}
+
 }  // namespace
 
 extern "C" gmrfb_status gmrfb_fem_create(gmrfb_ctx* ctx, int64_t nnodes, const double* nodes, int64_t ntri,
@@ -146,48 +234,25 @@ extern "C" gmrfb_status gmrfb_fem_create(gmrfb_ctx* ctx, int64_t nnodes, const d
     for (int c = 0; c < 2; c++)
       F->centroid[2 * t + c] = (nodes[2 * (int64_t)tr[3 * t] + c] + nodes[2 * (int64_t)tr[3 * t + 1] + c] +
                                 nodes[2 * (int64_t)tr[3 * t + 2] + c]) / 3.0;
-  // pattern: one (row, col) pair per element entry, sorted by (col, row, element entry)
+  // pattern of the stiffness matrix and the element entries that fall on every nonzero
   const int64_t ne = 9 * ntri;
-  std::vector<int64_t> key((size_t)ne);
-  std::vector<int32_t> ord((size_t)ne);
-  std::iota(ord.begin(), ord.end(), 0);
-  for (int64_t t = 0; t < ntri; t++)
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) key[9 * t + 3 * i + j] = (int64_t)tr[3 * t + j] * nnodes + tr[3 * t + i];
-  std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return key[a] < key[b] || (key[a] == key[b] && a < b); });
-  std::vector<int64_t> colptr((size_t)nnodes + 1, 0), rowval, cptr, diag((size_t)nnodes, -1);
-  std::vector<int32_t> cidx((size_t)ne);
-  rowval.reserve((size_t)ne / 2);
-  cptr.reserve((size_t)ne / 2);
-  int64_t prev = -1;
-  for (int64_t q = 0; q < ne; q++) {
-    const int32_t e = ord[q];
-    if (key[e] != prev) {
-      prev = key[e];
-      const int64_t c = prev / nnodes, r = prev % nnodes;
-      if (r == c) diag[c] = (int64_t)rowval.size();
-      rowval.push_back(r);
-      cptr.push_back(q);
-      colptr[c + 1]++;
-    }
-    cidx[q] = e;
-  }
-  cptr.push_back(ne);
-  for (int64_t c = 0; c < nnodes; c++) {
-    if (diag[c] < 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem_create: a node belongs to no element");
-    colptr[c + 1] += colptr[c];
-  }
+  ElementPattern P;
+  if (!build_element_pattern(nnodes, ntri, 3, tr.data(), P))
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem_create: a node belongs to no element");
+  const std::vector<int64_t>&colptr = P.colptr, &rowval = P.rowval, &cptr = P.cptr, &diag = P.diag;
+  const std::vector<int32_t>& cidx = P.cidx;
   gmrfb_status rc = spm_build(ctx, &F->G, nnodes, nnodes, colptr.data(), rowval.data(), nullptr, 0);
   if (rc != GMRFB_OK) return rc;
   if ((rc = spm_build(ctx, &F->K, nnodes, nnodes, colptr.data(), rowval.data(), nullptr, 0)) != GMRFB_OK) return rc;
+  if ((rc = spm_build(ctx, &F->J, nnodes, nnodes, colptr.data(), rowval.data(), nullptr, 0)) != GMRFB_OK) return rc;
   {
     std::vector<int64_t> zp((size_t)nnodes + 1, 0);
     if ((rc = spm_build(ctx, &F->Z, nnodes, nnodes, zp.data(), nullptr, nullptr, 0)) != GMRFB_OK) return rc;
   }
-  F->G.owned_by_plan = F->K.owned_by_plan = F->Z.owned_by_plan = true;  // borrowed views: not destroyed by the caller
+  F->G.owned_by_plan = F->K.owned_by_plan = F->J.owned_by_plan = F->Z.owned_by_plan = true;  // borrowed views: not destroyed by the caller
   cudaStream_t st = ctx->stream;
   DevBuf<double> d_nodes;
-  DevBuf<int32_t> d_tris;
+  DevBuf<int32_t>& d_tris = F->d_tris;
   {
     std::vector<double> nd(nodes, nodes + 2 * nnodes);
     GMRFB_CU(ctx, d_nodes.upload(nd, st));
@@ -329,4 +394,51 @@ extern "C" gmrfb_status gmrfb_fem_matern_precision(gmrfb_fem* F, double kappa, d
     if (rc != GMRFB_OK) return rc;
   }
   return gmrfb_postprec_compute(F->matern_plan, 0.0, F->d_w.p, Q_out);
+}
+
+extern "C" gmrfb_status gmrfb_fem_assemble_cubic(gmrfb_fem* F, const double* u, int32_t quad_degree,
+                                                 double stiffness_scale, const uint8_t* prescribed,
+                                                 const gmrfb_spm** J_out, double* f_out) {
+  if (!F || !u) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem_assemble_cubic: NULL argument");
+  gmrfb_ctx* ctx = F->ctx;
+  if (quad_degree != 1 && quad_degree != 2 && quad_degree != 4)
+    return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem_assemble_cubic: quad_degree must be 1, 2 or 4");
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (F->quad_degree != quad_degree) {
+    const std::vector<double> r = tri_rule(quad_degree);
+    GMRFB_CU(ctx, cudaStreamSynchronize(st));  // a previous call may still read the old table
+    GMRFB_CU(ctx, F->d_quad.upload(r, st));
+    GMRFB_CU(ctx, cudaStreamSynchronize(st));  // `r` is a pageable temporary
+    F->quad_degree = quad_degree;
+    F->nq = (int)(r.size() / 4);
+  }
+  if (!F->d_u.p) {
+    GMRFB_CU(ctx, F->d_u.alloc((size_t)F->nn));
+    GMRFB_CU(ctx, F->d_f.alloc((size_t)F->nn));
+  }
+  GMRFB_CU(ctx, cudaMemcpyAsync(F->d_u.p, u, F->nn * sizeof(double), cudaMemcpyDefault, st));  // host or device
+  gmrfb_status rc = fem_upload_presc(F, prescribed);
+  if (rc != GMRFB_OK) return rc;
+  const uint8_t* pr = prescribed ? F->d_presc.p : nullptr;
+  {
+    ProfScope ps(ctx, PK_FEM, 0, 12.0 * 9 * F->nt + 8.0 * F->J.nnz, 0, 0);
+    k_fem_cubic_J<<<(unsigned)((F->J.nnz + 255) / 256), 256, 0, st>>>(F->J.nnz, F->d_cptr.p, F->d_cidx.p, F->d_kloc.p,
+                                                                     F->d_area.p, F->d_tris.p, F->d_u.p, F->J.d_rowidx.p,
+                                                                     pr, stiffness_scale, F->d_quad.p, F->nq, F->J.d_val.p);
+  }
+  GMRFB_CU(ctx, cudaGetLastError());
+  GMRFB_CU(ctx, launch_gather_values(F->J.d_val.p, F->J.d_tmap.p, F->J.nnz, F->J.d_tval.p, st));
+  ctx->launches += 2;
+  if (f_out) {
+    k_fem_cubic_f<<<(unsigned)((F->nn + 255) / 256), 256, 0, st>>>(F->nn, F->d_diag.p, F->d_cptr.p, F->d_cidx.p, F->d_kloc.p,
+                                                                  F->d_area.p, F->d_tris.p, F->d_u.p, pr, stiffness_scale,
+                                                                  F->d_quad.p, F->nq, F->d_f.p);
+    GMRFB_CU(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    GMRFB_CU(ctx, cudaMemcpyAsync(f_out, F->d_f.p, F->nn * sizeof(double), cudaMemcpyDefault, st));
+  }
+  GMRFB_CU(ctx, cudaStreamSynchronize(st));
+  if (J_out) *J_out = &F->J;
+  return GMRFB_OK;
 }

@@ -248,6 +248,109 @@ class FEMP1:
         return M
 
 
+    def assemble_cubic(self, u, prescribed=None, quad_degree=2, stiffness_scale=1.0, out=None):
+        """Gauss-Newton tangent and residual of ``-lap u + u^3`` at the iterate ``u`` (``f_and_J`` of
+        _research/elliptic_chen24.jl:280-285 without the static load vector): returns ``(f, J)`` with
+        ``J = s G + 3 int u^2 phi_i phi_j`` (device matrix owned by this object) and ``f = s G u + int u^3 phi_i``,
+        rows of ``prescribed`` dofs skipped.  ``u`` / ``out``: NumPy arrays or CUDA float64 tensors."""
+        up, _keep_u = _vec_ptr(u, self.n)
+        if out is None:
+            out = np.empty(self.n)
+        fp, _keep_f = _vec_ptr(out, self.n)
+        J = C.c_void_p()
+        B.check(B.lib().gmrfb_fem_assemble_cubic(self.h, up, int(quad_degree), float(stiffness_scale),
+                                                 self._presc(prescribed), C.byref(J), fp), self.ctx.h)
+        M = SparseMatrix(None, ctx=self.ctx, _handle=J, _owner=self)
+        M.shape = (self.n, self.n)
+        return out, M
+
+
+def _vec_ptr(v, n):
+    """(pointer, keep-alive) of a length-n float64 vector: NumPy (host) or a contiguous CUDA tensor (device)."""
+    if hasattr(v, "data_ptr"):
+        assert v.is_cuda and v.is_contiguous() and str(v.dtype) == "torch.float64" and v.numel() == n
+        _torch_ready(v)
+        return C.c_void_p(v.data_ptr()), v
+    assert isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.c_contiguous and v.size == n, \
+        "expected a contiguous float64 vector of length %d" % n
+    return C.c_void_p(v.ctypes.data), v
+
+
+class FEM1D:
+    """Lagrange line elements of order 1 or 2 on the device (gmrfb_fem1d) for the Burgers Gauss-Newton loop:
+    ``assemble_burgers_mass_diffusion_matrices`` / ``assemble_burgers_advection_matrix`` (src/problems/burgers.jl:5-98)
+    and the space-time ``f_and_J`` of scripts/burgers/solve_burgers_gmrf-fem.jl:115-142 in one kernel.
+    ``elems``: E x (order + 1) node ids (0-based; quadratic: left, right, middle); ``x``: either the n node
+    coordinates or, for a periodic mesh whose last element closes the ring, the E x (order + 1) coordinates of the
+    element nodes."""
+
+    def __init__(self, x, elems, order=1, nquad=0, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        elems = np.ascontiguousarray(elems)
+        assert elems.ndim == 2 and elems.shape[1] == order + 1
+        x = np.asarray(x, dtype=np.float64)
+        xe = x if x.ndim == 2 else x[elems]
+        assert xe.shape == elems.shape
+        xe, xp = B.f64(np.ascontiguousarray(xe).reshape(-1))
+        el, ep = B.i64(elems.reshape(-1))
+        self.n, self.order = int(elems.max()) + 1, order
+        h = C.c_void_p()
+        B.check(B.lib().gmrfb_fem1d_create(self.ctx.h, self.n, elems.shape[0], ep, xp, int(order), 0, int(nquad),
+                                           C.byref(h)), self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_fem1d_destroy, h)
+        self._presc_keep = None
+
+    @classmethod
+    def periodic_unit_interval(cls, n_elems, order=2, **kw):
+        """``periodic_unit_interval_discretization(N_x; element_order)`` (src/utils.jl:42-49) with the periodic
+        constraint condensed into the connectivity: the last element closes the ring (no slave dof)."""
+        from .workloads import periodic_line_mesh
+
+        x, el = periodic_line_mesh(n_elems, order)
+        return cls(x, el, order=order, **kw)
+
+    def _presc(self, prescribed):
+        if prescribed is None:
+            return None
+        self._presc_keep = np.ascontiguousarray(np.asarray(prescribed) != 0, dtype=np.uint8)
+        assert self._presc_keep.size == self.n
+        return C.c_void_p(self._presc_keep.ctypes.data)
+
+    def _wrap(self, h, shape):
+        M = SparseMatrix(None, ctx=self.ctx, _handle=h, _owner=self)
+        M.shape = shape
+        return M
+
+    def mass_stiffness(self, lumping=False, prescribed=None):
+        M, G = C.c_void_p(), C.c_void_p()
+        B.check(B.lib().gmrfb_fem1d_mass_stiffness(self.h, int(bool(lumping)), self._presc(prescribed), C.byref(M),
+                                                   C.byref(G)), self.ctx.h)
+        return self._wrap(M, (self.n, self.n)), self._wrap(G, (self.n, self.n))
+
+    def advection(self, u, prescribed=None, out=None):
+        """``(G_adv, v)`` of ``assemble_burgers_advection_matrix(disc, u)``."""
+        up, _ku = _vec_ptr(u, self.n)
+        if out is None:
+            out = np.empty(self.n)
+        vp, _kv = _vec_ptr(out, self.n)
+        A = C.c_void_p()
+        B.check(B.lib().gmrfb_fem1d_advection(self.h, up, self._presc(prescribed), C.byref(A), vp), self.ctx.h)
+        return self._wrap(A, (self.n, self.n)), out
+
+    def spacetime_tangent(self, w, nt, dt, nu, prescribed=None, out=None):
+        """``(f, J)`` of the script's ``f_and_J(w)``: ``w`` time-major with ``nt`` steps; J is a device matrix
+        ((nt-1) n x nt n, fixed pattern, values of the last call) owned by this object."""
+        wp, _kw = _vec_ptr(w, nt * self.n)
+        if out is None:
+            out = np.empty((nt - 1) * self.n)
+        fp, _kf = _vec_ptr(out, (nt - 1) * self.n)
+        J = C.c_void_p()
+        B.check(B.lib().gmrfb_fem1d_spacetime_tangent(self.h, int(nt), float(dt), float(nu), wp, self._presc(prescribed),
+                                                      C.byref(J), fp), self.ctx.h)
+        return out, self._wrap(J, ((nt - 1) * self.n, nt * self.n))
+
+
 # ------------------------------------------------------------------------------------ symbolic + numeric --
 class Symbolic:
     """Symbolic analysis of one sparsity pattern (gmrfb_sym).  ``perm`` is 0-based new->old (Julia's
@@ -748,11 +851,18 @@ class GaussNewtonOptimizer:
     def step(self):
         ctx = self.bp.ctx or default_context()
         fx, J = self.f_and_J(self.xk)
-        J = _csc(J)
+        # f_and_J may assemble its tangent on the device (FEMP1.assemble_cubic, FEM1D.spacetime_tangent): the matrix is
+        # then a fixed-pattern SparseMatrix whose values were just overwritten in place - no upload, no host SpGEMM
+        on_device = isinstance(J, SparseMatrix)
+        if not on_device:
+            J = _csc(J)
         if self._plan is None:
             self._Qd = SparseMatrix(self.Q_prior, ctx=ctx)
-            self._Jd = SparseMatrix(J, ctx=ctx)
+            self._Jd = J if on_device else SparseMatrix(J, ctx=ctx)
             self._plan = PosteriorPrecision(self._Qd, self._Jd)
+        elif on_device:
+            if J.h.value != self._Jd.h.value:
+                raise ValueError("f_and_J must return the same device matrix (fixed pattern) at every iteration")
         else:
             self._Jd.set_values(J.data)
         Apost = self._plan.compute(self.noise)
@@ -761,9 +871,14 @@ class GaussNewtonOptimizer:
             self._sym = Symbolic(pat, perm=self.bp.perm, coords=self.bp.coords, ctx=ctx)
             self._fac = CholeskyFactor(self._sym)
         self._fac.factorize_dev(Apost.values_dev())
-        rhs = self.Q_prior @ self.mu + self.noise * (J.T @ (J @ self.xk + (self.y - fx)))
+        fx = np.asarray(fx, dtype=np.float64)
+        if on_device:
+            lin = self._Jd.matvec(self.xk) + (self.y - fx)
+            rhs = self.Q_prior @ self.mu + self.noise * self._Jd.matvec(lin, trans=True)
+        else:
+            rhs = self.Q_prior @ self.mu + self.noise * (J.T @ (J @ self.xk + (self.y - fx)))
         self.xk = self._fac.solve(rhs)
-        self.Jk = J
+        self.Jk = J  # a device tangent holds the values of the LAST f_and_J evaluation
         self._Apost = Apost
         return self.xk
 

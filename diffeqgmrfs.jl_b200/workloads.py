@@ -30,6 +30,21 @@ def structured_mesh(nx: int, ny: int | None = None, jitter: float = 0.2, seed: i
     return nodes, tris
 
 
+def periodic_line_mesh(n_elems: int, order: int = 2):
+    """Periodic mesh of the unit interval with `n_elems` Lagrange lines of `order` 1 or 2
+    (periodic_unit_interval_discretization, src/utils.jl:42-49, with the periodic constraint condensed: the last
+    element closes the ring, node 0 stands for x = 0 and x = 1).  Returns (xe, elems): quadratic elements are numbered
+    (left, right, middle), the `n_elems` vertex nodes come first; xe holds the coordinates per element node
+    (E x (order + 1)) because the shared node 0 has coordinate 1 as the right end of the last element."""
+    h = 1.0 / n_elems
+    left = np.arange(n_elems)
+    right = (left + 1) % n_elems
+    if order == 1:
+        return np.stack([left * h, (left + 1) * h], axis=1), np.stack([left, right], axis=1)
+    mid = n_elems + left
+    return np.stack([left * h, (left + 1) * h, (left + 0.5) * h], axis=1), np.stack([left, right, mid], axis=1)
+
+
 def p1_mass_stiffness(nodes, tris, coeff=None):
     """Lumped mass vector and stiffness matrix of P1 elements; `coeff` is an optional per-triangle diffusion
     coefficient (the piecewise-constant Darcy coefficient, src/problems/darcy.jl:39)."""

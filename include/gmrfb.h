@@ -308,6 +308,50 @@ gmrfb_status gmrfb_fem_assemble(gmrfb_fem* fem, const double* coeff_grid, const 
 gmrfb_status gmrfb_fem_matern_precision(gmrfb_fem* fem, double kappa, double ratio, const uint8_t* prescribed,
                                         double prescribed_mass, const gmrfb_spm** Q_out);
 
+/* Gauss-Newton tangent of the cubic reaction term -lap u + u^3 = g by quadrature of the current iterate
+ * (_research/elliptic_chen24.jl: assemble_J_diff_and_f :180-228, assemble_J_cube :231-278, f_and_J :280-285):
+ *     J = s G + J_cube,  J_cube[i,j] = sum_q 3 phi_i u_q^2 phi_j dOmega,
+ *     f = s G u + f_cube,  f_cube[i] = sum_q phi_i u_q^3 dOmega      (the caller subtracts its static load vector),
+ * s = stiffness_scale (0: the cubic part alone, as assemble_J_cube returns it).  Rows of prescribed dofs are skipped
+ * (stay zero) in both parts, as the reference's `continue` does (:207-209,:259-261).  u: nnodes doubles, host or
+ * device; quad_degree in {1, 2, 4}: symmetric triangle rule exact to that degree (2 = the 3-point rule of
+ * QuadratureRule{RefTriangle}(2), :121).  *J_out is owned by the handle (pattern of the stiffness matrix, values of
+ * the last call); f_out (nnodes doubles, host or device) may be NULL. */
+gmrfb_status gmrfb_fem_assemble_cubic(gmrfb_fem* fem, const double* u, int32_t quad_degree, double stiffness_scale,
+                                      const uint8_t* prescribed, const gmrfb_spm** J_out, double* f_out);
+
+/* ------------------------------------------- 1-D finite elements (Burgers) --- */
+/* Lagrange line elements of order 1 or 2 (quadratic lines numbered left, right, middle as Ferrite's QuadraticLine;
+ * periodic_unit_interval_discretization, src/utils.jl:42-49, uses order 2 with QuadratureRule{RefLine}(order + 1)):
+ *   assemble_burgers_mass_diffusion_matrices(disc; lumping)   src/problems/burgers.jl:61-98  -> gmrfb_fem1d_mass_stiffness
+ *   assemble_burgers_advection_matrix(disc, cur_weights)      src/problems/burgers.jl:5-59   -> gmrfb_fem1d_advection
+ *   f_and_J of the Gauss-Newton loop (J_static + dt J_adv over all time steps)
+ *                              scripts/burgers/solve_burgers_gmrf-fem.jl:115-142              -> gmrfb_fem1d_spacetime_tangent
+ *   elems : nelem x (order + 1) node indices (`base`-based), element-major;  elem_x : the coordinates of those nodes,
+ *   same layout (per element, so that the last element of a periodic mesh can close the ring: its right end has
+ *   coordinate 1 while the node it shares with the first element has coordinate 0).
+ *   nquad: Gauss-Legendre points per element (0: order + 1; at most 4).
+ * prescribed (optional, nnodes bytes): rows and columns of those dofs are zero in every matrix and their vector
+ * entries are zero (apply! followed by the explicit zeroing of :53-57,:88-93).  Returned matrices are owned by the
+ * handle (fixed pattern, values of the last call). */
+typedef struct gmrfb_fem1d gmrfb_fem1d;
+gmrfb_status gmrfb_fem1d_create(gmrfb_ctx* ctx, int64_t nnodes, int64_t nelem, const int64_t* elems, const double* elem_x,
+                                int32_t order, int32_t base, int32_t nquad, gmrfb_fem1d** out);
+gmrfb_status gmrfb_fem1d_destroy(gmrfb_fem1d* fem);
+/* M = int phi_i phi_j (lumping != 0: diagonal of its row sums), G = int phi_i' phi_j' */
+gmrfb_status gmrfb_fem1d_mass_stiffness(gmrfb_fem1d* fem, int32_t lumping, const uint8_t* prescribed,
+                                        const gmrfb_spm** M_out, const gmrfb_spm** G_out);
+/* A[i,j] = sum_q phi_i (phi_j u_x + u phi_j') dOmega, v[i] = sum_q phi_i u u_x dOmega for the iterate u (nnodes
+ * doubles, host or device); v_out (host or device) may be NULL */
+gmrfb_status gmrfb_fem1d_advection(gmrfb_fem1d* fem, const double* u, const uint8_t* prescribed, const gmrfb_spm** A_out,
+                                   double* v_out);
+/* w: nt * nnodes doubles, time-major (step t = entries [t nnodes, (t+1) nnodes)), host or device.
+ * J ((nt-1) nnodes x nt nnodes): block (t, t) = -M, block (t, t+1) = M + dt nu G + dt A(w_{t+1}), t = 0 .. nt-2;
+ * f = J_static w + dt [v(w_1); ...; v(w_{nt-1})] ((nt-1) nnodes doubles, host or device, may be NULL).  One kernel
+ * writes all values of J; hand *J_out to gmrfb_postprec_create once and re-use the plan at every iteration. */
+gmrfb_status gmrfb_fem1d_spacetime_tangent(gmrfb_fem1d* fem, int64_t nt, double dt, double nu, const double* w,
+                                           const uint8_t* prescribed, const gmrfb_spm** J_out, double* f_out);
+
 /* ------------------------------------------- Gauss-Newton on the device ------ */
 /* The explicit loop of scripts/solve_burger.jl:143-180 (packaged as GaussNewtonOptimizer / optimize in
  * scripts/burgers/solve_burgers_gmrf-fem.jl:172-182) for a bilinear collocation residual

@@ -31,6 +31,23 @@ import scipy.linalg as sla
 import scipy.sparse as sp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load_fem():
+    """oracle/fem_oracle.py (element-loop restatements of the reference's tangent assemblies) as ``orc.fem``."""
+    import importlib.util
+    import sys
+
+    if "gmrf_fem_oracle" in sys.modules:
+        return sys.modules["gmrf_fem_oracle"]
+    spec = importlib.util.spec_from_file_location("gmrf_fem_oracle", os.path.join(_HERE, "fem_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["gmrf_fem_oracle"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+fem = _load_fem()
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 _lib = None
 

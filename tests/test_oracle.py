@@ -149,3 +149,57 @@ def test_oracle_nd_separators_separate(orc, W):
     rnd = orc.supernodal_symbolic(Q, np.random.default_rng(0).permutation(Q.shape[0]))["nnz_L"]
     nat = orc.supernodal_symbolic(Q, np.arange(Q.shape[0]))["nnz_L"]
     assert nd < 0.65 * nat and nd < 0.2 * rnd  # 60 x 60 mesh: banded (natural) fill is n^1.5, nested dissection n log n
+
+
+# ------------------------------------------------------------------ FEM tangent restatements (oracle/fem_oracle.py) --
+def test_fem_oracle_tangents_are_derivatives_of_residuals(orc, W):
+    """The restated element loops are pinned by what they must satisfy independently of any implementation: the
+    tangent matrix is the derivative of the residual vector (central differences), constants integrate exactly and
+    the quadrature rules integrate their polynomial degree."""
+    fo = orc.fem
+    rng = np.random.default_rng(0)
+    for deg, pw in ((1, 1), (2, 2), (4, 4)):  # int over the reference triangle of l0^a l1^b = a! b! 2 / (a+b+2)! x area
+        lam, wq = fo.tri_quadrature(deg)
+        assert abs(wq.sum() - 1) < 1e-14
+        from math import factorial
+        for a in range(pw + 1):
+            b = pw - a
+            exact = factorial(a) * factorial(b) * 2 / factorial(a + b + 2)
+            assert abs(np.sum(wq * lam[:, 0]**a * lam[:, 1]**b) - exact) < 1e-14
+    nodes, tris = W.structured_mesh(9, 9, seed=1)
+    n = nodes.shape[0]
+    w = rng.standard_normal(n)
+    bnd = (nodes[:, 0] == 0) | (nodes[:, 0] == 1)
+    for deg in (1, 2, 4):
+        J, f = fo.assemble_cubic_p1(nodes, tris, w, bnd, deg)
+        for k in (5, 40):
+            e = np.zeros(n)
+            e[k] = 1e-6
+            fd = (fo.assemble_cubic_p1(nodes, tris, w + e, bnd, deg)[1] - fo.assemble_cubic_p1(nodes, tris, w - e, bnd, deg)[1]) / 2e-6
+            assert abs(fd - J[:, k].toarray().ravel()).max() < 1e-8
+        assert abs(J[np.flatnonzero(bnd)]).max() == 0 and np.all(f[bnd] == 0)
+    m, K = W.p1_mass_stiffness(nodes, tris)
+    J4, f4 = fo.assemble_cubic_p1(nodes, tris, np.full(n, 2.0), None, 4)
+    assert abs(f4 - 8 * m).max() < 1e-15 and abs(np.asarray(J4.sum(1)).ravel() - 12 * m).max() < 1e-15
+    assert abs(fo.assemble_stiffness_skipped_rows_p1(nodes, tris) - K).max() < 1e-12
+    for order in (1, 2):
+        xe, el = W.periodic_line_mesh(11, order)
+        ns = int(el.max()) + 1
+        u = rng.standard_normal(ns)
+        G, v = fo.assemble_burgers_advection(xe, el, u, order)
+        e = np.zeros(ns)
+        e[3] = 1e-6
+        fd = (fo.assemble_burgers_advection(xe, el, u + e, order)[1] - fo.assemble_burgers_advection(xe, el, u - e, order)[1]) / 2e-6
+        assert abs(fd - G[:, 3].toarray().ravel()).max() < 1e-8
+        assert abs(v.sum()) < 1e-12  # int u u_x over a ring = 0 (exact: the rule integrates the integrand's degree)
+        M, Gs = fo.assemble_mass_stiffness_1d(xe, el, order)
+        assert abs(M.sum() - 1.0) < 1e-14 and abs(Gs @ np.ones(ns)).max() < 1e-11
+        Ml, _ = fo.assemble_mass_stiffness_1d(xe, el, order, lumping=True)
+        assert abs(Ml.diagonal() - np.asarray(M.sum(1)).ravel()).max() < 1e-15
+        nt = 4
+        w = rng.standard_normal(nt * ns)
+        f, J = fo.burgers_spacetime_tangent(xe, el, w, nt, 0.01, 0.02, order)
+        e = np.zeros(nt * ns)
+        e[ns + 2] = 1e-6
+        fd = (fo.burgers_spacetime_tangent(xe, el, w + e, nt, 0.01, 0.02, order)[0] - fo.burgers_spacetime_tangent(xe, el, w - e, nt, 0.01, 0.02, order)[0]) / 2e-6
+        assert abs(fd - J[:, ns + 2].toarray().ravel()).max() < 1e-8
