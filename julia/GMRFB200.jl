@@ -16,7 +16,9 @@ using LinearAlgebra, SparseArrays
 
 export B200Context, B200Factor, b200_cholesky, b200_tridiagonal_cholesky, B200TridiagonalCholeskyFactor,
        B200CholeskySolverBlueprint, B200GNCholeskySolverBlueprint, forward_solve, backward_solve, ldiv, ldiv!,
-       var_selinv, var_rbmc, logdet_factor, issuccess
+       var_selinv, var_rbmc, logdet_factor, issuccess, B200SparseMatrix, to_sparse, B200FEMP1, B200FEM1D, lumped_mass,
+       set_coeff_grid!, assemble_darcy, matern_precision, assemble_cubic, assemble_burgers_mass_diffusion_matrices,
+       assemble_burgers_advection_matrix, burgers_f_and_J
 
 const libgmrfb = get(ENV, "GMRFB_LIB", joinpath(@__DIR__, "..", "diffeqgmrfs.jl_b200", "libgmrfb.so"))
 
@@ -349,6 +351,152 @@ function LinearAlgebra.logdet(F::B200TridiagonalCholeskyFactor)
     out = Ref(0.0)
     _check(F.ctx, ccall((:gmrfb_btd_logdet, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Float64}), F.h, out))
     return out[]
+end
+
+# ------------------------------------------------------------- finite-element assembly on the device --
+# The matrices the reference rebuilds inside its hot loops (SURVEY.md section 8(f) N2/N3).  Results are device matrices
+# owned by the assembler handle (fixed pattern, values of the last call); `to_sparse` copies one back.
+"Borrowed view of a device CSC matrix (gmrfb_spm) owned by `owner`."
+struct B200SparseMatrix
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    owner::Any
+end
+
+function Base.size(M::B200SparseMatrix)
+    m, n, z = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    _check(M.ctx, ccall((:gmrfb_spm_dims, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), M.h, m, n, z))
+    return (Int(m[]), Int(n[]))
+end
+
+function to_sparse(M::B200SparseMatrix)
+    m, n, z = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    _check(M.ctx, ccall((:gmrfb_spm_dims, libgmrfb), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), M.h, m, n, z))
+    colptr, rowval, nzval = Vector{Int64}(undef, n[] + 1), Vector{Int64}(undef, z[]), Vector{Float64}(undef, z[])
+    GC.@preserve colptr rowval nzval _check(M.ctx, ccall((:gmrfb_spm_get, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), M.h, 1, colptr, rowval, nzval))
+    return SparseMatrixCSC(Int(m[]), Int(n[]), colptr, rowval, nzval)
+end
+
+_mask(p::Nothing, n) = (C_NULL, nothing)
+function _mask(p, n)
+    m = zeros(UInt8, n)
+    m[collect(p)] .= 0x01          # a collection of 1-based dof indices (ch.prescribed_dofs)
+    return (pointer(m), m)
+end
+
+"P1 triangles: `nodes` 2 x n coordinates, `tris` 3 x T vertex indices (1-based)."
+mutable struct B200FEMP1
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    n::Int
+end
+
+function B200FEMP1(nodes::Matrix{Float64}, tris::Matrix{Int64}; ctx::B200Context = default_context())
+    size(nodes, 1) == 2 && size(tris, 1) == 3 || throw(ArgumentError("nodes must be 2 x n and tris 3 x T"))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve nodes tris _check(ctx, ccall((:gmrfb_fem_create, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, size(nodes, 2), nodes, size(tris, 2), tris, 1, out))
+    F = B200FEMP1(ctx, out[], size(nodes, 2))
+    finalizer(f -> ccall((:gmrfb_fem_destroy, libgmrfb), Int32, (Ptr{Cvoid},), f.h), F)
+    return F
+end
+
+"Lumped mass vector (load vector of f = 1)."
+function lumped_mass(F::B200FEMP1)
+    m = Vector{Float64}(undef, F.n)
+    GC.@preserve m _check(F.ctx, ccall((:gmrfb_fem_get_mass, libgmrfb), Int32, (Ptr{Cvoid}, Ptr{Float64}), F.h, m))
+    return m
+end
+
+function set_coeff_grid!(F::B200FEMP1, x_coords::Vector{Float64}, y_coords::Vector{Float64})
+    GC.@preserve x_coords y_coords _check(F.ctx, ccall((:gmrfb_fem_set_coeff_grid, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}), F.h, length(x_coords), x_coords, length(y_coords), y_coords))
+    return F
+end
+
+"assemble_darcy_diff_matrix (src/problems/darcy.jl:5-63): `coeff_mat[ix, iy]` as in the reference, or nothing for a unit coefficient."
+function assemble_darcy(F::B200FEMP1, coeff_mat::Union{Nothing,Matrix{Float64}} = nothing; prescribed = nothing)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    pm, keep = _mask(prescribed, F.n)
+    cp = coeff_mat === nothing ? Ptr{Float64}(C_NULL) : pointer(coeff_mat)
+    GC.@preserve coeff_mat keep _check(F.ctx, ccall((:gmrfb_fem_assemble, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ref{Ptr{Cvoid}}), F.h, cp, pm, out))
+    return B200SparseMatrix(F.ctx, out[], F)
+end
+
+"ratio * K' Mt^-1 K, K = kappa^2 Mt + G (src/spdes/shallow_water.jl:177-194)."
+function matern_precision(F::B200FEMP1, kappa::Real, ratio::Real; prescribed = nothing, prescribed_mass::Real = 1e-2)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    pm, keep = _mask(prescribed, F.n)
+    GC.@preserve keep _check(F.ctx, ccall((:gmrfb_fem_matern_precision, libgmrfb), Int32,
+        (Ptr{Cvoid}, Float64, Float64, Ptr{UInt8}, Float64, Ref{Ptr{Cvoid}}),
+        F.h, Float64(kappa), Float64(ratio), pm, Float64(prescribed_mass), out))
+    return B200SparseMatrix(F.ctx, out[], F)
+end
+
+"f_and_J of _research/elliptic_chen24.jl:280-285 without the static load vector: (s G u + f_cube, s G + J_cube)."
+function assemble_cubic(F::B200FEMP1, u::Vector{Float64}; prescribed = nothing, quad_degree::Integer = 2,
+                        stiffness_scale::Real = 1.0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    f = Vector{Float64}(undef, F.n)
+    pm, keep = _mask(prescribed, F.n)
+    GC.@preserve u f keep _check(F.ctx, ccall((:gmrfb_fem_assemble_cubic, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{UInt8}, Ref{Ptr{Cvoid}}, Ptr{Float64}),
+        F.h, u, Int32(quad_degree), Float64(stiffness_scale), pm, out, f))
+    return f, B200SparseMatrix(F.ctx, out[], F)
+end
+
+"Lagrange lines of order 1 or 2: `elems` (order+1) x E node indices (1-based; quadratic: left, right, middle), `elem_x` their coordinates."
+mutable struct B200FEM1D
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    n::Int
+end
+
+function B200FEM1D(elems::Matrix{Int64}, elem_x::Matrix{Float64}; order::Integer = size(elems, 1) - 1, nquad::Integer = 0,
+                   ctx::B200Context = default_context())
+    size(elems) == size(elem_x) && size(elems, 1) == order + 1 || throw(ArgumentError("elems and elem_x must be (order+1) x E"))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    n = Int(maximum(elems))
+    GC.@preserve elems elem_x _check(ctx, ccall((:gmrfb_fem1d_create, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, n, size(elems, 2), elems, elem_x, Int32(order), 1, Int32(nquad), out))
+    F = B200FEM1D(ctx, out[], n)
+    finalizer(f -> ccall((:gmrfb_fem1d_destroy, libgmrfb), Int32, (Ptr{Cvoid},), f.h), F)
+    return F
+end
+
+"assemble_burgers_mass_diffusion_matrices(disc; lumping) (src/problems/burgers.jl:61-98)."
+function assemble_burgers_mass_diffusion_matrices(F::B200FEM1D; lumping::Bool = false, prescribed = nothing)
+    M, G = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+    pm, keep = _mask(prescribed, F.n)
+    GC.@preserve keep _check(F.ctx, ccall((:gmrfb_fem1d_mass_stiffness, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}), F.h, Int32(lumping), pm, M, G))
+    return B200SparseMatrix(F.ctx, M[], F), B200SparseMatrix(F.ctx, G[], F)
+end
+
+"assemble_burgers_advection_matrix(disc, cur_weights) (src/problems/burgers.jl:5-59): (G_adv, v)."
+function assemble_burgers_advection_matrix(F::B200FEM1D, u::Vector{Float64}; prescribed = nothing)
+    A = Ref{Ptr{Cvoid}}(C_NULL)
+    v = Vector{Float64}(undef, F.n)
+    pm, keep = _mask(prescribed, F.n)
+    GC.@preserve u v keep _check(F.ctx, ccall((:gmrfb_fem1d_advection, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ref{Ptr{Cvoid}}, Ptr{Float64}), F.h, u, pm, A, v))
+    return B200SparseMatrix(F.ctx, A[], F), v
+end
+
+"f_and_J(w) of scripts/burgers/solve_burgers_gmrf-fem.jl:115-142 for `nt` time steps (w time-major): (f, J)."
+function burgers_f_and_J(F::B200FEM1D, w::Vector{Float64}, nt::Integer, dt::Real, nu::Real; prescribed = nothing)
+    length(w) == nt * F.n || throw(DimensionMismatch("w must hold nt * n values"))
+    J = Ref{Ptr{Cvoid}}(C_NULL)
+    f = Vector{Float64}(undef, (nt - 1) * F.n)
+    pm, keep = _mask(prescribed, F.n)
+    GC.@preserve w f keep _check(F.ctx, ccall((:gmrfb_fem1d_spacetime_tangent, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Float64, Float64, Ptr{Float64}, Ptr{UInt8}, Ref{Ptr{Cvoid}}, Ptr{Float64}),
+        F.h, Int64(nt), Float64(dt), Float64(nu), w, pm, J, f))
+    return f, B200SparseMatrix(F.ctx, J[], F)
 end
 
 end # module
