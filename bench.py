@@ -250,7 +250,9 @@ class Lane:
         self.d_rhs = self.rhs_host.to(dev)
         self.d_x = torch.empty_like(self.d_rhs)
         self.d_var = torch.empty_like(self.d_rhs)
-        self.x_host = np.empty(self.n)
+        # page-locked result buffers of the end-to-end leg (the solve works in place on x_pin, as the C ABI does)
+        self.x_pin = torch.empty(self.n, dtype=torch.float64).pin_memory()
+        self.v_pin = torch.empty(self.n, dtype=torch.float64).pin_memory()
         self.end = torch.cuda.Event(enable_timing=True)
         self.torch, self.local = torch, local
         self.xs = self.v = None
@@ -271,9 +273,9 @@ class Lane:
         self.torch.cuda.set_device(self.local)
         for _ in range(k):
             self.fac.factorize(self.nz_host.numpy())
-            self.x_host[:] = self.rhs_host.numpy()
-            self.xs = self.fac.solve(self.x_host)
-            self.v = self.fac.var_selinv()
+            self.x_pin.copy_(self.rhs_host)
+            self.xs = self.fac.solve_inplace(self.x_pin.numpy())
+            self.v = self.fac.var_selinv(out=self.v_pin.numpy())
 
 
 def run_gpu_arm(args):

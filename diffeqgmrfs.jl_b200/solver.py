@@ -526,6 +526,17 @@ class CholeskyFactor:
         out = X[:, 0].copy() if one else X
         return (out, res) if return_residual else out
 
+    def solve_inplace(self, X, mode=B.SOLVE_A):
+        """``ldiv!(F, X)``: X (length n, or n x k column-major) is a caller-owned float64 array that is overwritten by
+        the solution - exactly what the C ABI does, with no temporary on the host.  Page-locked arrays (e.g.
+        ``torch.empty(n, dtype=torch.float64).pin_memory().numpy()``) make both transfers asynchronous DMA."""
+        assert isinstance(X, np.ndarray) and X.dtype == np.float64 and X.shape[0] == self.sym.n
+        assert X.ndim == 1 or X.flags.f_contiguous, "X must be a vector or a column-major matrix"
+        assert X.flags.writeable and (X.ndim > 1 or X.flags.c_contiguous)
+        nrhs = 1 if X.ndim == 1 else X.shape[1]
+        B.check(B.lib().gmrfb_solve(self.h, mode, X.ctypes.data_as(B._F64P), self.sym.n, nrhs), self.ctx.h)
+        return X
+
     def PtL_solve(self, b):
         return self._solve(B.SOLVE_PTL, b)
 
@@ -553,8 +564,11 @@ class CholeskyFactor:
                                      self.sym.n, Zf.shape[1]), self.ctx.h)
         return X[:, 0].copy() if one else X
 
-    def var_selinv(self):
-        out = np.empty(self.sym.n)
+    def var_selinv(self, out=None):
+        """diag(Q^-1) by Takahashi selected inversion; ``out``: optional caller-owned (e.g. page-locked) result array."""
+        if out is None:
+            out = np.empty(self.sym.n)
+        assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.size == self.sym.n and out.flags.c_contiguous
         B.check(B.lib().gmrfb_var_selinv(self.h, out.ctypes.data_as(B._F64P)), self.ctx.h)
         return out
 

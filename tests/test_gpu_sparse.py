@@ -79,6 +79,30 @@ def test_selected_inversion(pkg, orc, ctx, problems, nx):
     _selected_inversion(pkg, orc, ctx, problems, nx, "nd")
 
 
+def test_inplace_solve_and_caller_owned_outputs(pkg, orc, ctx, problems):
+    """``solve_inplace`` (ldiv!: the C ABI overwrites the caller's buffer) and ``var_selinv(out=...)`` with page-locked
+    host buffers give the same numbers as the allocating forms, for a vector and for a column-major panel."""
+    import torch
+    P = problems[24]
+    n = P["Qpost"].shape[0]
+    sym = pkg.Symbolic(P["Qpost"], coords=P["nodes"], ctx=ctx)
+    fac = pkg.CholeskyFactor(sym).factorize(P["Qpost"].data)
+    x_ref = fac.solve(P["rhs"])
+    xp = torch.empty(n, dtype=torch.float64).pin_memory()
+    xp.copy_(torch.from_numpy(P["rhs"]))
+    out = fac.solve_inplace(xp.numpy())
+    assert out.ctypes.data == xp.numpy().ctypes.data and np.array_equal(out, x_ref)
+    Bm = np.asfortranarray(np.random.default_rng(0).standard_normal((n, 7)))
+    X_ref = fac.solve(Bm)
+    fac.solve_inplace(Bm)
+    assert np.array_equal(Bm, X_ref)
+    vp = torch.empty(n, dtype=torch.float64).pin_memory()
+    v = fac.var_selinv(out=vp.numpy())
+    assert np.array_equal(v, fac.var_selinv())
+    with pytest.raises(AssertionError):
+        fac.solve_inplace(np.ascontiguousarray(Bm))  # row-major panel: not what the ABI reads
+
+
 @pytest.mark.parametrize("nx", [24, 130])
 def test_selected_inversion_amd_ordering(pkg, orc, ctx, problems, nx):
     _selected_inversion(pkg, orc, ctx, problems, nx, "amd")
