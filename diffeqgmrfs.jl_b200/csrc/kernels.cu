@@ -288,10 +288,14 @@ __global__ void __launch_bounds__(256) k_potrf64(const Task* __restrict__ tasks,
 
 // ------------------------------------------------------------------------------------- apply inverse ----
 // X (M x N, N <= 64) <- +-X W' (TRANS: "X L^{-T}") or +-X W (!TRANS: "X L^{-1}") with W = L^{-1} from k_potrf64.
-// One CTA = 128 rows, one warp = 16 rows: the A fragments are loaded straight from global memory (issued before W
-// is staged, so their latency overlaps), the product runs on DMMA, the result is written in place.
+// The launch sits on the dependent chain of every blocked factorisation (POTRF -> apply inverse -> panel update), so it
+// is cut for latency, not for throughput: one CTA = TRSM_ROWS = 32 rows, one warp = 8 rows = one DMMA row tile on its
+// own SM sub-core (128 dependent-chain DMMAs per warp instead of 512 with 128-row CTAs), which also spreads a
+// 4096-row panel over 128 SMs instead of 32.  The A fragments are loaded straight from global memory (issued before W
+// is staged, so their latency overlaps), the result is written in place.
+constexpr int AI_NT = 128;
 template <bool TRANS>
-__global__ void __launch_bounds__(256) k_apply_inv(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
+__global__ void __launch_bounds__(AI_NT) k_apply_inv(const Task* __restrict__ tasks, int ntasks, Arenas ar) {
   __shared__ double Ws[64 * PLD];
   const int tix = find_task(tasks, ntasks, blockIdx.x);
   const Task T = tasks[tix];
@@ -301,37 +305,35 @@ __global__ void __launch_bounds__(256) k_apply_inv(const Task* __restrict__ task
   const int ldw = T.ldb, ldx = T.ldc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  const int row0 = (blockIdx.x - T.tile0) * TRSM_ROWS + warp * 16;
-  double a[2][16];
+  const int row0 = (blockIdx.x - T.tile0) * TRSM_ROWS + warp * 8;
+  const int r = row0 + lr;
+  double a[16];
 #pragma unroll
-  for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-    for (int kk = 0; kk < 16; kk++) {
-      const int r = row0 + mt * 8 + lr, c = 4 * kk + lc;
-      a[mt][kk] = (r < M && c < N) ? X[r + (int64_t)c * ldx] : 0.0;
-    }
+  for (int kk = 0; kk < 16; kk++) {
+    const int c = 4 * kk + lc;
+    a[kk] = (r < M && c < N) ? X[r + (int64_t)c * ldx] : 0.0;
+  }
   const int nw = (T.flags & TF_B_DINV) ? 64 : N;
-  {
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
     double v[16];
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      const int e = tid + u * 256, i = e & 63, k = e >> 6;
+      const int e = tid + (half * 16 + u) * AI_NT, i = e & 63, k = e >> 6;
       // W is lower triangular: the strict upper part is never fetched
       v[u] = (i < nw && k < nw && i >= k) ? Wg[i + (int64_t)k * ldw] : ((i == k) ? 1.0 : 0.0);
     }
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      const int e = tid + u * 256, i = e & 63, k = e >> 6;
+      const int e = tid + (half * 16 + u) * AI_NT, i = e & 63, k = e >> 6;
       Ws[k * PLD + i] = v[u];
     }
   }
   __syncthreads();
   if (row0 >= M) return;
-  double acc[2][8][2];
+  double acc[8][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  for (int nt = 0; nt < 8; nt++) acc[nt][0] = acc[nt][1] = 0.0;
 #pragma unroll
   for (int kk = 0; kk < 16; kk++)
 #pragma unroll
@@ -339,19 +341,18 @@ __global__ void __launch_bounds__(256) k_apply_inv(const Task* __restrict__ task
       // W is lower triangular: (X W')[:, n] needs k <= n, (X W)[:, n] needs k >= n
       if (TRANS ? (kk > 2 * nt + 1) : (kk < 2 * nt)) continue;
       const double b = TRANS ? Ws[(4 * kk + lc) * PLD + nt * 8 + lr] : Ws[(nt * 8 + lr) * PLD + 4 * kk + lc];
-      dmma884(acc[0][nt][0], acc[0][nt][1], a[0][kk], b);
-      dmma884(acc[1][nt][0], acc[1][nt][1], a[1][kk], b);
+      dmma884(acc[nt][0], acc[nt][1], a[kk], b);
     }
   const double sgn = (T.flags & TF_NEG) ? -1.0 : 1.0;
-#pragma unroll
-  for (int mt = 0; mt < 2; mt++)
+  if (r < M) {
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int r = row0 + mt * 8 + lr, c = nt * 8 + 2 * lc + h;
-        if (r < M && c < N) X[r + (int64_t)c * ldx] = sgn * acc[mt][nt][h];
+        const int c = nt * 8 + 2 * lc + h;
+        if (c < N) X[r + (int64_t)c * ldx] = sgn * acc[nt][h];
       }
+  }
 }
 
 // ------------------------------------------------------------------------------ multifrontal assembly ----
@@ -973,10 +974,10 @@ cudaError_t run_launch(const Launch& L, const Task* d_tasks, const Arenas& ar, c
       k_potrf64<<<L.grid, 256, potrf_smem(), st>>>(t, L.ntasks, ar, aux.d_info);
       break;
     case LK_TRSM_RLT:
-      k_apply_inv<true><<<L.grid, 256, 0, st>>>(t, L.ntasks, ar);
+      k_apply_inv<true><<<L.grid, AI_NT, 0, st>>>(t, L.ntasks, ar);
       break;
     case LK_TRSM_RLN:
-      k_apply_inv<false><<<L.grid, 256, 0, st>>>(t, L.ntasks, ar);
+      k_apply_inv<false><<<L.grid, AI_NT, 0, st>>>(t, L.ntasks, ar);
       break;
     case LK_EXTEND_ADD:
       k_extend_add<<<L.grid, 256, 0, st>>>(t, L.ntasks, ar, aux.d_relmap);

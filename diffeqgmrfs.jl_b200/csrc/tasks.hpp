@@ -96,7 +96,7 @@ enum : int32_t { GCFG_BIG = 0, GCFG_SMALL = 1, GCFG_COUNT = 2 };
 constexpr int GEMM_TILE_M[GCFG_COUNT] = {128, 64};
 constexpr int GEMM_TILE_N[GCFG_COUNT] = {64, 64};
 constexpr int NB = 64;           // panel width of the blocked POTRF/TRSM
-constexpr int TRSM_ROWS = 128;   // rows per CTA in the apply-inverse (TRSM) kernels
+constexpr int TRSM_ROWS = 32;    // rows per CTA in the apply-inverse (TRSM) kernels (4 warps of 8 rows)
 constexpr int DINV_SLOT = 64 * 64;  // doubles per inverse-block scratch slot
 constexpr int EA_TILE = 64;      // extend-add / gather tile edge
 constexpr int SMALL_FRONT_MAX = 152;  // fronts up to this order are processed by one CTA in shared memory

@@ -20,7 +20,9 @@
  *  - Dense matrices are column-major Float64 with an explicit leading dimension.
  *  - There is no CPU fallback: every numeric entry point runs CUDA kernels on the context's device
  *    and fails with GMRFB_ERR_CUDA if that is impossible.
- *  - One handle is used by one host thread at a time; distinct contexts may be used concurrently.
+ *  - A context and every handle created from it (they share its stream, its buffer bookkeeping and the caches of
+ *    captured CUDA graphs kept by the symbolic handles) are used by one host thread at a time; distinct contexts may
+ *    be used concurrently (bench.py: one context per problem in flight).
  */
 #ifndef GMRFB_H
 #define GMRFB_H
