@@ -149,6 +149,9 @@ static const char* prof_name(int kind) {
     case PK_BWD_LEVEL: return "k_bwd_step";
     case PK_FWD_ASM: return "k_fwd_assemble";
     case PK_BWD_RPART: return "k_bwd_rpart";
+    case PK_WIDE_FWD: return "k_wide_gemv";
+    case PK_WIDE_BWD: return "k_wide_trmv_t";
+    case PK_WIDE_NORM: return "k_wide_norms";
     case PK_FWD_SMALL: return "k_fwd_small";
     case PK_BWD_SMALL: return "k_bwd_small";
     case PK_SCATTER: return "k_scatter_values";
@@ -422,12 +425,42 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
       std::memcpy(&t.alpha, &woff, sizeof(double));
       return t;
     };
-    for (size_t l = 0; l < S.levels.size(); l++) {
-      const auto& sn = S.levels[l].snodes;
-      auto& SL = sym->solve_levels[l];
+    // wide supernodes keep their full inverse (see sparse_kernels.cu); GMRFB_WIDE_INV=0 turns the path off
+    {
+      const char* we = std::getenv("GMRFB_WIDE_INV");
+      sym->wide_enabled = !(we && we[0] == '0');
+      sym->wide.clear(), sym->wide_off.clear(), sym->wide_ld.clear();
+      int64_t off = 0;
+      if (sym->wide_enabled)
+        for (int32_t s = 0; s < S.nsuper; s++) {
+          if (solve_small(s) || S.ncols(s) < SOLVE_WIDE_MIN) continue;
+          const int sc = S.ncols(s), ldw = (sc + 1) & ~1;
+          sym->wide.push_back(s);
+          sym->wide_off.push_back(off);
+          sym->wide_ld.push_back(ldw);
+          off += (int64_t)ldw * sc;
+          off = (off + 15) & ~(int64_t)15;
+        }
+      sym->wide_doubles = off;
+      if (sym->wide.empty()) sym->wide_enabled = false;
+    }
+    std::vector<int32_t> wide_idx(S.nsuper, -1);
+    for (size_t i = 0; i < sym->wide.size(); i++) wide_idx[sym->wide[i]] = (int32_t)i;
+    auto wide_task = [&](int32_t s) {  // solve-task fields, K = leading dimension of W_J, alpha = bits of its offset
+      Task t = base_task(s, 0);
+      const int32_t wi = wide_idx[s];
+      t.K = sym->wide_ld[wi];
+      t.aux0 = wi;  // (the row-list offset is not needed by the wide kernels)
+      const int64_t wo = sym->wide_off[wi];
+      std::memcpy(&t.alpha, &wo, sizeof(double));
+      return t;
+    };
+    auto build_steps = [&](const std::vector<int32_t>& sn, bool skip_wide, std::vector<Launch>& fwd,
+                           std::vector<Launch>& bwd) {
+      auto skip = [&](int32_t s) { return solve_small(s) || (skip_wide && wide_idx[s] >= 0); };
       int maxs = 0;
       for (int32_t s : sn)
-        if (!solve_small(s)) maxs = std::max(maxs, S.ncols(s));
+        if (!skip(s)) maxs = std::max(maxs, S.ncols(s));
       int nsteps = cdiv(maxs, 64);
       for (int k = 0; k < nsteps; k++) {
         Launch Lf{};
@@ -437,7 +470,7 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
         // forward step k: CTAs over the rows below block k (at least one CTA to solve and publish the block)
         for (int32_t s : sn) {
           int sc = S.ncols(s), d = S.front_order(s);
-          if (k * 64 >= sc || solve_small(s)) continue;
+          if (k * 64 >= sc || skip(s)) continue;
           int nb = std::min(64, sc - k * 64);
           Task t = base_task(s, k);
           t.tile0 = Lf.grid;
@@ -449,12 +482,12 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
           Lf.bytes += 8.0 * trap;
           Lf.flops += 2.0 * trap;
         }
-        SL.fwd_steps.push_back(Lf);
+        fwd.push_back(Lf);
         Lb.kind = PK_BWD_LEVEL;
         Lb.task0 = (int32_t)tasks.size();
         for (int32_t s : sn) {
           int sc = S.ncols(s);
-          if (k * 64 >= sc || solve_small(s)) continue;
+          if (k * 64 >= sc || skip(s)) continue;
           int nb = std::min(64, sc - k * 64);
           Task t = base_task(s, k);
           t.tile0 = Lb.grid;
@@ -465,7 +498,38 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
           Lb.bytes += 8.0 * tri;
           Lb.flops += 2.0 * tri;
         }
-        SL.bwd_steps.push_back(Lb);
+        bwd.push_back(Lb);
+      }
+    };
+    for (size_t l = 0; l < S.levels.size(); l++) {
+      const auto& sn = S.levels[l].snodes;
+      auto& SL = sym->solve_levels[l];
+      build_steps(sn, false, SL.fwd_steps, SL.bwd_steps);
+      if (sym->wide_enabled) {
+        build_steps(sn, true, SL.fwd_steps_nw, SL.bwd_steps_nw);
+        auto wide_launch = [&](int kind, auto ctas_of, auto bytes_of) {
+          Launch L{};
+          L.kind = kind;
+          L.task0 = (int32_t)tasks.size();
+          for (int32_t s : sn) {
+            if (wide_idx[s] < 0) continue;
+            const int c = ctas_of(s);
+            if (c <= 0) continue;
+            Task t = wide_task(s);
+            t.tile0 = L.grid;
+            tasks.push_back(t);
+            L.ntasks++;
+            L.grid += c;
+            L.bytes += bytes_of(s);
+            L.flops += bytes_of(s) / 4.0;
+          }
+          return L;
+        };
+        auto tri_bytes = [&](int32_t s) { double sc = S.ncols(s); return 8.0 * sc * (sc + 1) / 2; };
+        SL.wide_trmv = wide_launch(PK_WIDE_FWD, [&](int32_t s) { return cdiv(S.ncols(s), SOLVE_WG_ROWS); }, tri_bytes);
+        SL.wide_below = wide_launch(PK_WIDE_FWD, [&](int32_t s) { return cdiv(S.front_order(s) - S.ncols(s), SOLVE_WG_ROWS); },
+                                    [&](int32_t s) { return 8.0 * (double)(S.front_order(s) - S.ncols(s)) * S.ncols(s); });
+        SL.wide_bwd = wide_launch(PK_WIDE_BWD, [&](int32_t s) { return cdiv(S.ncols(s), 4); }, tri_bytes);
       }
       Launch Lr{};
       Lr.kind = PK_BWD_RPART;
@@ -483,6 +547,23 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
       }
       SL.rpart = Lr;
     }
+    if (sym->wide_enabled) {
+      Launch Ln{};
+      Ln.kind = PK_WIDE_NORM;
+      Ln.task0 = (int32_t)tasks.size();
+      for (int32_t s : sym->wide) {
+        Task t = wide_task(s);
+        t.tile0 = Ln.grid;
+        tasks.push_back(t);
+        Ln.ntasks++;
+        Ln.grid += cdiv(S.ncols(s), 8);
+        Ln.bytes += 8.0 * (double)S.ncols(s) * (S.ncols(s) + 1);
+      }
+      sym->wide_norms = Ln;
+      build_wide_inverse_plan(S, sym->wide, sym->wide_off, sym->wide_ld, sym->wide_doubles, sym->wide_plan.host);
+      GMRFB_CU(ctx, sym->wide_plan.tasks.upload(sym->wide_plan.host.tasks, st));
+      sym->wide_plan.ready = true;
+    }
     GMRFB_CU(ctx, sym->d_solve_tasks.upload(tasks, st));
   }
   GMRFB_CU(ctx, sym->factor_plan.tasks.upload(sym->factor_plan.host.tasks, st));
@@ -497,7 +578,13 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
 static gmrfb_status sym_ensure_selinv(gmrfb_sym* sym) {
   if (sym->selinv_plan.ready) return GMRFB_OK;
   gmrfb_ctx* ctx = sym->ctx;
-  build_selinv_plan(sym->S, sym->selinv_plan.host);
+  if (sym->wide_enabled) {
+    std::vector<int32_t> wide_idx(sym->S.nsuper, -1);
+    for (size_t i = 0; i < sym->wide.size(); i++) wide_idx[sym->wide[i]] = (int32_t)i;
+    build_selinv_plan(sym->S, sym->selinv_plan.host, &wide_idx, &sym->wide_off, &sym->wide_ld);
+  } else {
+    build_selinv_plan(sym->S, sym->selinv_plan.host);
+  }
   GMRFB_CU(ctx, sym->selinv_plan.tasks.upload(sym->selinv_plan.host.tasks, ctx->stream));
   sym->selinv_plan.ready = true;
   return GMRFB_OK;
@@ -523,6 +610,11 @@ extern "C" gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out) {
   GMRFB_CU(ctx, f->bwork.alloc((size_t)std::max<int64_t>(S.n, 1) * SOLVE_NRC));
   GMRFB_CU(ctx, f->uvec.alloc((size_t)std::max<int64_t>(sym->uvec_rows, 1) * SOLVE_NRC));
   GMRFB_CU(ctx, f->dinv.alloc((size_t)std::max<int64_t>(sym->factor_plan.host.dinv, 1)));
+  if (sym->wide_enabled) {
+    GMRFB_CU(ctx, f->winv_full.alloc((size_t)(2 * sym->wide_doubles)));
+    GMRFB_CU(ctx, f->wide_norms.alloc(2 * sym->wide.size()));
+    f->wide_norms_host.assign(2 * sym->wide.size(), 0.0);
+  }
   *out = f.release();
   return GMRFB_OK;
 }
@@ -568,13 +660,46 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
     aux.d_snodes = sym->d_snodes.p;
     aux.d_child_idx = sym->d_child_idx.p;
     aux.d_sparent = sym->d_sparent.p;
-    return run_plan(ctx, sym->factor_plan, ar, aux);
+    gmrfb_status frc = run_plan(ctx, sym->factor_plan, ar, aux);
+    if (frc != GMRFB_OK || !sym->wide_enabled) return frc;
+    // full inverses of the wide supernodes (the solves use them when they are well enough conditioned) and the two
+    // infinity norms per supernode that decide it
+    GMRFB_CU(ctx, cudaMemsetAsync(fac->wide_norms.p, 0, fac->wide_norms.n * sizeof(double), st));
+    ar.p[AR_WINV] = fac->winv_full.p;
+    frc = run_plan(ctx, sym->wide_plan, ar, aux);
+    if (frc != GMRFB_OK) return frc;
+    {
+      const Launch& Ln = sym->wide_norms;
+      ProfScope ps(ctx, PK_WIDE_NORM, 0, Ln.bytes, Ln.grid, Ln.ntasks);
+      GMRFB_CU(ctx, launch_wide_norms(sym->d_solve_tasks.p + Ln.task0, Ln.ntasks, Ln.grid, fac->arena.p, fac->winv_full.p,
+                                      fac->wide_norms.p, st));
+    }
+    ctx->launches++;
+    return GMRFB_OK;
   };
+  fac->wide_ok = false;
   gmrfb_status rc = run_graphed(ctx, sym->graphs, graph_key({1, (uint64_t)(uintptr_t)d_nzval, fac->buffers_key()}), body);
   if (rc != GMRFB_OK) return rc;
   int info = 0;
   GMRFB_CU(ctx, cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (sym->wide_enabled)
+    GMRFB_CU(ctx, cudaMemcpyAsync(fac->wide_norms_host.data(), fac->wide_norms.p, fac->wide_norms.n * sizeof(double),
+                                  cudaMemcpyDeviceToHost, st));
   GMRFB_CU(ctx, cudaStreamSynchronize(st));
+  if (sym->wide_enabled && info == INT_MAX) {
+    // cond_1(L_JJ) bounds the error the explicit inverse adds to a solve (~ cond * eps): beyond the threshold the
+    // sweeps keep to the block-step substitution (GMRFB_WIDE_COND_MAX, default 1e5)
+    const char* ce = std::getenv("GMRFB_WIDE_COND_MAX");
+    const double cond_max = ce ? std::atof(ce) : 1e5;
+    double c = 0.0;
+    for (size_t i = 0; i < sym->wide.size(); i++)
+      c = std::max(c, fac->wide_norms_host[2 * i] * fac->wide_norms_host[2 * i + 1]);
+    fac->wide_cond = c;
+    fac->wide_ok = std::isfinite(c) && c <= cond_max;
+    if (std::getenv("GMRFB_WIDE_DEBUG"))
+      fprintf(stderr, "[gmrfb] wide supernodes: %zu, max cond_1(L_JJ) = %.3e, inverse path %s\n", sym->wide.size(), c,
+              fac->wide_ok ? "on" : "off");
+  }
   if (info != INT_MAX) {
     fac->status = GMRFB_ERR_NOT_SPD;
     fac->fail_column = (info >= 0 && info < S.n) ? S.post[info] : -1;
@@ -705,6 +830,7 @@ gmrfb_status sweep_fwd(gmrfb_fac* fac, double* w, double* y, int nr) {
   gmrfb_sym* sym = fac->sym;
   const int64_t n = sym->S.n;
   const int nlev = (int)sym->S.levels.size();
+  const bool wide = sym->wide_enabled && fac->wide_ok;
   for (int l = 0; l < nlev; l++) {
     if (sym->small_cnt[l] > 0) {  // fused: children's contributions, substitution and update vector by one warp each
       ProfScope ps(ctx, PK_FWD_SMALL, 0, sym->small_bytes[l], sym->small_cnt[l], sym->small_cnt[l]);
@@ -719,11 +845,28 @@ gmrfb_status sweep_fwd(gmrfb_fac* fac, double* w, double* y, int nr) {
                                         sym->d_child_idx.p, sym->d_relmap.p, w, n, fac->uvec.p, ctx->stream));
       ctx->launches++;
     }
-    for (const Launch& L : sym->solve_levels[l].fwd_steps) {
+    const auto& SL = sym->solve_levels[l];
+    for (const Launch& L : (wide ? SL.fwd_steps_nw : SL.fwd_steps)) {
       ProfScope ps(ctx, PK_FWD_LEVEL, L.flops * nr, L.bytes, L.grid, L.ntasks);
       GMRFB_CU(ctx, launch_fwd_step(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, w, y, n,
                                     fac->uvec.p, nr, fac->dinv.p, ctx->stream));
       ctx->launches++;
+    }
+    if (wide && SL.wide_trmv.grid > 0) {  // y_J = W_J x_J, then u_J -= L21 y_J
+      {
+        const Launch& L = SL.wide_trmv;
+        ProfScope ps(ctx, PK_WIDE_FWD, L.flops * nr, L.bytes, L.grid, L.ntasks);
+        GMRFB_CU(ctx, launch_wide_fwd(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, 0, fac->arena.p, fac->winv_full.p, w,
+                                      y, n, fac->uvec.p, nr, ctx->stream));
+        ctx->launches++;
+      }
+      if (SL.wide_below.grid > 0) {
+        const Launch& L = SL.wide_below;
+        ProfScope ps(ctx, PK_WIDE_FWD, L.flops * nr, L.bytes, L.grid, L.ntasks);
+        GMRFB_CU(ctx, launch_wide_fwd_below(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, y, n, fac->uvec.p,
+                                            nr, ctx->stream));
+        ctx->launches++;
+      }
     }
   }
   return GMRFB_OK;
@@ -734,6 +877,7 @@ gmrfb_status sweep_bwd(gmrfb_fac* fac, double* t, double* xs, int nr) {
   gmrfb_sym* sym = fac->sym;
   const int64_t n = sym->S.n;
   const int nlev = (int)sym->S.levels.size();
+  const bool wide = sym->wide_enabled && fac->wide_ok;
   for (int l = nlev - 1; l >= 0; l--) {
     const auto& SL = sym->solve_levels[l];
     if (SL.rpart.grid > 0) {
@@ -742,11 +886,19 @@ gmrfb_status sweep_bwd(gmrfb_fac* fac, double* t, double* xs, int nr) {
                                      fac->arena.p, sym->d_rows.p, xs, n, fac->partial.p, nr, ctx->stream));
       ctx->launches++;
     }
-    for (int k = (int)SL.bwd_steps.size() - 1; k >= 0; k--) {
-      const Launch& L = SL.bwd_steps[k];
+    const auto& bsteps = wide ? SL.bwd_steps_nw : SL.bwd_steps;
+    for (int k = (int)bsteps.size() - 1; k >= 0; k--) {
+      const Launch& L = bsteps[k];
       ProfScope ps(ctx, PK_BWD_LEVEL, L.flops * nr, L.bytes, L.grid, L.ntasks);
       GMRFB_CU(ctx, launch_bwd_step(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->arena.p, t, xs, n,
                                     fac->partial.p, nr, fac->dinv.p, ctx->stream));
+      ctx->launches++;
+    }
+    if (wide && SL.wide_bwd.grid > 0) {  // x_J = W_J' (t_J - R-part partial sums)
+      const Launch& L = SL.wide_bwd;
+      ProfScope ps(ctx, PK_WIDE_BWD, L.flops * nr, L.bytes, L.grid, L.ntasks);
+      GMRFB_CU(ctx, launch_wide_bwd(sym->d_solve_tasks.p + L.task0, L.ntasks, L.grid, fac->winv_full.p, t, xs, n,
+                                    fac->partial.p, nr, ctx->stream));
       ctx->launches++;
     }
     if (sym->small_cnt[l] > 0) {
@@ -893,7 +1045,7 @@ gmrfb_status solve_device(gmrfb_fac* fac, int mode, const double* d_in, int64_t 
     gmrfb_status rc = run_graphed(ctx, sym->graphs,
                                   graph_key({2, (uint64_t)mode, (uint64_t)(uintptr_t)(d_in + c0 * ldin), (uint64_t)ldin,
                                              (uint64_t)(uintptr_t)(d_out + c0 * ldout), (uint64_t)ldout, (uint64_t)nr,
-                                             (uint64_t)(uintptr_t)d_mean, fac->buffers_key()}), body);
+                                             (uint64_t)(uintptr_t)d_mean, fac->buffers_key(), (uint64_t)fac->wide_ok}), body);
     if (rc != GMRFB_OK) return rc;
   }
   return GMRFB_OK;
@@ -1067,7 +1219,7 @@ static gmrfb_status selinv_run(gmrfb_fac* fac) {
   // the selected inversion has its own inverse-block scratch: fac->dinv keeps the factor's inverses for the solves
   if ((int64_t)fac->dinv_sel.n < sym->selinv_plan.host.dinv)
     GMRFB_CU(ctx, fac->dinv_sel.alloc((size_t)std::max<int64_t>(sym->selinv_plan.host.dinv, 1)));
-  Arenas ar{{fac->arena.p, fac->zarena.p, fac->zwork.p, nullptr}};
+  Arenas ar{{fac->arena.p, fac->zarena.p, fac->zwork.p, fac->winv_full.p}};
   ar.dinv = fac->dinv_sel.p;
   LaunchAux aux;
   aux.d_info = ctx->d_info;

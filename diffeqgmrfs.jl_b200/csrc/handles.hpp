@@ -24,12 +24,25 @@ struct gmrfb_sym {
   gmrfb::DevPlan factor_plan, selinv_plan, zero_plan;
   // solve schedule: per level, one launch per 64-column block step
   struct SolveLevel {
-    std::vector<gmrfb::Launch> fwd_steps, bwd_steps;
+    std::vector<gmrfb::Launch> fwd_steps, bwd_steps;  // block steps of every large supernode of the level
     gmrfb::Launch rpart;
+    // the same with the wide supernodes taken out of the block steps and solved through their full inverses
+    std::vector<gmrfb::Launch> fwd_steps_nw, bwd_steps_nw;
+    gmrfb::Launch wide_trmv, wide_below, wide_bwd;
   };
   std::vector<SolveLevel> solve_levels;
   gmrfb::DevBuf<gmrfb::Task> d_solve_tasks;
   int64_t partial_doubles = 0;
+  // wide supernodes (>= SOLVE_WIDE_MIN columns): the factorisation keeps W_J = L_JJ^{-1} at wide_off[i] (leading
+  // dimension wide_ld[i]) of the factor's wide-inverse buffer; wide_doubles = size of the W region (the TRTRI scratch
+  // of the same size follows it)
+  std::vector<int32_t> wide;
+  std::vector<int64_t> wide_off;
+  std::vector<int32_t> wide_ld;
+  int64_t wide_doubles = 0;
+  gmrfb::DevPlan wide_plan;
+  gmrfb::Launch wide_norms;
+  bool wide_enabled = false;
   // panel (multi-right-hand-side) sweeps, one pair of plans per panel width (built on first use)
   struct MrPlans {
     gmrfb::DevPlan fwd, bwd;
@@ -50,11 +63,18 @@ struct gmrfb_fac {
                              (uint64_t)(uintptr_t)zdiag.p, (uint64_t)(uintptr_t)nzval.p, (uint64_t)(uintptr_t)xwork.p,
                              (uint64_t)(uintptr_t)ywork.p, (uint64_t)(uintptr_t)bwork.p, (uint64_t)(uintptr_t)owork.p,
                              (uint64_t)(uintptr_t)uvec.p, (uint64_t)(uintptr_t)partial.p, (uint64_t)(uintptr_t)dinv.p,
-                             (uint64_t)(uintptr_t)dinv_sel.p, (uint64_t)(uintptr_t)mr_x.p, (uint64_t)(uintptr_t)mr_u.p});
+                             (uint64_t)(uintptr_t)dinv_sel.p, (uint64_t)(uintptr_t)mr_x.p, (uint64_t)(uintptr_t)mr_u.p,
+                             (uint64_t)(uintptr_t)winv_full.p, (uint64_t)(uintptr_t)wide_norms.p});
   }
   gmrfb::DevBuf<double> arena, zarena, zwork, zdiag, nzval, xwork, ywork, bwork, owork, uvec, partial, dinv, dinv_sel;
   // panel solves: node-major panel X (MR_MAX x n), update panels U (MR_MAX x sum of r_J), column-major staging (n x MR_MAX)
   gmrfb::DevBuf<double> mr_x, mr_u, mr_io;
+  // full inverses of the wide supernodes + TRTRI scratch; |L_JJ|_1, |W_J|_1 per wide supernode (device / host);
+  // wide_ok: the last factorisation found every cond_inf(L_JJ) below the threshold => sweeps use the inverses
+  gmrfb::DevBuf<double> winv_full, wide_norms;
+  std::vector<double> wide_norms_host;
+  bool wide_ok = false;
+  double wide_cond = 0.0;
   gmrfb::DevBuf<double> meanbuf, rbmc_x, refine_ws;  // persistent workspaces of gmrfb_sample / gmrfb_var_rbmc
   bool factored = false, z_valid = false, logdet_valid = false;
   int32_t status = GMRFB_ERR_STATE;

@@ -309,6 +309,36 @@ static void plan_trtri_batch(PlanBuilder& B, Plan& P, const std::vector<TrtriPro
   }
 }
 
+// Full inverses W_J = L_JJ^{-1} of the wide supernodes (all levels in one batch: the dependent chain is
+// 2 + 2 log2(max s / 64) launches), written to arena AR_WINV at woff[J] with leading dimension ldw[J]; the scratch of
+// the merge levels lies `toff_base` doubles further in the same arena.
+void build_wide_inverse_plan(const Symbolic& S, const std::vector<int32_t>& wide, const std::vector<int64_t>& woff,
+                             const std::vector<int32_t>& ldw, int64_t toff_base, Plan& P) {
+  P = Plan();
+  if (wide.empty()) return;
+  PlanBuilder B(P);
+  B.begin(LK_SET_IDENTITY);
+  for (size_t i = 0; i < wide.size(); i++) {
+    const int sc = S.ncols(wide[i]);
+    Task t = make_task();
+    t.c = woff[i];
+    t.ldc = ldw[i];
+    t.M = sc;
+    t.N = sc;
+    t.flags = arena_flags(0, 0, AR_WINV);
+    B.add(t, cdiv(sc, 64) * cdiv(sc, 64));
+  }
+  B.end();
+  std::vector<TrtriProb> tp;
+  for (size_t i = 0; i < wide.size(); i++) {
+    const int32_t s = wide[i];
+    TrtriProb p{AR_FRONT, S.foff[s], S.ld[s], AR_WINV, woff[i], toff_base + woff[i], ldw[i], S.ncols(s)};
+    p.arenaT = AR_WINV;
+    tp.push_back(p);
+  }
+  plan_trtri_batch(B, P, tp);
+}
+
 void plan_trtri(PlanBuilder& B, Plan& P, int arenaL, int64_t loff, int ldl, int arenaW, int64_t woff, int ldw, int arenaT,
                 int64_t toff, int n) {
   TrtriProb p{arenaL, loff, ldl, arenaW, woff, toff, ldw, n};
@@ -465,7 +495,8 @@ void build_factor_plan(const Symbolic& S, Plan& P) {
 //   T    = -Z_RR L21                     (r x s)
 //   H    = I - L21' T = I + L21' Z_RR L21 (s x s)
 //   Z_RC = T L11^{-1},   Z_CC = L11^{-T} H L11^{-1}
-void build_selinv_plan(const Symbolic& S, Plan& P) {
+void build_selinv_plan(const Symbolic& S, Plan& P, const std::vector<int32_t>* wide_idx,
+                       const std::vector<int64_t>* wide_off, const std::vector<int32_t>* wide_ld) {
   PlanBuilder B(P);
   for (int lev = (int)S.levels.size() - 1; lev >= 0; lev--) {
     const auto& all = S.levels[lev].snodes;
@@ -506,12 +537,21 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
     //   Z_CC = W'W - Y' Z_RC         (s x s, lower triangle)
     // W is used for the variances only (never for the factor or the solves), where its conditioning-dependent
     // error (~cond(L11) eps) is far inside the 1e-8 tolerance and cannot propagate to posterior means.
+    // (supernodes whose full inverse the factorisation already keeps for the solves - `wide` - read it from AR_WINV)
     std::vector<int64_t> woff(sn.size()), toff(sn.size());
-    std::vector<int> ldw(sn.size());
+    std::vector<int> ldw(sn.size()), warena(sn.size(), AR_WORK);
     {
       int64_t off = 0;
       for (size_t i = 0; i < sn.size(); i++) {
         int sc = S.ncols(sn[i]);
+        const int32_t wi = wide_idx ? (*wide_idx)[sn[i]] : -1;
+        if (wi >= 0) {
+          warena[i] = AR_WINV;
+          woff[i] = (*wide_off)[wi];
+          ldw[i] = (*wide_ld)[wi];
+          toff[i] = -1;
+          continue;
+        }
         ldw[i] = (sc + 1) & ~1;
         woff[i] = off;
         off += (int64_t)ldw[i] * sc;
@@ -544,6 +584,7 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
     // W = I L11^{-1}
     B.begin(LK_SET_IDENTITY);
     for (size_t i = 0; i < sn.size(); i++) {
+      if (warena[i] != AR_WORK) continue;
       int sc = S.ncols(sn[i]);
       Task t = make_task();
       t.c = woff[i];
@@ -557,10 +598,11 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
     {
       std::vector<TrtriProb> tp;
       for (size_t i = 0; i < sn.size(); i++) {
+        if (warena[i] != AR_WORK) continue;
         int32_t s = sn[i];
         tp.push_back({AR_FRONT, S.foff[s], S.ld[s], AR_WORK, woff[i], toff[i], ldw[i], S.ncols(s)});
       }
-      plan_trtri_batch(B, P, tp);
+      if (!tp.empty()) plan_trtri_batch(B, P, tp);
     }
     B.begin(LK_GEMM_TT);  // Y' = W' L21'
     for (size_t i = 0; i < sn.size(); i++) {
@@ -579,7 +621,7 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
       t.K = sc;
       t.alpha = 1.0;
       t.beta = 0.0;
-      t.flags = arena_flags(AR_WORK, AR_FRONT, AR_ZINV) | TF_KLOW;
+      t.flags = arena_flags(warena[i], AR_FRONT, AR_ZINV) | TF_KLOW;
       B.add(t, gemm_tiles(sc, r, false, GCFG_BIG));
       P.flops += (double)sc * sc * r;
     }
@@ -607,7 +649,7 @@ void build_selinv_plan(const Symbolic& S, Plan& P) {
       t.K = sc;
       t.alpha = 1.0;
       t.beta = 0.0;
-      t.flags = arena_flags(AR_WORK, AR_WORK, AR_ZINV) | TF_TRI | TF_KLOW;
+      t.flags = arena_flags(warena[i], warena[i], AR_ZINV) | TF_TRI | TF_KLOW;
       B.add(t, gemm_tiles(sc, sc, true, GCFG_BIG));
       P.flops += (double)sc * sc * sc / 3.0;
     }

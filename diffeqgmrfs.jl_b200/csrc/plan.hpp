@@ -95,7 +95,7 @@ inline Task make_task() {
 }
 
 // Arena indices used by the sparse plans.
-enum { AR_FRONT = 0, AR_ZINV = 1, AR_WORK = 2 };
+enum { AR_FRONT = 0, AR_ZINV = 1, AR_WORK = 2, AR_WINV = 3 };
 
 // One launch that clears the parts of the frontal arena the factorisation accumulates into (runs before the scatter).
 void build_zero_plan(const Symbolic& S, Plan& P);
@@ -103,7 +103,12 @@ void build_zero_plan(const Symbolic& S, Plan& P);
 void build_factor_plan(const Symbolic& S, Plan& P);
 // Takahashi selected inversion, top-down (arena 0 = factor fronts, arena 1 = inverse fronts);
 // DIAG_OUT tasks write diag(Z) by internal column index.
-void build_selinv_plan(const Symbolic& S, Plan& P);
+// wide_idx (per supernode: index into wide_off / wide_ld or -1), when given: those supernodes' inverses W_J are read
+// from arena AR_WINV (kept by the factorisation) instead of being recomputed
+void build_selinv_plan(const Symbolic& S, Plan& P, const std::vector<int32_t>* wide_idx = nullptr,
+                       const std::vector<int64_t>* wide_off = nullptr, const std::vector<int32_t>* wide_ld = nullptr);
+void build_wide_inverse_plan(const Symbolic& S, const std::vector<int32_t>& wide, const std::vector<int64_t>& woff,
+                             const std::vector<int32_t>& ldw, int64_t toff_base, Plan& P);
 
 // Panel (multi-right-hand-side) forward / backward sweeps for nr right-hand sides held node-major with leading dimension
 // ldk (solve_mr.cu); winv_slot = Plan::winv_slot of the factor plan (kept inverses of the 64 x 64 diagonal blocks).

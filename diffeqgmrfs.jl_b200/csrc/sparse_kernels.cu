@@ -212,6 +212,165 @@ __global__ void __launch_bounds__(FS_ROWS) k_fwd_step(const Task* __restrict__ t
   }
 }
 
+// ------------------------------------------------------------------ wide supernodes: full inverse ----
+// Supernodes with many columns (the top separators: up to ~3000 columns on the 1M-node mesh) put s/64 dependent block
+// steps on the chain of every sweep - 128 launches of 10-20 us with a handful of CTAs each.  For those the
+// factorisation keeps the full inverse W_J = L_JJ^{-1} (recursive-doubling TRTRI, the same product the selected
+// inversion needs), and a sweep over J becomes two bandwidth-bound products with no dependency inside the supernode:
+//   forward : y_J = W_J x_J,            u_J -= L21 y_J
+//   backward: x_J = W_J' (t_J - L21' x_R)        (the R-part reduction stays k_bwd_rpart)
+// The explicit inverse is only used when the factorisation measured cond_1(L_JJ) = |L_JJ|_1 |W_J|_1 below a
+// threshold (api.cu); otherwise the block-step path above runs.
+// Wide task encoding: the solve-task fields, with K = leading dimension of W_J and alpha = bits of W_J's offset.
+constexpr int WG_ROWS = 32;   // rows per CTA of the row-oriented products
+constexpr int WG_CH = 128;    // vector entries staged per chunk
+
+// out[i] = sum_j A[i, j] v[j] for WG_ROWS rows per CTA: lanes = rows (contiguous in memory), the 8 warps take the
+// columns j = w (mod 8) of every staged chunk (8 independent loads in flight per thread: the product is latency bound
+// on grids of a few dozen CTAs); fixed-order reduction over the warps.
+//   TRI : A = W_J (lower triangular), v = x[C_J],  y[C_J] = result                (forward, first product)
+//   !TRI: A = L21 of the front,       v = y[C_J],  u_J -= result                  (forward, second product)
+constexpr int WG_WARPS = 8;
+template <int NRC, bool TRI>
+__global__ void __launch_bounds__(32 * WG_WARPS) k_wide_gemv(const Task* __restrict__ tasks, int ntasks, const double* __restrict__ F,
+                                                   const double* __restrict__ Wf, const double* __restrict__ v,
+                                                   double* __restrict__ ysol, int64_t ldx, double* __restrict__ uvec,
+                                                   int nr) {
+  __shared__ double vs[NRC][WG_CH];
+  __shared__ double red[WG_WARPS - 1][WG_ROWS][NRC];
+  const int tix = find_task_s(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int d = T.M, s = T.N, col0 = T.ldb;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = (blockIdx.x - T.tile0) * WG_ROWS, i = i0 + lane;
+  const int nrows = TRI ? s : d - s;
+  const int lda = TRI ? T.K : T.lda;
+  const double* __restrict__ A = TRI ? Wf + __double_as_longlong(T.alpha) : F + T.a + s;
+  const int ncols = TRI ? min(s, i0 + WG_ROWS) : s;
+  double acc[NRC];
+#pragma unroll
+  for (int q = 0; q < NRC; q++) acc[q] = 0.0;
+  for (int c0 = 0; c0 < ncols; c0 += WG_CH) {
+    __syncthreads();  // the previous chunk has been consumed
+    for (int e = tid; e < NRC * WG_CH; e += 32 * WG_WARPS) {
+      const int q = e / WG_CH, j = e % WG_CH;
+      vs[q][j] = (q < nr && c0 + j < ncols) ? v[col0 + c0 + j + q * ldx] : 0.0;
+    }
+    __syncthreads();
+    if (i < nrows) {
+      const int jn = min(WG_CH, ncols - c0);
+      const double* __restrict__ ap = A + i + (int64_t)c0 * lda;
+#pragma unroll 8
+      for (int j = warp; j < jn; j += WG_WARPS) {
+        double a = ap[(int64_t)j * lda];
+        if (TRI && c0 + j > i) a = 0.0;
+#pragma unroll
+        for (int q = 0; q < NRC; q++) acc[q] += a * vs[q][j];
+      }
+    }
+  }
+  if (warp > 0)
+#pragma unroll
+    for (int q = 0; q < NRC; q++) red[warp - 1][lane][q] = acc[q];
+  __syncthreads();
+  if (warp == 0 && i < nrows) {
+    const int r = d - s;
+    double* __restrict__ uj = uvec + T.b * NRC;
+#pragma unroll
+    for (int q = 0; q < NRC; q++) {
+      double val = acc[q];
+#pragma unroll
+      for (int w = 0; w < WG_WARPS - 1; w++) val += red[w][lane][q];
+      if (TRI) {
+        if (q < nr) ysol[col0 + i + q * ldx] = val;
+      } else {
+        uj[i + q * r] -= val;
+      }
+    }
+  }
+}
+
+// x[C_J][j] = sum_{i >= j} W_J[i, j] t'[i],  t' = t[C_J] - sum over the R-part chunks (fixed order).  One warp per
+// column (rows contiguous across lanes), 4 columns per CTA; t' is staged chunk by chunk.
+template <int NRC>
+__global__ void __launch_bounds__(128) k_wide_trmv_t(const Task* __restrict__ tasks, int ntasks,
+                                                     const double* __restrict__ Wf, const double* __restrict__ t,
+                                                     double* __restrict__ xsol, int64_t ldx,
+                                                     const double* __restrict__ partial, int nr) {
+  __shared__ double ts[NRC][WG_CH];
+  const int tix = find_task_s(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int s = T.N, col0 = T.ldb, ldw = T.K, nchunk = T.ldc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = (blockIdx.x - T.tile0) * 4, j = j0 + warp;
+  const double* __restrict__ W = Wf + __double_as_longlong(T.alpha);
+  const double* __restrict__ pj = partial + T.c;
+  double acc[NRC];
+#pragma unroll
+  for (int q = 0; q < NRC; q++) acc[q] = 0.0;
+  for (int c0 = (j0 / WG_CH) * WG_CH; c0 < s; c0 += WG_CH) {
+    __syncthreads();
+    for (int e = tid; e < NRC * WG_CH; e += 128) {
+      const int q = e / WG_CH, ii = e % WG_CH, i = c0 + ii;
+      double val = 0.0;
+      if (q < nr && i < s) {
+        val = t[col0 + i + q * ldx];
+        for (int ch = 0; ch < nchunk; ch++) val -= pj[(int64_t)ch * s * NRC + (int64_t)i * NRC + q];
+      }
+      ts[q][ii] = val;
+    }
+    __syncthreads();
+    if (j < s) {
+      const double* __restrict__ wc = W + (int64_t)j * ldw + c0;
+#pragma unroll
+      for (int ii = lane; ii < WG_CH; ii += 32) {
+        const int i = c0 + ii;
+        const double a = (i >= j && i < s) ? wc[ii] : 0.0;
+#pragma unroll
+        for (int q = 0; q < NRC; q++) acc[q] += a * ts[q][ii];
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NRC; q++) {
+    double val = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if (lane == 0 && j < s && q < nr) xsol[col0 + j + q * ldx] = val;
+  }
+}
+
+// norms[2 w] = max(norms[2 w], |L_JJ|_1 over this CTA's columns), norms[2 w + 1] likewise for W_J (w = T.aux0, the
+// index of the wide supernode): one warp per column (rows contiguous across lanes), 8 columns per CTA.  Non-negative
+// doubles order like their bit patterns, so the maximum is an integer atomicMax (order independent => deterministic).
+__global__ void __launch_bounds__(256) k_wide_norms(const Task* __restrict__ tasks, int ntasks, const double* __restrict__ F,
+                                                    const double* __restrict__ Wf, double* __restrict__ norms) {
+  const int tix = find_task_s(tasks, ntasks, blockIdx.x);
+  const Task T = tasks[tix];
+  const int s = T.N, ld = T.lda, ldw = T.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = (blockIdx.x - T.tile0) * 8 + warp;
+  if (j >= s) return;
+  const double* __restrict__ lp = F + T.a + (int64_t)j * ld;
+  const double* __restrict__ wp = Wf + __double_as_longlong(T.alpha) + (int64_t)j * ldw;
+  double sl = 0.0, sw = 0.0;
+#pragma unroll 4
+  for (int i = j + lane; i < s; i += 32) {
+    sl += fabs(lp[i]);
+    sw += fabs(wp[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+  }
+  if (lane < 2) {
+    double m = lane == 0 ? sl : sw;
+    if (!(m == m)) m = __longlong_as_double(0x7ff0000000000000LL);  // NaN counts as infinite
+    atomicMax(reinterpret_cast<unsigned long long*>(norms) + 2 * T.aux0 + lane, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
 // ------------------------------------------------------------------ fused solves of small supernodes ----
 // Supernodes whose front has order d <= SOLVE_SMALL_MAX (the large majority: 31 of 38 thousand on the 1M-node mesh,
 // a quarter of the factor's bytes) are solved by ONE WARP each, the whole panel [L11; L21] streamed once, column
@@ -749,6 +908,32 @@ cudaError_t launch_bwd_step(const Task* tasks, int ntasks, int grid, const doubl
                             int64_t ldx, const double* partial, int nr, const double* dinv, cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
   k_bwd_step<SOLVE_NRC><<<grid, 128, 0, st>>>(tasks, ntasks, F, t, xsol, ldx, partial, nr, dinv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wide_fwd(const Task* tasks, int ntasks, int grid_trmv, int grid_gemv, const double* F, const double* Wf,
+                            const double* w, double* ysol, int64_t ldx, double* uvec, int nr, cudaStream_t st) {
+  if (grid_trmv > 0) k_wide_gemv<SOLVE_NRC, true><<<grid_trmv, 32 * WG_WARPS, 0, st>>>(tasks, ntasks, F, Wf, w, ysol, ldx, uvec, nr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return cudaSuccess;
+}
+cudaError_t launch_wide_fwd_below(const Task* tasks, int ntasks, int grid, const double* F, const double* ysol, int64_t ldx,
+                                  double* uvec, int nr, cudaStream_t st) {
+  if (grid <= 0) return cudaSuccess;
+  k_wide_gemv<SOLVE_NRC, false><<<grid, 32 * WG_WARPS, 0, st>>>(tasks, ntasks, F, nullptr, ysol, nullptr, ldx, uvec, nr);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_bwd(const Task* tasks, int ntasks, int grid, const double* Wf, const double* t, double* xsol,
+                            int64_t ldx, const double* partial, int nr, cudaStream_t st) {
+  if (grid <= 0) return cudaSuccess;
+  k_wide_trmv_t<SOLVE_NRC><<<grid, 128, 0, st>>>(tasks, ntasks, Wf, t, xsol, ldx, partial, nr);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_norms(const Task* tasks, int ntasks, int grid, const double* F, const double* Wf, double* norms,
+                              cudaStream_t st) {
+  if (grid <= 0) return cudaSuccess;
+  k_wide_norms<<<grid, 256, 0, st>>>(tasks, ntasks, F, Wf, norms);
   return cudaGetLastError();
 }
 

@@ -43,6 +43,17 @@ cudaError_t launch_bwd_rpart(const Task* tasks, int ntasks, int grid, const doub
                              const double* x, int64_t ldx, double* partial, int nr, cudaStream_t st);
 cudaError_t launch_bwd_step(const Task* tasks, int ntasks, int grid, const double* F, double* t, double* xsol,
                             int64_t ldx, const double* partial, int nr, const double* dinv, cudaStream_t st);
+// wide supernodes (full inverse W_J kept by the factorisation): y_J = W_J x_J; u_J -= L21 y_J; x_J = W_J' (t_J - partials)
+constexpr int SOLVE_WIDE_MIN = 256;  // supernodes with at least this many columns keep their full inverse
+constexpr int SOLVE_WG_ROWS = 32;    // rows per CTA of the row-oriented wide products
+cudaError_t launch_wide_fwd(const Task* tasks, int ntasks, int grid_trmv, int grid_gemv, const double* F, const double* Wf,
+                            const double* w, double* ysol, int64_t ldx, double* uvec, int nr, cudaStream_t st);
+cudaError_t launch_wide_fwd_below(const Task* tasks, int ntasks, int grid, const double* F, const double* ysol, int64_t ldx,
+                                  double* uvec, int nr, cudaStream_t st);
+cudaError_t launch_wide_bwd(const Task* tasks, int ntasks, int grid, const double* Wf, const double* t, double* xsol,
+                            int64_t ldx, const double* partial, int nr, cudaStream_t st);
+cudaError_t launch_wide_norms(const Task* tasks, int ntasks, int grid, const double* F, const double* Wf, double* norms,
+                              cudaStream_t st);
 cudaError_t launch_spmv_rows(int64_t nrows, const int64_t* ptr, const int32_t* idx, const double* val,
                              const double* x, double* y, double alpha, double beta, cudaStream_t st);
 cudaError_t launch_rbmc(int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, const double* X,

@@ -88,6 +88,9 @@ enum : int32_t {
   PK_BWD_SMALL = 28,
   PK_PERM_MR = 29,
   PK_FEM = 30,
+  PK_WIDE_FWD = 37,   // wide supernodes: y = W x and u -= L21 y
+  PK_WIDE_BWD = 38,   // wide supernodes: x = W' t
+  PK_WIDE_NORM = 39,  // |L_JJ|_inf, |W_J|_inf of the wide supernodes
   PK_MAX = 40
 };
 

@@ -73,6 +73,52 @@ def test_posterior_at_scale(pkg, orc, ctx, big_problems, nx, ordering):
     assert np.linalg.norm(Q @ x - prob["rhs"]) < 1e-11 * np.linalg.norm(prob["rhs"])
 
 
+def test_wide_supernode_inverse_path(pkg, orc, ctx, big_problems, monkeypatch):
+    """Supernodes with >= 256 columns are solved through their full inverse W_J = L_JJ^{-1} (two bandwidth-bound
+    products instead of s/64 dependent block steps) when the factorisation measured cond_1(L_JJ) below the threshold.
+    Same answers as the block-step path (GMRFB_WIDE_INV=0), for 1-4 right-hand sides, all solve modes; a threshold of 1
+    forces the fallback at factorisation time; both against the oracle."""
+    prob = big_problems[601]
+    Q = prob["Qpost"]
+    n = Q.shape[0]
+    rng = np.random.default_rng(1)
+    B4 = rng.standard_normal((n, 4))
+    monkeypatch.setenv("GMRFB_WIDE_INV", "0")
+    sym0 = pkg.Symbolic(Q, ctx=ctx, coords=prob["nodes"])
+    fac0 = pkg.CholeskyFactor(sym0).factorize(Q.data)
+    l0 = ctx.launch_count
+    x0 = fac0.solve(prob["rhs"])
+    steps_launches = ctx.launch_count - l0
+    monkeypatch.setenv("GMRFB_WIDE_INV", "1")
+    sym1 = pkg.Symbolic(Q, perm=sym0.p, ctx=ctx)
+    fac1 = pkg.CholeskyFactor(sym1).factorize(Q.data)
+    l0 = ctx.launch_count
+    x1 = fac1.solve(prob["rhs"])
+    wide_launches = ctx.launch_count - l0
+    assert wide_launches < steps_launches - 40  # the dependent block-step chain of the top separators is gone
+    ref = oracle_supernodal(orc, Q, sym1)
+    xr = ref.solve(prob["rhs"])
+    assert rel(x1, xr) < TOL_SOLVE and rel(x0, xr) < TOL_SOLVE and rel(x1, x0) < 1e-12
+    assert np.linalg.norm(Q @ x1 - prob["rhs"]) < 1e-11 * np.linalg.norm(prob["rhs"])
+    for nr in (2, 3, 4):
+        assert rel(fac1.solve(B4[:, :nr]), fac0.solve(B4[:, :nr])) < 1e-12
+    for mode in ("PtL_solve", "UP_solve", "L_solve", "Lt_solve"):
+        assert rel(getattr(fac1, mode)(B4[:, :3]), getattr(fac0, mode)(B4[:, :3])) < 1e-12
+    z = rng.standard_normal(n)
+    assert rel(fac1.sample(z), fac0.sample(z)) < 1e-12
+    # repeated solves replay the captured graph of the wide schedule
+    assert np.array_equal(fac1.solve(prob["rhs"]), x1) and np.array_equal(fac1.solve(prob["rhs"]), x1)
+    # threshold 1: the next factorisation of the same handle falls back to the block steps (bit-identical to fac0)
+    monkeypatch.setenv("GMRFB_WIDE_COND_MAX", "1")
+    fac1.factorize(Q.data)
+    assert np.array_equal(fac1.solve(prob["rhs"]), x0)
+    monkeypatch.delenv("GMRFB_WIDE_COND_MAX")
+    fac1.factorize(Q.data)
+    assert np.array_equal(fac1.solve(prob["rhs"]), x1)
+    v1, v0 = fac1.var_selinv(), fac0.var_selinv()
+    assert np.max(np.abs(v1 - v0) / np.abs(v0)) < 1e-12
+
+
 @pytest.mark.parametrize("nrhs", [5, 8, 33, 50, 64, 70, 130])
 def test_panel_solves_all_modes(pkg, orc, ctx, W, nrhs):
     """Every solve mode through the panel path, for ragged panel widths (one and several panels per call)."""
