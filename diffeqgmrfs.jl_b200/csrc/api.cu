@@ -431,9 +431,11 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
       sym->wide_enabled = !(we && we[0] == '0');
       sym->wide.clear(), sym->wide_off.clear(), sym->wide_ld.clear();
       int64_t off = 0;
+      const char* wm = std::getenv("GMRFB_WIDE_MIN");
+      const int wide_min = wm ? std::max(65, std::atoi(wm)) : SOLVE_WIDE_MIN;
       if (sym->wide_enabled)
         for (int32_t s = 0; s < S.nsuper; s++) {
-          if (solve_small(s) || S.ncols(s) < SOLVE_WIDE_MIN) continue;
+          if (solve_small(s) || S.ncols(s) < wide_min) continue;
           const int sc = S.ncols(s), ldw = (sc + 1) & ~1;
           sym->wide.push_back(s);
           sym->wide_off.push_back(off);

@@ -260,12 +260,19 @@ __global__ void __launch_bounds__(32 * WG_WARPS) k_wide_gemv(const Task* __restr
     if (i < nrows) {
       const int jn = min(WG_CH, ncols - c0);
       const double* __restrict__ ap = A + i + (int64_t)c0 * lda;
-#pragma unroll 8
-      for (int j = warp; j < jn; j += WG_WARPS) {
-        double a = ap[(int64_t)j * lda];
-        if (TRI && c0 + j > i) a = 0.0;
+      // all loads of the chunk are issued before the first multiply-add (WG_CH / WG_WARPS independent loads in flight)
+      constexpr int U = WG_CH / WG_WARPS;
+      double a[U];
 #pragma unroll
-        for (int q = 0; q < NRC; q++) acc[q] += a * vs[q][j];
+      for (int u = 0; u < U; u++) {
+        const int j = warp + u * WG_WARPS;
+        a[u] = (j < jn && !(TRI && c0 + j > i)) ? ap[(int64_t)j * lda] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int j = warp + u * WG_WARPS;
+#pragma unroll
+        for (int q = 0; q < NRC; q++) acc[q] += a[u] * vs[q][j];
       }
     }
   }
@@ -322,12 +329,17 @@ __global__ void __launch_bounds__(128) k_wide_trmv_t(const Task* __restrict__ ta
     __syncthreads();
     if (j < s) {
       const double* __restrict__ wc = W + (int64_t)j * ldw + c0;
+      double a[WG_CH / 32];
 #pragma unroll
-      for (int ii = lane; ii < WG_CH; ii += 32) {
-        const int i = c0 + ii;
-        const double a = (i >= j && i < s) ? wc[ii] : 0.0;
+      for (int u = 0; u < WG_CH / 32; u++) {
+        const int ii = lane + 32 * u, i = c0 + ii;
+        a[u] = (i >= j && i < s) ? wc[ii] : 0.0;
+      }
 #pragma unroll
-        for (int q = 0; q < NRC; q++) acc[q] += a * ts[q][ii];
+      for (int u = 0; u < WG_CH / 32; u++) {
+        const int ii = lane + 32 * u;
+#pragma unroll
+        for (int q = 0; q < NRC; q++) acc[q] += a[u] * ts[q][ii];
       }
     }
   }

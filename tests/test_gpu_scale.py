@@ -74,7 +74,7 @@ def test_posterior_at_scale(pkg, orc, ctx, big_problems, nx, ordering):
 
 
 def test_wide_supernode_inverse_path(pkg, orc, ctx, big_problems, monkeypatch):
-    """Supernodes with >= 256 columns are solved through their full inverse W_J = L_JJ^{-1} (two bandwidth-bound
+    """Supernodes with >= 128 columns are solved through their full inverse W_J = L_JJ^{-1} (two bandwidth-bound
     products instead of s/64 dependent block steps) when the factorisation measured cond_1(L_JJ) below the threshold.
     Same answers as the block-step path (GMRFB_WIDE_INV=0), for 1-4 right-hand sides, all solve modes; a threshold of 1
     forces the fallback at factorisation time; both against the oracle."""
