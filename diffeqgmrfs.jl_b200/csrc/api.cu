@@ -435,7 +435,9 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
       const int wide_min = wm ? std::max(65, std::atoi(wm)) : SOLVE_WIDE_MIN;
       if (sym->wide_enabled)
         for (int32_t s = 0; s < S.nsuper; s++) {
-          if (solve_small(s) || S.ncols(s) < wide_min) continue;
+          // (beyond SOLVE_WIDE_MAX columns - the time-slice separators of a space-time precision - the s^2 doubles
+          //  of an inverse and the s^3/3 flops of its TRTRI are no longer small against the front itself)
+          if (solve_small(s) || S.ncols(s) < wide_min || S.ncols(s) > SOLVE_WIDE_MAX) continue;
           const int sc = S.ncols(s), ldw = (sc + 1) & ~1;
           sym->wide.push_back(s);
           sym->wide_off.push_back(off);
@@ -444,7 +446,12 @@ static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
           off = (off + 15) & ~(int64_t)15;
         }
       sym->wide_doubles = off;
-      if (sym->wide.empty()) sym->wide_enabled = false;
+      // inverses + TRTRI scratch must stay a small addition to the frontal arena
+      if (sym->wide.empty() || 2 * off > S.arena / 8) {
+        sym->wide.clear(), sym->wide_off.clear(), sym->wide_ld.clear();
+        sym->wide_doubles = 0;
+        sym->wide_enabled = false;
+      }
     }
     std::vector<int32_t> wide_idx(S.nsuper, -1);
     for (size_t i = 0; i < sym->wide.size(); i++) wide_idx[sym->wide[i]] = (int32_t)i;

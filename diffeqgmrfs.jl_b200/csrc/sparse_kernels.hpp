@@ -45,6 +45,7 @@ cudaError_t launch_bwd_step(const Task* tasks, int ntasks, int grid, const doubl
                             int64_t ldx, const double* partial, int nr, const double* dinv, cudaStream_t st);
 // wide supernodes (full inverse W_J kept by the factorisation): y_J = W_J x_J; u_J -= L21 y_J; x_J = W_J' (t_J - partials)
 constexpr int SOLVE_WIDE_MIN = 128;  // supernodes with at least this many columns keep their full inverse (GMRFB_WIDE_MIN)
+constexpr int SOLVE_WIDE_MAX = 4096; // ... and at most this many
 constexpr int SOLVE_WG_ROWS = 32;    // rows per CTA of the row-oriented wide products
 cudaError_t launch_wide_fwd(const Task* tasks, int ntasks, int grid_trmv, int grid_gemv, const double* F, const double* Wf,
                             const double* w, double* ysol, int64_t ldx, double* uvec, int nr, cudaStream_t st);

@@ -199,7 +199,12 @@ gmrfb_status gmrfb_fac_get_L(gmrfb_fac* fac, int32_t base, int32_t drop_zeros, i
  *   A    : X <- Q^{-1} X            `F \ b`        (scripts/solve_burger.jl:148; posterior mean)
  *   PtL  : X <- L^{-1} P X          `F.PtL \ b`    (forward_solve)
  *   UP   : X <- P' L^{-T} X         `F.UP \ z`     (backward_solve; a N(0, Q^{-1}) sample for z ~ N(0,I))
- *   L, Lt: X <- L^{-1} X, L^{-T} X in the permuted ordering (no P). */
+ *   L, Lt: X <- L^{-1} X, L^{-T} X in the permuted ordering (no P).
+ * Batches of up to 4 right-hand sides run the level-scheduled kernels; for supernodes with >= 128 columns these apply
+ * the full inverse of the diagonal block that the factorisation kept (two bandwidth-bound products per supernode
+ * instead of a chain of 64-column substitution steps) whenever the factorisation measured cond_1 of every such block
+ * below 1e5 (environment: GMRFB_WIDE_COND_MAX; GMRFB_WIDE_INV=0 disables the inverses, GMRFB_WIDE_MIN the width).
+ * Larger batches are swept as panels of up to 64 columns. */
 enum { GMRFB_SOLVE_A = 0, GMRFB_SOLVE_PTL = 1, GMRFB_SOLVE_UP = 2, GMRFB_SOLVE_L = 3, GMRFB_SOLVE_LT = 4 };
 gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int64_t ldx, int64_t nrhs);
 /* Device-pointer variant: d_X is n-by-nrhs column-major on the context's device. */
