@@ -8,8 +8,8 @@ There is no CPU fallback: importing works anywhere, but every numeric call needs
 """
 from . import _lib, dist, workloads  # noqa: F401
 from .solver import (  # noqa: F401
-    CholeskyFactor, CholeskySolverBlueprint, Context, DeviceGaussNewton, FEM1D, FEMP1, GMRF, GNCholeskySolverBlueprint, GaussNewtonOptimizer,
-    PosteriorPrecision, RBMCStrategy, SparseMatrix, Symbolic, TakahashiStrategy, TridiagonalCholeskyFactor,
+    CholeskyFactor, CholeskySolverBlueprint, Context, DeviceGaussNewton, FEM1D, FEMLagrange, FEMP1, GMRF, GNCholeskySolverBlueprint, GaussNewtonOptimizer,
+    PosteriorPrecision, RBMCStrategy, SparseMatrix, SparseProduct, Symbolic, TakahashiStrategy, TridiagonalCholeskyFactor,
     backward_solve, cholesky, condition_on_observations, default_context, forward_solve, ldiv, ldiv_, mean, metrics,
     optimize, pool_trim, precision_map, rand, sqmahal, std, to_matrix, tridiagonal_cholesky, tridiagonal_cholesky_dense, tridiagonal_cholesky_ssm, var,
 )

@@ -112,6 +112,17 @@ SIGNATURES = {
     "gmrfb_fem_assemble": (C.c_int32, [_P, _P, _P, C.POINTER(_P)]),
     "gmrfb_fem_matern_precision": (C.c_int32, [_P, C.c_double, C.c_double, _P, C.c_double, C.POINTER(_P)]),
     "gmrfb_fem_assemble_cubic": (C.c_int32, [_P, _P, C.c_int32, C.c_double, _P, C.POINTER(_P), _P]),
+    "gmrfb_spgemm_create": (C.c_int32, [_P, _P, _P, C.POINTER(_P)]),
+    "gmrfb_spgemm_destroy": (C.c_int32, [_P]),
+    "gmrfb_spgemm_compute": (C.c_int32, [_P, C.c_double, _F64P, C.POINTER(_P)]),
+    "gmrfb_fem2d_create": (C.c_int32, [_P, C.c_int32, C.c_int64, _F64P, C.c_int64, _I64P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "gmrfb_fem2d_destroy": (C.c_int32, [_P]),
+    "gmrfb_fem2d_info": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _I64P]),
+    "gmrfb_fem2d_set_coeff_grid": (C.c_int32, [_P, C.c_int64, _F64P, C.c_int64, _F64P]),
+    "gmrfb_fem2d_stiffness": (C.c_int32, [_P, _P, _P, C.c_double, C.POINTER(_P), _P]),
+    "gmrfb_fem2d_mass": (C.c_int32, [_P, C.c_int32, C.POINTER(_P), _F64P]),
+    "gmrfb_fem2d_matern_precision": (C.c_int32, [_P, C.c_double, C.c_double, C.c_int32, _P, C.c_double, C.POINTER(_P)]),
+    "gmrfb_fem2d_assemble_cubic": (C.c_int32, [_P, _P, C.c_double, _P, C.POINTER(_P), _P]),
     "gmrfb_fem1d_create": (C.c_int32, [_P, C.c_int64, C.c_int64, _I64P, _F64P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "gmrfb_fem1d_destroy": (C.c_int32, [_P]),
     "gmrfb_fem1d_mass_stiffness": (C.c_int32, [_P, C.c_int32, _P, C.POINTER(_P), C.POINTER(_P)]),

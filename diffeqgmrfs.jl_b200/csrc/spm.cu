@@ -6,6 +6,7 @@
 
 #include "common.hpp"
 #include "handles.hpp"
+#include "spgemm_kernels.cuh"
 
 using namespace gmrfb;
 
@@ -284,6 +285,76 @@ extern "C" gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps
 extern "C" gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_spm** Qpost) {
   if (!plan || !Qpost) return fail(plan ? plan->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_postprec_result: NULL argument");
   *Qpost = &plan->out;
+  return GMRFB_OK;
+}
+
+// ---------------------------------------------------------------------------- fixed-pattern product ----
+// C = alpha A diag(w) B on patterns fixed at creation: the higher Matern powers K Mt^-1 K Mt^-1 K of
+// src/spdes/shallow_water.jl:186 (commented there, needed for smoothness 2 in two dimensions,
+// scripts/darcy/solve_darcy_gmrf-fem.jl:97) and any other repeated sparse product of a prior construction.
+// Symbolic (host, once): the pattern of C, column by column, as the sorted union of the columns of A selected by the
+// rows of B(:, j).  Numeric (device): one thread per nonzero C[i, j] walks B(:, j) in ascending row order and finds
+// A[i, k] by binary search in the sorted column k of A - fixed summation order, no atomics, no product lists.
+struct gmrfb_spgemm {
+  gmrfb_ctx* ctx = nullptr;
+  const gmrfb_spm* A = nullptr;
+  const gmrfb_spm* B = nullptr;
+  gmrfb_spm out;              // owned result matrix
+  DevBuf<int32_t> d_colnz;    // column of every (CSC) nonzero of C
+  DevBuf<double> d_w;
+};
+
+extern "C" gmrfb_status gmrfb_spgemm_create(gmrfb_ctx* ctx, const gmrfb_spm* A, const gmrfb_spm* B, gmrfb_spgemm** out) {
+  if (!ctx || !A || !B || !out) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_spgemm_create: NULL argument");
+  if (A->n != B->m) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_spgemm_create: shape mismatch");
+  *out = nullptr;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t m = A->m, n = B->n;
+  std::vector<int64_t> ccolptr, crow;
+  std::vector<int32_t> colnz;
+  spgemm::product_pattern(m, n, A->colptr.data(), A->rowidx.data(), B->colptr.data(), B->rowidx.data(), ccolptr, crow, colnz);
+  std::unique_ptr<gmrfb_spgemm> P(new gmrfb_spgemm());
+  P->ctx = ctx;
+  P->A = A;
+  P->B = B;
+  gmrfb_status rc = spm_build(ctx, &P->out, m, n, ccolptr.data(), crow.data(), nullptr, 0);
+  if (rc != GMRFB_OK) return rc;
+  P->out.owned_by_plan = true;
+  GMRFB_CU(ctx, P->d_colnz.upload(colnz, ctx->stream));
+  GMRFB_CU(ctx, P->d_w.alloc((size_t)std::max<int64_t>(A->n, 1)));
+  GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));  // `colnz` is a pageable temporary
+  *out = P.release();
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_spgemm_destroy(gmrfb_spgemm* plan) {
+  if (!plan) return GMRFB_OK;
+  cudaSetDevice(plan->ctx->device);
+  cudaStreamSynchronize(plan->ctx->stream);
+  delete plan;
+  return GMRFB_OK;
+}
+
+extern "C" gmrfb_status gmrfb_spgemm_compute(gmrfb_spgemm* plan, double alpha, const double* w_diag,
+                                             const gmrfb_spm** C_out) {
+  if (!plan) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spgemm_compute: NULL plan");
+  gmrfb_ctx* ctx = plan->ctx;
+  GMRFB_CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (w_diag)  // host or device pointer (unified addressing)
+    GMRFB_CU(ctx, cudaMemcpyAsync(plan->d_w.p, w_diag, plan->A->n * sizeof(double), cudaMemcpyDefault, st));
+  const int64_t nnz = plan->out.nnz;
+  if (nnz > 0) {
+    spgemm::k_spgemm<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, plan->out.d_rowidx.p, plan->d_colnz.p, plan->A->d_colptr.p,
+                                                           plan->A->d_rowidx.p, plan->A->d_val.p, plan->B->d_colptr.p,
+                                                           plan->B->d_rowidx.p, plan->B->d_val.p,
+                                                           w_diag ? plan->d_w.p : nullptr, alpha, plan->out.d_val.p);
+    GMRFB_CU(ctx, cudaGetLastError());
+  }
+  GMRFB_CU(ctx, launch_gather_values(plan->out.d_val.p, plan->out.d_tmap.p, nnz, plan->out.d_tval.p, st));
+  ctx->launches += 2;
+  GMRFB_CU(ctx, cudaStreamSynchronize(st));
+  if (C_out) *C_out = &plan->out;
   return GMRFB_OK;
 }
 

@@ -177,6 +177,26 @@ class PosteriorPrecision:
         return SparseMatrix(None, ctx=self.ctx, _handle=out, _owner=self)
 
 
+class SparseProduct:
+    """Fixed-pattern plan for ``alpha * A * diag(w) * B`` (gmrfb_spgemm): symbolic once, numeric per call."""
+
+    def __init__(self, A: SparseMatrix, Bm: SparseMatrix):
+        self.ctx = A.ctx
+        self.A, self.B = A, Bm
+        h = C.c_void_p()
+        B.check(B.lib().gmrfb_spgemm_create(self.ctx.h, A.h, Bm.h, C.byref(h)), self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_spgemm_destroy, h)
+
+    def compute(self, alpha=1.0, w=None) -> SparseMatrix:
+        out = C.c_void_p()
+        wp = None
+        if w is not None:
+            self._w_keep, wp = B.f64(w)
+        B.check(B.lib().gmrfb_spgemm_compute(self.h, float(alpha), wp, C.byref(out)), self.ctx.h)
+        return SparseMatrix(None, ctx=self.ctx, _handle=out, _owner=self)
+
+
 class FEMP1:
     """P1 finite-element assembly on the device (gmrfb_fem): the Darcy stiffness of a new coefficient field
     (``assemble_darcy_diff_matrix``, src/problems/darcy.jl:5-63, with the nearest-index coefficient lookup of
@@ -263,6 +283,104 @@ class FEMP1:
         M = SparseMatrix(None, ctx=self.ctx, _handle=J, _owner=self)
         M.shape = (self.n, self.n)
         return out, M
+
+
+class FEMLagrange:
+    """Lagrange triangles of order 1 or 2 on the device (gmrfb_fem2d) with the cell values Ferrite computes for them
+    (isoparametric geometry, ``QuadratureRule{RefTriangle}(order + 1)``): the discretisations of src/utils.jl:20-38
+    (Darcy, ``element_order=2``) and _research/elliptic_chen24.jl:118-122.  ``nodes``: n x 2; ``elems``: E x 3 or E x 6
+    (0-based; six-node elements numbered as Ferrite's QuadraticTriangle)."""
+
+    def __init__(self, nodes, elems, order=None, quad_degree=0, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self._nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        elems = np.ascontiguousarray(elems)
+        self.order = int(order) if order is not None else {3: 1, 6: 2}[elems.shape[1]]
+        assert elems.shape[1] == (3 if self.order == 1 else 6)
+        el, ep = B.i64(elems.reshape(-1))
+        self.n = self._nodes.shape[0]
+        h = C.c_void_p()
+        B.check(B.lib().gmrfb_fem2d_create(self.ctx.h, self.order, self.n, self._nodes.ctypes.data_as(B._F64P),
+                                           elems.shape[0], ep, 0, int(quad_degree), C.byref(h)), self.ctx.h)
+        self.h = h
+        self._fin = weakref.finalize(self, B.lib().gmrfb_fem2d_destroy, h)
+        self._presc_keep = None
+        self._grid = None
+
+    def _presc(self, prescribed):
+        if prescribed is None:
+            return None
+        self._presc_keep = np.ascontiguousarray(np.asarray(prescribed) != 0, dtype=np.uint8)
+        assert self._presc_keep.size == self.n
+        return C.c_void_p(self._presc_keep.ctypes.data)
+
+    def _wrap(self, h):
+        M = SparseMatrix(None, ctx=self.ctx, _handle=h, _owner=self)
+        M.shape = (self.n, self.n)
+        return M
+
+    @property
+    def info(self):
+        o, npe, nq, nnz = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        B.check(B.lib().gmrfb_fem2d_info(self.h, C.byref(o), C.byref(npe), C.byref(nq), C.byref(nnz)), self.ctx.h)
+        return dict(order=o.value, nodes_per_element=npe.value, nquad=nq.value, nnz=nnz.value)
+
+    def set_coeff_grid(self, x_coords, y_coords):
+        x, xp = B.f64(x_coords)
+        y, yp = B.f64(y_coords)
+        B.check(B.lib().gmrfb_fem2d_set_coeff_grid(self.h, x.size, xp, y.size, yp), self.ctx.h)
+        self._grid = (x.size, y.size)
+
+    def stiffness(self, coeff_grid=None, prescribed=None, beta=1.0, load=True):
+        """``assemble_darcy_diff_matrix`` (src/problems/darcy.jl:5-63): returns ``(G, f)``; ``coeff_grid[iy, ix]``
+        (NumPy, shape (gy, gx), or a CUDA float64 tensor of that layout) is ``coeff_mat[ix, iy]`` of the reference,
+        looked up at every quadrature point; rows of ``prescribed`` dofs become identity rows with a zero load."""
+        cp = None
+        if coeff_grid is not None:
+            if hasattr(coeff_grid, "data_ptr"):
+                assert coeff_grid.is_cuda and coeff_grid.is_contiguous() and str(coeff_grid.dtype) == "torch.float64"
+                assert tuple(coeff_grid.shape) == (self._grid[1], self._grid[0])
+                _torch_ready(coeff_grid)
+                cp = C.c_void_p(coeff_grid.data_ptr())
+                self._coeff_keep = coeff_grid
+            else:
+                self._coeff_keep = np.ascontiguousarray(coeff_grid, dtype=np.float64)
+                assert self._coeff_keep.shape == (self._grid[1], self._grid[0])
+                cp = C.c_void_p(self._coeff_keep.ctypes.data)
+        f = np.empty(self.n) if load else None
+        out = C.c_void_p()
+        B.check(B.lib().gmrfb_fem2d_stiffness(self.h, cp, self._presc(prescribed), float(beta), C.byref(out),
+                                              C.c_void_p(f.ctypes.data) if load else None), self.ctx.h)
+        return self._wrap(out), f
+
+    def mass(self, lumping=0):
+        """Mass matrix (``lumping`` 0 consistent, 1 row sums, 2 scaled element diagonals, 3 = ``lump_matrix`` for this
+        order); returns ``(M, lumped vector or None)``."""
+        out = C.c_void_p()
+        ml = np.empty(self.n) if lumping else None
+        B.check(B.lib().gmrfb_fem2d_mass(self.h, int(lumping), C.byref(out), ml.ctypes.data_as(B._F64P) if lumping else None),
+                self.ctx.h)
+        return self._wrap(out), ml
+
+    def matern_precision(self, kappa, ratio, alpha=2, prescribed=None, prescribed_mass=1e-2) -> SparseMatrix:
+        """``ratio * K' Mt^-1 K`` (alpha 2) or ``ratio * K Mt^-1 K Mt^-1 K`` (alpha 3), ``K = kappa^2 Mt + G``
+        (src/spdes/shallow_water.jl:172-190); device matrix owned by this object."""
+        out = C.c_void_p()
+        B.check(B.lib().gmrfb_fem2d_matern_precision(self.h, float(kappa), float(ratio), int(alpha), self._presc(prescribed),
+                                                     float(prescribed_mass), C.byref(out)), self.ctx.h)
+        return self._wrap(out)
+
+    def assemble_cubic(self, u, prescribed=None, stiffness_scale=1.0, out=None):
+        """``(f, J)`` of ``f_and_J`` (_research/elliptic_chen24.jl:280-285) without the static load vector, with the
+        quadrature rule of the handle; see FEMP1.assemble_cubic."""
+        up, _keep_u = _vec_ptr(u, self.n)
+        if out is None:
+            out = np.empty(self.n)
+        fp, _keep_f = _vec_ptr(out, self.n)
+        J = C.c_void_p()
+        B.check(B.lib().gmrfb_fem2d_assemble_cubic(self.h, up, float(stiffness_scale), self._presc(prescribed), C.byref(J),
+                                                   fp), self.ctx.h)
+        return out, self._wrap(J)
 
 
 def _vec_ptr(v, n):

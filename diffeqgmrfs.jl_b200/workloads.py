@@ -30,6 +30,31 @@ def structured_mesh(nx: int, ny: int | None = None, jitter: float = 0.2, seed: i
     return nodes, tris
 
 
+def quadratic_mesh(nodes, tris, curve: float = 0.0, seed: int = 0):
+    """Six-node (quadratic) triangles from a P1 mesh: one new node per edge, elements numbered as Ferrite's
+    QuadraticTriangle (vertices 0, 1, 2, then the nodes on the edges (0,1), (1,2), (2,0)) - the meshes of
+    `generate_grid(QuadraticTriangle, ...)` (_research/elliptic_chen24.jl:119-120) and of Gmsh with element_order = 2
+    (src/utils.jl:20-31).  `curve` > 0 moves the interior edge nodes off the edge midpoints by up to curve * edge
+    length (seeded): genuinely isoparametric elements for the tests.  Returns (nodes6, elems6)."""
+    tris = np.asarray(tris, dtype=np.int64)
+    n = nodes.shape[0]
+    e = np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]], axis=0)
+    lo, hi = e.min(axis=1), e.max(axis=1)
+    key = lo * n + hi
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    a, b = lo[first], hi[first]
+    mid = 0.5 * (nodes[a] + nodes[b])
+    if curve > 0:
+        counts = np.bincount(inv, minlength=uniq.size)
+        d = nodes[b] - nodes[a]
+        nrm = np.stack([-d[:, 1], d[:, 0]], axis=1)
+        rng = np.random.default_rng(seed)
+        mid = mid + (counts == 2)[:, None] * (rng.random(uniq.size)[:, None] - 0.5) * 2 * curve * nrm
+    T = tris.shape[0]
+    eid = n + inv.reshape(3, T).T
+    return np.concatenate([nodes, mid], axis=0), np.concatenate([tris, eid], axis=1)
+
+
 def periodic_line_mesh(n_elems: int, order: int = 2):
     """Periodic mesh of the unit interval with `n_elems` Lagrange lines of `order` 1 or 2
     (periodic_unit_interval_discretization, src/utils.jl:42-49, with the periodic constraint condensed: the last

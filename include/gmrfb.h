@@ -278,6 +278,17 @@ gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_spm** Qpost
 /* Device pointer to the matrix values (for gmrfb_factorize_dev). */
 const double* gmrfb_spm_values_dev(const gmrfb_spm* A);
 
+/* Fixed-pattern sparse product  C = alpha * A * diag(w) * B  (w: A's column count doubles, host or device, or NULL for
+ * the identity): the repeated products of a prior construction, e.g. the third Matern power
+ * `ratio * K * Mt^-1 * K * Mt^-1 * K` (src/spdes/shallow_water.jl:186; scripts/darcy/solve_darcy_gmrf-fem.jl:97 asks
+ * for smoothness 2).  The pattern of C is computed once (symbolic, host), the values by a device kernel with a fixed
+ * summation order; A and B must outlive the plan, new values of A / B on the same patterns re-use it.  *C_out is
+ * owned by the plan. */
+typedef struct gmrfb_spgemm gmrfb_spgemm;
+gmrfb_status gmrfb_spgemm_create(gmrfb_ctx* ctx, const gmrfb_spm* A, const gmrfb_spm* B, gmrfb_spgemm** out);
+gmrfb_status gmrfb_spgemm_destroy(gmrfb_spgemm* plan);
+gmrfb_status gmrfb_spgemm_compute(gmrfb_spgemm* plan, double alpha, const double* w_diag, const gmrfb_spm** C_out);
+
 /* Evaluation metrics of src/metrics.jl:3-13 on the device: pred = E x (E = evaluation matrix, e.g. the 241 x 241 grid
  * of scripts/darcy/solve_darcy_gmrf-fem.jl:86-89,190-196; NULL: pred = x), out3 = { rmse, max_err, rel_err } of pred
  * against `truth` (ntruth values).  x and truth may be host or device pointers. */
@@ -326,6 +337,47 @@ gmrfb_status gmrfb_fem_matern_precision(gmrfb_fem* fem, double kappa, double rat
  * the last call); f_out (nnodes doubles, host or device) may be NULL. */
 gmrfb_status gmrfb_fem_assemble_cubic(gmrfb_fem* fem, const double* u, int32_t quad_degree, double stiffness_scale,
                                       const uint8_t* prescribed, const gmrfb_spm** J_out, double* f_out);
+
+/* ------------------------------------------- Lagrange triangles of order 1 / 2 --- */
+/* The discretisations the reference's scripts run: `uniform_unit_square_discretization(N; element_order = 2)` with
+ * `QuadratureRule{RefTriangle}(element_order + 1)` (src/utils.jl:20-38) for the Darcy dataset loop, and
+ * `generate_grid(QuadraticTriangle, ...)` with the same rule (_research/elliptic_chen24.jl:118-122) for the elliptic
+ * Gauss-Newton solve.  Cell values as Ferrite computes them: isoparametric geometry, physical gradients and dOmega at
+ * every quadrature point.
+ *   order : 1 (3 nodes per element) or 2 (6 nodes: vertices 0, 1, 2, then the nodes on the edges (0,1), (1,2), (2,0) -
+ *           Ferrite's QuadraticTriangle);  elems : nelem x nodes_per_element indices (`base`-based), element-major;
+ *   quad_degree : 0 = order + 1, else 1, 2, 3 or 4 (symmetric rules of 1, 3, 4 and 6 points; 3 is Dunavant's rule with
+ *           the negative centroid weight). */
+typedef struct gmrfb_fem2d gmrfb_fem2d;
+gmrfb_status gmrfb_fem2d_create(gmrfb_ctx* ctx, int32_t order, int64_t nnodes, const double* nodes, int64_t nelem,
+                                const int64_t* elems, int32_t base, int32_t quad_degree, gmrfb_fem2d** out);
+gmrfb_status gmrfb_fem2d_destroy(gmrfb_fem2d* fem);
+gmrfb_status gmrfb_fem2d_info(gmrfb_fem2d* fem, int32_t* order, int32_t* nodes_per_element, int32_t* nquad, int64_t* nnz);
+/* coefficient grid axes; every QUADRATURE POINT is mapped to its grid cell by nearest index per axis, first minimum on
+ * ties (`coeff_mat[get_xy_idcs(x, x_coords, y_coords)...]`, src/problems/darcy.jl:33-39, src/datasets/darcy.jl:30-34) */
+gmrfb_status gmrfb_fem2d_set_coeff_grid(gmrfb_fem2d* fem, int64_t gx, const double* x_coords, int64_t gy,
+                                        const double* y_coords);
+/* assemble_darcy_diff_matrix (src/problems/darcy.jl:5-63): G[i,j] = sum_q coeff(x_q) grad phi_i . grad phi_j dOmega and
+ * the load f[i] = beta sum_q phi_i dOmega.  coeff_grid: gx*gy doubles, entry ix + iy*gx = coeff_mat[ix, iy] (host or
+ * device), or NULL for a unit coefficient; prescribed: nnodes bytes (non-zero = Dirichlet dof: identity row, zero
+ * load) or NULL; load_out: nnodes doubles (host or device) or NULL.  *G_out is owned by the handle (fixed pattern,
+ * values of the last call). */
+gmrfb_status gmrfb_fem2d_stiffness(gmrfb_fem2d* fem, const double* coeff_grid, const uint8_t* prescribed, double beta,
+                                   const gmrfb_spm** G_out, double* load_out);
+/* Mass matrix on the stiffness pattern.  lumping 0: consistent, sum_q phi_i phi_j dOmega; 1: row sums of every element
+ * mass; 2: the diagonal of every element mass scaled to the element's total mass, diag(me) sum(me) / sum(diag(me));
+ * 3: what `lump_matrix(me, ip)` (src/spdes/shallow_water.jl:115) does for this order - 1 for order 1, 2 for order 2,
+ * where the row sums of the vertex functions vanish.  lumped_out (nnodes doubles, host) may be NULL. */
+gmrfb_status gmrfb_fem2d_mass(gmrfb_fem2d* fem, int32_t lumping, const gmrfb_spm** M_out, double* lumped_out);
+/* Matern prior (src/spdes/shallow_water.jl:172-190): K = kappa^2 Mt + G with the lumped mass of the order (above) and,
+ * for prescribed dofs, Mt_ii = prescribed_mass, G_ii = 1;  alpha 2: Q = ratio K' Mt^-1 K (:187), alpha 3:
+ * Q = ratio K Mt^-1 K Mt^-1 K (:186).  *Q_out is owned by the handle. */
+gmrfb_status gmrfb_fem2d_matern_precision(gmrfb_fem2d* fem, double kappa, double ratio, int32_t alpha,
+                                          const uint8_t* prescribed, double prescribed_mass, const gmrfb_spm** Q_out);
+/* f_and_J of _research/elliptic_chen24.jl:180-285 with the rule the handle was created with: J = s J_diff + J_cube,
+ * f = s J_diff u + f_cube (see gmrfb_fem_assemble_cubic); rows of prescribed dofs skipped. */
+gmrfb_status gmrfb_fem2d_assemble_cubic(gmrfb_fem2d* fem, const double* u, double stiffness_scale,
+                                        const uint8_t* prescribed, const gmrfb_spm** J_out, double* f_out);
 
 /* ------------------------------------------- 1-D finite elements (Burgers) --- */
 /* Lagrange line elements of order 1 or 2 (quadratic lines numbered left, right, middle as Ferrite's QuadraticLine;

@@ -18,7 +18,7 @@ export B200Context, B200Factor, b200_cholesky, b200_tridiagonal_cholesky, B200Tr
        B200CholeskySolverBlueprint, B200GNCholeskySolverBlueprint, forward_solve, backward_solve, ldiv, ldiv!,
        var_selinv, var_rbmc, logdet_factor, issuccess, B200SparseMatrix, to_sparse, B200FEMP1, B200FEM1D, lumped_mass,
        set_coeff_grid!, assemble_darcy, matern_precision, assemble_cubic, assemble_burgers_mass_diffusion_matrices,
-       assemble_burgers_advection_matrix, burgers_f_and_J
+       assemble_burgers_advection_matrix, burgers_f_and_J, B200FEMLagrange, assemble_mass, B200SparseProduct, product!
 
 const libgmrfb = get(ENV, "GMRFB_LIB", joinpath(@__DIR__, "..", "diffeqgmrfs.jl_b200", "libgmrfb.so"))
 
@@ -446,6 +446,104 @@ function assemble_cubic(F::B200FEMP1, u::Vector{Float64}; prescribed = nothing, 
         (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{UInt8}, Ref{Ptr{Cvoid}}, Ptr{Float64}),
         F.h, u, Int32(quad_degree), Float64(stiffness_scale), pm, out, f))
     return f, B200SparseMatrix(F.ctx, out[], F)
+end
+
+"""
+Lagrange triangles of order 1 or 2 with Ferrite's cell values (isoparametric geometry, `QuadratureRule{RefTriangle}(order + 1)`
+unless `quad_degree` says otherwise): the discretisations of src/utils.jl:20-38 and _research/elliptic_chen24.jl:118-122.
+`nodes` 2 x n, `elems` 3 x E or 6 x E node indices (1-based; six-node cells numbered as Ferrite's QuadraticTriangle).
+"""
+mutable struct B200FEMLagrange
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    n::Int
+    order::Int
+end
+
+function B200FEMLagrange(nodes::Matrix{Float64}, elems::Matrix{Int64}; order::Integer = size(elems, 1) == 3 ? 1 : 2,
+                         quad_degree::Integer = 0, ctx::B200Context = default_context())
+    size(nodes, 1) == 2 && size(elems, 1) == (order == 1 ? 3 : 6) || throw(ArgumentError("nodes must be 2 x n, elems 3 x E or 6 x E"))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve nodes elems _check(ctx, ccall((:gmrfb_fem2d_create, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Int32, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, Int32(order), size(nodes, 2), nodes, size(elems, 2), elems, 1, Int32(quad_degree), out))
+    F = B200FEMLagrange(ctx, out[], size(nodes, 2), order)
+    finalizer(f -> ccall((:gmrfb_fem2d_destroy, libgmrfb), Int32, (Ptr{Cvoid},), f.h), F)
+    return F
+end
+
+function set_coeff_grid!(F::B200FEMLagrange, x_coords::Vector{Float64}, y_coords::Vector{Float64})
+    GC.@preserve x_coords y_coords _check(F.ctx, ccall((:gmrfb_fem2d_set_coeff_grid, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}), F.h, length(x_coords), x_coords, length(y_coords), y_coords))
+    return F
+end
+
+"assemble_darcy_diff_matrix (src/problems/darcy.jl:5-63): (G, f); the coefficient `coeff_mat[ix, iy]` is looked up at every quadrature point."
+function assemble_darcy(F::B200FEMLagrange, coeff_mat::Union{Nothing,Matrix{Float64}} = nothing; prescribed = nothing,
+                        beta::Real = 1.0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    f = Vector{Float64}(undef, F.n)
+    pm, keep = _mask(prescribed, F.n)
+    cp = coeff_mat === nothing ? Ptr{Float64}(C_NULL) : pointer(coeff_mat)
+    GC.@preserve coeff_mat keep f _check(F.ctx, ccall((:gmrfb_fem2d_stiffness, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Float64, Ref{Ptr{Cvoid}}, Ptr{Float64}), F.h, cp, pm, Float64(beta), out, f))
+    return B200SparseMatrix(F.ctx, out[], F), f
+end
+
+"Mass matrix; lumping 0 consistent, 1 row sums, 2 scaled element diagonals, 3 = `lump_matrix(me, ip)` for this order: (M, lumped vector)."
+function assemble_mass(F::B200FEMLagrange; lumping::Integer = 0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    ml = Vector{Float64}(undef, F.n)
+    GC.@preserve ml _check(F.ctx, ccall((:gmrfb_fem2d_mass, libgmrfb), Int32,
+        (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}, Ptr{Float64}), F.h, Int32(lumping), out, ml))
+    return B200SparseMatrix(F.ctx, out[], F), (lumping == 0 ? nothing : ml)
+end
+
+"ratio K' Mt^-1 K (alpha = 2) or ratio K Mt^-1 K Mt^-1 K (alpha = 3), K = kappa^2 Mt + G (src/spdes/shallow_water.jl:172-190)."
+function matern_precision(F::B200FEMLagrange, kappa::Real, ratio::Real; alpha::Integer = 2, prescribed = nothing,
+                          prescribed_mass::Real = 1e-2)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    pm, keep = _mask(prescribed, F.n)
+    GC.@preserve keep _check(F.ctx, ccall((:gmrfb_fem2d_matern_precision, libgmrfb), Int32,
+        (Ptr{Cvoid}, Float64, Float64, Int32, Ptr{UInt8}, Float64, Ref{Ptr{Cvoid}}),
+        F.h, Float64(kappa), Float64(ratio), Int32(alpha), pm, Float64(prescribed_mass), out))
+    return B200SparseMatrix(F.ctx, out[], F)
+end
+
+"f_and_J of _research/elliptic_chen24.jl:280-285 without the static load vector, with the rule of the handle: (f, J)."
+function assemble_cubic(F::B200FEMLagrange, u::Vector{Float64}; prescribed = nothing, stiffness_scale::Real = 1.0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    f = Vector{Float64}(undef, F.n)
+    pm, keep = _mask(prescribed, F.n)
+    GC.@preserve u f keep _check(F.ctx, ccall((:gmrfb_fem2d_assemble_cubic, libgmrfb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Float64, Ptr{UInt8}, Ref{Ptr{Cvoid}}, Ptr{Float64}),
+        F.h, u, Float64(stiffness_scale), pm, out, f))
+    return f, B200SparseMatrix(F.ctx, out[], F)
+end
+
+"Fixed-pattern product plan  C = alpha A diag(w) B  (gmrfb_spgemm): symbolic once, `product!(plan; alpha, w)` per call."
+mutable struct B200SparseProduct
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    A::B200SparseMatrix
+    B::B200SparseMatrix
+end
+
+function B200SparseProduct(A::B200SparseMatrix, B::B200SparseMatrix)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(A.ctx, ccall((:gmrfb_spgemm_create, libgmrfb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+        A.ctx.h, A.h, B.h, out))
+    P = B200SparseProduct(A.ctx, out[], A, B)
+    finalizer(p -> ccall((:gmrfb_spgemm_destroy, libgmrfb), Int32, (Ptr{Cvoid},), p.h), P)
+    return P
+end
+
+function product!(P::B200SparseProduct; alpha::Real = 1.0, w::Union{Nothing,Vector{Float64}} = nothing)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    wp = w === nothing ? Ptr{Float64}(C_NULL) : pointer(w)
+    GC.@preserve w _check(P.ctx, ccall((:gmrfb_spgemm_compute, libgmrfb), Int32,
+        (Ptr{Cvoid}, Float64, Ptr{Float64}, Ref{Ptr{Cvoid}}), P.h, Float64(alpha), wp, out))
+    return B200SparseMatrix(P.ctx, out[], P)
 end
 
 "Lagrange lines of order 1 or 2: `elems` (order+1) x E node indices (1-based; quadratic: left, right, middle), `elem_x` their coordinates."

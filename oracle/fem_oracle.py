@@ -9,6 +9,11 @@ nonlinear FEM tangent assemblies - the producers of the Gauss-Newton Jacobians (
   * ``assemble_burgers_mass_diffusion_matrices`` src/problems/burgers.jl:61-98    (1-D, mass and stiffness)
   * the space-time tangent  J = J_static + dt J_adv,  f = J_static w + dt f_adv
                                            scripts/burgers/solve_burgers_gmrf-fem.jl:115-142
+  * ``assemble_darcy_diff_matrix``         src/problems/darcy.jl:5-63             (2-D, coefficient looked up at every
+                                           quadrature point by nearest grid index, src/datasets/darcy.jl:30-34)
+  * Lagrange triangles of order 1 AND 2 with the cell values Ferrite computes for them (isoparametric geometry,
+    ``QuadratureRule{RefTriangle}(order + 1)``, src/utils.jl:29-31, _research/elliptic_chen24.jl:118-122): the
+    ``*_lagrange`` functions below; the lumped element mass of src/spdes/shallow_water.jl:115 (``lump_matrix``)
 
 parity unpinned: the reference cannot run here (no Julia, no Ferrite) and holds no fixtures for these functions; the
 loops below follow its source line by line with Lagrange elements and Gauss rules written out (Ferrite's reference
@@ -22,12 +27,16 @@ import scipy.sparse as sp
 # ------------------------------------------------------------------------------------------ quadrature --
 def tri_quadrature(degree: int):
     """Barycentric points (nq x 3) and weights (sum 1; d Omega = weight * area) of symmetric triangle rules
-    (Strang-Fix / Dunavant) exact to `degree` in {1, 2, 4}."""
+    (Strang-Fix / Dunavant) exact to `degree` in {1, 2, 3, 4}; degree 3 is Dunavant's 4-point rule with the negative
+    centroid weight (what ``QuadratureRule{RefTriangle}(3)`` selects for quadratic triangles [RECALL])."""
     if degree == 1:
         return np.array([[1 / 3, 1 / 3, 1 / 3]]), np.array([1.0])
     if degree == 2:
         a, b = 1 / 6, 2 / 3
         return np.array([[b, a, a], [a, b, a], [a, a, b]]), np.full(3, 1 / 3)
+    if degree == 3:
+        return (np.array([[1 / 3, 1 / 3, 1 / 3], [0.6, 0.2, 0.2], [0.2, 0.6, 0.2], [0.2, 0.2, 0.6]]),
+                np.array([-27 / 48, 25 / 48, 25 / 48, 25 / 48]))
     if degree == 4:
         a1, w1 = 0.445948490915965, 0.223381589678011
         a2, w2 = 0.091576213509771, 0.109951743655322
@@ -36,7 +45,7 @@ def tri_quadrature(degree: int):
             b = 1 - 2 * a
             pts += [[b, a, a], [a, b, a], [a, a, b]]
         return np.array(pts), np.array([w1] * 3 + [w2] * 3)
-    raise ValueError("degree must be 1, 2 or 4")
+    raise ValueError("degree must be 1, 2, 3 or 4")
 
 
 def line_quadrature(npts: int):
@@ -196,3 +205,169 @@ def burgers_spacetime_tangent(x, elems, w, nt, dt, nu, order=1, nquad=None, pres
     J = (J_static + dt * J_adv).tocsc()
     J.sort_indices()
     return f, J
+
+
+# ------------------------------------------------------------------------------------------ 2-D, Lagrange triangles of order 1 / 2 --
+def tri_shapes(order: int, lam):
+    """Lagrange shape functions on the triangle at the barycentric points `lam` (nq x 3): (N, dN) with N[q, a] and
+    dN[q, a, b] = dN_a / dl_b (the three barycentric coordinates taken as independent variables).  Order 2 is numbered
+    as Ferrite's QuadraticTriangle: vertices 0, 1, 2, then the midpoints of the edges (0,1), (1,2), (2,0)."""
+    lam = np.asarray(lam, dtype=np.float64)
+    nq = lam.shape[0]
+    if order == 1:
+        return lam.copy(), np.broadcast_to(np.eye(3), (nq, 3, 3)).copy()
+    if order != 2:
+        raise ValueError("order must be 1 or 2")
+    N = np.zeros((nq, 6))
+    dN = np.zeros((nq, 6, 3))
+    for v in range(3):
+        N[:, v] = lam[:, v] * (2 * lam[:, v] - 1)
+        dN[:, v, v] = 4 * lam[:, v] - 1
+    for e, (a, b) in enumerate(((0, 1), (1, 2), (2, 0))):
+        N[:, 3 + e] = 4 * lam[:, a] * lam[:, b]
+        dN[:, 3 + e, a] = 4 * lam[:, b]
+        dN[:, 3 + e, b] = 4 * lam[:, a]
+    return N, dN
+
+
+def tri_cellvalues(nodes, elems, order, degree=None):
+    """What ``reinit!(cellvalues, cell)`` provides for every cell: N[q, a], physical gradients grad[c, q, a, :],
+    dOmega[c, q] (``getdetJdV``) and the quadrature points xq[c, q, :] (``spatial_coordinate``), with the geometry
+    interpolated by the same Lagrange basis (isoparametric).  Reference coordinates xi = l1, eta = l2."""
+    lam, wq = tri_quadrature(degree or order + 1)
+    N, dNl = tri_shapes(order, lam)
+    dref = np.stack([dNl[:, :, 1] - dNl[:, :, 0], dNl[:, :, 2] - dNl[:, :, 0]], axis=2)  # nq x npe x (xi, eta)
+    X = nodes[elems]                                        # cells x npe x 2
+    Jm = np.einsum("cad,qar->cqdr", X, dref)                # J[d, r] = d x_d / d ref_r
+    det = Jm[..., 0, 0] * Jm[..., 1, 1] - Jm[..., 0, 1] * Jm[..., 1, 0]
+    inv = np.empty_like(Jm)
+    inv[..., 0, 0], inv[..., 0, 1] = Jm[..., 1, 1], -Jm[..., 0, 1]
+    inv[..., 1, 0], inv[..., 1, 1] = -Jm[..., 1, 0], Jm[..., 0, 0]
+    inv /= det[..., None, None]
+    grad = np.einsum("qar,cqrd->cqad", dref, inv)           # [dN/dx, dN/dy] = [dN/dxi, dN/deta] J^-1
+    dO = 0.5 * np.abs(det) * wq[None, :]
+    xq = np.einsum("qa,cad->cqd", N, X)
+    return N, grad, dO, xq
+
+
+def _scatter(n, elems, Ae):
+    npe = elems.shape[1]
+    rows = np.repeat(elems[:, :, None], npe, axis=2)
+    cols = np.repeat(elems[:, None, :], npe, axis=1)
+    return _coo(n, n, rows, cols, Ae)
+
+
+def get_xy_idcs(points, x_coords, y_coords):
+    """src/datasets/darcy.jl:30-34: nearest grid index per axis, first minimum on ties (``argmin``)."""
+    ix = np.argmin(np.abs(np.asarray(x_coords)[None, :] - points[:, 0:1]), axis=1)
+    iy = np.argmin(np.abs(np.asarray(y_coords)[None, :] - points[:, 1:2]), axis=1)
+    return ix, iy
+
+
+def assemble_darcy_lagrange(nodes, elems, order, x_coords=None, y_coords=None, coeff_mat=None, beta=1.0,
+                            prescribed=None, degree=None):
+    """(G, f) of src/problems/darcy.jl:5-63: Ge[i, j] += coeff(x_q) grad phi_i . grad phi_j dOmega,
+    fe[i] += beta phi_i dOmega, the coefficient ``coeff_mat[x_idx, y_idx]`` looked up at every quadrature point (:39).
+    Dirichlet rows (``prescribed``) become identity rows with a zero load, as the host mirror does for P1."""
+    n = nodes.shape[0]
+    N, grad, dO, xq = tri_cellvalues(nodes, elems, order, degree)
+    nc, nq, npe = grad.shape[:3]
+    if coeff_mat is None:
+        cq = np.ones((nc, nq))
+    else:
+        ix, iy = get_xy_idcs(xq.reshape(-1, 2), x_coords, y_coords)
+        cq = np.asarray(coeff_mat)[ix, iy].reshape(nc, nq)
+    Ge = np.zeros((nc, npe, npe))
+    fe = np.zeros((nc, npe))
+    for q in range(nq):
+        for i in range(npe):
+            fe[:, i] += beta * N[q, i] * dO[:, q]
+            for j in range(npe):
+                Ge[:, i, j] += cq[:, q] * np.sum(grad[:, q, i] * grad[:, q, j], axis=1) * dO[:, q]
+    G = _scatter(n, elems, Ge)
+    f = np.zeros(n)
+    np.add.at(f, elems.ravel(), fe.ravel())
+    if prescribed is not None:
+        p = np.asarray(prescribed, dtype=bool)
+        G = (sp.diags((~p).astype(np.float64)) @ G + sp.diags(p.astype(np.float64))).tocsc()
+        G.sort_indices()
+        f[p] = 0.0
+    return G, f
+
+
+def assemble_mass_lagrange(nodes, elems, order, lumping=0, degree=None):
+    """Mass matrix: consistent (lumping 0), or lumped per element as src/spdes/shallow_water.jl:115 does with
+    ``lump_matrix(me, ip)`` - row sums (lumping 1: first-order elements) or the diagonal scaled to the element's total
+    mass (lumping 2: ``diag(me) * sum(me) / sum(diag(me))``, higher orders, where the row sums of the vertex functions
+    vanish) [RECALL: GaussianMarkovRandomFields.jl, not in the reference tree].  Lumped: returns the diagonal."""
+    n = nodes.shape[0]
+    N, _, dO, _ = tri_cellvalues(nodes, elems, order, degree)
+    nc, nq = dO.shape
+    npe = N.shape[1]
+    Me = np.zeros((nc, npe, npe))
+    for q in range(nq):
+        for i in range(npe):
+            for j in range(npe):
+                Me[:, i, j] += N[q, i] * N[q, j] * dO[:, q]
+    if lumping == 0:
+        return _scatter(n, elems, Me)
+    if lumping == 1:
+        ml = Me.sum(axis=2)
+    else:
+        d = np.einsum("cii->ci", Me)
+        ml = d * (Me.sum(axis=(1, 2)) / d.sum(axis=1))[:, None]
+    m = np.zeros(n)
+    np.add.at(m, elems.ravel(), ml.ravel())
+    return m
+
+
+def assemble_cubic_lagrange(nodes, elems, order, w, prescribed=None, degree=None, stiffness_scale=0.0):
+    """(J, f) with J = s J_diff + J_cube and f = s J_diff w + f_cube: ``assemble_J_cube``
+    (_research/elliptic_chen24.jl:231-278) and ``assemble_J_diff_and_f`` without its load (:180-228), rows of
+    prescribed dofs skipped (:207-209, :259-261)."""
+    n = nodes.shape[0]
+    N, grad, dO, _ = tri_cellvalues(nodes, elems, order, degree)
+    nc, nq, npe = grad.shape[:3]
+    wc = w[elems]
+    Je = np.zeros((nc, npe, npe))
+    Jd = np.zeros((nc, npe, npe))
+    ve = np.zeros((nc, npe))
+    for q in range(nq):
+        cur_u = wc @ N[q]
+        for i in range(npe):
+            for j in range(npe):
+                Je[:, i, j] += 3 * N[q, i] * cur_u**2 * N[q, j] * dO[:, q]
+                Jd[:, i, j] += np.sum(grad[:, q, i] * grad[:, q, j], axis=1) * dO[:, q]
+            ve[:, i] += N[q, i] * cur_u**3 * dO[:, q]
+    if prescribed is not None:
+        skip = np.asarray(prescribed, dtype=bool)[elems]
+        Je[skip] = 0.0
+        Jd[skip] = 0.0
+        ve[skip] = 0.0
+    J_cube, J_diff = _scatter(n, elems, Je), _scatter(n, elems, Jd)
+    f = np.zeros(n)
+    np.add.at(f, elems.ravel(), ve.ravel())
+    J = (stiffness_scale * J_diff + J_cube).tocsc()
+    J.sort_indices()
+    return J, stiffness_scale * (J_diff @ w) + f
+
+
+def matern_precision_lagrange(nodes, elems, order, kappa, ratio, alpha=2, prescribed=None, prescribed_mass=1e-2,
+                              degree=None):
+    """src/spdes/shallow_water.jl:172-190: Mt = lumped mass with Mt[dof, dof] = 1e-2 and G[dof, dof] = 1 for
+    prescribed dofs, K = kappa^2 Mt + G, Q = ratio K' Mt^-1 K (alpha 2); alpha 3 is the commented-out line :186,
+    Q = ratio K Mt^-1 K Mt^-1 K (what a Matern field of smoothness 2 in two dimensions needs,
+    scripts/darcy/solve_darcy_gmrf-fem.jl:97)."""
+    G, _ = assemble_darcy_lagrange(nodes, elems, order, degree=degree)
+    m = assemble_mass_lagrange(nodes, elems, order, lumping=1 if order == 1 else 2, degree=degree)
+    G = G.tolil()
+    if prescribed is not None:
+        for dof in np.flatnonzero(np.asarray(prescribed, dtype=bool)):
+            G[dof, dof] = 1.0
+            m[dof] = prescribed_mass
+    K = (kappa**2 * sp.diags(m) + G.tocsc()).tocsc()
+    Mi = sp.diags(1.0 / m)
+    Q = ratio * (K.T @ Mi @ K) if alpha == 2 else ratio * (K @ Mi @ K @ Mi @ K)
+    Q = Q.tocsc()
+    Q.sort_indices()
+    return Q

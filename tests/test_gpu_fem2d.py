@@ -1,0 +1,232 @@
+"""Lagrange triangles of order 1 / 2 on the device (gmrfb_fem2d_*, gmrfb_spgemm_*) against the restated element loops of
+oracle/fem_oracle.py: assemble_darcy_diff_matrix (src/problems/darcy.jl:5-63) with the coefficient looked up at every
+quadrature point, the element-lumped mass and the Matern powers of src/spdes/shallow_water.jl:115,172-190, and
+f_and_J of _research/elliptic_chen24.jl:180-285 - on the quadratic elements the reference's scripts actually use
+(src/utils.jl:20-38, element_order = 2)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def relmat(A, B):
+    return abs(A - B).max() / abs(B).max()
+
+
+def same_pattern(A, B):
+    return np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+
+
+def _mesh(W, nx, order, curve=0.0, seed=0):
+    nodes, tris = W.structured_mesh(nx, nx, seed=seed + nx)
+    return (nodes, tris) if order == 1 else W.quadratic_mesh(nodes, tris, curve=curve, seed=seed)
+
+
+def _boundary(nodes):
+    x, y = nodes[:, 0], nodes[:, 1]
+    return (x == 0) | (x == 1) | (y == 0) | (y == 1)
+
+
+@pytest.mark.parametrize("order,nx,degree,curve", [(1, 5, 0, 0.0), (1, 40, 2, 0.0), (2, 4, 0, 0.0), (2, 33, 0, 0.0),
+                                                   (2, 33, 4, 0.06), (2, 90, 3, 0.0), (1, 33, 4, 0.0), (2, 9, 2, 0.05)])
+def test_unit_stiffness_load_and_mass(pkg, orc, ctx, W, order, nx, degree, curve):
+    nodes, elems = _mesh(W, nx, order, curve)
+    fem = pkg.FEMLagrange(nodes, elems, quad_degree=degree, ctx=ctx)
+    deg = degree or order + 1
+    assert fem.info["nodes_per_element"] == (3 if order == 1 else 6)
+    assert fem.info["nquad"] == {1: 1, 2: 3, 3: 4, 4: 6}[deg]
+    Gref, fref = orc.fem.assemble_darcy_lagrange(nodes, elems, order, beta=2.5, degree=deg)
+    G, f = fem.stiffness(beta=2.5)
+    Gd = G.to_scipy()
+    assert same_pattern(Gd, Gref)
+    assert relmat(Gd, Gref) < 1e-13
+    np.testing.assert_allclose(f, fref, rtol=0, atol=1e-14 * np.abs(fref).max())
+    # mass: consistent and the three lumpings
+    Mref = orc.fem.assemble_mass_lagrange(nodes, elems, order, 0, degree=deg)
+    M, _ = fem.mass(0)
+    assert relmat(M.to_scipy(), Mref) < 1e-13
+    for kind in (1, 2):
+        mref = orc.fem.assemble_mass_lagrange(nodes, elems, order, kind, degree=deg)
+        Ml, ml = fem.mass(kind)
+        np.testing.assert_allclose(ml, mref, rtol=0, atol=1e-13 * np.abs(mref).max())
+        Mld = Ml.to_scipy()
+        np.testing.assert_allclose(Mld.diagonal(), ml, rtol=0, atol=0)
+        assert abs(Mld - sp.diags(ml)).max() == 0.0
+    _, m3 = fem.mass(3)
+    np.testing.assert_array_equal(m3, fem.mass(1 if order == 1 else 2)[1])
+    # SpMV through the row-wise copy of the device matrix
+    u = np.random.default_rng(nx).standard_normal(nodes.shape[0])
+    np.testing.assert_allclose(G.matvec(u), Gref @ u, rtol=0, atol=1e-12 * np.abs(Gref @ u).max())
+
+
+def test_order1_general_path_equals_p1_path(pkg, ctx, W):
+    """Order 1 through the general kernels against the specialised P1 assembler (same mesh, unit coefficient)."""
+    nodes, tris = W.structured_mesh(57, 57, seed=5)
+    g1 = pkg.FEMP1(nodes, tris, ctx=ctx)
+    g2 = pkg.FEMLagrange(nodes, tris, ctx=ctx)
+    A, B = g1.assemble().to_scipy(), g2.stiffness()[0].to_scipy()
+    assert same_pattern(A, B) and relmat(B, A) < 1e-13
+    np.testing.assert_allclose(g2.mass(1)[1], g1.mass, rtol=1e-13)
+    u = np.sin(3 * nodes[:, 0]) + nodes[:, 1] ** 2
+    f1, J1 = g1.assemble_cubic(u, quad_degree=2, stiffness_scale=0.7)
+    f2, J2 = g2.assemble_cubic(u, stiffness_scale=0.7)  # order + 1 = 2
+    assert relmat(J2.to_scipy(), J1.to_scipy()) < 1e-13
+    np.testing.assert_allclose(f2, f1, rtol=0, atol=1e-13 * np.abs(f1).max())
+
+
+@pytest.mark.parametrize("order,nx,seed", [(2, 21, 0), (2, 61, 3), (1, 61, 1)])
+def test_darcy_stiffness_per_quadrature_point_lookup(pkg, orc, ctx, W, order, nx, seed):
+    """Config 3's observation operator on quadratic triangles: the two-level coefficient of a 241 x 241 grid looked up
+    at every quadrature point (elements straddling a jump get both levels), identity rows on the boundary."""
+    nodes, elems = _mesh(W, nx, order)
+    g = 241
+    coeff_grid = W.darcy_problem(nx=9, seed=seed)["coeff_grid"]          # (gy, gx), levels 3 / 12
+    xc = yc = np.linspace(0, 1, g)
+    bnd = _boundary(nodes)
+    # the reference indexes coeff_mat[x_idx, y_idx]: coeff_mat = coeff_grid.T
+    Gref, fref = orc.fem.assemble_darcy_lagrange(nodes, elems, order, xc, yc, coeff_grid.T, beta=1.0, prescribed=bnd)
+    fem = pkg.FEMLagrange(nodes, elems, ctx=ctx)
+    fem.set_coeff_grid(xc, yc)
+    G, f = fem.stiffness(coeff_grid, prescribed=bnd)
+    Gd = G.to_scipy()
+    assert abs(Gd - Gref).max() < 1e-12 * abs(Gref).max()
+    np.testing.assert_allclose(f, fref, rtol=0, atol=1e-14 * np.abs(fref).max())
+    assert np.all(f[bnd] == 0.0)
+    # the lookup really is per quadrature point: a per-element (centroid) coefficient gives a different matrix
+    if order == 2:
+        N, grad, dO, xq = orc.fem.tri_cellvalues(nodes, elems, order)
+        ix, iy = orc.fem.get_xy_idcs(xq.reshape(-1, 2), xc, yc)
+        cq = coeff_grid.T[ix, iy].reshape(xq.shape[:2])
+        assert np.any(cq.min(axis=1) != cq.max(axis=1))
+    # next coefficient field of the dataset loop on the same handle, as a device tensor
+    import torch
+
+    cg2 = W.darcy_problem(nx=9, seed=seed + 7)["coeff_grid"]
+    G2ref, _ = orc.fem.assemble_darcy_lagrange(nodes, elems, order, xc, yc, cg2.T, prescribed=bnd)
+    G2, _ = fem.stiffness(torch.from_numpy(np.ascontiguousarray(cg2)).to(f"cuda:{ctx.device}"), prescribed=bnd, load=False)
+    assert abs(G2.to_scipy() - G2ref).max() < 1e-12 * abs(G2ref).max()
+
+
+def test_nearest_index_ties_and_unsorted_axes(pkg, orc, ctx, W):
+    """`argmin(abs.(coords .- x))` takes the first minimum: quadrature points exactly between two grid lines, and a
+    descending axis (the general search)."""
+    nodes, tris = W.structured_mesh(9, 9, jitter=0.0)
+    nodes6, elems6 = W.quadratic_mesh(nodes, tris)
+    rng = np.random.default_rng(2)
+    for xc, yc in ((np.linspace(0, 1, 13), np.linspace(0, 1, 25)), (np.linspace(1, 0, 17), np.linspace(0, 1, 6))):
+        cm = rng.uniform(1, 5, size=(xc.size, yc.size))                 # coeff_mat[x_idx, y_idx]
+        Gref, _ = orc.fem.assemble_darcy_lagrange(nodes6, elems6, 2, xc, yc, cm, degree=2)
+        fem = pkg.FEMLagrange(nodes6, elems6, quad_degree=2, ctx=ctx)
+        fem.set_coeff_grid(xc, yc)
+        G, _ = fem.stiffness(np.ascontiguousarray(cm.T), load=False)
+        assert abs(G.to_scipy() - Gref).max() < 1e-12 * abs(Gref).max()
+
+
+@pytest.mark.parametrize("order,nx,scale,with_bc,curve", [(2, 6, 1.0, True, 0.0), (2, 40, 0.0, False, 0.0),
+                                                          (2, 40, 2.5, True, 0.05), (1, 40, 1.0, True, 0.0)])
+def test_cubic_tangent_on_lagrange_triangles(pkg, orc, ctx, W, order, nx, scale, with_bc, curve):
+    nodes, elems = _mesh(W, nx, order, curve)
+    n = nodes.shape[0]
+    u = np.random.default_rng(nx).standard_normal(n)
+    bnd = _boundary(nodes) if with_bc else None
+    Jref, fref = orc.fem.assemble_cubic_lagrange(nodes, elems, order, u, bnd, stiffness_scale=scale)
+    fem = pkg.FEMLagrange(nodes, elems, ctx=ctx)
+    f, J = fem.assemble_cubic(u, prescribed=bnd, stiffness_scale=scale)
+    Jg = J.to_scipy()
+    assert abs(Jg - Jref).max() < 1e-13 * abs(Jref).max()
+    np.testing.assert_allclose(f, fref, rtol=0, atol=1e-13 * np.abs(fref).max())
+    if with_bc:
+        assert abs(Jg[np.flatnonzero(bnd)]).max() == 0.0 and np.all(f[bnd] == 0.0)
+    import torch
+
+    ud = torch.as_tensor(u, device="cuda")
+    fd = torch.empty(n, dtype=torch.float64, device="cuda")
+    fem.assemble_cubic(ud, prescribed=bnd, stiffness_scale=scale, out=fd)
+    assert np.array_equal(fd.cpu().numpy(), f)
+
+
+@pytest.mark.parametrize("order,nx,alpha,with_bc", [(2, 7, 2, False), (2, 25, 3, False), (1, 30, 3, False), (2, 25, 2, True),
+                                                    (2, 12, 3, True)])
+def test_matern_powers_on_device(pkg, orc, ctx, W, order, nx, alpha, with_bc):
+    nodes, elems = _mesh(W, nx, order)
+    kappa, ratio = np.sqrt(8.0) / 0.2, 0.37
+    bnd = _boundary(nodes) if with_bc else None
+    Qref = orc.fem.matern_precision_lagrange(nodes, elems, order, kappa, ratio, alpha=alpha, prescribed=bnd)
+    fem = pkg.FEMLagrange(nodes, elems, ctx=ctx)
+    Q = fem.matern_precision(kappa, ratio, alpha=alpha, prescribed=bnd).to_scipy()
+    assert abs(Q - Qref).max() < 1e-12 * abs(Qref).max()
+    assert abs(Q - Q.T).max() < 1e-12 * abs(Q).max()
+    # the prior factorises and its marginal variances are positive (what `discretize` hands to the solver); the odd
+    # power with overwritten diagonal entries of prescribed dofs is indefinite by construction (K is), so not that one
+    if not (alpha == 3 and with_bc):
+        F = pkg.cholesky(sp.csc_matrix((Q + Q.T) * 0.5), ctx=ctx)
+        assert F.issuccess() and np.all(F.var_selinv() > 0)
+    # second call on the same handle re-uses both plans
+    Q2 = fem.matern_precision(kappa * 1.3, ratio, alpha=alpha, prescribed=bnd).to_scipy()
+    Q2ref = orc.fem.matern_precision_lagrange(nodes, elems, order, kappa * 1.3, ratio, alpha=alpha, prescribed=bnd)
+    assert abs(Q2 - Q2ref).max() < 1e-12 * abs(Q2ref).max()
+
+
+def test_sparse_product_plan(pkg, ctx):
+    rng = np.random.default_rng(0)
+    A = sp.random(70, 50, density=0.08, random_state=1, format="csc")
+    Bm = sp.random(50, 90, density=0.1, random_state=2, format="csc")
+    A.sort_indices(), Bm.sort_indices()
+    w = rng.uniform(0.5, 2.0, 50)
+    Ad, Bd = pkg.SparseMatrix(A, ctx=ctx), pkg.SparseMatrix(Bm, ctx=ctx)
+    plan = pkg.SparseProduct(Ad, Bd)
+    Cref = (A @ sp.diags(w) @ Bm).tocsc()
+    C = plan.compute(alpha=-1.5, w=w).to_scipy()
+    assert abs(C + 1.5 * Cref).max() < 1e-14 * abs(Cref).max()
+    # structural pattern (no numerical cancellation dropped), columns sorted
+    S = ((abs(A) > 0).astype(np.float64) @ (abs(Bm) > 0).astype(np.float64)).tocsc()
+    S.sort_indices()
+    assert same_pattern(C, S)
+    C1 = plan.compute().to_scipy()
+    assert abs(C1 - (A @ Bm)).max() < 1e-14 * abs(Cref).max()
+
+
+def test_sparse_product_with_an_empty_factor(pkg, ctx):
+    A = sp.random(70, 50, density=0.08, random_state=1, format="csc")
+    A.sort_indices()
+    E = sp.csc_matrix((50, 90))
+    C0 = pkg.SparseProduct(pkg.SparseMatrix(A, ctx=ctx), pkg.SparseMatrix(E, ctx=ctx)).compute()
+    assert C0.dims() == (70, 90, 0)
+
+
+def test_elliptic_gauss_newton_on_quadratic_triangles(pkg, orc, ctx, W):
+    """Config 1 on the element the script uses (P2, QuadratureRule(3)): the Gauss-Newton loop with the device tangent
+    reproduces the loop driven by the restated element loops."""
+    nodes, elems = W.quadratic_mesh(*W.structured_mesh(13, 13, seed=2))
+    n = nodes.shape[0]
+    bnd = _boundary(nodes)
+    x, y = nodes[:, 0], nodes[:, 1]
+    truth = np.sin(np.pi * x) * np.sin(np.pi * y)
+    fem = pkg.FEMLagrange(nodes, elems, ctx=ctx)
+    kappa = np.sqrt(8.0) / 0.3
+    Q = fem.matern_precision(kappa, 1.0 / (4 * np.pi * kappa**2), alpha=2).to_scipy()
+    Q = sp.csc_matrix((Q + Q.T) * 0.5) + 1e4 * sp.diags(bnd.astype(np.float64))   # boundary pinned to 0 by the prior
+    # manufactured load: -lap u + u^3 with the oracle's consistent mass
+    M = orc.fem.assemble_mass_lagrange(nodes, elems, 2, 0)
+    G0, _ = orc.fem.assemble_darcy_lagrange(nodes, elems, 2)
+    load = M @ (2 * np.pi**2 * truth + truth**3)
+    load[bnd] = 0.0
+
+    def f_and_J_dev(u):
+        f, J = fem.assemble_cubic(u, prescribed=bnd)
+        return f - load, J
+
+    def f_and_J_ref(u):
+        J, f = orc.fem.assemble_cubic_lagrange(nodes, elems, 2, u, bnd, stiffness_scale=1.0)
+        return f - load, J
+
+    outs = []
+    for fj in (f_and_J_ref, f_and_J_dev):
+        gno = pkg.GaussNewtonOptimizer(np.zeros(n), Q, fj, 1e6, np.zeros(n), np.zeros(n), max_steps=6,
+                                       solver_bp=pkg.GNCholeskySolverBlueprint(ctx=ctx))
+        outs.append((pkg.optimize(gno), gno.n_steps))
+    assert outs[0][1] == outs[1][1] >= 2
+    assert np.linalg.norm(outs[1][0] - outs[0][0]) < 1e-8 * np.linalg.norm(outs[0][0])
+    # and the loop solves the PDE: P2 on a 12 x 12 mesh resolves sin(pi x) sin(pi y) to a few percent at worst
+    assert np.linalg.norm(outs[0][0] - truth) < 0.1 * np.linalg.norm(truth)

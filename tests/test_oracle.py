@@ -203,3 +203,87 @@ def test_fem_oracle_tangents_are_derivatives_of_residuals(orc, W):
         e[ns + 2] = 1e-6
         fd = (fo.burgers_spacetime_tangent(xe, el, w + e, nt, 0.01, 0.02, order)[0] - fo.burgers_spacetime_tangent(xe, el, w - e, nt, 0.01, 0.02, order)[0]) / 2e-6
         assert abs(fd - J[:, ns + 2].toarray().ravel()).max() < 1e-8
+
+
+def test_fem_oracle_lagrange_triangles(orc, W):
+    """The order-1 / order-2 triangle restatements (tri_cellvalues and the *_lagrange assemblies) pinned by what any
+    correct implementation must satisfy: agreement with the independent P1 formulas, exactness of the P2 space on
+    quadratics (energies and masses against closed-form integrals), partition of unity on curved (isoparametric)
+    elements, the Dunavant degree-3 rule integrating cubics, tangent = derivative of the residual, and the mass
+    lumpings conserving the element mass."""
+    from math import factorial
+
+    fo = orc.fem
+    lam, wq = fo.tri_quadrature(3)
+    assert abs(wq.sum() - 1) < 1e-14 and wq[0] < 0
+    for a in range(4):
+        for b in range(4 - a):
+            exact = factorial(a) * factorial(b) * 2 / factorial(a + b + 2)
+            assert abs(np.sum(wq * lam[:, 0]**a * lam[:, 1]**b) - exact) < 1e-14
+    # shape functions: Kronecker property at the six nodes, partition of unity, gradients sum to zero
+    nodes_ref = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [.5, .5, 0], [0, .5, .5], [.5, 0, .5]])
+    N, dN = fo.tri_shapes(2, nodes_ref)
+    assert abs(N - np.eye(6)).max() < 1e-15
+    Nq, dNq = fo.tri_shapes(2, lam)
+    assert abs(Nq.sum(1) - 1).max() < 1e-15
+    assert abs((dNq[:, :, 1] - dNq[:, :, 0]).sum(1)).max() < 1e-14 and abs((dNq[:, :, 2] - dNq[:, :, 0]).sum(1)).max() < 1e-14
+
+    nodes, tris = W.structured_mesh(9, 7, jitter=0.2, seed=1)
+    n6, e6 = W.quadratic_mesh(nodes, tris)
+    assert n6.shape[0] == (2 * 9 - 1) * (2 * 7 - 1) and e6.shape == (tris.shape[0], 6)
+    assert abs(n6[e6[:, 3]] - 0.5 * (n6[e6[:, 0]] + n6[e6[:, 1]])).max() < 1e-15    # Ferrite's edge numbering
+    assert abs(n6[e6[:, 4]] - 0.5 * (n6[e6[:, 1]] + n6[e6[:, 2]])).max() < 1e-15
+    assert abs(n6[e6[:, 5]] - 0.5 * (n6[e6[:, 2]] + n6[e6[:, 0]])).max() < 1e-15
+    # order 1 through the general code == the independent P1 formulas
+    m, Kp = W.p1_mass_stiffness(nodes, tris)
+    G1, f1 = fo.assemble_darcy_lagrange(nodes, tris, 1)
+    assert abs(G1 - Kp).max() < 1e-13 and abs(f1 - m).max() < 1e-15
+    w1 = np.sin(3 * nodes[:, 0]) + nodes[:, 1]
+    Jc, fc = fo.assemble_cubic_lagrange(nodes, tris, 1, w1, degree=2)
+    Jp, fp = fo.assemble_cubic_p1(nodes, tris, w1, None, 2)
+    assert abs(Jc - Jp).max() < 1e-15 and abs(fc - fp).max() < 1e-15
+    assert abs(fo.assemble_mass_lagrange(nodes, tris, 1, 1) - m).max() < 1e-15
+    # P2 reproduces quadratics: u = x^2 + xy/2 - 2y^2 + x  =>  int |grad u|^2 = 59/6, and the load integrates to the area
+    x, y = n6[:, 0], n6[:, 1]
+    u = x * x + 0.5 * x * y - 2 * y * y + x
+    G2, f2 = fo.assemble_darcy_lagrange(n6, e6, 2)
+    assert abs(u @ (G2 @ u) - 59 / 6) < 1e-12 and abs(f2.sum() - 1) < 1e-13 and abs(G2 @ np.ones(n6.shape[0])).max() < 1e-11
+    ul = 1 + 2 * x - y                                  # int ul^2 over the unit square = 8/3 (degree-4 integrand)
+    M4 = fo.assemble_mass_lagrange(n6, e6, 2, 0, degree=4)
+    assert abs(ul @ (M4 @ ul) - 8 / 3) < 1e-12
+    for deg in (3, 4):
+        for kind in (1, 2):
+            ml = fo.assemble_mass_lagrange(n6, e6, 2, kind, degree=deg)
+            assert abs(ml.sum() - 1) < 1e-12
+        assert fo.assemble_mass_lagrange(n6, e6, 2, 2, degree=deg).min() > 0
+    assert abs(fo.assemble_mass_lagrange(n6, e6, 2, 1, degree=4)[:nodes.shape[0]]).max() < 1e-15  # vertex row sums vanish
+    # curved elements: area and constants are still exact, the stiffness annihilates constants
+    n6c, e6c = W.quadratic_mesh(nodes, tris, curve=0.08, seed=3)
+    assert abs(n6c - n6).max() > 1e-3
+    Gc, fcu = fo.assemble_darcy_lagrange(n6c, e6c, 2, degree=4)
+    assert abs(fcu.sum() - 1) < 1e-12 and abs(Gc @ np.ones(n6c.shape[0])).max() < 1e-11
+    # coefficient lookup: first minimum on ties, per quadrature point
+    ix, iy = fo.get_xy_idcs(np.array([[0.25, 0.5], [0.0, 1.0]]), [0.0, 0.5, 1.0], [1.0, 0.0])
+    assert list(ix) == [0, 0] and list(iy) == [0, 0]
+    cm = np.array([[1.0, 2.0], [3.0, 4.0]])
+    Gq, _ = fo.assemble_darcy_lagrange(n6, e6, 2, [0.0, 1.0], [0.0, 1.0], cm)
+    assert abs(Gq @ np.ones(n6.shape[0])).max() < 1e-11 and abs(Gq - Gq.T).max() < 1e-12
+    lo = fo.assemble_darcy_lagrange(n6, e6, 2)[0]
+    q = np.random.default_rng(0).standard_normal(n6.shape[0])
+    assert 1.0 * (q @ (lo @ q)) < q @ (Gq @ q) < 4.0 * (q @ (lo @ q))
+    # tangent = derivative of the residual, rows of prescribed dofs skipped
+    bnd = (x == 0) | (x == 1)
+    w = np.sin(3 * x) + y
+    J, f = fo.assemble_cubic_lagrange(n6, e6, 2, w, bnd, stiffness_scale=0.7)
+    d = np.cos(5 * x) * y
+    fpl = fo.assemble_cubic_lagrange(n6, e6, 2, w + 1e-6 * d, bnd, stiffness_scale=0.7)[1]
+    fmi = fo.assemble_cubic_lagrange(n6, e6, 2, w - 1e-6 * d, bnd, stiffness_scale=0.7)[1]
+    assert abs((fpl - fmi) / 2e-6 - J @ d).max() < 1e-7 * abs(J @ d).max()
+    assert abs(J[np.flatnonzero(bnd)]).max() == 0 and np.all(f[bnd] == 0)
+    # Matern powers: symmetric positive definite (alpha 3 without prescribed dofs: overwriting G[dof, dof] = 1 makes K
+    # indefinite, which K' Mt^-1 K tolerates and the odd power does not)
+    Q2 = fo.matern_precision_lagrange(n6, e6, 2, 3.0, 0.5, alpha=2, prescribed=bnd)
+    Q3 = fo.matern_precision_lagrange(n6, e6, 2, 3.0, 0.5, alpha=3)
+    for Q in (Q2, Q3):
+        assert abs(Q - Q.T).max() < 1e-9 * abs(Q).max()
+        assert np.linalg.eigvalsh(((Q + Q.T) / 2).toarray()).min() > 0
