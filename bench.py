@@ -42,6 +42,10 @@ import __graft_entry__ as entry  # noqa: E402
 
 METRIC = "GMRF posterior (mean+marginal var) solves/sec"
 UNIT = "solves/s"
+# worker stagger of the two timed legs (see --stagger-ms / --e2e-stagger-ms; profiles/r02_stagger_ab.md)
+STAGGER_DEFAULT_MS = 0.0
+E2E_STAGGER_DEFAULT_MS = 0.0
+E2E_STAGGER_MIN_STEPS = 4
 FP64_PEAK_TFLOPS_FALLBACK = 35.5  # cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_fp64_probe.json)
 OBS_FRAC, Q_EPS, CORR_RANGE = 0.1, 1e2, 0.05
 TOL_MEAN_VS_CPU, TOL_VAR_VS_CPU = 1e-10, 1e-8  # north-star tolerances, gated at N = 1 on the 1M-node problem
@@ -257,10 +261,13 @@ class Lane:
         self.torch, self.local = torch, local
         self.xs = self.v = None
 
-    def steps_device(self, k):
-        """k posterior solves, everything resident in HBM: numeric factor + mean + selected-inversion variances."""
+    def steps_device(self, k, delay_s=0.0):
+        """k posterior solves, everything resident in HBM: numeric factor + mean + selected-inversion variances.
+        `delay_s`: see steps_e2e."""
         torch = self.torch
         torch.cuda.set_device(self.local)
+        if delay_s > 0:
+            time.sleep(delay_s)
         for _ in range(k):
             with torch.cuda.stream(self.ext):
                 self.d_x.copy_(self.d_rhs, non_blocking=True)
@@ -268,9 +275,13 @@ class Lane:
             self.fac.solve_dev(self.d_x.data_ptr(), 1)
             self.fac.var_selinv_dev(self.d_var.data_ptr())
 
-    def steps_e2e(self, k):
-        """The same through the host C-ABI calls: pinned host inputs, host outputs (H2D/D2H inside)."""
+    def steps_e2e(self, k, delay_s=0.0):
+        """The same through the host C-ABI calls: pinned host inputs, host outputs (H2D/D2H inside).  `delay_s`: this
+        lane's worker starts that much later (inside the timed region), so that the lanes' 152 MB uploads do not all
+        hit the PCIe link at the same moment with no kernels left to hide them."""
         self.torch.cuda.set_device(self.local)
+        if delay_s > 0:
+            time.sleep(delay_s)
         for _ in range(k):
             self.fac.factorize(self.nz_host.numpy())
             self.x_pin.copy_(self.rhs_host)
@@ -316,9 +327,10 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(which, k, use):
+    def timed(which, k, use, stagger_s=0.0):
         """Run k steps on each lane of `use` concurrently (one host thread per lane); device time from a start event
-        every lane's stream waits on to an end event that waits on every lane's stream."""
+        every lane's stream waits on to an end event that waits on every lane's stream.  `stagger_s`: lane b's worker
+        sleeps b * stagger_s before its first step - inside the timed region."""
         barrier()
         cur = torch.cuda.current_stream()
         e0 = torch.cuda.Event(enable_timing=True)
@@ -326,7 +338,8 @@ def run_gpu_arm(args):
         e0.record(cur)
         for L in use:
             L.ext.wait_event(e0)
-        th = [threading.Thread(target=getattr(L, which), args=(k,)) for L in use]
+        th = [threading.Thread(target=getattr(L, which), args=(k,) + ((b * stagger_s,) if stagger_s > 0 else ()))
+              for b, L in enumerate(use)]
         for t in th:
             t.start()
         for t in th:
@@ -343,7 +356,7 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
     l0 = sum(L.ctx.launch_count for L in lanes)
-    ms = timed("steps_device", args.steps, lanes)
+    ms = timed("steps_device", args.steps, lanes, stagger_s=args.stagger_ms * 1e-3)
     launches = sum(L.ctx.launch_count for L in lanes) - l0
     clocks = sampler.stop() if rank == 0 else None
     # latency of a single posterior solve with nothing else in flight
@@ -351,7 +364,9 @@ def run_gpu_arm(args):
 
     # end-to-end through the host C-ABI calls (pinned host inputs, host outputs): the same number of steps
     timed("steps_e2e", 1, lanes)
-    ms_e2e = timed("steps_e2e", args.steps, lanes) / args.steps
+    if args.e2e_stagger_ms < 0:  # auto: spread the workers over one step of the device-resident run
+        args.e2e_stagger_ms = round(ms / args.steps / (B + 1), 1) if args.steps >= E2E_STAGGER_MIN_STEPS else 0.0
+    ms_e2e = timed("steps_e2e", args.steps, lanes, stagger_s=args.e2e_stagger_ms * 1e-3) / args.steps
 
     if dist is not None:
         t = torch.tensor([ms, ms_e2e, ms_single], device=dev, dtype=torch.float64)
@@ -467,11 +482,12 @@ def run_gpu_arm(args):
                                 "ndgraph": "library nested dissection (graph bisection, no coordinates)",
                                 "nd_amd": "library nested dissection (graph) with halo-AMD leaves",
                                 "amd": "library approximate minimum degree"}[args.ordering],
-                   "problems_per_gpu_in_flight": B, "solves_per_step": B,
+                   "problems_per_gpu_in_flight": B, "solves_per_step": B, "worker_stagger_ms": args.stagger_ms,
                    "single_solve_latency_ms": ms_single,
                    "analyze_s": round(t_analyze, 2), "setup_s_outside_timing": round(t_setup, 2)},
         "e2e": {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "steps": args.steps,
-                "h2d_bytes_per_step": int(B * (Qp.nnz * 8 + n * 8)), "d2h_bytes_per_step": int(B * 2 * n * 8)},
+                "h2d_bytes_per_step": int(B * (Qp.nnz * 8 + n * 8)), "d2h_bytes_per_step": int(B * 2 * n * 8),
+                "worker_stagger_ms": args.e2e_stagger_ms},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -734,6 +750,14 @@ def main():
     ap.add_argument("--ordering", choices=["nd", "ndgraph", "nd_amd", "amd"], default="nd",
                     help="fill-reducing ordering computed once by the library and reused as perm=p (default: geometric "
                          "nested dissection with minimum-vertex-cover separators)")
+    ap.add_argument("--e2e-stagger-ms", dest="e2e_stagger_ms", type=float,
+                    default=float(os.environ.get("GMRFB_BENCH_E2E_STAGGER_MS", E2E_STAGGER_DEFAULT_MS)),
+                    help="end-to-end leg: worker b of a GPU starts b * this many milliseconds late (inside the timed "
+                         "region) so that the workers are not in lock step (all uploading, then all in their "
+                         "latency-bound top-of-tree chains at the same moment); negative = one device step / (B + 1)")
+    ap.add_argument("--stagger-ms", dest="stagger_ms", type=float,
+                    default=float(os.environ.get("GMRFB_BENCH_STAGGER_MS", STAGGER_DEFAULT_MS)),
+                    help="the same for the device-resident leg")
     ap.add_argument("--inflight", type=int, default=4,
                     help="independent posterior problems in flight per GPU (one CUDA stream each)")
     args = ap.parse_args()

@@ -134,9 +134,13 @@ __global__ void k_fem2d_geom(int64_t ne, int npe, int nq, const double* __restri
   const int q = (int)(idx - t * nq);
   const int32_t* c = conn + t * npe;
   const double* dr = dref + (size_t)q * npe * 2;
+  // J = sum_a x_a (x) dN_a/dref.  The reference derivatives sum to zero (partition of unity), so the coordinates are
+  // taken relative to the first vertex: same Jacobian in exact arithmetic, without the cancellation of absolute
+  // coordinates of size 1 in an element of size h (relative rounding error eps instead of eps / h)
+  const double x0 = nodes[2 * (int64_t)c[0]], y0 = nodes[2 * (int64_t)c[0] + 1];
   double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
-  for (int a = 0; a < npe; a++) {
-    const double x = nodes[2 * (int64_t)c[a]], y = nodes[2 * (int64_t)c[a] + 1];
+  for (int a = 1; a < npe; a++) {
+    const double x = nodes[2 * (int64_t)c[a]] - x0, y = nodes[2 * (int64_t)c[a] + 1] - y0;
     j00 += x * dr[2 * a];
     j01 += x * dr[2 * a + 1];
     j10 += y * dr[2 * a];

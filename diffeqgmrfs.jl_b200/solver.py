@@ -996,6 +996,9 @@ class GaussNewtonOptimizer:
             if J.h.value != self._Jd.h.value:
                 raise ValueError("f_and_J must return the same device matrix (fixed pattern) at every iteration")
         else:
+            if J.nnz != self._Jd.dims()[2]:
+                raise ValueError("f_and_J must return a tangent with the same sparsity pattern at every iteration "
+                                 f"({J.nnz} stored entries now, {self._Jd.dims()[2]} at the first step)")
             self._Jd.set_values(J.data)
         Apost = self._plan.compute(self.noise)
         if self._sym is None:

@@ -344,11 +344,12 @@ def assemble_cubic_lagrange(nodes, elems, order, w, prescribed=None, degree=None
         Je[skip] = 0.0
         Jd[skip] = 0.0
         ve[skip] = 0.0
-    J_cube, J_diff = _scatter(n, elems, Je), _scatter(n, elems, Jd)
+    J_diff = _scatter(n, elems, Jd)
     f = np.zeros(n)
     np.add.at(f, elems.ravel(), ve.ravel())
-    J = (stiffness_scale * J_diff + J_cube).tocsc()
-    J.sort_indices()
+    # one matrix on the pattern `allocate_matrix(dh)` gives both parts (a sparse sum would drop entries that happen to
+    # be exactly zero and change the pattern from one Gauss-Newton iterate to the next)
+    J = _scatter(n, elems, stiffness_scale * Jd + Je)
     return J, stiffness_scale * (J_diff @ w) + f
 
 
