@@ -11,6 +11,8 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdio>
@@ -122,24 +124,55 @@ void column_counts(int32_t n, const std::vector<int64_t>& xadj, const std::vecto
 // Nested dissection.
 namespace {
 
+// int32 with relaxed atomic loads and stores: `label` is the one per-vertex array a worker reads for vertices OUTSIDE its
+// own range (a neighbour across a separator may be relabelled by another worker at that moment; either value it can
+// see differs from the reader's own, unique label, so the comparison has one outcome)
+struct RelaxedI32 {
+  std::atomic<int32_t> v;
+  RelaxedI32(int32_t x = 0) : v(x) {}
+  RelaxedI32(const RelaxedI32& o) : v(o.v.load(std::memory_order_relaxed)) {}
+  RelaxedI32& operator=(const RelaxedI32& o) {
+    v.store(o.v.load(std::memory_order_relaxed), std::memory_order_relaxed);
+    return *this;
+  }
+  operator int32_t() const { return v.load(std::memory_order_relaxed); }
+  RelaxedI32& operator=(int32_t x) {
+    v.store(x, std::memory_order_relaxed);
+    return *this;
+  }
+};
+
+// per-vertex state of a dissection, shared by all workers: every open range owns a disjoint set of vertices, and a
+// worker touches `verts` positions, `lvl`, `stamp` and `posv` entries of its own range only
+struct NDShared {
+  std::vector<int32_t> verts;   // current elimination order, rearranged in place
+  std::vector<RelaxedI32> label;  // subset id of each vertex
+  std::vector<int32_t> lvl;     // BFS level scratch (valid where stamp matches)
+  std::vector<int32_t> stamp;   // visit stamp
+  std::vector<int32_t> posv;    // vertex -> position in its current range (separator refinement)
+  std::atomic<int32_t> next_label{1}, next_stamp{1};  // ids are unique across workers
+  explicit NDShared(int32_t n) : verts(n), label(n, RelaxedI32(0)), lvl(n, 0), stamp(n, 0), posv(n, 0) {
+    std::iota(verts.begin(), verts.end(), 0);
+  }
+};
+
 struct NDWork {
   int32_t n;
   const std::vector<int64_t>& xadj;
   const std::vector<int32_t>& adj;
-  std::vector<int32_t> verts;   // current elimination order, rearranged in place
-  std::vector<int32_t> label;   // subset id of each vertex
-  std::vector<int32_t> lvl;     // BFS level scratch (valid where stamp matches)
-  std::vector<int32_t> stamp;   // visit stamp
-  std::vector<int32_t> queue;
-  int32_t next_label = 1, next_stamp = 1;
+  std::vector<int32_t>& verts;
+  std::vector<RelaxedI32>& label;
+  std::vector<int32_t>& lvl;
+  std::vector<int32_t>& stamp;
+  std::vector<int32_t> queue;   // this worker's BFS queue
+  std::atomic<int32_t>& next_label;
+  std::atomic<int32_t>& next_stamp;
   int leaf;
   int coord_dim;
   const double* coords;
-  NDWork(int32_t n_, const std::vector<int64_t>& xa, const std::vector<int32_t>& a)
-      : n(n_), xadj(xa), adj(a), verts(n_), label(n_, 0), lvl(n_, 0), stamp(n_, 0) {
-    std::iota(verts.begin(), verts.end(), 0);
-    queue.reserve(n_);
-  }
+  NDWork(int32_t n_, const std::vector<int64_t>& xa, const std::vector<int32_t>& a, NDShared& sh)
+      : n(n_), xadj(xa), adj(a), verts(sh.verts), label(sh.label), lvl(sh.lvl), stamp(sh.stamp),
+        next_label(sh.next_label), next_stamp(sh.next_stamp) {}
 
   // BFS inside subset `lab` from `root`; fills queue (visit order) and lvl; returns number of levels.
   int bfs(int32_t root, int32_t lab, int32_t st, bool append) {
@@ -175,25 +208,33 @@ struct NDWork {
 
 void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::vector<int32_t>& adj,
                        int leaf, int coord_dim, const double* coords, std::vector<int32_t>& perm, bool amd_leaves) {
-  NDWork W(n, xadj, adj);
-  W.leaf = leaf > 0 ? leaf : (amd_leaves ? 200 : 24);
-  W.coord_dim = coord_dim;
-  W.coords = coords;
+  NDShared SH(n);
+  const int leaf_size = leaf > 0 ? leaf : (amd_leaves ? 200 : 24);
+  auto make_work = [&]() {
+    NDWork w(n, xadj, adj, SH);
+    w.leaf = leaf_size;
+    w.coord_dim = coord_dim;
+    w.coords = coords;
+    return w;
+  };
   struct Range {
     int32_t lo, hi;
   };
-  std::vector<Range> todo, leaves;  // leaves: ranges that are not split further
-  todo.push_back({0, n});
-  std::vector<int32_t> side;  // scratch: 0 = A, 1 = B, 2 = S for vertices of the current range (by position)
-  std::vector<int32_t> posv;  // vertex -> position in the current range (separator refinement)
-  std::vector<int32_t> tmp;
-  while (!todo.empty()) {
-    Range r = todo.back();
-    todo.pop_back();
+  struct Scratch {
+    std::vector<int32_t> side;  // 0 = A, 1 = B, 2 = S for vertices of the current range (by position)
+    std::vector<int32_t> tmp;
+  };
+  std::vector<int32_t>& posv = SH.posv;
+  // One bisection step: splits range r into A | B | S in place, pushes the open parts onto `todo`, ranges that are not
+  // split further onto `leaves`.  Everything it reads and writes belongs to the vertices of r (see NDShared), so open
+  // ranges can be processed in any order, and concurrently, with the same result.
+  auto process_range = [&](NDWork& W, Scratch& SC, Range r, std::vector<Range>& todo, std::vector<Range>& leaves) {
+    std::vector<int32_t>& side = SC.side;
+    std::vector<int32_t>& tmp = SC.tmp;
     int32_t m = r.hi - r.lo;
     if (m <= W.leaf) {  // leaf: keeps the order it inherited (BFS order of the parent bisection) unless amd_leaves
       leaves.push_back(r);
-      continue;
+      return;
     }
     int32_t lab = W.next_label++;
     for (int32_t k = r.lo; k < r.hi; k++) W.label[W.verts[k]] = lab;
@@ -330,7 +371,7 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
         // connected: q holds the BFS order from `root`, levels in W.lvl, nl levels
         if (nl < 3) {  // (near-)clique: no useful separator, treat as leaf
           leaves.push_back(r);
-          continue;
+          return;
         }
         // smallest level index mcut with |levels <= mcut| >= m/2, but keep at least one level on each side
         std::vector<int32_t> cnt(nl, 0);
@@ -392,7 +433,6 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
     // GMRFB_ND_COVER=0 restores the plain boundary separators.
     static const bool cover = !(std::getenv("GMRFB_ND_COVER") && std::getenv("GMRFB_ND_COVER")[0] == '0');
     if (cover && split_done) {
-      if ((int32_t)posv.size() != n) posv.assign(n, 0);
       for (int32_t k = 0; k < m; k++) posv[W.verts[r.lo + k]] = k;
       std::vector<int32_t> sl, bl, bid(m, -1);  // separator positions, boundary-of-B positions, position -> B id
       for (int32_t k = 0; k < m; k++)
@@ -502,7 +542,7 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
       // degenerate split (everything on one side): accept as leaf to guarantee progress
       if (ns == 0 || na + nb == 0) {
         leaves.push_back(r);
-        continue;
+        return;
       }
     }
     int32_t pa = 0, pb = na, ps = na + nb;
@@ -520,7 +560,57 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
     for (int32_t k = na + nb; k < m; k++) W.label[W.verts[r.lo + k]] = -1;
     if (nb > 0) todo.push_back({r.lo + na, r.lo + na + nb});
     if (na > 0) todo.push_back({r.lo, r.lo + na});
-  }
+  };
+
+  // Workers take open ranges (largest first) from a shared counter.  Phase 1: rounds in which every open range is split
+  // ONCE, until there are enough ranges to share out (the root alone, then its two parts side by side, then four, ...:
+  // the sequential part is about twice the root's bisection instead of one bisection per level).  Phase 2: every range
+  // is dissected depth first down to its leaves.  GMRFB_ND_THREADS (default: the hardware threads, at most 16;
+  // 1 = no worker threads).
+  int nthreads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = std::getenv("GMRFB_ND_THREADS")) nthreads = std::max(1, std::atoi(e));
+  if (n < 50000) nthreads = 1;
+  std::vector<Range> leaves;  // ranges that are not split further
+  std::vector<Range> open;
+  open.push_back({0, n});
+  auto run = [&](bool to_leaves) {
+    std::sort(open.begin(), open.end(), [](const Range& a, const Range& b) { return a.hi - a.lo > b.hi - b.lo; });
+    const int nw = (int)std::min<size_t>((size_t)nthreads, open.size());
+    std::atomic<size_t> next{0};
+    std::vector<std::vector<Range>> wleaves(nw), wopen(nw);
+    auto worker = [&](int t) {
+      NDWork W = make_work();
+      Scratch SC;
+      std::vector<Range> todo;
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= open.size()) break;
+        if (!to_leaves) {
+          process_range(W, SC, open[i], wopen[t], wleaves[t]);
+          continue;
+        }
+        todo.assign(1, open[i]);
+        while (!todo.empty()) {
+          Range r = todo.back();
+          todo.pop_back();
+          process_range(W, SC, r, todo, wleaves[t]);
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nw; t++) pool.emplace_back(worker, t);
+    worker(0);
+    for (std::thread& th : pool) th.join();
+    open.clear();
+    for (int t = 0; t < nw; t++) {
+      leaves.insert(leaves.end(), wleaves[t].begin(), wleaves[t].end());
+      open.insert(open.end(), wopen[t].begin(), wopen[t].end());
+    }
+  };
+  if (nthreads > 1)
+    while (!open.empty() && open.size() < (size_t)(2 * nthreads)) run(false);
+  if (!open.empty()) run(true);
+  NDWork W = make_work();  // (the leaf ordering below reads W.verts)
   if (amd_leaves) {
     // Halo-AMD inside every leaf subdomain: the leaf's vertices are ordered by approximate minimum degree on the leaf's
     // subgraph extended by its halo (the neighbours outside the leaf: separator vertices of the enclosing dissections,

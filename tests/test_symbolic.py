@@ -235,3 +235,22 @@ def test_amd_dense_rows_are_ordered_last(pkg, orc):
     H.setdiag(10.0)
     sym = _check(pkg, orc, H.tocsc(), ordering="amd")
     assert sym.p[-1] == m * m
+
+
+def test_nested_dissection_is_independent_of_the_worker_threads(pkg, W, monkeypatch):
+    """The dissection of disjoint vertex ranges runs on worker threads (GMRFB_ND_THREADS): every bisection reads and
+    writes the state of its own range only, so the permutation is the same for any number of workers - geometric and
+    graph bisection, with and without halo-AMD leaves (meshes above the 50 000-vertex threshold of the parallel path)."""
+    prob = W.matern_posterior(230, obs_frac=0.1, q_eps=1e2, corr_range=0.05, seed=3)
+    Q, nodes = prob["Qpost"], prob["nodes"]
+    assert Q.shape[0] > 50000
+    for ordering, coords in (("nd", nodes), ("nd", None), ("nd_amd", None)):
+        ref = None
+        for threads in (1, 3, 8):
+            monkeypatch.setenv("GMRFB_ND_THREADS", str(threads))
+            s = pkg.Symbolic(Q, coords=coords, ordering=ordering, host_only=True)
+            p = np.asarray(s.p).copy()
+            assert np.array_equal(np.sort(p), np.arange(Q.shape[0]))
+            if ref is None:
+                ref = (p, s.info.nnz_L)
+            assert np.array_equal(p, ref[0]) and s.info.nnz_L == ref[1]

@@ -87,7 +87,11 @@ try:
     mean, res["mean_s"] = timed(lambda: fac.solve(rhs), reps=3)
     r = pat @ mean - rhs
     res["mean_residual"] = float(np.linalg.norm(r) / np.linalg.norm(rhs))
-    Z = np.random.default_rng(0).standard_normal((n, 50))
+    import torch
+
+    # the normals live on the device, one sample per row, as in the dataset loop of tools/bench_configs.py (a NumPy
+    # array would add a 144 MB host transpose and a pageable upload to every call)
+    Z = torch.randn((50, n), dtype=torch.float64, device=f"cuda:{ctx.device}", generator=torch.Generator(f"cuda:{ctx.device}").manual_seed(0))
     _, res["rbmc50_first_s"] = timed(lambda: fac.var_rbmc(Apost, Z))
     v, res["rbmc50_s"] = timed(lambda: fac.var_rbmc(Apost, Z), reps=3)
     res["var_positive"] = bool(np.all(v > 0))
