@@ -236,3 +236,70 @@ def test_elliptic_gauss_newton_on_quadratic_triangles(pkg, orc, ctx, W):
     assert np.linalg.norm(outs[1][0] - outs[0][0]) < 1e-8 * np.linalg.norm(outs[0][0])
     # and the loop solves the PDE: P2 on a 12 x 12 mesh resolves sin(pi x) sin(pi y) to a few percent at worst
     assert np.linalg.norm(outs[0][0] - truth) < 0.1 * np.linalg.norm(truth)
+
+
+def test_darcy_dataset_loop_on_quadratic_triangles(pkg, orc, ctx, W):
+    """scripts/darcy/solve_darcy_gmrf-fem.jl:93-100,165-196 on the script's own discretisation (element_order = 2): Matern
+    prior of smoothness 2 built on the device, then per problem of the dataset loop the stiffness of a new coefficient
+    field (device), condition_on_observations with the device matrix, posterior mean, a sample and RBMC variances -
+    against the oracle's sparse Cholesky on the matrices of the restated element loops."""
+    nodes, elems = W.quadratic_mesh(*W.structured_mesh(21, 21, seed=0))
+    n = nodes.shape[0]
+    bnd = _boundary(nodes)
+    xc = yc = np.linspace(0, 1, 241)
+    fem = pkg.FEMLagrange(nodes, elems, ctx=ctx)
+    fem.set_coeff_grid(xc, yc)
+    kappa = np.sqrt(8.0 * 2) / 0.25
+    ratio = 1.0 / (8.0 * np.pi * kappa**4)
+    Qd = fem.matern_precision(kappa, ratio, alpha=3)
+    Qref = orc.fem.matern_precision_lagrange(nodes, elems, 2, kappa, ratio, alpha=3)
+    Qref = sp.csc_matrix((Qref + Qref.T) * 0.5)
+    Qdev = Qd.to_scipy()
+    bp = pkg.CholeskySolverBlueprint(var_strategy=pkg.RBMCStrategy(40, rng=np.random.default_rng(1)), coords=nodes, ctx=ctx)
+    x = pkg.GMRF(np.zeros(n), sp.csc_matrix((Qdev + Qdev.T) * 0.5), bp)
+    q_eps = 1e4
+    for seed in (0, 1):
+        cg = W.darcy_problem(nx=9, seed=seed)["coeff_grid"]
+        Ad, y = fem.stiffness(cg, prescribed=bnd)
+        xc_dev = pkg.condition_on_observations(x, Ad, q_eps, y)
+        m_dev = pkg.mean(xc_dev)
+        Aref, yref = orc.fem.assemble_darcy_lagrange(nodes, elems, 2, xc, yc, cg.T, prescribed=bnd)
+        Qpost = orc.posterior_precision(Qref, Aref, q_eps)
+        sym = xc_dev.solver_ref.value.precision_chol.sym
+        ch = orc.SparseCholesky(Qpost, sym.p)
+        m_ref = orc.posterior_mean(ch, Qref, Aref, q_eps, yref, np.zeros(n))
+        assert np.linalg.norm(m_dev - m_ref) < 1e-7 * np.linalg.norm(m_ref)
+        v_dev = pkg.var(xc_dev)
+        assert np.all(v_dev > 0)
+        # RBMC(40) against the exact marginal variances of the oracle: a Monte-Carlo estimate, so a loose band
+        v_ref = ch.selinv_diag()
+        assert np.median(np.abs(v_dev - v_ref) / v_ref) < 0.35
+        s = pkg.rand(np.random.default_rng(seed), xc_dev)
+        assert s.shape == (n,) and np.all(np.isfinite(s))
+
+
+def test_invalid_arguments_are_reported(pkg, ctx, W):
+    """Error behaviour at the boundary: status codes with a message, never a crash."""
+    nodes, tris = W.structured_mesh(5, 5, seed=0)
+    n6, e6 = W.quadratic_mesh(nodes, tris)
+    with pytest.raises(pkg.GmrfbError):
+        pkg.FEMLagrange(n6, e6 * 0 + n6.shape[0], ctx=ctx)  # node index out of range
+    with pytest.raises(pkg.GmrfbError):
+        pkg.FEMLagrange(n6, e6, quad_degree=7, ctx=ctx)
+    flat = n6.copy()
+    flat[:, 1] = 0.0                                   # every element degenerate: det J = 0
+    with pytest.raises(pkg.GmrfbError):
+        pkg.FEMLagrange(flat, e6, ctx=ctx)
+    lonely = np.concatenate([n6, [[2.0, 2.0]]], axis=0)  # a node that belongs to no element
+    with pytest.raises(pkg.GmrfbError):
+        pkg.FEMLagrange(lonely, e6, ctx=ctx)
+    fem = pkg.FEMLagrange(n6, e6, ctx=ctx)
+    fem._grid = (3, 3)
+    with pytest.raises(pkg.GmrfbError):                # coefficient grid before gmrfb_fem2d_set_coeff_grid
+        fem.stiffness(np.ones((3, 3)))
+    with pytest.raises(pkg.GmrfbError):
+        fem.matern_precision(-1.0, 1.0)
+    with pytest.raises(pkg.GmrfbError):
+        fem.matern_precision(1.0, 1.0, alpha=4)
+    G, f = fem.stiffness()                             # the handle is still usable afterwards
+    assert abs(f.sum() - 1.0) < 1e-12
