@@ -3,6 +3,9 @@
 //                                Q + noise*J'*J, scripts/solve_burger.jl:145)
 #include <algorithm>
 #include <memory>
+#include <thread>
+#include <climits>
+#include <cstdlib>
 
 #include "common.hpp"
 #include "handles.hpp"
@@ -186,57 +189,10 @@ extern "C" gmrfb_status gmrfb_postprec_create(gmrfb_ctx* ctx, const gmrfb_spm* Q
   *out = nullptr;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   const int64_t n = Q->n, m = A->m;
-  // rows of A (host): rowptr / (col, csc position)
-  std::vector<int64_t> rptr(m + 1, 0);
-  for (int64_t p = 0; p < A->nnz; p++) rptr[A->rowidx[p] + 1]++;
-  for (int64_t i = 0; i < m; i++) rptr[i + 1] += rptr[i];
-  std::vector<int32_t> rcol(A->nnz);
-  std::vector<int64_t> rpos(A->nnz);
-  {
-    std::vector<int64_t> fillp(rptr.begin(), rptr.end() - 1);
-    for (int64_t j = 0; j < A->n; j++)
-      for (int64_t p = A->colptr[j]; p < A->colptr[j + 1]; p++) {
-        int64_t q = fillp[A->rowidx[p]]++;
-        rcol[q] = (int32_t)j;
-        rpos[q] = p;
-      }
-  }
-  // column by column: merge pattern(Q[:,j]) with the columns i reached through shared rows k
-  struct Prod {
-    int32_t i;   // output row
-    int32_t k;   // observation row
-    int64_t pa;  // position of A[k,i]
-    int64_t pb;  // position of A[k,j]
-  };
-  std::vector<int64_t> ocolptr(n + 1, 0), qsrc, pptr, pa, pb;
+  std::vector<int64_t> ocolptr, qsrc, pptr, pa, pb;
   std::vector<int32_t> orow, prow;
-  std::vector<Prod> prods;
-  pptr.push_back(0);
-  for (int64_t j = 0; j < n; j++) {
-    prods.clear();
-    for (int64_t p = A->colptr[j]; p < A->colptr[j + 1]; p++) {
-      int32_t k = A->rowidx[p];
-      for (int64_t q = rptr[k]; q < rptr[k + 1]; q++) prods.push_back({rcol[q], k, rpos[q], p});
-    }
-    std::sort(prods.begin(), prods.end(), [](const Prod& a, const Prod& b) { return a.i < b.i || (a.i == b.i && a.k < b.k); });
-    size_t ip = 0;
-    int64_t qp = Q->colptr[j], qe = Q->colptr[j + 1];
-    while (ip < prods.size() || qp < qe) {
-      int32_t ri = ip < prods.size() ? prods[ip].i : INT32_MAX;
-      int32_t rq = qp < qe ? Q->rowidx[qp] : INT32_MAX;
-      int32_t r = std::min(ri, rq);
-      orow.push_back(r);
-      qsrc.push_back(rq == r ? qp++ : -1);
-      while (ip < prods.size() && prods[ip].i == r) {
-        prow.push_back(prods[ip].k);
-        pa.push_back(prods[ip].pa);
-        pb.push_back(prods[ip].pb);
-        ip++;
-      }
-      pptr.push_back((int64_t)prow.size());
-    }
-    ocolptr[j + 1] = (int64_t)orow.size();
-  }
+  spgemm::postprec_pattern(n, m, Q->colptr.data(), Q->rowidx.data(), A->colptr.data(), A->rowidx.data(), A->nnz, 0, ocolptr,
+                           orow, qsrc, pptr, prow, pa, pb);
   std::unique_ptr<gmrfb_postprec> P(new gmrfb_postprec());
   P->ctx = ctx;
   P->Q = Q;

@@ -131,10 +131,6 @@ struct RelaxedI32 {
   std::atomic<int32_t> v;
   RelaxedI32(int32_t x = 0) : v(x) {}
   RelaxedI32(const RelaxedI32& o) : v(o.v.load(std::memory_order_relaxed)) {}
-  RelaxedI32& operator=(const RelaxedI32& o) {
-    v.store(o.v.load(std::memory_order_relaxed), std::memory_order_relaxed);
-    return *this;
-  }
   operator int32_t() const { return v.load(std::memory_order_relaxed); }
   RelaxedI32& operator=(int32_t x) {
     v.store(x, std::memory_order_relaxed);

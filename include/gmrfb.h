@@ -125,7 +125,10 @@ typedef struct gmrfb_analyze_opts {
 /* Analyse the pattern of a symmetric n-by-n matrix.  `perm` (length n, `base`-based, new->old as in
  * Julia/CHOLMOD: row k of the permuted matrix is row perm[k] of A) is required for ORDER_GIVEN and
  * ignored otherwise.  Produces: the fill-reducing permutation, elimination tree, column counts,
- * supernode partition and every index map the numeric phases need (uploaded to the device once). */
+ * supernode partition and every index map the numeric phases need (uploaded to the device once).
+ * The data-parallel phases run as CUDA kernels on the context's device; the nested dissection runs on host worker
+ * threads (environment: GMRFB_ND_THREADS, default the hardware threads, at most 16; the permutation does not depend on
+ * it).  The host-side plan builders of gmrfb_postprec_create / gmrfb_spgemm_create use GMRFB_HOST_THREADS likewise. */
 gmrfb_status gmrfb_analyze(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
                            const int64_t* perm, const gmrfb_analyze_opts* opts, gmrfb_sym** out);
 gmrfb_status gmrfb_sym_destroy(gmrfb_sym* sym);

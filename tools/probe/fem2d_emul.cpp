@@ -149,4 +149,24 @@ int64_t emul_spgemm(int64_t m, int64_t k, int64_t n, const int64_t* acolptr, con
   });
   return nnz;
 }
+
+// Qpost = Q + A' diag(w) A through the plan of spgemm::postprec_pattern with `nthreads` workers; values by the formula of
+// k_postprec (sparse_kernels.cu).  First call with orow_out == NULL returns nnz(Qpost).
+int64_t emul_postprec(int64_t n, int64_t m, const int64_t* qcolptr, const int32_t* qrow, const double* qval,
+                      const int64_t* acolptr, const int32_t* arow, const double* aval, int64_t nnzA, const double* w,
+                      int nthreads, int64_t* ocolptr_out, int32_t* orow_out, double* oval) {
+  std::vector<int64_t> ocolptr, qsrc, pptr, pa, pb;
+  std::vector<int32_t> orow, prow;
+  spgemm::postprec_pattern(n, m, qcolptr, qrow, acolptr, arow, nnzA, nthreads, ocolptr, orow, qsrc, pptr, prow, pa, pb);
+  const int64_t nnz = (int64_t)orow.size();
+  if (!orow_out) return nnz;
+  std::memcpy(ocolptr_out, ocolptr.data(), (n + 1) * sizeof(int64_t));
+  std::memcpy(orow_out, orow.data(), nnz * sizeof(int32_t));
+  for (int64_t k = 0; k < nnz; k++) {
+    double v = qsrc[k] >= 0 ? qval[qsrc[k]] : 0.0;
+    for (int64_t t = pptr[k]; t < pptr[k + 1]; t++) v += w[prow[t]] * aval[pa[t]] * aval[pb[t]];
+    oval[k] = v;
+  }
+  return nnz;
+}
 }

@@ -194,6 +194,61 @@ assert np.array_equal(Cm.indptr, S.indptr) and np.array_equal(Cm.indices, S.indi
 e = abs(Cm + 1.5 * Cref).max() / abs(Cref).max()
 print("spgemm", "%.1e" % e, "empty:", spgemm(A, sp.csc_matrix((50, 90))).nnz)
 worst = max(worst, e)
+# posterior-precision plan: same result for any number of builder threads, equal to Q + A' W A
+L.emul_postprec.restype = C.c_int64
+L.emul_postprec.argtypes = [C.c_int64, C.c_int64, P, P, P, P, P, P, C.c_int64, P, C.c_int, P, P, P]
+
+
+def postprec(Q, A, w, threads):
+    Q, A = Q.tocsc(), A.tocsc()
+    Q.sort_indices(), A.sort_indices()
+    qc, qr, qv = Q.indptr.astype(np.int64), Q.indices.astype(np.int32), Q.data.astype(np.float64)
+    ac, ar, av = A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.astype(np.float64)
+    n, m = Q.shape[0], A.shape[0]
+    wv = np.ascontiguousarray(w, dtype=np.float64)
+    nnz = L.emul_postprec(n, m, ptr(qc), ptr(qr), ptr(qv), ptr(ac), ptr(ar), ptr(av), A.nnz, ptr(wv), threads, None, None, None)
+    cp, cr, cv = np.empty(n + 1, dtype=np.int64), np.empty(nnz, dtype=np.int32), np.empty(nnz)
+    L.emul_postprec(n, m, ptr(qc), ptr(qr), ptr(qv), ptr(ac), ptr(ar), ptr(av), A.nnz, ptr(wv), threads, ptr(cp), ptr(cr), ptr(cv))
+    return sp.csc_matrix((cv, cr, cp), shape=(n, n))
+
+
+for (mq, nq_, dens) in ((60, 40, 0.1), (500, 700, 0.01), (1, 1, 1.0)):
+    Aobs = sp.random(mq, nq_, density=dens, random_state=3, format="csc")
+    Qp = sp.random(nq_, nq_, density=dens, random_state=4, format="csc")
+    Qp = (Qp + Qp.T + sp.identity(nq_)).tocsc()
+    wobs = rng.uniform(0.5, 2.0, mq)
+    ref = (Qp + Aobs.T @ sp.diags(wobs) @ Aobs).tocsc()
+    outs = [postprec(Qp, Aobs, wobs, t) for t in (1, 2, 3, 7)]
+    for o in outs[1:]:
+        assert np.array_equal(o.indptr, outs[0].indptr) and np.array_equal(o.indices, outs[0].indices)
+        assert np.array_equal(o.data, outs[0].data)
+    e = abs(outs[0] - ref).max() / abs(ref).max()
+    print("postprec", mq, nq_, "%.1e" % e, "nnz", outs[0].nnz)
+    worst = max(worst, e)
+nodes_, tris_ = W.structured_mesh(40, 40, seed=1)
+n6_, e6_ = W.quadratic_mesh(nodes_, tris_)
+G_, _ = fo.assemble_darcy_lagrange(n6_, e6_, 2)
+Q_ = fo.matern_precision_lagrange(n6_, e6_, 2, 5.0, 0.1, alpha=2)
+w_ = rng.uniform(0.5, 2.0, n6_.shape[0])
+o1, o5 = postprec(Q_, G_, w_, 1), postprec(Q_, G_, w_, 5)
+assert np.array_equal(o1.indices, o5.indices) and np.array_equal(o1.data, o5.data)
+ref = (Q_ + G_.T @ sp.diags(w_) @ G_).tocsc()
+e = abs(o1 - ref).max() / abs(ref).max()
+print("postprec P2 mesh", "%.1e" % e)
+worst = max(worst, e)
+# sparse-product pattern: the same for any number of builder threads (n >= 20000 takes the threaded path)
+Kbig = fo.assemble_darcy_lagrange(*W.quadratic_mesh(*W.structured_mesh(80, 80, seed=2)), 2)[0]
+pats = []
+for th in ("1", "3", "8"):
+    os.environ["GMRFB_HOST_THREADS"] = th
+    Cb = spgemm(Kbig, Kbig)
+    pats.append(Cb)
+os.environ.pop("GMRFB_HOST_THREADS")
+for o in pats[1:]:
+    assert np.array_equal(o.indptr, pats[0].indptr) and np.array_equal(o.indices, pats[0].indices) and np.array_equal(o.data, pats[0].data)
+e = abs(pats[0] - Kbig @ Kbig).max() / abs(Kbig @ Kbig).max()
+print("spgemm threaded pattern", Kbig.shape[0], "%.1e" % e)
+worst = max(worst, e)
 print("worst relative difference", "%.2e" % worst)
 assert worst < 1e-12
 print("OK")
