@@ -117,83 +117,6 @@ def boundary(nodes):
     return (x == 0) | (x == 1) | (y == 0) | (y == 1)
 
 
-worst = 0.0
-for order, nx, degree, curve in [(1, 5, 0, 0.0), (1, 40, 2, 0.0), (2, 4, 0, 0.0), (2, 33, 0, 0.0), (2, 33, 4, 0.06),
-                                 (2, 60, 3, 0.0), (1, 33, 4, 0.0), (2, 9, 2, 0.05)]:
-    nodes, elems = mesh(nx, order, curve)
-    deg = degree or order + 1
-    E = Emul(nodes, elems, order, degree)
-    Gref, fref = fo.assemble_darcy_lagrange(nodes, elems, order, beta=2.5, degree=deg)
-    G, f = E.stiffness(beta=2.5)
-    assert np.array_equal(G.indptr, Gref.indptr) and np.array_equal(G.indices, Gref.indices), "pattern"
-    e = [relmat(G, Gref), abs(f - fref).max() / abs(fref).max()]
-    e.append(relmat(E.mass(0)[0], fo.assemble_mass_lagrange(nodes, elems, order, 0, degree=deg)))
-    for kind in (1, 2):
-        mref = fo.assemble_mass_lagrange(nodes, elems, order, kind, degree=deg)
-        Ml, ml = E.mass(kind)
-        e.append(abs(ml - mref).max() / abs(mref).max())
-        assert abs(Ml - sp.diags(ml)).max() == 0
-    print("unit", order, nx, deg, curve, ["%.1e" % v for v in e])
-    worst = max(worst, max(e))
-
-for order, nx, seed in [(2, 21, 0), (2, 61, 3), (1, 61, 1)]:
-    nodes, elems = mesh(nx, order)
-    cg = W.darcy_problem(nx=9, seed=seed)["coeff_grid"]
-    xc = yc = np.linspace(0, 1, 241)
-    bnd = boundary(nodes)
-    Gref, fref = fo.assemble_darcy_lagrange(nodes, elems, order, xc, yc, cg.T, beta=1.0, prescribed=bnd)
-    E = Emul(nodes, elems, order)
-    E.set_grid(xc, yc)
-    G, f = E.stiffness(cg, presc=bnd)            # row-major (gy, gx) = entry ix + iy gx
-    e = [abs(G - Gref).max() / abs(Gref).max(), abs(f - fref).max() / abs(fref).max()]
-    print("darcy", order, nx, ["%.1e" % v for v in e])
-    worst = max(worst, max(e))
-
-nodes, tris = W.structured_mesh(9, 9, jitter=0.0)
-n6, e6 = W.quadratic_mesh(nodes, tris)
-rng = np.random.default_rng(2)
-for xc, yc in ((np.linspace(0, 1, 13), np.linspace(0, 1, 25)), (np.linspace(1, 0, 17), np.linspace(0, 1, 6))):
-    cm = rng.uniform(1, 5, size=(xc.size, yc.size))
-    Gref, _ = fo.assemble_darcy_lagrange(n6, e6, 2, xc, yc, cm, degree=2)
-    E = Emul(n6, e6, 2, 2)
-    E.set_grid(xc, yc)
-    G, _ = E.stiffness(np.ascontiguousarray(cm.T))
-    e = abs(G - Gref).max() / abs(Gref).max()
-    print("ties", "%.1e" % e)
-    worst = max(worst, e)
-
-for order, nx, scale, with_bc, curve in [(2, 6, 1.0, True, 0.0), (2, 40, 0.0, False, 0.0), (2, 40, 2.5, True, 0.05),
-                                         (1, 40, 1.0, True, 0.0)]:
-    nodes, elems = mesh(nx, order, curve)
-    u = np.random.default_rng(nx).standard_normal(nodes.shape[0])
-    bnd = boundary(nodes) if with_bc else None
-    Jref, fref = fo.assemble_cubic_lagrange(nodes, elems, order, u, bnd, stiffness_scale=scale)
-    J, f = Emul(nodes, elems, order).cubic(u, scale, bnd)
-    e = [abs(J - Jref).max() / abs(Jref).max(), abs(f - fref).max() / abs(fref).max()]
-    print("cubic", order, nx, ["%.1e" % v for v in e])
-    worst = max(worst, max(e))
-
-for order, nx, alpha, with_bc in [(2, 7, 2, False), (2, 25, 3, False), (1, 30, 3, False), (2, 25, 2, True), (2, 12, 3, True)]:
-    nodes, elems = mesh(nx, order)
-    kappa, ratio = np.sqrt(8.0) / 0.2, 0.37
-    bnd = boundary(nodes) if with_bc else None
-    Qref = fo.matern_precision_lagrange(nodes, elems, order, kappa, ratio, alpha=alpha, prescribed=bnd)
-    Q = Emul(nodes, elems, order).matern(kappa, ratio, alpha, bnd, order=order)
-    e = abs(Q - Qref).max() / abs(Qref).max()
-    print("matern", order, nx, alpha, with_bc, "%.1e" % e)
-    worst = max(worst, e)
-
-A = sp.random(70, 50, density=0.08, random_state=1, format="csc")
-Bm = sp.random(50, 90, density=0.1, random_state=2, format="csc")
-w = rng.uniform(0.5, 2.0, 50)
-Cm = spgemm(A, Bm, w, -1.5)
-Cref = (A @ sp.diags(w) @ Bm).tocsc()
-S = ((abs(A) > 0).astype(np.float64) @ (abs(Bm) > 0).astype(np.float64)).tocsc()
-S.sort_indices()
-assert np.array_equal(Cm.indptr, S.indptr) and np.array_equal(Cm.indices, S.indices)
-e = abs(Cm + 1.5 * Cref).max() / abs(Cref).max()
-print("spgemm", "%.1e" % e, "empty:", spgemm(A, sp.csc_matrix((50, 90))).nnz)
-worst = max(worst, e)
 # posterior-precision plan: same result for any number of builder threads, equal to Q + A' W A
 L.emul_postprec.restype = C.c_int64
 L.emul_postprec.argtypes = [C.c_int64, C.c_int64, P, P, P, P, P, P, C.c_int64, P, C.c_int, P, P, P]
@@ -212,43 +135,126 @@ def postprec(Q, A, w, threads):
     return sp.csc_matrix((cv, cr, cp), shape=(n, n))
 
 
-for (mq, nq_, dens) in ((60, 40, 0.1), (500, 700, 0.01), (1, 1, 1.0)):
-    Aobs = sp.random(mq, nq_, density=dens, random_state=3, format="csc")
-    Qp = sp.random(nq_, nq_, density=dens, random_state=4, format="csc")
-    Qp = (Qp + Qp.T + sp.identity(nq_)).tocsc()
-    wobs = rng.uniform(0.5, 2.0, mq)
-    ref = (Qp + Aobs.T @ sp.diags(wobs) @ Aobs).tocsc()
-    outs = [postprec(Qp, Aobs, wobs, t) for t in (1, 2, 3, 7)]
-    for o in outs[1:]:
-        assert np.array_equal(o.indptr, outs[0].indptr) and np.array_equal(o.indices, outs[0].indices)
-        assert np.array_equal(o.data, outs[0].data)
-    e = abs(outs[0] - ref).max() / abs(ref).max()
-    print("postprec", mq, nq_, "%.1e" % e, "nnz", outs[0].nnz)
+
+def main():
+    worst = 0.0
+    for order, nx, degree, curve in [(1, 5, 0, 0.0), (1, 40, 2, 0.0), (2, 4, 0, 0.0), (2, 33, 0, 0.0), (2, 33, 4, 0.06),
+                                     (2, 60, 3, 0.0), (1, 33, 4, 0.0), (2, 9, 2, 0.05)]:
+        nodes, elems = mesh(nx, order, curve)
+        deg = degree or order + 1
+        E = Emul(nodes, elems, order, degree)
+        Gref, fref = fo.assemble_darcy_lagrange(nodes, elems, order, beta=2.5, degree=deg)
+        G, f = E.stiffness(beta=2.5)
+        assert np.array_equal(G.indptr, Gref.indptr) and np.array_equal(G.indices, Gref.indices), "pattern"
+        e = [relmat(G, Gref), abs(f - fref).max() / abs(fref).max()]
+        e.append(relmat(E.mass(0)[0], fo.assemble_mass_lagrange(nodes, elems, order, 0, degree=deg)))
+        for kind in (1, 2):
+            mref = fo.assemble_mass_lagrange(nodes, elems, order, kind, degree=deg)
+            Ml, ml = E.mass(kind)
+            e.append(abs(ml - mref).max() / abs(mref).max())
+            assert abs(Ml - sp.diags(ml)).max() == 0
+        print("unit", order, nx, deg, curve, ["%.1e" % v for v in e])
+        worst = max(worst, max(e))
+
+    for order, nx, seed in [(2, 21, 0), (2, 61, 3), (1, 61, 1)]:
+        nodes, elems = mesh(nx, order)
+        cg = W.darcy_problem(nx=9, seed=seed)["coeff_grid"]
+        xc = yc = np.linspace(0, 1, 241)
+        bnd = boundary(nodes)
+        Gref, fref = fo.assemble_darcy_lagrange(nodes, elems, order, xc, yc, cg.T, beta=1.0, prescribed=bnd)
+        E = Emul(nodes, elems, order)
+        E.set_grid(xc, yc)
+        G, f = E.stiffness(cg, presc=bnd)            # row-major (gy, gx) = entry ix + iy gx
+        e = [abs(G - Gref).max() / abs(Gref).max(), abs(f - fref).max() / abs(fref).max()]
+        print("darcy", order, nx, ["%.1e" % v for v in e])
+        worst = max(worst, max(e))
+
+    nodes, tris = W.structured_mesh(9, 9, jitter=0.0)
+    n6, e6 = W.quadratic_mesh(nodes, tris)
+    rng = np.random.default_rng(2)
+    for xc, yc in ((np.linspace(0, 1, 13), np.linspace(0, 1, 25)), (np.linspace(1, 0, 17), np.linspace(0, 1, 6))):
+        cm = rng.uniform(1, 5, size=(xc.size, yc.size))
+        Gref, _ = fo.assemble_darcy_lagrange(n6, e6, 2, xc, yc, cm, degree=2)
+        E = Emul(n6, e6, 2, 2)
+        E.set_grid(xc, yc)
+        G, _ = E.stiffness(np.ascontiguousarray(cm.T))
+        e = abs(G - Gref).max() / abs(Gref).max()
+        print("ties", "%.1e" % e)
+        worst = max(worst, e)
+
+    for order, nx, scale, with_bc, curve in [(2, 6, 1.0, True, 0.0), (2, 40, 0.0, False, 0.0), (2, 40, 2.5, True, 0.05),
+                                             (1, 40, 1.0, True, 0.0)]:
+        nodes, elems = mesh(nx, order, curve)
+        u = np.random.default_rng(nx).standard_normal(nodes.shape[0])
+        bnd = boundary(nodes) if with_bc else None
+        Jref, fref = fo.assemble_cubic_lagrange(nodes, elems, order, u, bnd, stiffness_scale=scale)
+        J, f = Emul(nodes, elems, order).cubic(u, scale, bnd)
+        e = [abs(J - Jref).max() / abs(Jref).max(), abs(f - fref).max() / abs(fref).max()]
+        print("cubic", order, nx, ["%.1e" % v for v in e])
+        worst = max(worst, max(e))
+
+    for order, nx, alpha, with_bc in [(2, 7, 2, False), (2, 25, 3, False), (1, 30, 3, False), (2, 25, 2, True), (2, 12, 3, True)]:
+        nodes, elems = mesh(nx, order)
+        kappa, ratio = np.sqrt(8.0) / 0.2, 0.37
+        bnd = boundary(nodes) if with_bc else None
+        Qref = fo.matern_precision_lagrange(nodes, elems, order, kappa, ratio, alpha=alpha, prescribed=bnd)
+        Q = Emul(nodes, elems, order).matern(kappa, ratio, alpha, bnd, order=order)
+        e = abs(Q - Qref).max() / abs(Qref).max()
+        print("matern", order, nx, alpha, with_bc, "%.1e" % e)
+        worst = max(worst, e)
+
+    A = sp.random(70, 50, density=0.08, random_state=1, format="csc")
+    Bm = sp.random(50, 90, density=0.1, random_state=2, format="csc")
+    w = rng.uniform(0.5, 2.0, 50)
+    Cm = spgemm(A, Bm, w, -1.5)
+    Cref = (A @ sp.diags(w) @ Bm).tocsc()
+    S = ((abs(A) > 0).astype(np.float64) @ (abs(Bm) > 0).astype(np.float64)).tocsc()
+    S.sort_indices()
+    assert np.array_equal(Cm.indptr, S.indptr) and np.array_equal(Cm.indices, S.indices)
+    e = abs(Cm + 1.5 * Cref).max() / abs(Cref).max()
+    print("spgemm", "%.1e" % e, "empty:", spgemm(A, sp.csc_matrix((50, 90))).nnz)
     worst = max(worst, e)
-nodes_, tris_ = W.structured_mesh(40, 40, seed=1)
-n6_, e6_ = W.quadratic_mesh(nodes_, tris_)
-G_, _ = fo.assemble_darcy_lagrange(n6_, e6_, 2)
-Q_ = fo.matern_precision_lagrange(n6_, e6_, 2, 5.0, 0.1, alpha=2)
-w_ = rng.uniform(0.5, 2.0, n6_.shape[0])
-o1, o5 = postprec(Q_, G_, w_, 1), postprec(Q_, G_, w_, 5)
-assert np.array_equal(o1.indices, o5.indices) and np.array_equal(o1.data, o5.data)
-ref = (Q_ + G_.T @ sp.diags(w_) @ G_).tocsc()
-e = abs(o1 - ref).max() / abs(ref).max()
-print("postprec P2 mesh", "%.1e" % e)
-worst = max(worst, e)
-# sparse-product pattern: the same for any number of builder threads (n >= 20000 takes the threaded path)
-Kbig = fo.assemble_darcy_lagrange(*W.quadratic_mesh(*W.structured_mesh(80, 80, seed=2)), 2)[0]
-pats = []
-for th in ("1", "3", "8"):
-    os.environ["GMRFB_HOST_THREADS"] = th
-    Cb = spgemm(Kbig, Kbig)
-    pats.append(Cb)
-os.environ.pop("GMRFB_HOST_THREADS")
-for o in pats[1:]:
-    assert np.array_equal(o.indptr, pats[0].indptr) and np.array_equal(o.indices, pats[0].indices) and np.array_equal(o.data, pats[0].data)
-e = abs(pats[0] - Kbig @ Kbig).max() / abs(Kbig @ Kbig).max()
-print("spgemm threaded pattern", Kbig.shape[0], "%.1e" % e)
-worst = max(worst, e)
-print("worst relative difference", "%.2e" % worst)
-assert worst < 1e-12
-print("OK")
+    for (mq, nq_, dens) in ((60, 40, 0.1), (500, 700, 0.01), (1, 1, 1.0)):
+        Aobs = sp.random(mq, nq_, density=dens, random_state=3, format="csc")
+        Qp = sp.random(nq_, nq_, density=dens, random_state=4, format="csc")
+        Qp = (Qp + Qp.T + sp.identity(nq_)).tocsc()
+        wobs = rng.uniform(0.5, 2.0, mq)
+        ref = (Qp + Aobs.T @ sp.diags(wobs) @ Aobs).tocsc()
+        outs = [postprec(Qp, Aobs, wobs, t) for t in (1, 2, 3, 7)]
+        for o in outs[1:]:
+            assert np.array_equal(o.indptr, outs[0].indptr) and np.array_equal(o.indices, outs[0].indices)
+            assert np.array_equal(o.data, outs[0].data)
+        e = abs(outs[0] - ref).max() / abs(ref).max()
+        print("postprec", mq, nq_, "%.1e" % e, "nnz", outs[0].nnz)
+        worst = max(worst, e)
+    nodes_, tris_ = W.structured_mesh(40, 40, seed=1)
+    n6_, e6_ = W.quadratic_mesh(nodes_, tris_)
+    G_, _ = fo.assemble_darcy_lagrange(n6_, e6_, 2)
+    Q_ = fo.matern_precision_lagrange(n6_, e6_, 2, 5.0, 0.1, alpha=2)
+    w_ = rng.uniform(0.5, 2.0, n6_.shape[0])
+    o1, o5 = postprec(Q_, G_, w_, 1), postprec(Q_, G_, w_, 5)
+    assert np.array_equal(o1.indices, o5.indices) and np.array_equal(o1.data, o5.data)
+    ref = (Q_ + G_.T @ sp.diags(w_) @ G_).tocsc()
+    e = abs(o1 - ref).max() / abs(ref).max()
+    print("postprec P2 mesh", "%.1e" % e)
+    worst = max(worst, e)
+    # sparse-product pattern: the same for any number of builder threads (n >= 20000 takes the threaded path)
+    Kbig = fo.assemble_darcy_lagrange(*W.quadratic_mesh(*W.structured_mesh(80, 80, seed=2)), 2)[0]
+    pats = []
+    for th in ("1", "3", "8"):
+        os.environ["GMRFB_HOST_THREADS"] = th
+        Cb = spgemm(Kbig, Kbig)
+        pats.append(Cb)
+    os.environ.pop("GMRFB_HOST_THREADS")
+    for o in pats[1:]:
+        assert np.array_equal(o.indptr, pats[0].indptr) and np.array_equal(o.indices, pats[0].indices) and np.array_equal(o.data, pats[0].data)
+    e = abs(pats[0] - Kbig @ Kbig).max() / abs(Kbig @ Kbig).max()
+    print("spgemm threaded pattern", Kbig.shape[0], "%.1e" % e)
+    worst = max(worst, e)
+    print("worst relative difference", "%.2e" % worst)
+    assert worst < 1e-12
+    print("OK")
+
+
+if __name__ == "__main__":
+    main()
