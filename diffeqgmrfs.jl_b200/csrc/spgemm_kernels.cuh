@@ -5,11 +5,29 @@
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
+#include <system_error>
 #include <thread>
 #include <vector>
 
 namespace gmrfb {
 namespace spgemm {
+
+// run body(0), ..., body(nblocks - 1), one worker thread per block; a block whose thread cannot be created runs on
+// the calling thread (no exception leaves a joinable thread behind)
+template <class F>
+inline void run_blocks(int nblocks, F body) {
+  std::vector<std::thread> pool;
+  std::vector<int> here(1, 0);
+  for (int t = 1; t < nblocks; t++) {
+    try {
+      pool.emplace_back(body, t);
+    } catch (const std::system_error&) {
+      here.push_back(t);
+    }
+  }
+  for (int t : here) body(t);
+  for (std::thread& th : pool) th.join();
+}
 
 // Symbolic phase of Qpost = Q + A' diag(w) A (gmrfb_postprec, spm.cu): the pattern of Qpost (ocolptr / orow), for every
 // output entry the position of the Q entry it starts from (qsrc, -1: none) and its list of products
@@ -85,12 +103,7 @@ inline void postprec_pattern(int64_t n, int64_t m, const int64_t* Qcolptr, const
       R.colcnt.push_back((int64_t)(R.orow.size() - before));
     }
   };
-  {
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nthreads; t++) pool.emplace_back(build_block, t);
-    build_block(0);
-    for (std::thread& th : pool) th.join();
-  }
+  run_blocks(nthreads, build_block);
   ocolptr.assign((size_t)n + 1, 0);
   qsrc.clear(), pptr.clear(), pa.clear(), pb.clear(), orow.clear(), prow.clear();
   {
@@ -155,12 +168,7 @@ inline void product_pattern(int64_t m, int64_t n, const int64_t* acolptr, const 
       R.colcnt.push_back((int64_t)rows.size());
     }
   };
-  {
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nthreads; t++) pool.emplace_back(build_block, t);
-    build_block(0);
-    for (std::thread& th : pool) th.join();
-  }
+  run_blocks(nthreads, build_block);
   ccolptr.assign((size_t)n + 1, 0);
   crow.clear();
   colnz.clear();

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <system_error>
 #include <thread>
 #include <chrono>
 #include <cstdio>
@@ -594,7 +595,13 @@ void nested_dissection(int32_t n, const std::vector<int64_t>& xadj, const std::v
       }
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < nw; t++) pool.emplace_back(worker, t);
+    for (int t = 1; t < nw; t++) {
+      try {
+        pool.emplace_back(worker, t);
+      } catch (const std::system_error&) {
+        break;  // the ranges come from a shared counter: fewer workers take more of them
+      }
+    }
     worker(0);
     for (std::thread& th : pool) th.join();
     open.clear();
