@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgmrfb.so")
 
-OK, ERR_INVALID, ERR_NOT_SPD, ERR_ALLOC, ERR_CUDA, ERR_COMM, ERR_STATE = range(7)
+OK, ERR_INVALID, ERR_NOT_SPD, ERR_ALLOC, ERR_CUDA, ERR_COMM, ERR_STATE, ERR_INTERNAL = range(8)
 ORDER_GIVEN, ORDER_NATURAL, ORDER_ND, ORDER_AMD, ORDER_ND_AMD = 0, 1, 2, 3, 4
 STORAGE_FULL, STORAGE_LOWER, STORAGE_UPPER = 0, 1, 2
 SOLVE_A, SOLVE_PTL, SOLVE_UP, SOLVE_L, SOLVE_LT = range(5)

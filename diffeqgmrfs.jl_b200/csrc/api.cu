@@ -36,7 +36,7 @@ using namespace gmrfb;
 // ------------------------------------------------------------------------------------------ context ----
 extern "C" int32_t gmrfb_version(void) { return 100; }
 
-extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) {
+extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) try {
   if (!out) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_ctx_create: out is NULL");
   *out = nullptr;
   int count = 0;
@@ -80,14 +80,16 @@ extern "C" gmrfb_status gmrfb_ctx_create(int32_t device, gmrfb_ctx** out) {
   *out = c.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_pool_trim(int64_t keep_bytes, int64_t* cached_bytes_out) {
+extern "C" gmrfb_status gmrfb_pool_trim(int64_t keep_bytes, int64_t* cached_bytes_out) try {
   DevPool::get().trim(keep_bytes > 0 ? (size_t)keep_bytes : 0);
   if (cached_bytes_out) *cached_bytes_out = (int64_t)DevPool::get().cached();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx) {
+extern "C" gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx) try {
   if (!ctx) return GMRFB_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -104,16 +106,20 @@ extern "C" gmrfb_status gmrfb_ctx_destroy(gmrfb_ctx* ctx) {
   DevPool::get().ctx_destroyed();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" const char* gmrfb_last_error(gmrfb_ctx* ctx) { return ctx ? ctx->err.c_str() : global_error().c_str(); }
+extern "C" const char* gmrfb_last_error(gmrfb_ctx* ctx) {
+  return (ctx && !ctx->err.empty()) ? ctx->err.c_str() : global_error().c_str();
+}
 
-extern "C" gmrfb_status gmrfb_ctx_sync(gmrfb_ctx* ctx) {
+extern "C" gmrfb_status gmrfb_ctx_sync(gmrfb_ctx* ctx) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "ctx is NULL");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
-extern "C" gmrfb_status gmrfb_ctx_profile_begin(gmrfb_ctx* ctx) {
+GMRFB_ABI_CATCH
+extern "C" gmrfb_status gmrfb_ctx_profile_begin(gmrfb_ctx* ctx) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "ctx is NULL");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   for (auto& r : ctx->prof) {
@@ -124,6 +130,7 @@ extern "C" gmrfb_status gmrfb_ctx_profile_begin(gmrfb_ctx* ctx) {
   ctx->profiling = true;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 static const char* prof_name(int kind) {
   switch (kind) {
@@ -169,7 +176,7 @@ static const char* prof_name(int kind) {
 }
 
 extern "C" gmrfb_status gmrfb_ctx_profile_end(gmrfb_ctx* ctx, gmrfb_profile_entry* entries, int32_t cap,
-                                              int32_t* count) {
+                                              int32_t* count) try {
   if (!ctx || !count) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_ctx_profile_end: NULL argument");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -212,13 +219,14 @@ extern "C" gmrfb_status gmrfb_ctx_profile_end(gmrfb_ctx* ctx, gmrfb_profile_entr
   *count = n;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" uint64_t gmrfb_ctx_stream(gmrfb_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 extern "C" int64_t gmrfb_ctx_launch_count(gmrfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ------------------------------------------------------------------------------------------ symbolic ----
 extern "C" gmrfb_status gmrfb_analyze(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
-                                      const int64_t* perm, const gmrfb_analyze_opts* opts, gmrfb_sym** out) {
+                                      const int64_t* perm, const gmrfb_analyze_opts* opts, gmrfb_sym** out) try {
   if (!out) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_analyze: out is NULL");
   *out = nullptr;
   AnalyzeOptions o;
@@ -247,15 +255,17 @@ extern "C" gmrfb_status gmrfb_analyze(gmrfb_ctx* ctx, int64_t n, const int64_t* 
   *out = s.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_sym_destroy(gmrfb_sym* sym) {
+extern "C" gmrfb_status gmrfb_sym_destroy(gmrfb_sym* sym) try {
   if (!sym) return GMRFB_OK;
   if (sym->ctx) cudaSetDevice(sym->ctx->device);
   delete sym;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_sym_get_info(const gmrfb_sym* sym, gmrfb_sym_info* info) {
+extern "C" gmrfb_status gmrfb_sym_get_info(const gmrfb_sym* sym, gmrfb_sym_info* info) try {
   if (!sym || !info) return fail(sym ? sym->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get_info: NULL argument");
   const Symbolic& S = sym->S;
   info->n = S.n;
@@ -269,9 +279,10 @@ extern "C" gmrfb_status gmrfb_sym_get_info(const gmrfb_sym* sym, gmrfb_sym_info*
   info->front_bytes = S.arena * (int64_t)sizeof(double);
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_sym_get(const gmrfb_sym* sym, int64_t* perm, int64_t* parent, int64_t* colcount,
-                                      int64_t* super_ptr, int64_t* ipost) {
+                                      int64_t* super_ptr, int64_t* ipost) try {
   if (!sym) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get: sym is NULL");
   const Symbolic& S = sym->S;
   const int b = S.base;
@@ -285,9 +296,10 @@ extern "C" gmrfb_status gmrfb_sym_get(const gmrfb_sym* sym, int64_t* perm, int64
     for (int32_t s = 0; s <= S.nsuper; s++) super_ptr[s] = S.sptr[s] + b;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_sym_get_super_rows(const gmrfb_sym* sym, int64_t s, int64_t* rows, int64_t cap,
-                                                 int64_t* nrows) {
+                                                 int64_t* nrows) try {
   if (!sym || s < 0 || s >= sym->S.nsuper)
     return fail(sym ? sym->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get_super_rows: bad argument");
   const Symbolic& S = sym->S;
@@ -297,9 +309,10 @@ extern "C" gmrfb_status gmrfb_sym_get_super_rows(const gmrfb_sym* sym, int64_t s
     for (int64_t k = 0; k < std::min(cnt, cap); k++) rows[k] = S.rows[S.rptr[s] + k] + S.base;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_sym_get_maps(const gmrfb_sym* sym, int64_t* amap, int64_t* relmap, int64_t* nnz_out,
-                                           int64_t* total_rows_out) {
+                                           int64_t* total_rows_out) try {
   if (!sym) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_sym_get_maps: sym is NULL");
   const Symbolic& S = sym->S;
   if (nnz_out) *nnz_out = (int64_t)S.amap.size();
@@ -309,6 +322,7 @@ extern "C" gmrfb_status gmrfb_sym_get_maps(const gmrfb_sym* sym, int64_t* amap, 
     for (size_t k = 0; k < S.relmap.size(); k++) relmap[k] = S.relmap[k];
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // Upload everything the numeric phases need (once per symbolic handle).
 static gmrfb_status sym_ensure_device(gmrfb_sym* sym) {
@@ -600,7 +614,7 @@ static gmrfb_status sym_ensure_selinv(gmrfb_sym* sym) {
 }
 
 // ------------------------------------------------------------------------------------------- numeric ----
-extern "C" gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out) {
+extern "C" gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out) try {
   if (!sym || !out) return fail(sym ? sym->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_create: NULL argument");
   *out = nullptr;
   gmrfb_status rc = sym_ensure_device(sym);
@@ -627,16 +641,18 @@ extern "C" gmrfb_status gmrfb_fac_create(gmrfb_sym* sym, gmrfb_fac** out) {
   *out = f.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_fac_destroy(gmrfb_fac* fac) {
+extern "C" gmrfb_status gmrfb_fac_destroy(gmrfb_fac* fac) try {
   if (!fac) return GMRFB_OK;
   cudaSetDevice(fac->ctx->device);
   cudaStreamSynchronize(fac->ctx->stream);
   delete fac;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzval) {
+extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzval) try {
   if (!fac || !d_nzval) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_factorize_dev: NULL argument");
   gmrfb_ctx* ctx = fac->ctx;
   gmrfb_sym* sym = fac->sym;
@@ -720,8 +736,9 @@ extern "C" gmrfb_status gmrfb_factorize_dev(gmrfb_fac* fac, const double* d_nzva
   fac->factored = true;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_factorize(gmrfb_fac* fac, const double* nzval) {
+extern "C" gmrfb_status gmrfb_factorize(gmrfb_fac* fac, const double* nzval) try {
   if (!fac || !nzval) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_factorize: NULL argument");
   gmrfb_ctx* ctx = fac->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -729,6 +746,7 @@ extern "C" gmrfb_status gmrfb_factorize(gmrfb_fac* fac, const double* nzval) {
                                 ctx->stream));
   return gmrfb_factorize_dev(fac, fac->nzval.p);
 }
+GMRFB_ABI_CATCH
 
 static gmrfb_status fac_diag_host(gmrfb_fac* fac, std::vector<double>& dl) {
   // diag(L) in the internal ordering
@@ -744,7 +762,7 @@ static gmrfb_status fac_diag_host(gmrfb_fac* fac, std::vector<double>& dl) {
   return GMRFB_OK;
 }
 
-extern "C" gmrfb_status gmrfb_fac_get_info(gmrfb_fac* fac, gmrfb_fac_info* info) {
+extern "C" gmrfb_status gmrfb_fac_get_info(gmrfb_fac* fac, gmrfb_fac_info* info) try {
   if (!fac || !info) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_get_info: NULL argument");
   GMRFB_CU(fac->ctx, cudaSetDevice(fac->ctx->device));
   info->status = fac->status;
@@ -765,8 +783,9 @@ extern "C" gmrfb_status gmrfb_fac_get_info(gmrfb_fac* fac, gmrfb_fac_info* info)
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_fac_diag(gmrfb_fac* fac, double* diagL) {
+extern "C" gmrfb_status gmrfb_fac_diag(gmrfb_fac* fac, double* diagL) try {
   if (!fac || !diagL) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_diag: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_fac_diag: no successful factorisation");
   GMRFB_CU(fac->ctx, cudaSetDevice(fac->ctx->device));
@@ -777,9 +796,10 @@ extern "C" gmrfb_status gmrfb_fac_diag(gmrfb_fac* fac, double* diagL) {
   for (int64_t k = 0; k < S.n; k++) diagL[S.post[k]] = dl[k];
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fac_get_L(gmrfb_fac* fac, int32_t base, int32_t drop_zeros, int64_t* colptr,
-                                        int64_t* rowval, double* nzval) {
+                                        int64_t* rowval, double* nzval) try {
   if (!fac || !colptr) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fac_get_L: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_fac_get_L: no successful factorisation");
   gmrfb_ctx* ctx = fac->ctx;
@@ -828,6 +848,7 @@ extern "C" gmrfb_status gmrfb_fac_get_L(gmrfb_fac* fac, int32_t base, int32_t dr
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ---------------------------------------------------------------------------------------------- solves ----
 namespace {
@@ -1062,7 +1083,7 @@ gmrfb_status solve_device(gmrfb_fac* fac, int mode, const double* d_in, int64_t 
 
 }  // namespace
 
-extern "C" gmrfb_status gmrfb_solve_dev(gmrfb_fac* fac, int32_t mode, double* d_X, int64_t ldx, int64_t nrhs) {
+extern "C" gmrfb_status gmrfb_solve_dev(gmrfb_fac* fac, int32_t mode, double* d_X, int64_t ldx, int64_t nrhs) try {
   if (!fac || !d_X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_solve_dev: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_solve: no successful factorisation");
   if (ldx < fac->sym->S.n || nrhs < 0) return fail(fac->ctx, GMRFB_ERR_INVALID, "gmrfb_solve: bad ldx/nrhs");
@@ -1081,8 +1102,9 @@ extern "C" gmrfb_status gmrfb_solve_dev(gmrfb_fac* fac, int32_t mode, double* d_
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int64_t ldx, int64_t nrhs) {
+extern "C" gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int64_t ldx, int64_t nrhs) try {
   if (!fac || !X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_solve: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_solve: no successful factorisation");
   gmrfb_ctx* ctx = fac->ctx;
@@ -1118,9 +1140,10 @@ extern "C" gmrfb_status gmrfb_solve(gmrfb_fac* fac, int32_t mode, double* X, int
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_solve_refined(gmrfb_fac* fac, const gmrfb_spm* Q, double* X, int64_t ldx, int64_t nrhs,
-                                            int32_t max_iter, double* resid_out) {
+                                            int32_t max_iter, double* resid_out) try {
   if (!fac || !Q || !X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_solve_refined: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_solve_refined: no successful factorisation");
   gmrfb_ctx* ctx = fac->ctx;
@@ -1172,9 +1195,10 @@ extern "C" gmrfb_status gmrfb_solve_refined(gmrfb_fac* fac, const gmrfb_spm* Q, 
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_sample(gmrfb_fac* fac, const double* mean, const double* Z, int64_t ldz, double* X,
-                                     int64_t ldx, int64_t nrhs) {
+                                     int64_t ldx, int64_t nrhs) try {
   if (!fac || !Z || !X) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sample: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_sample: no successful factorisation");
   gmrfb_ctx* ctx = fac->ctx;
@@ -1215,6 +1239,7 @@ extern "C" gmrfb_status gmrfb_sample(gmrfb_fac* fac, const double* mean, const d
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ------------------------------------------------------------------------------------ marginal variances ----
 static gmrfb_status selinv_run(gmrfb_fac* fac) {
@@ -1244,7 +1269,7 @@ static gmrfb_status selinv_run(gmrfb_fac* fac) {
   return GMRFB_OK;
 }
 
-extern "C" gmrfb_status gmrfb_var_selinv_dev(gmrfb_fac* fac, double* d_var_out) {
+extern "C" gmrfb_status gmrfb_var_selinv_dev(gmrfb_fac* fac, double* d_var_out) try {
   if (!fac || !d_var_out) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_var_selinv: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_var_selinv: no successful factorisation");
   gmrfb_ctx* ctx = fac->ctx;
@@ -1256,8 +1281,9 @@ extern "C" gmrfb_status gmrfb_var_selinv_dev(gmrfb_fac* fac, double* d_var_out) 
   ctx->launches++;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_var_selinv(gmrfb_fac* fac, double* var_out) {
+extern "C" gmrfb_status gmrfb_var_selinv(gmrfb_fac* fac, double* var_out) try {
   if (!fac || !var_out) return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_var_selinv: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_var_selinv: no successful factorisation");
   gmrfb_ctx* ctx = fac->ctx;
@@ -1270,9 +1296,10 @@ extern "C" gmrfb_status gmrfb_var_selinv(gmrfb_fac* fac, double* var_out) {
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_selinv_entries(gmrfb_fac* fac, int32_t base, int64_t count, const int64_t* rows,
-                                             const int64_t* cols, double* out) {
+                                             const int64_t* cols, double* out) try {
   if (!fac || (count > 0 && (!rows || !cols || !out)))
     return fail(fac ? fac->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_selinv_entries: NULL argument");
   if (!fac->factored) return fail(fac->ctx, GMRFB_ERR_STATE, "gmrfb_selinv_entries: no successful factorisation");
@@ -1314,18 +1341,21 @@ extern "C" gmrfb_status gmrfb_selinv_entries(gmrfb_fac* fac, int32_t base, int64
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 static gmrfb_status var_rbmc_core(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz, int64_t nsamp,
                                   double* var_out, bool out_on_device);
 
 extern "C" gmrfb_status gmrfb_var_rbmc(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
-                                       int64_t nsamp, double* var_out) {
+                                       int64_t nsamp, double* var_out) try {
   return var_rbmc_core(fac, Q, Z, ldz, nsamp, var_out, false);
 }
+GMRFB_ABI_CATCH
 extern "C" gmrfb_status gmrfb_var_rbmc_dev(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz,
-                                           int64_t nsamp, double* d_var_out) {
+                                           int64_t nsamp, double* d_var_out) try {
   return var_rbmc_core(fac, Q, Z, ldz, nsamp, d_var_out, true);
 }
+GMRFB_ABI_CATCH
 
 static gmrfb_status var_rbmc_core(gmrfb_fac* fac, const gmrfb_spm* Q, const double* Z, int64_t ldz, int64_t nsamp,
                                   double* var_out, bool out_on_device) {

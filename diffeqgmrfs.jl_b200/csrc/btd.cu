@@ -330,7 +330,7 @@ static gmrfb_status btd_load_dense(gmrfb_btd* f, const double* D, const double* 
 }
 
 extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D,
-                                               const double* Bsub, gmrfb_btd** out) {
+                                               const double* Bsub, gmrfb_btd** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor_dense: ctx is NULL");
   if (!out || !D || (nblocks > 1 && !Bsub)) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_factor_dense: NULL argument");
   *out = nullptr;
@@ -343,6 +343,7 @@ extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_
   *out = f.release();  // the handle is returned even when not SPD so that get_info can report the block
   return rc;
 }
+GMRFB_ABI_CATCH
 
 // Block-tridiagonal precision of a constant-mesh implicit-Euler state-space model built directly in block form
 // (ingredients of src/spdes/shallow_water.jl:198-228): with G = M + dt K and noise precision q,
@@ -351,7 +352,7 @@ extern "C" gmrfb_status gmrfb_btd_factor_dense(gmrfb_ctx* ctx, int64_t b, int64_
 // N-block host array of gmrfb_btd_factor_dense or the sparse -> dense gather of src/tridiagonal_cholesky.jl:73,76.
 extern "C" gmrfb_status gmrfb_btd_factor_ssm(gmrfb_ctx* ctx, int64_t b, int64_t nblocks, const double* D_first,
                                              const double* D_mid, const double* D_last, const double* B_sub,
-                                             gmrfb_btd** out) {
+                                             gmrfb_btd** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor_ssm: ctx is NULL");
   if (!out || !D_first || (nblocks > 1 && (!D_last || !B_sub)) || (nblocks > 2 && !D_mid))
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_factor_ssm: NULL argument");
@@ -379,9 +380,10 @@ extern "C" gmrfb_status gmrfb_btd_factor_ssm(gmrfb_ctx* ctx, int64_t b, int64_t 
   *out = f.release();
   return rc;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_btd_factor(gmrfb_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
-                                         const double* nzval, int32_t base, int64_t nblocks, gmrfb_btd** out) {
+                                         const double* nzval, int32_t base, int64_t nblocks, gmrfb_btd** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_factor: ctx is NULL");
   if (!out || !colptr || !rowval || !nzval || n <= 0 || nblocks <= 0 || (base != 0 && base != 1))
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_factor: bad argument");
@@ -410,8 +412,9 @@ extern "C" gmrfb_status gmrfb_btd_factor(gmrfb_ctx* ctx, int64_t n, const int64_
   *out = f.release();
   return rc;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_btd_destroy(gmrfb_btd* f) {
+extern "C" gmrfb_status gmrfb_btd_destroy(gmrfb_btd* f) try {
   if (!f) return GMRFB_OK;
   cudaSetDevice(f->ctx->device);
   cudaStreamSynchronize(f->ctx->stream);
@@ -428,8 +431,9 @@ extern "C" gmrfb_status gmrfb_btd_destroy(gmrfb_btd* f) {
   delete f;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_btd_get_info(gmrfb_btd* f, gmrfb_btd_info* info) {
+extern "C" gmrfb_status gmrfb_btd_get_info(gmrfb_btd* f, gmrfb_btd_info* info) try {
   if (!f || !info) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_get_info: NULL argument");
   info->b = f->b;
   info->nblocks = f->N;
@@ -439,8 +443,9 @@ extern "C" gmrfb_status gmrfb_btd_get_info(gmrfb_btd* f, gmrfb_btd_info* info) {
   info->flops = (double)(f->N - 1) * (7.0 / 3.0) * b3 + b3 / 3.0;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_btd_get_block(gmrfb_btd* f, int64_t i, int32_t which, double* out, int64_t ldo) {
+extern "C" gmrfb_status gmrfb_btd_get_block(gmrfb_btd* f, int64_t i, int32_t which, double* out, int64_t ldo) try {
   if (!f || !out) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_get_block: NULL argument");
   gmrfb_ctx* ctx = f->ctx;
   if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_get_block: no successful factorisation");
@@ -465,8 +470,9 @@ extern "C" gmrfb_status gmrfb_btd_get_block(gmrfb_btd* f, int64_t i, int32_t whi
       for (int64_t r = 0; r < c; r++) out[r + c * ldo] = 0.0;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_btd_logdet(gmrfb_btd* f, double* logdet) {
+extern "C" gmrfb_status gmrfb_btd_logdet(gmrfb_btd* f, double* logdet) try {
   if (!f || !logdet) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_logdet: NULL argument");
   gmrfb_ctx* ctx = f->ctx;
   if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_logdet: no successful factorisation");
@@ -484,6 +490,7 @@ extern "C" gmrfb_status gmrfb_btd_logdet(gmrfb_btd* f, double* logdet) {
   *logdet = 2.0 * s;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ---------------------------------------------------------------------------------------------- solve ----
 // Device RHS layout: node-major, nrhs x (b*N) with leading dimension ldr; block i occupies columns [i*b, (i+1)*b).
@@ -677,7 +684,7 @@ static gmrfb_status transpose_dev(gmrfb_ctx* ctx, const double* in, int64_t ldi,
   return GMRFB_OK;
 }
 
-extern "C" gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, int64_t ldx, int64_t nrhs) {
+extern "C" gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, int64_t ldx, int64_t nrhs) try {
   if (!f || !X) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_solve: NULL argument");
   gmrfb_ctx* ctx = f->ctx;
   if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_solve: no successful factorisation");
@@ -702,11 +709,12 @@ extern "C" gmrfb_status gmrfb_btd_solve(gmrfb_btd* f, int32_t mode, double* X, i
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ------------------------------------------------------------------------------- selected inversion ----
 // S_N = L_N^{-T} L_N^{-1};  S_i = L_i^{-T} (I + C_{i+1}' S_{i+1} C_{i+1}) L_i^{-1}.
 // Arena 0 = factor slot i (C_{i+1} in the next slot), 1 = S_{i+1} (b x b, ld), 2 = T scratch, 3 = S_i (output).
-extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
+extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) try {
   if (!f || !var_out) return fail(f ? f->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_selinv_diag: NULL argument");
   gmrfb_ctx* ctx = f->ctx;
   if (!f->factored) return fail(ctx, GMRFB_ERR_STATE, "gmrfb_btd_selinv_diag: no successful factorisation");
@@ -810,6 +818,7 @@ extern "C" gmrfb_status gmrfb_btd_selinv_diag(gmrfb_btd* f, double* var_out) {
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ======================================================================= time-sharded block tridiagonal ====
 // Rank r owns a contiguous slab of blocks.  Ranks 0..P-2 treat their last block as a *separator*; all other blocks
@@ -895,7 +904,7 @@ gmrfb_status gemm_once(gmrfb_ctx* ctx, int kind, const double* A, int lda, const
 }  // namespace
 
 extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int32_t nranks, int64_t b, int64_t nloc,
-                                              const double* D_local, const double* B_local, gmrfb_btd_dist** out) {
+                                              const double* D_local, const double* B_local, gmrfb_btd_dist** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_create: ctx is NULL");
   if (!out || !D_local || !B_local || rank < 0 || nranks < 1 || rank >= nranks || b <= 0)
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_btd_dist_create: bad argument");
@@ -1049,10 +1058,11 @@ extern "C" gmrfb_status gmrfb_btd_dist_create(gmrfb_ctx* ctx, int32_t rank, int3
   *out = h.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" int64_t gmrfb_btd_dist_iface_count(const gmrfb_btd_dist* h) { return h ? 3 * h->b * h->b : 0; }
 
-extern "C" gmrfb_status gmrfb_btd_dist_get_iface(gmrfb_btd_dist* h, double* d_out) {
+extern "C" gmrfb_status gmrfb_btd_dist_get_iface(gmrfb_btd_dist* h, double* d_out) try {
   if (!h || !d_out) return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_get_iface: NULL argument");
   GMRFB_CU(h->ctx, cudaSetDevice(h->ctx->device));
   GMRFB_CU(h->ctx, cudaMemcpyAsync(d_out, h->iface.p, 3 * h->b * h->b * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -1060,8 +1070,9 @@ extern "C" gmrfb_status gmrfb_btd_dist_get_iface(gmrfb_btd_dist* h, double* d_ou
   GMRFB_CU(h->ctx, cudaStreamSynchronize(h->ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_btd_dist_reduce(gmrfb_btd_dist* h, const double* d_all) {
+extern "C" gmrfb_status gmrfb_btd_dist_reduce(gmrfb_btd_dist* h, const double* d_all) try {
   if (!h || (h->P > 1 && !d_all)) return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_reduce: NULL argument");
   gmrfb_ctx* ctx = h->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -1091,6 +1102,7 @@ extern "C" gmrfb_status gmrfb_btd_dist_reduce(gmrfb_btd_dist* h, const double* d
   h->reduced_ready = true;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" int64_t gmrfb_btd_dist_solve_count(const gmrfb_btd_dist* h, int64_t nrhs) {
   if (!h) return 0;
@@ -1100,7 +1112,7 @@ extern "C" int64_t gmrfb_btd_dist_solve_count(const gmrfb_btd_dist* h, int64_t n
 
 // Phase 1: local forward elimination; d_send (device) receives [ (b_S - V y_last)' | (sum_i W_i y_i)' ], each ldr x b.
 extern "C" gmrfb_status gmrfb_btd_dist_solve_begin(gmrfb_btd_dist* h, const double* X_local, int64_t ldx, int64_t nrhs,
-                                                   double* d_send) {
+                                                   double* d_send) try {
   if (!h || !X_local || (h->P > 1 && !d_send))
     return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_solve_begin: NULL argument");
   gmrfb_ctx* ctx = h->ctx;
@@ -1141,10 +1153,11 @@ extern "C" gmrfb_status gmrfb_btd_dist_solve_begin(gmrfb_btd_dist* h, const doub
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // Phase 2: reduced solve (redundant on every rank), local back-substitution, copy out this rank's rows.
 extern "C" gmrfb_status gmrfb_btd_dist_solve_end(gmrfb_btd_dist* h, const double* d_all, double* X_local, int64_t ldx,
-                                                 int64_t nrhs) {
+                                                 int64_t nrhs) try {
   if (!h || !X_local || (h->P > 1 && !d_all))
     return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_solve_end: NULL argument");
   gmrfb_ctx* ctx = h->ctx;
@@ -1191,8 +1204,9 @@ extern "C" gmrfb_status gmrfb_btd_dist_solve_end(gmrfb_btd_dist* h, const double
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_btd_dist_logdet(gmrfb_btd_dist* h, double* local_part, double* reduced_part) {
+extern "C" gmrfb_status gmrfb_btd_dist_logdet(gmrfb_btd_dist* h, double* local_part, double* reduced_part) try {
   if (!h || !local_part || !reduced_part)
     return fail(h ? h->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_btd_dist_logdet: NULL argument");
   if (!h->reduced_ready) return fail(h->ctx, GMRFB_ERR_STATE, "gmrfb_btd_dist_logdet: call gmrfb_btd_dist_reduce first");
@@ -1202,11 +1216,13 @@ extern "C" gmrfb_status gmrfb_btd_dist_logdet(gmrfb_btd_dist* h, double* local_p
   if (h->reduced) rc = gmrfb_btd_logdet(h->reduced, reduced_part);
   return rc;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_btd_dist_destroy(gmrfb_btd_dist* h) {
+extern "C" gmrfb_status gmrfb_btd_dist_destroy(gmrfb_btd_dist* h) try {
   if (!h) return GMRFB_OK;
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   delete h;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH

@@ -1,5 +1,7 @@
 // Internal definitions shared by the C-ABI translation units.
 #pragma once
+#include <exception>
+#include <new>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -53,6 +55,20 @@ inline gmrfb_status fail(gmrfb_ctx* ctx, gmrfb_status code, const std::string& m
     global_error() = msg;
   return code;
 }
+
+// Every gmrfb_status entry point is a function-try-block closed by this macro: no C++ exception (std::bad_alloc of a
+// host vector, std::system_error of a worker thread, ...) crosses the C ABI.  The message goes to the process-wide slot
+// (gmrfb_last_error(NULL)); gmrfb_last_error(ctx) returns it too while the context has no message of its own.
+#define GMRFB_ABI_CATCH                                                                                        \
+  catch (const std::bad_alloc&) {                                                                              \
+    return gmrfb::fail(nullptr, GMRFB_ERR_ALLOC, "host allocation failed (std::bad_alloc)");                   \
+  }                                                                                                            \
+  catch (const std::exception& e_) {                                                                           \
+    return gmrfb::fail(nullptr, GMRFB_ERR_INTERNAL, std::string("unexpected C++ exception: ") + e_.what());    \
+  }                                                                                                            \
+  catch (...) {                                                                                                \
+    return gmrfb::fail(nullptr, GMRFB_ERR_INTERNAL, "unexpected C++ exception");                               \
+  }
 
 #define GMRFB_CU(ctx, call)                                                                          \
   do {                                                                                               \

@@ -212,7 +212,7 @@ std::vector<double> tri_rule(int degree) {
 }  // namespace
 
 extern "C" gmrfb_status gmrfb_fem_create(gmrfb_ctx* ctx, int64_t nnodes, const double* nodes, int64_t ntri,
-                                         const int64_t* tris, int32_t base, gmrfb_fem** out) {
+                                         const int64_t* tris, int32_t base, gmrfb_fem** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem_create: ctx is NULL");
   if (!out || !nodes || !tris || nnodes <= 0 || ntri <= 0 || (base != 0 && base != 1))
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem_create: bad argument");
@@ -276,8 +276,9 @@ extern "C" gmrfb_status gmrfb_fem_create(gmrfb_ctx* ctx, int64_t nnodes, const d
   *out = F.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_fem_destroy(gmrfb_fem* F) {
+extern "C" gmrfb_status gmrfb_fem_destroy(gmrfb_fem* F) try {
   if (!F) return GMRFB_OK;
   cudaSetDevice(F->ctx->device);
   cudaStreamSynchronize(F->ctx->stream);
@@ -285,15 +286,17 @@ extern "C" gmrfb_status gmrfb_fem_destroy(gmrfb_fem* F) {
   delete F;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_fem_get_mass(gmrfb_fem* F, double* mass_out) {
+extern "C" gmrfb_status gmrfb_fem_get_mass(gmrfb_fem* F, double* mass_out) try {
   if (!F || !mass_out) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem_get_mass: NULL argument");
   std::copy(F->mass.begin(), F->mass.end(), mass_out);
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem_set_coeff_grid(gmrfb_fem* F, int64_t gx, const double* x_coords, int64_t gy,
-                                                 const double* y_coords) {
+                                                 const double* y_coords) try {
   if (!F || !x_coords || !y_coords || gx <= 0 || gy <= 0)
     return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem_set_coeff_grid: bad argument");
   gmrfb_ctx* ctx = F->ctx;
@@ -330,6 +333,7 @@ extern "C" gmrfb_status gmrfb_fem_set_coeff_grid(gmrfb_fem* F, int64_t gx, const
   GMRFB_CU(ctx, F->d_coeff.alloc((size_t)F->ncell));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 static gmrfb_status fem_upload_presc(gmrfb_fem* F, const uint8_t* prescribed) {
   gmrfb_ctx* ctx = F->ctx;
@@ -340,7 +344,7 @@ static gmrfb_status fem_upload_presc(gmrfb_fem* F, const uint8_t* prescribed) {
 }
 
 extern "C" gmrfb_status gmrfb_fem_assemble(gmrfb_fem* F, const double* coeff_grid, const uint8_t* prescribed,
-                                           const gmrfb_spm** G_out) {
+                                           const gmrfb_spm** G_out) try {
   if (!F) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem_assemble: NULL handle");
   gmrfb_ctx* ctx = F->ctx;
   if (coeff_grid && !F->d_cell.p)
@@ -365,9 +369,10 @@ extern "C" gmrfb_status gmrfb_fem_assemble(gmrfb_fem* F, const double* coeff_gri
   if (G_out) *G_out = &F->G;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem_matern_precision(gmrfb_fem* F, double kappa, double ratio, const uint8_t* prescribed,
-                                                   double prescribed_mass, const gmrfb_spm** Q_out) {
+                                                   double prescribed_mass, const gmrfb_spm** Q_out) try {
   if (!F || !Q_out) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem_matern_precision: NULL argument");
   gmrfb_ctx* ctx = F->ctx;
   if (!(kappa > 0) || !(ratio > 0) || (prescribed && !(prescribed_mass > 0)))
@@ -395,10 +400,11 @@ extern "C" gmrfb_status gmrfb_fem_matern_precision(gmrfb_fem* F, double kappa, d
   }
   return gmrfb_postprec_compute(F->matern_plan, 0.0, F->d_w.p, Q_out);
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem_assemble_cubic(gmrfb_fem* F, const double* u, int32_t quad_degree,
                                                  double stiffness_scale, const uint8_t* prescribed,
-                                                 const gmrfb_spm** J_out, double* f_out) {
+                                                 const gmrfb_spm** J_out, double* f_out) try {
   if (!F || !u) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem_assemble_cubic: NULL argument");
   gmrfb_ctx* ctx = F->ctx;
   if (quad_degree != 1 && quad_degree != 2 && quad_degree != 4)
@@ -442,3 +448,4 @@ extern "C" gmrfb_status gmrfb_fem_assemble_cubic(gmrfb_fem* F, const double* u, 
   if (J_out) *J_out = &F->J;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH

@@ -337,7 +337,7 @@ gmrfb_status build_static(gmrfb_fem1d* F, bool lumping, const uint8_t* prescribe
 
 extern "C" gmrfb_status gmrfb_fem1d_create(gmrfb_ctx* ctx, int64_t nnodes, int64_t nelem, const int64_t* elems,
                                            const double* elem_x, int32_t order, int32_t base, int32_t nquad,
-                                           gmrfb_fem1d** out) {
+                                           gmrfb_fem1d** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem1d_create: ctx is NULL");
   if (!out || !elem_x || !elems || nnodes <= 0 || nelem <= 0 || (base != 0 && base != 1) || (order != 1 && order != 2))
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem1d_create: bad argument (order must be 1 or 2)");
@@ -414,17 +414,19 @@ extern "C" gmrfb_status gmrfb_fem1d_create(gmrfb_ctx* ctx, int64_t nnodes, int64
   *out = F.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_fem1d_destroy(gmrfb_fem1d* F) {
+extern "C" gmrfb_status gmrfb_fem1d_destroy(gmrfb_fem1d* F) try {
   if (!F) return GMRFB_OK;
   cudaSetDevice(F->ctx->device);
   cudaStreamSynchronize(F->ctx->stream);
   delete F;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem1d_mass_stiffness(gmrfb_fem1d* F, int32_t lumping, const uint8_t* prescribed,
-                                                   const gmrfb_spm** M_out, const gmrfb_spm** G_out) {
+                                                   const gmrfb_spm** M_out, const gmrfb_spm** G_out) try {
   if (!F) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem1d_mass_stiffness: NULL handle");
   gmrfb_ctx* ctx = F->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -435,9 +437,10 @@ extern "C" gmrfb_status gmrfb_fem1d_mass_stiffness(gmrfb_fem1d* F, int32_t lumpi
   if (G_out) *G_out = &F->G;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem1d_advection(gmrfb_fem1d* F, const double* u, const uint8_t* prescribed,
-                                              const gmrfb_spm** A_out, double* v_out) {
+                                              const gmrfb_spm** A_out, double* v_out) try {
   if (!F || !u) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem1d_advection: NULL argument");
   gmrfb_ctx* ctx = F->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -468,10 +471,11 @@ extern "C" gmrfb_status gmrfb_fem1d_advection(gmrfb_fem1d* F, const double* u, c
   if (A_out) *A_out = &F->A;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem1d_spacetime_tangent(gmrfb_fem1d* F, int64_t nt, double dt, double nu, const double* w,
                                                       const uint8_t* prescribed, const gmrfb_spm** J_out,
-                                                      double* f_out) {
+                                                      double* f_out) try {
   if (!F || !w) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem1d_spacetime_tangent: NULL argument");
   gmrfb_ctx* ctx = F->ctx;
   if (nt < 2 || nt > 65535) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem1d_spacetime_tangent: nt must be in 2..65535");
@@ -543,3 +547,4 @@ extern "C" gmrfb_status gmrfb_fem1d_spacetime_tangent(gmrfb_fem1d* F, int64_t nt
   if (J_out) *J_out = F->J.get();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH

@@ -102,7 +102,7 @@ gmrfb_status ensure_lumped(gmrfb_fem2d* F, int kind) {
 
 extern "C" gmrfb_status gmrfb_fem2d_create(gmrfb_ctx* ctx, int32_t order, int64_t nnodes, const double* nodes,
                                            int64_t nelem, const int64_t* elems, int32_t base, int32_t quad_degree,
-                                           gmrfb_fem2d** out) {
+                                           gmrfb_fem2d** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem2d_create: ctx is NULL");
   if (!out || !nodes || !elems || nnodes <= 0 || nelem <= 0 || (base != 0 && base != 1) || (order != 1 && order != 2))
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem2d_create: bad argument (order must be 1 or 2)");
@@ -168,8 +168,9 @@ extern "C" gmrfb_status gmrfb_fem2d_create(gmrfb_ctx* ctx, int32_t order, int64_
   *out = F.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_fem2d_destroy(gmrfb_fem2d* F) {
+extern "C" gmrfb_status gmrfb_fem2d_destroy(gmrfb_fem2d* F) try {
   if (!F) return GMRFB_OK;
   cudaSetDevice(F->ctx->device);
   cudaStreamSynchronize(F->ctx->stream);
@@ -178,9 +179,10 @@ extern "C" gmrfb_status gmrfb_fem2d_destroy(gmrfb_fem2d* F) {
   delete F;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem2d_info(gmrfb_fem2d* F, int32_t* order, int32_t* nodes_per_element, int32_t* nquad,
-                                         int64_t* nnz) {
+                                         int64_t* nnz) try {
   if (!F) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem2d_info: NULL handle");
   if (order) *order = F->order;
   if (nodes_per_element) *nodes_per_element = F->npe;
@@ -188,9 +190,10 @@ extern "C" gmrfb_status gmrfb_fem2d_info(gmrfb_fem2d* F, int32_t* order, int32_t
   if (nnz) *nnz = F->G.nnz;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem2d_set_coeff_grid(gmrfb_fem2d* F, int64_t gx, const double* x_coords, int64_t gy,
-                                                   const double* y_coords) {
+                                                   const double* y_coords) try {
   if (!F || !x_coords || !y_coords || gx <= 0 || gy <= 0)
     return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem2d_set_coeff_grid: bad argument");
   gmrfb_ctx* ctx = F->ctx;
@@ -206,9 +209,10 @@ extern "C" gmrfb_status gmrfb_fem2d_set_coeff_grid(gmrfb_fem2d* F, int64_t gx, c
   GMRFB_CU(ctx, F->d_coeff.alloc((size_t)F->ncell));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem2d_stiffness(gmrfb_fem2d* F, const double* coeff_grid, const uint8_t* prescribed,
-                                              double beta, const gmrfb_spm** G_out, double* load_out) {
+                                              double beta, const gmrfb_spm** G_out, double* load_out) try {
   if (!F) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem2d_stiffness: NULL handle");
   gmrfb_ctx* ctx = F->ctx;
   if (coeff_grid && !F->d_cellq.p)
@@ -244,8 +248,9 @@ extern "C" gmrfb_status gmrfb_fem2d_stiffness(gmrfb_fem2d* F, const double* coef
   if (G_out) *G_out = &F->G;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_fem2d_mass(gmrfb_fem2d* F, int32_t lumping, const gmrfb_spm** M_out, double* lumped_out) {
+extern "C" gmrfb_status gmrfb_fem2d_mass(gmrfb_fem2d* F, int32_t lumping, const gmrfb_spm** M_out, double* lumped_out) try {
   if (!F) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_fem2d_mass: NULL handle");
   gmrfb_ctx* ctx = F->ctx;
   if (lumping < 0 || lumping > 3) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_fem2d_mass: lumping must be 0 ... 3");
@@ -267,10 +272,11 @@ extern "C" gmrfb_status gmrfb_fem2d_mass(gmrfb_fem2d* F, int32_t lumping, const 
   if (M_out) *M_out = &F->M;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem2d_matern_precision(gmrfb_fem2d* F, double kappa, double ratio, int32_t alpha,
                                                      const uint8_t* prescribed, double prescribed_mass,
-                                                     const gmrfb_spm** Q_out) {
+                                                     const gmrfb_spm** Q_out) try {
   if (!F || !Q_out) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem2d_matern_precision: NULL argument");
   gmrfb_ctx* ctx = F->ctx;
   if (!(kappa > 0) || !(ratio > 0) || (prescribed && !(prescribed_mass > 0)) || (alpha != 2 && alpha != 3))
@@ -310,9 +316,10 @@ extern "C" gmrfb_status gmrfb_fem2d_matern_precision(gmrfb_fem2d* F, double kapp
   }
   return gmrfb_spgemm_compute(F->matern_plan3, ratio, F->d_w.p, Q_out);  // ratio (K W K) W K
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_fem2d_assemble_cubic(gmrfb_fem2d* F, const double* u, double stiffness_scale,
-                                                   const uint8_t* prescribed, const gmrfb_spm** J_out, double* f_out) {
+                                                   const uint8_t* prescribed, const gmrfb_spm** J_out, double* f_out) try {
   if (!F || !u) return fail(F ? F->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_fem2d_assemble_cubic: NULL argument");
   gmrfb_ctx* ctx = F->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -346,3 +353,4 @@ extern "C" gmrfb_status gmrfb_fem2d_assemble_cubic(gmrfb_fem2d* F, const double*
   if (J_out) *J_out = &F->J;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH

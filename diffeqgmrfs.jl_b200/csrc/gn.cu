@@ -147,7 +147,7 @@ extern "C" gmrfb_status gmrfb_gn_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, int6
                                         const int64_t* rowval, const double* lval, const double* aval,
                                         const double* dval, const double* cubic, int32_t base, double c, double noise,
                                         const double* y, const double* mu, const int64_t* perm,
-                                        const gmrfb_analyze_opts* opts, gmrfb_gn** out) {
+                                        const gmrfb_analyze_opts* opts, gmrfb_gn** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_gn_create: ctx is NULL");
   if (!Q || !colptr || !rowval || !lval || !aval || !dval || !y || !mu || !out || m <= 0 || Q->m != Q->n)
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_gn_create: bad argument");
@@ -219,9 +219,10 @@ extern "C" gmrfb_status gmrfb_gn_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, int6
   *out = g.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_gn_optimize(gmrfb_gn* g, double* x, int32_t max_steps, double rel_tol, int32_t* steps,
-                                          double* obj_hist) {
+                                          double* obj_hist) try {
   if (!g || !x || max_steps < 0) return fail(g ? g->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_gn_optimize: bad argument");
   gmrfb_ctx* ctx = g->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -245,9 +246,10 @@ extern "C" gmrfb_status gmrfb_gn_optimize(gmrfb_gn* g, double* x, int32_t max_st
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_gn_get(gmrfb_gn* g, gmrfb_fac** fac, gmrfb_sym** sym, const gmrfb_spm** J,
-                                     const gmrfb_spm** Qpost) {
+                                     const gmrfb_spm** Qpost) try {
   if (!g) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_gn_get: NULL handle");
   if (fac) *fac = g->fac;
   if (sym) *sym = g->sym;
@@ -261,8 +263,9 @@ extern "C" gmrfb_status gmrfb_gn_get(gmrfb_gn* g, gmrfb_fac** fac, gmrfb_sym** s
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_gn_destroy(gmrfb_gn* g) {
+extern "C" gmrfb_status gmrfb_gn_destroy(gmrfb_gn* g) try {
   if (!g) return GMRFB_OK;
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
@@ -273,3 +276,4 @@ extern "C" gmrfb_status gmrfb_gn_destroy(gmrfb_gn* g) {
   delete g;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH

@@ -76,7 +76,7 @@ gmrfb_status gmrfb::spm_build(gmrfb_ctx* ctx, gmrfb_spm* M, int64_t m, int64_t n
 }
 
 extern "C" gmrfb_status gmrfb_spm_create(gmrfb_ctx* ctx, int64_t m, int64_t n, const int64_t* colptr,
-                                         const int64_t* rowval, const double* nzval, int32_t base, gmrfb_spm** out) {
+                                         const int64_t* rowval, const double* nzval, int32_t base, gmrfb_spm** out) try {
   if (!ctx) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_create: ctx is NULL");
   if (!out || !colptr || m < 0 || n < 0 || (base != 0 && base != 1))
     return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_spm_create: bad argument");
@@ -89,8 +89,9 @@ extern "C" gmrfb_status gmrfb_spm_create(gmrfb_ctx* ctx, int64_t m, int64_t n, c
   *out = M.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_spm_set_values(gmrfb_spm* A, const double* nzval) {
+extern "C" gmrfb_status gmrfb_spm_set_values(gmrfb_spm* A, const double* nzval) try {
   if (!A || !nzval) return fail(A ? A->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_set_values: NULL argument");
   gmrfb_ctx* ctx = A->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -100,8 +101,9 @@ extern "C" gmrfb_status gmrfb_spm_set_values(gmrfb_spm* A, const double* nzval) 
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_spm_destroy(gmrfb_spm* A) {
+extern "C" gmrfb_status gmrfb_spm_destroy(gmrfb_spm* A) try {
   if (!A) return GMRFB_OK;
   if (A->owned_by_plan) return fail(A->ctx, GMRFB_ERR_INVALID, "matrix is owned by a posterior-precision plan");
   cudaSetDevice(A->ctx->device);
@@ -109,17 +111,19 @@ extern "C" gmrfb_status gmrfb_spm_destroy(gmrfb_spm* A) {
   delete A;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_spm_dims(const gmrfb_spm* A, int64_t* m, int64_t* n, int64_t* nnz) {
+extern "C" gmrfb_status gmrfb_spm_dims(const gmrfb_spm* A, int64_t* m, int64_t* n, int64_t* nnz) try {
   if (!A) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_dims: NULL argument");
   if (m) *m = A->m;
   if (n) *n = A->n;
   if (nnz) *nnz = A->nnz;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_spm_get(const gmrfb_spm* A, int32_t base, int64_t* colptr, int64_t* rowval,
-                                      double* nzval) {
+                                      double* nzval) try {
   if (!A) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spm_get: NULL argument");
   gmrfb_ctx* ctx = A->ctx;
   if (colptr)
@@ -133,11 +137,12 @@ extern "C" gmrfb_status gmrfb_spm_get(const gmrfb_spm* A, int32_t base, int64_t*
   }
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" const double* gmrfb_spm_values_dev(const gmrfb_spm* A) { return A ? A->d_val.p : nullptr; }
 
 extern "C" gmrfb_status gmrfb_spmv(const gmrfb_spm* A, int32_t trans, double alpha, const double* x, double beta,
-                                   double* y) {
+                                   double* y) try {
   if (!A || !x || !y) return fail(A ? A->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_spmv: NULL argument");
   gmrfb_ctx* ctx = A->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -156,8 +161,9 @@ extern "C" gmrfb_status gmrfb_spmv(const gmrfb_spm* A, int32_t trans, double alp
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_sqmahal(const gmrfb_spm* Q, const double* mu, const double* v, double* out) {
+extern "C" gmrfb_status gmrfb_sqmahal(const gmrfb_spm* Q, const double* mu, const double* v, double* out) try {
   if (!Q || !v || !out) return fail(Q ? Q->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_sqmahal: NULL argument");
   if (Q->m != Q->n) return fail(Q->ctx, GMRFB_ERR_INVALID, "gmrfb_sqmahal: Q must be square");
   gmrfb_ctx* ctx = Q->ctx;
@@ -180,10 +186,11 @@ extern "C" gmrfb_status gmrfb_sqmahal(const gmrfb_spm* Q, const double* mu, cons
   GMRFB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ------------------------------------------------------------------------------ posterior precision ----
 extern "C" gmrfb_status gmrfb_postprec_create(gmrfb_ctx* ctx, const gmrfb_spm* Q, const gmrfb_spm* A,
-                                              gmrfb_postprec** out) {
+                                              gmrfb_postprec** out) try {
   if (!ctx || !Q || !A || !out) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_postprec_create: NULL argument");
   if (Q->m != Q->n || A->n != Q->n) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_postprec_create: shape mismatch");
   *out = nullptr;
@@ -212,17 +219,19 @@ extern "C" gmrfb_status gmrfb_postprec_create(gmrfb_ctx* ctx, const gmrfb_spm* Q
   *out = P.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_postprec_destroy(gmrfb_postprec* plan) {
+extern "C" gmrfb_status gmrfb_postprec_destroy(gmrfb_postprec* plan) try {
   if (!plan) return GMRFB_OK;
   cudaSetDevice(plan->ctx->device);
   cudaStreamSynchronize(plan->ctx->stream);
   delete plan;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps_scalar, const double* qeps_diag,
-                                               const gmrfb_spm** Qpost) {
+                                               const gmrfb_spm** Qpost) try {
   if (!plan) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_postprec_compute: NULL plan");
   gmrfb_ctx* ctx = plan->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -237,12 +246,14 @@ extern "C" gmrfb_status gmrfb_postprec_compute(gmrfb_postprec* plan, double qeps
   if (Qpost) *Qpost = &plan->out;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_spm** Qpost) {
+extern "C" gmrfb_status gmrfb_postprec_result(gmrfb_postprec* plan, const gmrfb_spm** Qpost) try {
   if (!plan || !Qpost) return fail(plan ? plan->ctx : nullptr, GMRFB_ERR_INVALID, "gmrfb_postprec_result: NULL argument");
   *Qpost = &plan->out;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ---------------------------------------------------------------------------- fixed-pattern product ----
 // C = alpha A diag(w) B on patterns fixed at creation: the higher Matern powers K Mt^-1 K Mt^-1 K of
@@ -260,7 +271,7 @@ struct gmrfb_spgemm {
   DevBuf<double> d_w;
 };
 
-extern "C" gmrfb_status gmrfb_spgemm_create(gmrfb_ctx* ctx, const gmrfb_spm* A, const gmrfb_spm* B, gmrfb_spgemm** out) {
+extern "C" gmrfb_status gmrfb_spgemm_create(gmrfb_ctx* ctx, const gmrfb_spm* A, const gmrfb_spm* B, gmrfb_spgemm** out) try {
   if (!ctx || !A || !B || !out) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_spgemm_create: NULL argument");
   if (A->n != B->m) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_spgemm_create: shape mismatch");
   *out = nullptr;
@@ -282,17 +293,19 @@ extern "C" gmrfb_status gmrfb_spgemm_create(gmrfb_ctx* ctx, const gmrfb_spm* A, 
   *out = P.release();
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
-extern "C" gmrfb_status gmrfb_spgemm_destroy(gmrfb_spgemm* plan) {
+extern "C" gmrfb_status gmrfb_spgemm_destroy(gmrfb_spgemm* plan) try {
   if (!plan) return GMRFB_OK;
   cudaSetDevice(plan->ctx->device);
   cudaStreamSynchronize(plan->ctx->stream);
   delete plan;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 extern "C" gmrfb_status gmrfb_spgemm_compute(gmrfb_spgemm* plan, double alpha, const double* w_diag,
-                                             const gmrfb_spm** C_out) {
+                                             const gmrfb_spm** C_out) try {
   if (!plan) return fail(nullptr, GMRFB_ERR_INVALID, "gmrfb_spgemm_compute: NULL plan");
   gmrfb_ctx* ctx = plan->ctx;
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -313,6 +326,7 @@ extern "C" gmrfb_status gmrfb_spgemm_compute(gmrfb_spgemm* plan, double alpha, c
   if (C_out) *C_out = &plan->out;
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH
 
 // ------------------------------------------------------------------------------- evaluation metrics ----
 // src/metrics.jl:3-13 on the device: pred = E x (or x), then
@@ -373,7 +387,7 @@ __global__ void k_metrics_final(int nb, int64_t n, const double* __restrict__ pa
 }  // namespace
 
 extern "C" gmrfb_status gmrfb_metrics(gmrfb_ctx* ctx, const gmrfb_spm* E, const double* x, const double* truth,
-                                      int64_t ntruth, double* out3) {
+                                      int64_t ntruth, double* out3) try {
   if (!ctx || !x || !truth || !out3 || ntruth <= 0) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_metrics: bad argument");
   if (E && E->m != ntruth) return fail(ctx, GMRFB_ERR_INVALID, "gmrfb_metrics: E has the wrong number of rows");
   GMRFB_CU(ctx, cudaSetDevice(ctx->device));
@@ -402,3 +416,4 @@ extern "C" gmrfb_status gmrfb_metrics(gmrfb_ctx* ctx, const gmrfb_spm* E, const 
   GMRFB_CU(ctx, cudaStreamSynchronize(st));
   return GMRFB_OK;
 }
+GMRFB_ABI_CATCH

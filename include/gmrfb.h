@@ -41,7 +41,8 @@ enum {
   GMRFB_ERR_ALLOC = 3,    /* host or device allocation failed */
   GMRFB_ERR_CUDA = 4,     /* CUDA runtime error, or no usable device */
   GMRFB_ERR_COMM = 5,     /* multi-GPU exchange failed */
-  GMRFB_ERR_STATE = 6     /* handle used in the wrong state (e.g. solve before a successful factorize) */
+  GMRFB_ERR_STATE = 6,    /* handle used in the wrong state (e.g. solve before a successful factorize) */
+  GMRFB_ERR_INTERNAL = 7  /* an unexpected C++ exception was caught at the boundary (message: gmrfb_last_error) */
 };
 
 typedef struct gmrfb_ctx gmrfb_ctx; /* device + stream + scratch              */
