@@ -1,0 +1,143 @@
+"""CPU tier: the static launch plans of the numeric phases (csrc/plan.cpp) checked without a GPU
+(tools/plancheck/plancheck.py).
+
+1. Hazards.  The tasks of one launch run concurrently on the GPU and the kernels use no atomics, so within every launch
+   no two tasks may write the same arena entry and none may read what another one writes.  compute-sanitizer's racecheck
+   is refused on the GPU pool; here the read and write sets of every task are derived from the same Task records the
+   kernels consume and intersected on the host.  Negative controls: merging two extend-add launches of sibling children,
+   or a POTRF launch with the apply-inverse launch that follows it, must be reported.
+2. Interpretation.  Every launch kind is restated in NumPy from its kernel and the plans are executed on NaN-poisoned
+   arenas: the factor must satisfy L L' = P A P', the kept inverses W L11 = I, the selected inverse must equal
+   inv(P A P') on the pattern of L - which also pins the read / write model of (1) and shows that nothing is read before
+   it is written."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pc():
+    spec = importlib.util.spec_from_file_location("plancheck", os.path.join(ROOT, "tools", "plancheck", "plancheck.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+    return mod
+
+
+def _check(res):
+    assert res["violations"] == []
+    assert res["factor_err"] < 1e-13 and res["selinv_err"] < 1e-11 and res["zdiag_err"] < 1e-11
+    if "wide_err" in res:
+        assert res["wide_err"] < 1e-12
+
+
+@pytest.mark.parametrize("nx,ordering,use_wide", [(12, "nd", False), (40, "nd", False), (58, "nd", True), (45, "amd", False),
+                                                  (45, "nd_amd", False)])
+def test_plans_of_a_2d_posterior(pc, W, nx, ordering, use_wide):
+    prob = W.matern_posterior(nx, obs_frac=0.2, q_eps=1e2, corr_range=0.2, seed=nx)
+    res = pc.check_matrix(prob["Qpost"], ordering=ordering, coords=prob["nodes"] if ordering == "nd" else None,
+                          use_wide=use_wide, wide_min=65)
+    _check(res)
+    if use_wide:
+        assert res["n_wide"] > 0 and res["max_front"] > pc.SMALL_FRONT_MAX
+
+
+@pytest.mark.parametrize("ordering,use_wide", [("nd", True), ("amd", False)])
+def test_plans_of_a_spacetime_precision(pc, W, ordering, use_wide):
+    """3-D separators: fronts of several hundred columns (recursive blocking over several 64-column blocks, multi-level
+    recursive-doubling inverses, many children per parent)."""
+    st = W.heat_spacetime_sparse(14, 6)
+    res = pc.check_matrix(st["A"], ordering=ordering, coords=st["coords"] if ordering == "nd" else None, use_wide=use_wide,
+                          wide_min=65)
+    _check(res)
+    assert res["max_front"] > 256 and res["factor"]["tasks"] > res["nsuper"]
+
+
+def test_plans_of_a_banded_chain(pc):
+    """Natural ordering of a banded matrix: a chain of supernodes (one child each), given permutation path."""
+    n, bw = 700, 40
+    rng = np.random.default_rng(0)
+    B = sp.diags([rng.standard_normal(n - k) for k in range(1, bw)], list(range(1, bw)), format="csc")
+    A = (B + B.T + sp.identity(n) * (2.0 * bw)).tocsc()
+    res = pc.check_matrix(A, perm=np.arange(n))
+    _check(res)
+
+
+def test_hazard_checker_reports_injected_hazards(pc, W):
+    prob = W.matern_posterior(58, obs_frac=0.2, q_eps=1e2, corr_range=0.2, seed=58)
+    P = pc.Plans(prob["Qpost"], ordering="nd", coords=prob["nodes"], wide_min=65)
+    plan = P.plan("factor")
+    L = plan["launches"]
+    kinds = [int(k) for k in L["kind"]]
+
+    def merged(i, j):
+        """a plan with the single launch made of the tasks of launches i and j"""
+        ti = plan["tasks"][int(L[i]["task0"]):int(L[i]["task0"]) + int(L[i]["ntasks"])]
+        tj = plan["tasks"][int(L[j]["task0"]):int(L[j]["task0"]) + int(L[j]["ntasks"])]
+        one = np.zeros(1, dtype=pc.LAUNCH)
+        one[0]["kind"] = L[i]["kind"]
+        one[0]["ntasks"] = len(ti) + len(tj)
+        return dict(tasks=np.concatenate([ti, tj]), launches=one)
+
+    # (a) two child ranks of the same parents in ONE launch: both add into the same separator entries
+    pairs = [i for i in range(len(kinds) - 1) if kinds[i] == pc.LK_EXTEND_ADD and kinds[i + 1] == pc.LK_EXTEND_ADD]
+    assert pairs
+    found = False
+    for i in pairs:
+        _, _, bad = pc.hazards(P, merged(i, i + 1))
+        found = found or any(b[0] == "write/write" for b in bad)
+    assert found
+    # (b) the apply-inverse launch reads the inverse blocks the POTRF launch before it writes
+    i = next(i for i in range(len(kinds) - 1) if kinds[i] == pc.LK_POTRF and kinds[i + 1] == pc.LK_TRSM_RLT)
+    mp = merged(i, i + 1)
+    # the merged launch is interpreted task by task with each task's own kind for the access model
+    kind_of = [pc.LK_POTRF] * int(L[i]["ntasks"]) + [pc.LK_TRSM_RLT] * int(L[i + 1]["ntasks"])
+    writes = {}
+    hit = False
+    for k, t in enumerate(mp["tasks"]):
+        R, Wr = pc.task_access(P, kind_of[k], t)
+        for a, ix in R:
+            for (a2, k2), ix2 in writes.items():
+                if a2 == a and k2 != k and np.intersect1d(ix, ix2).size:
+                    hit = True
+        for a, ix in Wr:
+            writes[(a, k)] = ix
+    assert hit
+    # and the unmodified plans are clean
+    for w in ("zero", "factor", "selinv"):
+        assert pc.hazards(P, P.plan(w))[2] == []
+
+
+def test_poison_shows_a_missing_clear(pc, W):
+    """Without the zero plan the factorisation reads entries nobody wrote: the NaN poison reaches the factor."""
+    prob = W.matern_posterior(40, obs_frac=0.2, q_eps=1e2, corr_range=0.2, seed=40)
+    P = pc.Plans(prob["Qpost"], ordering="nd", coords=prob["nodes"])
+    S = pc.State(P, poison=True)
+    pc.scatter_values(P, S)
+    try:
+        pc.run(P, S, P.plan("factor"))
+        Lm = pc.factor_matrix(P, S)
+        assert not np.all(np.isfinite(Lm.data))
+    except np.linalg.LinAlgError:
+        pass  # a NaN front is not positive definite either
+
+
+@pytest.mark.parametrize("case,nr", [("mesh12", 3), ("mesh58", 7), ("mesh58", 32), ("spacetime", 9)])
+def test_panel_sweep_plans(pc, W, case, nr):
+    """The multi-right-hand-side sweeps (build_solve_mr_plans): forward and backward plans are hazard-free and, run
+    after the factor plan on poisoned arenas, solve (P A P') X' = B' for a node-major panel of nr right-hand sides."""
+    if case == "spacetime":
+        st = W.heat_spacetime_sparse(14, 6)
+        A, coords = st["A"], st["coords"]
+    else:
+        nx = int(case[4:])
+        prob = W.matern_posterior(nx, obs_frac=0.2, q_eps=1e2, corr_range=0.2, seed=nx)
+        A, coords = prob["Qpost"], prob["nodes"]
+    res = pc.check_panel_solves(A, nr=nr, ordering="nd", coords=coords)
+    assert res["violations"] == []
+    assert res["fwd_err"] < 1e-12 and res["solve_err"] < 1e-11
