@@ -141,3 +141,42 @@ def test_panel_sweep_plans(pc, W, case, nr):
     res = pc.check_panel_solves(A, nr=nr, ordering="nd", coords=coords)
     assert res["violations"] == []
     assert res["fwd_err"] < 1e-12 and res["solve_err"] < 1e-11
+
+
+def test_plans_of_random_patterns(pc):
+    """Seeded fuzz over patterns the meshes do not produce - random, arrow (one dense row), disconnected blocks, fully
+    dense; n from 1 to 333; every ordering kind - through the hazard check and the interpreter (factor, selected
+    inversion, kept inverses, panel sweeps)."""
+    rng = np.random.default_rng(123)
+
+    def spd(n, dens, kind):
+        seed = int(rng.integers(1 << 30))
+        if kind == "dense":
+            B = sp.csc_matrix(rng.standard_normal((n, n)))
+        elif kind == "arrow":
+            B = sp.random(n, n, density=dens, random_state=seed, format="lil")
+            B[0, :] = 1.0
+            B[:, 0] = 1.0
+            B = B.tocsc()
+        elif kind == "blocks" and n >= 6:
+            k = n // 3
+            B = sp.block_diag([sp.random(k, k, density=min(1.0, 3 * dens), random_state=seed + i) for i in range(3)] +
+                              [sp.identity(n - 3 * k)], format="csc")
+        else:
+            B = sp.random(n, n, density=dens, random_state=seed, format="csc")
+        S = (abs(B) + abs(B).T).tocsc()
+        A = (-S + sp.diags(2.0 * (np.asarray(S.sum(axis=1)).ravel() + 1.0))).tocsc()  # diagonally dominant
+        A.sort_indices()
+        return A
+
+    for _ in range(45):
+        n = int(rng.choice([1, 2, 3, 5, 17, 64, 65, 130, 200, 333]))
+        kind = str(rng.choice(["random", "arrow", "blocks", "dense"]))
+        n = min(n, 130) if kind == "dense" else n
+        A = spd(n, float(rng.choice([0.005, 0.02, 0.1, 0.4])), kind)
+        ordering = str(rng.choice(["nd", "amd", "nd_amd", "natural"]))
+        res = pc.check_matrix(A, ordering=ordering, use_wide=bool(rng.integers(2)), wide_min=65)
+        assert res["violations"] == [], (n, kind, ordering, res["violations"][:2])
+        assert res["factor_err"] < 1e-12 and res["selinv_err"] < 1e-9, (n, kind, ordering, res)
+        r2 = pc.check_panel_solves(A, nr=int(rng.choice([1, 5, 8, 33])), ordering=ordering)
+        assert r2["violations"] == [] and r2["solve_err"] < 1e-9, (n, kind, ordering, r2)
