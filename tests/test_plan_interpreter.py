@@ -180,3 +180,43 @@ def test_plans_of_random_patterns(pc):
         assert res["factor_err"] < 1e-12 and res["selinv_err"] < 1e-9, (n, kind, ordering, res)
         r2 = pc.check_panel_solves(A, nr=int(rng.choice([1, 5, 8, 33])), ordering=ordering)
         assert r2["violations"] == [] and r2["solve_err"] < 1e-9, (n, kind, ordering, r2)
+
+
+@pytest.mark.parametrize("b,nblocks", [(64, 3), (100, 4), (320, 4), (700, 3)])
+def test_btd_lookahead_schedule(pc, b, nblocks):
+    """The three-stream look-ahead schedule of the block-tridiagonal factor (btd.cu: btd_run_factor): POTRF_i, TRSM_{i+1}
+    and the rank-512 SYRK_{i+1} run on separate streams ordered by per-panel events only.  The host issue sequence is
+    replayed into a happens-before relation; no two launches that may overlap touch a common entry unless both read it,
+    everything is ordered before the end of the stream the host waits for, and the launches - in host order and in random
+    topological orders of that relation - produce the factor of src/tridiagonal_cholesky.jl:70-80 from lower triangles
+    only (the rest of the arena and the inverse slots are NaN)."""
+    res = pc.check_btd_lookahead(b, nblocks=nblocks, orders=2)
+    assert res["violations"] == []
+    assert max(res["factor_err"]) < 1e-13
+    if b > 64:
+        assert res["concurrent_pairs"] > 0  # the schedule does overlap launches: the check is not vacuous
+
+
+@pytest.mark.parametrize("b,nblocks", [(100, 4), (320, 3)])
+def test_btd_time_sharded_lane_schedule(pc, b, nblocks):
+    """The fourth stream of the time-sharded factor (gmrfb_btd_dist_factor's after_block): W_i = L_i^-1 by recursive
+    doubling and the spike step of block i run behind POTRF_i, ordered by one event, while the chains of the next blocks
+    go on.  Same check; in every order the interpreted launches give W_i L_i = I, the spike blocks
+    S_1 = E_l' W_1', S_i = -S_{i-1} C_i' W_i' and Q = sum S_i S_i'."""
+    res = pc.check_btd_lookahead(b, nblocks=nblocks, orders=2, lane=True)
+    assert res["violations"] == []
+    assert max(res["factor_err"]) < 1e-12
+
+
+@pytest.mark.parametrize("mutation,b", [(dict(drop_trsm_waits=True), 320), (dict(drop_potrf_wait=True), 320),
+                                        (dict(syrk_wait_shift=1), 700), (dict(lane=True, drop_lane_wait=True), 200)])
+def test_btd_schedule_checker_reports_missing_synchronisation(pc, mutation, b):
+    """Negative controls: without the per-panel waits of the TRSM, without the wait of POTRF_{i+1} for the last update,
+    with a rank-512 update waiting one column block too early, or without the event between POTRF_i and the time-sharded
+    lane, the checker names the unordered launches."""
+    BP = pc.BtdPlans(b)
+    nodes, issues = pc.btd_schedule(BP, 3, **mutation)
+    races, _ = pc.btd_races(BP, nodes)
+    assert races
+    kinds = {r[0] for r in races}
+    assert "read after write" in kinds

@@ -150,4 +150,105 @@ void pc_get(PC* h, int which, void* tasks, void* launches, int64_t* winv_slot) {
   std::memcpy(launches, P.launches.data(), P.launches.size() * sizeof(Launch));
   if (winv_slot && !P.winv_slot.empty()) std::memcpy(winv_slot, P.winv_slot.data(), P.winv_slot.size() * 8);
 }
+
+// ---- block-tridiagonal look-ahead schedule (btd.cu: btd_alloc builds these plans, btd_run_factor runs them) ----
+// The POTRF and TRSM plans come from plan.cpp (plan_potrf_events / plan_trsm_rlt_events: the event numbering under test);
+// the rank-512 SYRK launches restate the loop of btd_alloc.  Offsets are relative to the current block's slot
+// [L_i | C_i] (the previous slot lies `slot` doubles before).  which: 0 POTRF_i, 1 TRSM_{i+1}, 2 SYRK_{i+1};
+// time-sharded factor (gmrfb_btd_dist_factor: a further lane behind POTRF_i): 3 W_i = L_i^-1 by recursive doubling
+// (btd_prepare_winv: arenas 0 = slot i, 1 = W_i, 2 = scratch), 4 / 5 first / later step of the spike recurrence
+// (arenas 0 = slot i, 1 = spike block i with block i-1 one block before, 2 = [T | E_l | Q], 3 = W_i).
+struct PCB {
+  int b, ld;
+  int64_t slot;
+  Plan plans[6];
+};
+PCB* pcb_create(int b) {
+  PCB* h = new PCB();
+  h->b = b;
+  h->ld = (b + 1) & ~1;
+  h->slot = 2 * (int64_t)h->ld * b;
+  const int64_t coff = (int64_t)h->ld * b;
+  {
+    PlanBuilder B(h->plans[0]);
+    plan_potrf_events(B, h->plans[0], 0, 0, b, h->ld, 0);
+  }
+  {
+    PlanBuilder B(h->plans[1]);
+    plan_trsm_rlt_events(B, h->plans[1], 0, -h->slot, h->ld, 0, coff, b, b, h->ld);
+  }
+  {
+    Plan& P = h->plans[2];
+    PlanBuilder B(P);
+    const int LA_SYRK_K = 512;
+    for (int c0 = 0; c0 < b; c0 += LA_SYRK_K) {
+      const int kc = std::min(LA_SYRK_K, b - c0);
+      B.begin(LK_GEMM_NT);
+      B.set_wait((c0 + kc - 1) / NB);
+      Task t = make_task();
+      t.a = coff + (int64_t)c0 * h->ld;
+      t.b = t.a;
+      t.c = 0;
+      t.lda = t.ldb = t.ldc = h->ld;
+      t.M = t.N = b;
+      t.K = kc;
+      t.alpha = -1.0;
+      t.beta = 1.0;
+      t.flags = TF_TRI;
+      B.add(t, gemm_tiles(b, b, true, GCFG_BIG));
+      B.end();
+    }
+  }
+  {
+    PlanBuilder B(h->plans[3]);
+    plan_trtri(B, h->plans[3], 0, 0, h->ld, 1, 0, h->ld, 2, 0, b);
+  }
+  {
+    const int64_t bs = coff;
+    const int ld = h->ld;
+    auto gemm = [&](PlanBuilder& B, int kind, int aa, int64_t a, int ab, int64_t bo, int ac, int64_t c, bool tri, double alpha,
+                    double beta, int32_t extra) {
+      B.begin(kind);
+      Task t = make_task();
+      t.a = a;
+      t.b = bo;
+      t.c = c;
+      t.lda = t.ldb = t.ldc = ld;
+      t.M = t.N = t.K = b;
+      t.alpha = alpha;
+      t.beta = beta;
+      t.flags = (aa << TF_A_SHIFT) | (ab << TF_B_SHIFT) | (ac << TF_C_SHIFT) | (tri ? TF_TRI : 0) | extra;
+      B.add(t, gemm_tiles(b, b, tri, GCFG_BIG));
+      B.end();
+    };
+    {  // S_1 = E_l' W_1';  Q = S_1 S_1'
+      PlanBuilder B(h->plans[4]);
+      gemm(B, LK_GEMM_TT, 2, bs, 3, 0, 1, 0, false, 1.0, 0.0, TF_BUPP);
+      gemm(B, LK_GEMM_NT, 1, 0, 1, 0, 2, 2 * bs, true, 1.0, 1.0, 0);
+    }
+    {  // T = S_{i-1} C_i';  S_i = -T W_i';  Q += S_i S_i'
+      PlanBuilder B(h->plans[5]);
+      gemm(B, LK_GEMM_NT, 1, -bs, 0, bs, 2, 0, false, 1.0, 0.0, 0);
+      gemm(B, LK_GEMM_NT, 2, 0, 3, 0, 1, 0, false, -1.0, 0.0, TF_BUPP);
+      gemm(B, LK_GEMM_NT, 1, 0, 1, 0, 2, 2 * bs, true, 1.0, 1.0, 0);
+    }
+  }
+  return h;
+}
+void pcb_destroy(PCB* h) { delete h; }
+// out: [ld, slot, then per plan: tasks, launches, dinv doubles]
+void pcb_sizes(PCB* h, int64_t* out) {
+  out[0] = h->ld;
+  out[1] = h->slot;
+  for (int w = 0; w < 6; w++) {
+    out[2 + 3 * w] = (int64_t)h->plans[w].tasks.size();
+    out[3 + 3 * w] = (int64_t)h->plans[w].launches.size();
+    out[4 + 3 * w] = h->plans[w].dinv;
+  }
+}
+void pcb_get(PCB* h, int which, void* tasks, void* launches) {
+  const Plan& P = h->plans[which];
+  std::memcpy(tasks, P.tasks.data(), P.tasks.size() * sizeof(Task));
+  std::memcpy(launches, P.launches.data(), P.launches.size() * sizeof(Launch));
+}
 }

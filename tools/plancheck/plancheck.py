@@ -659,6 +659,319 @@ def check_panel_solves(A, nr=7, ordering="nd", coords=None, perm=None):
     return out
 
 
+# ------------------------------------------------- block-tridiagonal look-ahead schedule (csrc/btd.cu) ----
+# btd_run_factor runs three plans per block on three streams (POTRF_i on the context's stream, TRSM_{i+1} and the rank-512
+# SYRK_{i+1} on two further streams) ordered only by per-panel events.  Launches of different streams run concurrently,
+# so the hazard to exclude is between LAUNCHES: any two launches that are not ordered by stream order + events must not
+# touch the same entry unless both only read it.  The host issue sequence of btd_run_factor is replayed here (same
+# event bookkeeping as cudaEventRecord / cudaStreamWaitEvent: a wait refers to the most recent record at the time of the
+# call), giving a happens-before relation; the access sets come from the same Task records as above.
+class BtdPlans:
+    """The three look-ahead plans of a block-tridiagonal factor with blocks of order b (plan.cpp builders)."""
+
+    def __init__(self, b):
+        self.L = _lib()
+        P = C.c_void_p
+        self.L.pcb_create.restype = P
+        self.L.pcb_create.argtypes = [C.c_int]
+        self.L.pcb_destroy.argtypes = [P]
+        self.L.pcb_sizes.argtypes = [P, P]
+        self.L.pcb_get.argtypes = [P, C.c_int, P, P]
+        h = self.L.pcb_create(int(b))
+        sz = np.zeros(20, dtype=np.int64)
+        self.L.pcb_sizes(h, _p(sz))
+        self.b, self.ld, self.slot = int(b), int(sz[0]), int(sz[1])
+        self.nblk = (self.b + 63) // 64
+        self.bs = self.ld * self.b
+        self.plans = []  # 0 POTRF_i, 1 TRSM_{i+1}, 2 SYRK_{i+1}; time-sharded lane: 3 W_i = L_i^-1, 4 / 5 spike first / step
+        for w in range(6):
+            nt, nl, dinv = (int(v) for v in sz[2 + 3 * w:5 + 3 * w])
+            tasks = np.zeros(max(nt, 1), dtype=TASK)
+            launches = np.zeros(max(nl, 1), dtype=LAUNCH)
+            self.L.pcb_get(h, w, _p(tasks), _p(launches))
+            self.plans.append(dict(tasks=tasks[:nt], launches=launches[:nl], dinv=dinv))
+        self.L.pcb_destroy(h)
+        self.setsz = self.nblk * DINV_SLOT
+
+
+def _shift_task(BP, t, bases, dset=0):
+    """the Task as the kernel sees it once Arenas holds `bases` (arena index -> start of that arena in one flat array that
+    stands for all device buffers) and inverse set `dset`: absolute offsets, every operand in arena 0."""
+    t = t.copy()
+    f = int(t["flags"])
+    t["a"] += bases[_arena(t, 0)]
+    t["c"] += bases[_arena(t, 4)]
+    t["b"] += dset * BP.setsz if f & TF_B_DINV else bases[_arena(t, 2)]
+    t["flags"] = f & ~0x3f
+    return t
+
+
+LK_ZERO_UPPER = 100  # k_zero_upper of btd_winv_block (not a plan launch): strict upper triangle of a b x b block <- 0
+
+
+def _node_access(nd):
+    if nd["kind"] == LK_ZERO_UPPER:
+        off, ld, b = nd["tasks"][0]
+        i, j = np.triu_indices(b, 1)
+        return [], [(0, off + i.astype(np.int64) + j.astype(np.int64) * ld)]
+    R, Wr = [], []
+    for t in nd["tasks"]:
+        r, w = task_access(None, nd["kind"], t)
+        R += r
+        Wr += w
+    return R, Wr
+
+
+def _node_run(nd, S):
+    if nd["kind"] == LK_ZERO_UPPER:
+        off, ld, b = nd["tasks"][0]
+        i, j = np.triu_indices(b, 1)
+        S.ar[0][off + i.astype(np.int64) + j.astype(np.int64) * ld] = 0.0
+        return
+    for t in nd["tasks"]:
+        _run_task(None, S, nd["kind"], t)
+
+
+def btd_layout(BP, nblocks):
+    """one flat array for every device buffer of the (time-sharded) factor: the factor slots, W (nblocks blocks), the
+    scratch of the recursive doubling, the spike blocks S (nblocks blocks), the work arena [T | E_l | Q]."""
+    o, lay = 0, {}
+    for name, sz in (("arena", BP.slot * nblocks), ("W", BP.bs * nblocks), ("scratch", BP.bs), ("S", BP.bs * nblocks),
+                     ("work", 3 * BP.bs)):
+        lay[name] = o
+        o += sz
+    lay["total"] = o
+    return lay
+
+
+def btd_schedule(BP, nblocks, drop_trsm_waits=False, drop_potrf_wait=False, syrk_wait_shift=0, lane=False,
+                 drop_lane_wait=False):
+    """Replay of the host side of btd_run_factor (look-ahead branch).  Returns the launches in host issue order as dicts
+    (stream, block, which, kind, tasks (absolute offsets), preds) plus the issues found while replaying (a wait on an
+    event that was never recorded).  The keyword arguments remove / misplace synchronisation (negative controls)."""
+    nodes, issues = [], []
+    last = {0: None, 1: None, 2: None, 3: None}  # stream -> index of its last launch
+    pending = {0: [], 1: [], 2: [], 3: []}       # stream -> launches its next launch must wait for
+    events = {}
+    lay = btd_layout(BP, nblocks)
+
+    def record(ev, st):
+        events[ev] = last[st]
+
+    def wait(st, ev):
+        if ev not in events:
+            issues.append(("wait on an event never recorded", ev))
+        elif events[ev] is not None:
+            pending[st].append(events[ev])
+
+    def push(st, block, which, li, kind, tasks):
+        preds = ([last[st]] if last[st] is not None else []) + pending[st]
+        pending[st] = []
+        nodes.append(dict(stream=st, block=block, which=which, li=li, kind=kind, tasks=tasks, preds=preds))
+        last[st] = len(nodes) - 1
+
+    def run_plan(which, st, block, dset, wait_evs, rec_evs):
+        pl = BP.plans[which]
+        slot_i = lay["arena"] + block * BP.slot
+        bases = {0: [slot_i] * 4, 1: [slot_i] * 4, 2: [slot_i] * 4,
+                 3: [slot_i, lay["W"] + block * BP.bs, lay["scratch"], 0],
+                 4: [slot_i, lay["S"] + block * BP.bs, lay["work"], lay["W"] + block * BP.bs]}[min(which, 4)]
+        for li, L in enumerate(pl["launches"]):
+            wv = int(L["wait_ev"])
+            if which == 2 and wv >= 0:
+                wv = max(0, wv - syrk_wait_shift)
+            if wv >= 0 and wait_evs is not None:
+                wait(st, (wait_evs, wv))
+            tasks = [_shift_task(BP, pl["tasks"][int(L["task0"]) + k], bases, dset) for k in range(int(L["ntasks"]))]
+            push(st, block, which, li, int(L["kind"]), tasks)
+            if int(L["rec_ev"]) >= 0 and rec_evs is not None:
+                record((rec_evs, int(L["rec_ev"])), st)
+
+    record("done", 0)
+    wait(1, "done")
+    wait(2, "done")
+    for i in range(nblocks):
+        s = i & 1
+        if i > 0:
+            run_plan(1, 1, i, 1 - s, None if drop_trsm_waits else ("ev", 1 - s), ("cev", s))
+            run_plan(2, 2, i, 1 - s, ("cev", s), None)
+            record("done", 2)
+            if not drop_potrf_wait:
+                wait(0, "done")
+        run_plan(0, 0, i, s, None, ("ev", s))
+        if lane:
+            # gmrfb_btd_dist_factor's after_block: W_i = L_i^-1 and the spike step of block i on a further stream, ordered
+            # behind POTRF_i by one event; the next blocks' chains go on meanwhile
+            record("lane", 0)
+            if not drop_lane_wait:
+                wait(3, "lane")
+            if BP.b > 1:
+                push(3, i, 3, -1, LK_ZERO_UPPER, [(lay["arena"] + i * BP.slot, BP.ld, BP.b)])
+            run_plan(3, 3, i, 0, None, None)
+            run_plan(4 if i == 0 else 5, 3, i, 0, None, None)
+    # the host synchronises the context's stream (then, with the lane, that stream too)
+    return nodes, issues
+
+
+def _happens_before(nodes):
+    n = len(nodes)
+    hb = np.zeros((n, n), dtype=bool)           # hb[k, j]: launch j completes before launch k starts
+    for k, nd in enumerate(nodes):
+        for p in nd["preds"]:
+            hb[k] |= hb[p]
+            hb[k, p] = True
+    return hb
+
+
+def btd_races(BP, nodes):
+    """Launch pairs that touch a common entry (at least one writing) without being ordered.  One forward pass (each
+    access against the last earlier writer of the entry) and one backward pass (each read against the next later writer)
+    over the host order find every such pair up to transitivity."""
+    hb = _happens_before(nodes)
+    size = {0: 0, DINV_ARENA: 2 * BP.setsz}
+    acc = []
+    for nd in nodes:
+        R, Wr = {}, {}
+        r, w = _node_access(nd)
+        for a, ix in r:
+            R.setdefault(a, []).append(ix)
+        for a, ix in w:
+            Wr.setdefault(a, []).append(ix)
+        R = {a: np.unique(np.concatenate(v)) for a, v in R.items()}
+        Wr = {a: np.unique(np.concatenate(v)) for a, v in Wr.items()}
+        for d in (R, Wr):
+            for a, ix in d.items():
+                size[a] = max(size.get(a, 0), int(ix.max()) + 1 if ix.size else 0)
+        acc.append((R, Wr))
+    bad = []
+    name = {0: "POTRF", 1: "TRSM", 2: "SYRK", 3: "WINV", 4: "SPIKE", 5: "SPIKE"}
+
+    def label(k):
+        nd = nodes[k]
+        return f"{name[nd['which']]}_{nd['block']}[{nd['li']}:{KIND_NAME.get(nd['kind'], 'ZERO_UPPER')}]"
+
+    lastw = {a: np.full(s, -1, dtype=np.int64) for a, s in size.items()}
+    for k, (R, Wr) in enumerate(acc):
+        for what, d in (("read after write", R), ("write after write", Wr)):
+            for a, ix in d.items():
+                for w in np.unique(lastw[a][ix]):
+                    if w >= 0 and w != k and not hb[k, w]:
+                        bad.append((what, label(int(w)), label(k), a))
+        for a, ix in Wr.items():
+            lastw[a][ix] = k
+    nextw = {a: np.full(s, -1, dtype=np.int64) for a, s in size.items()}
+    for k in range(len(nodes) - 1, -1, -1):
+        R, Wr = acc[k]
+        for a, ix in R.items():
+            for w in np.unique(nextw[a][ix]):
+                if w >= 0 and w != k and not hb[w, k]:
+                    bad.append(("write after read", label(k), label(int(w)), a))
+        for a, ix in Wr.items():
+            nextw[a][ix] = k
+    # completion: the last launch of the context's stream (what the host waits for) is after every other launch
+    sink = max(k for k, nd in enumerate(nodes) if nd["stream"] == 0)
+    for k in range(len(nodes)):
+        if k != sink and nodes[k]["stream"] != 3 and not hb[sink, k]:
+            bad.append(("not ordered before the end of the context's stream", label(k), label(sink), -1))
+    return bad, hb
+
+
+class _BtdState:
+    def __init__(self, arena, dinv):
+        self.ar = [arena, None, None, None, dinv, None]
+
+
+def check_btd_lookahead(b, nblocks=4, seed=0, orders=3, lane=False, **mutations):
+    """Hazard check of the look-ahead schedule of a b x b, nblocks-block factor + interpretation of the launches in host
+    order and in `orders` random topological orders of the happens-before relation, on arenas whose unused parts are
+    NaN: every order must give the block Cholesky factor of src/tridiagonal_cholesky.jl:70-80."""
+    BP = BtdPlans(b)
+    out = dict(b=b, ld=BP.ld, nblocks=nblocks, violations=[])
+    for w, nm in enumerate(("potrf", "trsm", "syrk") + (("winv", "spike_first", "spike_step") if lane else ())):
+        nl, nt, bad = hazards(None, BP.plans[w])
+        out[nm] = dict(launches=nl, tasks=nt)
+        out["violations"] += [(nm,) + x for x in bad]
+    nodes, issues = btd_schedule(BP, nblocks, lane=lane, **mutations)
+    lay = btd_layout(BP, nblocks)
+    out["violations"] += issues
+    races, hb = btd_races(BP, nodes)
+    out["violations"] += races
+    out["launches"] = len(nodes)
+    # pairs of launches that may overlap on the GPU (neither ordered before the other)
+    free = ~(hb | hb.T)
+    np.fill_diagonal(free, False)
+    out["concurrent_pairs"] = int(free.sum() // 2)
+    # interpretation
+    rng = np.random.default_rng(seed)
+    ld, slot = BP.ld, BP.slot
+    D, Bs = [], []
+    for i in range(nblocks):
+        G = rng.standard_normal((b, b))
+        D.append(G @ G.T / b + 4.0 * np.eye(b))
+        Bs.append(rng.standard_normal((b, b)) / np.sqrt(b))
+    Lr, Cr = [np.linalg.cholesky(D[0])], [None]
+    for i in range(1, nblocks):
+        Ci = np.linalg.solve(Lr[i - 1], Bs[i].T).T
+        Cr.append(Ci)
+        Lr.append(np.linalg.cholesky(D[i] - Ci @ Ci.T))
+    # spike recurrence of the time-sharded factor: S_1 = E_l' W_1', S_i = -S_{i-1} C_i' W_i', Q = sum S_i S_i'
+    El = Bs[0]
+    Wr_ = [np.linalg.inv(Lm) for Lm in Lr]
+    Sr = [El.T @ Wr_[0].T]
+    for i in range(1, nblocks):
+        Sr.append(-(Sr[i - 1] @ Cr[i].T) @ Wr_[i].T)
+    Qr = sum(Sm @ Sm.T for Sm in Sr)
+    errs = []
+    n = len(nodes)
+    for o in range(orders + 1):
+        if o == 0:
+            order = list(range(n))
+        else:  # random topological order: repeatedly pick any launch whose predecessors have all run
+            indeg = np.array([len(set(nd["preds"])) for nd in nodes])
+            succ = [[] for _ in range(n)]
+            for k, nd in enumerate(nodes):
+                for p in set(nd["preds"]):
+                    succ[p].append(k)
+            ready = [k for k in range(n) if indeg[k] == 0]
+            order = []
+            while ready:
+                k = ready.pop(int(rng.integers(len(ready))))
+                order.append(k)
+                for q in succ[k]:
+                    indeg[q] -= 1
+                    if indeg[q] == 0:
+                        ready.append(q)
+            assert len(order) == n
+        arena = np.full(lay["total"], np.nan)
+        if lane:  # what gmrfb_btd_dist_factor queues on the context's stream before the factor: W <- 0, Q <- 0, E_l
+            arena[lay["W"]:lay["W"] + BP.bs * nblocks] = 0.0
+            arena[lay["work"] + 2 * BP.bs:lay["work"] + 3 * BP.bs] = 0.0
+            _view(arena, lay["work"] + BP.bs, ld, b, b)[:, :] = El
+        for i in range(nblocks):
+            Dv = _view(arena, i * slot, ld, b, b)
+            il, jl = np.tril_indices(b)
+            Dv[il, jl] = D[i][il, jl]                    # only the lower triangle is supplied
+            if i > 0:
+                _view(arena, i * slot + ld * b, ld, b, b)[:, :] = Bs[i]
+        S = _BtdState(arena, np.full(2 * BP.setsz, np.nan))
+        for k in order:
+            _node_run(nodes[k], S)
+        e = 0.0
+        for i in range(nblocks):
+            e = max(e, float(np.abs(np.tril(_view(arena, i * slot, ld, b, b)) - Lr[i]).max()))
+            if i > 0:
+                e = max(e, float(np.abs(_view(arena, i * slot + ld * b, ld, b, b) - Cr[i]).max()))
+            if lane:
+                e = max(e, float(np.abs(_view(arena, lay["W"] + i * BP.bs, ld, b, b) - Wr_[i]).max() / np.abs(Wr_[i]).max()))
+                e = max(e, float(np.abs(_view(arena, lay["S"] + i * BP.bs, ld, b, b) - Sr[i]).max() / np.abs(Sr[i]).max()))
+        if lane:
+            Qv = np.tril(_view(arena, lay["work"] + 2 * BP.bs, ld, b, b))
+            e = max(e, float(np.abs(Qv - np.tril(Qr)).max() / np.abs(Qr).max()))
+        errs.append(e)
+    out["factor_err"] = errs
+    return out
+
+
 def main():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
@@ -669,6 +982,9 @@ def main():
         res = check_matrix(prob["Qpost"], ordering=ordering, coords=prob["nodes"] if ordering == "nd" else None,
                            use_wide=uw, wide_min=65)
         print(nx, ordering, {k: v for k, v in res.items() if k != "violations"}, "violations:", res["violations"][:3])
+    for b, nb, lane in ((320, 4, False), (700, 4, True), (1100, 3, False)):
+        res = check_btd_lookahead(b, nblocks=nb, orders=1, lane=lane)
+        print("btd look-ahead", {k: v for k, v in res.items() if k != "violations"}, "violations:", res["violations"][:3])
 
 
 if __name__ == "__main__":
