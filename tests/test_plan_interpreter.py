@@ -220,3 +220,15 @@ def test_btd_schedule_checker_reports_missing_synchronisation(pc, mutation, b):
     assert races
     kinds = {r[0] for r in races}
     assert "read after write" in kinds
+
+
+def test_btd_schedule_model_bounds(pc):
+    """The fluid model of the look-ahead schedule (profiles/r02_btd_schedule_model.md): its makespan lies between the two
+    lower bounds (critical path with unlimited SMs; SM-seconds of work over 148 SMs) and the serial schedule."""
+    BP = pc.BtdPlans(700)
+    nodes, issues = pc.btd_schedule(BP, 5)
+    assert not issues
+    t, cp, work = pc.btd_simulate(nodes)
+    serial, _, _ = pc.btd_simulate(nodes, serial=True)
+    assert max(cp, work) <= t * (1 + 1e-9) and t <= serial * (1 + 1e-9)
+    assert t < 0.9 * serial  # the look-ahead does overlap the three chains

@@ -196,6 +196,7 @@ PCB* pcb_create(int b) {
       t.beta = 1.0;
       t.flags = TF_TRI;
       B.add(t, gemm_tiles(b, b, true, GCFG_BIG));
+      P.flops += (double)kc * b * (b + 1);
       B.end();
     }
   }

@@ -764,10 +764,11 @@ def btd_schedule(BP, nblocks, drop_trsm_waits=False, drop_potrf_wait=False, syrk
         elif events[ev] is not None:
             pending[st].append(events[ev])
 
-    def push(st, block, which, li, kind, tasks):
+    def push(st, block, which, li, kind, tasks, grid=1, flops=0.0):
         preds = ([last[st]] if last[st] is not None else []) + pending[st]
         pending[st] = []
-        nodes.append(dict(stream=st, block=block, which=which, li=li, kind=kind, tasks=tasks, preds=preds))
+        nodes.append(dict(stream=st, block=block, which=which, li=li, kind=kind, tasks=tasks, preds=preds, grid=grid,
+                          flops=flops))
         last[st] = len(nodes) - 1
 
     def run_plan(which, st, block, dset, wait_evs, rec_evs):
@@ -783,7 +784,7 @@ def btd_schedule(BP, nblocks, drop_trsm_waits=False, drop_potrf_wait=False, syrk
             if wv >= 0 and wait_evs is not None:
                 wait(st, (wait_evs, wv))
             tasks = [_shift_task(BP, pl["tasks"][int(L["task0"]) + k], bases, dset) for k in range(int(L["ntasks"]))]
-            push(st, block, which, li, int(L["kind"]), tasks)
+            push(st, block, which, li, int(L["kind"]), tasks, int(L["grid"]), float(L["flops"]))
             if int(L["rec_ev"]) >= 0 and rec_evs is not None:
                 record((rec_evs, int(L["rec_ev"])), st)
 
@@ -874,6 +875,66 @@ def btd_races(BP, nodes):
         if k != sink and nodes[k]["stream"] != 3 and not hb[sink, k]:
             bad.append(("not ordered before the end of the context's stream", label(k), label(sink), -1))
     return bad, hb
+
+
+def btd_simulate(nodes, t_potrf=22.7e-6, t_apply=8.8e-6, t_launch=5e-6, peak=33e12, sms=148, serial=False):
+    """Fluid model of the schedule on `sms` SMs: a launch becomes ready when its predecessors have finished, asks for
+    min(grid, sms) SMs and, given all of them, takes t_launch + flops / (peak * share of the machine) (GEMM kinds) or a
+    fixed latency (64 x 64 POTRF + inverse; apply-inverse) - the per-launch figures of profiles/r02_launch_list.md.
+    The launches of the context's stream (highest priority) are served first, the others share what is left in
+    proportion to their demand.  Returns (makespan, length of the critical path with unlimited SMs, SM-seconds of work /
+    sms).  serial=True: one stream, launches back to back (the schedule without look-ahead)."""
+    n = len(nodes)
+    dem = np.array([min(max(nd["grid"], 1), sms) for nd in nodes], dtype=float)
+    ideal = np.empty(n)
+    for k, nd in enumerate(nodes):
+        if nd["kind"] == LK_POTRF:
+            ideal[k] = t_potrf
+        elif nd["kind"] in (LK_TRSM_RLT, LK_TRSM_RLN, LK_ZERO_UPPER, LK_SET_IDENTITY):
+            ideal[k] = t_apply
+        else:
+            ideal[k] = t_launch + nd["flops"] / (peak * dem[k] / sms)
+    work = float((ideal * dem).sum() / sms)
+    if serial:
+        return float(ideal.sum()), float(ideal.sum()), work
+    preds = [sorted(set(nd["preds"])) for nd in nodes]
+    cp = np.zeros(n)
+    for k in range(n):
+        cp[k] = ideal[k] + max([cp[p] for p in preds[k]], default=0.0)
+    succ = [[] for _ in range(n)]
+    left = np.array([len(p) for p in preds])
+    for k, pp in enumerate(preds):
+        for p in pp:
+            succ[p].append(k)
+    remaining = ideal.copy()          # seconds of work at full demand
+    running = [k for k in range(n) if left[k] == 0]
+    t = 0.0
+    while running:
+        free = float(sms)
+        rate = {}
+        hi = [k for k in running if nodes[k]["stream"] == 0]
+        lo = [k for k in running if nodes[k]["stream"] != 0]
+        for k in hi:
+            a = min(dem[k], free)
+            free -= a
+            rate[k] = a / dem[k]
+        tot = sum(dem[k] for k in lo)
+        for k in lo:
+            rate[k] = min(1.0, free / tot) if tot > 0 else 0.0
+        dt = min(remaining[k] / rate[k] for k in running if rate[k] > 0)
+        t += dt
+        done = []
+        for k in running:
+            remaining[k] -= dt * rate[k]
+            if remaining[k] <= 1e-15:
+                done.append(k)
+        for k in done:
+            running.remove(k)
+            for q in succ[k]:
+                left[q] -= 1
+                if left[q] == 0:
+                    running.append(q)
+    return t, float(cp.max()), work
 
 
 class _BtdState:
