@@ -287,3 +287,37 @@ def test_fem_oracle_lagrange_triangles(orc, W):
     for Q in (Q2, Q3):
         assert abs(Q - Q.T).max() < 1e-9 * abs(Q).max()
         assert np.linalg.eigvalsh(((Q + Q.T) / 2).toarray()).min() > 0
+
+
+@pytest.mark.parametrize("nx", [151, 301])
+def test_oracles_against_superlu_beyond_dense_sizes(orc, W, nx):
+    """Tier B of SURVEY.md section 8(c): at sizes dense LAPACK cannot reach (n = 22 801 / 90 601) both CPU oracles - the
+    scalar up-looking Cholesky and the supernodal baseline of `bench.py --impl reference` - are compared with SciPy's
+    SuperLU, an independent sparse direct solver (LU with partial pivoting and COLAMD, no code or ordering in common):
+    posterior mean, log-determinant (sum of log |U_ii|: the L of SuperLU has a unit diagonal) and marginal variances at
+    probe nodes (columns of the inverse by unit-vector solves against the Takahashi recurrences)."""
+    import scipy.sparse.linalg as spla
+
+    prob = W.matern_posterior(nx, obs_frac=0.1, q_eps=1e2, corr_range=0.1, seed=nx)
+    Q = prob["Qpost"].tocsc()
+    n = Q.shape[0]
+    rng = np.random.default_rng(nx)
+    lu = spla.splu(Q)
+    B = rng.standard_normal((n, 2))
+    Xlu = lu.solve(B)
+    logdet_lu = float(np.sum(np.log(np.abs(lu.U.diagonal()))))
+    probes = rng.choice(n, size=12, replace=False)
+    E = np.zeros((n, probes.size))
+    E[probes, np.arange(probes.size)] = 1.0
+    var_lu = lu.solve(E)[probes, np.arange(probes.size)]
+    F = orc.SupernodalCholesky.analyze(Q, coords=prob["nodes"])
+    Xs = F.solve(B)
+    assert np.linalg.norm(Xs - Xlu) <= 1e-10 * np.linalg.norm(Xlu)
+    assert abs(F.logdet() - logdet_lu) <= 1e-10 * abs(logdet_lu)
+    np.testing.assert_allclose(F.selinv_diag()[probes], var_lu, rtol=1e-9)
+    if nx <= 151:  # the scalar oracle's Takahashi recurrence is a Python-driven column loop
+        p = orc.nested_dissection(Q, prob["nodes"], leaf=32)
+        ch = orc.SparseCholesky(Q, p)
+        assert np.linalg.norm(ch.solve(B) - Xlu) <= 1e-10 * np.linalg.norm(Xlu)
+        assert abs(ch.logdet() - logdet_lu) <= 1e-10 * abs(logdet_lu)
+        np.testing.assert_allclose(ch.selinv_diag()[probes], var_lu, rtol=1e-9)

@@ -626,6 +626,28 @@ def check_matrix(A, ordering="nd", coords=None, perm=None, use_wide=False, wide_
     return out
 
 
+def check_hazards_only(A, ordering="nd", coords=None, perm=None, nr=50, wide_min=128):
+    """Hazard check of every plan of `A` (zero, factor, wide inverses, selected inversion with the kept inverses, panel
+    sweeps for nr right-hand sides) without interpreting them: for patterns whose dense inverse is out of reach."""
+    import time
+    P = Plans(A, ordering=ordering, coords=coords, perm=perm, wide_min=wide_min)
+    out = dict(n=P.n, nsuper=P.nsuper, n_wide=int(P.wide.size), max_front=max(P.d(s) for s in range(P.nsuper)),
+               arena_doubles=P.arena, violations=[])
+    t0 = time.time()
+    uw = P.wide.size > 0
+    for w in ["zero", "factor"] + (["wide"] if uw else []) + ["selinv"]:
+        nl, nt, bad = hazards(P, P.plan(w, uw and w == "selinv"))
+        out[w] = dict(launches=nl, tasks=nt)
+        out["violations"] += [(w,) + b for b in bad]
+    fwd, bwd = P.mr_plans(nr, (nr + 1) & ~1)
+    for name, pl in (("panel_fwd", fwd), ("panel_bwd", bwd)):
+        nl, nt, bad = hazards(P, pl)
+        out[name] = dict(launches=nl, tasks=nt)
+        out["violations"] += [(name,) + b for b in bad]
+    out["seconds"] = round(time.time() - t0, 1)
+    return out
+
+
 def check_panel_solves(A, nr=7, ordering="nd", coords=None, perm=None):
     """Hazard check + interpretation of the panel (multi-right-hand-side) sweeps: zero, scatter, factor, then forward
     and backward sweep of a node-major panel of nr right-hand sides; the result must solve (P A P') X' = B'."""
