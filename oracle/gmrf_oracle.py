@@ -12,7 +12,8 @@ The oracle therefore has three tiers, each pinned against something independent:
 * Tier A (dense, n <~ 8000): LAPACK through numpy/scipy — ``cho_factor``, triangular solves, ``inv``.
 * Tier B (sparse, mid size): ``sparse_chol.c`` — CHOLMOD's published simplicial algorithm
   (Liu etree, row-subtree column counts, up-looking Cholesky, Takahashi recurrences); pinned against
-  Tier A in tests/test_oracle.py.
+  Tier A in tests/test_oracle.py and, like the supernodal baseline (``supernodal_chol.c``), against SciPy's
+  SuperLU (an independent sparse direct solver: LU, COLAMD) at n = 22 801 / 90 601, beyond dense sizes.
 * Block-tridiagonal: a line-by-line restatement of src/tridiagonal_cholesky.jl:65-82 (factor) and of the
   *intended* semantics of :24-63 (solves; the three defects documented in SURVEY.md §8a T4/T5/T7 are not
   reproduced), pinned against Tier A on the assembled matrix.
