@@ -243,7 +243,6 @@ mutable struct B200TridiagonalCholeskyFactor
     nblocks::Int
 end
 
-"`tridiagonal_cholesky(A::SparseMatrixCSC, N_blocks)` (src/tridiagonal_cholesky.jl:65-82)."
 # ---------------------------------------------------------------------------------------------------------------
 # Gauss-Newton on the device (gmrfb_gn_*): the loop of scripts/solve_burger.jl:143-180 for a bilinear collocation
 # residual f(w) = L w + c (A w).*(D w)  (Burgers, :127-134: L = A1 - A0 - dt*nu*D2, A = A1, c = dt).
@@ -307,6 +306,7 @@ function optimize!(gn::B200GaussNewton, x0::Vector{Float64}; max_steps::Integer 
     return x
 end
 
+"`tridiagonal_cholesky(A::SparseMatrixCSC, N_blocks)` (src/tridiagonal_cholesky.jl:65-82)."
 function b200_tridiagonal_cholesky(A::SparseMatrixCSC{Float64,Int64}, N_blocks::Integer; ctx::B200Context = default_context())
     out = Ref{Ptr{Cvoid}}(C_NULL)
     st = GC.@preserve A ccall((:gmrfb_btd_factor, libgmrfb), Int32,
@@ -345,7 +345,8 @@ backward_solve(F::B200TridiagonalCholeskyFactor, b) = _btd_solve(F, BTD_SOLVE_BW
 forward_solve(F::B200Factor, b) = F.PtL \ b          # :39-41
 backward_solve(F::B200Factor, b) = F.UP \ b          # :20-22
 ldiv(F::B200TridiagonalCholeskyFactor, b) = _btd_solve(F, BTD_SOLVE_A, b)
-ldiv!(y, F::B200TridiagonalCholeskyFactor, b) = (y .= ldiv(F, b); y)
+# extends LinearAlgebra.ldiv! (a `using`-visible name that is not imported must be qualified to receive methods)
+LinearAlgebra.ldiv!(y, F::B200TridiagonalCholeskyFactor, b) = (y .= ldiv(F, b); y)
 
 function LinearAlgebra.logdet(F::B200TridiagonalCholeskyFactor)
     out = Ref(0.0)
