@@ -74,3 +74,47 @@ def test_no_exception_crosses_the_abi(entry):
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "STATUS 3" in out.stdout and "bad_alloc" in out.stdout, out.stdout + out.stderr[-500:]
+
+
+def test_ctypes_signatures_match_the_header_types(entry, pkg):
+    """Every entry of the ctypes table has the header's argument kinds in the header's order (an int32 / int64 or value /
+    pointer mismatch would otherwise only show up as garbage in the upper half of a register), the same return kind, and
+    the Structure mirrors have the header's field order and widths."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(entry.ROOT, "include", "gmrfb.h")).read(), flags=re.S)
+
+    def c_kind(t):
+        t = re.sub(r"\bconst\b", "", t).strip()
+        if "*" in t:
+            return "ptr"
+        return {"int32_t": "i32", "gmrfb_status": "i32", "int": "i32", "int64_t": "i64", "uint64_t": "u64", "double": "f64",
+                "size_t": "u64"}.get(t.split()[0], "?" + t)
+
+    def py_kind(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_int32: "i32", ctypes.c_int64: "i64", ctypes.c_uint64: "u64", ctypes.c_double: "f64"}[t]
+
+    checked = 0
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(gmrfb_[A-Za-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", hdr, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        kinds = []
+        if args not in ("", "void"):
+            for a in args.split(","):
+                a = a.strip()
+                kinds.append(c_kind(a if a.endswith("*") else re.sub(r"[A-Za-z_][A-Za-z0-9_]*$", "", a)))
+        restype, argtypes = pkg._lib.SIGNATURES[name]
+        assert [py_kind(t) for t in argtypes] == kinds, (name, kinds)
+        assert py_kind(restype) == c_kind(ret), (name, ret)
+        checked += 1
+    assert checked == len(pkg._lib.SIGNATURES)
+    for cname, S in (("gmrfb_analyze_opts", pkg._lib.AnalyzeOpts), ("gmrfb_sym_info", pkg._lib.SymInfo),
+                     ("gmrfb_fac_info", pkg._lib.FacInfo), ("gmrfb_btd_info", pkg._lib.BtdInfo)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, flags=re.S).group(1)
+        cf = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names = [x.strip() for x in decl.split(",")]
+                first = re.search(r"([A-Za-z_][A-Za-z0-9_]*)$", names[0]).group(1)
+                cf += [(nm, c_kind(names[0][:-len(first)])) for nm in [first] + names[1:]]
+        assert [(n, py_kind(t)) for n, t in S._fields_] == cf, cname

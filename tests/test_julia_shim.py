@@ -12,7 +12,7 @@ def header_prototypes():
     src = open(os.path.join(ROOT, "include", "gmrfb.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(gmrfb_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(gmrfb_[A-Za-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
         name, args = m.group(1), m.group(2).strip()
         protos[name] = 0 if args in ("", "void") else args.count(",") + 1
     return protos
@@ -39,7 +39,7 @@ def ccalls(text):
     """(symbol, number of argument types, number of arguments passed) of every ccall((:sym, libgmrfb), ...)."""
     out = []
     text = re.sub(r"#=.*?=#", "", text, flags=re.S)  # inline comments may hold commas
-    for m in re.finditer(r"ccall\(\(:(gmrfb_[a-z0-9_]+),\s*libgmrfb\)", text):
+    for m in re.finditer(r"ccall\(\(:(gmrfb_[A-Za-z0-9_]+),\s*libgmrfb\)", text):
         i = m.end()
         depth, j = 1, i
         while depth > 0:  # to the parenthesis that closes the ccall
@@ -121,7 +121,7 @@ def header_signatures():
     src = open(os.path.join(ROOT, "include", "gmrfb.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     sigs = {}
-    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(gmrfb_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(gmrfb_[A-Za-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
         kinds = []
         if args not in ("", "void"):
@@ -138,7 +138,7 @@ def test_ccall_argument_types_match_the_header():
     checked = 0
     for path in julia_sources():
         text = re.sub(r"#=.*?=#", "", open(path).read(), flags=re.S)
-        for m in re.finditer(r"ccall\(\(:(gmrfb_[a-z0-9_]+),\s*libgmrfb\)", text):
+        for m in re.finditer(r"ccall\(\(:(gmrfb_[A-Za-z0-9_]+),\s*libgmrfb\)", text):
             i = m.end()
             depth, j = 1, i
             while depth > 0:
