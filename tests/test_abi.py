@@ -118,3 +118,29 @@ def test_ctypes_signatures_match_the_header_types(entry, pkg):
                 first = re.search(r"([A-Za-z_][A-Za-z0-9_]*)$", names[0]).group(1)
                 cf += [(nm, c_kind(names[0][:-len(first)])) for nm in [first] + names[1:]]
         assert [(n, py_kind(t)) for n, t in S._fields_] == cf, cname
+
+
+def test_header_is_plain_c_and_a_c_program_links(entry, pkg, tmp_path):
+    """include/gmrfb.h compiles as C99 (what cgo / ccall / any FFI generator consumes) and a C program linked against
+    libgmrfb.so calls through it: the version, and a context creation that reports - not aborts - when there is no GPU."""
+    import subprocess
+
+    src = tmp_path / "driver.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "gmrfb.h"\n'
+        "int main(void) {\n"
+        "  gmrfb_ctx* ctx = NULL;\n"
+        "  gmrfb_status st = gmrfb_ctx_create(0, &ctx);\n"
+        '  printf("version %d status %d msg %s\\n", (int)gmrfb_version(), (int)st, st ? gmrfb_last_error(NULL) : "ok");\n'
+        "  if (ctx) gmrfb_ctx_destroy(ctx);\n"
+        "  return 0;\n}\n")
+    inc = os.path.join(entry.ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    exe = tmp_path / "driver"
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", entry.PKG_DIR, "-lgmrfb",
+                           "-Wl,-rpath," + entry.PKG_DIR])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.startswith("version ") and int(out.stdout.split()[1]) >= 100
+    if " status 0 " not in out.stdout:
+        assert "no CPU fallback" in out.stdout
