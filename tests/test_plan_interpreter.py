@@ -182,7 +182,7 @@ def test_plans_of_random_patterns(pc):
         assert r2["violations"] == [] and r2["solve_err"] < 1e-9, (n, kind, ordering, r2)
 
 
-@pytest.mark.parametrize("b,nblocks", [(64, 3), (100, 4), (320, 4), (700, 3)])
+@pytest.mark.parametrize("b,nblocks", [(1, 3), (64, 3), (65, 4), (100, 4), (193, 4), (320, 4), (700, 3)])
 def test_btd_lookahead_schedule(pc, b, nblocks):
     """The three-stream look-ahead schedule of the block-tridiagonal factor (btd.cu: btd_run_factor): POTRF_i, TRSM_{i+1}
     and the rank-512 SYRK_{i+1} run on separate streams ordered by per-panel events only.  The host issue sequence is
@@ -197,7 +197,7 @@ def test_btd_lookahead_schedule(pc, b, nblocks):
         assert res["concurrent_pairs"] > 0  # the schedule does overlap launches: the check is not vacuous
 
 
-@pytest.mark.parametrize("b,nblocks", [(100, 4), (320, 3)])
+@pytest.mark.parametrize("b,nblocks", [(2, 3), (100, 4), (129, 4), (320, 3)])
 def test_btd_time_sharded_lane_schedule(pc, b, nblocks):
     """The fourth stream of the time-sharded factor (gmrfb_btd_dist_factor's after_block): W_i = L_i^-1 by recursive
     doubling and the spike step of block i run behind POTRF_i, ordered by one event, while the chains of the next blocks
